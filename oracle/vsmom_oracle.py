@@ -1,0 +1,810 @@
+"""
+CPU oracle for the vSmartMOM CoreRT matrix-operator hot path.
+
+TEST INFRASTRUCTURE ONLY.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import this
+module.  The product path (``vsmartmom.jl_b200/``) never imports it and has
+no CPU fallback.
+
+This is a NumPy restatement (batch-first arrays ``(nSpec, N, N)`` instead of
+Julia's column-major ``(N, N, nSpec)``; same arithmetic) of the reference's
+pure-Julia algorithm.  The reference cannot be executed in this container (no
+Julia toolchain), so the oracle is pinned against the reference's own golden
+tables instead (tests/test_oracle_golden.py):
+
+* Natraj (2009) polarized Rayleigh table   test/benchmarks/natraj_trues.jl
+  asserted at                              test/test_CoreRT.jl:110-157
+* 6SV1 scalar Rayleigh reflectances        test/benchmarks/6SV1_R_trues.jl
+  asserted at                              test/test_CoreRT.jl:7-43
+* Siewert (2000) problem IIA / VLIDORT     test/vlidort_baseline/reference_data/
+  asserted at                              test/vlidort_baseline/cases/case_A_siewert2000.jl
+
+Each function cites the reference file:line it follows (paths relative to
+/root/reference).  Per-slice dense algebra is ``np.matmul`` (BLAS gemm per
+slice) and ``np.linalg.inv`` (LAPACK getrf+getri per slice) -- the same
+family as the reference CPU path src/CoreRT/tools/cpu_batched.jl:32-37,65-82.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+
+# --------------------------------------------------------------------------
+# small helpers
+# --------------------------------------------------------------------------
+def cosd(x: float) -> float:
+    """Julia's cosd: exact at multiples of 30/45/60/90 degrees where the
+    result is rational."""
+    r = math.fmod(float(x), 360.0)
+    if r < 0:
+        r += 360.0
+    exact = {0.0: 1.0, 60.0: 0.5, 90.0: 0.0, 120.0: -0.5, 180.0: -1.0,
+             240.0: -0.5, 270.0: 0.0, 300.0: 0.5}
+    if r in exact:
+        return exact[r]
+    return math.cos(math.radians(r))
+
+
+def sind(x: float) -> float:
+    r = math.fmod(float(x), 360.0)
+    if r < 0:
+        r += 360.0
+    exact = {0.0: 0.0, 30.0: 0.5, 90.0: 1.0, 150.0: 0.5, 180.0: 0.0,
+             210.0: -0.5, 270.0: -1.0, 330.0: -0.5}
+    if r in exact:
+        return exact[r]
+    return math.sin(math.radians(r))
+
+
+def _unique_preserve(x: Sequence[float]) -> np.ndarray:
+    """Julia ``unique``: first occurrence order, exact equality."""
+    seen = set()
+    out = []
+    for v in x:
+        if v not in seen:
+            seen.add(v)
+            out.append(v)
+    return np.asarray(out)
+
+
+def nearest_point(f_array: np.ndarray, f: float) -> int:
+    """src/CoreRT/tools/rt_helper_functions.jl:76 (0-based result)."""
+    return int(np.argmin(np.abs(np.asarray(f_array) - f)))
+
+
+# --------------------------------------------------------------------------
+# quadrature   src/CoreRT/tools/rt_set_streams.jl:25-47
+# --------------------------------------------------------------------------
+@dataclass
+class QuadPoints:
+    mu0: float
+    imu0: int            # 0-based index of the solar stream in qp_mu
+    qp_mu: np.ndarray    # (Nquad,)
+    wt_mu: np.ndarray    # (Nquad,)
+    qp_muN: np.ndarray   # (Nquad*pol_n,)
+    wt_muN: np.ndarray
+    Nquad: int
+    Nstreams: int
+    pol_n: int
+
+
+def gauleg(n: int, xmin: float, xmax: float):
+    """src/Scattering/mie_helper_functions.jl:330-335 (FastGaussQuadrature
+    gausslegendre mapped to [xmin, xmax])."""
+    xi, w = np.polynomial.legendre.leggauss(n)
+    xi = (xmax - xmin) / 2 * xi + (xmin + xmax) / 2
+    w = w * (xmax - xmin) / 2
+    return xi, w
+
+
+def rt_set_streams_gauss(nstreams: int, sza: float, vza: Sequence[float],
+                         pol_n: int, FT=np.float64) -> QuadPoints:
+    """rt_set_streams(::GaussLegQuad, ...) src/CoreRT/tools/rt_set_streams.jl:25-47,153-161
+    (kwarg form: Ltrunc = 2*nstreams-2 so (Ltrunc+2)//2 == nstreams)."""
+    qp, wt = gauleg(nstreams, 0.0, 1.0)
+    mu0 = cosd(sza)
+    allmu = [FT(v) for v in qp] + [FT(cosd(v)) for v in vza] + [FT(mu0)]
+    qp_mu = _unique_preserve(allmu).astype(FT)
+    wt_mu = np.concatenate([wt.astype(FT), np.zeros(len(qp_mu) - len(wt), FT)])
+    Nquad = len(qp_mu)
+    Nstreams = int(np.count_nonzero(wt_mu))
+    imu0 = nearest_point(qp_mu, FT(mu0))
+    qp_muN = np.repeat(qp_mu, pol_n)
+    wt_muN = np.repeat(wt_mu, pol_n)
+    return QuadPoints(float(FT(mu0)), imu0, qp_mu, wt_mu, qp_muN, wt_muN, Nquad,
+                      Nstreams, pol_n)
+
+
+# --------------------------------------------------------------------------
+# Greek coefficients and phase-matrix Fourier moments
+# --------------------------------------------------------------------------
+@dataclass
+class GreekCoefs:
+    alpha: np.ndarray
+    beta: np.ndarray
+    gamma: np.ndarray
+    delta: np.ndarray
+    epsilon: np.ndarray
+    zeta: np.ndarray
+
+
+def get_greek_rayleigh(depol: float) -> GreekCoefs:
+    """src/Scattering/mie_helper_functions.jl:454-468"""
+    dpl_p = (1 - depol) / (1 + depol / 2)
+    dpl_r = (1 - 2 * depol) / (1 - depol)
+    a = np.array([0.0, 0.0, 3 * dpl_p])
+    b = np.array([1.0, 0.0, 0.5 * dpl_p])
+    g = np.array([0.0, 0.0, dpl_p * math.sqrt(1.5)])
+    d = np.array([0.0, dpl_p * dpl_r * 1.5, 0.0])
+    e = np.zeros(3)
+    z = np.zeros(3)
+    return GreekCoefs(a, b, g, d, e, z)
+
+
+def compute_associated_legendre_PRT(mu: np.ndarray, Lmax: int):
+    """src/Scattering/legendre_functions.jl:24-185.  Returns (P, R, -T) with
+    shape (len(mu), Lmax, Lmax), index [imu, l, m] (0-based l, m)."""
+    mu = np.asarray(mu, dtype=np.float64)
+    nmu = len(mu)
+    P = np.zeros((nmu, Lmax, Lmax))
+    R = np.zeros((nmu, Lmax, Lmax))
+    T = np.zeros((nmu, Lmax, Lmax))
+    sq = math.sqrt
+    for m in range(Lmax):
+        for l in range(m, Lmax):
+            for i in range(nmu):
+                cmu = mu[i]
+                smu = sq(1.0 - cmu * cmu)
+                if m == 0:
+                    if l == 0:
+                        P[i, l, m] = 1
+                    elif l == 1:
+                        P[i, l, m] = cmu
+                    elif l == 2:
+                        P[i, l, m] = 0.5 * (3.0 * cmu * cmu - 1.0)
+                        R[i, l, m] = 0.5 * sq(1.5) * smu * smu
+                    else:
+                        P[i, l, m] = (P[i, l - 1, m] * (2 * l - 1) * cmu
+                                      - P[i, l - 2, m] * (l - 1)) / l
+                        Y = sq((l + 1) * (l - 3))
+                        X = sq(l * l - 4)
+                        R[i, l, m] = (R[i, l - 1, m] * (2 * l - 1) * cmu
+                                      - R[i, l - 2, m] * Y) / X
+                elif m == 1:
+                    if l == 1:
+                        P[i, l, m] = sq(0.5) * smu
+                    elif l == 2:
+                        m1 = sq(1 / 6)
+                        cA = 3 * cmu * smu
+                        cB = sq(1.5) * smu
+                        P[i, l, m] = m1 * cA
+                        R[i, l, m] = -m1 * cmu * cB
+                        T[i, l, m] = m1 * cB
+                    else:
+                        m1 = sq((l - 1) / (l + 1))
+                        m2 = m1 * sq((l - 2) / l)
+                        Y = (l - 1 + m)
+                        X = (l - m)
+                        P[i, l, m] = (m1 * P[i, l - 1, m] * (2 * l - 1) * cmu
+                                      - m2 * P[i, l - 2, m] * Y) / X
+                        Z = (2 * m * (2 * l - 1)) / (l * (l - 1))
+                        Y = ((l + m - 1) / (l - 1)) * sq((l - 3) * (l + 1))
+                        X = ((l - m) / l) * sq(l * l - 4)
+                        R[i, l, m] = (m1 * R[i, l - 1, m] * (2 * l - 1) * cmu
+                                      - m2 * R[i, l - 2, m] * Y
+                                      + m1 * T[i, l - 1, m] * Z) / X
+                        T[i, l, m] = (m1 * T[i, l - 1, m] * (2 * l - 1) * cmu
+                                      - m2 * T[i, l - 2, m] * Y
+                                      + m1 * R[i, l - 1, m] * Z) / X
+                else:
+                    if l == m:
+                        fact1 = 1.0
+                        fact2 = 1.0
+                        sfull = smu
+                        shalf = sfull / 2
+                        for k in range(1, m + 1):
+                            fact1 = fact1 * ((2 * k - 1) * sfull) / sq(k * (k + m))
+                            if k > 2:
+                                fact2 = fact2 * shalf * sq((m + k) / (k - 2))
+                            else:
+                                fact2 = fact2 * shalf
+                        if smu > 1e-8:
+                            Km = fact2
+                            Aii = Km * (1.0 + cmu * cmu) / (smu * smu)
+                            Aij = Km * (2 * cmu) / (smu * smu)
+                        else:
+                            if m == 2:
+                                Aii = 0.5
+                                Aij = 0.5
+                            else:
+                                Aii = 0.0
+                                Aij = 0.0
+                        P[i, l, m] = fact1
+                        R[i, l, m] = Aii
+                        T[i, l, m] = -Aij
+                    elif l == m + 1:
+                        m1 = sq(1 / (l + m))
+                        X = (l - m)
+                        P[i, l, m] = (m1 * P[i, l - 1, m] * (2 * l - 1) * cmu) / X
+                        Z = (2 * m * (2 * l - 1)) / (l * (l - 1))
+                        X = ((l - m) / l) * sq(l * l - 4)
+                        R[i, l, m] = (m1 * R[i, l - 1, m] * (2 * l - 1) * cmu
+                                      + m1 * T[i, l - 1, m] * Z) / X
+                        T[i, l, m] = (m1 * T[i, l - 1, m] * (2 * l - 1) * cmu
+                                      + m1 * R[i, l - 1, m] * Z) / X
+                    else:
+                        m1 = sq((l - m) / (l + m))
+                        m2 = m1 * sq((l - m - 1) / (l + m - 1))
+                        Y = (l - 1 + m)
+                        X = (l - m)
+                        P[i, l, m] = (m1 * P[i, l - 1, m] * (2 * l - 1) * cmu
+                                      - m2 * P[i, l - 2, m] * Y) / X
+                        Z = (2 * m * (2 * l - 1)) / (l * (l - 1))
+                        Y = ((l + m - 1) / (l - 1)) * sq((l - 3) * (l + 1))
+                        X = ((l - m) / l) * sq(l * l - 4)
+                        R[i, l, m] = (m1 * R[i, l - 1, m] * (2 * l - 1) * cmu
+                                      - m2 * R[i, l - 2, m] * Y
+                                      + m1 * T[i, l - 1, m] * Z) / X
+                        T[i, l, m] = (m1 * T[i, l - 1, m] * (2 * l - 1) * cmu
+                                      - m2 * T[i, l - 2, m] * Y
+                                      + m1 * R[i, l - 1, m] * Z) / X
+    return P, R, -T
+
+
+def _construct_B(pol_n: int, g: GreekCoefs, l: int) -> np.ndarray:
+    """src/Scattering/mie_helper_functions.jl:593-614 (l 0-based here)."""
+    a, b, c, d, e, z = (g.alpha[l], g.beta[l], g.gamma[l], g.delta[l],
+                        g.epsilon[l], g.zeta[l])
+    if pol_n == 4:
+        return np.array([[b, c, 0, 0], [c, a, 0, 0], [0, 0, z, e], [0, 0, -e, d]])
+    if pol_n == 3:
+        return np.array([[b, c, 0], [c, a, 0], [0, 0, z]])
+    if pol_n == 2:
+        return np.array([[b, c], [c, a]])
+    return np.array([[b]])
+
+
+def _construct_Pi(pol_n: int, P, R, T, l: int, m: int) -> np.ndarray:
+    """src/Scattering/mie_helper_functions.jl:532-585 (sign_change=false).
+    Returns (nmu, pol_n, pol_n)."""
+    p, r, t = P[:, l, m], R[:, l, m], T[:, l, m]
+    nmu = len(p)
+    Pi = np.zeros((nmu, pol_n, pol_n))
+    Pi[:, 0, 0] = p
+    if pol_n >= 2:
+        Pi[:, 1, 1] = r
+    if pol_n >= 3:
+        Pi[:, 1, 2] = -t
+        Pi[:, 2, 1] = -t
+        Pi[:, 2, 2] = r
+    if pol_n == 4:
+        Pi[:, 3, 3] = p
+    return Pi
+
+
+def compute_Z_moments(pol_n: int, mu: np.ndarray, greek: GreekCoefs, m: int,
+                      FT=np.float64):
+    """src/Scattering/compute_Z_matrices.jl:26-110.  ``m`` is the 0-based
+    Fourier moment.  Returns (Zpp, Zmp), each (N, N) with N = len(mu)*pol_n."""
+    mu = np.asarray(mu, dtype=np.float64)
+    n = len(mu)
+    fact = 0.5 if m == 0 else 1.0
+    l_max = len(greek.beta)
+    assert np.all((mu > 0) & (mu <= 1))
+    P, R, T = compute_associated_legendre_PRT(mu, l_max)
+    Pm, Rm, Tm = compute_associated_legendre_PRT(-mu, l_max)
+    App = np.zeros((n, n, pol_n, pol_n))
+    Amp = np.zeros((n, n, pol_n, pol_n))
+    for l in range(m, l_max):
+        B = _construct_B(pol_n, greek, l)
+        Pi = _construct_Pi(pol_n, P, R, T, l, m)
+        Pim = _construct_Pi(pol_n, Pm, Rm, Tm, l, m)
+        left = Pi @ B                                   # (n, p, p)
+        App += np.einsum('iab,jbc->ijac', left, Pi)
+        Amp += np.einsum('iab,jbc->ijac', left, Pim)
+    Zpp = np.zeros((n * pol_n, n * pol_n))
+    Zmp = np.zeros((n * pol_n, n * pol_n))
+    for i in range(pol_n):
+        for j in range(pol_n):
+            Zpp[i::pol_n, j::pol_n] = 2 * fact * App[:, :, i, j]
+            if (i <= 1 and j >= 2) or (i >= 2 and j <= 1):
+                Zmp[i::pol_n, j::pol_n] = -2 * fact * Amp[:, :, i, j]
+            else:
+                Zmp[i::pol_n, j::pol_n] = 2 * fact * Amp[:, :, i, j]
+    return Zpp.astype(FT), Zmp.astype(FT)
+
+
+# --------------------------------------------------------------------------
+# Model container (the arrays model_from_parameters would produce)
+# --------------------------------------------------------------------------
+@dataclass
+class Aerosol:
+    greek: GreekCoefs
+    omega: float          # ω̃
+    ft: float = 0.0       # fᵗ (δ-truncation fraction)
+
+
+@dataclass
+class Model:
+    pol_n: int
+    quad: QuadPoints
+    vza: Sequence[float]
+    vaz: Sequence[float]
+    tau_rayl: np.ndarray              # (nSpec, Nz)
+    tau_abs: np.ndarray               # (nSpec, Nz)
+    tau_aer: np.ndarray               # (nAer, Nz)
+    aerosols: List[Aerosol]
+    greek_rayleigh: GreekCoefs
+    albedo: float
+    m_max: int
+    varpi_cabannes: float = 1.0
+    dtau_max_threshold: float = 1e-3
+    dtau_min_floor: Optional[float] = None   # None -> 1024*eps(FT)
+    F0: Optional[np.ndarray] = None          # (pol_n, nSpec); default unit Stokes-I
+    FT: type = np.float64
+
+    @property
+    def nSpec(self):
+        return self.tau_abs.shape[0]
+
+    @property
+    def Nz(self):
+        return self.tau_abs.shape[1]
+
+
+def derive_m_max(model_aerosols: List[Aerosol], nstreams: int) -> int:
+    """src/CoreRT/component_m_max.jl:51-117 for Rayleigh + aerosols +
+    Lambertian surface: max(2, len(beta)-1) clamped to 2*nstreams-1."""
+    m = 2
+    for a in model_aerosols:
+        m = max(m, len(a.greek.beta) - 1)
+    return max(min(m, 2 * nstreams - 1), 0)
+
+
+# --------------------------------------------------------------------------
+# doubling number   src/CoreRT/tools/rt_helper_functions.jl:49-69
+# --------------------------------------------------------------------------
+def doubling_number(dtau_max, tau_end, FT=np.float64):
+    dtau_max = FT(dtau_max)
+    tau_end = FT(tau_end)
+    if tau_end <= dtau_max:
+        return tau_end, 0
+    q1 = np.log10(FT(2))
+    q2 = np.log10(dtau_max)
+    q3 = np.log10(tau_end)
+    tlimit = FT((q3 - q2) / q1)
+    nlimit = int(np.floor(tlimit))
+    diff = FT(tlimit - FT(nlimit))
+    if diff < np.finfo(FT).eps:
+        return dtau_max, nlimit
+    ndoubl = nlimit + 1
+    x = FT(q3 - q1 * FT(ndoubl))
+    return FT(10) ** x, ndoubl
+
+
+def get_ndoubl(max_tau_varpi, quad: QuadPoints, FT, threshold=None, floor=None) -> int:
+    """src/CoreRT/CoreKernel/rt_kernel.jl:266-287 (returns ndoubl only; the
+    caller forms dτ = τ / 2^ndoubl)."""
+    eps = np.finfo(FT).eps
+    thr = FT(1e-3 if threshold is None else threshold)
+    flo = FT(1024 * eps if floor is None else floor)
+    real = quad.qp_mu[quad.wt_mu > eps]
+    mu_min = FT(real.min() if real.size else quad.qp_mu.min())
+    mx = FT(max_tau_varpi)
+    dtau_max = max(flo, min(mx, FT(thr * mu_min)))
+    _, nd = doubling_number(dtau_max, mx, FT)
+    return nd
+
+
+# --------------------------------------------------------------------------
+# layer optical properties
+#   src/CoreRT/LayerOpticalProperties/compEffectiveLayerProperties.jl:11-117
+#   src/CoreRT/types.jl:1262-1308
+# --------------------------------------------------------------------------
+@dataclass
+class CoreProps:
+    tau: np.ndarray         # (nSpec,) or scalar
+    varpi: np.ndarray       # (nSpec,) or scalar
+    Zpp: np.ndarray         # (N, N) or (nSpec, N, N)
+    Zmp: np.ndarray
+
+
+def _add_scatt(x: CoreProps, y: CoreProps) -> CoreProps:
+    """Base.:+ of two CoreScatteringOpticalProperties, types.jl:1262-1293."""
+    tau = x.tau + y.tau
+    wx = x.tau * x.varpi
+    wy = y.tau * y.varpi
+    w = wx + wy
+    varpi = w / np.where(tau > 0, tau, np.ones_like(tau))
+    if np.all(wx == 0.0):
+        return CoreProps(tau, varpi, y.Zpp, y.Zmp)
+    if np.all(wy == 0.0):
+        return CoreProps(tau, varpi, x.Zpp, x.Zmp)
+    wy = np.atleast_1d(wy / w)
+    wx = np.atleast_1d(wx / w)
+    n = max(wx.size, wy.size)
+    wx = np.broadcast_to(wx, (n,)).reshape(n, 1, 1)
+    wy = np.broadcast_to(wy, (n,)).reshape(n, 1, 1)
+    Zpp = wx * x.Zpp + wy * y.Zpp
+    Zmp = wx * x.Zmp + wy * y.Zmp
+    return CoreProps(tau, varpi, Zpp, Zmp)
+
+
+def _add_abs(x: CoreProps, tau_abs: np.ndarray) -> CoreProps:
+    """types.jl:1302-1308"""
+    tau = x.tau + tau_abs
+    wx = x.tau * x.varpi
+    varpi = wx / np.where(tau > 0, tau, np.ones_like(tau))
+    return CoreProps(tau, varpi, x.Zpp, x.Zmp)
+
+
+def construct_core_optical_properties(model: Model, m: int, sel=slice(None)):
+    """constructCoreOpticalProperties, single band.  ``sel`` restricts the
+    spectral axis (control-flow scalars must come from the full band; see
+    band_control)."""
+    FT = model.FT
+    mu = model.quad.qp_mu
+    Zpp_r, Zmp_r = compute_Z_moments(model.pol_n, mu, model.greek_rayleigh, m, FT)
+    aerZ = [compute_Z_moments(model.pol_n, mu, a.greek, m, FT) for a in model.aerosols]
+    out = []
+    for iz in range(model.Nz):
+        combo = CoreProps(model.tau_rayl[sel, iz].astype(FT),
+                          FT(model.varpi_cabannes), Zpp_r, Zmp_r)
+        for ia, a in enumerate(model.aerosols):
+            # createAero, compEffectiveLayerProperties.jl:67-72
+            tau_mod = FT((1 - a.ft * a.omega) * model.tau_aer[ia, iz])
+            varpi_mod = FT((1 - a.ft) * a.omega / (1 - a.ft * a.omega))
+            combo = _add_scatt(combo, CoreProps(tau_mod, varpi_mod, *aerZ[ia]))
+        combo = _add_abs(combo, model.tau_abs[sel, iz].astype(FT))
+        out.append(combo)
+    return out
+
+
+@dataclass
+class BandControl:
+    """Per-layer control flow derived from FULL-band reductions
+    (rt_kernel.jl:197,282-283; compEffectiveLayerProperties.jl:75-93)."""
+    scatter: List[bool]
+    ndoubl: List[int]
+    interface: List[int]     # 0=00, 1=01, 2=10, 3=11
+    tau_sum: np.ndarray      # (nSpec, Nz+1)
+
+
+def get_scattering_interface(prev: int, scatter: bool, iz: int) -> int:
+    """rt_helper_functions.jl:15-33 (iz 0-based)."""
+    if iz == 0:
+        return 3 if scatter else 0
+    if prev == 0:
+        return 1 if scatter else 0
+    return 3 if scatter else 2
+
+
+def band_control(model: Model, m: int) -> BandControl:
+    FT = model.FT
+    props = construct_core_optical_properties(model, m)
+    eps = np.finfo(FT).eps
+    scat, nds, itf = [], [], []
+    tau_sum = np.zeros((model.nSpec, model.Nz + 1), FT)
+    prev = 0
+    for iz, p in enumerate(props):
+        mx = np.max(p.tau * p.varpi)
+        s = bool(mx > 2 * eps)
+        prev = get_scattering_interface(prev, s, iz)
+        scat.append(s)
+        itf.append(prev)
+        nds.append(get_ndoubl(mx, model.quad, FT, model.dtau_max_threshold,
+                              model.dtau_min_floor) if s else 0)
+        tau_sum[:, iz + 1] = tau_sum[:, iz] + p.tau
+    return BandControl(scat, nds, itf, tau_sum)
+
+
+# --------------------------------------------------------------------------
+# elemental   src/CoreRT/CoreKernel/elemental.jl:174-462, rt_helpers.jl:15-40
+# --------------------------------------------------------------------------
+def expdiff_neg(a, b):
+    """exp(-a) - exp(-b), rt_helpers.jl:32-40 (vectorised)."""
+    a, b = np.broadcast_arrays(a, b)
+    lo = np.minimum(a, b)
+    d = np.abs(a - b)
+    v = np.exp(-lo) * (-np.expm1(-d))
+    return np.where(a == b, np.zeros_like(v), np.where(a < b, v, -v))
+
+
+def _D_diag(pol_n: int, Nquad: int, FT) -> np.ndarray:
+    D = np.array([1, 1, -1, -1][:pol_n], FT)
+    return np.tile(D, Nquad)
+
+
+def elemental(model: Model, m: int, ndoubl: int, dtau, varpi, Zpp, Zmp,
+              tau_sum, F0):
+    """elemental! + get_elem_rt! + get_elem_rt_SFI! + apply_D_elemental!.
+    dtau, varpi, tau_sum: (nS,);  Z: (nS,N,N) or (N,N);  F0: (pol_n, nS).
+    Returns r_mp, t_pp, r_pm, t_mm, j0p, j0m (r_pm/t_mm only valid when
+    ndoubl == 0, as in the reference)."""
+    FT = model.FT
+    q = model.quad
+    pol_n = model.pol_n
+    mu = q.qp_muN.astype(FT)
+    eps = np.finfo(FT).eps
+    wct02 = FT(0.5 if m == 0 else 0.25)
+    wct = (q.wt_muN / 2 if m == 0 else q.wt_muN / 4).astype(FT)
+    nS = dtau.shape[0]
+    N = mu.size
+    if Zpp.ndim == 2:
+        Zpp = np.broadcast_to(Zpp, (nS, N, N))
+        Zmp = np.broadcast_to(Zmp, (nS, N, N))
+    mui = mu[None, :, None]
+    muj = mu[None, None, :]
+    w_j = wct[None, None, :]
+    w = varpi[:, None, None]
+    d = dtau[:, None, None]
+    # r⁻⁺  (elemental.jl:298-302)
+    r = w * Zmp * (muj / (mui + muj)) * w_j * (-np.expm1(-d * ((1 / mui) + (1 / muj))))
+    # t⁺⁺ off-diagonal (elemental.jl:319-323)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        t_off = w * Zpp * (muj / (mui - muj)) * w_j * expdiff_neg(d / mui, d / muj)
+    # μ[i]==μ[j] branch (elemental.jl:304-314)
+    eye = np.eye(N, dtype=bool)[None]
+    same = (mui == muj)
+    t_same_diag = np.exp(-d / mui) * (1 + w * Zpp * (d / mui) * wct[None, :, None])
+    t_same_off = np.exp(-d / muj) * (w * Zpp * (d / mui) * w_j)
+    t = np.where(same, np.where(eye, t_same_diag, t_same_off), t_off)
+    # zero-weight columns (elemental.jl:325-332)
+    active = (wct > eps)[None, None, :]
+    r = np.where(active, r, 0).astype(FT)
+    t_beer = np.where(eye, np.exp(-d / mui), 0)
+    t = np.where(active, t, t_beer).astype(FT)
+
+    # SFI (elemental.jl:348-392)
+    i_start = pol_n * q.imu0
+    i_end = i_start + pol_n
+    ZppI = np.einsum('nik,kn->ni', Zpp[:, :, i_start:i_end], F0.astype(FT))
+    ZmpI = np.einsum('nik,kn->ni', Zmp[:, :, i_start:i_end], F0.astype(FT))
+    mu_i = mu[None, :]
+    mu_s = mu[i_start]
+    dd = dtau[:, None]
+    ww = varpi[:, None]
+    insun = np.zeros(N, bool)
+    insun[i_start:i_end] = True
+    jp_in = wct02 * ww * ZppI * (dd / mu_i) * np.exp(-dd / mu_i)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        jp_out = wct02 * ww * ZppI * (mu_s / (mu_i - mu_s)) * expdiff_neg(dd / mu_i, dd / mu_s)
+    j0p = np.where(insun[None, :], jp_in, jp_out)
+    j0m = wct02 * ww * ZmpI * (mu_s / (mu_i + mu_s)) * (-np.expm1(-dd * ((1 / mu_i) + (1 / mu_s))))
+    att = np.exp(-tau_sum / mu_s)[:, None]
+    j0p = (j0p * att).astype(FT)
+    j0m = (j0m * att).astype(FT)
+    Dd = _D_diag(pol_n, q.Nquad, FT)
+    if ndoubl >= 1:
+        j0m = Dd[None, :] * j0m
+    # apply_D_elemental! (elemental.jl:403-422)
+    r_pm = t_mm = None
+    if ndoubl < 1:
+        sgn = (Dd[:, None] * Dd[None, :])[None]
+        r_pm = sgn * r
+        t_mm = sgn * t
+    else:
+        r = Dd[None, :, None] * r
+    return r, t, r_pm, t_mm, j0p, j0m
+
+
+# --------------------------------------------------------------------------
+# doubling   src/CoreRT/CoreKernel/doubling.jl:38-99, rt_helpers.jl:102-166
+# --------------------------------------------------------------------------
+def doubling(model: Model, ndoubl: int, expk, r, t, j0p, j0m):
+    """Returns r_mp, t_pp, r_pm, t_mm, j0p, j0m after ndoubl doublings and
+    apply_D_matrix!/apply_D_matrix_SFI!.  Must only be called for ndoubl>=1."""
+    FT = model.FT
+    N = r.shape[1]
+    I = np.eye(N, dtype=FT)[None]
+    expk = expk.copy()
+    jp = j0p[:, :, None]
+    jm = j0m[:, :, None]
+    for _ in range(ndoubl):
+        gp = np.linalg.inv(I - r @ r)
+        tt = t @ gp
+        e = expk[:, None, None]
+        j1p = jp * e
+        j1m = jm * e
+        jm_new = jm + tt @ (j1m + r @ jp)
+        jp_new = j1p + tt @ (jp + r @ j1m)
+        jm, jp = jm_new, jp_new
+        r_new = r + (tt @ r) @ t
+        t = tt @ t
+        r = r_new
+        expk = expk ** 2
+    Dd = _D_diag(model.pol_n, model.quad.Nquad, FT)
+    if model.pol_n == 1:
+        return r, t, r.copy(), t.copy(), jp[:, :, 0], jm[:, :, 0]
+    r = Dd[None, :, None] * r
+    sgn = (Dd[:, None] * Dd[None, :])[None]
+    r_pm = sgn * r
+    t_mm = sgn * t
+    jm = Dd[None, :, None] * jm
+    return r, t, r_pm, t_mm, jp[:, :, 0], jm[:, :, 0]
+
+
+# --------------------------------------------------------------------------
+# interaction   src/CoreRT/CoreKernel/interaction.jl:52-266
+# --------------------------------------------------------------------------
+@dataclass
+class Composite:
+    Rmp: np.ndarray
+    Rpm: np.ndarray
+    Tpp: np.ndarray
+    Tmm: np.ndarray
+    J0p: np.ndarray      # (nS, N)
+    J0m: np.ndarray
+
+
+def _mv(A, x):
+    return (A @ x[:, :, None])[:, :, 0]
+
+
+def interaction(itf: int, C: Composite, r_mp, r_pm, t_pp, t_mm, j0p, j0m):
+    FT = C.Rmp.dtype
+    N = C.Rmp.shape[1]
+    I = np.eye(N, dtype=FT)[None]
+    if itf == 0:     # interaction.jl:52-72
+        C.J0p = j0p + _mv(t_pp, C.J0p)
+        C.J0m = C.J0m + _mv(C.Tmm, j0m)
+        C.Tmm = t_mm @ C.Tmm
+        C.Tpp = t_pp @ C.Tpp
+    elif itf == 1:   # interaction.jl:96-118
+        C.J0m = C.J0m + _mv(C.Tmm, _mv(r_mp, C.J0p) + j0m)
+        C.J0p = j0p + _mv(t_pp, C.J0p)
+        C.Rmp = (C.Tmm @ r_mp) @ C.Tpp
+        C.Rpm = r_pm.copy()
+        C.Tpp = t_pp @ C.Tpp
+        C.Tmm = C.Tmm @ t_mm
+    elif itf == 2:   # interaction.jl:141-162
+        C.J0p = j0p + _mv(t_pp, C.J0p + _mv(C.Rpm, j0m))
+        C.J0m = C.J0m + _mv(C.Tmm, j0m)
+        C.Tpp = t_pp @ C.Tpp
+        C.Tmm = C.Tmm @ t_mm
+        C.Rpm = (t_pp @ C.Rpm) @ t_mm
+    else:            # interaction.jl:207-266
+        tmp = np.linalg.inv(I - r_mp @ C.Rpm)
+        T01 = C.Tmm @ tmp
+        J0m = C.J0m + _mv(T01, _mv(r_mp, C.J0p) + j0m)
+        Rmp = C.Rmp + (T01 @ r_mp) @ C.Tpp
+        Tmm = T01 @ t_mm
+        tmp = np.linalg.inv(I - C.Rpm @ r_mp)
+        T21 = t_pp @ tmp
+        J0p = j0p + _mv(T21, C.J0p + _mv(C.Rpm, j0m))
+        Tpp = T21 @ C.Tpp
+        Rpm = r_pm + (T21 @ C.Rpm) @ t_mm
+        C.J0m, C.Rmp, C.Tmm, C.J0p, C.Tpp, C.Rpm = J0m, Rmp, Tmm, J0p, Tpp, Rpm
+    return C
+
+
+# --------------------------------------------------------------------------
+# Lambertian surface   src/CoreRT/Surfaces/lambertian_surface.jl:41-95
+# --------------------------------------------------------------------------
+def lambertian_surface(model: Model, m: int, tau_sum_end):
+    FT = model.FT
+    q = model.quad
+    pol_n = model.pol_n
+    N = q.qp_muN.size
+    nS = tau_sum_end.shape[0]
+    I = np.eye(N, dtype=FT)
+    t = np.broadcast_to(I, (nS, N, N))
+    zeros = np.zeros((nS, N, N), FT)
+    if m != 0:
+        z = np.zeros((nS, N), FT)
+        return zeros, zeros, t, t, z, z
+    rho = FT(2) * FT(model.albedo)
+    blk = np.zeros((pol_n, pol_n), FT)
+    blk[0, 0] = rho
+    R_surf = np.tile(blk, (q.Nquad, q.Nquad))
+    I0 = np.zeros(N, FT)
+    I0[pol_n * q.imu0] = 1           # pol_type.I₀ = (1,0,0,0)
+    att = np.exp(-tau_sum_end / FT(q.mu0))[:, None]
+    j0p = (I0[None, :] * att).astype(FT)
+    j0m = (FT(q.mu0) * (R_surf @ I0)[None, :] * att).astype(FT)
+    r_mp = R_surf * (q.qp_muN * q.wt_muN).astype(FT)[None, :]
+    r_mp = np.broadcast_to(r_mp, (nS, N, N))
+    return r_mp, zeros, t, t, j0p, j0m
+
+
+# --------------------------------------------------------------------------
+# rt_run (noRS, SFI)   src/CoreRT/rt_run.jl:238-539, rt_kernel.jl:175-250
+# --------------------------------------------------------------------------
+def rt_kernel_layer(model: Model, m: int, iz: int, ctl: BandControl, props: CoreProps,
+                    C: Optional[Composite], F0, tau_sum_iz):
+    """One layer of rt_kernel!(::noRS, ...) for the selected spectral points.
+    Returns the updated composite (created at iz == 0)."""
+    FT = model.FT
+    q = model.quad
+    nS = props.tau.shape[0]
+    N = q.qp_muN.size
+    if ctl.scatter[iz]:
+        nd = ctl.ndoubl[iz]
+        dtau = (props.tau / FT(2 ** nd)).astype(FT)
+        expk = np.exp(-dtau / FT(q.mu0))
+        r, t, r_pm, t_mm, j0p, j0m = elemental(model, m, nd, dtau, props.varpi,
+                                               props.Zpp, props.Zmp, tau_sum_iz, F0)
+        if nd > 0:
+            r, t, r_pm, t_mm, j0p, j0m = doubling(model, nd, expk, r, t, j0p, j0m)
+    else:
+        # zero_added_noscat!, rt_helpers.jl:174-180 (j₀⁺ is left untouched by the
+        # reference; it is never read by the 00/10 interaction with zero sources
+        # except through j0p, which for a non-scattering first layer is zero).
+        r = np.zeros((nS, N, N), FT)
+        r_pm = np.zeros((nS, N, N), FT)
+        tb = np.exp(-props.tau[:, None] / q.qp_muN.astype(FT)[None, :])
+        t = np.zeros((nS, N, N), FT)
+        idx = np.arange(N)
+        t[:, idx, idx] = tb
+        t_mm = t.copy()
+        j0p = np.zeros((nS, N), FT)
+        j0m = np.zeros((nS, N), FT)
+    if iz == 0:
+        return Composite(r.copy(), r_pm.copy(), t.copy(), t_mm.copy(), j0p.copy(), j0m.copy())
+    return interaction(ctl.interface[iz], C, r, r_pm, t, t_mm, j0p, j0m)
+
+
+def rt_run(model: Model, sel=slice(None), return_streams: bool = False):
+    """rt_run(::noRS, model, iBand) for one band, SFI = true.  ``sel`` picks a
+    subset of spectral points; control flow (ndoubl, scatter, interface) is
+    always derived from the full band."""
+    FT = model.FT
+    q = model.quad
+    pol_n = model.pol_n
+    nS_all = model.nSpec
+    idx = np.arange(nS_all)[sel]
+    nS = idx.size
+    nV = len(model.vza)
+    R_SFI = np.zeros((nV, pol_n, nS), FT)
+    T_SFI = np.zeros((nV, pol_n, nS), FT)
+    hdr = np.zeros((nV, pol_n, nS), FT)
+    bhr_uw = np.zeros((pol_n, nS), FT)
+    bhr_dw = np.zeros((pol_n, nS), FT)
+    F0 = model.F0
+    if F0 is None:
+        F0 = np.zeros((pol_n, nS_all), FT)
+        F0[0, :] = 1
+    F0 = F0[:, idx]
+    streams = []
+    for m in range(model.m_max + 1):
+        weight = FT(0.5 / math.pi) if m == 0 else FT(1.0 / math.pi)
+        ctl = band_control(model, m)
+        props = construct_core_optical_properties(model, m, idx)
+        C = None
+        for iz in range(model.Nz):
+            C = rt_kernel_layer(model, m, iz, ctl, props[iz], C, F0,
+                                ctl.tau_sum[idx, iz])
+        # surface + final interaction (rt_run.jl:423-465)
+        s = lambertian_surface(model, m, ctl.tau_sum[idx, -1])
+        r_mp_s, r_pm_s, t_s, t_mm_s, j0p_s, j0m_s = s
+        C = interaction(ctl.interface[-1], C, r_mp_s, r_pm_s, t_s, t_mm_s, j0p_s, j0m_s)
+        # interaction_hdrf!, interaction_hdrf.jl:4-42
+        hdr_J0m = _mv(r_mp_s, C.J0p) + j0m_s
+        if m == 0:
+            wq = (q.wt_muN * q.qp_muN).astype(FT)
+            i0 = pol_n * q.imu0
+            for i in range(pol_n):
+                j = slice(i, None, pol_n)
+                bhr_uw[i, :] = np.sum(hdr_J0m[:, j] * wq[j][None, :], axis=1)
+                bhr_dw[i, :] = (np.sum(C.J0p[:, j] * wq[j][None, :], axis=1)
+                                + j0p_s[:, i0] * q.qp_muN[i0])
+        # postprocessing_vza!, postprocessing_vza.jl:23-94
+        for i in range(nV):
+            imu = nearest_point(q.qp_mu, FT(cosd(model.vza[i])))
+            ist = imu * pol_n
+            c = cosd(m * model.vaz[i])
+            sn = sind(m * model.vaz[i])
+            wv = (weight * np.array([c, c, sn, sn][:pol_n])).astype(FT)
+            R_SFI[i] += wv[:, None] * C.J0m[:, ist:ist + pol_n].T
+            T_SFI[i] += wv[:, None] * C.J0p[:, ist:ist + pol_n].T
+            hdr[i] += wv[:, None] * hdr_J0m[:, ist:ist + pol_n].T
+        if return_streams:
+            streams.append(C)
+    out = dict(R_SFI=R_SFI, T_SFI=T_SFI, hdr=hdr, bhr_uw=bhr_uw[0], bhr_dw=bhr_dw[0])
+    if return_streams:
+        out['streams'] = streams
+    return out
