@@ -1,0 +1,168 @@
+/*
+ * vsmom_b200.h -- C-ABI of the B200-native CoreRT matrix-operator core.
+ *
+ * Drop-in boundary for the reference's CUDA package extension
+ * (vSmartMOM.jl: ext/vSmartMOMCUDAExt.jl, ext/gpu_batched_cuda.jl) and for the
+ * per-layer / per-column hot loop of rt_run (src/CoreRT/rt_run.jl:383-517).
+ * A Julia `ccall` stub for every entry point is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - All arrays are column-major exactly as Julia lays them out; the spectral
+ *    index n is the slowest dimension of every (N,N,nSpec) / (N,1,nSpec) array.
+ *  - Pointers documented "device" are CUDA device pointers owned by the caller
+ *    (CuArray memory); the library only borrows them for the duration of a call.
+ *    Pointers documented "host" are ordinary host memory.
+ *  - Every function returns 0 on success, non-zero on failure; the message is
+ *    available from vsm_last_error().  Nothing throws across the ABI.
+ *  - Work is enqueued on the cudaStream_t given to vsm_create(); entry points
+ *    return after enqueueing unless stated otherwise (the reference calls
+ *    CUDA.synchronize() after each op; the Julia glue does the same).
+ *  - There is NO CPU fallback: without a CUDA device vsm_create() fails.
+ */
+#ifndef VSMOM_B200_H
+#define VSMOM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSM_OK                 0
+#define VSM_ERR_INVALID_ARG    1
+#define VSM_ERR_CUDA           2
+#define VSM_ERR_UNSUPPORTED    3
+#define VSM_ERR_NOMEM          4
+
+/* ScatteringInterface tags (src/CoreRT/types.jl AbstractScatteringInterface;
+ * chosen by get_scattering_interface, src/CoreRT/tools/rt_helper_functions.jl:15-33) */
+#define VSM_IFACE_00 0
+#define VSM_IFACE_01 1
+#define VSM_IFACE_10 2
+#define VSM_IFACE_11 3
+
+/* surface kinds handled natively by vsm_rt_column_* */
+#define VSM_SURFACE_LAMBERTIAN_SCALAR 0   /* src/CoreRT/Surfaces/lambertian_surface.jl:41-95 */
+
+typedef struct vsm_ctx vsm_ctx;   /* opaque; one per (device, host task) */
+
+/* -- context -- replaces vSmartMOMCUDAExt.__init__ (ext/vSmartMOMCUDAExt.jl:36-66) */
+int  vsm_version(void);
+int  vsm_create(vsm_ctx** out, int device, void* cuda_stream /* cudaStream_t or NULL */);
+int  vsm_destroy(vsm_ctx* ctx);
+const char* vsm_last_error(vsm_ctx* ctx);       /* ctx may be NULL: last create error */
+int  vsm_synchronize(vsm_ctx* ctx);             /* Architectures._sync_gpu[] (ext/vSmartMOMCUDAExt.jl:55) */
+/* cap (bytes) on the library-owned scratch used by vsm_rt_column_*; 0 = default */
+int  vsm_set_workspace_limit(vsm_ctx* ctx, uint64_t bytes);
+/* number of kernels this context has launched since creation (bench bookkeeping) */
+uint64_t vsm_kernel_launches(vsm_ctx* ctx);
+
+/* -- L0: batched dense algebra -- same semantics as ext/gpu_batched_cuda.jl ----
+ * batched_mul  (gpu_batched_cuda.jl:208-218):  C[:,:,k] = A[:,:,k] * B[:,:,k]
+ *   A: (M,K,batch)  B: (K,Ncols,batch)  C: (M,Ncols,batch), all device, dense.
+ * batch_inv!   (gpu_batched_cuda.jl:97-182):   X[:,:,k] = inv(A[:,:,k])
+ *   A is overwritten (as getrf does); info[k] = 0 or the 1-based index of a
+ *   zero pivot (device int array, may be NULL -- the reference never reads it).
+ * batch_solve! (gpu_batched_cuda.jl:72-94):    X[:,:,k] = A[:,:,k] \ B[:,:,k]   */
+int vsm_batched_mul_f64(vsm_ctx*, double* C, const double* A, const double* B,
+                        int M, int K, int Ncols, int batch);
+int vsm_batched_mul_f32(vsm_ctx*, float* C, const float* A, const float* B,
+                        int M, int K, int Ncols, int batch);
+int vsm_batch_inv_f64(vsm_ctx*, double* X, double* A, int N, int batch, int* info);
+int vsm_batch_inv_f32(vsm_ctx*, float* X, float* A, int N, int batch, int* info);
+int vsm_batch_solve_f64(vsm_ctx*, double* X, double* A, const double* B, int N, int Ncols, int batch);
+int vsm_batch_solve_f32(vsm_ctx*, float* X, float* A, const float* B, int N, int Ncols, int batch);
+
+/* -- L1: one layer, one Fourier moment -- drop-in for
+ * rt_kernel!(::noRS, ...) src/CoreRT/CoreKernel/rt_kernel.jl:175-250
+ * (elemental! + doubling! + interaction!/copy_added_to_composite!).
+ * All array pointers are device pointers.                                      */
+typedef struct vsm_layer_desc {
+    int32_t struct_size;     /* sizeof(vsm_layer_desc) */
+    int32_t N;               /* NquadN = Nquad*nStokes */
+    int32_t nStokes;         /* pol_type.n */
+    int32_t nSpec;
+    int32_t m;               /* Fourier moment */
+    int32_t imu0;            /* 1-based iμ₀ (stream index) */
+    int32_t ndoubl;          /* from get_dtau_ndoubl (rt_kernel.jl:266-287) on the FULL band */
+    int32_t scatter;         /* maximum(τ.*ϖ) > 2eps(FT) on the FULL band (rt_kernel.jl:197) */
+    int32_t iface;           /* VSM_IFACE_* for this layer */
+    int32_t iz;              /* 1 => copy_added_to_composite! instead of interaction! */
+    int32_t z_is_spectral;   /* size(Z,3) > 1 */
+    int32_t reserved;
+    double  mu0;             /* quad_points.μ₀ */
+    const void* tau;         /* [nSpec]  total layer optical depth τ */
+    const void* varpi;       /* [nSpec]  ϖ */
+    const void* Zpp;         /* (N,N,nSpec) or (N,N,1) */
+    const void* Zmp;
+    const void* tau_sum;     /* [nSpec]  τ above the layer */
+    const void* F0;          /* (nStokes,nSpec) */
+    const void* mu;          /* [N] qp_μN */
+    const void* wt;          /* [N] wt_μN */
+    /* CompositeLayer (in/out) src/CoreRT/types.jl:155-174 */
+    void *Rmp, *Rpm, *Tpp, *Tmm;   /* (N,N,nSpec) */
+    void *J0p, *J0m;               /* (N,1,nSpec) */
+    /* AddedLayer (out; any may be NULL => kept on-chip only) types.jl:196-230 */
+    void *rmp, *rpm, *tpp, *tmm;
+    void *j0p, *j0m;
+} vsm_layer_desc;
+int vsm_rt_layer_f64(vsm_ctx*, const vsm_layer_desc*);
+int vsm_rt_layer_f32(vsm_ctx*, const vsm_layer_desc*);
+
+/* -- L2: whole column, all Fourier moments, device epilogue -- drop-in for the
+ * body of rt_run(::noRS, model, iBand) src/CoreRT/rt_run.jl:383-517 including
+ * constructCoreOpticalProperties/expandOpticalProperties
+ * (LayerOpticalProperties/compEffectiveLayerProperties.jl:11-117), the
+ * Lambertian create_surface_layer!, interaction_hdrf! and postprocessing_vza!.
+ * "host" arrays are small and always double; "device" arrays are f32/f64
+ * according to the entry point.                                               */
+typedef struct vsm_column_desc {
+    int32_t struct_size;     /* sizeof(vsm_column_desc) */
+    int32_t N;               /* NquadN */
+    int32_t nStokes;
+    int32_t nSpec;           /* spectral points in THIS call (a shard of the band) */
+    int32_t Nz;
+    int32_t nAer;
+    int32_t nVZA;
+    int32_t n_moments;       /* m_max + 1 */
+    int32_t imu0;            /* 1-based iμ₀ */
+    int32_t surface_kind;    /* VSM_SURFACE_* */
+    double  mu0;
+    double  albedo;          /* LambertianSurfaceScalar.albedo */
+    double  varpi_cabannes;  /* RS_type.ϖ_Cabannes[iB] (1 for noRS) */
+    /* host, double */
+    const double*  mu;         /* [N] qp_μN */
+    const double*  wt;         /* [N] wt_μN */
+    const double*  aer_omega;  /* [nAer] ω̃ */
+    const double*  aer_ft;     /* [nAer] fᵗ */
+    const double*  tau_aer;    /* (nAer,Nz) */
+    const double*  vza_weight; /* (nStokes,nVZA,n_moments): weight·(cos mφ | sin mφ)
+                                  (_precompute_vza_weights, postprocessing_vza.jl:23-37) */
+    /* host, int32 -- control flow derived from FULL-band reductions */
+    const int32_t* ndoubl;       /* [Nz] */
+    const int32_t* scatter;      /* [Nz] */
+    const int32_t* iface;        /* [Nz]; the surface step reuses iface[Nz-1] (rt_run.jl:459-465) */
+    const int32_t* rayl_allzero; /* [Nz] all(τ_rayl[:,iz].*ϖ_Cabannes .== 0) (types.jl:1279) */
+    const int32_t* vza_stream;   /* [nVZA] 1-based nearest stream index iμ of each VZA */
+    /* device, FT */
+    const void* tau_rayl;    /* (nSpec,Nz) */
+    const void* tau_abs;     /* (nSpec,Nz) */
+    const void* F0;          /* (nStokes,nSpec) */
+    const void* Zpp;         /* (N,N,1+nAer,n_moments); component 0 = Rayleigh
+                                (Scattering.compute_Z_moments, compute_Z_matrices.jl:26-110) */
+    const void* Zmp;
+} vsm_column_desc;
+/* outputs: device; R_SFI/T_SFI/hdr (nVZA,nStokes,nSpec); bhr_* (nStokes,nSpec);
+ * hdr/bhr_uw/bhr_dw may be NULL.  Outputs are overwritten (not accumulated).  */
+int vsm_rt_column_f64(vsm_ctx*, const vsm_column_desc*, double* R_SFI, double* T_SFI,
+                      double* hdr, double* bhr_uw, double* bhr_dw);
+int vsm_rt_column_f32(vsm_ctx*, const vsm_column_desc*, float* R_SFI, float* T_SFI,
+                      float* hdr, float* bhr_uw, float* bhr_dw);
+/* device time (ms) of the most recent vsm_rt_column_* call, measured with CUDA
+ * events on the context's stream; blocks until that call has finished.        */
+int vsm_last_column_ms(vsm_ctx*, float* total_ms, float* doubling_ms, float* adding_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSMOM_B200_H */

@@ -1,0 +1,540 @@
+// vsm_api.cu -- C-ABI (include/vsmom_b200.h): context, workspace planning, launches.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/vsmom_b200.h"
+#include "vsm_launch.cuh"
+#include "vsm_l0.cuh"
+
+using namespace vsm;
+
+static thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct vsm_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 0;
+    int max_smem_optin = 0;
+    uint64_t ws_limit = 0;
+    uint64_t launches = 0;
+    std::string err;
+    // grow-only scratch
+    DevBuf consts, props, added, slabs, partial, counter, l0tmp;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float t_total = 0, t_layer = 0, t_add = 0;
+    bool timing_valid = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> seg_layer, seg_add;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+};
+
+#define CK(call)                                                                  \
+    do {                                                                          \
+        cudaError_t e_ = (call);                                                  \
+        if (e_ != cudaSuccess) {                                                  \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);        \
+            return VSM_ERR_CUDA;                                                  \
+        }                                                                         \
+    } while (0)
+
+static int fail(vsm_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg; else g_create_error = msg;
+    return code;
+}
+
+static int ensure(vsm_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return VSM_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        e = cudaMalloc(&b.p, bytes);
+        want = bytes;
+    }
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        char buf[128];
+        snprintf(buf, sizeof buf, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return fail(ctx, VSM_ERR_NOMEM, buf);
+    }
+    b.cap = want;
+    return VSM_OK;
+}
+
+static cudaEvent_t get_event(vsm_ctx* ctx) {
+    if (ctx->ev_used == ctx->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ctx->ev_pool.push_back(e);
+    }
+    return ctx->ev_pool[ctx->ev_used++];
+}
+
+extern "C" int vsm_version(void) { return 100; }
+
+extern "C" int vsm_create(vsm_ctx** out, int device, void* cuda_stream) {
+    if (!out) return fail(nullptr, VSM_ERR_INVALID_ARG, "vsm_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, VSM_ERR_CUDA,
+                    std::string("vsm_create: no CUDA device (there is no CPU fallback): ") +
+                        cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, VSM_ERR_INVALID_ARG, "vsm_create: bad device index");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, VSM_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, VSM_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+    if (prop.major < 10)
+        return fail(nullptr, VSM_ERR_UNSUPPORTED, "vsm_create: this library is built for sm_100a (Blackwell B200) only");
+    vsm_ctx* ctx = new vsm_ctx();
+    ctx->device = device;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    ctx->ws_limit = 0;
+    *out = ctx;
+    return VSM_OK;
+}
+
+extern "C" int vsm_destroy(vsm_ctx* ctx) {
+    if (!ctx) return VSM_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->consts, &ctx->props, &ctx->added, &ctx->slabs, &ctx->partial, &ctx->counter, &ctx->l0tmp};
+    for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    delete ctx;
+    return VSM_OK;
+}
+
+extern "C" const char* vsm_last_error(vsm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int vsm_synchronize(vsm_ctx* ctx) {
+    if (!ctx) return VSM_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VSM_OK;
+}
+
+extern "C" int vsm_set_workspace_limit(vsm_ctx* ctx, uint64_t bytes) {
+    if (!ctx) return VSM_ERR_INVALID_ARG;
+    ctx->ws_limit = bytes;
+    return VSM_OK;
+}
+
+extern "C" uint64_t vsm_kernel_launches(vsm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------
+// L0
+// ---------------------------------------------------------------------------
+template <typename T>
+static int bmm_impl(vsm_ctx* ctx, T* C, const T* A, const T* B, int M, int K, int Nc, int batch) {
+    if (!ctx || !C || !A || !B) return fail(ctx, VSM_ERR_INVALID_ARG, "batched_mul: NULL argument");
+    if (M <= 0 || K <= 0 || Nc <= 0 || batch < 0) return fail(ctx, VSM_ERR_INVALID_ARG, "batched_mul: bad dims");
+    if (batch == 0) return VSM_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t sm = ((size_t)(M | 1) * K + (size_t)(K | 1) * Nc) * sizeof(T);
+    const int stage = sm <= (size_t)ctx->max_smem_optin ? 1 : 0;
+    const size_t smem = stage ? sm : 0;
+    const int grid = std::min(batch, ctx->num_sms * 8);
+    const bool vec = (Nc == 1);
+    if (vec) {
+        auto kern = k_bmm<T, 1, 1>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 128, smem, ctx->stream>>>(C, A, B, M, K, Nc, batch, stage);
+    } else if (M <= 24) {
+        auto kern = k_bmm<T, 2, 2>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 128, smem, ctx->stream>>>(C, A, B, M, K, Nc, batch, stage);
+    } else {
+        auto kern = k_bmm<T, 4, 4>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 256, smem, ctx->stream>>>(C, A, B, M, K, Nc, batch, stage);
+    }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return VSM_OK;
+}
+
+template <typename T>
+static int binv_impl(vsm_ctx* ctx, T* X, T* A, int N, int batch, int* info) {
+    if (!ctx || !X || !A) return fail(ctx, VSM_ERR_INVALID_ARG, "batch_inv: NULL argument");
+    if (N <= 0 || batch < 0) return fail(ctx, VSM_ERR_INVALID_ARG, "batch_inv: bad dims");
+    if (batch == 0) return VSM_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t vecb = (size_t)3 * N * sizeof(T) + (size_t)N * sizeof(int);
+    const size_t full = (size_t)(N | 1) * N * sizeof(T) + vecb;
+    const int stage = full <= (size_t)ctx->max_smem_optin ? 1 : 0;
+    const size_t smem = stage ? full : vecb;
+    auto kern = k_binv<T>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = std::min(batch, ctx->num_sms * 8);
+    const int threads = N <= 8 ? 64 : (N <= 24 ? 128 : 256);
+    kern<<<grid, threads, smem, ctx->stream>>>(X, A, N, batch, info, stage);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return VSM_OK;
+}
+
+template <typename T>
+static int bsolve_impl(vsm_ctx* ctx, T* X, T* A, const T* B, int N, int Nc, int batch) {
+    if (!ctx || !X || !A || !B) return fail(ctx, VSM_ERR_INVALID_ARG, "batch_solve: NULL argument");
+    if (batch == 0) return VSM_OK;
+    int rc = ensure(ctx, ctx->l0tmp, (size_t)N * N * batch * sizeof(T));
+    if (rc) return rc;
+    T* inv = (T*)ctx->l0tmp.p;
+    rc = binv_impl<T>(ctx, inv, A, N, batch, nullptr);
+    if (rc) return rc;
+    return bmm_impl<T>(ctx, X, inv, B, N, N, Nc, batch);
+}
+
+extern "C" int vsm_batched_mul_f64(vsm_ctx* c, double* C, const double* A, const double* B, int M, int K, int Nc, int batch) { return bmm_impl<double>(c, C, A, B, M, K, Nc, batch); }
+extern "C" int vsm_batched_mul_f32(vsm_ctx* c, float* C, const float* A, const float* B, int M, int K, int Nc, int batch) { return bmm_impl<float>(c, C, A, B, M, K, Nc, batch); }
+extern "C" int vsm_batch_inv_f64(vsm_ctx* c, double* X, double* A, int N, int batch, int* info) { return binv_impl<double>(c, X, A, N, batch, info); }
+extern "C" int vsm_batch_inv_f32(vsm_ctx* c, float* X, float* A, int N, int batch, int* info) { return binv_impl<float>(c, X, A, N, batch, info); }
+extern "C" int vsm_batch_solve_f64(vsm_ctx* c, double* X, double* A, const double* B, int N, int Nc, int batch) { return bsolve_impl<double>(c, X, A, B, N, Nc, batch); }
+extern "C" int vsm_batch_solve_f32(vsm_ctx* c, float* X, float* A, const float* B, int N, int Nc, int batch) { return bsolve_impl<float>(c, X, A, B, N, Nc, batch); }
+
+// ---------------------------------------------------------------------------
+// kernel launch helpers (tile size is a compile-time parameter chosen from N)
+// ---------------------------------------------------------------------------
+struct KernelCfg {
+    int threads;
+    int tm;
+};
+static KernelCfg pick_cfg(int N) {
+    if (N <= 8) return {64, 1};
+    if (N <= 24) return {128, 2};
+    if (N <= 48) return {256, 3};
+    return {256, 4};
+}
+
+template <typename T>
+struct Plan {
+    int ld;
+    size_t msz_bytes;
+    int layer_smem_mats, add_smem_mats;
+    size_t layer_smem, add_smem;
+    int layer_grid_per_sm, add_grid_per_sm;
+};
+
+template <typename T>
+static size_t layer_vec_bytes(int n) { return ((size_t)17 * n + kMaxComp) * sizeof(T) + (size_t)2 * n * 4; }
+template <typename T>
+static size_t add_vec_bytes(int n) { return ((size_t)17 * n) * sizeof(T) + (size_t)2 * n * 4; }
+
+template <typename T>
+static int do_launch(vsm_ctx* ctx, bool layer, int tm, const ColArgs<T>& a, unsigned total, int grid, int threads, size_t smem) {
+    cudaError_t e = cudaSuccess;
+    if (layer) {
+        switch (tm) {
+            case 1: e = launch_layer<T, 1>(ctx->stream, a, total, grid, threads, smem); break;
+            case 2: e = launch_layer<T, 2>(ctx->stream, a, total, grid, threads, smem); break;
+            case 3: e = launch_layer<T, 3>(ctx->stream, a, total, grid, threads, smem); break;
+            default: e = launch_layer<T, 4>(ctx->stream, a, total, grid, threads, smem); break;
+        }
+    } else {
+        switch (tm) {
+            case 1: e = launch_adding<T, 1>(ctx->stream, a, total, grid, threads, smem); break;
+            case 2: e = launch_adding<T, 2>(ctx->stream, a, total, grid, threads, smem); break;
+            case 3: e = launch_adding<T, 3>(ctx->stream, a, total, grid, threads, smem); break;
+            default: e = launch_adding<T, 4>(ctx->stream, a, total, grid, threads, smem); break;
+        }
+    }
+    ctx->launches++;
+    if (e != cudaSuccess) {
+        ctx->err = std::string(layer ? "k_layer launch: " : "k_adding launch: ") + cudaGetErrorString(e);
+        return VSM_ERR_CUDA;
+    }
+    return VSM_OK;
+}
+
+template <typename T>
+static int occupancy(const void* kern, int threads, size_t smem) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) != cudaSuccess) {
+        cudaGetLastError();
+        nb = 1;
+    }
+    return std::max(nb, 1);
+}
+
+// ---------------------------------------------------------------------------
+// L2: whole column
+// ---------------------------------------------------------------------------
+template <typename T>
+static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T_SFI, T* hdr,
+                          T* bhr_uw, T* bhr_dw) {
+    if (!ctx) return VSM_ERR_INVALID_ARG;
+    if (!d || d->struct_size != (int)sizeof(vsm_column_desc))
+        return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column: descriptor NULL or struct_size mismatch");
+    if (!R_SFI || !T_SFI) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column: R_SFI/T_SFI NULL");
+    const int N = d->N, nSt = d->nStokes, Nz = d->Nz, nAer = d->nAer, nV = d->nVZA, nM = d->n_moments;
+    const int nSpec = d->nSpec;
+    if (N <= 0 || nSt < 1 || nSt > 4 || N % nSt != 0 || Nz <= 0 || nAer < 0 || nAer + 1 > kMaxComp ||
+        nV <= 0 || nM <= 0 || nSpec < 0 || d->imu0 < 1 || d->imu0 * nSt > N)
+        return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column: bad dimensions");
+    if (d->surface_kind != VSM_SURFACE_LAMBERTIAN_SCALAR)
+        return fail(ctx, VSM_ERR_UNSUPPORTED, "rt_column: only LambertianSurfaceScalar is handled natively");
+    if (!d->mu || !d->wt || !d->vza_weight || !d->ndoubl || !d->scatter || !d->iface ||
+        !d->rayl_allzero || !d->vza_stream || !d->tau_rayl || !d->tau_abs || !d->F0 || !d->Zpp ||
+        !d->Zmp || (nAer > 0 && (!d->aer_omega || !d->aer_ft || !d->tau_aer)))
+        return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column: NULL input array");
+    if (nSpec == 0) return VSM_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int nC = nAer + 1;
+    const int nOut = nV * nSt;
+
+    // ---- small constant tables -> one device blob
+    std::vector<T> fT;
+    std::vector<int> fI;
+    auto pushT = [&](const double* p, size_t n) { size_t o = fT.size(); for (size_t i = 0; i < n; ++i) fT.push_back((T)p[i]); return o; };
+    const size_t o_mu = pushT(d->mu, N), o_wt = pushT(d->wt, N);
+    std::vector<double> taumod((size_t)std::max(1, nAer * Nz)), varmod((size_t)std::max(1, nAer));
+    for (int c = 0; c < nAer; ++c) {
+        // createAero (compEffectiveLayerProperties.jl:67-72), evaluated in FT like the reference
+        const T ft = (T)d->aer_ft[c], om = (T)d->aer_omega[c];
+        varmod[c] = (double)(T)((T(1) - ft) * om / (T(1) - ft * om));
+        for (int iz = 0; iz < Nz; ++iz)
+            taumod[c + (size_t)nAer * iz] = (double)(T)((T(1) - ft * om) * (T)d->tau_aer[c + (size_t)nAer * iz]);
+    }
+    const size_t o_taumod = pushT(taumod.data(), taumod.size());
+    const size_t o_varmod = pushT(varmod.data(), varmod.size());
+    const size_t o_vw = pushT(d->vza_weight, (size_t)nSt * nV * nM);
+    auto pushI = [&](const int32_t* p, size_t n) { size_t o = fI.size(); for (size_t i = 0; i < n; ++i) fI.push_back(p[i]); return o; };
+    const size_t o_nd = pushI(d->ndoubl, Nz), o_sc = pushI(d->scatter, Nz), o_if = pushI(d->iface, Nz);
+    const size_t o_rz = pushI(d->rayl_allzero, Nz);
+    // heavy-first order of the scattering layers
+    std::vector<int> order;
+    for (int iz = 0; iz < Nz; ++iz) if (d->scatter[iz]) order.push_back(iz);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return d->ndoubl[x] > d->ndoubl[y]; });
+    const int nSched = (int)order.size();
+    std::vector<int> order_pad(order);
+    order_pad.resize(Nz, 0);
+    const size_t o_ord = pushI(order_pad.data(), Nz);
+    std::vector<int> vrow(nV);
+    for (int i = 0; i < nV; ++i) {
+        if (d->vza_stream[i] < 1 || d->vza_stream[i] * nSt > N) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column: vza_stream out of range");
+        vrow[i] = (d->vza_stream[i] - 1) * nSt;
+    }
+    const size_t o_vrow = pushI(vrow.data(), nV);
+    for (int iz = 0; iz < Nz; ++iz)
+        if (d->ndoubl[iz] < 0 || d->ndoubl[iz] > 60 || d->iface[iz] < 0 || d->iface[iz] > 3)
+            return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column: ndoubl/iface out of range");
+    const size_t bytesT = fT.size() * sizeof(T), bytesI = fI.size() * sizeof(int);
+    const size_t offI = (bytesT + 15) & ~size_t(15);
+    int rc = ensure(ctx, ctx->consts, offI + bytesI);
+    if (rc) return rc;
+    // the previous call on this stream may still read the blob: order the copy on the stream
+    CK(cudaMemcpyAsync(ctx->consts.p, fT.data(), bytesT, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync((char*)ctx->consts.p + offI, fI.data(), bytesI, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // fT/fI are stack-owned vectors
+    const T* cT = (const T*)ctx->consts.p;
+    const int* cI = (const int*)((char*)ctx->consts.p + offI);
+
+    // ---- arena plan
+    const KernelCfg cfg = pick_cfg(N);
+    const int ld = N | 1;
+    const size_t msz = (size_t)ld * N * sizeof(T);
+    const size_t smax = (size_t)ctx->max_smem_optin;
+    const size_t lv = layer_vec_bytes<T>(N), av = add_vec_bytes<T>(N);
+    if (lv + 1024 > smax) return fail(ctx, VSM_ERR_UNSUPPORTED, "rt_column: N too large");
+    int l_mats = (int)std::min<size_t>(5, (smax - lv) / msz);
+    int a_mats = (int)std::min<size_t>(9, (smax - av) / msz);
+    const size_t l_smem = lv + (size_t)l_mats * msz, a_smem = av + (size_t)a_mats * msz;
+    const size_t l_slab = (size_t)(5 - l_mats) * msz, a_slab = (size_t)(9 - a_mats) * msz;
+
+    const void* kl = nullptr; const void* ka = nullptr;
+    switch (cfg.tm) {
+        case 1: kernel_ptrs<T, 1>(&kl, &ka); break;
+        case 2: kernel_ptrs<T, 2>(&kl, &ka); break;
+        case 3: kernel_ptrs<T, 3>(&kl, &ka); break;
+        default: kernel_ptrs<T, 4>(&kl, &ka); break;
+    }
+    CK(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l_smem));
+    CK(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
+    const int l_occ = occupancy<T>(kl, cfg.threads, l_smem);
+    const int a_occ = occupancy<T>(ka, cfg.threads, a_smem);
+    const int l_grid_max = ctx->num_sms * l_occ, a_grid_max = ctx->num_sms * a_occ;
+
+    // ---- workspace plan: chunk over spectral points and moments
+    const size_t add_item = (size_t)std::max(1, nSched) * ((size_t)2 * N * N + 2 * N) * sizeof(T);
+    const size_t props_pt = ((size_t)Nz * (2 + nC) + (Nz + 1)) * sizeof(T);
+    const size_t part_pt = (size_t)3 * nM * nOut * sizeof(T);
+    uint64_t limit = ctx->ws_limit ? ctx->ws_limit : (uint64_t)24 << 30;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t avail = (uint64_t)free_b + ctx->added.cap + ctx->props.cap + ctx->partial.cap + ctx->slabs.cap;
+    limit = std::min<uint64_t>(limit, avail * 8 / 10);
+    const uint64_t slab_bytes = (uint64_t)l_slab * l_grid_max + (uint64_t)a_slab * a_grid_max;
+    if (limit < slab_bytes + add_item + props_pt + part_pt)
+        return fail(ctx, VSM_ERR_NOMEM, "rt_column: workspace limit too small for one spectral point");
+    const uint64_t budget = limit - slab_bytes;
+    int chunk, Mb;
+    {
+        const uint64_t per_pt_all = (uint64_t)add_item * nM + props_pt + part_pt;
+        if ((uint64_t)nSpec * per_pt_all <= budget) {
+            chunk = nSpec; Mb = nM;
+        } else {
+            const uint64_t per_pt_1 = (uint64_t)add_item + props_pt + part_pt;
+            if ((uint64_t)nSpec * per_pt_1 <= budget) {
+                chunk = nSpec;
+                Mb = (int)std::min<uint64_t>(nM, (budget / nSpec - props_pt - part_pt) / add_item);
+                Mb = std::max(Mb, 1);
+            } else {
+                Mb = 1;
+                chunk = (int)std::max<uint64_t>(1, budget / per_pt_1);
+            }
+        }
+        // keep a launch no larger than needed to fill the machine many times over
+        const uint64_t enough = (uint64_t)a_grid_max * 64;
+        if (Mb > 1 && (uint64_t)chunk * Mb > enough) Mb = (int)std::max<uint64_t>(1, enough / chunk);
+    }
+    if ((rc = ensure(ctx, ctx->added, (size_t)add_item * chunk * Mb))) return rc;
+    if ((rc = ensure(ctx, ctx->props, (size_t)props_pt * chunk))) return rc;
+    if ((rc = ensure(ctx, ctx->partial, (size_t)part_pt * chunk + (size_t)2 * nSt * chunk * sizeof(T)))) return rc;
+    if ((rc = ensure(ctx, ctx->slabs, (size_t)std::max<uint64_t>(slab_bytes, 16)))) return rc;
+    if ((rc = ensure(ctx, ctx->counter, 256))) return rc;
+
+    // timing events
+    ctx->ev_used = 0;
+    ctx->seg_layer.clear();
+    ctx->seg_add.clear();
+    cudaEvent_t ev_begin = get_event(ctx), ev_end = get_event(ctx);
+    CK(cudaEventRecord(ev_begin, ctx->stream));
+
+    const size_t NN = (size_t)N * N;
+    for (int n0 = 0; n0 < nSpec; n0 += chunk) {
+        const int nS = std::min(chunk, nSpec - n0);
+        // --- k_props
+        T* pw = (T*)ctx->props.p;
+        PropsArgs<T> pa;
+        pa.nS = nS; pa.Nz = Nz; pa.nAer = nAer; pa.ldspec = (size_t)nSpec;
+        pa.tau_rayl = (const T*)d->tau_rayl + n0;
+        pa.tau_abs = (const T*)d->tau_abs + n0;
+        pa.varpi_cab = (T)d->varpi_cabannes;
+        pa.aer_tau_mod = cT + o_taumod; pa.aer_varpi_mod = cT + o_varmod;
+        pa.rayl_allzero = cI + o_rz;
+        pa.tau = pw; pa.varpi = pw + (size_t)Nz * nS; pa.tausum = pw + (size_t)2 * Nz * nS;
+        pa.W = pw + (size_t)(2 * Nz + Nz + 1) * nS;
+        k_props<T><<<(nS + 127) / 128, 128, 0, ctx->stream>>>(pa);
+        ctx->launches++;
+        CK(cudaGetLastError());
+
+        T* part = (T*)ctx->partial.p;
+        const size_t per_m = (size_t)nS * nOut;
+        T* cb_uw = part + (size_t)3 * nM * per_m;
+        T* cb_dw = cb_uw + (size_t)nSt * nS;
+
+        ColArgs<T> a;
+        memset(&a, 0, sizeof a);
+        a.N = N; a.nStokes = nSt; a.Nz = Nz; a.nC = nC; a.nVZA = nV; a.ld = ld;
+        a.istart = (d->imu0 - 1) * nSt;
+        a.nS = nS; a.n_sched_layers = nSched; a.z_spectral = 0;
+        a.mu0 = (T)d->mu0; a.albedo = (T)d->albedo;
+        a.mu = cT + o_mu; a.wt = cT + o_wt;
+        a.ndoubl = cI + o_nd; a.scatter = cI + o_sc; a.iface = cI + o_if; a.layer_order = cI + o_ord;
+        a.Zpp = (const T*)d->Zpp; a.Zmp = (const T*)d->Zmp;
+        a.p_tau = pa.tau; a.p_varpi = pa.varpi; a.p_tausum = pa.tausum; a.p_W = pa.W;
+        a.F0 = (const T*)d->F0; a.F0_off = (size_t)n0;
+        a.counter = (unsigned int*)ctx->counter.p;
+        a.vza_row = cI + o_vrow; a.vza_w = cT + o_vw;
+        a.part_R = part; a.part_T = part + (size_t)nM * per_m; a.part_H = part + (size_t)2 * nM * per_m;
+        a.bhr_uw = cb_uw; a.bhr_dw = cb_dw;
+
+        for (int m0 = 0; m0 < nM; m0 += Mb) {
+            const int mb = std::min(Mb, nM - m0);
+            a.m0 = m0; a.Mb = mb;
+            T* ad = (T*)ctx->added.p;
+            const size_t slots = (size_t)mb * Nz * nS;
+            a.add_r = ad; a.add_t = ad + slots * NN; a.add_jp = ad + 2 * slots * NN; a.add_jm = a.add_jp + slots * N;
+            // --- k_layer
+            if (nSched > 0) {
+                const unsigned total = (unsigned)((size_t)nSched * mb * nS);
+                const int grid = (int)std::min<size_t>(total, (size_t)l_grid_max);
+                a.n_smem_mats = l_mats; a.slab = (T*)ctx->slabs.p; a.slab_stride = l_slab / sizeof(T);
+                CK(cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
+                cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+                CK(cudaEventRecord(e0, ctx->stream));
+                rc = do_launch<T>(ctx, true, cfg.tm, a, total, grid, cfg.threads, l_smem);
+                if (rc) return rc;
+                CK(cudaEventRecord(e1, ctx->stream));
+                ctx->seg_layer.push_back({e0, e1});
+            }
+            // --- k_adding
+            {
+                const unsigned total = (unsigned)((size_t)mb * nS);
+                const int grid = (int)std::min<size_t>(total, (size_t)a_grid_max);
+                a.n_smem_mats = a_mats;
+                a.slab = (T*)ctx->slabs.p + ((size_t)l_slab * l_grid_max) / sizeof(T);
+                a.slab_stride = a_slab / sizeof(T);
+                CK(cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
+                cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+                CK(cudaEventRecord(e0, ctx->stream));
+                rc = do_launch<T>(ctx, false, cfg.tm, a, total, grid, cfg.threads, a_smem);
+                if (rc) return rc;
+                CK(cudaEventRecord(e1, ctx->stream));
+                ctx->seg_add.push_back({e0, e1});
+            }
+        }
+        // --- k_reduce into the caller's outputs (chunk window)
+        k_reduce<T><<<(unsigned)((per_m + 255) / 256), 256, 0, ctx->stream>>>(
+            nM, per_m, a.part_R, a.part_T, hdr ? a.part_H : (const T*)nullptr,
+            R_SFI + (size_t)n0 * nOut, T_SFI + (size_t)n0 * nOut, hdr ? hdr + (size_t)n0 * nOut : (T*)nullptr);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        if (bhr_uw) CK(cudaMemcpyAsync(bhr_uw + (size_t)n0 * nSt, cb_uw, (size_t)nSt * nS * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+        if (bhr_dw) CK(cudaMemcpyAsync(bhr_dw + (size_t)n0 * nSt, cb_dw, (size_t)nSt * nS * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    CK(cudaEventRecord(ev_end, ctx->stream));
+    ctx->ev[0] = ev_begin;
+    ctx->ev[1] = ev_end;
+    ctx->timing_valid = true;
+    return VSM_OK;
+}
+
+extern "C" int vsm_rt_column_f64(vsm_ctx* c, const vsm_column_desc* d, double* R, double* T_, double* hdr, double* uw, double* dw) { return rt_column_impl<double>(c, d, R, T_, hdr, uw, dw); }
+extern "C" int vsm_rt_column_f32(vsm_ctx* c, const vsm_column_desc* d, float* R, float* T_, float* hdr, float* uw, float* dw) { return rt_column_impl<float>(c, d, R, T_, hdr, uw, dw); }
+
+extern "C" int vsm_last_column_ms(vsm_ctx* ctx, float* total_ms, float* doubling_ms, float* adding_ms) {
+    if (!ctx) return VSM_ERR_INVALID_ARG;
+    if (!ctx->timing_valid) return fail(ctx, VSM_ERR_INVALID_ARG, "vsm_last_column_ms: no column call yet");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->ev[1]));
+    float t = 0, tl = 0, ta = 0, x = 0;
+    CK(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]));
+    for (auto& s : ctx->seg_layer) { CK(cudaEventElapsedTime(&x, s.first, s.second)); tl += x; }
+    for (auto& s : ctx->seg_add) { CK(cudaEventElapsedTime(&x, s.first, s.second)); ta += x; }
+    if (total_ms) *total_ms = t;
+    if (doubling_ms) *doubling_ms = tl;
+    if (adding_ms) *adding_ms = ta;
+    return VSM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// L1: one layer (implemented in vsm_layer.cu)
+// ---------------------------------------------------------------------------
+template <typename T> int rt_layer_impl(vsm_ctx* ctx, const vsm_layer_desc* d);
+extern "C" int vsm_rt_layer_f64(vsm_ctx* c, const vsm_layer_desc* d) {
+    return fail(c, VSM_ERR_UNSUPPORTED, "vsm_rt_layer: not built yet");
+}
+extern "C" int vsm_rt_layer_f32(vsm_ctx* c, const vsm_layer_desc* d) {
+    return fail(c, VSM_ERR_UNSUPPORTED, "vsm_rt_layer: not built yet");
+}

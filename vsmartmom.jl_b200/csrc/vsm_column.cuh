@@ -1,0 +1,627 @@
+// vsm_column.cuh -- fused kernels of the column solver (L2) and layer step (L1).
+//
+//   k_props   : per-(layer, spectral point) optical-property mixing + tau prefix sum
+//               (constructCoreOpticalProperties / extractEffectiveProps,
+//                LayerOpticalProperties/compEffectiveLayerProperties.jl:11-93, types.jl:1262-1308)
+//   k_layer   : elemental! + ndoubl x doubling! for one (point, layer, moment), all on-chip
+//               (CoreKernel/elemental.jl:174-462, doubling.jl:38-252, rt_helpers.jl:102-166)
+//   k_adding  : the whole interaction! chain over layers + Lambertian surface + hdrf +
+//               postprocessing_vza! for one (point, moment), composite layer on-chip
+//               (CoreKernel/interaction.jl:52-266, Surfaces/lambertian_surface.jl:41-95,
+//                interaction_hdrf.jl:4-42, tools/postprocessing_vza.jl:23-94)
+//   k_reduce  : deterministic sum of per-moment partial outputs (rt_run.jl:383 loop order)
+#pragma once
+#include "vsm_device.cuh"
+
+namespace vsm {
+
+constexpr int kMaxComp = 8;      // Rayleigh + up to 7 aerosol types
+
+// ----------------------------------------------------------------------------
+// Arena: matrix k lives in shared memory if k < n_smem, else in the CTA's slab.
+// ----------------------------------------------------------------------------
+template <typename T>
+struct Arena {
+    T* smem;
+    T* slab;
+    int n_smem;
+    size_t msz;
+    __device__ T* mat(int k) const {
+        return k < n_smem ? smem + (size_t)k * msz : slab + (size_t)(k - n_smem) * msz;
+    }
+};
+
+// ----------------------------------------------------------------------------
+// k_props
+// ----------------------------------------------------------------------------
+template <typename T>
+struct PropsArgs {
+    int nS;              // points in this chunk
+    int Nz, nAer;
+    size_t ldspec;       // stride between layers in tau_rayl / tau_abs (= nSpec of the call)
+    const T* tau_rayl;   // already offset to the chunk start
+    const T* tau_abs;
+    T varpi_cab;
+    const T* aer_tau_mod;    // [nAer*Nz] (a + nAer*iz)   createAero τ_mod
+    const T* aer_varpi_mod;  // [nAer]
+    const int* rayl_allzero; // [Nz]
+    // outputs, layout [iz*nS + p]
+    T* tau; T* varpi; T* tausum /* (Nz+1) rows */; T* W /* [(c*Nz + iz)*nS + p] */;
+};
+
+template <typename T>
+__global__ void k_props(PropsArgs<T> a) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.nS) return;
+    const int nC = a.nAer + 1;
+    T ts = T(0);
+    a.tausum[p] = ts;
+    for (int iz = 0; iz < a.Nz; ++iz) {
+        T tau = a.tau_rayl[p + (size_t)iz * a.ldspec];
+        T varpi = a.varpi_cab;
+        T W[kMaxComp];
+        W[0] = T(1);
+        bool xz = a.rayl_allzero[iz] != 0;
+        for (int c = 0; c < a.nAer; ++c) {
+            const T ty = a.aer_tau_mod[c + a.nAer * iz];
+            const T py = a.aer_varpi_mod[c];
+            const T wx = tau * varpi, wy = ty * py, w = wx + wy;
+            const T tnew = tau + ty;
+            const T vnew = w / (tnew > T(0) ? tnew : T(1));
+            if (xz) {
+                for (int q = 0; q <= c; ++q) W[q] = T(0);
+                W[c + 1] = T(1);
+            } else if (wy == T(0)) {
+                W[c + 1] = T(0);
+            } else {
+                const T fx = wx / w, fy = wy / w;
+                for (int q = 0; q <= c; ++q) W[q] *= fx;
+                W[c + 1] = fy;
+            }
+            xz = xz && (wy == T(0));
+            tau = tnew;
+            varpi = vnew;
+        }
+        {   // + CoreAbsorptionOpticalProperties (types.jl:1302-1308)
+            const T tnew = tau + a.tau_abs[p + (size_t)iz * a.ldspec];
+            const T wx = tau * varpi;
+            varpi = wx / (tnew > T(0) ? tnew : T(1));
+            tau = tnew;
+        }
+        a.tau[(size_t)iz * a.nS + p] = tau;
+        a.varpi[(size_t)iz * a.nS + p] = varpi;
+        for (int c = 0; c < nC; ++c) a.W[((size_t)c * a.Nz + iz) * a.nS + p] = W[c];
+        ts = ts + tau;                       // τ_sum_all[:,iz+1] = τ_sum_all[:,iz] + τ
+        a.tausum[(size_t)(iz + 1) * a.nS + p] = ts;
+    }
+}
+
+// ----------------------------------------------------------------------------
+// shared argument block of k_layer / k_adding
+// ----------------------------------------------------------------------------
+template <typename T>
+struct ColArgs {
+    int N, nStokes, Nz, nC, nVZA;
+    int ld;                  // arena leading dimension (odd, >= N)
+    int istart;              // 0-based first row of the solar stream  (iμ₀Nstart-1)
+    int nS;                  // points in this chunk
+    int m0, Mb;              // first moment and number of moments of this batch
+    int n_sched_layers;      // number of scattering layers (entries of layer_order)
+    int n_smem_mats;
+    int z_spectral;          // L1 only: Z given per spectral point
+    T mu0, albedo;
+    const T* mu; const T* wt;                         // [N]
+    const int* ndoubl; const int* scatter; const int* iface; const int* layer_order;  // [Nz]
+    const T* Zpp; const T* Zmp;                       // (N,N,nC,n_moments)
+    const T* p_tau; const T* p_varpi; const T* p_tausum; const T* p_W;   // k_props outputs
+    const T* F0; size_t F0_off;                       // (nStokes, nSpec) ; column offset of chunk
+    // added-layer scratch: slot = (mi*Nz + iz)*nS + p
+    T* add_r; T* add_t; T* add_jp; T* add_jm;
+    // spill slabs and the work counter
+    T* slab; size_t slab_stride;
+    unsigned int* counter;
+    // epilogue
+    const int* vza_row;      // [nVZA] 0-based first row of the VZA stream
+    const T* vza_w;          // (nStokes,nVZA,n_moments)
+    T* part_R; T* part_T; T* part_H;   // [(m*nS + p)*nOut + o]
+    T* bhr_uw; T* bhr_dw;              // (nStokes, nS) chunk-local, may be null
+};
+
+__device__ inline unsigned int next_item(unsigned int* counter, unsigned int* sh) {
+    __syncthreads();
+    if (threadIdx.x == 0) *sh = atomicAdd(counter, 1u);
+    __syncthreads();
+    return *sh;
+}
+
+// ----------------------------------------------------------------------------
+// elemental r⁻⁺/t⁺⁺ and solar sources into the arena  (elemental.jl:289-392)
+// ----------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void elemental_fill(const ColArgs<T>& a, int m, int nd, T dtau, T varpi,
+                                               T tausum, const T* __restrict__ Wc,
+                                               const T* __restrict__ Zpp, const T* __restrict__ Zmp,
+                                               size_t zstride, const T* __restrict__ F0n,
+                                               const uint32_t* __restrict__ dmask,
+                                               T* r, T* t, T* jp, T* jm) {
+    const int n = a.N, ld = a.ld, nC = a.nC;
+    const T wsc = (m == 0) ? T(0.5) : T(0.25);       // scaled_weights / fourier_weight
+    const T eps = Num<T>::eps();
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        const int i = e % n, j = e / n;
+        T zm = T(0), zp = T(0);
+        if (nC == 1) {
+            zm = Zmp[e]; zp = Zpp[e];
+        } else {
+            for (int c = 0; c < nC; ++c) {
+                zm = fma(Wc[c], Zmp[(size_t)c * zstride + e], zm);
+                zp = fma(Wc[c], Zpp[(size_t)c * zstride + e], zp);
+            }
+        }
+        const T mui = a.mu[i], muj = a.mu[j];
+        const T wj = a.wt[j] * wsc;
+        T rv, tv;
+        if (wj > eps) {
+            rv = varpi * zm * (muj / (mui + muj)) * wj *
+                 (-Num<T>::expm1_(-dtau * ((T(1) / mui) + (T(1) / muj))));
+            if (mui == muj) {
+                if (i == j)
+                    tv = Num<T>::exp_(-dtau / mui) * (T(1) + varpi * zp * (dtau / mui) * (a.wt[i] * wsc));
+                else
+                    tv = Num<T>::exp_(-dtau / muj) * (varpi * zp * (dtau / mui) * wj);
+            } else {
+                tv = varpi * zp * (muj / (mui - muj)) * wj * expdiff_neg<T>(dtau / mui, dtau / muj);
+            }
+        } else {
+            rv = T(0);
+            tv = (i == j) ? Num<T>::exp_(-dtau / mui) : T(0);
+        }
+        if (nd >= 1) rv = Num<T>::flip(rv, dmask[i]);      // apply_D_elemental!, nd>=1 branch
+        r[i + (size_t)j * ld] = rv;
+        t[i + (size_t)j * ld] = tv;
+    }
+    const T wct02 = wsc;
+    const T mus = a.mu[a.istart];
+    const T att = Num<T>::exp_(-tausum / mus);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        T zpI = T(0), zmI = T(0);
+        for (int s = 0; s < a.nStokes; ++s) {
+            const size_t e = (size_t)i + (size_t)(a.istart + s) * n;
+            T zp = T(0), zm = T(0);
+            if (nC == 1) { zp = Zpp[e]; zm = Zmp[e]; }
+            else for (int c = 0; c < nC; ++c) {
+                zp = fma(Wc[c], Zpp[(size_t)c * zstride + e], zp);
+                zm = fma(Wc[c], Zmp[(size_t)c * zstride + e], zm);
+            }
+            zpI += zp * F0n[s];
+            zmI += zm * F0n[s];
+        }
+        const T mui = a.mu[i];
+        T vp;
+        if (i >= a.istart && i < a.istart + a.nStokes)
+            vp = wct02 * varpi * zpI * (dtau / mui) * Num<T>::exp_(-dtau / mui);
+        else
+            vp = wct02 * varpi * zpI * (mus / (mui - mus)) * expdiff_neg<T>(dtau / mui, dtau / mus);
+        T vm = wct02 * varpi * zmI * (mus / (mui + mus)) *
+               (-Num<T>::expm1_(-dtau * ((T(1) / mui) + (T(1) / mus))));
+        vp *= att;
+        vm *= att;
+        if (nd >= 1) vm = Num<T>::flip(vm, dmask[i]);
+        jp[i] = vp;
+        jm[i] = vm;
+    }
+}
+
+// ----------------------------------------------------------------------------
+// ndoubl doublings in the arena.  mats: r, t, X1, X2, X3 (pointers are rotated).
+// ----------------------------------------------------------------------------
+template <typename T, int TM>
+__device__ __forceinline__ void doubling_loop(int n, int ld, int nd, T expk, T*& r, T*& t, T*& X1,
+                                              T* X2, T* X3, T* jp, T* jm, T* j1p, T* j1m, T* v1,
+                                              T* v2, T* vec, T* part, int* piv,
+                                              const uint32_t* dmask) {
+    for (int it = 0; it < nd; ++it) {
+        // X1 = I - r r          (compute_geometric_progression!, rt_helpers.jl:103)
+        cta_mm<T, TM, TM, false>(n, r, ld, r, ld, dmask, [&](int i, int j, T acc) {
+            X1[i + (size_t)j * ld] = (i == j ? T(1) : T(0)) - acc;
+        });
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {   // doubling_source_update!, :131-132
+            j1p[i] = jp[i] * expk;
+            j1m[i] = jm[i] * expk;
+        }
+        __syncthreads();
+        cta_inverse<T>(n, X1, ld, vec, piv, nullptr);          // :104
+        // X2 = t * gp           (:105)
+        cta_mm<T, TM, TM, false>(n, t, ld, X1, ld, dmask,
+                                 [&](int i, int j, T acc) { X2[i + (size_t)j * ld] = acc; });
+        // v1 = j1m + r jp ; v2 = jp + r j1m      (:133-134)
+        cta_mv<T, false>(n, r, ld, jp, dmask, part, [&](int i, T s) { v1[i] = j1m[i] + s; });
+        cta_mv<T, false>(n, r, ld, j1m, dmask, part, [&](int i, T s) { v2[i] = jp[i] + s; });
+        cta_mv<T, false>(n, X2, ld, v1, dmask, part, [&](int i, T s) { jm[i] = jm[i] + s; });
+        cta_mv<T, false>(n, X2, ld, v2, dmask, part, [&](int i, T s) { jp[i] = j1p[i] + s; });
+        // X3 = tt r ; X1 = tt t   (doubling_rt_update!, :162-163)
+        cta_mm<T, TM, TM, false>(n, X2, ld, r, ld, dmask,
+                                 [&](int i, int j, T acc) { X3[i + (size_t)j * ld] = acc; });
+        cta_mm<T, TM, TM, false>(n, X2, ld, t, ld, dmask,
+                                 [&](int i, int j, T acc) { X1[i + (size_t)j * ld] = acc; });
+        __syncthreads();
+        // r += (tt r) t
+        cta_mm<T, TM, TM, false>(n, X3, ld, t, ld, dmask,
+                                 [&](int i, int j, T acc) { r[i + (size_t)j * ld] += acc; });
+        __syncthreads();
+        T* tmp = t; t = X1; X1 = tmp;        // t = tt t
+        expk = expk * expk;                  // :164
+    }
+}
+
+template <typename T, int TM>
+__global__ void __launch_bounds__(256) k_layer(ColArgs<T> a, unsigned int total) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = a.N, ld = a.ld;
+    const size_t msz = (size_t)ld * n;
+    T* sm = reinterpret_cast<T*>(smem_raw);
+    Arena<T> ar{sm, a.slab + (size_t)blockIdx.x * a.slab_stride, a.n_smem_mats, msz};
+    T* vbase = sm + (size_t)a.n_smem_mats * msz;
+    T* jp = vbase;           T* jm = jp + n;     T* j1p = jm + n;   T* j1m = j1p + n;
+    T* v1 = j1m + n;         T* v2 = v1 + n;     T* vec = v2 + n;   /* 3n */
+    T* part = vec + 3 * n;   /* 8n */            T* Wc = part + 8 * n;   /* kMaxComp */
+    uint32_t* dmask = reinterpret_cast<uint32_t*>(Wc + kMaxComp);
+    int* piv = reinterpret_cast<int*>(dmask + n);
+    __shared__ unsigned int sh_item;
+
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dmask[i] = dmask_of(i, a.nStokes);
+
+    for (;;) {
+        const unsigned int item = next_item(a.counter, &sh_item);
+        if (item >= total) break;
+        const int p = item % a.nS;
+        const unsigned int rest = item / a.nS;
+        const int mi = rest % a.Mb;
+        const int iz = a.layer_order[rest / a.Mb];
+        const int m = a.m0 + mi;
+        const int nd = a.ndoubl[iz];
+        const size_t pi = (size_t)iz * a.nS + p;
+        const T tau = a.p_tau[pi], varpi = a.p_varpi[pi], tausum = a.p_tausum[pi];
+        const T dtau = tau / (T)exp2((double)nd);          // dτ = τ ./ 2^ndoubl (rt_kernel.jl:285)
+        const T expk = Num<T>::exp_(-dtau / a.mu0);        // init_layer (rt_kernel.jl:347)
+        if (threadIdx.x < a.nC) Wc[threadIdx.x] = a.p_W[((size_t)threadIdx.x * a.Nz + iz) * a.nS + p];
+        __syncthreads();
+        T* r = ar.mat(0); T* t = ar.mat(1); T* X1 = ar.mat(2); T* X2 = ar.mat(3); T* X3 = ar.mat(4);
+        const size_t zstride = (size_t)n * n;
+        const T* Zpp = a.Zpp + (size_t)m * a.nC * zstride;
+        const T* Zmp = a.Zmp + (size_t)m * a.nC * zstride;
+        elemental_fill<T>(a, m, nd, dtau, varpi, tausum, Wc, Zpp, Zmp, zstride,
+                          a.F0 + (a.F0_off + p) * a.nStokes, dmask, r, t, jp, jm);
+        __syncthreads();
+        doubling_loop<T, TM>(n, ld, nd, expk, r, t, X1, X2, X3, jp, jm, j1p, j1m, v1, v2, vec, part,
+                             piv, dmask);
+        // apply_D_matrix! / apply_D_matrix_SFI! (doubling.jl:178-216): r⁻⁺ <- D r*, j₀⁻ <- D j*
+        const size_t slot = ((size_t)mi * a.Nz + iz) * a.nS + p;
+        T* gr = a.add_r + slot * zstride;
+        T* gt = a.add_t + slot * zstride;
+        for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+            const int i = e % n, j = e / n;
+            T rv = r[i + (size_t)j * ld];
+            if (nd >= 1) rv = Num<T>::flip(rv, dmask[i]);
+            gr[e] = rv;
+            gt[e] = t[i + (size_t)j * ld];
+        }
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            T vm = jm[i];
+            if (nd >= 1) vm = Num<T>::flip(vm, dmask[i]);
+            a.add_jp[slot * n + i] = jp[i];
+            a.add_jm[slot * n + i] = vm;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------
+// interaction!  (interaction.jl:52-266) on arena-resident composite + added layer.
+// Composite: RA=R⁻⁺ RB=R⁺⁻ TC=T⁺⁺ TD=T⁻⁻ ; added: r=r⁻⁺ t=t⁺⁺ (r⁺⁻ = D r D, t⁻⁻ = D t D
+// folded in through dmask; rpm_zero / t_ident describe the surface layer where
+// r⁺⁻ = 0 and t = I).
+// ----------------------------------------------------------------------------
+template <typename T>
+struct CompPtrs {
+    T *RA, *RB, *TC, *TD, *r, *t, *X1, *X2, *X3;
+};
+
+template <typename T, int TM>
+__device__ __forceinline__ void interact(int iface, int n, int ld, CompPtrs<T>& c, T* J0p, T* J0m,
+                                         const T* jp, const T* jm, T* v1, T* vec, T* part,
+                                         int* piv, const uint32_t* dmask, bool rpm_zero,
+                                         bool t_ident) {
+    auto at = [ld](T* M, int i, int j) -> T& { return M[i + (size_t)j * ld]; };
+    if (iface == 3) {
+        // temp2 = I - r⁻⁺ R⁺⁻ ; temp1 = inv ; T01_inv = T⁻⁻ temp1        (:220-226)
+        cta_mm<T, TM, TM, false>(n, c.r, ld, c.RB, ld, dmask, [&](int i, int j, T acc) {
+            at(c.X1, i, j) = (i == j ? T(1) : T(0)) - acc;
+        });
+        __syncthreads();
+        cta_inverse<T>(n, c.X1, ld, vec, piv, nullptr);
+        cta_mm<T, TM, TM, false>(n, c.TD, ld, c.X1, ld, dmask,
+                                 [&](int i, int j, T acc) { at(c.X2, i, j) = acc; });
+        // J₀⁻ += T01_inv (r⁻⁺ J₀⁺ + j₀⁻)                                   (:229)
+        cta_mv<T, false>(n, c.r, ld, J0p, dmask, part, [&](int i, T s) { v1[i] = s + jm[i]; });
+        cta_mv<T, false>(n, c.X2, ld, v1, dmask, part, [&](int i, T s) { J0m[i] = J0m[i] + s; });
+        // R⁻⁺ += T01_inv r⁻⁺ T⁺⁺                                          (:237)
+        cta_mm<T, TM, TM, false>(n, c.X2, ld, c.r, ld, dmask,
+                                 [&](int i, int j, T acc) { at(c.X3, i, j) = acc; });
+        __syncthreads();
+        cta_mm<T, TM, TM, false>(n, c.X3, ld, c.TC, ld, dmask,
+                                 [&](int i, int j, T acc) { at(c.RA, i, j) += acc; });
+        // T⁻⁻ = T01_inv t⁻⁻                                               (:240)
+        if (t_ident) {
+            T* tmp = c.TD; c.TD = c.X2; c.X2 = tmp;
+        } else {
+            cta_mm<T, TM, TM, true>(n, c.X2, ld, c.t, ld, dmask, [&](int i, int j, T acc) {
+                at(c.TD, i, j) = Num<T>::flip(acc, dmask[j]);
+            });
+        }
+        __syncthreads();
+        // temp2 = I - R⁺⁻ r⁻⁺ ; inv ; T21_inv = t⁺⁺ temp1                  (:248-251)
+        cta_mm<T, TM, TM, false>(n, c.RB, ld, c.r, ld, dmask, [&](int i, int j, T acc) {
+            at(c.X1, i, j) = (i == j ? T(1) : T(0)) - acc;
+        });
+        __syncthreads();
+        cta_inverse<T>(n, c.X1, ld, vec, piv, nullptr);
+        T* T21;
+        if (t_ident) {
+            T21 = c.X1;
+        } else {
+            cta_mm<T, TM, TM, false>(n, c.t, ld, c.X1, ld, dmask,
+                                     [&](int i, int j, T acc) { at(c.X2, i, j) = acc; });
+            T21 = c.X2;
+        }
+        // J₀⁺ = j₀⁺ + T21_inv (J₀⁺ + R⁺⁻ j₀⁻)                              (:254)
+        cta_mv<T, false>(n, c.RB, ld, jm, dmask, part, [&](int i, T s) { v1[i] = J0p[i] + s; });
+        cta_mv<T, false>(n, T21, ld, v1, dmask, part, [&](int i, T s) { J0p[i] = jp[i] + s; });
+        // T⁺⁺ = T21_inv T⁺⁺                                               (:262)
+        cta_mm<T, TM, TM, false>(n, T21, ld, c.TC, ld, dmask,
+                                 [&](int i, int j, T acc) { at(c.X3, i, j) = acc; });
+        __syncthreads();
+        { T* tmp = c.TC; c.TC = c.X3; c.X3 = tmp; }
+        // R⁺⁻ = r⁺⁻ + T21_inv R⁺⁻ t⁻⁻                                      (:265)
+        cta_mm<T, TM, TM, false>(n, T21, ld, c.RB, ld, dmask,
+                                 [&](int i, int j, T acc) { at(c.X3, i, j) = acc; });
+        __syncthreads();
+        if (t_ident) {
+            if (rpm_zero) {
+                T* tmp = c.RB; c.RB = c.X3; c.X3 = tmp;
+            } else {
+                for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+                    const int i = e % n, j = e / n;
+                    at(c.RB, i, j) = Num<T>::flip(at(c.r, i, j), dmask[i] ^ dmask[j]) + at(c.X3, i, j);
+                }
+            }
+        } else {
+            cta_mm<T, TM, TM, true>(n, c.X3, ld, c.t, ld, dmask, [&](int i, int j, T acc) {
+                const T rpm = rpm_zero ? T(0) : Num<T>::flip(at(c.r, i, j), dmask[i] ^ dmask[j]);
+                at(c.RB, i, j) = rpm + Num<T>::flip(acc, dmask[j]);
+            });
+        }
+        __syncthreads();
+    } else if (iface == 1) {
+        // J₀⁻ += T⁻⁻ (r⁻⁺ J₀⁺ + j₀⁻) ; J₀⁺ = j₀⁺ + t⁺⁺ J₀⁺                  (:104-105)
+        cta_mv<T, false>(n, c.r, ld, J0p, dmask, part, [&](int i, T s) { v1[i] = s + jm[i]; });
+        cta_mv<T, false>(n, c.TD, ld, v1, dmask, part, [&](int i, T s) { J0m[i] = J0m[i] + s; });
+        if (t_ident) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) J0p[i] = jp[i] + J0p[i];
+            __syncthreads();
+        } else {
+            cta_mv<T, false>(n, c.t, ld, J0p, dmask, part, [&](int i, T s) { v1[i] = jp[i] + s; });
+            for (int i = threadIdx.x; i < n; i += blockDim.x) J0p[i] = v1[i];
+            __syncthreads();
+        }
+        // R⁻⁺ = T⁻⁻ r⁻⁺ T⁺⁺ ; R⁺⁻ = r⁺⁻ ; T⁺⁺ = t⁺⁺ T⁺⁺ ; T⁻⁻ = T⁻⁻ t⁻⁻     (:114-117)
+        cta_mm<T, TM, TM, false>(n, c.TD, ld, c.r, ld, dmask,
+                                 [&](int i, int j, T acc) { at(c.X3, i, j) = acc; });
+        __syncthreads();
+        cta_mm<T, TM, TM, false>(n, c.X3, ld, c.TC, ld, dmask,
+                                 [&](int i, int j, T acc) { at(c.RA, i, j) = acc; });
+        for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+            const int i = e % n, j = e / n;
+            at(c.RB, i, j) = rpm_zero ? T(0) : Num<T>::flip(at(c.r, i, j), dmask[i] ^ dmask[j]);
+        }
+        if (!t_ident) {
+            cta_mm<T, TM, TM, false>(n, c.t, ld, c.TC, ld, dmask,
+                                     [&](int i, int j, T acc) { at(c.X1, i, j) = acc; });
+            cta_mm<T, TM, TM, true>(n, c.TD, ld, c.t, ld, dmask, [&](int i, int j, T acc) {
+                at(c.X2, i, j) = Num<T>::flip(acc, dmask[j]);
+            });
+            __syncthreads();
+            T* tmp = c.TC; c.TC = c.X1; c.X1 = tmp;
+            tmp = c.TD; c.TD = c.X2; c.X2 = tmp;
+        }
+        __syncthreads();
+    } else if (iface == 2) {
+        // J₀⁺ = j₀⁺ + t⁺⁺ (J₀⁺ + R⁺⁻ j₀⁻) ; J₀⁻ += T⁻⁻ j₀⁻                  (:149-150)
+        cta_mv<T, false>(n, c.RB, ld, jm, dmask, part, [&](int i, T s) { v1[i] = J0p[i] + s; });
+        if (t_ident) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) J0p[i] = jp[i] + v1[i];
+            __syncthreads();
+        } else {
+            cta_mv<T, false>(n, c.t, ld, v1, dmask, part, [&](int i, T s) { J0p[i] = jp[i] + s; });
+        }
+        cta_mv<T, false>(n, c.TD, ld, jm, dmask, part, [&](int i, T s) { J0m[i] = J0m[i] + s; });
+        // T⁺⁺ = t⁺⁺ T⁺⁺ ; T⁻⁻ = T⁻⁻ t⁻⁻ ; R⁺⁻ = t⁺⁺ R⁺⁻ t⁻⁻                  (:159-161)
+        if (!t_ident) {
+            cta_mm<T, TM, TM, false>(n, c.t, ld, c.TC, ld, dmask,
+                                     [&](int i, int j, T acc) { at(c.X1, i, j) = acc; });
+            cta_mm<T, TM, TM, true>(n, c.TD, ld, c.t, ld, dmask, [&](int i, int j, T acc) {
+                at(c.X2, i, j) = Num<T>::flip(acc, dmask[j]);
+            });
+            cta_mm<T, TM, TM, false>(n, c.t, ld, c.RB, ld, dmask,
+                                     [&](int i, int j, T acc) { at(c.X3, i, j) = acc; });
+            __syncthreads();
+            T* tmp = c.TC; c.TC = c.X1; c.X1 = tmp;
+            tmp = c.TD; c.TD = c.X2; c.X2 = tmp;
+            cta_mm<T, TM, TM, true>(n, c.X3, ld, c.t, ld, dmask, [&](int i, int j, T acc) {
+                at(c.RB, i, j) = Num<T>::flip(acc, dmask[j]);
+            });
+        }
+        __syncthreads();
+    } else {
+        // J₀⁺ = j₀⁺ + t⁺⁺ J₀⁺ ; J₀⁻ += T⁻⁻ j₀⁻ ; T⁻⁻ = t⁻⁻ T⁻⁻ ; T⁺⁺ = t⁺⁺ T⁺⁺    (:60-71)
+        if (t_ident) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) J0p[i] = jp[i] + J0p[i];
+            __syncthreads();
+        } else {
+            cta_mv<T, false>(n, c.t, ld, J0p, dmask, part, [&](int i, T s) { v1[i] = jp[i] + s; });
+            for (int i = threadIdx.x; i < n; i += blockDim.x) J0p[i] = v1[i];
+            __syncthreads();
+        }
+        cta_mv<T, false>(n, c.TD, ld, jm, dmask, part, [&](int i, T s) { J0m[i] = J0m[i] + s; });
+        if (!t_ident) {
+            // t⁻⁻ T⁻⁻ = D t D T⁻⁻ : row sign D_i outside, D_k inside
+            cta_mm<T, TM, TM, true>(n, c.t, ld, c.TD, ld, dmask, [&](int i, int j, T acc) {
+                at(c.X2, i, j) = Num<T>::flip(acc, dmask[i]);
+            });
+            cta_mm<T, TM, TM, false>(n, c.t, ld, c.TC, ld, dmask,
+                                     [&](int i, int j, T acc) { at(c.X1, i, j) = acc; });
+            __syncthreads();
+            T* tmp = c.TC; c.TC = c.X1; c.X1 = tmp;
+            tmp = c.TD; c.TD = c.X2; c.X2 = tmp;
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T, int TM>
+__global__ void __launch_bounds__(256) k_adding(ColArgs<T> a, unsigned int total) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = a.N, ld = a.ld;
+    const size_t msz = (size_t)ld * n;
+    T* sm = reinterpret_cast<T*>(smem_raw);
+    Arena<T> ar{sm, a.slab + (size_t)blockIdx.x * a.slab_stride, a.n_smem_mats, msz};
+    T* vbase = sm + (size_t)a.n_smem_mats * msz;
+    T* J0p = vbase;         T* J0m = J0p + n;   T* jp = J0m + n;   T* jm = jp + n;
+    T* v1 = jm + n;         T* hv = v1 + n;     T* vec = hv + n;   /* 3n */
+    T* part = vec + 3 * n;  /* 8n */
+    uint32_t* dmask = reinterpret_cast<uint32_t*>(part + 8 * n);
+    int* piv = reinterpret_cast<int*>(dmask + n);
+    __shared__ unsigned int sh_item;
+    const size_t zstride = (size_t)n * n;
+    const int nOut = a.nVZA * a.nStokes;
+
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dmask[i] = dmask_of(i, a.nStokes);
+
+    for (;;) {
+        const unsigned int item = next_item(a.counter, &sh_item);
+        if (item >= total) break;
+        const int p = item % a.nS;
+        const int mi = item / a.nS;
+        const int m = a.m0 + mi;
+        CompPtrs<T> c{ar.mat(0), ar.mat(1), ar.mat(2), ar.mat(3), ar.mat(4),
+                      ar.mat(5), ar.mat(6), ar.mat(7), ar.mat(8)};
+        for (int iz = 0; iz < a.Nz; ++iz) {
+            const bool sc = a.scatter[iz] != 0;
+            T* dr = (iz == 0) ? c.RA : c.r;
+            T* dt = (iz == 0) ? c.TC : c.t;
+            T* djp = (iz == 0) ? J0p : jp;
+            T* djm = (iz == 0) ? J0m : jm;
+            if (sc) {
+                const size_t slot = ((size_t)mi * a.Nz + iz) * a.nS + p;
+                const T* gr = a.add_r + slot * zstride;
+                const T* gt = a.add_t + slot * zstride;
+                for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+                    const int i = e % n, j = e / n;
+                    dr[i + (size_t)j * ld] = gr[e];
+                    dt[i + (size_t)j * ld] = gt[e];
+                }
+                for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                    djp[i] = a.add_jp[slot * n + i];
+                    djm[i] = a.add_jm[slot * n + i];
+                }
+            } else {
+                // zero_added_noscat! (rt_helpers.jl:174-180): r = 0, t = diag(exp(-τ/μ)), j = 0
+                const T tau = a.p_tau[(size_t)iz * a.nS + p];
+                for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+                    const int i = e % n, j = e / n;
+                    dr[i + (size_t)j * ld] = T(0);
+                    dt[i + (size_t)j * ld] = (i == j) ? Num<T>::exp_(-tau / a.mu[i]) : T(0);
+                }
+                for (int i = threadIdx.x; i < n; i += blockDim.x) { djp[i] = T(0); djm[i] = T(0); }
+            }
+            __syncthreads();
+            if (iz == 0) {
+                // copy_added_to_composite! (rt_helpers.jl:204-215)
+                for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+                    const int i = e % n, j = e / n;
+                    const uint32_t s = dmask[i] ^ dmask[j];
+                    c.RB[i + (size_t)j * ld] = sc ? Num<T>::flip(c.RA[i + (size_t)j * ld], s) : T(0);
+                    c.TD[i + (size_t)j * ld] = Num<T>::flip(c.TC[i + (size_t)j * ld], s);
+                }
+                __syncthreads();
+            } else {
+                interact<T, TM>(a.iface[iz], n, ld, c, J0p, J0m, jp, jm, v1, vec, part, piv, dmask,
+                                !sc, false);
+            }
+        }
+        // ---- Lambertian surface (lambertian_surface.jl:41-95) + last interaction (rt_run.jl:459-465)
+        const T ts_end = a.p_tausum[(size_t)a.Nz * a.nS + p];
+        T jps_sun = T(0);
+        if (m == 0) {
+            const T rho = T(2) * a.albedo;
+            const T att = Num<T>::exp_(-ts_end / a.mu0);
+            for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+                const int i = e % n, j = e / n;
+                const bool ii = (i % a.nStokes) == 0 && (j % a.nStokes) == 0;
+                c.r[i + (size_t)j * ld] = ii ? rho * (a.mu[j] * a.wt[j]) : T(0);
+            }
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                jp[i] = (i == a.istart) ? att : T(0);
+                jm[i] = ((i % a.nStokes) == 0) ? a.mu0 * rho * att : T(0);
+            }
+            jps_sun = att;
+            __syncthreads();
+            interact<T, TM>(a.iface[a.Nz - 1], n, ld, c, J0p, J0m, jp, jm, v1, vec, part, piv, dmask,
+                            true, true);
+            // interaction_hdrf!: hdr_J₀⁻ = r⁻⁺ J₀⁺ + j₀⁻
+            cta_mv<T, false>(n, c.r, ld, J0p, dmask, part, [&](int i, T s) { hv[i] = s + jm[i]; });
+        } else {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) hv[i] = T(0);
+            __syncthreads();
+        }
+        // ---- postprocessing_vza! into per-moment partials
+        const size_t pbase = ((size_t)m * a.nS + p) * nOut;
+        for (int o = threadIdx.x; o < nOut; o += blockDim.x) {
+            const int iv = o % a.nVZA, s = o / a.nVZA;
+            const T w = a.vza_w[s + a.nStokes * (iv + (size_t)a.nVZA * m)];
+            const int row = a.vza_row[iv] + s;
+            a.part_R[pbase + o] = w * J0m[row];
+            a.part_T[pbase + o] = w * J0p[row];
+            a.part_H[pbase + o] = w * hv[row];
+        }
+        if (m == 0 && a.bhr_uw && threadIdx.x < a.nStokes) {
+            const int s = threadIdx.x;
+            T up = T(0), dw = T(0);
+            for (int j = s; j < n; j += a.nStokes) {
+                up += hv[j] * a.wt[j] * a.mu[j];
+                dw += J0p[j] * a.wt[j] * a.mu[j];
+            }
+            a.bhr_uw[s + (size_t)a.nStokes * p] = up;
+            a.bhr_dw[s + (size_t)a.nStokes * p] = dw + jps_sun * a.mu[a.istart];
+        }
+    }
+}
+
+// out[o + nOut*p] = sum_m part[(m*nS + p)*nOut + o]   (m ascending, as the Fourier loop)
+template <typename T>
+__global__ void k_reduce(int n_moments, size_t per_m, const T* __restrict__ pR,
+                         const T* __restrict__ pT, const T* __restrict__ pH, T* __restrict__ R,
+                         T* __restrict__ Tt, T* __restrict__ H) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= per_m) return;
+    T r = T(0), t = T(0), h = T(0);
+    for (int m = 0; m < n_moments; ++m) {
+        r += pR[(size_t)m * per_m + e];
+        t += pT[(size_t)m * per_m + e];
+        if (H) h += pH[(size_t)m * per_m + e];
+    }
+    R[e] = r;
+    Tt[e] = t;
+    if (H) H[e] = h;
+}
+
+}  // namespace vsm

@@ -1,0 +1,120 @@
+"""ctypes binding of libvsmom_b200.so (include/vsmom_b200.h).
+
+There is no CPU fallback: if the shared library is missing this module raises
+at import, and ``Context()`` raises if no CUDA device is present."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("VSMOM_B200_LIB", os.path.join(_HERE, "..", "lib", "libvsmom_b200.so"))
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"libvsmom_b200.so not found at {LIB_PATH}: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(nvcc, sm_100a).  The B200 path has no CPU fallback.")
+lib = C.CDLL(os.path.abspath(LIB_PATH))
+
+c_void_p, c_int, c_double, c_float = C.c_void_p, C.c_int, C.c_double, C.c_float
+i32p = C.POINTER(C.c_int32)
+f64p = C.POINTER(C.c_double)
+
+
+class LayerDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("N", C.c_int32), ("nStokes", C.c_int32), ("nSpec", C.c_int32),
+                ("m", C.c_int32), ("imu0", C.c_int32), ("ndoubl", C.c_int32), ("scatter", C.c_int32),
+                ("iface", C.c_int32), ("iz", C.c_int32), ("z_is_spectral", C.c_int32), ("reserved", C.c_int32),
+                ("mu0", c_double),
+                ("tau", c_void_p), ("varpi", c_void_p), ("Zpp", c_void_p), ("Zmp", c_void_p),
+                ("tau_sum", c_void_p), ("F0", c_void_p), ("mu", c_void_p), ("wt", c_void_p),
+                ("Rmp", c_void_p), ("Rpm", c_void_p), ("Tpp", c_void_p), ("Tmm", c_void_p),
+                ("J0p", c_void_p), ("J0m", c_void_p),
+                ("rmp", c_void_p), ("rpm", c_void_p), ("tpp", c_void_p), ("tmm", c_void_p),
+                ("j0p", c_void_p), ("j0m", c_void_p)]
+
+
+class ColumnDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("N", C.c_int32), ("nStokes", C.c_int32), ("nSpec", C.c_int32),
+                ("Nz", C.c_int32), ("nAer", C.c_int32), ("nVZA", C.c_int32), ("n_moments", C.c_int32),
+                ("imu0", C.c_int32), ("surface_kind", C.c_int32),
+                ("mu0", c_double), ("albedo", c_double), ("varpi_cabannes", c_double),
+                ("mu", f64p), ("wt", f64p), ("aer_omega", f64p), ("aer_ft", f64p), ("tau_aer", f64p),
+                ("vza_weight", f64p),
+                ("ndoubl", i32p), ("scatter", i32p), ("iface", i32p), ("rayl_allzero", i32p), ("vza_stream", i32p),
+                ("tau_rayl", c_void_p), ("tau_abs", c_void_p), ("F0", c_void_p), ("Zpp", c_void_p), ("Zmp", c_void_p)]
+
+
+EXPORTS = [
+    "vsm_version", "vsm_create", "vsm_destroy", "vsm_last_error", "vsm_synchronize",
+    "vsm_set_workspace_limit", "vsm_kernel_launches",
+    "vsm_batched_mul_f64", "vsm_batched_mul_f32", "vsm_batch_inv_f64", "vsm_batch_inv_f32",
+    "vsm_batch_solve_f64", "vsm_batch_solve_f32",
+    "vsm_rt_layer_f64", "vsm_rt_layer_f32", "vsm_rt_column_f64", "vsm_rt_column_f32",
+    "vsm_last_column_ms",
+]
+
+lib.vsm_version.restype = c_int
+lib.vsm_create.argtypes = [C.POINTER(c_void_p), c_int, c_void_p]
+lib.vsm_destroy.argtypes = [c_void_p]
+lib.vsm_last_error.argtypes = [c_void_p]
+lib.vsm_last_error.restype = C.c_char_p
+lib.vsm_synchronize.argtypes = [c_void_p]
+lib.vsm_set_workspace_limit.argtypes = [c_void_p, C.c_uint64]
+lib.vsm_kernel_launches.argtypes = [c_void_p]
+lib.vsm_kernel_launches.restype = C.c_uint64
+for _s in ("f64", "f32"):
+    getattr(lib, f"vsm_batched_mul_{_s}").argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int]
+    getattr(lib, f"vsm_batch_inv_{_s}").argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
+    getattr(lib, f"vsm_batch_solve_{_s}").argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]
+    getattr(lib, f"vsm_rt_layer_{_s}").argtypes = [c_void_p, C.POINTER(LayerDesc)]
+    getattr(lib, f"vsm_rt_column_{_s}").argtypes = [c_void_p, C.POINTER(ColumnDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+lib.vsm_last_column_ms.argtypes = [c_void_p, C.POINTER(c_float), C.POINTER(c_float), C.POINTER(c_float)]
+
+
+class VsmError(RuntimeError):
+    pass
+
+
+class Context:
+    """One ``vsm_ctx`` (device + stream).  Mirrors what ``vSmartMOMCUDAExt.__init__``
+    sets up (ext/vSmartMOMCUDAExt.jl:36-66): a functional-device check and the
+    synchronisation hook."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        h = c_void_p()
+        rc = lib.vsm_create(C.byref(h), int(device), c_void_p(stream) if stream else None)
+        if rc != 0:
+            raise VsmError(f"vsm_create failed ({rc}): {lib.vsm_last_error(None).decode()}")
+        self.handle = h
+        self.device = device
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise VsmError(f"libvsmom_b200 error {rc}: {lib.vsm_last_error(self.handle).decode()}")
+
+    def synchronize(self):
+        self.check(lib.vsm_synchronize(self.handle))
+
+    def set_workspace_limit(self, nbytes: int):
+        self.check(lib.vsm_set_workspace_limit(self.handle, int(nbytes)))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(lib.vsm_kernel_launches(self.handle))
+
+    def last_column_ms(self):
+        a, b, c = c_float(), c_float(), c_float()
+        self.check(lib.vsm_last_column_ms(self.handle, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib.vsm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

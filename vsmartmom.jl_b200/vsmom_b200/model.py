@@ -1,0 +1,403 @@
+"""Host-side model for the B200 CoreRT path: the arrays that the reference's
+``model_from_parameters`` hands to ``rt_run`` (src/CoreRT/tools/model_from_parameters.jl:211-524),
+built here with NumPy.  This is setup code that runs once per scene; the
+per-Fourier-moment / per-layer hot loop runs in the CUDA library.
+
+Names mirror the reference: ``QuadPoints`` (src/CoreRT/types.jl:872-891),
+``GreekCoefs``, ``rt_set_streams`` (src/CoreRT/tools/rt_set_streams.jl:25-47),
+``compute_Z_moments`` (src/Scattering/compute_Z_matrices.jl:26-110),
+``get_greek_rayleigh`` (src/Scattering/mie_helper_functions.jl:454-468).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+POL_N = {"Stokes_I": 1, "Stokes_IQ": 2, "Stokes_IQU": 3, "Stokes_IQUV": 4}
+
+
+def _cosd(x: float) -> float:
+    r = math.fmod(float(x), 360.0)
+    r = r + 360.0 if r < 0 else r
+    table = {0.0: 1.0, 60.0: 0.5, 90.0: 0.0, 120.0: -0.5, 180.0: -1.0, 240.0: -0.5, 270.0: 0.0, 300.0: 0.5}
+    return table[r] if r in table else math.cos(math.radians(r))
+
+
+def _sind(x: float) -> float:
+    r = math.fmod(float(x), 360.0)
+    r = r + 360.0 if r < 0 else r
+    table = {0.0: 0.0, 30.0: 0.5, 90.0: 1.0, 150.0: 0.5, 180.0: 0.0, 210.0: -0.5, 270.0: -1.0, 330.0: -0.5}
+    return table[r] if r in table else math.sin(math.radians(r))
+
+
+@dataclass
+class QuadPoints:
+    """src/CoreRT/types.jl:872-891 (``iμ₀`` is 1-based as in Julia)."""
+    mu0: float
+    imu0: int
+    imu0Nstart: int
+    qp_mu: np.ndarray
+    wt_mu: np.ndarray
+    qp_muN: np.ndarray
+    wt_muN: np.ndarray
+    Nquad: int
+    Nstreams: int
+
+
+def rt_set_streams(nstreams: int, sza: float, vza: Sequence[float], pol_n: int, FT=np.float64) -> QuadPoints:
+    """GaussLegQuad streams: ``nstreams`` weighted half-space nodes plus the
+    zero-weight VZA / SZA output nodes (rt_set_streams.jl:25-47,153-161)."""
+    x, w = np.polynomial.legendre.leggauss(nstreams)
+    nodes = [FT(0.5 * v + 0.5) for v in x]
+    weights = [FT(0.5 * v) for v in w]
+    mu0 = _cosd(sza)
+    seen, qp = set(), []
+    for v in nodes + [FT(_cosd(z)) for z in vza] + [FT(mu0)]:
+        if v not in seen:
+            seen.add(v)
+            qp.append(v)
+    qp_mu = np.asarray(qp, dtype=FT)
+    wt_mu = np.zeros(len(qp), FT)
+    wt_mu[:nstreams] = weights
+    imu0 = int(np.argmin(np.abs(qp_mu - FT(mu0)))) + 1
+    return QuadPoints(float(FT(mu0)), imu0, pol_n * (imu0 - 1) + 1, qp_mu, wt_mu,
+                      np.repeat(qp_mu, pol_n), np.repeat(wt_mu, pol_n), len(qp),
+                      int(np.count_nonzero(wt_mu)))
+
+
+@dataclass
+class GreekCoefs:
+    alpha: np.ndarray
+    beta: np.ndarray
+    gamma: np.ndarray
+    delta: np.ndarray
+    epsilon: np.ndarray
+    zeta: np.ndarray
+
+
+def get_greek_rayleigh(depol: float) -> GreekCoefs:
+    p = (1 - depol) / (1 + depol / 2)
+    r = (1 - 2 * depol) / (1 - depol)
+    z3 = np.zeros(3)
+    return GreekCoefs(np.array([0, 0, 3 * p]), np.array([1, 0, 0.5 * p]),
+                      np.array([0, 0, p * math.sqrt(1.5)]), np.array([0, 1.5 * p * r, 0]), z3.copy(), z3.copy())
+
+
+def _prt(mu: np.ndarray, lmax: int, m: int):
+    """Normalised generalised spherical functions P_l^m, R_l^m, T_l^m for one
+    Fourier order ``m`` and l = 0..lmax-1, vectorised over mu
+    (recurrences of src/Scattering/legendre_functions.jl:24-185; returns the
+    "true" T, i.e. minus the array that routine fills)."""
+    n = mu.size
+    P = np.zeros((lmax, n)); R = np.zeros((lmax, n)); Tn = np.zeros((lmax, n))
+    c = mu
+    s = np.sqrt(1.0 - c * c)
+    sq = math.sqrt
+    for l in range(m, lmax):
+        if m == 0:
+            if l == 0:
+                P[l] = 1.0
+            elif l == 1:
+                P[l] = c
+            elif l == 2:
+                P[l] = 0.5 * (3.0 * c * c - 1.0)
+                R[l] = 0.5 * sq(1.5) * s * s
+            else:
+                P[l] = (P[l - 1] * (2 * l - 1) * c - P[l - 2] * (l - 1)) / l
+                R[l] = (R[l - 1] * (2 * l - 1) * c - R[l - 2] * sq((l + 1) * (l - 3))) / sq(l * l - 4)
+        elif m == 1 and l == 1:
+            P[l] = sq(0.5) * s
+        elif m == 1 and l == 2:
+            m1 = sq(1 / 6)
+            P[l] = m1 * 3 * c * s
+            R[l] = -m1 * c * sq(1.5) * s
+            Tn[l] = m1 * sq(1.5) * s
+        elif l == m:            # m >= 2 seed
+            f1 = np.ones(n); f2 = np.ones(n)
+            half = s / 2
+            for k in range(1, m + 1):
+                f1 = f1 * ((2 * k - 1) * s) / sq(k * (k + m))
+                f2 = f2 * half * (sq((m + k) / (k - 2)) if k > 2 else 1.0)
+            big = s > 1e-8
+            s2 = np.where(big, s * s, 1.0)
+            aii = np.where(big, f2 * (1.0 + c * c) / s2, 0.5 if m == 2 else 0.0)
+            aij = np.where(big, f2 * (2 * c) / s2, 0.5 if m == 2 else 0.0)
+            P[l] = f1
+            R[l] = aii
+            Tn[l] = -aij
+        else:
+            if m == 1:
+                m1 = sq((l - 1) / (l + 1))
+                m2 = m1 * sq((l - 2) / l)
+            elif l == m + 1:
+                m1 = sq(1 / (l + m))
+                m2 = 0.0
+            else:
+                m1 = sq((l - m) / (l + m))
+                m2 = m1 * sq((l - m - 1) / (l + m - 1))
+            Pm2 = P[l - 2] if l - 2 >= 0 else 0.0
+            Rm2 = R[l - 2] if l - 2 >= 0 else 0.0
+            Tm2 = Tn[l - 2] if l - 2 >= 0 else 0.0
+            P[l] = (m1 * P[l - 1] * (2 * l - 1) * c - m2 * Pm2 * (l - 1 + m)) / (l - m)
+            Z = (2 * m * (2 * l - 1)) / (l * (l - 1))
+            Y = ((l + m - 1) / (l - 1)) * sq((l - 3) * (l + 1)) if (l - 3) * (l + 1) >= 0 else 0.0
+            X = ((l - m) / l) * sq(l * l - 4)
+            R[l] = (m1 * R[l - 1] * (2 * l - 1) * c - m2 * Rm2 * Y + m1 * Tn[l - 1] * Z) / X
+            Tn[l] = (m1 * Tn[l - 1] * (2 * l - 1) * c - m2 * Tm2 * Y + m1 * R[l - 1] * Z) / X
+    return P, R, -Tn
+
+
+def compute_Z_moments(pol_n: int, mu: np.ndarray, greek: GreekCoefs, m: int):
+    """Fourier moment ``m`` (0-based) of the phase matrix on the stream cosines:
+    returns ``(Z⁺⁺, Z⁻⁺)`` of shape (N, N), N = len(mu)*pol_n, float64
+    (compute_Z_matrices.jl:26-110)."""
+    mu = np.asarray(mu, dtype=np.float64)
+    nmu = mu.size
+    lmax = len(greek.beta)
+    fact = 0.5 if m == 0 else 1.0
+    Pp, Rp, Tp = _prt(mu, lmax, m)
+    Pn, Rn, Tn = _prt(-mu, lmax, m)
+
+    def pi_mats(P, R, T):
+        Pi = np.zeros((lmax, nmu, pol_n, pol_n))
+        Pi[:, :, 0, 0] = P
+        if pol_n >= 2:
+            Pi[:, :, 1, 1] = R
+        if pol_n >= 3:
+            Pi[:, :, 1, 2] = -T
+            Pi[:, :, 2, 1] = -T
+            Pi[:, :, 2, 2] = R
+        if pol_n == 4:
+            Pi[:, :, 3, 3] = P
+        return Pi
+
+    B = np.zeros((lmax, 4, 4))
+    B[:, 0, 0] = greek.beta; B[:, 0, 1] = greek.gamma; B[:, 1, 0] = greek.gamma
+    B[:, 1, 1] = greek.alpha; B[:, 2, 2] = greek.zeta; B[:, 2, 3] = greek.epsilon
+    B[:, 3, 2] = -np.asarray(greek.epsilon); B[:, 3, 3] = greek.delta
+    B = B[:, :pol_n, :pol_n]
+    Pi_p = pi_mats(Pp, Rp, Tp)[m:]
+    Pi_n = pi_mats(Pn, Rn, Tn)[m:]
+    left = np.einsum('liab,lbc->liac', Pi_p, B[m:])
+    App = np.einsum('liac,ljcd->iajd', left, Pi_p)
+    Amp = np.einsum('liac,ljcd->iajd', left, Pi_n)
+    N = nmu * pol_n
+    sgn = np.ones((pol_n, pol_n))
+    for i in range(pol_n):
+        for j in range(pol_n):
+            if (i <= 1 and j >= 2) or (i >= 2 and j <= 1):
+                sgn[i, j] = -1.0
+    Zpp = (2 * fact * App).reshape(N, N)
+    Zmp = (2 * fact * Amp * sgn[None, :, None, :]).reshape(N, N)
+    return Zpp, Zmp
+
+
+@dataclass
+class AerosolOptics:
+    """Scattering.AerosolOptics: Greek coefficients, ω̃, truncation factor fᵗ."""
+    greek_coefs: GreekCoefs
+    omega: float
+    ft: float = 0.0
+
+
+@dataclass
+class RTNumericalParameters:
+    """src/CoreRT/types.jl:713-756"""
+    dtau_max_threshold: float = 1e-3
+    dtau_min_floor: Optional[float] = None
+
+
+@dataclass
+class RTModel:
+    """The slice of the reference's ``RTModel`` that the noRS hot path reads."""
+    polarization_type: str
+    quad_points: QuadPoints
+    sza: float
+    vza: Sequence[float]
+    vaz: Sequence[float]
+    tau_rayl: np.ndarray            # (nSpec, Nz)   model.τ_rayl[iB]
+    tau_abs: np.ndarray             # (nSpec, Nz)   model.τ_abs[iB]
+    tau_aer: np.ndarray             # (nAer, Nz)    model.τ_aer[iB]
+    aerosol_optics: List[AerosolOptics]
+    greek_rayleigh: GreekCoefs
+    albedo: float                   # LambertianSurfaceScalar
+    m_max: int
+    varpi_cabannes: float = 1.0
+    numerics: RTNumericalParameters = field(default_factory=RTNumericalParameters)
+    float_type: type = np.float64
+    spec_grid: Optional[np.ndarray] = None
+
+    @property
+    def pol_n(self) -> int:
+        return POL_N[self.polarization_type]
+
+    @property
+    def nSpec(self) -> int:
+        return self.tau_abs.shape[0]
+
+    @property
+    def Nz(self) -> int:
+        return self.tau_abs.shape[1]
+
+
+def derive_m_max(aerosols: Sequence[AerosolOptics], nstreams: int) -> int:
+    """Rayleigh (2), aerosol (len(β)-1), Lambertian surface (0), clamped to the
+    stream cap 2·nstreams-1 (src/CoreRT/component_m_max.jl:51-117)."""
+    m = 2
+    for a in aerosols:
+        m = max(m, len(a.greek_coefs.beta) - 1)
+    return max(min(m, 2 * nstreams - 1), 0)
+
+
+# ---------------------------------------------------------------------------
+# control flow that the reference derives from FULL-band reductions
+# ---------------------------------------------------------------------------
+def doubling_number(dtau_max, tau_end, FT):
+    """src/CoreRT/tools/rt_helper_functions.jl:49-69 -> ndoubl"""
+    dtau_max = FT(dtau_max); tau_end = FT(tau_end)
+    if tau_end <= dtau_max:
+        return 0
+    q1 = np.log10(FT(2)); q2 = np.log10(dtau_max); q3 = np.log10(tau_end)
+    tlimit = FT((q3 - q2) / q1)
+    nlimit = int(np.floor(tlimit))
+    if FT(tlimit - FT(nlimit)) < np.finfo(FT).eps:
+        return nlimit
+    return nlimit + 1
+
+
+@dataclass
+class LayerControl:
+    ndoubl: np.ndarray
+    scatter: np.ndarray
+    iface: np.ndarray
+    rayl_allzero: np.ndarray
+
+
+def layer_control(model: RTModel) -> LayerControl:
+    """ndoubl / scatter / ScatteringInterface per layer from maximum(τ.*ϖ) over the
+    whole band (rt_kernel.jl:197,266-287; compEffectiveLayerProperties.jl:75-93;
+    rt_helper_functions.jl:15-33).  Must be evaluated on the full band before the
+    spectral axis is sharded across GPUs."""
+    FT = model.float_type
+    eps = np.finfo(FT).eps
+    q = model.quad_points
+    thr = FT(model.numerics.dtau_max_threshold)
+    flo = FT(1024 * eps if model.numerics.dtau_min_floor is None else model.numerics.dtau_min_floor)
+    real = q.qp_mu[q.wt_mu > eps]
+    mu_min = FT(real.min() if real.size else q.qp_mu.min())
+    Nz = model.Nz
+    nd = np.zeros(Nz, np.int32); sc = np.zeros(Nz, np.int32)
+    itf = np.zeros(Nz, np.int32); rz = np.zeros(Nz, np.int32)
+    prev = 0
+    for iz in range(Nz):
+        tau = model.tau_rayl[:, iz].astype(FT)
+        varpi = np.full_like(tau, FT(model.varpi_cabannes))
+        rz[iz] = int(np.all(tau * varpi == 0))
+        for ia, a in enumerate(model.aerosol_optics):
+            ft, om = FT(a.ft), FT(a.omega)
+            ty = FT((FT(1) - ft * om) * FT(model.tau_aer[ia, iz]))
+            py = FT((FT(1) - ft) * om / (FT(1) - ft * om))
+            w = tau * varpi + ty * py
+            tau = tau + ty
+            varpi = w / np.where(tau > 0, tau, FT(1))
+        wx = tau * varpi
+        tau = tau + model.tau_abs[:, iz].astype(FT)
+        varpi = wx / np.where(tau > 0, tau, FT(1))
+        mx = FT(np.max(tau * varpi))
+        s = bool(mx > 2 * eps)
+        if iz == 0:
+            prev = 3 if s else 0
+        elif prev == 0:
+            prev = 1 if s else 0
+        else:
+            prev = 3 if s else 2
+        sc[iz] = int(s); itf[iz] = prev
+        if s:
+            dtau_max = max(flo, min(mx, FT(thr * mu_min)))
+            nd[iz] = doubling_number(dtau_max, mx, FT)
+    return LayerControl(nd, sc, itf, rz)
+
+
+def vza_tables(model: RTModel):
+    """``_precompute_vza_weights`` (postprocessing_vza.jl:23-37) for every moment:
+    returns (vza_stream [nVZA] 1-based, weights (n_moments, nVZA, pol_n))."""
+    FT = model.float_type
+    q = model.quad_points
+    n = model.pol_n
+    nV = len(model.vza)
+    stream = np.array([int(np.argmin(np.abs(q.qp_mu - FT(_cosd(v))))) + 1 for v in model.vza], np.int32)
+    w = np.zeros((model.m_max + 1, nV, n))
+    for m in range(model.m_max + 1):
+        weight = float(FT(0.5 / math.pi)) if m == 0 else float(FT(1.0 / math.pi))
+        for i in range(nV):
+            c, s = _cosd(m * model.vaz[i]), _sind(m * model.vaz[i])
+            w[m, i, :] = [weight * v for v in (c, c, s, s)[:n]]
+    return stream, w
+
+
+# ---------------------------------------------------------------------------
+# synthetic O2-A-band scene: no HITRAN / Mie needed
+# ---------------------------------------------------------------------------
+DEFAULT_P_HALF = np.array([
+    0.14, 0.22, 0.30, 0.39, 0.53, 0.71, 0.96, 1.28, 1.70, 2.27, 3.03, 4.03, 5.44, 7.26, 9.67,
+    12.90, 17.23, 23.30, 31.00, 42.07, 56.09, 74.78, 99.69, 131.00, 176.85, 236.64, 314.58,
+    418.87, 557.76, 735.00, 800.12, 849.00, 912.00, 980.00, 1005.0])   # DefaultParameters.yaml:87-92
+DEFAULT_VZA = [60, 45, 30, 15, 0, 15, 30, 45, 60]                      # DefaultParameters.yaml:67-69
+DEFAULT_VAZ = [180, 180, 180, 180, 0, 0, 0, 0, 0]
+
+
+def bodhaine_tau_rayleigh(wl_um: np.ndarray, psurf_hpa: float) -> np.ndarray:
+    """Bodhaine (1999) Eq. 30 column Rayleigh optical depth (atmo_prof.jl:251-256)."""
+    l2 = wl_um ** 2
+    t = 0.002152 * (1.0455996 - 341.29061 / l2 - 0.90230850 * l2) / (1 + 0.0027059889 / l2 - 85.968563 * l2)
+    return t * (psurf_hpa / 1013.25)
+
+
+def hg_greek(g: float, nterms: int) -> GreekCoefs:
+    """Henyey-Greenstein-like Greek set: β_l=(2l+1)g^l; α, ζ, δ follow β for
+    l>=2 (δ from l>=0); γ = ε = 0."""
+    l = np.arange(nterms)
+    beta = (2 * l + 1) * g ** l
+    a = np.where(l >= 2, beta, 0.0)
+    return GreekCoefs(a, beta, np.zeros(nterms), beta.copy(), np.zeros(nterms), a.copy())
+
+
+def synthetic_o2a_model(nSpec: int = 10000, nstreams: int = 10, polarization_type: str = "Stokes_IQU",
+                        aerosol: bool = True, float_type=np.float64, sza: float = 60.0,
+                        vza=DEFAULT_VZA, vaz=DEFAULT_VAZ, albedo: float = 0.15,
+                        p_half: np.ndarray = DEFAULT_P_HALF, depol: float = 0.0279,
+                        seed: int = 20251017) -> RTModel:
+    FT = float_type
+    pol_n = POL_N[polarization_type]
+    q = rt_set_streams(nstreams, sza, vza, pol_n, FT)
+    nu = 12870.01 + 0.015 * np.arange(nSpec)
+    wl = 1e4 / nu
+    dp = np.diff(p_half)
+    pbar = 0.5 * (p_half[1:] + p_half[:-1])
+    tau_R = bodhaine_tau_rayleigh(wl, p_half[-1])
+    tau_rayl = tau_R[:, None] * (dp / dp.sum())[None, :]
+    rng = np.random.default_rng(seed)
+    nlines = 60
+    nu_l = rng.uniform(12900.0, 13180.0, nlines)
+    a_l = 10.0 ** rng.uniform(-3.0, 1.0, nlines)
+    wz = dp * pbar
+    wz = wz / wz.sum()
+    tau_abs = np.zeros((nSpec, len(dp)))
+    for iz in range(len(dp)):
+        gam = 0.05 * pbar[iz] / 1013.0 + 0.002
+        lor = (gam / math.pi) / ((nu[:, None] - nu_l[None, :]) ** 2 + gam * gam)
+        tau_abs[:, iz] = wz[iz] * (lor * a_l[None, :]).sum(axis=1)
+    col = tau_abs.sum(axis=1)
+    tau_abs *= 100.0 / max(col.max(), 1e-300)
+    tau_abs += 1e-4 * wz[None, :]
+    aerosols, tau_aer = [], np.zeros((0, len(dp)))
+    if aerosol:
+        aerosols = [AerosolOptics(hg_greek(0.7, 2 * nstreams), 0.95, 0.0)]
+        prof = np.exp(-0.5 * ((pbar - 900.0) / 50.0) ** 2) * dp
+        tau_aer = (0.3 * prof / prof.sum())[None, :]
+    return RTModel(polarization_type, q, sza, list(vza), list(vaz), tau_rayl.astype(FT), tau_abs.astype(FT),
+                   tau_aer, aerosols, get_greek_rayleigh(depol), albedo, derive_m_max(aerosols, nstreams),
+                   1.0, RTNumericalParameters(), FT, nu)

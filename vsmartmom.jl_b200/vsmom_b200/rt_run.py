@@ -1,0 +1,148 @@
+"""``rt_run`` for the B200 path -- host-side mirror of
+``rt_run(::noRS, model, iBand)`` (src/CoreRT/rt_run.jl:238-539): same inputs,
+same outputs ``(R_SFI, T_SFI, hdr, bhr_uw, bhr_dw)``; the Fourier/layer loop runs
+in ``vsm_rt_column_*`` on the GPU.  PyTorch is used only for device memory and
+streams."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .model import RTModel, compute_Z_moments, layer_control, vza_tables
+
+
+def _tdtype(FT):
+    return torch.float64 if FT == np.float64 else torch.float32
+
+
+@dataclass
+class PreparedColumn:
+    """Scene-constant inputs (everything except the spectral arrays): the Z-moment
+    tables, quadrature and full-band control flow.  Built once per model."""
+    model: RTModel
+    Zpp: torch.Tensor
+    Zmp: torch.Tensor
+    ctl: object
+    vza_stream: np.ndarray
+    vza_weight: np.ndarray
+
+
+def z_tables(model: RTModel) -> tuple[np.ndarray, np.ndarray]:
+    """(N,N,1+nAer,n_moments) column-major Z⁺⁺ / Z⁻⁺ tables in the model's FT."""
+    mu = model.quad_points.qp_mu.astype(np.float64)
+    comps = [model.greek_rayleigh] + [a.greek_coefs for a in model.aerosol_optics]
+    N = model.quad_points.qp_muN.size
+    nM = model.m_max + 1
+    Zpp = np.zeros((nM, len(comps), N, N), model.float_type)
+    Zmp = np.zeros_like(Zpp)
+    for m in range(nM):
+        for c, g in enumerate(comps):
+            zp, zm = compute_Z_moments(model.pol_n, mu, g, m)
+            # memory order (m, c, j, i) == Julia (i, j, c, m)
+            Zpp[m, c] = zp.T
+            Zmp[m, c] = zm.T
+    return Zpp, Zmp
+
+
+def prepare(model: RTModel, device: torch.device | str = "cuda:0") -> PreparedColumn:
+    Zpp, Zmp = z_tables(model)
+    stream, w = vza_tables(model)
+    return PreparedColumn(model, torch.from_numpy(Zpp).to(device), torch.from_numpy(Zmp).to(device),
+                          layer_control(model), stream, np.ascontiguousarray(w, dtype=np.float64))
+
+
+def _f64p(a: np.ndarray):
+    return a.ctypes.data_as(_lib.f64p)
+
+
+def _i32p(a: np.ndarray):
+    return a.ctypes.data_as(_lib.i32p)
+
+
+def rt_column_device(ctx: _lib.Context, prep: PreparedColumn, tau_rayl: torch.Tensor, tau_abs: torch.Tensor,
+                     F0: torch.Tensor, want_hdr: bool = True):
+    """Device-resident entry: ``tau_rayl``/``tau_abs`` are (Nz, nS) torch CUDA tensors
+    (memory order == Julia (nSpec, Nz)); ``F0`` is (nS, pol_n).  Returns device
+    tensors R_SFI, T_SFI, hdr of shape (nS, pol_n, nVZA) (memory order == Julia
+    (nVZA, pol_n, nSpec)) and bhr_uw, bhr_dw of shape (nS, pol_n)."""
+    model = prep.model
+    FT = model.float_type
+    dt = _tdtype(FT)
+    q = model.quad_points
+    Nz, nS = tau_rayl.shape
+    assert tau_abs.shape == (Nz, nS) and tau_rayl.dtype == dt and tau_rayl.is_contiguous() and tau_abs.is_contiguous()
+    dev = tau_rayl.device
+    nV, n = len(model.vza), model.pol_n
+    R = torch.empty((nS, n, nV), dtype=dt, device=dev)
+    T = torch.empty_like(R)
+    H = torch.empty_like(R) if want_hdr else None
+    uw = torch.empty((nS, n), dtype=dt, device=dev) if want_hdr else None
+    dw = torch.empty((nS, n), dtype=dt, device=dev) if want_hdr else None
+    mu = np.ascontiguousarray(q.qp_muN, dtype=np.float64)
+    wt = np.ascontiguousarray(q.wt_muN, dtype=np.float64)
+    nAer = len(model.aerosol_optics)
+    om = np.array([a.omega for a in model.aerosol_optics] or [0.0], np.float64)
+    ft = np.array([a.ft for a in model.aerosol_optics] or [0.0], np.float64)
+    taer = np.ascontiguousarray(model.tau_aer.T if nAer else np.zeros((1, 1)), dtype=np.float64)  # (Nz, nAer) mem == Julia (nAer,Nz)
+    ctl = prep.ctl
+    nd = np.ascontiguousarray(ctl.ndoubl, np.int32); sc = np.ascontiguousarray(ctl.scatter, np.int32)
+    itf = np.ascontiguousarray(ctl.iface, np.int32); rz = np.ascontiguousarray(ctl.rayl_allzero, np.int32)
+    vs = np.ascontiguousarray(prep.vza_stream, np.int32)
+    d = _lib.ColumnDesc()
+    d.struct_size = C.sizeof(_lib.ColumnDesc)
+    d.N, d.nStokes, d.nSpec, d.Nz, d.nAer, d.nVZA = q.qp_muN.size, n, nS, Nz, nAer, nV
+    d.n_moments, d.imu0, d.surface_kind = model.m_max + 1, q.imu0, 0
+    d.mu0, d.albedo, d.varpi_cabannes = float(q.mu0), float(model.albedo), float(model.varpi_cabannes)
+    d.mu, d.wt, d.aer_omega, d.aer_ft, d.tau_aer = _f64p(mu), _f64p(wt), _f64p(om), _f64p(ft), _f64p(taer)
+    d.vza_weight = _f64p(prep.vza_weight)
+    d.ndoubl, d.scatter, d.iface, d.rayl_allzero, d.vza_stream = _i32p(nd), _i32p(sc), _i32p(itf), _i32p(rz), _i32p(vs)
+    d.tau_rayl, d.tau_abs, d.F0 = tau_rayl.data_ptr(), tau_abs.data_ptr(), F0.data_ptr()
+    d.Zpp, d.Zmp = prep.Zpp.data_ptr(), prep.Zmp.data_ptr()
+    fn = _lib.lib.vsm_rt_column_f64 if FT == np.float64 else _lib.lib.vsm_rt_column_f32
+    ctx.check(fn(ctx.handle, C.byref(d), R.data_ptr(), T.data_ptr(),
+                 H.data_ptr() if want_hdr else None, uw.data_ptr() if want_hdr else None,
+                 dw.data_ptr() if want_hdr else None))
+    return R, T, H, uw, dw
+
+
+def rt_run(model: RTModel, ctx: Optional[_lib.Context] = None, prep: Optional[PreparedColumn] = None,
+           device: str = "cuda:0", sel: slice = slice(None), F0: Optional[np.ndarray] = None):
+    """Host-buffer entry, the call a user makes: NumPy in, NumPy out, like the
+    reference's ``rt_run(model)``.  Returns a dict with ``R_SFI``, ``T_SFI``,
+    ``hdr`` of shape (nVZA, pol_n, nSpec) and ``bhr_uw``, ``bhr_dw`` (nSpec,).
+    ``sel`` restricts the spectral axis (a shard); control flow always comes from
+    the full band."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("vsmom_b200.rt_run needs a CUDA device (B200); there is no CPU fallback")
+    own = ctx is None
+    if own:
+        ctx = _lib.Context(torch.device(device).index or 0)
+    if prep is None:
+        prep = prepare(model, device)
+    FT = model.float_type
+    dt = _tdtype(FT)
+    tr = np.ascontiguousarray(model.tau_rayl[sel].T)      # (Nz, nS)
+    ta = np.ascontiguousarray(model.tau_abs[sel].T)
+    nS = tr.shape[1]
+    if F0 is None:
+        f0 = np.zeros((nS, model.pol_n), FT)
+        f0[:, 0] = 1
+    else:
+        f0 = np.ascontiguousarray(F0[:, sel].T.astype(FT))
+    with torch.cuda.device(device):
+        d_tr = torch.from_numpy(tr).pin_memory().to(device, non_blocking=True)
+        d_ta = torch.from_numpy(ta).pin_memory().to(device, non_blocking=True)
+        d_f0 = torch.from_numpy(f0).to(device)
+        R, T, H, uw, dw = rt_column_device(ctx, prep, d_tr, d_ta, d_f0)
+        ctx.synchronize()
+        out = dict(R_SFI=R.cpu().numpy().transpose(2, 1, 0), T_SFI=T.cpu().numpy().transpose(2, 1, 0),
+                   hdr=H.cpu().numpy().transpose(2, 1, 0), bhr_uw=uw.cpu().numpy()[:, 0].copy(),
+                   bhr_dw=dw.cpu().numpy()[:, 0].copy())
+    if own:
+        ctx.close()
+    return out
