@@ -56,6 +56,9 @@ int  vsm_synchronize(vsm_ctx* ctx);             /* Architectures._sync_gpu[] (ex
 int  vsm_set_workspace_limit(vsm_ctx* ctx, uint64_t bytes);
 /* number of kernels this context has launched since creation (bench bookkeeping) */
 uint64_t vsm_kernel_launches(vsm_ctx* ctx);
+/* roofline denominator: measured register-resident FMA throughput (TFLOP/s) of this
+ * device; kind 0 = fp64 FMA, 1 = fp32 FMA.  Blocks until done (~50 ms).            */
+int  vsm_measure_fma_peak(vsm_ctx* ctx, int kind, double* tflops);
 
 /* -- L0: batched dense algebra -- same semantics as ext/gpu_batched_cuda.jl ----
  * batched_mul  (gpu_batched_cuda.jl:208-218):  C[:,:,k] = A[:,:,k] * B[:,:,k]
@@ -161,6 +164,8 @@ int vsm_rt_column_f32(vsm_ctx*, const vsm_column_desc*, float* R_SFI, float* T_S
 /* device time (ms) of the most recent vsm_rt_column_* call, measured with CUDA
  * events on the context's stream; blocks until that call has finished.        */
 int vsm_last_column_ms(vsm_ctx*, float* total_ms, float* doubling_ms, float* adding_ms);
+/* number of k_layer (elemental+doubling) and k_adding launches of that call */
+int vsm_last_column_launches(vsm_ctx*, int* layer_launches, int* adding_launches);
 
 #ifdef __cplusplus
 }

@@ -413,13 +413,16 @@ class CoreProps:
     Zmp: np.ndarray
 
 
-def _add_scatt(x: CoreProps, y: CoreProps) -> CoreProps:
-    """Base.:+ of two CoreScatteringOpticalProperties, types.jl:1262-1293."""
+def _add_scatt(x: CoreProps, y: CoreProps, with_Z: bool = True) -> CoreProps:
+    """Base.:+ of two CoreScatteringOpticalProperties, types.jl:1262-1293.
+    ``with_Z=False`` skips the Z mixing (only τ, ϖ are needed for control flow)."""
     tau = x.tau + y.tau
     wx = x.tau * x.varpi
     wy = y.tau * y.varpi
     w = wx + wy
     varpi = w / np.where(tau > 0, tau, np.ones_like(tau))
+    if not with_Z:
+        return CoreProps(tau, varpi, x.Zpp, x.Zmp)
     if np.all(wx == 0.0):
         return CoreProps(tau, varpi, y.Zpp, y.Zmp)
     if np.all(wy == 0.0):
@@ -442,14 +445,19 @@ def _add_abs(x: CoreProps, tau_abs: np.ndarray) -> CoreProps:
     return CoreProps(tau, varpi, x.Zpp, x.Zmp)
 
 
-def construct_core_optical_properties(model: Model, m: int, sel=slice(None)):
+def z_tables(model: Model, m: int):
+    """Z-moment matrices of Rayleigh and every aerosol for Fourier moment m."""
+    mu = model.quad.qp_mu
+    return (compute_Z_moments(model.pol_n, mu, model.greek_rayleigh, m, model.FT),
+            [compute_Z_moments(model.pol_n, mu, a.greek, m, model.FT) for a in model.aerosols])
+
+
+def construct_core_optical_properties(model: Model, m: int, sel=slice(None), ztab=None, with_Z: bool = True):
     """constructCoreOpticalProperties, single band.  ``sel`` restricts the
     spectral axis (control-flow scalars must come from the full band; see
     band_control)."""
     FT = model.FT
-    mu = model.quad.qp_mu
-    Zpp_r, Zmp_r = compute_Z_moments(model.pol_n, mu, model.greek_rayleigh, m, FT)
-    aerZ = [compute_Z_moments(model.pol_n, mu, a.greek, m, FT) for a in model.aerosols]
+    (Zpp_r, Zmp_r), aerZ = ztab if ztab is not None else z_tables(model, m)
     out = []
     for iz in range(model.Nz):
         combo = CoreProps(model.tau_rayl[sel, iz].astype(FT),
@@ -458,7 +466,7 @@ def construct_core_optical_properties(model: Model, m: int, sel=slice(None)):
             # createAero, compEffectiveLayerProperties.jl:67-72
             tau_mod = FT((1 - a.ft * a.omega) * model.tau_aer[ia, iz])
             varpi_mod = FT((1 - a.ft) * a.omega / (1 - a.ft * a.omega))
-            combo = _add_scatt(combo, CoreProps(tau_mod, varpi_mod, *aerZ[ia]))
+            combo = _add_scatt(combo, CoreProps(tau_mod, varpi_mod, *aerZ[ia]), with_Z)
         combo = _add_abs(combo, model.tau_abs[sel, iz].astype(FT))
         out.append(combo)
     return out
@@ -483,9 +491,9 @@ def get_scattering_interface(prev: int, scatter: bool, iz: int) -> int:
     return 3 if scatter else 2
 
 
-def band_control(model: Model, m: int) -> BandControl:
+def band_control(model: Model, m: int, ztab=None) -> BandControl:
     FT = model.FT
-    props = construct_core_optical_properties(model, m)
+    props = construct_core_optical_properties(model, m, ztab=ztab, with_Z=False)
     eps = np.finfo(FT).eps
     scat, nds, itf = [], [], []
     tau_sum = np.zeros((model.nSpec, model.Nz + 1), FT)
@@ -748,7 +756,20 @@ def rt_kernel_layer(model: Model, m: int, iz: int, ctl: BandControl, props: Core
     return interaction(ctl.interface[iz], C, r, r_pm, t, t_mm, j0p, j0m)
 
 
-def rt_run(model: Model, sel=slice(None), return_streams: bool = False):
+@dataclass
+class Prepared:
+    """m-independent control flow + per-m Z tables, shareable between the
+    spectral chunks of one band (used by the threaded CPU baseline)."""
+    ctl: BandControl
+    ztabs: list
+
+
+def prepare(model: Model) -> Prepared:
+    ztabs = [z_tables(model, m) for m in range(model.m_max + 1)]
+    return Prepared(band_control(model, 0, ztabs[0]), ztabs)
+
+
+def rt_run(model: Model, sel=slice(None), return_streams: bool = False, prep: Optional[Prepared] = None):
     """rt_run(::noRS, model, iBand) for one band, SFI = true.  ``sel`` picks a
     subset of spectral points; control flow (ndoubl, scatter, interface) is
     always derived from the full band."""
@@ -772,8 +793,12 @@ def rt_run(model: Model, sel=slice(None), return_streams: bool = False):
     streams = []
     for m in range(model.m_max + 1):
         weight = FT(0.5 / math.pi) if m == 0 else FT(1.0 / math.pi)
-        ctl = band_control(model, m)
-        props = construct_core_optical_properties(model, m, idx)
+        if prep is not None:
+            ctl = prep.ctl
+            props = construct_core_optical_properties(model, m, idx, prep.ztabs[m])
+        else:
+            ctl = band_control(model, m)
+            props = construct_core_optical_properties(model, m, idx)
         C = None
         for iz in range(model.Nz):
             C = rt_kernel_layer(model, m, iz, ctl, props[iz], C, F0,
@@ -808,3 +833,58 @@ def rt_run(model: Model, sel=slice(None), return_streams: bool = False):
     if return_streams:
         out['streams'] = streams
     return out
+
+
+def rt_run_threaded(model: Model, idx: np.ndarray, threads: int, chunk: int = 8,
+                    prep: Optional[Prepared] = None):
+    """CPU baseline driver: the reference threads its per-slice BLAS/LAPACK calls
+    over the spectral axis (cpu_batched.jl:26,33,78); here the selected spectral
+    points are split into chunks processed by a thread pool (NumPy releases the
+    GIL inside matmul / LAPACK; BLAS itself is pinned to one thread by the caller).
+    Returns R_SFI, T_SFI for the selected points."""
+    from concurrent.futures import ThreadPoolExecutor
+    if prep is None:
+        prep = prepare(model)
+    idx = np.asarray(idx)
+    parts = [idx[i:i + chunk] for i in range(0, idx.size, chunk)]
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        outs = list(ex.map(lambda sl: rt_run(model, sl, prep=prep), parts))
+    return (np.concatenate([o["R_SFI"] for o in outs], axis=2),
+            np.concatenate([o["T_SFI"] for o in outs], axis=2))
+
+
+_MP_STATE = {}
+
+
+def _mp_worker(part):
+    try:
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=1):
+            o = rt_run(_MP_STATE["model"], part, prep=_MP_STATE["prep"])
+    except ImportError:
+        o = rt_run(_MP_STATE["model"], part, prep=_MP_STATE["prep"])
+    return o["R_SFI"], o["T_SFI"]
+
+
+class ProcessPoolBaseline:
+    """CPU baseline over all host cores: one forked worker per core, each running
+    the oracle on chunks of the spectral axis with BLAS pinned to one thread -- the
+    reference's own CPU layout (Threads.@threads over nSpec with single-threaded
+    per-slice gemm / getrf, cpu_batched.jl:26-37,65-82)."""
+
+    def __init__(self, model: Model, workers: int, prep: Optional[Prepared] = None):
+        import multiprocessing as mp
+        _MP_STATE["model"] = model
+        _MP_STATE["prep"] = prep if prep is not None else prepare(model)
+        self.workers = workers
+        self.pool = mp.get_context("fork").Pool(workers)
+
+    def run(self, idx: np.ndarray, chunk: int = 8):
+        idx = np.asarray(idx)
+        parts = [idx[i:i + chunk] for i in range(0, idx.size, chunk)]
+        outs = self.pool.map(_mp_worker, parts, chunksize=1)
+        return (np.concatenate([o[0] for o in outs], axis=2), np.concatenate([o[1] for o in outs], axis=2))
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()

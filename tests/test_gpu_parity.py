@@ -1,0 +1,247 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on the
+same seeded inputs, against the reference's golden tables, and -- at BASELINE.json's
+full size -- through size-independent properties.
+
+Tolerances: fp64 GPU vs fp64 oracle  max|Δ|/max|ref| <= 1e-9;
+fp32 GPU vs fp64 oracle <= 1e-2 max-rel on I (test/test_float32.jl:64), target 1e-3."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import vsmom_b200 as vb
+import vsmom_oracle as orc
+from helpers import golden, rayleigh_slab_model, relerr, to_oracle
+from test_oracle_golden import siewert_compare, siewert_model
+
+pytestmark = pytest.mark.gpu
+F64_TOL = 1e-9
+KEYS = ("R_SFI", "T_SFI", "hdr", "bhr_uw", "bhr_dw")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from vsmom_b200 import _lib
+    c = _lib.Context(0)
+    yield c
+    c.close()
+
+
+def run_gpu(model, ctx, **kw):
+    from vsmom_b200 import rt_run as rr
+    return rr.rt_run(model, ctx, **kw)
+
+
+def assert_close(out, ref, tol, keys=KEYS, sel=slice(None)):
+    for k in keys:
+        a = out[k][..., sel] if out[k].ndim == 3 else out[k][sel]
+        assert np.isfinite(a).all(), k
+        e = relerr(a, ref[k])
+        assert e <= tol, (k, e)
+
+
+def test_quickstart_scalar_config(ctx):
+    # configs[0]: quickstart.yaml shape -- Stokes_I, 3 streams (+sza/vza node), 2 layers, 16 points
+    m = vb.synthetic_o2a_model(nSpec=16, nstreams=3, polarization_type="Stokes_I", aerosol=False, vza=[60.0],
+                               vaz=[180.0], p_half=np.array([100.0, 500.0, 1000.0]))
+    assert m.quad_points.qp_muN.size == 4
+    assert_close(run_gpu(m, ctx), orc.rt_run(to_oracle(m)), F64_TOL)
+
+
+@pytest.mark.parametrize("aerosol,nspec,nref", [(False, 96, 96), (True, 40, 12)])
+def test_o2a_vector_config_f64(ctx, aerosol, nspec, nref):
+    # configs[1]: IQU, 10 streams (N=45), 34 layers
+    m = vb.synthetic_o2a_model(nSpec=nspec, aerosol=aerosol)
+    out = run_gpu(m, ctx)
+    ref = orc.rt_run(to_oracle(m), slice(0, nref))
+    assert_close(out, ref, F64_TOL, sel=slice(0, nref))
+
+
+@pytest.mark.parametrize("pol", ["Stokes_I", "Stokes_IQ", "Stokes_IQUV"])
+def test_other_polarisations(ctx, pol):
+    m = vb.synthetic_o2a_model(nSpec=8, nstreams=4, polarization_type=pol, aerosol=True)
+    assert_close(run_gpu(m, ctx), orc.rt_run(to_oracle(m)), F64_TOL)
+
+
+def test_o2a_vector_config_f32(ctx):
+    m32 = vb.synthetic_o2a_model(nSpec=32, aerosol=True, float_type=np.float32)
+    m64 = vb.synthetic_o2a_model(nSpec=32, aerosol=True)
+    out = run_gpu(m32, ctx)
+    ref64 = orc.rt_run(to_oracle(m64), slice(0, 8))
+    I32, I64 = out["R_SFI"][:, 0, :8], ref64["R_SFI"][:, 0]
+    assert np.isfinite(out["R_SFI"]).all() and np.isfinite(out["T_SFI"]).all()
+    assert np.max(np.abs(I32 - I64) / np.abs(I64)) < 1e-2          # test/test_float32.jl:64
+    ref32 = orc.rt_run(to_oracle(m32), slice(0, 8))
+    assert relerr(out["R_SFI"][..., :8], ref32["R_SFI"]) < 1e-3
+
+
+def test_natraj_golden_on_gpu(ctx):
+    # test/test_CoreRT.jl:110-157 straight against the published table (N = 108, IQUV)
+    d = golden()["natraj"]
+    vza = [math.degrees(math.acos(x)) for x in d["mu"]]
+    for k in (1, 3):
+        phi = d["phi"][k]
+        m = rayleigh_slab_model("Stokes_IQUV", d["nstreams"], math.degrees(math.acos(d["mu0"])), vza, [phi] * 16,
+                                d["tau"], d["albedo"])
+        out = run_gpu(m, ctx)
+        R = math.pi * out["R_SFI"]
+        I, Q, U = (np.array(d[s])[:, k] for s in "IQU")
+        assert np.max(np.abs(I - R[:, 0, 0]) / I) < d["tol"]["I"]
+        sel = R[:, 2, 0] >= 0.01
+        assert np.max(np.abs(U[sel] - R[sel, 2, 0]) / U[sel]) < d["tol"]["U"]
+        assert_close(out, orc.rt_run(to_oracle(m)), F64_TOL, keys=("R_SFI", "T_SFI"))
+
+
+def test_6sv1_golden_on_gpu(ctx):
+    # near-coincident streams (sza 0.0001 vs vza 0): the expdiff_neg / L'Hopital branches
+    d = golden()["sixsv1"]
+    azs, szas, lam, tau, rho = d["cases"][1]
+    worst = 0.0
+    for si, sza in enumerate(szas[:2]):
+        m = rayleigh_slab_model("Stokes_IQUV", d["nstreams"], sza, d["vza"], [azs[0]] * 16, tau, rho)
+        out = run_gpu(m, ctx)
+        R = math.pi * out["R_SFI"][:, 0, 0] / m.quad_points.mu0
+        tr = np.array(d["R_trues"][1][si][0])
+        worst = max(worst, float(np.max(np.abs(tr - R) / tr)))
+        assert_close(out, orc.rt_run(to_oracle(m)), F64_TOL)
+    assert worst < d["tol"]
+
+
+def test_siewert_golden_on_gpu(ctx):
+    # aerosol-only slab with supplied Greek coefficients: Rayleigh weight all-zero branch (types.jl:1279)
+    m = siewert_model(90.0)
+    out = run_gpu(m, ctx)
+    for st, e in siewert_compare(out["R_SFI"], 90.0).items():
+        assert e < (1e-2 if st == 1 else 5e-4), (st, e)
+    assert_close(out, orc.rt_run(to_oracle(m)), F64_TOL, keys=("R_SFI", "T_SFI"))
+
+
+def test_nonscattering_layers_all_interfaces(ctx):
+    # layers that only absorb exercise ScatteringInterface_00/_01/_10 and zero_added_noscat!
+    m = vb.synthetic_o2a_model(nSpec=6, nstreams=4, aerosol=False, p_half=np.array([1., 50., 200., 400., 600., 800., 1000.]))
+    m.tau_rayl[:, 0] = 0; m.tau_rayl[:, 1] = 0; m.tau_rayl[:, 3] = 0
+    m.tau_abs[:, 0] += 0.05; m.tau_abs[:, 3] += 0.2
+    c = vb.layer_control(m)
+    assert list(c.iface) == [0, 0, 1, 2, 3, 3]
+    assert_close(run_gpu(m, ctx), orc.rt_run(to_oracle(m)), F64_TOL)
+
+
+def test_single_point_and_empty(ctx):
+    m = vb.synthetic_o2a_model(nSpec=1, nstreams=4, aerosol=True)
+    assert_close(run_gpu(m, ctx), orc.rt_run(to_oracle(m)), F64_TOL)      # batch == 1 must work
+    from vsmom_b200 import rt_run as rr
+    prep = rr.prepare(m)
+    z = torch.zeros((m.Nz, 0), dtype=torch.float64, device="cuda")
+    R, T, H, uw, dw = rr.rt_column_device(ctx, prep, z, z, torch.zeros((0, 3), dtype=torch.float64, device="cuda"))
+    assert R.shape[0] == 0
+
+
+def test_workspace_chunking_is_bit_identical(ctx):
+    m = vb.synthetic_o2a_model(nSpec=64, nstreams=4, aerosol=True)
+    a = run_gpu(m, ctx)
+    ctx.set_workspace_limit(3 << 20)       # forces several spectral chunks / moment batches
+    try:
+        b = run_gpu(m, ctx)
+    finally:
+        ctx.set_workspace_limit(0)
+    for k in KEYS:
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_shard_invariance_and_determinism(ctx):
+    # two half-band shards with full-band control flow == the full band, bit for bit
+    from vsmom_b200 import rt_run as rr
+    m = vb.synthetic_o2a_model(nSpec=64, aerosol=False)
+    prep = rr.prepare(m)
+    full = run_gpu(m, ctx, prep=prep)
+    again = run_gpu(m, ctx, prep=prep)
+    lo = run_gpu(m, ctx, prep=prep, sel=slice(0, 32))
+    hi = run_gpu(m, ctx, prep=prep, sel=slice(32, 64))
+    for k in ("R_SFI", "T_SFI", "hdr"):
+        assert np.array_equal(full[k], again[k])
+        assert np.array_equal(full[k], np.concatenate([lo[k], hi[k]], axis=2))
+
+
+def test_full_size_properties(ctx):
+    # BASELINE.json configs[1] size (10k points, Rayleigh-only so it stays short): invariants that
+    # need no full-size oracle run -- finite, I > 0, |Q|,|U| <= I (test/test_forward_noRS.jl), spot
+    # points equal the oracle, and the strongly absorbing points are darker than the continuum.
+    m = vb.synthetic_o2a_model(nSpec=10000, aerosol=False)
+    out = run_gpu(m, ctx)
+    R = out["R_SFI"]
+    assert np.isfinite(R).all() and (R[:, 0] > 0).all()
+    assert (np.abs(R[:, 1]) <= R[:, 0] + 1e-15).all() and (np.abs(R[:, 2]) <= R[:, 0] + 1e-15).all()
+    idx = np.array([0, 1234, 5000, 9999])
+    ref = orc.rt_run(to_oracle(m), idx)
+    assert relerr(R[..., idx], ref["R_SFI"]) <= F64_TOL
+    col = m.tau_abs.sum(axis=1)
+    assert R[4, 0, np.argmax(col)] < R[4, 0, np.argmin(col)]
+
+
+# ---- L0: batched_mul / batch_inv! / batch_solve!  (KAT recipe: test/test_batched_kernels.jl:3-37)
+def _dd(batch, n, dtype, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    A = torch.rand((batch, n, n), generator=g, dtype=torch.float64)
+    A = A + n * torch.eye(n, dtype=torch.float64)
+    return A.to(dtype).cuda()
+
+
+@pytest.mark.parametrize("n,batch", [(4, 6), (15, 33), (45, 200), (112, 7), (200, 3), (45, 1)])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_batch_inv_matches_lapack(ctx, n, batch, dtype):
+    from vsmom_b200 import batched
+    A = _dd(batch, n, dtype)
+    ref = torch.linalg.inv(A.double().cpu())
+    X = torch.empty_like(A)
+    info = torch.full((batch,), -1, dtype=torch.int32, device="cuda")
+    batched.batch_inv_(ctx, X, A.clone(), info)
+    ctx.synchronize()
+    tol = 50 * (1.2e-7 if dtype == torch.float32 else 2.3e-16) * n
+    assert (X.double().cpu() - ref).abs().max() <= tol * ref.abs().max()
+    assert (info == 0).all()
+
+
+@pytest.mark.parametrize("m,k,nc,batch", [(4, 4, 4, 6), (45, 45, 45, 100), (45, 45, 1, 100), (112, 112, 112, 5),
+                                           (200, 200, 200, 2), (45, 45, 45, 1), (7, 13, 5, 9)])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_batched_mul_matches_matmul(ctx, m, k, nc, batch, dtype):
+    from vsmom_b200 import batched
+    g = torch.Generator().manual_seed(1)
+    A = torch.randn((batch, k, m), generator=g, dtype=torch.float64).to(dtype).cuda()   # Julia (m,k,batch)
+    B = torch.randn((batch, nc, k), generator=g, dtype=torch.float64).to(dtype).cuda()  # Julia (k,nc,batch)
+    Cm = batched.batched_mul(ctx, A, B)
+    ctx.synchronize()
+    ref = torch.matmul(B.double(), A.double())          # (C^T = B^T A^T in this memory order)
+    tol = 50 * (1.2e-7 if dtype == torch.float32 else 2.3e-16) * k
+    assert (Cm.double() - ref).abs().max() <= tol * ref.abs().max()
+
+
+def test_batch_inv_flags_singular(ctx):
+    from vsmom_b200 import batched
+    A = _dd(3, 8, torch.float64)
+    A[1] = 0
+    info = torch.zeros(3, dtype=torch.int32, device="cuda")
+    batched.batch_inv_(ctx, torch.empty_like(A), A, info)
+    ctx.synchronize()
+    assert info[0] == 0 and info[2] == 0 and info[1] > 0
+
+
+def test_batch_solve(ctx):
+    from vsmom_b200 import batched
+    A = _dd(20, 45, torch.float64)
+    g = torch.Generator().manual_seed(2)
+    B = torch.randn((20, 3, 45), generator=g, dtype=torch.float64).cuda()
+    X = torch.empty_like(B)
+    batched.batch_solve_(ctx, X, A.clone(), B)
+    ctx.synchronize()
+    # memory order: X_torch[k] = X_julia^T ; A_julia X_julia = B_julia  <=>  X_t A_t = B_t
+    assert (torch.matmul(X, A) - B).abs().max() < 1e-10
+
+
+def test_invalid_arguments_fail_loudly(ctx):
+    from vsmom_b200 import _lib, batched
+    with pytest.raises(_lib.VsmError):
+        ctx.check(_lib.lib.vsm_batch_inv_f64(ctx.handle, None, None, 4, 1, None))
+    with pytest.raises(ValueError):
+        batched.batched_mul(ctx, torch.zeros((2, 3, 3)), torch.zeros((2, 3, 3)))

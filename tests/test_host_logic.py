@@ -1,0 +1,75 @@
+"""CPU tests of the host-side mirror (vsmom_b200.model) against the oracle's
+independent restatement: quadrature, Z moments, full-band control flow."""
+import numpy as np
+import pytest
+
+import vsmom_b200 as vb
+import vsmom_oracle as orc
+from helpers import to_oracle
+
+
+@pytest.mark.parametrize("pol", ["Stokes_I", "Stokes_IQU", "Stokes_IQUV"])
+def test_streams_match_oracle(pol):
+    n = vb.model.POL_N[pol]
+    q = vb.rt_set_streams(10, 60.0, vb.model.DEFAULT_VZA, n)
+    o = orc.rt_set_streams_gauss(10, 60.0, vb.model.DEFAULT_VZA, n)
+    assert q.Nquad == o.Nquad == 15 and q.Nstreams == 10
+    assert np.array_equal(q.qp_mu, o.qp_mu) and np.array_equal(q.wt_muN, o.wt_muN)
+    assert q.imu0 == o.imu0 + 1 and q.imu0Nstart == n * o.imu0 + 1
+
+
+@pytest.mark.parametrize("pol_n", [1, 3, 4])
+@pytest.mark.parametrize("m", [0, 1, 2, 5, 19])
+def test_z_moments_match_oracle(pol_n, m):
+    q = vb.rt_set_streams(10, 60.0, vb.model.DEFAULT_VZA, pol_n)
+    g = vb.hg_greek(0.7, 20)
+    a = vb.compute_Z_moments(pol_n, q.qp_mu, g, m)
+    b = orc.compute_Z_moments(pol_n, q.qp_mu, orc.GreekCoefs(g.alpha, g.beta, g.gamma, g.delta, g.epsilon, g.zeta), m)
+    for x, y in zip(a, b):
+        assert np.max(np.abs(x - y)) <= 1e-12 * max(1.0, np.max(np.abs(y)))
+
+
+def test_rayleigh_z_has_three_moments():
+    q = vb.rt_set_streams(4, 30.0, [0.0], 3)
+    zp, zm = vb.compute_Z_moments(3, q.qp_mu, vb.get_greek_rayleigh(0.03), 2)
+    assert np.abs(zp).max() > 0
+
+
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
+@pytest.mark.parametrize("aerosol", [False, True])
+def test_layer_control_matches_oracle(FT, aerosol):
+    m = vb.synthetic_o2a_model(nSpec=200, aerosol=aerosol, float_type=FT)
+    c = vb.layer_control(m)
+    o = orc.band_control(to_oracle(m), 0)
+    assert list(c.ndoubl) == o.ndoubl
+    assert list(c.scatter) == [int(s) for s in o.scatter]
+    assert list(c.iface) == o.interface
+    assert c.ndoubl.max() >= 4          # thick lower layers need several doublings
+
+
+def test_doubling_number_edges():
+    # rt_helper_functions.jl:49-69: tau_end <= dtau_max -> 0 ; exact powers of two hit the eps tie rule
+    assert vb.model.doubling_number(1e-3, 5e-4, np.float64) == 0
+    assert vb.model.doubling_number(1e-3, 1e-3, np.float64) == 0
+    assert vb.model.doubling_number(0.125, 1.0, np.float64) == 3
+    assert vb.model.doubling_number(0.1, 1.0, np.float64) == 4
+    for nd_ref, (a, b) in {3: (0.125, 1.0), 10: (2.0 ** -10, 1.0)}.items():
+        assert orc.doubling_number(a, b)[1] == nd_ref
+
+
+def test_interface_sequence_with_nonscattering_layers():
+    # get_scattering_interface (rt_helper_functions.jl:15-33)
+    seq = []
+    prev = 0
+    for iz, s in enumerate([False, False, True, False, True]):
+        prev = orc.get_scattering_interface(prev, s, iz)
+        seq.append(prev)
+    assert seq == [0, 0, 1, 2, 3]
+
+
+def test_synthetic_scene_shape():
+    m = vb.synthetic_o2a_model(nSpec=100)
+    assert m.quad_points.qp_muN.size == 45 and m.Nz == 34 and m.m_max == 19
+    col = m.tau_abs.sum(axis=1)
+    assert col.max() <= 100.0 * 1.01 and col.min() > 0
+    assert abs(m.tau_aer.sum() - 0.3) < 1e-12

@@ -142,6 +142,55 @@ extern "C" int vsm_set_workspace_limit(vsm_ctx* ctx, uint64_t bytes) {
 extern "C" uint64_t vsm_kernel_launches(vsm_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // ---------------------------------------------------------------------------
+// FMA peak microbenchmark (roofline denominator for the fp64 / fp32 SIMT path)
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_fma_peak(T* out, int iters, T seed) {
+    T a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const T m = T(0.999), c = T(0.001);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == T(123.456)) out[0] = a0;
+}
+
+template <typename T>
+static int fma_peak_impl(vsm_ctx* ctx, double* tflops) {
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure(ctx, ctx->l0tmp, 256);
+    if (rc) return rc;
+    const int iters = sizeof(T) == 8 ? 4096 : 16384;
+    const int grid = ctx->num_sms * 8;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(e0, ctx->stream));
+        k_fma_peak<T><<<grid, 256, 0, ctx->stream>>>((T*)ctx->l0tmp.p, iters, T(1));
+        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 64.0 * iters * 256.0 * grid;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return VSM_OK;
+}
+
+extern "C" int vsm_measure_fma_peak(vsm_ctx* ctx, int kind, double* tflops) {
+    if (!ctx || !tflops) return VSM_ERR_INVALID_ARG;
+    return kind == 0 ? fma_peak_impl<double>(ctx, tflops) : fma_peak_impl<float>(ctx, tflops);
+}
+
+// ---------------------------------------------------------------------------
 // L0
 // ---------------------------------------------------------------------------
 template <typename T>
@@ -525,6 +574,14 @@ extern "C" int vsm_last_column_ms(vsm_ctx* ctx, float* total_ms, float* doubling
     if (total_ms) *total_ms = t;
     if (doubling_ms) *doubling_ms = tl;
     if (adding_ms) *adding_ms = ta;
+    return VSM_OK;
+}
+
+extern "C" int vsm_last_column_launches(vsm_ctx* ctx, int* layer_launches, int* adding_launches) {
+    if (!ctx) return VSM_ERR_INVALID_ARG;
+    if (!ctx->timing_valid) return fail(ctx, VSM_ERR_INVALID_ARG, "vsm_last_column_launches: no column call yet");
+    if (layer_launches) *layer_launches = (int)ctx->seg_layer.size();
+    if (adding_launches) *adding_launches = (int)ctx->seg_add.size();
     return VSM_OK;
 }
 

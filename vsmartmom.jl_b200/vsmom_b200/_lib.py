@@ -47,11 +47,11 @@ class ColumnDesc(C.Structure):
 
 EXPORTS = [
     "vsm_version", "vsm_create", "vsm_destroy", "vsm_last_error", "vsm_synchronize",
-    "vsm_set_workspace_limit", "vsm_kernel_launches",
+    "vsm_set_workspace_limit", "vsm_kernel_launches", "vsm_measure_fma_peak",
     "vsm_batched_mul_f64", "vsm_batched_mul_f32", "vsm_batch_inv_f64", "vsm_batch_inv_f32",
     "vsm_batch_solve_f64", "vsm_batch_solve_f32",
     "vsm_rt_layer_f64", "vsm_rt_layer_f32", "vsm_rt_column_f64", "vsm_rt_column_f32",
-    "vsm_last_column_ms",
+    "vsm_last_column_ms", "vsm_last_column_launches",
 ]
 
 lib.vsm_version.restype = c_int
@@ -63,6 +63,7 @@ lib.vsm_synchronize.argtypes = [c_void_p]
 lib.vsm_set_workspace_limit.argtypes = [c_void_p, C.c_uint64]
 lib.vsm_kernel_launches.argtypes = [c_void_p]
 lib.vsm_kernel_launches.restype = C.c_uint64
+lib.vsm_measure_fma_peak.argtypes = [c_void_p, c_int, C.POINTER(c_double)]
 for _s in ("f64", "f32"):
     getattr(lib, f"vsm_batched_mul_{_s}").argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int]
     getattr(lib, f"vsm_batch_inv_{_s}").argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
@@ -70,6 +71,7 @@ for _s in ("f64", "f32"):
     getattr(lib, f"vsm_rt_layer_{_s}").argtypes = [c_void_p, C.POINTER(LayerDesc)]
     getattr(lib, f"vsm_rt_column_{_s}").argtypes = [c_void_p, C.POINTER(ColumnDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
 lib.vsm_last_column_ms.argtypes = [c_void_p, C.POINTER(c_float), C.POINTER(c_float), C.POINTER(c_float)]
+lib.vsm_last_column_launches.argtypes = [c_void_p, C.POINTER(c_int), C.POINTER(c_int)]
 
 
 class VsmError(RuntimeError):
@@ -103,10 +105,21 @@ class Context:
     def kernel_launches(self) -> int:
         return int(lib.vsm_kernel_launches(self.handle))
 
+    def measure_fma_peak(self, kind: int) -> float:
+        """TFLOP/s of register-resident FMA chains: kind 0 = fp64, 1 = fp32."""
+        v = c_double()
+        self.check(lib.vsm_measure_fma_peak(self.handle, int(kind), C.byref(v)))
+        return v.value
+
     def last_column_ms(self):
         a, b, c = c_float(), c_float(), c_float()
         self.check(lib.vsm_last_column_ms(self.handle, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+    def last_column_launches(self):
+        a, b = c_int(), c_int()
+        self.check(lib.vsm_last_column_launches(self.handle, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def close(self):
         if getattr(self, "handle", None):

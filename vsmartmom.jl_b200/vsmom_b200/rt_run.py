@@ -146,3 +146,41 @@ def rt_run(model: RTModel, ctx: Optional[_lib.Context] = None, prep: Optional[Pr
     if own:
         ctx.close()
     return out
+
+
+def rt_run_sharded(model: RTModel, ctx: Optional[_lib.Context] = None, device: Optional[str] = None):
+    """``rt_run`` with the spectral axis sharded over the ranks of the default
+    torch.distributed process group (NCCL, one process per GPU).  Every rank passes
+    the same full-band model and gets the full-band result."""
+    import torch.distributed as dist
+    from .sharding import gather_spectral, shard_bounds
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    device = device or f"cuda:{torch.cuda.current_device()}"
+    own = ctx is None
+    if own:
+        ctx = _lib.Context(torch.device(device).index or 0)
+    prep = prepare(model, device)                      # full-band control flow
+    lo, hi = shard_bounds(model.nSpec, world)[rank]
+    FT = model.float_type
+    nS = hi - lo
+    dt = _tdtype(FT)
+    nV, n = len(model.vza), model.pol_n
+    if nS > 0:
+        d_tr = torch.from_numpy(np.ascontiguousarray(model.tau_rayl[lo:hi].T)).to(device)
+        d_ta = torch.from_numpy(np.ascontiguousarray(model.tau_abs[lo:hi].T)).to(device)
+        f0 = np.zeros((nS, n), FT); f0[:, 0] = 1
+        R, T, H, uw, dw = rt_column_device(ctx, prep, d_tr, d_ta, torch.from_numpy(f0).to(device))
+    else:
+        R = torch.zeros((0, n, nV), dtype=dt, device=device); T = R.clone(); H = R.clone()
+        uw = torch.zeros((0, n), dtype=dt, device=device); dw = uw.clone()
+    packed = torch.cat([R.reshape(nS, -1), T.reshape(nS, -1), H.reshape(nS, -1), uw, dw], dim=1)
+    full = gather_spectral(packed, model.nSpec, world, rank).cpu().numpy()
+    k = n * nV
+    out = dict(R_SFI=full[:, :k].reshape(-1, n, nV).transpose(2, 1, 0),
+               T_SFI=full[:, k:2 * k].reshape(-1, n, nV).transpose(2, 1, 0),
+               hdr=full[:, 2 * k:3 * k].reshape(-1, n, nV).transpose(2, 1, 0),
+               bhr_uw=full[:, 3 * k].copy(), bhr_dw=full[:, 3 * k + n].copy())
+    if own:
+        ctx.close()
+    return out
