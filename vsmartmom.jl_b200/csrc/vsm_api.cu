@@ -334,6 +334,7 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
     if (!ctx) return VSM_ERR_INVALID_ARG;
     if (!d || d->struct_size != (int)sizeof(vsm_column_desc))
         return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column: descriptor NULL or struct_size mismatch");
+    if (d->nSpec == 0) return VSM_OK;            // empty shard: nothing to do
     if (!R_SFI || !T_SFI) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column: R_SFI/T_SFI NULL");
     const int N = d->N, nSt = d->nStokes, Nz = d->Nz, nAer = d->nAer, nV = d->nVZA, nM = d->n_moments;
     const int nSpec = d->nSpec;
