@@ -285,34 +285,44 @@ struct Plan {
 };
 
 template <typename T>
-static size_t layer_vec_bytes(int n) { return ((size_t)17 * n + kMaxComp) * sizeof(T) + (size_t)2 * n * 4; }
+static size_t layer_vec_bytes(int n) { return ((size_t)kVecUnits * n + kMaxComp) * sizeof(T) + ((size_t)2 * n + 4) * 4; }
 template <typename T>
-static size_t add_vec_bytes(int n) { return ((size_t)17 * n) * sizeof(T) + (size_t)2 * n * 4; }
+static size_t add_vec_bytes(int n) { return ((size_t)kVecUnits * n) * sizeof(T) + ((size_t)2 * n + 4) * 4; }
+
+// specialised (compile-time N) instantiations that exist in this build
+static bool has_fast(int N) { return N == 45; }
 
 template <typename T>
-static int do_launch(vsm_ctx* ctx, bool layer, int tm, const ColArgs<T>& a, unsigned total, int grid, int threads, size_t smem) {
+static int do_launch(vsm_ctx* ctx, bool layer, int tm, bool fast, int N, const ColArgs<T>& a, unsigned total, int grid,
+                     int threads, size_t smem) {
     cudaError_t e = cudaSuccess;
-    if (layer) {
-        switch (tm) {
-            case 1: e = launch_layer<T, 1>(ctx->stream, a, total, grid, threads, smem); break;
-            case 2: e = launch_layer<T, 2>(ctx->stream, a, total, grid, threads, smem); break;
-            case 3: e = launch_layer<T, 3>(ctx->stream, a, total, grid, threads, smem); break;
-            default: e = launch_layer<T, 4>(ctx->stream, a, total, grid, threads, smem); break;
-        }
-    } else {
-        switch (tm) {
-            case 1: e = launch_adding<T, 1>(ctx->stream, a, total, grid, threads, smem); break;
-            case 2: e = launch_adding<T, 2>(ctx->stream, a, total, grid, threads, smem); break;
-            case 3: e = launch_adding<T, 3>(ctx->stream, a, total, grid, threads, smem); break;
-            default: e = launch_adding<T, 4>(ctx->stream, a, total, grid, threads, smem); break;
-        }
+#define VSM_L(TM_, NN_) (layer ? launch_layer<T, TM_, NN_>(ctx->stream, a, total, grid, threads, smem) \
+                               : launch_adding<T, TM_, NN_>(ctx->stream, a, total, grid, threads, smem))
+    if (fast && N == 45) e = VSM_L(3, 45);
+    else switch (tm) {
+        case 1: e = VSM_L(1, 0); break;
+        case 2: e = VSM_L(2, 0); break;
+        case 3: e = VSM_L(3, 0); break;
+        default: e = VSM_L(4, 0); break;
     }
+#undef VSM_L
     ctx->launches++;
     if (e != cudaSuccess) {
         ctx->err = std::string(layer ? "k_layer launch: " : "k_adding launch: ") + cudaGetErrorString(e);
         return VSM_ERR_CUDA;
     }
     return VSM_OK;
+}
+
+template <typename T>
+static void get_kernel_ptrs(int tm, bool fast, int N, const void** kl, const void** ka) {
+    if (fast && N == 45) { kernel_ptrs<T, 3, 45>(kl, ka); return; }
+    switch (tm) {
+        case 1: kernel_ptrs<T, 1, 0>(kl, ka); break;
+        case 2: kernel_ptrs<T, 2, 0>(kl, ka); break;
+        case 3: kernel_ptrs<T, 3, 0>(kl, ka); break;
+        default: kernel_ptrs<T, 4, 0>(kl, ka); break;
+    }
 }
 
 template <typename T>
@@ -406,18 +416,14 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
     const size_t smax = (size_t)ctx->max_smem_optin;
     const size_t lv = layer_vec_bytes<T>(N), av = add_vec_bytes<T>(N);
     if (lv + 1024 > smax) return fail(ctx, VSM_ERR_UNSUPPORTED, "rt_column: N too large");
-    int l_mats = (int)std::min<size_t>(5, (smax - lv) / msz);
-    int a_mats = (int)std::min<size_t>(9, (smax - av) / msz);
+    int l_mats = (int)std::min<size_t>(kLayerMats, (smax - lv) / msz);
+    int a_mats = (int)std::min<size_t>(kAddMats, (smax - av) / msz);
     const size_t l_smem = lv + (size_t)l_mats * msz, a_smem = av + (size_t)a_mats * msz;
-    const size_t l_slab = (size_t)(5 - l_mats) * msz, a_slab = (size_t)(9 - a_mats) * msz;
+    const size_t l_slab = (size_t)(kLayerMats - l_mats) * msz, a_slab = (size_t)(kAddMats - a_mats) * msz;
+    const bool fast = has_fast(N) && l_mats == kLayerMats && a_mats == kAddMats;
 
     const void* kl = nullptr; const void* ka = nullptr;
-    switch (cfg.tm) {
-        case 1: kernel_ptrs<T, 1>(&kl, &ka); break;
-        case 2: kernel_ptrs<T, 2>(&kl, &ka); break;
-        case 3: kernel_ptrs<T, 3>(&kl, &ka); break;
-        default: kernel_ptrs<T, 4>(&kl, &ka); break;
-    }
+    get_kernel_ptrs<T>(cfg.tm, fast, N, &kl, &ka);
     CK(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l_smem));
     CK(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
     const int l_occ = occupancy<T>(kl, cfg.threads, l_smem);
@@ -497,7 +503,7 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
         memset(&a, 0, sizeof a);
         a.N = N; a.nStokes = nSt; a.Nz = Nz; a.nC = nC; a.nVZA = nV; a.ld = ld;
         a.istart = (d->imu0 - 1) * nSt;
-        a.nS = nS; a.n_sched_layers = nSched; a.z_spectral = 0;
+        a.nS = nS; a.n_sched_layers = nSched; a.z_spectral = 0; a.mz0 = 0;
         a.mu0 = (T)d->mu0; a.albedo = (T)d->albedo;
         a.mu = cT + o_mu; a.wt = cT + o_wt;
         a.ndoubl = cI + o_nd; a.scatter = cI + o_sc; a.iface = cI + o_if; a.layer_order = cI + o_ord;
@@ -523,7 +529,7 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
                 CK(cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
                 cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
                 CK(cudaEventRecord(e0, ctx->stream));
-                rc = do_launch<T>(ctx, true, cfg.tm, a, total, grid, cfg.threads, l_smem);
+                rc = do_launch<T>(ctx, true, cfg.tm, fast, N, a, total, grid, cfg.threads, l_smem);
                 if (rc) return rc;
                 CK(cudaEventRecord(e1, ctx->stream));
                 ctx->seg_layer.push_back({e0, e1});
@@ -538,7 +544,7 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
                 CK(cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
                 cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
                 CK(cudaEventRecord(e0, ctx->stream));
-                rc = do_launch<T>(ctx, false, cfg.tm, a, total, grid, cfg.threads, a_smem);
+                rc = do_launch<T>(ctx, false, cfg.tm, fast, N, a, total, grid, cfg.threads, a_smem);
                 if (rc) return rc;
                 CK(cudaEventRecord(e1, ctx->stream));
                 ctx->seg_add.push_back({e0, e1});

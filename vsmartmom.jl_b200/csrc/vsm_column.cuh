@@ -109,6 +109,7 @@ struct ColArgs {
     int n_sched_layers;      // number of scattering layers (entries of layer_order)
     int n_smem_mats;
     int z_spectral;          // L1 only: Z given per spectral point
+    int mz0;                 // moment index of the first Z table (0 for L2; m for L1)
     T mu0, albedo;
     const T* mu; const T* wt;                         // [N]
     const int* ndoubl; const int* scatter; const int* iface; const int* layer_order;  // [Nz]
@@ -137,14 +138,14 @@ __device__ inline unsigned int next_item(unsigned int* counter, unsigned int* sh
 // ----------------------------------------------------------------------------
 // elemental r⁻⁺/t⁺⁺ and solar sources into the arena  (elemental.jl:289-392)
 // ----------------------------------------------------------------------------
-template <typename T>
+template <typename T, int NN>
 __device__ __forceinline__ void elemental_fill(const ColArgs<T>& a, int m, int nd, T dtau, T varpi,
                                                T tausum, const T* __restrict__ Wc,
                                                const T* __restrict__ Zpp, const T* __restrict__ Zmp,
                                                size_t zstride, const T* __restrict__ F0n,
                                                const uint32_t* __restrict__ dmask,
                                                T* r, T* t, T* jp, T* jm) {
-    const int n = a.N, ld = a.ld, nC = a.nC;
+    const int n = NN ? NN : a.N, ld = NN ? (NN | 1) : a.ld, nC = a.nC;
     const T wsc = (m == 0) ? T(0.5) : T(0.25);       // scaled_weights / fourier_weight
     const T eps = Num<T>::eps();
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
@@ -177,8 +178,8 @@ __device__ __forceinline__ void elemental_fill(const ColArgs<T>& a, int m, int n
             tv = (i == j) ? Num<T>::exp_(-dtau / mui) : T(0);
         }
         if (nd >= 1) rv = Num<T>::flip(rv, dmask[i]);      // apply_D_elemental!, nd>=1 branch
-        r[i + (size_t)j * ld] = rv;
-        t[i + (size_t)j * ld] = tv;
+        r[i + j * ld] = rv;
+        t[i + j * ld] = tv;
     }
     const T wct02 = wsc;
     const T mus = a.mu[a.istart];
@@ -213,67 +214,82 @@ __device__ __forceinline__ void elemental_fill(const ColArgs<T>& a, int m, int n
 }
 
 // ----------------------------------------------------------------------------
-// ndoubl doublings in the arena.  mats: r, t, X1, X2, X3 (pointers are rotated).
+// ndoubl doublings in the arena (doubling_helper!, doubling.jl:38-99).
+// Four matrices: r, t, X1, X2 (pointers are rotated).
+//   X1 = (I - r r)^-1 ; X2 = t X1 ; sources ; r += X2 (r t) ; t = X2 t
+// (the reference forms (X2 r) t; the product is re-associated so that one scratch
+//  matrix less is live, which lets a third CTA share the SM).
 // ----------------------------------------------------------------------------
-template <typename T, int TM>
-__device__ __forceinline__ void doubling_loop(int n, int ld, int nd, T expk, T*& r, T*& t, T*& X1,
-                                              T* X2, T* X3, T* jp, T* jm, T* j1p, T* j1m, T* v1,
-                                              T* v2, T* vec, T* part, int* piv,
-                                              const uint32_t* dmask) {
+template <typename T, class Ops>
+__device__ __forceinline__ void doubling_loop(const Ops& op, int nd, T expk, T*& r, T*& t, T*& X1,
+                                              T* X2, T* jp, T* jm, T* j1p, T* j1m, T* v1, T* v2) {
+    const int n = op.N(), ld = op.LD();
     for (int it = 0; it < nd; ++it) {
-        // X1 = I - r r          (compute_geometric_progression!, rt_helpers.jl:103)
-        cta_mm<T, TM, TM, false>(n, r, ld, r, ld, dmask, [&](int i, int j, T acc) {
-            X1[i + (size_t)j * ld] = (i == j ? T(1) : T(0)) - acc;
-        });
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {   // doubling_source_update!, :131-132
+        auto build = [&]() {
+            op.template mm<false>(r, r, [&](int i, int j, T acc) {
+                X1[i + j * ld] = (i == j ? T(1) : T(0)) - acc;            // rt_helpers.jl:103
+            });
+        };
+        build();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {               // doubling_source_update!, :131-132
             j1p[i] = jp[i] * expk;
             j1m[i] = jm[i] * expk;
         }
         __syncthreads();
-        cta_inverse<T>(n, X1, ld, vec, piv, nullptr);          // :104
-        // X2 = t * gp           (:105)
-        cta_mm<T, TM, TM, false>(n, t, ld, X1, ld, dmask,
-                                 [&](int i, int j, T acc) { X2[i + (size_t)j * ld] = acc; });
-        // v1 = j1m + r jp ; v2 = jp + r j1m      (:133-134)
-        cta_mv<T, false>(n, r, ld, jp, dmask, part, [&](int i, T s) { v1[i] = j1m[i] + s; });
-        cta_mv<T, false>(n, r, ld, j1m, dmask, part, [&](int i, T s) { v2[i] = jp[i] + s; });
-        cta_mv<T, false>(n, X2, ld, v1, dmask, part, [&](int i, T s) { jm[i] = jm[i] + s; });
-        cta_mv<T, false>(n, X2, ld, v2, dmask, part, [&](int i, T s) { jp[i] = j1p[i] + s; });
-        // X3 = tt r ; X1 = tt t   (doubling_rt_update!, :162-163)
-        cta_mm<T, TM, TM, false>(n, X2, ld, r, ld, dmask,
-                                 [&](int i, int j, T acc) { X3[i + (size_t)j * ld] = acc; });
-        cta_mm<T, TM, TM, false>(n, X2, ld, t, ld, dmask,
-                                 [&](int i, int j, T acc) { X1[i + (size_t)j * ld] = acc; });
+        op.inverse(X1, build);                                            // :104
+        op.template mm<false>(t, X1, [&](int i, int j, T acc) { X2[i + j * ld] = acc; });   // :105
+        // v1 = j1m + r jp ; v2 = jp + r j1m ; jm += tt v1 ; jp = j1p + tt v2          (:133-134)
+        op.mv2(r, jp, j1m, [&](int i, T s) { v1[i] = j1m[i] + s; }, [&](int i, T s) { v2[i] = jp[i] + s; });
+        op.mv2(X2, v1, v2, [&](int i, T s) { jm[i] = jm[i] + s; }, [&](int i, T s) { jp[i] = j1p[i] + s; });
+        // doubling_rt_update! (:162-163)
+        op.template mm<false>(r, t, [&](int i, int j, T acc) { X1[i + j * ld] = acc; });
         __syncthreads();
-        // r += (tt r) t
-        cta_mm<T, TM, TM, false>(n, X3, ld, t, ld, dmask,
-                                 [&](int i, int j, T acc) { r[i + (size_t)j * ld] += acc; });
+        op.template mm<false>(X2, X1, [&](int i, int j, T acc) { r[i + j * ld] += acc; });
         __syncthreads();
-        T* tmp = t; t = X1; X1 = tmp;        // t = tt t
-        expk = expk * expk;                  // :164
+        op.template mm<false>(X2, t, [&](int i, int j, T acc) { X1[i + j * ld] = acc; });
+        __syncthreads();
+        T* tmp = t; t = X1; X1 = tmp;
+        expk = expk * expk;                                               // :164
     }
 }
 
-template <typename T, int TM>
-__global__ void __launch_bounds__(256) k_layer(ColArgs<T> a, unsigned int total) {
+constexpr int kLayerMats = 4;
+constexpr int kAddMats = 9;
+// vector scratch (in units of n elements of T) shared by both kernels: 6 vectors + vec(5) + part(8)
+constexpr int kVecUnits = 19;
+
+template <typename T, class Ops, int NN, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_layer(ColArgs<T> a, unsigned int total) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = a.N, ld = a.ld;
-    const size_t msz = (size_t)ld * n;
+    const int n = NN ? NN : a.N;
+    const int ld = NN ? (NN | 1) : a.ld;
+    const int msz = ld * n;
     T* sm = reinterpret_cast<T*>(smem_raw);
-    Arena<T> ar{sm, a.slab + (size_t)blockIdx.x * a.slab_stride, a.n_smem_mats, msz};
-    T* vbase = sm + (size_t)a.n_smem_mats * msz;
+    const int nsm = NN ? kLayerMats : a.n_smem_mats;
+    T* slab = NN ? sm : a.slab + (size_t)blockIdx.x * a.slab_stride;
+    auto mat = [&](int k) -> T* { return (NN || k < nsm) ? sm + k * msz : slab + (size_t)(k - nsm) * msz; };
+    T* vbase = sm + nsm * msz;
     T* jp = vbase;           T* jm = jp + n;     T* j1p = jm + n;   T* j1m = j1p + n;
-    T* v1 = j1m + n;         T* v2 = v1 + n;     T* vec = v2 + n;   /* 3n */
-    T* part = vec + 3 * n;   /* 8n */            T* Wc = part + 8 * n;   /* kMaxComp */
+    T* v1 = j1m + n;         T* v2 = v1 + n;     T* vec = v2 + n;   /* 5n */
+    T* part = vec + 5 * n;   /* 8n */            T* Wc = part + 8 * n;   /* kMaxComp */
     uint32_t* dmask = reinterpret_cast<uint32_t*>(Wc + kMaxComp);
     int* piv = reinterpret_cast<int*>(dmask + n);
     __shared__ unsigned int sh_item;
+    Ops op;
+    if constexpr (NN == 0) { op.n = n; op.ld = ld; }
+    op.vec = vec; op.part = part; op.piv = piv; op.dmask = dmask;
 
     for (int i = threadIdx.x; i < n; i += blockDim.x) dmask[i] = dmask_of(i, a.nStokes);
+    unsigned int nextv = 0;
+    if (threadIdx.x == 0) nextv = atomicAdd(a.counter, 1u);
 
     for (;;) {
-        const unsigned int item = next_item(a.counter, &sh_item);
+        __syncthreads();
+        if (threadIdx.x == 0) sh_item = nextv;
+        __syncthreads();
+        const unsigned int item = sh_item;
         if (item >= total) break;
+        if (threadIdx.x == 0) nextv = atomicAdd(a.counter, 1u);     // prefetch the next work item
         const int p = item % a.nS;
         const unsigned int rest = item / a.nS;
         const int mi = rest % a.Mb;
@@ -286,25 +302,24 @@ __global__ void __launch_bounds__(256) k_layer(ColArgs<T> a, unsigned int total)
         const T expk = Num<T>::exp_(-dtau / a.mu0);        // init_layer (rt_kernel.jl:347)
         if (threadIdx.x < a.nC) Wc[threadIdx.x] = a.p_W[((size_t)threadIdx.x * a.Nz + iz) * a.nS + p];
         __syncthreads();
-        T* r = ar.mat(0); T* t = ar.mat(1); T* X1 = ar.mat(2); T* X2 = ar.mat(3); T* X3 = ar.mat(4);
+        T* r = mat(0); T* t = mat(1); T* X1 = mat(2); T* X2 = mat(3);
         const size_t zstride = (size_t)n * n;
-        const T* Zpp = a.Zpp + (size_t)m * a.nC * zstride;
-        const T* Zmp = a.Zmp + (size_t)m * a.nC * zstride;
-        elemental_fill<T>(a, m, nd, dtau, varpi, tausum, Wc, Zpp, Zmp, zstride,
-                          a.F0 + (a.F0_off + p) * a.nStokes, dmask, r, t, jp, jm);
+        const T* Zpp = a.Zpp + (size_t)(m - a.mz0) * a.nC * zstride + (a.z_spectral ? p * zstride : 0);
+        const T* Zmp = a.Zmp + (size_t)(m - a.mz0) * a.nC * zstride + (a.z_spectral ? p * zstride : 0);
+        elemental_fill<T, NN>(a, m, nd, dtau, varpi, tausum, Wc, Zpp, Zmp, zstride,
+                              a.F0 + (a.F0_off + p) * a.nStokes, dmask, r, t, jp, jm);
         __syncthreads();
-        doubling_loop<T, TM>(n, ld, nd, expk, r, t, X1, X2, X3, jp, jm, j1p, j1m, v1, v2, vec, part,
-                             piv, dmask);
+        doubling_loop<T, Ops>(op, nd, expk, r, t, X1, X2, jp, jm, j1p, j1m, v1, v2);
         // apply_D_matrix! / apply_D_matrix_SFI! (doubling.jl:178-216): r⁻⁺ <- D r*, j₀⁻ <- D j*
         const size_t slot = ((size_t)mi * a.Nz + iz) * a.nS + p;
         T* gr = a.add_r + slot * zstride;
         T* gt = a.add_t + slot * zstride;
         for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
             const int i = e % n, j = e / n;
-            T rv = r[i + (size_t)j * ld];
+            T rv = r[i + j * ld];
             if (nd >= 1) rv = Num<T>::flip(rv, dmask[i]);
             gr[e] = rv;
-            gt[e] = t[i + (size_t)j * ld];
+            gt[e] = t[i + j * ld];
         }
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             T vm = jm[i];
@@ -326,64 +341,64 @@ struct CompPtrs {
     T *RA, *RB, *TC, *TD, *r, *t, *X1, *X2, *X3;
 };
 
-template <typename T, int TM>
-__device__ __forceinline__ void interact(int iface, int n, int ld, CompPtrs<T>& c, T* J0p, T* J0m,
-                                         const T* jp, const T* jm, T* v1, T* vec, T* part,
-                                         int* piv, const uint32_t* dmask, bool rpm_zero,
-                                         bool t_ident) {
-    auto at = [ld](T* M, int i, int j) -> T& { return M[i + (size_t)j * ld]; };
+template <typename T, class Ops>
+__device__ __forceinline__ void interact(const Ops& op, int iface, CompPtrs<T>& c, T* J0p, T* J0m,
+                                         const T* jp, const T* jm, T* v1, bool rpm_zero, bool t_ident) {
+    const int n = op.N(), ld = op.LD();
+    const uint32_t* dmask = op.dmask;
+    auto at = [ld](T* M, int i, int j) -> T& { return M[i + j * ld]; };
     if (iface == 3) {
         // temp2 = I - r⁻⁺ R⁺⁻ ; temp1 = inv ; T01_inv = T⁻⁻ temp1        (:220-226)
-        cta_mm<T, TM, TM, false>(n, c.r, ld, c.RB, ld, dmask, [&](int i, int j, T acc) {
-            at(c.X1, i, j) = (i == j ? T(1) : T(0)) - acc;
-        });
+        auto build1 = [&]() {
+            op.template mm<false>(c.r, c.RB, [&](int i, int j, T acc) {
+                at(c.X1, i, j) = (i == j ? T(1) : T(0)) - acc;
+            });
+        };
+        build1();
         __syncthreads();
-        cta_inverse<T>(n, c.X1, ld, vec, piv, nullptr);
-        cta_mm<T, TM, TM, false>(n, c.TD, ld, c.X1, ld, dmask,
-                                 [&](int i, int j, T acc) { at(c.X2, i, j) = acc; });
+        op.inverse(c.X1, build1);
+        op.template mm<false>(c.TD, c.X1, [&](int i, int j, T acc) { at(c.X2, i, j) = acc; });
         // J₀⁻ += T01_inv (r⁻⁺ J₀⁺ + j₀⁻)                                   (:229)
-        cta_mv<T, false>(n, c.r, ld, J0p, dmask, part, [&](int i, T s) { v1[i] = s + jm[i]; });
-        cta_mv<T, false>(n, c.X2, ld, v1, dmask, part, [&](int i, T s) { J0m[i] = J0m[i] + s; });
+        op.template mv<false>(c.r, J0p, [&](int i, T s) { v1[i] = s + jm[i]; });
+        op.template mv<false>(c.X2, v1, [&](int i, T s) { J0m[i] = J0m[i] + s; });
         // R⁻⁺ += T01_inv r⁻⁺ T⁺⁺                                          (:237)
-        cta_mm<T, TM, TM, false>(n, c.X2, ld, c.r, ld, dmask,
-                                 [&](int i, int j, T acc) { at(c.X3, i, j) = acc; });
+        op.template mm<false>(c.X2, c.r, [&](int i, int j, T acc) { at(c.X3, i, j) = acc; });
         __syncthreads();
-        cta_mm<T, TM, TM, false>(n, c.X3, ld, c.TC, ld, dmask,
-                                 [&](int i, int j, T acc) { at(c.RA, i, j) += acc; });
+        op.template mm<false>(c.X3, c.TC, [&](int i, int j, T acc) { at(c.RA, i, j) += acc; });
         // T⁻⁻ = T01_inv t⁻⁻                                               (:240)
         if (t_ident) {
             T* tmp = c.TD; c.TD = c.X2; c.X2 = tmp;
         } else {
-            cta_mm<T, TM, TM, true>(n, c.X2, ld, c.t, ld, dmask, [&](int i, int j, T acc) {
+            op.template mm<true>(c.X2, c.t, [&](int i, int j, T acc) {
                 at(c.TD, i, j) = Num<T>::flip(acc, dmask[j]);
             });
         }
         __syncthreads();
         // temp2 = I - R⁺⁻ r⁻⁺ ; inv ; T21_inv = t⁺⁺ temp1                  (:248-251)
-        cta_mm<T, TM, TM, false>(n, c.RB, ld, c.r, ld, dmask, [&](int i, int j, T acc) {
-            at(c.X1, i, j) = (i == j ? T(1) : T(0)) - acc;
-        });
+        auto build2 = [&]() {
+            op.template mm<false>(c.RB, c.r, [&](int i, int j, T acc) {
+                at(c.X1, i, j) = (i == j ? T(1) : T(0)) - acc;
+            });
+        };
+        build2();
         __syncthreads();
-        cta_inverse<T>(n, c.X1, ld, vec, piv, nullptr);
+        op.inverse(c.X1, build2);
         T* T21;
         if (t_ident) {
             T21 = c.X1;
         } else {
-            cta_mm<T, TM, TM, false>(n, c.t, ld, c.X1, ld, dmask,
-                                     [&](int i, int j, T acc) { at(c.X2, i, j) = acc; });
+            op.template mm<false>(c.t, c.X1, [&](int i, int j, T acc) { at(c.X2, i, j) = acc; });
             T21 = c.X2;
         }
         // J₀⁺ = j₀⁺ + T21_inv (J₀⁺ + R⁺⁻ j₀⁻)                              (:254)
-        cta_mv<T, false>(n, c.RB, ld, jm, dmask, part, [&](int i, T s) { v1[i] = J0p[i] + s; });
-        cta_mv<T, false>(n, T21, ld, v1, dmask, part, [&](int i, T s) { J0p[i] = jp[i] + s; });
+        op.template mv<false>(c.RB, jm, [&](int i, T s) { v1[i] = J0p[i] + s; });
+        op.template mv<false>(T21, v1, [&](int i, T s) { J0p[i] = jp[i] + s; });
         // T⁺⁺ = T21_inv T⁺⁺                                               (:262)
-        cta_mm<T, TM, TM, false>(n, T21, ld, c.TC, ld, dmask,
-                                 [&](int i, int j, T acc) { at(c.X3, i, j) = acc; });
+        op.template mm<false>(T21, c.TC, [&](int i, int j, T acc) { at(c.X3, i, j) = acc; });
         __syncthreads();
         { T* tmp = c.TC; c.TC = c.X3; c.X3 = tmp; }
         // R⁺⁻ = r⁺⁻ + T21_inv R⁺⁻ t⁻⁻                                      (:265)
-        cta_mm<T, TM, TM, false>(n, T21, ld, c.RB, ld, dmask,
-                                 [&](int i, int j, T acc) { at(c.X3, i, j) = acc; });
+        op.template mm<false>(T21, c.RB, [&](int i, int j, T acc) { at(c.X3, i, j) = acc; });
         __syncthreads();
         if (t_ident) {
             if (rpm_zero) {
@@ -395,7 +410,7 @@ __device__ __forceinline__ void interact(int iface, int n, int ld, CompPtrs<T>& 
                 }
             }
         } else {
-            cta_mm<T, TM, TM, true>(n, c.X3, ld, c.t, ld, dmask, [&](int i, int j, T acc) {
+            op.template mm<true>(c.X3, c.t, [&](int i, int j, T acc) {
                 const T rpm = rpm_zero ? T(0) : Num<T>::flip(at(c.r, i, j), dmask[i] ^ dmask[j]);
                 at(c.RB, i, j) = rpm + Num<T>::flip(acc, dmask[j]);
             });
@@ -403,30 +418,27 @@ __device__ __forceinline__ void interact(int iface, int n, int ld, CompPtrs<T>& 
         __syncthreads();
     } else if (iface == 1) {
         // J₀⁻ += T⁻⁻ (r⁻⁺ J₀⁺ + j₀⁻) ; J₀⁺ = j₀⁺ + t⁺⁺ J₀⁺                  (:104-105)
-        cta_mv<T, false>(n, c.r, ld, J0p, dmask, part, [&](int i, T s) { v1[i] = s + jm[i]; });
-        cta_mv<T, false>(n, c.TD, ld, v1, dmask, part, [&](int i, T s) { J0m[i] = J0m[i] + s; });
+        op.template mv<false>(c.r, J0p, [&](int i, T s) { v1[i] = s + jm[i]; });
+        op.template mv<false>(c.TD, v1, [&](int i, T s) { J0m[i] = J0m[i] + s; });
         if (t_ident) {
             for (int i = threadIdx.x; i < n; i += blockDim.x) J0p[i] = jp[i] + J0p[i];
             __syncthreads();
         } else {
-            cta_mv<T, false>(n, c.t, ld, J0p, dmask, part, [&](int i, T s) { v1[i] = jp[i] + s; });
+            op.template mv<false>(c.t, J0p, [&](int i, T s) { v1[i] = jp[i] + s; });
             for (int i = threadIdx.x; i < n; i += blockDim.x) J0p[i] = v1[i];
             __syncthreads();
         }
         // R⁻⁺ = T⁻⁻ r⁻⁺ T⁺⁺ ; R⁺⁻ = r⁺⁻ ; T⁺⁺ = t⁺⁺ T⁺⁺ ; T⁻⁻ = T⁻⁻ t⁻⁻     (:114-117)
-        cta_mm<T, TM, TM, false>(n, c.TD, ld, c.r, ld, dmask,
-                                 [&](int i, int j, T acc) { at(c.X3, i, j) = acc; });
+        op.template mm<false>(c.TD, c.r, [&](int i, int j, T acc) { at(c.X3, i, j) = acc; });
         __syncthreads();
-        cta_mm<T, TM, TM, false>(n, c.X3, ld, c.TC, ld, dmask,
-                                 [&](int i, int j, T acc) { at(c.RA, i, j) = acc; });
+        op.template mm<false>(c.X3, c.TC, [&](int i, int j, T acc) { at(c.RA, i, j) = acc; });
         for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
             const int i = e % n, j = e / n;
             at(c.RB, i, j) = rpm_zero ? T(0) : Num<T>::flip(at(c.r, i, j), dmask[i] ^ dmask[j]);
         }
         if (!t_ident) {
-            cta_mm<T, TM, TM, false>(n, c.t, ld, c.TC, ld, dmask,
-                                     [&](int i, int j, T acc) { at(c.X1, i, j) = acc; });
-            cta_mm<T, TM, TM, true>(n, c.TD, ld, c.t, ld, dmask, [&](int i, int j, T acc) {
+            op.template mm<false>(c.t, c.TC, [&](int i, int j, T acc) { at(c.X1, i, j) = acc; });
+            op.template mm<true>(c.TD, c.t, [&](int i, int j, T acc) {
                 at(c.X2, i, j) = Num<T>::flip(acc, dmask[j]);
             });
             __syncthreads();
@@ -436,27 +448,25 @@ __device__ __forceinline__ void interact(int iface, int n, int ld, CompPtrs<T>& 
         __syncthreads();
     } else if (iface == 2) {
         // J₀⁺ = j₀⁺ + t⁺⁺ (J₀⁺ + R⁺⁻ j₀⁻) ; J₀⁻ += T⁻⁻ j₀⁻                  (:149-150)
-        cta_mv<T, false>(n, c.RB, ld, jm, dmask, part, [&](int i, T s) { v1[i] = J0p[i] + s; });
+        op.template mv<false>(c.RB, jm, [&](int i, T s) { v1[i] = J0p[i] + s; });
         if (t_ident) {
             for (int i = threadIdx.x; i < n; i += blockDim.x) J0p[i] = jp[i] + v1[i];
             __syncthreads();
         } else {
-            cta_mv<T, false>(n, c.t, ld, v1, dmask, part, [&](int i, T s) { J0p[i] = jp[i] + s; });
+            op.template mv<false>(c.t, v1, [&](int i, T s) { J0p[i] = jp[i] + s; });
         }
-        cta_mv<T, false>(n, c.TD, ld, jm, dmask, part, [&](int i, T s) { J0m[i] = J0m[i] + s; });
+        op.template mv<false>(c.TD, jm, [&](int i, T s) { J0m[i] = J0m[i] + s; });
         // T⁺⁺ = t⁺⁺ T⁺⁺ ; T⁻⁻ = T⁻⁻ t⁻⁻ ; R⁺⁻ = t⁺⁺ R⁺⁻ t⁻⁻                  (:159-161)
         if (!t_ident) {
-            cta_mm<T, TM, TM, false>(n, c.t, ld, c.TC, ld, dmask,
-                                     [&](int i, int j, T acc) { at(c.X1, i, j) = acc; });
-            cta_mm<T, TM, TM, true>(n, c.TD, ld, c.t, ld, dmask, [&](int i, int j, T acc) {
+            op.template mm<false>(c.t, c.TC, [&](int i, int j, T acc) { at(c.X1, i, j) = acc; });
+            op.template mm<true>(c.TD, c.t, [&](int i, int j, T acc) {
                 at(c.X2, i, j) = Num<T>::flip(acc, dmask[j]);
             });
-            cta_mm<T, TM, TM, false>(n, c.t, ld, c.RB, ld, dmask,
-                                     [&](int i, int j, T acc) { at(c.X3, i, j) = acc; });
+            op.template mm<false>(c.t, c.RB, [&](int i, int j, T acc) { at(c.X3, i, j) = acc; });
             __syncthreads();
             T* tmp = c.TC; c.TC = c.X1; c.X1 = tmp;
             tmp = c.TD; c.TD = c.X2; c.X2 = tmp;
-            cta_mm<T, TM, TM, true>(n, c.X3, ld, c.t, ld, dmask, [&](int i, int j, T acc) {
+            op.template mm<true>(c.X3, c.t, [&](int i, int j, T acc) {
                 at(c.RB, i, j) = Num<T>::flip(acc, dmask[j]);
             });
         }
@@ -467,18 +477,17 @@ __device__ __forceinline__ void interact(int iface, int n, int ld, CompPtrs<T>& 
             for (int i = threadIdx.x; i < n; i += blockDim.x) J0p[i] = jp[i] + J0p[i];
             __syncthreads();
         } else {
-            cta_mv<T, false>(n, c.t, ld, J0p, dmask, part, [&](int i, T s) { v1[i] = jp[i] + s; });
+            op.template mv<false>(c.t, J0p, [&](int i, T s) { v1[i] = jp[i] + s; });
             for (int i = threadIdx.x; i < n; i += blockDim.x) J0p[i] = v1[i];
             __syncthreads();
         }
-        cta_mv<T, false>(n, c.TD, ld, jm, dmask, part, [&](int i, T s) { J0m[i] = J0m[i] + s; });
+        op.template mv<false>(c.TD, jm, [&](int i, T s) { J0m[i] = J0m[i] + s; });
         if (!t_ident) {
             // t⁻⁻ T⁻⁻ = D t D T⁻⁻ : row sign D_i outside, D_k inside
-            cta_mm<T, TM, TM, true>(n, c.t, ld, c.TD, ld, dmask, [&](int i, int j, T acc) {
+            op.template mm<true>(c.t, c.TD, [&](int i, int j, T acc) {
                 at(c.X2, i, j) = Num<T>::flip(acc, dmask[i]);
             });
-            cta_mm<T, TM, TM, false>(n, c.t, ld, c.TC, ld, dmask,
-                                     [&](int i, int j, T acc) { at(c.X1, i, j) = acc; });
+            op.template mm<false>(c.t, c.TC, [&](int i, int j, T acc) { at(c.X1, i, j) = acc; });
             __syncthreads();
             T* tmp = c.TC; c.TC = c.X1; c.X1 = tmp;
             tmp = c.TD; c.TD = c.X2; c.X2 = tmp;
@@ -487,33 +496,44 @@ __device__ __forceinline__ void interact(int iface, int n, int ld, CompPtrs<T>& 
     }
 }
 
-template <typename T, int TM>
+template <typename T, class Ops, int NN>
 __global__ void __launch_bounds__(256) k_adding(ColArgs<T> a, unsigned int total) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = a.N, ld = a.ld;
-    const size_t msz = (size_t)ld * n;
+    const int n = NN ? NN : a.N;
+    const int ld = NN ? (NN | 1) : a.ld;
+    const int msz = ld * n;
     T* sm = reinterpret_cast<T*>(smem_raw);
-    Arena<T> ar{sm, a.slab + (size_t)blockIdx.x * a.slab_stride, a.n_smem_mats, msz};
-    T* vbase = sm + (size_t)a.n_smem_mats * msz;
+    const int nsm = NN ? kAddMats : a.n_smem_mats;
+    T* slab = NN ? sm : a.slab + (size_t)blockIdx.x * a.slab_stride;
+    auto mat = [&](int k) -> T* { return (NN || k < nsm) ? sm + k * msz : slab + (size_t)(k - nsm) * msz; };
+    T* vbase = sm + nsm * msz;
     T* J0p = vbase;         T* J0m = J0p + n;   T* jp = J0m + n;   T* jm = jp + n;
-    T* v1 = jm + n;         T* hv = v1 + n;     T* vec = hv + n;   /* 3n */
-    T* part = vec + 3 * n;  /* 8n */
+    T* v1 = jm + n;         T* hv = v1 + n;     T* vec = hv + n;   /* 5n */
+    T* part = vec + 5 * n;  /* 8n */
     uint32_t* dmask = reinterpret_cast<uint32_t*>(part + 8 * n);
     int* piv = reinterpret_cast<int*>(dmask + n);
     __shared__ unsigned int sh_item;
     const size_t zstride = (size_t)n * n;
     const int nOut = a.nVZA * a.nStokes;
+    Ops op;
+    if constexpr (NN == 0) { op.n = n; op.ld = ld; }
+    op.vec = vec; op.part = part; op.piv = piv; op.dmask = dmask;
 
     for (int i = threadIdx.x; i < n; i += blockDim.x) dmask[i] = dmask_of(i, a.nStokes);
+    unsigned int nextv = 0;
+    if (threadIdx.x == 0) nextv = atomicAdd(a.counter, 1u);
 
     for (;;) {
-        const unsigned int item = next_item(a.counter, &sh_item);
+        __syncthreads();
+        if (threadIdx.x == 0) sh_item = nextv;
+        __syncthreads();
+        const unsigned int item = sh_item;
         if (item >= total) break;
+        if (threadIdx.x == 0) nextv = atomicAdd(a.counter, 1u);
         const int p = item % a.nS;
         const int mi = item / a.nS;
         const int m = a.m0 + mi;
-        CompPtrs<T> c{ar.mat(0), ar.mat(1), ar.mat(2), ar.mat(3), ar.mat(4),
-                      ar.mat(5), ar.mat(6), ar.mat(7), ar.mat(8)};
+        CompPtrs<T> c{mat(0), mat(1), mat(2), mat(3), mat(4), mat(5), mat(6), mat(7), mat(8)};
         for (int iz = 0; iz < a.Nz; ++iz) {
             const bool sc = a.scatter[iz] != 0;
             T* dr = (iz == 0) ? c.RA : c.r;
@@ -526,8 +546,8 @@ __global__ void __launch_bounds__(256) k_adding(ColArgs<T> a, unsigned int total
                 const T* gt = a.add_t + slot * zstride;
                 for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
                     const int i = e % n, j = e / n;
-                    dr[i + (size_t)j * ld] = gr[e];
-                    dt[i + (size_t)j * ld] = gt[e];
+                    dr[i + j * ld] = gr[e];
+                    dt[i + j * ld] = gt[e];
                 }
                 for (int i = threadIdx.x; i < n; i += blockDim.x) {
                     djp[i] = a.add_jp[slot * n + i];
@@ -538,8 +558,8 @@ __global__ void __launch_bounds__(256) k_adding(ColArgs<T> a, unsigned int total
                 const T tau = a.p_tau[(size_t)iz * a.nS + p];
                 for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
                     const int i = e % n, j = e / n;
-                    dr[i + (size_t)j * ld] = T(0);
-                    dt[i + (size_t)j * ld] = (i == j) ? Num<T>::exp_(-tau / a.mu[i]) : T(0);
+                    dr[i + j * ld] = T(0);
+                    dt[i + j * ld] = (i == j) ? Num<T>::exp_(-tau / a.mu[i]) : T(0);
                 }
                 for (int i = threadIdx.x; i < n; i += blockDim.x) { djp[i] = T(0); djm[i] = T(0); }
             }
@@ -549,13 +569,12 @@ __global__ void __launch_bounds__(256) k_adding(ColArgs<T> a, unsigned int total
                 for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
                     const int i = e % n, j = e / n;
                     const uint32_t s = dmask[i] ^ dmask[j];
-                    c.RB[i + (size_t)j * ld] = sc ? Num<T>::flip(c.RA[i + (size_t)j * ld], s) : T(0);
-                    c.TD[i + (size_t)j * ld] = Num<T>::flip(c.TC[i + (size_t)j * ld], s);
+                    c.RB[i + j * ld] = sc ? Num<T>::flip(c.RA[i + j * ld], s) : T(0);
+                    c.TD[i + j * ld] = Num<T>::flip(c.TC[i + j * ld], s);
                 }
                 __syncthreads();
             } else {
-                interact<T, TM>(a.iface[iz], n, ld, c, J0p, J0m, jp, jm, v1, vec, part, piv, dmask,
-                                !sc, false);
+                interact<T, Ops>(op, a.iface[iz], c, J0p, J0m, jp, jm, v1, !sc, false);
             }
         }
         // ---- Lambertian surface (lambertian_surface.jl:41-95) + last interaction (rt_run.jl:459-465)
@@ -567,7 +586,7 @@ __global__ void __launch_bounds__(256) k_adding(ColArgs<T> a, unsigned int total
             for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
                 const int i = e % n, j = e / n;
                 const bool ii = (i % a.nStokes) == 0 && (j % a.nStokes) == 0;
-                c.r[i + (size_t)j * ld] = ii ? rho * (a.mu[j] * a.wt[j]) : T(0);
+                c.r[i + j * ld] = ii ? rho * (a.mu[j] * a.wt[j]) : T(0);
             }
             for (int i = threadIdx.x; i < n; i += blockDim.x) {
                 jp[i] = (i == a.istart) ? att : T(0);
@@ -575,10 +594,9 @@ __global__ void __launch_bounds__(256) k_adding(ColArgs<T> a, unsigned int total
             }
             jps_sun = att;
             __syncthreads();
-            interact<T, TM>(a.iface[a.Nz - 1], n, ld, c, J0p, J0m, jp, jm, v1, vec, part, piv, dmask,
-                            true, true);
+            interact<T, Ops>(op, a.iface[a.Nz - 1], c, J0p, J0m, jp, jm, v1, true, true);
             // interaction_hdrf!: hdr_J₀⁻ = r⁻⁺ J₀⁺ + j₀⁻
-            cta_mv<T, false>(n, c.r, ld, J0p, dmask, part, [&](int i, T s) { hv[i] = s + jm[i]; });
+            op.template mv<false>(c.r, J0p, [&](int i, T s) { hv[i] = s + jm[i]; });
         } else {
             for (int i = threadIdx.x; i < n; i += blockDim.x) hv[i] = T(0);
             __syncthreads();

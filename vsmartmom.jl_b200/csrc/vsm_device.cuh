@@ -230,4 +230,232 @@ __device__ __forceinline__ void cta_inverse(int n, T* __restrict__ M, int ld,
     __syncthreads();
 }
 
+// ==========================================================================
+// Ops policies.  The fused kernels are written against an Ops object providing
+//   mm<KSIGN>(A, B, epi), mv<KSIGN>(A, x, epi), mv2(A, x1, x2, epi1, epi2),
+//   inverse(M, rebuild)
+// OpsGeneric: run-time N, generic (shared-or-global) pointers, any size.
+// OpsFast   : compile-time N (NN), exact TMxTM tiling with one register tile per
+//             thread, everything in shared memory.
+// ==========================================================================
+template <typename T, int TM>
+struct OpsGeneric {
+    int n, ld;
+    T* vec;                  // >= 5n
+    T* part;                 // >= 8n
+    int* piv;                // >= n+4
+    const uint32_t* dmask;
+    __device__ __forceinline__ int N() const { return n; }
+    __device__ __forceinline__ int LD() const { return ld; }
+    template <bool KSIGN, class Epi>
+    __device__ __forceinline__ void mm(const T* A, const T* B, Epi epi) const {
+        cta_mm<T, TM, TM, KSIGN>(n, A, ld, B, ld, dmask, epi);
+    }
+    template <bool KSIGN, class Epi>
+    __device__ __forceinline__ void mv(const T* A, const T* x, Epi epi) const {
+        cta_mv<T, KSIGN>(n, A, ld, x, dmask, part, epi);
+    }
+    template <class E1, class E2>
+    __device__ __forceinline__ void mv2(const T* A, const T* x1, const T* x2, E1 e1, E2 e2) const {
+        cta_mv<T, false>(n, A, ld, x1, dmask, part, e1);
+        cta_mv<T, false>(n, A, ld, x2, dmask, part, e2);
+    }
+    template <class Rebuild>
+    __device__ __forceinline__ void inverse(T* M, Rebuild) const {
+        cta_inverse<T>(n, M, ld, vec, piv, nullptr);
+    }
+};
+
+template <typename T, int TM, int NN>
+struct OpsFast {
+    static_assert(NN % TM == 0, "OpsFast needs exact tiling");
+    static constexpr int NT = NN / TM;            // tiles per dimension
+    static_assert(NT * NT <= 256, "one register tile per thread");
+    static constexpr int kLd = NN | 1;
+    static constexpr int RP = (NN + 31) & ~31;    // rows padded to whole warps for mv
+    T* vec;                  // >= 5*NN : colb[2][NN] rowb[2][NN] ipv[2]
+    T* part;                 // >= 8*NN
+    int* piv;                // >= NN+4 ; piv[NN] = "unsafe pivot" flag
+    const uint32_t* dmask;
+    __device__ __forceinline__ constexpr int N() const { return NN; }
+    __device__ __forceinline__ constexpr int LD() const { return kLd; }
+
+    template <bool KSIGN, class Epi>
+    __device__ __forceinline__ void mm(const T* __restrict__ A, const T* __restrict__ B, Epi epi) const {
+        const int tid = threadIdx.x;
+        if (tid < NT * NT) {
+            const int i0 = (tid % NT) * TM, j0 = (tid / NT) * TM;
+            const T* Ap = A + i0;
+            const T* Bp = B + j0 * kLd;
+            T acc[TM][TM];
+#pragma unroll
+            for (int x = 0; x < TM; ++x)
+#pragma unroll
+                for (int y = 0; y < TM; ++y) acc[x][y] = T(0);
+#pragma unroll 9
+            for (int k = 0; k < NN; ++k) {
+                T a[TM], b[TM];
+#pragma unroll
+                for (int x = 0; x < TM; ++x) a[x] = Ap[k * kLd + x];
+#pragma unroll
+                for (int y = 0; y < TM; ++y) b[y] = Bp[y * kLd + k];
+                if (KSIGN) {
+                    const uint32_t mk = dmask[k];
+#pragma unroll
+                    for (int x = 0; x < TM; ++x) a[x] = Num<T>::flip(a[x], mk);
+                }
+#pragma unroll
+                for (int x = 0; x < TM; ++x)
+#pragma unroll
+                    for (int y = 0; y < TM; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+            }
+#pragma unroll
+            for (int y = 0; y < TM; ++y)
+#pragma unroll
+                for (int x = 0; x < TM; ++x) epi(i0 + x, j0 + y, acc[x][y]);
+        }
+    }
+
+    // y = A x (one or two right-hand sides), k split over blockDim/RP segments
+    template <bool KSIGN, int NV, class E1, class E2>
+    __device__ __forceinline__ void mv_impl(const T* __restrict__ A, const T* __restrict__ x1,
+                                            const T* __restrict__ x2, E1 e1, E2 e2) const {
+        constexpr int NSEG = (256 / RP) < 1 ? 1 : (256 / RP);
+        constexpr int KL = (NN + NSEG - 1) / NSEG;
+        const int tid = threadIdx.x;
+        const int seg = tid / RP, i = tid % RP;
+        if (seg < NSEG && i < NN) {
+            const int k0 = seg * KL;
+            T s1 = T(0), s2 = T(0);
+#pragma unroll 4
+            for (int kk = 0; kk < KL; ++kk) {
+                const int k = k0 + kk;
+                if (k < NN) {
+                    const T av = A[i + k * kLd];
+                    T xv = x1[k];
+                    if (KSIGN) xv = Num<T>::flip(xv, dmask[k]);
+                    s1 = fma(av, xv, s1);
+                    if (NV == 2) s2 = fma(av, x2[k], s2);
+                }
+            }
+            part[seg * NN + i] = s1;
+            if (NV == 2) part[(NSEG + seg) * NN + i] = s2;
+        }
+        __syncthreads();
+        if (tid < NN) {
+            T s = part[tid];
+#pragma unroll
+            for (int g = 1; g < NSEG; ++g) s += part[g * NN + tid];
+            e1(tid, s);
+        } else if (NV == 2 && tid >= 64 && tid < 64 + NN) {
+            const int r = tid - 64;
+            T s = part[NSEG * NN + r];
+#pragma unroll
+            for (int g = 1; g < NSEG; ++g) s += part[(NSEG + g) * NN + r];
+            e2(r, s);
+        }
+        __syncthreads();
+    }
+    template <bool KSIGN, class Epi>
+    __device__ __forceinline__ void mv(const T* A, const T* x, Epi epi) const {
+        mv_impl<KSIGN, 1>(A, x, x, epi, epi);
+    }
+    template <class E1, class E2>
+    __device__ __forceinline__ void mv2(const T* A, const T* x1, const T* x2, E1 e1, E2 e2) const {
+        static_assert(NN <= 64, "mv2 epilogue layout");
+        mv_impl<false, 2>(A, x1, x2, e1, e2);
+    }
+
+    // In-place inverse.  Register-resident Gauss-Jordan on the diagonal pivots, one
+    // barrier per step; every multiplier is checked against the threshold-pivoting
+    // bound |a_ik| <= 4|a_kk|.  If a step violates it (or a pivot is zero/NaN) the
+    // matrix is rebuilt by `rebuild()` and inverted by the partial-pivoting routine,
+    // so the result is always that of a pivoted, backward-stable elimination.
+    template <class Rebuild>
+    __device__ __forceinline__ void inverse(T* __restrict__ M, Rebuild rebuild) const {
+        T* colb = vec;
+        T* rowb = vec + 2 * NN;
+        T* ipvb = vec + 4 * NN;
+        int* bad = piv + NN;
+        const int tid = threadIdx.x;
+        const bool act = tid < NT * NT;
+        const int i0 = (tid % NT) * TM, j0 = (tid / NT) * TM;
+        T m[TM][TM];
+        if (tid == 0) *bad = 0;
+        if (act) {
+#pragma unroll
+            for (int y = 0; y < TM; ++y)
+#pragma unroll
+                for (int x = 0; x < TM; ++x) m[x][y] = M[(i0 + x) + (j0 + y) * kLd];
+            if (j0 == 0) {
+#pragma unroll
+                for (int x = 0; x < TM; ++x) colb[i0 + x] = m[x][0];
+            }
+            if (i0 == 0) {
+#pragma unroll
+                for (int y = 0; y < TM; ++y) rowb[j0 + y] = m[0][y];
+            }
+            if (i0 == 0 && j0 == 0) ipvb[0] = T(1) / m[0][0];
+        }
+        __syncthreads();
+        bool mybad = false;
+#pragma unroll 1
+        for (int k = 0; k < NN; ++k) {
+            const int cur = (k & 1) * NN, nxt = NN - cur;
+            if (act) {
+                const T ipv = ipvb[k & 1];
+                const T lim = T(4) * Num<T>::abs_(colb[cur + k]);
+                T c[TM], r[TM];
+#pragma unroll
+                for (int x = 0; x < TM; ++x) c[x] = colb[cur + i0 + x];
+#pragma unroll
+                for (int y = 0; y < TM; ++y) r[y] = (j0 + y == k) ? ipv : rowb[cur + j0 + y] * ipv;
+#pragma unroll
+                for (int x = 0; x < TM; ++x)
+                    if (i0 + x != k && !(Num<T>::abs_(c[x]) <= lim)) mybad = true;
+#pragma unroll
+                for (int x = 0; x < TM; ++x)
+#pragma unroll
+                    for (int y = 0; y < TM; ++y) {
+                        const T base = (j0 + y == k) ? T(0) : m[x][y];
+                        const T v = fma(-c[x], r[y], base);
+                        m[x][y] = (i0 + x == k) ? r[y] : v;
+                    }
+                const int k1 = k + 1;
+                if (k1 < NN) {
+#pragma unroll
+                    for (int y = 0; y < TM; ++y)
+                        if (j0 + y == k1) {
+#pragma unroll
+                            for (int x = 0; x < TM; ++x) colb[nxt + i0 + x] = m[x][y];
+                        }
+#pragma unroll
+                    for (int x = 0; x < TM; ++x)
+                        if (i0 + x == k1) {
+#pragma unroll
+                            for (int y = 0; y < TM; ++y) {
+                                rowb[nxt + j0 + y] = m[x][y];
+                                if (j0 + y == k1) ipvb[k1 & 1] = T(1) / m[x][y];
+                            }
+                        }
+                }
+            }
+            __syncthreads();
+        }
+        if (mybad) *bad = 1;
+        if (act) {
+#pragma unroll
+            for (int y = 0; y < TM; ++y)
+#pragma unroll
+                for (int x = 0; x < TM; ++x) M[(i0 + x) + (j0 + y) * kLd] = m[x][y];
+        }
+        __syncthreads();
+        if (*bad) {                       // uniform: taken by the whole CTA or not at all
+            rebuild();
+            __syncthreads();
+            cta_inverse<T>(NN, M, kLd, vec, piv, nullptr);
+        }
+    }
+};
+
 }  // namespace vsm

@@ -1,5 +1,5 @@
 #define VSM_T float
 #define VSM_TM 3
-#define VSM_NN 0
-#define VSM_MINB 1
+#define VSM_NN 45
+#define VSM_MINB 3
 #include "vsm_inst.inc"

@@ -1,13 +1,20 @@
-// vsm_launch.cuh -- per-(precision, tile) kernel instantiations live in their own
-// translation units (vsm_inst_*.cu) so the library builds in parallel.
+// vsm_launch.cuh -- per-(precision, tile, size) kernel instantiations live in their
+// own translation units (vsm_inst_*.cu) so the library builds in parallel.
+//   NN = 0 : run-time N, generic arena (any size; spills to a global slab)
+//   NN > 0 : compile-time N, one register tile per thread, all-shared-memory arena
 #pragma once
 #include "vsm_column.cuh"
 
 namespace vsm {
-template <typename T, int TM>
+template <typename T, int TM, int NN>
 cudaError_t launch_layer(cudaStream_t s, const ColArgs<T>& a, unsigned total, int grid, int threads, size_t smem);
-template <typename T, int TM>
+template <typename T, int TM, int NN>
 cudaError_t launch_adding(cudaStream_t s, const ColArgs<T>& a, unsigned total, int grid, int threads, size_t smem);
-template <typename T, int TM>
+template <typename T, int TM, int NN>
 void kernel_ptrs(const void** layer, const void** adding);
+
+template <typename T, int TM, int NN>
+struct OpsSel { using type = OpsFast<T, TM, NN>; };
+template <typename T, int TM>
+struct OpsSel<T, TM, 0> { using type = OpsGeneric<T, TM>; };
 }  // namespace vsm
