@@ -298,7 +298,7 @@ static int do_launch(vsm_ctx* ctx, bool layer, int tm, bool fast, int N, const C
     cudaError_t e = cudaSuccess;
 #define VSM_L(TM_, NN_) (layer ? launch_layer<T, TM_, NN_>(ctx->stream, a, total, grid, threads, smem) \
                                : launch_adding<T, TM_, NN_>(ctx->stream, a, total, grid, threads, smem))
-    if (fast && N == 45) e = VSM_L(3, 45);
+    if (fast && N == 45) e = VSM_L(5, 45);
     else switch (tm) {
         case 1: e = VSM_L(1, 0); break;
         case 2: e = VSM_L(2, 0); break;
@@ -316,7 +316,7 @@ static int do_launch(vsm_ctx* ctx, bool layer, int tm, bool fast, int N, const C
 
 template <typename T>
 static void get_kernel_ptrs(int tm, bool fast, int N, const void** kl, const void** ka) {
-    if (fast && N == 45) { kernel_ptrs<T, 3, 45>(kl, ka); return; }
+    if (fast && N == 45) { kernel_ptrs<T, 5, 45>(kl, ka); return; }
     switch (tm) {
         case 1: kernel_ptrs<T, 1, 0>(kl, ka); break;
         case 2: kernel_ptrs<T, 2, 0>(kl, ka); break;
@@ -426,8 +426,11 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
     get_kernel_ptrs<T>(cfg.tm, fast, N, &kl, &ka);
     CK(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l_smem));
     CK(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
-    const int l_occ = occupancy<T>(kl, cfg.threads, l_smem);
-    const int a_occ = occupancy<T>(ka, cfg.threads, a_smem);
+    // CTA sizes: the specialised kernels fix theirs at compile time
+    const int l_threads = fast ? 128 : cfg.threads;
+    const int a_threads = fast ? 256 : cfg.threads;
+    const int l_occ = occupancy<T>(kl, l_threads, l_smem);
+    const int a_occ = occupancy<T>(ka, a_threads, a_smem);
     const int l_grid_max = ctx->num_sms * l_occ, a_grid_max = ctx->num_sms * a_occ;
 
     // ---- workspace plan: chunk over spectral points and moments
@@ -529,7 +532,7 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
                 CK(cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
                 cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
                 CK(cudaEventRecord(e0, ctx->stream));
-                rc = do_launch<T>(ctx, true, cfg.tm, fast, N, a, total, grid, cfg.threads, l_smem);
+                rc = do_launch<T>(ctx, true, cfg.tm, fast, N, a, total, grid, l_threads, l_smem);
                 if (rc) return rc;
                 CK(cudaEventRecord(e1, ctx->stream));
                 ctx->seg_layer.push_back({e0, e1});
@@ -544,7 +547,7 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
                 CK(cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
                 cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
                 CK(cudaEventRecord(e0, ctx->stream));
-                rc = do_launch<T>(ctx, false, cfg.tm, fast, N, a, total, grid, cfg.threads, a_smem);
+                rc = do_launch<T>(ctx, false, cfg.tm, fast, N, a, total, grid, a_threads, a_smem);
                 if (rc) return rc;
                 CK(cudaEventRecord(e1, ctx->stream));
                 ctx->seg_add.push_back({e0, e1});

@@ -231,11 +231,11 @@ __device__ __forceinline__ void doubling_loop(const Ops& op, int nd, T expk, T*&
             });
         };
         build();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {               // doubling_source_update!, :131-132
+        for (int i = op.tid; i < n; i += op.nthreads()) {                 // doubling_source_update!, :131-132
             j1p[i] = jp[i] * expk;
             j1m[i] = jm[i] * expk;
         }
-        __syncthreads();
+        op.sync();
         op.inverse(X1, build);                                            // :104
         op.template mm<false>(t, X1, [&](int i, int j, T acc) { X2[i + j * ld] = acc; });   // :105
         // v1 = j1m + r jp ; v2 = jp + r j1m ; jm += tt v1 ; jp = j1p + tt v2          (:133-134)
@@ -243,11 +243,11 @@ __device__ __forceinline__ void doubling_loop(const Ops& op, int nd, T expk, T*&
         op.mv2(X2, v1, v2, [&](int i, T s) { jm[i] = jm[i] + s; }, [&](int i, T s) { jp[i] = j1p[i] + s; });
         // doubling_rt_update! (:162-163)
         op.template mm<false>(r, t, [&](int i, int j, T acc) { X1[i + j * ld] = acc; });
-        __syncthreads();
+        op.sync();
         op.template mm<false>(X2, X1, [&](int i, int j, T acc) { r[i + j * ld] += acc; });
-        __syncthreads();
+        op.sync();
         op.template mm<false>(X2, t, [&](int i, int j, T acc) { X1[i + j * ld] = acc; });
-        __syncthreads();
+        op.sync();
         T* tmp = t; t = X1; X1 = tmp;
         expk = expk * expk;                                               // :164
     }
@@ -258,8 +258,8 @@ constexpr int kAddMats = 9;
 // vector scratch (in units of n elements of T) shared by both kernels: 6 vectors + vec(5) + part(8)
 constexpr int kVecUnits = 19;
 
-template <typename T, class Ops, int NN, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_layer(ColArgs<T> a, unsigned int total) {
+template <typename T, class Ops, int NN, int NTHR, int MINB>
+__global__ void __launch_bounds__(NTHR, MINB) k_layer(ColArgs<T> a, unsigned int total) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = NN ? NN : a.N;
     const int ld = NN ? (NN | 1) : a.ld;
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256, MINB) k_layer(ColArgs<T> a, unsigned int 
     __shared__ unsigned int sh_item;
     Ops op;
     if constexpr (NN == 0) { op.n = n; op.ld = ld; }
-    op.vec = vec; op.part = part; op.piv = piv; op.dmask = dmask;
+    op.vec = vec; op.part = part; op.piv = piv; op.dmask = dmask; op.tid = threadIdx.x; op.bar = 0;
 
     for (int i = threadIdx.x; i < n; i += blockDim.x) dmask[i] = dmask_of(i, a.nStokes);
     unsigned int nextv = 0;
@@ -496,8 +496,8 @@ __device__ __forceinline__ void interact(const Ops& op, int iface, CompPtrs<T>& 
     }
 }
 
-template <typename T, class Ops, int NN>
-__global__ void __launch_bounds__(256) k_adding(ColArgs<T> a, unsigned int total) {
+template <typename T, class Ops, int NN, int NTHR>
+__global__ void __launch_bounds__(NTHR) k_adding(ColArgs<T> a, unsigned int total) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = NN ? NN : a.N;
     const int ld = NN ? (NN | 1) : a.ld;
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(256) k_adding(ColArgs<T> a, unsigned int total
     const int nOut = a.nVZA * a.nStokes;
     Ops op;
     if constexpr (NN == 0) { op.n = n; op.ld = ld; }
-    op.vec = vec; op.part = part; op.piv = piv; op.dmask = dmask;
+    op.vec = vec; op.part = part; op.piv = piv; op.dmask = dmask; op.tid = threadIdx.x; op.bar = 0;
 
     for (int i = threadIdx.x; i < n; i += blockDim.x) dmask[i] = dmask_of(i, a.nStokes);
     unsigned int nextv = 0;

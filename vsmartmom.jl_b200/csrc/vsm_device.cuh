@@ -27,6 +27,15 @@ template <> struct Num<double> {
         int hi = __double2hiint(x) ^ (int)mask;
         return __hiloint2double(hi, __double2loint(x));
     }
+    // branch-free reciprocal for |x| in the normal float range: fp32 seed + 2 Newton steps
+    // in fp64 (23 -> 46 -> 92 bits): <= 1 ulp, no slow-path call on the critical path.
+    __device__ static double rcp(double x) {
+        double r = (double)__frcp_rn((float)x);
+        double e = fma(-x, r, 1.0);
+        r = fma(r, e, r);
+        e = fma(-x, r, 1.0);
+        return fma(r, e, r);
+    }
 };
 template <> struct Num<float> {
     __device__ static float eps() { return 1.1920929e-07f; }
@@ -36,6 +45,7 @@ template <> struct Num<float> {
     __device__ static float flip(float x, uint32_t mask) {
         return __uint_as_float(__float_as_uint(x) ^ mask);
     }
+    __device__ static float rcp(float x) { return __frcp_rn(x); }
 };
 
 // exp(-a) - exp(-b), stable for a ~ b   (rt_helpers.jl:32-40)
@@ -245,8 +255,11 @@ struct OpsGeneric {
     T* part;                 // >= 8n
     int* piv;                // >= n+4
     const uint32_t* dmask;
+    int tid, bar;            // whole CTA: tid = threadIdx.x
     __device__ __forceinline__ int N() const { return n; }
     __device__ __forceinline__ int LD() const { return ld; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ int nthreads() const { return blockDim.x; }
     template <bool KSIGN, class Epi>
     __device__ __forceinline__ void mm(const T* A, const T* B, Epi epi) const {
         cta_mm<T, TM, TM, KSIGN>(n, A, ld, B, ld, dmask, epi);
@@ -266,23 +279,34 @@ struct OpsGeneric {
     }
 };
 
-template <typename T, int TM, int NN>
+// Named barrier over the NTHR threads of one Ops group (bar 0 == __syncthreads when
+// the group is the whole CTA).
+template <int NTHR, int BAR>
+__device__ __forceinline__ void group_sync() {
+    asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NTHR) : "memory");
+}
+
+template <typename T, int TM, int NN, int NTHR, int BAR = 0>
 struct OpsFast {
     static_assert(NN % TM == 0, "OpsFast needs exact tiling");
     static constexpr int NT = NN / TM;            // tiles per dimension
-    static_assert(NT * NT <= 256, "one register tile per thread");
+    static_assert(NT * NT <= NTHR, "one register tile per thread");
     static constexpr int kLd = NN | 1;
     static constexpr int RP = (NN + 31) & ~31;    // rows padded to whole warps for mv
+    static_assert(NTHR >= RP + NN || NTHR >= 2 * RP, "mv2 epilogue layout");
     T* vec;                  // >= 5*NN : colb[2][NN] rowb[2][NN] ipv[2]
     T* part;                 // >= 8*NN
     int* piv;                // >= NN+4 ; piv[NN] = "unsafe pivot" flag
     const uint32_t* dmask;
+    int tid;                 // thread index inside the group
+    int bar;                 // (unused: the barrier id is the BAR template parameter)
     __device__ __forceinline__ constexpr int N() const { return NN; }
     __device__ __forceinline__ constexpr int LD() const { return kLd; }
+    __device__ __forceinline__ void sync() const { group_sync<NTHR, BAR>(); }
+    __device__ __forceinline__ int nthreads() const { return NTHR; }
 
     template <bool KSIGN, class Epi>
     __device__ __forceinline__ void mm(const T* __restrict__ A, const T* __restrict__ B, Epi epi) const {
-        const int tid = threadIdx.x;
         if (tid < NT * NT) {
             const int i0 = (tid % NT) * TM, j0 = (tid / NT) * TM;
             const T* Ap = A + i0;
@@ -292,7 +316,7 @@ struct OpsFast {
             for (int x = 0; x < TM; ++x)
 #pragma unroll
                 for (int y = 0; y < TM; ++y) acc[x][y] = T(0);
-#pragma unroll 9
+#pragma unroll 5
             for (int k = 0; k < NN; ++k) {
                 T a[TM], b[TM];
 #pragma unroll
@@ -316,13 +340,12 @@ struct OpsFast {
         }
     }
 
-    // y = A x (one or two right-hand sides), k split over blockDim/RP segments
+    // y = A x (one or two right-hand sides), k split over NTHR/RP segments
     template <bool KSIGN, int NV, class E1, class E2>
     __device__ __forceinline__ void mv_impl(const T* __restrict__ A, const T* __restrict__ x1,
                                             const T* __restrict__ x2, E1 e1, E2 e2) const {
-        constexpr int NSEG = (256 / RP) < 1 ? 1 : (256 / RP);
+        constexpr int NSEG = (NTHR / RP) < 1 ? 1 : (NTHR / RP);
         constexpr int KL = (NN + NSEG - 1) / NSEG;
-        const int tid = threadIdx.x;
         const int seg = tid / RP, i = tid % RP;
         if (seg < NSEG && i < NN) {
             const int k0 = seg * KL;
@@ -341,20 +364,20 @@ struct OpsFast {
             part[seg * NN + i] = s1;
             if (NV == 2) part[(NSEG + seg) * NN + i] = s2;
         }
-        __syncthreads();
+        sync();
         if (tid < NN) {
             T s = part[tid];
 #pragma unroll
             for (int g = 1; g < NSEG; ++g) s += part[g * NN + tid];
             e1(tid, s);
-        } else if (NV == 2 && tid >= 64 && tid < 64 + NN) {
-            const int r = tid - 64;
+        } else if (NV == 2 && tid >= RP && tid < RP + NN) {
+            const int r = tid - RP;
             T s = part[NSEG * NN + r];
 #pragma unroll
             for (int g = 1; g < NSEG; ++g) s += part[(NSEG + g) * NN + r];
             e2(r, s);
         }
-        __syncthreads();
+        sync();
     }
     template <bool KSIGN, class Epi>
     __device__ __forceinline__ void mv(const T* A, const T* x, Epi epi) const {
@@ -362,26 +385,32 @@ struct OpsFast {
     }
     template <class E1, class E2>
     __device__ __forceinline__ void mv2(const T* A, const T* x1, const T* x2, E1 e1, E2 e2) const {
-        static_assert(NN <= 64, "mv2 epilogue layout");
         mv_impl<false, 2>(A, x1, x2, e1, e2);
     }
 
     // In-place inverse.  Register-resident Gauss-Jordan on the diagonal pivots, one
-    // barrier per step; every multiplier is checked against the threshold-pivoting
-    // bound |a_ik| <= 4|a_kk|.  If a step violates it (or a pivot is zero/NaN) the
-    // matrix is rebuilt by `rebuild()` and inverted by the partial-pivoting routine,
-    // so the result is always that of a pivoted, backward-stable elimination.
+    // barrier per step.  Step k is the rank-1 update  M <- M - c' r'^T  with
+    //   c'_i = a_ik (i != k), c'_k = a_kk - 1 ;  r'_j = a_kj / a_kk (j != k), r'_k = 1 + 1/a_kk
+    // which produces the in-place Gauss-Jordan result for every element (pivot row,
+    // pivot column and the rest) without per-element selects.  Column k, row k and the
+    // current diagonal are exchanged through double-buffered shared vectors; every thread
+    // forms the NEXT pivot and its reciprocal itself (a_{k+1,k+1} - a_{k+1,k} a_{k,k+1}/a_kk),
+    // so the reciprocal chain never waits on a store + barrier.  Every multiplier is checked
+    // against the threshold-pivoting bound |a_ik| <= 4|a_kk|; if a step violates it (or a
+    // pivot is zero/NaN/out of range) the matrix is rebuilt by `rebuild()` and inverted by
+    // the partial-pivoting routine, so the result is always that of a stable elimination.
     template <class Rebuild>
     __device__ __forceinline__ void inverse(T* __restrict__ M, Rebuild rebuild) const {
-        T* colb = vec;
-        T* rowb = vec + 2 * NN;
-        T* ipvb = vec + 4 * NN;
+        T* colb = vec;               // [2][NN]
+        T* rowb = vec + 2 * NN;      // [2][NN]
+        T* diab = part;              // [2][NN]  (part is free during the inverse)
         int* bad = piv + NN;
-        const int tid = threadIdx.x;
         const bool act = tid < NT * NT;
         const int i0 = (tid % NT) * TM, j0 = (tid / NT) * TM;
+        const bool isdiag = act && (i0 == j0);
         T m[TM][TM];
         if (tid == 0) *bad = 0;
+        T ipv = Num<T>::rcp(M[0]);
         if (act) {
 #pragma unroll
             for (int y = 0; y < TM; ++y)
@@ -395,52 +424,72 @@ struct OpsFast {
 #pragma unroll
                 for (int y = 0; y < TM; ++y) rowb[j0 + y] = m[0][y];
             }
-            if (i0 == 0 && j0 == 0) ipvb[0] = T(1) / m[0][0];
+            if (isdiag) {
+#pragma unroll
+                for (int x = 0; x < TM; ++x) diab[i0 + x] = m[x][x];
+            }
         }
-        __syncthreads();
+        sync();
         bool mybad = false;
+        const int ti = tid % NT, tj = tid / NT;
+        // steps k = K*TM + d : d is unrolled so every register-tile index is static
 #pragma unroll 1
-        for (int k = 0; k < NN; ++k) {
-            const int cur = (k & 1) * NN, nxt = NN - cur;
-            if (act) {
-                const T ipv = ipvb[k & 1];
-                const T lim = T(4) * Num<T>::abs_(colb[cur + k]);
-                T c[TM], r[TM];
+        for (int K = 0; K < NT; ++K) {
+            const bool tiK = act && (ti == K), tjK = act && (tj == K);
 #pragma unroll
-                for (int x = 0; x < TM; ++x) c[x] = colb[cur + i0 + x];
+            for (int d = 0; d < TM; ++d) {
+                const int k = K * TM + d, k1 = k + 1;
+                const int cur = (k & 1) * NN, nxt = NN - cur;
+                constexpr int dummy = 0; (void)dummy;
+                const int d1 = (d + 1 < TM) ? d + 1 : 0;
+                const int K1 = (d + 1 < TM) ? K : K + 1;
+                T ipv_next = T(0);
+                if (k1 < NN) {         // next pivot and its reciprocal, off the critical path
+                    const T pn = fma(-colb[cur + k1], rowb[cur + k1] * ipv, diab[cur + k1]);
+                    ipv_next = Num<T>::rcp(pn);
+                }
+                if (act) {
+                    const T pv = colb[cur + k];
+                    const T apv = Num<T>::abs_(pv);
+                    const T lim = T(4) * apv;
+                    if (!(apv > T(1e-30) && apv < T(1e30))) mybad = true;
+                    T c[TM], r[TM];
 #pragma unroll
-                for (int y = 0; y < TM; ++y) r[y] = (j0 + y == k) ? ipv : rowb[cur + j0 + y] * ipv;
-#pragma unroll
-                for (int x = 0; x < TM; ++x)
-                    if (i0 + x != k && !(Num<T>::abs_(c[x]) <= lim)) mybad = true;
-#pragma unroll
-                for (int x = 0; x < TM; ++x)
+                    for (int x = 0; x < TM; ++x) {
+                        const T cv = colb[cur + i0 + x];
+                        if (x == d) {
+                            if (!tiK && !(Num<T>::abs_(cv) <= lim)) mybad = true;
+                            c[x] = tiK ? pv - T(1) : cv;
+                        } else {
+                            if (!(Num<T>::abs_(cv) <= lim)) mybad = true;
+                            c[x] = cv;
+                        }
+                    }
 #pragma unroll
                     for (int y = 0; y < TM; ++y) {
-                        const T base = (j0 + y == k) ? T(0) : m[x][y];
-                        const T v = fma(-c[x], r[y], base);
-                        m[x][y] = (i0 + x == k) ? r[y] : v;
+                        const T rv = rowb[cur + j0 + y] * ipv;
+                        r[y] = (y == d && tjK) ? T(1) + ipv : rv;
                     }
-                const int k1 = k + 1;
-                if (k1 < NN) {
-#pragma unroll
-                    for (int y = 0; y < TM; ++y)
-                        if (j0 + y == k1) {
-#pragma unroll
-                            for (int x = 0; x < TM; ++x) colb[nxt + i0 + x] = m[x][y];
-                        }
 #pragma unroll
                     for (int x = 0; x < TM; ++x)
-                        if (i0 + x == k1) {
 #pragma unroll
-                            for (int y = 0; y < TM; ++y) {
-                                rowb[nxt + j0 + y] = m[x][y];
-                                if (j0 + y == k1) ipvb[k1 & 1] = T(1) / m[x][y];
-                            }
-                        }
+                        for (int y = 0; y < TM; ++y) m[x][y] = fma(-c[x], r[y], m[x][y]);
+                    if (tj == K1) {
+#pragma unroll
+                        for (int x = 0; x < TM; ++x) colb[nxt + i0 + x] = m[x][d1];
+                    }
+                    if (ti == K1) {
+#pragma unroll
+                        for (int y = 0; y < TM; ++y) rowb[nxt + j0 + y] = m[d1][y];
+                    }
+                    if (isdiag) {
+#pragma unroll
+                        for (int x = 0; x < TM; ++x) diab[nxt + i0 + x] = m[x][x];
+                    }
                 }
+                ipv = ipv_next;
+                sync();
             }
-            __syncthreads();
         }
         if (mybad) *bad = 1;
         if (act) {
@@ -449,12 +498,67 @@ struct OpsFast {
 #pragma unroll
                 for (int x = 0; x < TM; ++x) M[(i0 + x) + (j0 + y) * kLd] = m[x][y];
         }
-        __syncthreads();
-        if (*bad) {                       // uniform: taken by the whole CTA or not at all
+        sync();
+        if (*bad) {                       // uniform over the group
             rebuild();
-            __syncthreads();
-            cta_inverse<T>(NN, M, kLd, vec, piv, nullptr);
+            sync();
+            group_inverse_pivoted(M);
         }
+    }
+
+    // partial-pivoting fallback on the group's threads (same algorithm as cta_inverse)
+    __device__ __forceinline__ void group_inverse_pivoted(T* __restrict__ M) const {
+        T* colb = vec; T* rowb = vec + NN; T* oldk = vec + 2 * NN;
+        for (int k = 0; k < NN; ++k) {
+            if (tid < 32) {
+                T best = T(-1); int bi = k;
+                for (int i = k + tid; i < NN; i += 32) {
+                    T v = Num<T>::abs_(M[i + k * kLd]);
+                    if (v > best) { best = v; bi = i; }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    T ob = __shfl_xor_sync(0xffffffffu, best, off);
+                    int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                }
+                if (tid == 0) piv[k] = bi;
+            }
+            sync();
+            const int p = piv[k];
+            const T pv = M[p + k * kLd];
+            const T ipv = T(1) / pv;
+            for (int i = tid; i < NN; i += NTHR) {
+                colb[i] = (i == k) ? pv : ((i == p) ? M[k + k * kLd] : M[i + k * kLd]);
+                const T rp = M[p + i * kLd];
+                oldk[i] = M[k + i * kLd];
+                rowb[i] = (i == k) ? ipv : rp * ipv;
+            }
+            sync();
+            for (int e = tid; e < NN * NN; e += NTHR) {
+                const int i = e % NN, j = e / NN;
+                T* mij = M + i + j * kLd;
+                if (i == k) {
+                    *mij = rowb[j];
+                } else {
+                    T base = (i == p) ? oldk[j] : *mij;
+                    if (j == k) base = T(0);
+                    *mij = fma(-colb[i], rowb[j], base);
+                }
+            }
+            sync();
+        }
+        for (int i = tid; i < NN; i += NTHR) {
+            for (int k = NN - 1; k >= 0; --k) {
+                const int p = piv[k];
+                if (p != k) {
+                    const T x = M[i + k * kLd], y = M[i + p * kLd];
+                    M[i + k * kLd] = y;
+                    M[i + p * kLd] = x;
+                }
+            }
+        }
+        sync();
     }
 };
 

@@ -13,8 +13,8 @@ cudaError_t launch_adding(cudaStream_t s, const ColArgs<T>& a, unsigned total, i
 template <typename T, int TM, int NN>
 void kernel_ptrs(const void** layer, const void** adding);
 
-template <typename T, int TM, int NN>
-struct OpsSel { using type = OpsFast<T, TM, NN>; };
-template <typename T, int TM>
-struct OpsSel<T, TM, 0> { using type = OpsGeneric<T, TM>; };
+template <typename T, int TM, int NN, int NTHR>
+struct OpsSel { using type = OpsFast<T, TM, NN, NTHR>; };
+template <typename T, int TM, int NTHR>
+struct OpsSel<T, TM, 0, NTHR> { using type = OpsGeneric<T, TM>; };
 }  // namespace vsm
