@@ -298,7 +298,7 @@ static int do_launch(vsm_ctx* ctx, bool layer, int tm, bool fast, int N, const C
     cudaError_t e = cudaSuccess;
 #define VSM_L(TM_, NN_) (layer ? launch_layer<T, TM_, NN_>(ctx->stream, a, total, grid, threads, smem) \
                                : launch_adding<T, TM_, NN_>(ctx->stream, a, total, grid, threads, smem))
-    if (fast && N == 45) e = VSM_L(5, 45);
+    if (fast && N == 45) e = VSM_L(0, 45);
     else switch (tm) {
         case 1: e = VSM_L(1, 0); break;
         case 2: e = VSM_L(2, 0); break;
@@ -316,7 +316,7 @@ static int do_launch(vsm_ctx* ctx, bool layer, int tm, bool fast, int N, const C
 
 template <typename T>
 static void get_kernel_ptrs(int tm, bool fast, int N, const void** kl, const void** ka) {
-    if (fast && N == 45) { kernel_ptrs<T, 5, 45>(kl, ka); return; }
+    if (fast && N == 45) { kernel_ptrs<T, 0, 45>(kl, ka); return; }
     switch (tm) {
         case 1: kernel_ptrs<T, 1, 0>(kl, ka); break;
         case 2: kernel_ptrs<T, 2, 0>(kl, ka); break;
@@ -418,17 +418,25 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
     if (lv + 1024 > smax) return fail(ctx, VSM_ERR_UNSUPPORTED, "rt_column: N too large");
     int l_mats = (int)std::min<size_t>(kLayerMats, (smax - lv) / msz);
     int a_mats = (int)std::min<size_t>(kAddMats, (smax - av) / msz);
-    const size_t l_smem = lv + (size_t)l_mats * msz, a_smem = av + (size_t)a_mats * msz;
+    const size_t l_smem = lv + (size_t)l_mats * msz;
+    size_t a_smem = av + (size_t)a_mats * msz;
     const size_t l_slab = (size_t)(kLayerMats - l_mats) * msz, a_slab = (size_t)(kAddMats - a_mats) * msz;
-    const bool fast = has_fast(N) && l_mats == kLayerMats && a_mats == kAddMats;
+    bool fast = has_fast(N) && l_mats == kLayerMats;
+    FastCfg fc{cfg.threads, cfg.threads, 0};
+    if (fast) fc = fast_cfg<T, 45>();
+    // the two-group adding kernel has its own arena (11 matrices)
+    const size_t a2_smem = (size_t)kAdd2Mats * msz + (size_t)kAdd2VecUnits * N * sizeof(T) + ((size_t)3 * N + 8) * 4;
+    if (fast && fc.adding_two_group && a2_smem > smax) fast = false;
+    if (fast && !fc.adding_two_group && a_mats != kAddMats) fast = false;
 
+    if (fast && fc.adding_two_group) a_smem = a2_smem;
     const void* kl = nullptr; const void* ka = nullptr;
     get_kernel_ptrs<T>(cfg.tm, fast, N, &kl, &ka);
     CK(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l_smem));
     CK(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
     // CTA sizes: the specialised kernels fix theirs at compile time
-    const int l_threads = fast ? 128 : cfg.threads;
-    const int a_threads = fast ? 256 : cfg.threads;
+    const int l_threads = fast ? fc.layer_threads : cfg.threads;
+    const int a_threads = fast ? fc.adding_threads : cfg.threads;
     const int l_occ = occupancy<T>(kl, l_threads, l_smem);
     const int a_occ = occupancy<T>(ka, a_threads, a_smem);
     const int l_grid_max = ctx->num_sms * l_occ, a_grid_max = ctx->num_sms * a_occ;

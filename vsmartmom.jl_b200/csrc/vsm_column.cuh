@@ -624,6 +624,245 @@ __global__ void __launch_bounds__(NTHR) k_adding(ColArgs<T> a, unsigned int tota
     }
 }
 
+// ----------------------------------------------------------------------------
+// k_adding2 -- specialised (compile-time N) adding chain.  The two halves of the
+// ScatteringInterface_11 step (interaction.jl:220-240 "minus" half: T01, J0-, R-+, T-- ;
+// :248-265 "plus" half: T21, J0+, T++, R+-) only read the pre-step composite, so two
+// 96-thread groups run them concurrently on named barriers; the plus half writes its
+// results to spare buffers and the pointers are rotated at the end of the step.
+// Arena: RA RB TC TD r t | X1a X2a | X1b X2b X3b  (11 matrices, all shared memory).
+// ----------------------------------------------------------------------------
+constexpr int kAdd2Mats = 11;
+// vector scratch of k_adding2 in units of n: 6 shared vectors + 2 groups x (v1 + vec(5) + part(8))
+constexpr int kAdd2VecUnits = 6 + 2 * 14;
+
+template <typename T, int NN, int TM, int GT>
+struct Add2Ctx {
+    using OpsA = OpsFast<T, TM, NN, GT, 1>;
+    using OpsB = OpsFast<T, TM, NN, GT, 2>;
+    using OpsC = OpsFast<T, TM, NN, 2 * GT, 0>;
+    T *RA, *RB, *TC, *TD, *r, *t, *X1a, *X2a, *X1b, *X2b, *X3b;
+    T *J0pc, *J0pnew, *J0m, *jp, *jm, *v1A, *v1B;
+    OpsA opA; OpsB opB; OpsC opC;
+    const uint32_t* dmask;
+    int group, gtid;
+};
+
+// one ScatteringInterface_11 step on two groups; ends with the whole CTA synchronised
+template <typename T, int NN, int TM, int GT>
+__device__ __noinline__ void add2_step11(Add2Ctx<T, NN, TM, GT>& c, bool rpm_zero, bool t_ident) {
+    constexpr int n = NN, ld = NN | 1;
+    const uint32_t* dmask = c.dmask;
+    auto at = [](T* M, int i, int j) -> T& { return M[i + j * ld]; };
+    if (c.group == 0) {
+        const auto& op = c.opA;
+        T* r = c.r; T* RB = c.RB; T* X1a = c.X1a; T* X2a = c.X2a; T* TD = c.TD; T* TC = c.TC; T* RA = c.RA;
+        T* t = c.t; T* J0m = c.J0m; T* v1A = c.v1A; const T* jm = c.jm; const T* J0pc = c.J0pc;
+        auto build1 = [&]() {
+            op.template mm<false>(r, RB, [&](int i, int j, T acc) { at(X1a, i, j) = (i == j ? T(1) : T(0)) - acc; });
+        };
+        build1();
+        op.sync();
+        op.inverse(X1a, build1);                                                     // (:220-222)
+        op.template mm<false>(TD, X1a, [&](int i, int j, T acc) { at(X2a, i, j) = acc; });    // T01_inv (:226)
+        op.template mv<false>(r, J0pc, [&](int i, T s) { v1A[i] = s + jm[i]; });      // (:229)
+        op.template mv<false>(X2a, v1A, [&](int i, T s) { J0m[i] = J0m[i] + s; });
+        op.template mm<false>(X2a, r, [&](int i, int j, T acc) { at(X1a, i, j) = acc; });
+        op.sync();
+        op.template mm<false>(X1a, TC, [&](int i, int j, T acc) { at(RA, i, j) += acc; });    // (:237)
+        if (!t_ident)
+            op.template mm<true>(X2a, t, [&](int i, int j, T acc) { at(TD, i, j) = Num<T>::flip(acc, dmask[j]); });  // (:240)
+    } else {
+        const auto& op = c.opB;
+        T* r = c.r; T* RB = c.RB; T* X1b = c.X1b; T* X2b = c.X2b; T* X3b = c.X3b; T* TC = c.TC; T* t = c.t;
+        T* v1B = c.v1B; T* J0pnew = c.J0pnew; const T* jm = c.jm; const T* jp = c.jp; const T* J0pc = c.J0pc;
+        auto build2 = [&]() {
+            op.template mm<false>(RB, r, [&](int i, int j, T acc) { at(X1b, i, j) = (i == j ? T(1) : T(0)) - acc; });
+        };
+        build2();
+        op.sync();
+        op.inverse(X1b, build2);                                                     // (:248-249)
+        T* T21 = X1b;
+        if (!t_ident) {
+            op.template mm<false>(t, X1b, [&](int i, int j, T acc) { at(X2b, i, j) = acc; });     // T21_inv (:251)
+            T21 = X2b;
+        }
+        op.template mv<false>(RB, jm, [&](int i, T s) { v1B[i] = J0pc[i] + s; });     // (:254)
+        op.template mv<false>(T21, v1B, [&](int i, T s) { J0pnew[i] = jp[i] + s; });
+        T* TCn = t_ident ? X2b : X1b;
+        op.template mm<false>(T21, TC, [&](int i, int j, T acc) { at(TCn, i, j) = acc; });        // (:262)
+        op.template mm<false>(T21, RB, [&](int i, int j, T acc) { at(X3b, i, j) = acc; });
+        op.sync();
+        if (t_ident) {                                                                // (:265)
+            if (!rpm_zero)
+                for (int e = c.gtid; e < n * n; e += GT) {
+                    const int i = e % n, j = e / n;
+                    at(X3b, i, j) += Num<T>::flip(at(r, i, j), dmask[i] ^ dmask[j]);
+                }
+        } else {
+            op.template mm<true>(X3b, t, [&](int i, int j, T acc) {
+                const T rpm = rpm_zero ? T(0) : Num<T>::flip(at(r, i, j), dmask[i] ^ dmask[j]);
+                at(X2b, i, j) = rpm + Num<T>::flip(acc, dmask[j]);
+            });
+        }
+    }
+    __syncthreads();
+    T* tmp;
+    if (t_ident) {
+        tmp = c.TD; c.TD = c.X2a; c.X2a = tmp;
+        tmp = c.TC; c.TC = c.X2b; c.X2b = tmp;
+        tmp = c.RB; c.RB = c.X3b; c.X3b = tmp;
+    } else {
+        tmp = c.TC; c.TC = c.X1b; c.X1b = tmp;
+        tmp = c.RB; c.RB = c.X2b; c.X2b = tmp;
+    }
+    tmp = c.J0pc; c.J0pc = c.J0pnew; c.J0pnew = tmp;
+}
+
+// the rare interfaces (non-scattering layers) run on the whole CTA
+template <typename T, int NN, int TM, int GT>
+__device__ __noinline__ void add2_step_other(Add2Ctx<T, NN, TM, GT>& c, int iface, bool rpm_zero, bool t_ident) {
+    CompPtrs<T> q{c.RA, c.RB, c.TC, c.TD, c.r, c.t, c.X1a, c.X2a, c.X1b};
+    interact<T, typename Add2Ctx<T, NN, TM, GT>::OpsC>(c.opC, iface, q, c.J0pc, c.J0m, c.jp, c.jm, c.v1A, rpm_zero, t_ident);
+    c.RA = q.RA; c.RB = q.RB; c.TC = q.TC; c.TD = q.TD; c.X1a = q.X1; c.X2a = q.X2; c.X1b = q.X3;
+}
+
+template <typename T, int NN, int TM, int GT>
+__global__ void __launch_bounds__(2 * GT, 1) k_adding2(ColArgs<T> a, unsigned int total) {
+    constexpr int n = NN, ld = NN | 1, msz = ld * n;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* sm = reinterpret_cast<T*>(smem_raw);
+    T* vb = sm + kAdd2Mats * msz;
+    T* J0p = vb;            T* J0m = J0p + n;   T* J0pn = J0m + n;  T* jp = J0pn + n;
+    T* jm = jp + n;         T* hv = jm + n;
+    T* v1A = hv + n;        T* vecA = v1A + n;  T* partA = vecA + 5 * n;
+    T* v1B = partA + 8 * n; T* vecB = v1B + n;  T* partB = vecB + 5 * n;
+    uint32_t* dmask = reinterpret_cast<uint32_t*>(partB + 8 * n);
+    int* pivA = reinterpret_cast<int*>(dmask + n);
+    int* pivB = pivA + n + 4;
+    __shared__ unsigned int sh_item;
+    const int tid = threadIdx.x;
+    Add2Ctx<T, NN, TM, GT> c;
+    c.group = tid / GT; c.gtid = tid % GT; c.dmask = dmask;
+    c.opA.vec = vecA; c.opA.part = partA; c.opA.piv = pivA; c.opA.dmask = dmask; c.opA.tid = c.gtid; c.opA.bar = 1;
+    c.opB.vec = vecB; c.opB.part = partB; c.opB.piv = pivB; c.opB.dmask = dmask; c.opB.tid = c.gtid; c.opB.bar = 2;
+    c.opC.vec = vecA; c.opC.part = partA; c.opC.piv = pivA; c.opC.dmask = dmask; c.opC.tid = tid;   c.opC.bar = 0;
+    c.J0m = J0m; c.jp = jp; c.jm = jm; c.v1A = v1A; c.v1B = v1B;
+    const size_t zstride = (size_t)n * n;
+    const int nOut = a.nVZA * a.nStokes;
+
+    for (int i = tid; i < n; i += blockDim.x) dmask[i] = dmask_of(i, a.nStokes);
+    unsigned int nextv = 0;
+    if (tid == 0) nextv = atomicAdd(a.counter, 1u);
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sh_item = nextv;
+        __syncthreads();
+        const unsigned int item = sh_item;
+        if (item >= total) break;
+        if (tid == 0) nextv = atomicAdd(a.counter, 1u);
+        const int p = item % a.nS;
+        const int mi = item / a.nS;
+        const int m = a.m0 + mi;
+        c.RA = sm;             c.RB = sm + msz;      c.TC = sm + 2 * msz;  c.TD = sm + 3 * msz;
+        c.r = sm + 4 * msz;    c.t = sm + 5 * msz;   c.X1a = sm + 6 * msz; c.X2a = sm + 7 * msz;
+        c.X1b = sm + 8 * msz;  c.X2b = sm + 9 * msz; c.X3b = sm + 10 * msz;
+        c.J0pc = J0p; c.J0pnew = J0pn;
+
+        for (int iz = 0; iz < a.Nz; ++iz) {
+            const bool sc = a.scatter[iz] != 0;
+            T* dr = (iz == 0) ? c.RA : c.r;
+            T* dt = (iz == 0) ? c.TC : c.t;
+            T* djp = (iz == 0) ? c.J0pc : jp;
+            T* djm = (iz == 0) ? J0m : jm;
+            if (sc) {
+                const size_t slot = ((size_t)mi * a.Nz + iz) * a.nS + p;
+                const T* gr = a.add_r + slot * zstride;
+                const T* gt = a.add_t + slot * zstride;
+                for (int e = tid; e < n * n; e += blockDim.x) {
+                    const int i = e % n, j = e / n;
+                    dr[i + j * ld] = gr[e];
+                    dt[i + j * ld] = gt[e];
+                }
+                for (int i = tid; i < n; i += blockDim.x) {
+                    djp[i] = a.add_jp[slot * n + i];
+                    djm[i] = a.add_jm[slot * n + i];
+                }
+            } else {
+                const T tau = a.p_tau[(size_t)iz * a.nS + p];
+                for (int e = tid; e < n * n; e += blockDim.x) {
+                    const int i = e % n, j = e / n;
+                    dr[i + j * ld] = T(0);
+                    dt[i + j * ld] = (i == j) ? Num<T>::exp_(-tau / a.mu[i]) : T(0);
+                }
+                for (int i = tid; i < n; i += blockDim.x) { djp[i] = T(0); djm[i] = T(0); }
+            }
+            __syncthreads();
+            if (iz == 0) {
+                T* RA = c.RA; T* RB = c.RB; T* TC = c.TC; T* TD = c.TD;
+                for (int e = tid; e < n * n; e += blockDim.x) {
+                    const int i = e % n, j = e / n;
+                    const uint32_t sg = dmask[i] ^ dmask[j];
+                    RB[i + j * ld] = sc ? Num<T>::flip(RA[i + j * ld], sg) : T(0);
+                    TD[i + j * ld] = Num<T>::flip(TC[i + j * ld], sg);
+                }
+                __syncthreads();
+            } else if (a.iface[iz] == 3) {
+                add2_step11<T, NN, TM, GT>(c, !sc, false);
+            } else {
+                add2_step_other<T, NN, TM, GT>(c, a.iface[iz], !sc, false);
+            }
+        }
+        // ---- Lambertian surface + last interaction
+        const T ts_end = a.p_tausum[(size_t)a.Nz * a.nS + p];
+        T jps_sun = T(0);
+        if (m == 0) {
+            const T rho = T(2) * a.albedo;
+            const T att = Num<T>::exp_(-ts_end / a.mu0);
+            T* r = c.r;
+            for (int e = tid; e < n * n; e += blockDim.x) {
+                const int i = e % n, j = e / n;
+                const bool ii = (i % a.nStokes) == 0 && (j % a.nStokes) == 0;
+                r[i + j * ld] = ii ? rho * (a.mu[j] * a.wt[j]) : T(0);
+            }
+            for (int i = tid; i < n; i += blockDim.x) {
+                jp[i] = (i == a.istart) ? att : T(0);
+                jm[i] = ((i % a.nStokes) == 0) ? a.mu0 * rho * att : T(0);
+            }
+            jps_sun = att;
+            __syncthreads();
+            if (a.iface[a.Nz - 1] == 3) add2_step11<T, NN, TM, GT>(c, true, true);
+            else add2_step_other<T, NN, TM, GT>(c, a.iface[a.Nz - 1], true, true);
+            const T* J0pc = c.J0pc;
+            c.opC.template mv<false>(c.r, J0pc, [&](int i, T s) { hv[i] = s + jm[i]; });
+        } else {
+            for (int i = tid; i < n; i += blockDim.x) hv[i] = T(0);
+            __syncthreads();
+        }
+        const size_t pbase = ((size_t)m * a.nS + p) * nOut;
+        const T* J0pc = c.J0pc;
+        for (int o = tid; o < nOut; o += blockDim.x) {
+            const int iv = o % a.nVZA, s = o / a.nVZA;
+            const T w = a.vza_w[s + a.nStokes * (iv + (size_t)a.nVZA * m)];
+            const int row = a.vza_row[iv] + s;
+            a.part_R[pbase + o] = w * J0m[row];
+            a.part_T[pbase + o] = w * J0pc[row];
+            a.part_H[pbase + o] = w * hv[row];
+        }
+        if (m == 0 && a.bhr_uw && tid < a.nStokes) {
+            const int s = tid;
+            T up = T(0), dw = T(0);
+            for (int j = s; j < n; j += a.nStokes) {
+                up += hv[j] * a.wt[j] * a.mu[j];
+                dw += J0pc[j] * a.wt[j] * a.mu[j];
+            }
+            a.bhr_uw[s + (size_t)a.nStokes * p] = up;
+            a.bhr_dw[s + (size_t)a.nStokes * p] = dw + jps_sun * a.mu[a.istart];
+        }
+    }
+}
+
 // out[o + nOut*p] = sum_m part[(m*nS + p)*nOut + o]   (m ascending, as the Fourier loop)
 template <typename T>
 __global__ void k_reduce(int n_moments, size_t per_m, const T* __restrict__ pR,

@@ -293,7 +293,6 @@ struct OpsFast {
     static_assert(NT * NT <= NTHR, "one register tile per thread");
     static constexpr int kLd = NN | 1;
     static constexpr int RP = (NN + 31) & ~31;    // rows padded to whole warps for mv
-    static_assert(NTHR >= RP + NN || NTHR >= 2 * RP, "mv2 epilogue layout");
     T* vec;                  // >= 5*NN : colb[2][NN] rowb[2][NN] ipv[2]
     T* part;                 // >= 8*NN
     int* piv;                // >= NN+4 ; piv[NN] = "unsafe pivot" flag
@@ -365,12 +364,19 @@ struct OpsFast {
             if (NV == 2) part[(NSEG + seg) * NN + i] = s2;
         }
         sync();
+        constexpr bool SPLIT = (NTHR >= RP + NN);     // second vector reduced by a second thread range
         if (tid < NN) {
             T s = part[tid];
 #pragma unroll
             for (int g = 1; g < NSEG; ++g) s += part[g * NN + tid];
             e1(tid, s);
-        } else if (NV == 2 && tid >= RP && tid < RP + NN) {
+            if (NV == 2 && !SPLIT) {
+                T s2 = part[NSEG * NN + tid];
+#pragma unroll
+                for (int g = 1; g < NSEG; ++g) s2 += part[(NSEG + g) * NN + tid];
+                e2(tid, s2);
+            }
+        } else if (NV == 2 && SPLIT && tid >= RP && tid < RP + NN) {
             const int r = tid - RP;
             T s = part[NSEG * NN + r];
 #pragma unroll

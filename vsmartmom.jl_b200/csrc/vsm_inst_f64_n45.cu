@@ -1,8 +1,9 @@
-#define VSM_T float
+#define VSM_T double
 #define VSM_TM 5
 #define VSM_ATM 3
 #define VSM_NN 45
 #define VSM_MINB 3
 #define VSM_LTHR 128
 #define VSM_ATHR 256
+#define VSM_ADD2 0
 #include "vsm_inst.inc"

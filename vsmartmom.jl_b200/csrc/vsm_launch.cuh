@@ -12,6 +12,13 @@ template <typename T, int TM, int NN>
 cudaError_t launch_adding(cudaStream_t s, const ColArgs<T>& a, unsigned total, int grid, int threads, size_t smem);
 template <typename T, int TM, int NN>
 void kernel_ptrs(const void** layer, const void** adding);
+// launch geometry chosen at compile time by the specialised instantiation
+struct FastCfg {
+    int layer_threads, adding_threads;
+    int adding_two_group;      // 1: k_adding2 (11 matrices, two groups) ; 0: k_adding on OpsFast
+};
+template <typename T, int NN>
+FastCfg fast_cfg();
 
 template <typename T, int TM, int NN, int NTHR>
 struct OpsSel { using type = OpsFast<T, TM, NN, NTHR>; };
