@@ -245,3 +245,54 @@ def test_invalid_arguments_fail_loudly(ctx):
         ctx.check(_lib.lib.vsm_batch_inv_f64(ctx.handle, None, None, 4, 1, None))
     with pytest.raises(ValueError):
         batched.batched_mul(ctx, torch.zeros((2, 3, 3)), torch.zeros((2, 3, 3)))
+
+
+# ---- L1: vsm_rt_layer (drop-in for rt_kernel!) driven layer by layer like rt_run's loop
+@pytest.mark.parametrize("dtype,pol,nstreams", [(np.float64, "Stokes_IQU", 10), (np.float64, "Stokes_IQUV", 4),
+                                                (np.float32, "Stokes_IQU", 4)])
+def test_rt_layer_entry_matches_oracle(ctx, dtype, pol, nstreams):
+    from vsmom_b200 import layers
+    m = vb.synthetic_o2a_model(nSpec=6, nstreams=nstreams, polarization_type=pol, aerosol=True, float_type=dtype)
+    m.tau_rayl[:, 1] = 0                      # one purely absorbing layer: 10/11 interfaces + zero_added_noscat!
+    m.tau_aer[:, 1] = 0
+    om = to_oracle(m)
+    q = m.quad_points
+    N = q.qp_muN.size
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    dev = "cuda"
+    mu = torch.from_numpy(q.qp_muN.astype(dtype)).to(dev)
+    wt = torch.from_numpy(q.wt_muN.astype(dtype)).to(dev)
+    F0 = torch.zeros((m.nSpec, m.pol_n), dtype=tdt, device=dev)
+    F0[:, 0] = 1
+    for mom in (0, 2):
+        ctl = orc.band_control(om, mom)
+        props = orc.construct_core_optical_properties(om, mom)
+        comp = layers.make_composite_layer(N, m.nSpec, tdt)
+        added = layers.make_added_layer(N, m.nSpec, tdt)
+        Cref = None
+        F0o = np.zeros((m.pol_n, m.nSpec), dtype); F0o[0] = 1
+        for iz in range(m.Nz):
+            p = props[iz]
+            Zpp = np.broadcast_to(p.Zpp, (m.nSpec, N, N)) if p.Zpp.ndim == 2 else p.Zpp
+            Zmp = np.broadcast_to(p.Zmp, (m.nSpec, N, N)) if p.Zmp.ndim == 2 else p.Zmp
+            tz = lambda Z: torch.from_numpy(np.ascontiguousarray(Z.transpose(0, 2, 1)).astype(dtype)).to(dev)
+            layers.rt_kernel_(ctx, m.pol_n, added if iz % 2 == 0 else None, comp,
+                              torch.from_numpy(np.ascontiguousarray(p.tau.astype(dtype))).to(dev),
+                              torch.from_numpy(np.ascontiguousarray(np.broadcast_to(p.varpi, p.tau.shape).astype(dtype))).to(dev),
+                              tz(Zpp), tz(Zmp), ctl.interface[iz],
+                              torch.from_numpy(np.ascontiguousarray(ctl.tau_sum[:, iz])).to(dev), mom, q, F0, iz + 1,
+                              ctl.ndoubl[iz], ctl.scatter[iz], mu, wt)
+            Cref = orc.rt_kernel_layer(om, mom, iz, ctl, p, Cref, F0o, ctl.tau_sum[:, iz])
+        ctx.synchronize()
+        tol = 1e-9 if dtype == np.float64 else 2e-3
+        for name, ref in (("Rmp", Cref.Rmp), ("Rpm", Cref.Rpm), ("Tpp", Cref.Tpp), ("Tmm", Cref.Tmm)):
+            got = getattr(comp, name).cpu().numpy().transpose(0, 2, 1)
+            assert relerr(got, ref) <= tol, (mom, name, relerr(got, ref))
+        assert relerr(comp.J0m.cpu().numpy(), Cref.J0m) <= tol
+        assert relerr(comp.J0p.cpu().numpy(), Cref.J0p) <= tol
+        # AddedLayer outputs of the last even layer obey the D-symmetry r⁺⁻ = D r⁻⁺ D
+        Dd = np.tile(np.array([1, 1, -1, -1][:m.pol_n]), q.Nquad)
+        rmp = added.rmp.cpu().numpy().transpose(0, 2, 1)
+        rpm = added.rpm.cpu().numpy().transpose(0, 2, 1)
+        if np.abs(rmp).max() > 0:
+            assert np.allclose(rpm, Dd[None, :, None] * rmp * Dd[None, None, :], rtol=0, atol=0)

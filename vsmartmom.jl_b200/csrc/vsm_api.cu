@@ -604,12 +604,107 @@ extern "C" int vsm_last_column_launches(vsm_ctx* ctx, int* layer_launches, int* 
 }
 
 // ---------------------------------------------------------------------------
-// L1: one layer (implemented in vsm_layer.cu)
+// L1: one layer, one Fourier moment  (rt_kernel!(::noRS, ...), rt_kernel.jl:175-250)
 // ---------------------------------------------------------------------------
-template <typename T> int rt_layer_impl(vsm_ctx* ctx, const vsm_layer_desc* d);
-extern "C" int vsm_rt_layer_f64(vsm_ctx* c, const vsm_layer_desc* d) {
-    return fail(c, VSM_ERR_UNSUPPORTED, "vsm_rt_layer: not built yet");
+template <typename T>
+static int rt_layer_impl(vsm_ctx* ctx, const vsm_layer_desc* d) {
+    if (!ctx) return VSM_ERR_INVALID_ARG;
+    if (!d || d->struct_size != (int)sizeof(vsm_layer_desc))
+        return fail(ctx, VSM_ERR_INVALID_ARG, "rt_layer: descriptor NULL or struct_size mismatch");
+    const int N = d->N, nSt = d->nStokes, nSpec = d->nSpec;
+    if (N <= 0 || nSt < 1 || nSt > 4 || N % nSt != 0 || nSpec < 0 || d->imu0 < 1 || d->imu0 * nSt > N ||
+        d->ndoubl < 0 || d->ndoubl > 60 || d->iface < 0 || d->iface > 3 || d->m < 0 || d->iz < 1)
+        return fail(ctx, VSM_ERR_INVALID_ARG, "rt_layer: bad dimensions / control values");
+    if (nSpec == 0) return VSM_OK;
+    if (!d->tau || !d->varpi || !d->Zpp || !d->Zmp || !d->tau_sum || !d->F0 || !d->mu || !d->wt || !d->Rmp ||
+        !d->Rpm || !d->Tpp || !d->Tmm || !d->J0p || !d->J0m)
+        return fail(ctx, VSM_ERR_INVALID_ARG, "rt_layer: NULL input array");
+    CK(cudaSetDevice(ctx->device));
+    const KernelCfg cfg = pick_cfg(N);
+    const int ld = N | 1;
+    const size_t msz = (size_t)ld * N * sizeof(T);
+    const size_t smax = (size_t)ctx->max_smem_optin;
+    const size_t lv = layer_vec_bytes<T>(N), av = add_vec_bytes<T>(N);
+    if (lv + 1024 > smax) return fail(ctx, VSM_ERR_UNSUPPORTED, "rt_layer: N too large");
+    const int l_mats = (int)std::min<size_t>(kLayerMats, (smax - lv) / msz);
+    const int a_mats = (int)std::min<size_t>(kAddMats, (smax - av) / msz);
+    const size_t l_smem = lv + (size_t)l_mats * msz, a_smem = av + (size_t)a_mats * msz;
+    const size_t l_slab = (size_t)(kLayerMats - l_mats) * msz, a_slab = (size_t)(kAddMats - a_mats) * msz;
+    const void* kl = nullptr; const void* ka = nullptr; const void* ks = nullptr;
+    get_kernel_ptrs<T>(cfg.tm, false, N, &kl, &ka);
+    switch (cfg.tm) {
+        case 1: ks = step_kernel_ptr<T, 1>(); break;
+        case 2: ks = step_kernel_ptr<T, 2>(); break;
+        case 3: ks = step_kernel_ptr<T, 3>(); break;
+        default: ks = step_kernel_ptr<T, 4>(); break;
+    }
+    CK(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l_smem));
+    CK(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
+    const int l_grid_max = ctx->num_sms * occupancy<T>(kl, cfg.threads, l_smem);
+    const int s_grid_max = ctx->num_sms * occupancy<T>(ks, cfg.threads, a_smem);
+    const size_t NN2 = (size_t)N * N;
+    // AddedLayer storage: the caller's arrays when given, library scratch otherwise
+    const bool own_added = !(d->rmp && d->tpp && d->j0p && d->j0m);
+    int rc;
+    if (own_added && (rc = ensure(ctx, ctx->added, ((size_t)2 * NN2 + 2 * N) * nSpec * sizeof(T)))) return rc;
+    T* ad = (T*)ctx->added.p;
+    T* add_r = own_added ? ad : (T*)d->rmp;
+    T* add_t = own_added ? ad + NN2 * nSpec : (T*)d->tpp;
+    T* add_jp = own_added ? ad + 2 * NN2 * nSpec : (T*)d->j0p;
+    T* add_jm = own_added ? add_jp + (size_t)N * nSpec : (T*)d->j0m;
+    if ((rc = ensure(ctx, ctx->slabs, std::max<size_t>((size_t)l_slab * l_grid_max + (size_t)a_slab * s_grid_max, 16)))) return rc;
+    if ((rc = ensure(ctx, ctx->counter, 256))) return rc;
+    const int ctl[4] = {d->ndoubl, 1, d->iface, 0};    // ndoubl[0], scatter[0], iface[0], layer_order[0]
+    if ((rc = ensure(ctx, ctx->consts, 64))) return rc;
+    CK(cudaMemcpyAsync(ctx->consts.p, ctl, sizeof ctl, cudaMemcpyHostToDevice, ctx->stream));
+    const int* cI = (const int*)ctx->consts.p;
+    if (d->scatter) {
+        ColArgs<T> a;
+        memset(&a, 0, sizeof a);
+        a.N = N; a.nStokes = nSt; a.Nz = 1; a.nC = 1; a.nVZA = 0; a.ld = ld;
+        a.istart = (d->imu0 - 1) * nSt; a.nS = nSpec; a.m0 = d->m; a.Mb = 1; a.n_sched_layers = 1;
+        a.n_smem_mats = l_mats; a.z_spectral = d->z_is_spectral ? 1 : 0; a.mz0 = d->m;
+        a.mu0 = (T)d->mu0; a.albedo = T(0);
+        a.mu = (const T*)d->mu; a.wt = (const T*)d->wt;
+        a.ndoubl = cI; a.scatter = cI + 1; a.iface = cI + 2; a.layer_order = cI + 3;
+        a.Zpp = (const T*)d->Zpp; a.Zmp = (const T*)d->Zmp;
+        a.p_tau = (const T*)d->tau; a.p_varpi = (const T*)d->varpi; a.p_tausum = (const T*)d->tau_sum;
+        a.p_W = (const T*)d->tau;                      // nC == 1: weights unused
+        a.F0 = (const T*)d->F0; a.F0_off = 0;
+        a.add_r = add_r; a.add_t = add_t; a.add_jp = add_jp; a.add_jm = add_jm;
+        a.slab = (T*)ctx->slabs.p; a.slab_stride = l_slab / sizeof(T);
+        a.counter = (unsigned int*)ctx->counter.p;
+        CK(cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
+        const int grid = (int)std::min<size_t>((size_t)nSpec, (size_t)l_grid_max);
+        if ((rc = do_launch<T>(ctx, true, cfg.tm, false, N, a, (unsigned)nSpec, grid, cfg.threads, l_smem))) return rc;
+    }
+    {
+        StepArgs<T> s;
+        memset(&s, 0, sizeof s);
+        s.N = N; s.nStokes = nSt; s.nS = nSpec; s.ld = ld; s.n_smem_mats = a_mats;
+        s.iface = d->iface; s.first = (d->iz == 1) ? 1 : 0; s.scatter = d->scatter ? 1 : 0;
+        s.tau = (const T*)d->tau; s.mu = (const T*)d->mu;
+        s.add_r = add_r; s.add_t = add_t; s.add_jp = add_jp; s.add_jm = add_jm;
+        s.Rmp = (T*)d->Rmp; s.Rpm = (T*)d->Rpm; s.Tpp = (T*)d->Tpp; s.Tmm = (T*)d->Tmm;
+        s.J0p = (T*)d->J0p; s.J0m = (T*)d->J0m;
+        s.out_rpm = (T*)d->rpm; s.out_tmm = (T*)d->tmm;
+        s.out_rmp = (T*)d->rmp; s.out_tpp = (T*)d->tpp; s.out_jp = (T*)d->j0p; s.out_jm = (T*)d->j0m;
+        s.slab = (T*)ctx->slabs.p + ((size_t)l_slab * l_grid_max) / sizeof(T); s.slab_stride = a_slab / sizeof(T);
+        s.counter = (unsigned int*)ctx->counter.p;
+        CK(cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
+        const int grid = (int)std::min<size_t>((size_t)nSpec, (size_t)s_grid_max);
+        cudaError_t e;
+        switch (cfg.tm) {
+            case 1: e = launch_step<T, 1>(ctx->stream, s, (unsigned)nSpec, grid, cfg.threads, a_smem); break;
+            case 2: e = launch_step<T, 2>(ctx->stream, s, (unsigned)nSpec, grid, cfg.threads, a_smem); break;
+            case 3: e = launch_step<T, 3>(ctx->stream, s, (unsigned)nSpec, grid, cfg.threads, a_smem); break;
+            default: e = launch_step<T, 4>(ctx->stream, s, (unsigned)nSpec, grid, cfg.threads, a_smem); break;
+        }
+        ctx->launches++;
+        if (e != cudaSuccess) return fail(ctx, VSM_ERR_CUDA, std::string("k_interact_step launch: ") + cudaGetErrorString(e));
+    }
+    return VSM_OK;
 }
-extern "C" int vsm_rt_layer_f32(vsm_ctx* c, const vsm_layer_desc* d) {
-    return fail(c, VSM_ERR_UNSUPPORTED, "vsm_rt_layer: not built yet");
-}
+
+extern "C" int vsm_rt_layer_f64(vsm_ctx* c, const vsm_layer_desc* d) { return rt_layer_impl<double>(c, d); }
+extern "C" int vsm_rt_layer_f32(vsm_ctx* c, const vsm_layer_desc* d) { return rt_layer_impl<float>(c, d); }

@@ -863,6 +863,112 @@ __global__ void __launch_bounds__(2 * GT, 1) k_adding2(ColArgs<T> a, unsigned in
     }
 }
 
+// ----------------------------------------------------------------------------
+// k_interact_step -- L1 (vsm_rt_layer_*): ONE interaction!/copy_added_to_composite!
+// (rt_kernel.jl:244-249) per spectral point with the CompositeLayer in global memory
+// (the reference's (N,N,nSpec) arrays), staged through the arena.
+// ----------------------------------------------------------------------------
+template <typename T>
+struct StepArgs {
+    int N, nStokes, nS, ld, n_smem_mats;
+    int iface, first, scatter;          // first: iz == 1 -> copy
+    const T* tau; const T* mu;          // non-scattering layer: t = diag(exp(-tau/mu))
+    const T* add_r; const T* add_t; const T* add_jp; const T* add_jm;   // (N,N,nS)/(N,nS)
+    T* Rmp; T* Rpm; T* Tpp; T* Tmm; T* J0p; T* J0m;                     // composite, in/out
+    T* out_rpm; T* out_tmm;             // optional AddedLayer r+-, t-- outputs (may be null)
+    T* out_rmp; T* out_tpp; T* out_jp; T* out_jm;   // non-scattering: AddedLayer fill (may be null)
+    T* slab; size_t slab_stride;
+    unsigned int* counter;
+};
+
+template <typename T, class Ops>
+__global__ void __launch_bounds__(256) k_interact_step(StepArgs<T> a, unsigned int total) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = a.N, ld = a.ld;
+    const int msz = ld * n;
+    T* sm = reinterpret_cast<T*>(smem_raw);
+    const int nsm = a.n_smem_mats;
+    T* slab = a.slab + (size_t)blockIdx.x * a.slab_stride;
+    auto mat = [&](int k) -> T* { return k < nsm ? sm + k * msz : slab + (size_t)(k - nsm) * msz; };
+    T* vbase = sm + nsm * msz;
+    T* J0p = vbase;         T* J0m = J0p + n;   T* jp = J0m + n;   T* jm = jp + n;
+    T* v1 = jm + n;         T* hv = v1 + n;     T* vec = hv + n;
+    T* part = vec + 5 * n;
+    uint32_t* dmask = reinterpret_cast<uint32_t*>(part + 8 * n);
+    int* piv = reinterpret_cast<int*>(dmask + n);
+    __shared__ unsigned int sh_item;
+    Ops op;
+    op.n = n; op.ld = ld; op.vec = vec; op.part = part; op.piv = piv; op.dmask = dmask; op.tid = threadIdx.x; op.bar = 0;
+    const size_t NN2 = (size_t)n * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dmask[i] = dmask_of(i, a.nStokes);
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) sh_item = atomicAdd(a.counter, 1u);
+        __syncthreads();
+        const unsigned int p = sh_item;
+        if (p >= total) break;
+        CompPtrs<T> c{mat(0), mat(1), mat(2), mat(3), mat(4), mat(5), mat(6), mat(7), mat(8)};
+        const bool sc = a.scatter != 0;
+        T* dr = a.first ? c.RA : c.r;
+        T* dt = a.first ? c.TC : c.t;
+        T* djp = a.first ? J0p : jp;
+        T* djm = a.first ? J0m : jm;
+        for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+            const int i = e % n, j = e / n;
+            T rv, tv;
+            if (sc) { rv = a.add_r[p * NN2 + e]; tv = a.add_t[p * NN2 + e]; }
+            else { rv = T(0); tv = (i == j) ? Num<T>::exp_(-a.tau[p] / a.mu[i]) : T(0); }
+            dr[i + j * ld] = rv;
+            dt[i + j * ld] = tv;
+            const uint32_t sg = dmask[i] ^ dmask[j];
+            if (sc) {
+                if (a.out_rpm) a.out_rpm[p * NN2 + e] = Num<T>::flip(rv, sg);
+                if (a.out_tmm) a.out_tmm[p * NN2 + e] = Num<T>::flip(tv, sg);
+            } else {          // zero_added_noscat! (rt_helpers.jl:174-180)
+                if (a.out_rmp) a.out_rmp[p * NN2 + e] = T(0);
+                if (a.out_rpm) a.out_rpm[p * NN2 + e] = T(0);
+                if (a.out_tpp) a.out_tpp[p * NN2 + e] = tv;
+                if (a.out_tmm) a.out_tmm[p * NN2 + e] = tv;
+            }
+            if (!a.first) {
+                c.RA[i + j * ld] = a.Rmp[p * NN2 + e];
+                c.RB[i + j * ld] = a.Rpm[p * NN2 + e];
+                c.TC[i + j * ld] = a.Tpp[p * NN2 + e];
+                c.TD[i + j * ld] = a.Tmm[p * NN2 + e];
+            }
+        }
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            djp[i] = sc ? a.add_jp[(size_t)p * n + i] : T(0);
+            djm[i] = sc ? a.add_jm[(size_t)p * n + i] : T(0);
+            if (!sc && a.out_jm) a.out_jm[(size_t)p * n + i] = T(0);
+            if (!a.first) { J0p[i] = a.J0p[(size_t)p * n + i]; J0m[i] = a.J0m[(size_t)p * n + i]; }
+        }
+        __syncthreads();
+        if (a.first) {
+            for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+                const int i = e % n, j = e / n;
+                const uint32_t sg = dmask[i] ^ dmask[j];
+                c.RB[i + j * ld] = sc ? Num<T>::flip(c.RA[i + j * ld], sg) : T(0);
+                c.TD[i + j * ld] = Num<T>::flip(c.TC[i + j * ld], sg);
+            }
+            __syncthreads();
+        } else {
+            interact<T, Ops>(op, a.iface, c, J0p, J0m, jp, jm, v1, !sc, false);
+        }
+        for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+            const int i = e % n, j = e / n;
+            a.Rmp[p * NN2 + e] = c.RA[i + j * ld];
+            a.Rpm[p * NN2 + e] = c.RB[i + j * ld];
+            a.Tpp[p * NN2 + e] = c.TC[i + j * ld];
+            a.Tmm[p * NN2 + e] = c.TD[i + j * ld];
+        }
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            a.J0p[(size_t)p * n + i] = J0p[i];
+            a.J0m[(size_t)p * n + i] = J0m[i];
+        }
+    }
+}
+
 // out[o + nOut*p] = sum_m part[(m*nS + p)*nOut + o]   (m ascending, as the Fourier loop)
 template <typename T>
 __global__ void k_reduce(int n_moments, size_t per_m, const T* __restrict__ pR,

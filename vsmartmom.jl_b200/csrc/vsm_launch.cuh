@@ -12,6 +12,10 @@ template <typename T, int TM, int NN>
 cudaError_t launch_adding(cudaStream_t s, const ColArgs<T>& a, unsigned total, int grid, int threads, size_t smem);
 template <typename T, int TM, int NN>
 void kernel_ptrs(const void** layer, const void** adding);
+template <typename T, int TM>
+cudaError_t launch_step(cudaStream_t s, const StepArgs<T>& a, unsigned total, int grid, int threads, size_t smem);
+template <typename T, int TM>
+const void* step_kernel_ptr();
 // launch geometry chosen at compile time by the specialised instantiation
 struct FastCfg {
     int layer_threads, adding_threads;
