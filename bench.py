@@ -280,8 +280,9 @@ def run_b200(args):
         except Exception:
             pass
         traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json"))).get("bytes_per_launch")
+        try:   # dram bytes of the dominant kernel from the committed ncu --set full capture, scaled to this launch
+            tj = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
+            traffic = tj["bytes_per_point_moment"] * nS * nM / n_layer_launches
         except Exception:
             pass
         value = nS * world * args.steps / (ms * 1e-3)
