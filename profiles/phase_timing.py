@@ -1,0 +1,25 @@
+"""Developer tool: per-phase cycle split of the fused layer kernel (debug build with
+-DVSM_PHASE_TIMING; see csrc/vsm_column.cuh).  Run on the GPU box:
+    VSMOM_B200_LIB=vsmartmom.jl_b200/lib/libvsmom_b200_dbg.so python profiles/phase_timing.py"""
+import ctypes as C, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "vsmartmom.jl_b200"))
+import numpy as np, torch
+import vsmom_b200 as vb
+from vsmom_b200 import _lib, rt_run as rr
+m = vb.synthetic_o2a_model(nSpec=444, aerosol=True)
+ctx = _lib.Context(0)
+prep = rr.prepare(m)
+rr.rt_run(m, ctx, prep)
+buf = (C.c_ulonglong * 16)()
+_lib.lib.vsm_debug_phase_cycles(buf, 1)
+rr.rt_run(m, ctx, prep)
+_lib.lib.vsm_debug_phase_cycles(buf, 0)
+names = ["elemental", "mm r*r (+j1)", "inverse", "mm t*G", "mv2 x2", "mm r*t", "mm r+=tt*Y", "mm tt*t", "doubling loop total", "store"]
+v = np.array(list(buf)[:10], dtype=np.float64)
+nd = prep.ctl.ndoubl.sum() * 20 * 444
+items = 34 * 20 * 444
+print("doublings", nd, "items", items, "ms", ctx.last_column_ms())
+for k, nme in enumerate(names):
+    per = v[k] / (nd if 1 <= k <= 7 else items)
+    print(f"{nme:22s} total {v[k]:.3e} cyc   per {'doubling' if 1 <= k <= 7 else 'item'}: {per:9.0f} cyc")

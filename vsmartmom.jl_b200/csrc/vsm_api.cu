@@ -3,6 +3,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <string>
@@ -30,7 +31,7 @@ struct vsm_ctx {
     uint64_t launches = 0;
     std::string err;
     // grow-only scratch
-    DevBuf consts, props, added, slabs, partial, counter, l0tmp;
+    DevBuf consts, props, added, slabs, partial, counter, l0tmp, geom;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float t_total = 0, t_layer = 0, t_add = 0;
     bool timing_valid = false;
@@ -117,7 +118,7 @@ extern "C" int vsm_destroy(vsm_ctx* ctx) {
     if (!ctx) return VSM_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->consts, &ctx->props, &ctx->added, &ctx->slabs, &ctx->partial, &ctx->counter, &ctx->l0tmp};
+    DevBuf* bufs[] = {&ctx->consts, &ctx->props, &ctx->added, &ctx->slabs, &ctx->partial, &ctx->counter, &ctx->l0tmp, &ctx->geom};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     delete ctx;
@@ -408,6 +409,11 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
     CK(cudaStreamSynchronize(ctx->stream));   // fT/fI are stack-owned vectors
     const T* cT = (const T*)ctx->consts.p;
     const int* cI = (const int*)((char*)ctx->consts.p + offI);
+    if ((rc = ensure(ctx, ctx->geom, (size_t)2 * N * N * sizeof(T)))) return rc;
+    T* geo1 = (T*)ctx->geom.p; T* geo2 = geo1 + (size_t)N * N;
+    k_geom<T><<<(N * N + 255) / 256, 256, 0, ctx->stream>>>(N, cT + o_mu, cT + o_wt, geo1, geo2);
+    ctx->launches++;
+    CK(cudaGetLastError());
 
     // ---- arena plan
     const KernelCfg cfg = pick_cfg(N);
@@ -439,7 +445,8 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
     const int a_threads = fast ? fc.adding_threads : cfg.threads;
     const int l_occ = occupancy<T>(kl, l_threads, l_smem);
     const int a_occ = occupancy<T>(ka, a_threads, a_smem);
-    const int l_grid_max = ctx->num_sms * l_occ, a_grid_max = ctx->num_sms * a_occ;
+    int l_grid_max = ctx->num_sms * l_occ, a_grid_max = ctx->num_sms * a_occ;
+    if (const char* e = getenv("VSM_DEBUG_LAYER_CTAS_PER_SM")) l_grid_max = ctx->num_sms * std::max(1, std::min(l_occ, atoi(e)));
 
     // ---- workspace plan: chunk over spectral points and moments
     const size_t add_item = (size_t)std::max(1, nSched) * ((size_t)2 * N * N + 2 * N) * sizeof(T);
@@ -521,6 +528,7 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
         a.Zpp = (const T*)d->Zpp; a.Zmp = (const T*)d->Zmp;
         a.p_tau = pa.tau; a.p_varpi = pa.varpi; a.p_tausum = pa.tausum; a.p_W = pa.W;
         a.F0 = (const T*)d->F0; a.F0_off = (size_t)n0;
+        a.geo1 = geo1; a.geo2 = geo2;
         a.counter = (unsigned int*)ctx->counter.p;
         a.vza_row = cI + o_vrow; a.vza_w = cT + o_vw;
         a.part_R = part; a.part_T = part + (size_t)nM * per_m; a.part_H = part + (size_t)2 * nM * per_m;
@@ -659,6 +667,11 @@ static int rt_layer_impl(vsm_ctx* ctx, const vsm_layer_desc* d) {
     CK(cudaMemcpyAsync(ctx->consts.p, ctl, sizeof ctl, cudaMemcpyHostToDevice, ctx->stream));
     const int* cI = (const int*)ctx->consts.p;
     if (d->scatter) {
+        if ((rc = ensure(ctx, ctx->geom, (size_t)2 * N * N * sizeof(T)))) return rc;
+        T* geo1 = (T*)ctx->geom.p; T* geo2 = geo1 + (size_t)N * N;
+        k_geom<T><<<(N * N + 255) / 256, 256, 0, ctx->stream>>>(N, (const T*)d->mu, (const T*)d->wt, geo1, geo2);
+        ctx->launches++;
+        CK(cudaGetLastError());
         ColArgs<T> a;
         memset(&a, 0, sizeof a);
         a.N = N; a.nStokes = nSt; a.Nz = 1; a.nC = 1; a.nVZA = 0; a.ld = ld;
@@ -671,6 +684,7 @@ static int rt_layer_impl(vsm_ctx* ctx, const vsm_layer_desc* d) {
         a.p_tau = (const T*)d->tau; a.p_varpi = (const T*)d->varpi; a.p_tausum = (const T*)d->tau_sum;
         a.p_W = (const T*)d->tau;                      // nC == 1: weights unused
         a.F0 = (const T*)d->F0; a.F0_off = 0;
+        a.geo1 = geo1; a.geo2 = geo2;
         a.add_r = add_r; a.add_t = add_t; a.add_jp = add_jp; a.add_jm = add_jm;
         a.slab = (T*)ctx->slabs.p; a.slab_stride = l_slab / sizeof(T);
         a.counter = (unsigned int*)ctx->counter.p;

@@ -17,6 +17,22 @@ namespace vsm {
 
 constexpr int kMaxComp = 8;      // Rayleigh + up to 7 aerosol types
 
+// Debug-only phase timing (-DVSM_PHASE_TIMING): thread 0 of every CTA accumulates clock64()
+// deltas per phase of the doubling loop into vsm_phase_cycles[] (read with cudaMemcpyFromSymbol).
+#ifdef VSM_PHASE_TIMING
+static __device__ unsigned long long vsm_phase_cycles[16];
+#define VSM_T0() long long _t0 = clock64()
+#define VSM_TICK(k)                                                              \
+    do {                                                                         \
+        long long _t1 = clock64();                                               \
+        if (threadIdx.x == 0) atomicAdd(&vsm_phase_cycles[k], (unsigned long long)(_t1 - _t0)); \
+        _t0 = _t1;                                                               \
+    } while (0)
+#else
+#define VSM_T0()
+#define VSM_TICK(k)
+#endif
+
 // ----------------------------------------------------------------------------
 // Arena: matrix k lives in shared memory if k < n_smem, else in the CTA's slab.
 // ----------------------------------------------------------------------------
@@ -116,6 +132,7 @@ struct ColArgs {
     const T* Zpp; const T* Zmp;                       // (N,N,nC,n_moments)
     const T* p_tau; const T* p_varpi; const T* p_tausum; const T* p_W;   // k_props outputs
     const T* F0; size_t F0_off;                       // (nStokes, nSpec) ; column offset of chunk
+    const T* geo1; const T* geo2;                     // k_geom tables (N,N)
     // added-layer scratch: slot = (mi*Nz + iz)*nS + p
     T* add_r; T* add_t; T* add_jp; T* add_jm;
     // spill slabs and the work counter
@@ -138,16 +155,39 @@ __device__ inline unsigned int next_item(unsigned int* counter, unsigned int* sh
 // ----------------------------------------------------------------------------
 // elemental r⁻⁺/t⁺⁺ and solar sources into the arena  (elemental.jl:289-392)
 // ----------------------------------------------------------------------------
+// geometric factors of the elemental formulas, shared by every point / layer / moment:
+//   geo1[i,j] = mu_j/(mu_i+mu_j) * w_j ,  geo2[i,j] = mu_j/(mu_i-mu_j) * w_j  (0 where mu_i == mu_j)
+template <typename T>
+__global__ void k_geom(int n, const T* __restrict__ mu, const T* __restrict__ wt, T* __restrict__ geo1,
+                       T* __restrict__ geo2) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * n) return;
+    const int i = e % n, j = e / n;
+    const T mui = mu[i], muj = mu[j];
+    geo1[e] = (muj / (mui + muj)) * wt[j];
+    geo2[e] = (mui == muj) ? T(0) : (muj / (mui - muj)) * wt[j];
+}
+
 template <typename T, int NN>
 __device__ __forceinline__ void elemental_fill(const ColArgs<T>& a, int m, int nd, T dtau, T varpi,
                                                T tausum, const T* __restrict__ Wc,
                                                const T* __restrict__ Zpp, const T* __restrict__ Zmp,
                                                size_t zstride, const T* __restrict__ F0n,
                                                const uint32_t* __restrict__ dmask,
-                                               T* r, T* t, T* jp, T* jm) {
+                                               T* r, T* t, T* jp, T* jm, T* rowtmp /* >= 3n */) {
     const int n = NN ? NN : a.N, ld = NN ? (NN | 1) : a.ld, nC = a.nC;
     const T wsc = (m == 0) ? T(0.5) : T(0.25);       // scaled_weights / fourier_weight
     const T eps = Num<T>::eps();
+    // per-stream quantities: a_i = dtau/mu_i, e_i = exp(-a_i), em1_i = expm1(-a_i)
+    T* ai = rowtmp; T* ei = rowtmp + n; T* em1 = rowtmp + 2 * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const T x = dtau / a.mu[i];
+        ai[i] = x;
+        ei[i] = Num<T>::exp_(-x);
+        em1[i] = Num<T>::expm1_(-x);
+    }
+    __syncthreads();
+    const T vw = varpi * wsc;
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
         const int i = e % n, j = e / n;
         T zm = T(0), zp = T(0);
@@ -159,23 +199,26 @@ __device__ __forceinline__ void elemental_fill(const ColArgs<T>& a, int m, int n
                 zp = fma(Wc[c], Zpp[(size_t)c * zstride + e], zp);
             }
         }
-        const T mui = a.mu[i], muj = a.mu[j];
         const T wj = a.wt[j] * wsc;
         T rv, tv;
         if (wj > eps) {
-            rv = varpi * zm * (muj / (mui + muj)) * wj *
-                 (-Num<T>::expm1_(-dtau * ((T(1) / mui) + (T(1) / muj))));
-            if (mui == muj) {
-                if (i == j)
-                    tv = Num<T>::exp_(-dtau / mui) * (T(1) + varpi * zp * (dtau / mui) * (a.wt[i] * wsc));
-                else
-                    tv = Num<T>::exp_(-dtau / muj) * (varpi * zp * (dtau / mui) * wj);
+            // 1 - exp(-(a_i+a_j)) = -(em1_i + em1_j + em1_i em1_j)      (elemental.jl:298-302)
+            const T xi = em1[i], xj = em1[j];
+            rv = vw * zm * a.geo1[e] * (-(xi + xj + xi * xj));
+            const T mui = a.mu[i], muj = a.mu[j];
+            if (mui == muj) {                                            // (:304-314)
+                tv = (i == j) ? ei[i] * (T(1) + varpi * zp * ai[i] * wj) : ei[j] * (varpi * zp * ai[i] * wj);
             } else {
-                tv = varpi * zp * (muj / (mui - muj)) * wj * expdiff_neg<T>(dtau / mui, dtau / muj);
+                // exp(-a_i) - exp(-a_j) = em1_i - em1_j ; the exact expdiff_neg form (rt_helpers.jl:32-40)
+                // is used for nearly coincident streams where that difference would cancel
+                T dif;
+                if (Num<T>::abs_(mui - muj) > T(1e-3) * muj) dif = xi - xj;
+                else dif = expdiff_neg<T>(ai[i], ai[j]);
+                tv = vw * zp * a.geo2[e] * dif;                          // (:319-323)
             }
         } else {
             rv = T(0);
-            tv = (i == j) ? Num<T>::exp_(-dtau / mui) : T(0);
+            tv = (i == j) ? ei[i] : T(0);
         }
         if (nd >= 1) rv = Num<T>::flip(rv, dmask[i]);      // apply_D_elemental!, nd>=1 branch
         r[i + j * ld] = rv;
@@ -223,31 +266,55 @@ __device__ __forceinline__ void elemental_fill(const ColArgs<T>& a, int m, int n
 template <typename T, class Ops>
 __device__ __forceinline__ void doubling_loop(const Ops& op, int nd, T expk, T*& r, T*& t, T*& X1,
                                               T* X2, T* jp, T* jm, T* j1p, T* j1m, T* v1, T* v2) {
-    const int n = op.N(), ld = op.LD();
+    const int n = op.N();
     for (int it = 0; it < nd; ++it) {
-        auto build = [&]() {
-            op.template mm<false>(r, r, [&](int i, int j, T acc) {
-                X1[i + j * ld] = (i == j ? T(1) : T(0)) - acc;            // rt_helpers.jl:103
-            });
-        };
-        build();
+        VSM_T0();
         for (int i = op.tid; i < n; i += op.nthreads()) {                 // doubling_source_update!, :131-132
             j1p[i] = jp[i] * expk;
             j1m[i] = jm[i] * expk;
         }
-        op.sync();
+#ifdef VSM_DBL_LAMBDA
+        const int ld = op.LD();
+        auto build = [&]() {
+            op.template mm<false>(r, r, [&](int i, int j, T acc) { X1[i + j * ld] = (i == j ? T(1) : T(0)) - acc; });
+            op.sync();
+        };
+#else
+        auto build = [&]() { op.template mmC<false, 2>(r, r, X1); };     // X1 = I - r r   (rt_helpers.jl:103)
+#endif
+        build();
+        VSM_TICK(1);
         op.inverse(X1, build);                                            // :104
-        op.template mm<false>(t, X1, [&](int i, int j, T acc) { X2[i + j * ld] = acc; });   // :105
+        VSM_TICK(2);
+#ifdef VSM_DBL_LAMBDA
+        op.template mm<false>(t, X1, [&](int i, int j, T acc) { X2[i + j * ld] = acc; });
+#else
+        op.template mmC<false, 0>(t, X1, X2);                             // X2 = t gp      (:105)
+#endif
+        VSM_TICK(3);
         // v1 = j1m + r jp ; v2 = jp + r j1m ; jm += tt v1 ; jp = j1p + tt v2          (:133-134)
         op.mv2(r, jp, j1m, [&](int i, T s) { v1[i] = j1m[i] + s; }, [&](int i, T s) { v2[i] = jp[i] + s; });
         op.mv2(X2, v1, v2, [&](int i, T s) { jm[i] = jm[i] + s; }, [&](int i, T s) { jp[i] = j1p[i] + s; });
+        VSM_TICK(4);
         // doubling_rt_update! (:162-163)
+#ifdef VSM_DBL_LAMBDA
         op.template mm<false>(r, t, [&](int i, int j, T acc) { X1[i + j * ld] = acc; });
         op.sync();
+        VSM_TICK(5);
         op.template mm<false>(X2, X1, [&](int i, int j, T acc) { r[i + j * ld] += acc; });
         op.sync();
+        VSM_TICK(6);
         op.template mm<false>(X2, t, [&](int i, int j, T acc) { X1[i + j * ld] = acc; });
         op.sync();
+        VSM_TICK(7);
+#else
+        op.template mmC<false, 0>(r, t, X1);                              // X1 = r t
+        VSM_TICK(5);
+        op.template mmC<false, 1>(X2, X1, r);                             // r += tt (r t)
+        VSM_TICK(6);
+        op.template mmC<false, 0>(X2, t, X1);                             // X1 = tt t
+        VSM_TICK(7);
+#endif
         T* tmp = t; t = X1; X1 = tmp;
         expk = expk * expk;                                               // :164
     }
@@ -260,11 +327,10 @@ constexpr int kVecUnits = 19;
 
 template <typename T, class Ops, int NN, int NTHR, int MINB>
 __global__ void __launch_bounds__(NTHR, MINB) k_layer(ColArgs<T> a, unsigned int total) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = NN ? NN : a.N;
     const int ld = NN ? (NN | 1) : a.ld;
     const int msz = ld * n;
-    T* sm = reinterpret_cast<T*>(smem_raw);
+    T* sm = reinterpret_cast<T*>(vsm_smem);
     const int nsm = NN ? kLayerMats : a.n_smem_mats;
     T* slab = NN ? sm : a.slab + (size_t)blockIdx.x * a.slab_stride;
     auto mat = [&](int k) -> T* { return (NN || k < nsm) ? sm + k * msz : slab + (size_t)(k - nsm) * msz; };
@@ -306,10 +372,13 @@ __global__ void __launch_bounds__(NTHR, MINB) k_layer(ColArgs<T> a, unsigned int
         const size_t zstride = (size_t)n * n;
         const T* Zpp = a.Zpp + (size_t)(m - a.mz0) * a.nC * zstride + (a.z_spectral ? p * zstride : 0);
         const T* Zmp = a.Zmp + (size_t)(m - a.mz0) * a.nC * zstride + (a.z_spectral ? p * zstride : 0);
+        VSM_T0();
         elemental_fill<T, NN>(a, m, nd, dtau, varpi, tausum, Wc, Zpp, Zmp, zstride,
-                              a.F0 + (a.F0_off + p) * a.nStokes, dmask, r, t, jp, jm);
+                              a.F0 + (a.F0_off + p) * a.nStokes, dmask, r, t, jp, jm, part);
         __syncthreads();
+        VSM_TICK(0);
         doubling_loop<T, Ops>(op, nd, expk, r, t, X1, X2, jp, jm, j1p, j1m, v1, v2);
+        VSM_TICK(8);
         // apply_D_matrix! / apply_D_matrix_SFI! (doubling.jl:178-216): r⁻⁺ <- D r*, j₀⁻ <- D j*
         const size_t slot = ((size_t)mi * a.Nz + iz) * a.nS + p;
         T* gr = a.add_r + slot * zstride;
@@ -327,6 +396,7 @@ __global__ void __launch_bounds__(NTHR, MINB) k_layer(ColArgs<T> a, unsigned int
             a.add_jp[slot * n + i] = jp[i];
             a.add_jm[slot * n + i] = vm;
         }
+        VSM_TICK(9);
     }
 }
 
@@ -498,11 +568,10 @@ __device__ __forceinline__ void interact(const Ops& op, int iface, CompPtrs<T>& 
 
 template <typename T, class Ops, int NN, int NTHR>
 __global__ void __launch_bounds__(NTHR) k_adding(ColArgs<T> a, unsigned int total) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = NN ? NN : a.N;
     const int ld = NN ? (NN | 1) : a.ld;
     const int msz = ld * n;
-    T* sm = reinterpret_cast<T*>(smem_raw);
+    T* sm = reinterpret_cast<T*>(vsm_smem);
     const int nsm = NN ? kAddMats : a.n_smem_mats;
     T* slab = NN ? sm : a.slab + (size_t)blockIdx.x * a.slab_stride;
     auto mat = [&](int k) -> T* { return (NN || k < nsm) ? sm + k * msz : slab + (size_t)(k - nsm) * msz; };
@@ -730,8 +799,7 @@ __device__ __noinline__ void add2_step_other(Add2Ctx<T, NN, TM, GT>& c, int ifac
 template <typename T, int NN, int TM, int GT>
 __global__ void __launch_bounds__(2 * GT, 1) k_adding2(ColArgs<T> a, unsigned int total) {
     constexpr int n = NN, ld = NN | 1, msz = ld * n;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* sm = reinterpret_cast<T*>(smem_raw);
+    T* sm = reinterpret_cast<T*>(vsm_smem);
     T* vb = sm + kAdd2Mats * msz;
     T* J0p = vb;            T* J0m = J0p + n;   T* J0pn = J0m + n;  T* jp = J0pn + n;
     T* jm = jp + n;         T* hv = jm + n;
@@ -883,10 +951,9 @@ struct StepArgs {
 
 template <typename T, class Ops>
 __global__ void __launch_bounds__(256) k_interact_step(StepArgs<T> a, unsigned int total) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.N, ld = a.ld;
     const int msz = ld * n;
-    T* sm = reinterpret_cast<T*>(smem_raw);
+    T* sm = reinterpret_cast<T*>(vsm_smem);
     const int nsm = a.n_smem_mats;
     T* slab = a.slab + (size_t)blockIdx.x * a.slab_stride;
     auto mat = [&](int k) -> T* { return k < nsm ? sm + k * msz : slab + (size_t)(k - nsm) * msz; };

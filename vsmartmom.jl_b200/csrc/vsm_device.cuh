@@ -30,12 +30,17 @@ template <> struct Num<double> {
     // branch-free reciprocal for |x| in the normal float range: fp32 seed + 2 Newton steps
     // in fp64 (23 -> 46 -> 92 bits): <= 1 ulp, no slow-path call on the critical path.
     __device__ static double rcp(double x) {
-        double r = (double)__frcp_rn((float)x);
+        double r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));     // MUFU.RCP64H, ~20 bits
         double e = fma(-x, r, 1.0);
         r = fma(r, e, r);
         e = fma(-x, r, 1.0);
         return fma(r, e, r);
     }
+    // |x| as an order-preserving integer key (high word), and that key scaled by 4
+    __device__ static uint32_t key(double x) { return (uint32_t)__double2hiint(x) & 0x7fffffffu; }
+    static constexpr uint32_t kKeyTimes4 = 0x00200000u;
+    static constexpr uint32_t kKeyMin = 0x39b00000u, kKeyMax = 0x46200000u;   // ~1e-30 .. ~1e30
 };
 template <> struct Num<float> {
     __device__ static float eps() { return 1.1920929e-07f; }
@@ -46,6 +51,9 @@ template <> struct Num<float> {
         return __uint_as_float(__float_as_uint(x) ^ mask);
     }
     __device__ static float rcp(float x) { return __frcp_rn(x); }
+    __device__ static uint32_t key(float x) { return __float_as_uint(x) & 0x7fffffffu; }
+    static constexpr uint32_t kKeyTimes4 = 0x01000000u;
+    static constexpr uint32_t kKeyMin = 0x0d000000u, kKeyMax = 0x71000000u;   // ~4e-31 .. ~6e29
 };
 
 // exp(-a) - exp(-b), stable for a ~ b   (rt_helpers.jl:32-40)
@@ -264,6 +272,17 @@ struct OpsGeneric {
     __device__ __forceinline__ void mm(const T* A, const T* B, Epi epi) const {
         cta_mm<T, TM, TM, KSIGN>(n, A, ld, B, ld, dmask, epi);
     }
+    template <bool KSIGN, int MODE>
+    __device__ __forceinline__ void mmC(const T* A, const T* B, T* C) const {
+        const int l = ld;
+        cta_mm<T, TM, TM, KSIGN>(n, A, ld, B, ld, dmask, [&](int i, int j, T acc) {
+            T* c = C + i + j * l;
+            if (MODE == 1) *c += acc;
+            else if (MODE == 2) *c = (i == j ? T(1) : T(0)) - acc;
+            else *c = acc;
+        });
+        __syncthreads();
+    }
     template <bool KSIGN, class Epi>
     __device__ __forceinline__ void mv(const T* A, const T* x, Epi epi) const {
         cta_mv<T, KSIGN>(n, A, ld, x, dmask, part, epi);
@@ -279,6 +298,17 @@ struct OpsGeneric {
     }
 };
 
+// The dynamic shared-memory arena of the fused kernels.  OpsFast re-bases every operand on
+// this symbol (integer offset from it) so that the compiler addresses shared memory directly
+// instead of converting generic pointers (a special-register read per access group).
+extern __shared__ __align__(16) unsigned char vsm_smem[];
+template <typename T>
+__device__ __forceinline__ T* smem_base() { return reinterpret_cast<T*>(vsm_smem); }
+template <typename T>
+__device__ __forceinline__ T* rebase(const T* p) {
+    return smem_base<T>() + (int)(p - smem_base<T>());
+}
+
 // Named barrier over the NTHR threads of one Ops group (bar 0 == __syncthreads when
 // the group is the whole CTA).
 template <int NTHR, int BAR>
@@ -286,11 +316,14 @@ __device__ __forceinline__ void group_sync() {
     asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NTHR) : "memory");
 }
 
-template <typename T, int TM, int NN, int NTHR, int BAR = 0>
+// TM: GEMM register tile, KS: split-K factor of the GEMMs (KS*(NN/TM)^2 threads work),
+// TMI: register tile of the Gauss-Jordan inverse ((NN/TMI)^2 threads work).
+template <typename T, int TM, int NN, int NTHR, int BAR = 0, int TMI = TM, int KS = 1>
 struct OpsFast {
-    static_assert(NN % TM == 0, "OpsFast needs exact tiling");
-    static constexpr int NT = NN / TM;            // tiles per dimension
-    static_assert(NT * NT <= NTHR, "one register tile per thread");
+    static_assert(NN % TM == 0 && NN % TMI == 0, "OpsFast needs exact tiling");
+    static constexpr int NT = NN / TM;            // GEMM tiles per dimension
+    static constexpr int NTI = NN / TMI;          // inverse tiles per dimension
+    static_assert(NT * NT * KS <= NTHR && NTI * NTI <= NTHR, "one register tile per thread");
     static constexpr int kLd = NN | 1;
     static constexpr int RP = (NN + 31) & ~31;    // rows padded to whole warps for mv
     T* vec;                  // >= 5*NN : colb[2][NN] rowb[2][NN] ipv[2]
@@ -308,8 +341,8 @@ struct OpsFast {
     __device__ __forceinline__ void mm(const T* __restrict__ A, const T* __restrict__ B, Epi epi) const {
         if (tid < NT * NT) {
             const int i0 = (tid % NT) * TM, j0 = (tid / NT) * TM;
-            const T* Ap = A + i0;
-            const T* Bp = B + j0 * kLd;
+            const T* Ap = rebase(A) + i0;
+            const T* Bp = rebase(B) + j0 * kLd;
             T acc[TM][TM];
 #pragma unroll
             for (int x = 0; x < TM; ++x)
@@ -336,6 +369,71 @@ struct OpsFast {
             for (int y = 0; y < TM; ++y)
 #pragma unroll
                 for (int x = 0; x < TM; ++x) epi(i0 + x, j0 + y, acc[x][y]);
+        }
+    }
+
+    // C = f(A*B) with the result written to (or accumulated into) C itself; the k range is
+    // split over KS thread sets whose partial tiles are combined through C.
+    //   MODE 0: C = acc      MODE 1: C += acc      MODE 2: C = I - acc
+    // Ends with the group synchronised.
+    template <bool KSIGN, int MODE>
+    __device__ __forceinline__ void mmC(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C) const {
+        constexpr int TILES = NT * NT;
+        constexpr int KL = (NN + KS - 1) / KS;
+        const int tile = tid % TILES, kp = tid / TILES;
+        const bool act = tid < TILES * KS;
+        const int i0 = (tile % NT) * TM, j0 = (tile / NT) * TM;
+        T acc[TM][TM];
+#pragma unroll
+        for (int x = 0; x < TM; ++x)
+#pragma unroll
+            for (int y = 0; y < TM; ++y) acc[x][y] = T(0);
+        if (act) {
+            const int k0 = kp * KL;
+            const T* Ap = rebase(A) + i0 + k0 * kLd;
+            const T* Bp = rebase(B) + j0 * kLd + k0;
+#pragma unroll 5
+            for (int kk = 0; kk < KL; ++kk) {
+                if (k0 + kk < NN) {
+                    T a[TM], b[TM];
+#pragma unroll
+                    for (int x = 0; x < TM; ++x) a[x] = Ap[kk * kLd + x];
+#pragma unroll
+                    for (int y = 0; y < TM; ++y) b[y] = Bp[y * kLd + kk];
+                    if (KSIGN) {
+                        const uint32_t mk = dmask[k0 + kk];
+#pragma unroll
+                        for (int x = 0; x < TM; ++x) a[x] = Num<T>::flip(a[x], mk);
+                    }
+#pragma unroll
+                    for (int x = 0; x < TM; ++x)
+#pragma unroll
+                        for (int y = 0; y < TM; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+                }
+            }
+        }
+        // combine: sets KS-1 .. 1 deposit / add their partials, set 0 finishes
+#pragma unroll
+        for (int p = KS - 1; p >= 0; --p) {
+            if (act && kp == p) {
+#pragma unroll
+                for (int y = 0; y < TM; ++y)
+#pragma unroll
+                    for (int x = 0; x < TM; ++x) {
+                        T* c = rebase(C) + (i0 + x) + (j0 + y) * kLd;
+                        if (MODE == 1) {
+                            *c += acc[x][y];
+                        } else if (p == KS - 1 && KS > 1) {
+                            *c = acc[x][y];
+                        } else if (p > 0) {
+                            *c += acc[x][y];
+                        } else {
+                            const T tot = (KS > 1) ? acc[x][y] + *c : acc[x][y];
+                            *c = (MODE == 2) ? ((i0 + x == j0 + y) ? T(1) : T(0)) - tot : tot;
+                        }
+                    }
+            }
+            sync();
         }
     }
 
@@ -406,91 +504,99 @@ struct OpsFast {
     // pivot is zero/NaN/out of range) the matrix is rebuilt by `rebuild()` and inverted by
     // the partial-pivoting routine, so the result is always that of a stable elimination.
     template <class Rebuild>
-    __device__ __forceinline__ void inverse(T* __restrict__ M, Rebuild rebuild) const {
-        T* colb = vec;               // [2][NN]
-        T* rowb = vec + 2 * NN;      // [2][NN]
-        T* diab = part;              // [2][NN]  (part is free during the inverse)
+    __device__ __forceinline__ void inverse(T* M, Rebuild rebuild) const {
+        T* colb = rebase(vec);           // [2][NN]
+        T* rowb = colb + 2 * NN;         // [2][NN]
+        T* diab = rebase(part);          // [2][NN]  (part is free during the inverse)
+        M = rebase(M);
         int* bad = piv + NN;
-        const bool act = tid < NT * NT;
-        const int i0 = (tid % NT) * TM, j0 = (tid / NT) * TM;
+        const bool act = tid < NTI * NTI;
+        const int i0 = (tid % NTI) * TMI, j0 = (tid / NTI) * TMI;
         const bool isdiag = act && (i0 == j0);
-        T m[TM][TM];
+        T m[TMI][TMI];
         if (tid == 0) *bad = 0;
         T ipv = Num<T>::rcp(M[0]);
         if (act) {
 #pragma unroll
-            for (int y = 0; y < TM; ++y)
+            for (int y = 0; y < TMI; ++y)
 #pragma unroll
-                for (int x = 0; x < TM; ++x) m[x][y] = M[(i0 + x) + (j0 + y) * kLd];
+                for (int x = 0; x < TMI; ++x) m[x][y] = M[(i0 + x) + (j0 + y) * kLd];
             if (j0 == 0) {
 #pragma unroll
-                for (int x = 0; x < TM; ++x) colb[i0 + x] = m[x][0];
+                for (int x = 0; x < TMI; ++x) colb[i0 + x] = m[x][0];
             }
-            if (i0 == 0) {
+            if (i0 == 0) {           // row 0, pre-scaled by 1/a_00
 #pragma unroll
-                for (int y = 0; y < TM; ++y) rowb[j0 + y] = m[0][y];
+                for (int y = 0; y < TMI; ++y) rowb[j0 + y] = m[0][y] * ipv;
             }
             if (isdiag) {
 #pragma unroll
-                for (int x = 0; x < TM; ++x) diab[i0 + x] = m[x][x];
+                for (int x = 0; x < TMI; ++x) diab[i0 + x] = m[x][x];
             }
         }
         sync();
         bool mybad = false;
-        const int ti = tid % NT, tj = tid / NT;
-        // steps k = K*TM + d : d is unrolled so every register-tile index is static
+        const int ti = tid % NTI, tj = tid / NTI;
+        // steps k = K*TMI + d : d is unrolled so every register-tile index is static.
+        // rowb holds row k ALREADY scaled by 1/a_kk (its owners know the reciprocal).
 #pragma unroll 1
-        for (int K = 0; K < NT; ++K) {
+        for (int K = 0; K < NTI; ++K) {
             const bool tiK = act && (ti == K), tjK = act && (tj == K);
 #pragma unroll
-            for (int d = 0; d < TM; ++d) {
-                const int k = K * TM + d, k1 = k + 1;
+            for (int d = 0; d < TMI; ++d) {
+                const int k = K * TMI + d, k1 = k + 1;
                 const int cur = (k & 1) * NN, nxt = NN - cur;
-                constexpr int dummy = 0; (void)dummy;
-                const int d1 = (d + 1 < TM) ? d + 1 : 0;
-                const int K1 = (d + 1 < TM) ? K : K + 1;
+                const int d1 = (d + 1 < TMI) ? d + 1 : 0;
+                const int K1 = (d + 1 < TMI) ? K : K + 1;
                 T ipv_next = T(0);
-                if (k1 < NN) {         // next pivot and its reciprocal, off the critical path
-                    const T pn = fma(-colb[cur + k1], rowb[cur + k1] * ipv, diab[cur + k1]);
+                if (k1 < NN) {         // next pivot and its reciprocal: a thread-local recurrence
+                    const T pn = fma(-colb[cur + k1], rowb[cur + k1], diab[cur + k1]);
                     ipv_next = Num<T>::rcp(pn);
                 }
                 if (act) {
                     const T pv = colb[cur + k];
-                    const T apv = Num<T>::abs_(pv);
-                    const T lim = T(4) * apv;
-                    if (!(apv > T(1e-30) && apv < T(1e30))) mybad = true;
-                    T c[TM], r[TM];
+                    const uint32_t kp = Num<T>::key(pv);
+                    const uint32_t klim = kp + Num<T>::kKeyTimes4;
+                    if (kp < Num<T>::kKeyMin || kp > Num<T>::kKeyMax) mybad = true;
+                    T c[TMI], r[TMI];
 #pragma unroll
-                    for (int x = 0; x < TM; ++x) {
+                    for (int x = 0; x < TMI; ++x) {
                         const T cv = colb[cur + i0 + x];
                         if (x == d) {
-                            if (!tiK && !(Num<T>::abs_(cv) <= lim)) mybad = true;
+                            if (!tiK && Num<T>::key(cv) > klim) mybad = true;
                             c[x] = tiK ? pv - T(1) : cv;
                         } else {
-                            if (!(Num<T>::abs_(cv) <= lim)) mybad = true;
+                            if (Num<T>::key(cv) > klim) mybad = true;
                             c[x] = cv;
                         }
                     }
 #pragma unroll
-                    for (int y = 0; y < TM; ++y) {
-                        const T rv = rowb[cur + j0 + y] * ipv;
+                    for (int y = 0; y < TMI; ++y) {
+                        const T rv = rowb[cur + j0 + y];
                         r[y] = (y == d && tjK) ? T(1) + ipv : rv;
                     }
+                    // the column / row / diagonal the NEXT step needs are formed and published first
 #pragma unroll
-                    for (int x = 0; x < TM; ++x)
+                    for (int x = 0; x < TMI; ++x) m[x][d1] = fma(-c[x], r[d1], m[x][d1]);
 #pragma unroll
-                        for (int y = 0; y < TM; ++y) m[x][y] = fma(-c[x], r[y], m[x][y]);
+                    for (int y = 0; y < TMI; ++y)
+                        if (y != d1) m[d1][y] = fma(-c[d1], r[y], m[d1][y]);
                     if (tj == K1) {
 #pragma unroll
-                        for (int x = 0; x < TM; ++x) colb[nxt + i0 + x] = m[x][d1];
+                        for (int x = 0; x < TMI; ++x) colb[nxt + i0 + x] = m[x][d1];
                     }
                     if (ti == K1) {
 #pragma unroll
-                        for (int y = 0; y < TM; ++y) rowb[nxt + j0 + y] = m[d1][y];
+                        for (int y = 0; y < TMI; ++y) rowb[nxt + j0 + y] = m[d1][y] * ipv_next;
                     }
+#pragma unroll
+                    for (int x = 0; x < TMI; ++x)
+#pragma unroll
+                        for (int y = 0; y < TMI; ++y)
+                            if (x != d1 && y != d1) m[x][y] = fma(-c[x], r[y], m[x][y]);
                     if (isdiag) {
 #pragma unroll
-                        for (int x = 0; x < TM; ++x) diab[nxt + i0 + x] = m[x][x];
+                        for (int x = 0; x < TMI; ++x) diab[nxt + i0 + x] = m[x][x];
                     }
                 }
                 ipv = ipv_next;
@@ -500,9 +606,9 @@ struct OpsFast {
         if (mybad) *bad = 1;
         if (act) {
 #pragma unroll
-            for (int y = 0; y < TM; ++y)
+            for (int y = 0; y < TMI; ++y)
 #pragma unroll
-                for (int x = 0; x < TM; ++x) M[(i0 + x) + (j0 + y) * kLd] = m[x][y];
+                for (int x = 0; x < TMI; ++x) M[(i0 + x) + (j0 + y) * kLd] = m[x][y];
         }
         sync();
         if (*bad) {                       // uniform over the group

@@ -6,4 +6,6 @@
 #define VSM_LTHR 128
 #define VSM_ATHR 256
 #define VSM_ADD2 0
+#define VSM_LTMI 5
+#define VSM_LKS 1
 #include "vsm_inst.inc"

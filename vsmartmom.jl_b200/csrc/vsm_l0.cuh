@@ -11,8 +11,7 @@ template <typename T, int TM, int TN>
 __global__ void __launch_bounds__(256) k_bmm(T* __restrict__ C, const T* __restrict__ A,
                                              const T* __restrict__ B, int M, int K, int Nc,
                                              int batch, int stage) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* sA = reinterpret_cast<T*>(smem_raw);
+    T* sA = reinterpret_cast<T*>(vsm_smem);
     const int lda = M | 1, ldb = K | 1;
     T* sB = sA + (size_t)lda * K;
     for (int b = blockIdx.x; b < batch; b += gridDim.x) {
@@ -67,8 +66,7 @@ __global__ void __launch_bounds__(256) k_bmm(T* __restrict__ C, const T* __restr
 template <typename T>
 __global__ void __launch_bounds__(256) k_binv(T* __restrict__ X, T* __restrict__ A, int N, int batch,
                                               int* __restrict__ info, int stage) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* sm = reinterpret_cast<T*>(smem_raw);
+    T* sm = reinterpret_cast<T*>(vsm_smem);
     const int ld = stage ? (N | 1) : N;
     T* vec = stage ? sm + (size_t)ld * N : sm;
     int* piv = reinterpret_cast<int*>(vec + 3 * N);

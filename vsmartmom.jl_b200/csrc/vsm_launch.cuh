@@ -24,8 +24,8 @@ struct FastCfg {
 template <typename T, int NN>
 FastCfg fast_cfg();
 
-template <typename T, int TM, int NN, int NTHR>
-struct OpsSel { using type = OpsFast<T, TM, NN, NTHR>; };
-template <typename T, int TM, int NTHR>
-struct OpsSel<T, TM, 0, NTHR> { using type = OpsGeneric<T, TM>; };
+template <typename T, int TM, int NN, int NTHR, int TMI = TM, int KS = 1>
+struct OpsSel { using type = OpsFast<T, TM, NN, NTHR, 0, TMI, KS>; };
+template <typename T, int TM, int NTHR, int TMI, int KS>
+struct OpsSel<T, TM, 0, NTHR, TMI, KS> { using type = OpsGeneric<T, TM>; };
 }  // namespace vsm
