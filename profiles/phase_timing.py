@@ -11,7 +11,7 @@ m = vb.synthetic_o2a_model(nSpec=444, aerosol=True)
 ctx = _lib.Context(0)
 prep = rr.prepare(m)
 rr.rt_run(m, ctx, prep)
-buf = (C.c_ulonglong * 16)()
+buf = (C.c_ulonglong * 24)()
 _lib.lib.vsm_debug_phase_cycles(buf, 1)
 rr.rt_run(m, ctx, prep)
 _lib.lib.vsm_debug_phase_cycles(buf, 0)
@@ -23,3 +23,8 @@ print("doublings", nd, "items", items, "ms", ctx.last_column_ms())
 for k, nme in enumerate(names):
     per = v[k] / (nd if 1 <= k <= 7 else items)
     print(f"{nme:22s} total {v[k]:.3e} cyc   per {'doubling' if 1 <= k <= 7 else 'item'}: {per:9.0f} cyc")
+
+iv = np.array(list(buf)[16:19], dtype=np.float64)
+steps = nd * 45
+print("inverse step (thread 0): loads+rcp+first FMAs %.0f | rest of FMAs+stores %.0f | barrier wait %.0f  cycles/step"
+      % tuple(iv / steps))

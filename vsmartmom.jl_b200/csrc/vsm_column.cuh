@@ -273,7 +273,9 @@ __device__ __forceinline__ void doubling_loop(const Ops& op, int nd, T expk, T*&
             j1p[i] = jp[i] * expk;
             j1m[i] = jm[i] * expk;
         }
-#ifdef VSM_DBL_LAMBDA
+#if defined(VSM_DBL_DMMA)
+        auto build = [&]() { op.template mm_dmma<2>(r, r, X1); };
+#elif defined(VSM_DBL_LAMBDA)
         const int ld = op.LD();
         auto build = [&]() {
             op.template mm<false>(r, r, [&](int i, int j, T acc) { X1[i + j * ld] = (i == j ? T(1) : T(0)) - acc; });
@@ -286,7 +288,9 @@ __device__ __forceinline__ void doubling_loop(const Ops& op, int nd, T expk, T*&
         VSM_TICK(1);
         op.inverse(X1, build);                                            // :104
         VSM_TICK(2);
-#ifdef VSM_DBL_LAMBDA
+#if defined(VSM_DBL_DMMA)
+        op.template mm_dmma<0>(t, X1, X2);
+#elif defined(VSM_DBL_LAMBDA)
         op.template mm<false>(t, X1, [&](int i, int j, T acc) { X2[i + j * ld] = acc; });
 #else
         op.template mmC<false, 0>(t, X1, X2);                             // X2 = t gp      (:105)
@@ -297,7 +301,14 @@ __device__ __forceinline__ void doubling_loop(const Ops& op, int nd, T expk, T*&
         op.mv2(X2, v1, v2, [&](int i, T s) { jm[i] = jm[i] + s; }, [&](int i, T s) { jp[i] = j1p[i] + s; });
         VSM_TICK(4);
         // doubling_rt_update! (:162-163)
-#ifdef VSM_DBL_LAMBDA
+#if defined(VSM_DBL_DMMA)
+        op.template mm_dmma<0>(r, t, X1);
+        VSM_TICK(5);
+        op.template mm_dmma<1>(X2, X1, r);
+        VSM_TICK(6);
+        op.template mm_dmma<0>(X2, t, X1);
+        VSM_TICK(7);
+#elif defined(VSM_DBL_LAMBDA)
         op.template mm<false>(r, t, [&](int i, int j, T acc) { X1[i + j * ld] = acc; });
         op.sync();
         VSM_TICK(5);

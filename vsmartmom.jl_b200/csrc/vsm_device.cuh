@@ -309,6 +309,20 @@ __device__ __forceinline__ T* rebase(const T* p) {
     return smem_base<T>() + (int)(p - smem_base<T>());
 }
 
+#ifdef VSM_PHASE_TIMING
+static __device__ unsigned long long vsm_inv_cycles[8];
+#define VSM_IT0() long long _it0 = clock64()
+#define VSM_ITICK(k)                                                             \
+    do {                                                                         \
+        long long _it1 = clock64();                                              \
+        if (tid == 0) atomicAdd(&vsm_inv_cycles[k], (unsigned long long)(_it1 - _it0)); \
+        _it0 = _it1;                                                             \
+    } while (0)
+#else
+#define VSM_IT0()
+#define VSM_ITICK(k)
+#endif
+
 // Named barrier over the NTHR threads of one Ops group (bar 0 == __syncthreads when
 // the group is the whole CTA).
 template <int NTHR, int BAR>
@@ -339,6 +353,10 @@ struct OpsFast {
 
     template <bool KSIGN, class Epi>
     __device__ __forceinline__ void mm(const T* __restrict__ A, const T* __restrict__ B, Epi epi) const {
+        if constexpr (sizeof(T) == 8 && (NTHR % 32 == 0) && (NTHR / 32 >= 4)) {
+            mm_dmma_epi<KSIGN>(A, B, epi);
+            return;
+        }
         if (tid < NT * NT) {
             const int i0 = (tid % NT) * TM, j0 = (tid / NT) * TM;
             const T* Ap = rebase(A) + i0;
@@ -435,6 +453,76 @@ struct OpsFast {
             }
             sync();
         }
+    }
+
+    // fp64 tensor-core GEMM (mma.sync m8n8k4): C = f(A*B), same MODEs as mmC.  Every lane of a
+    // fragment load reads a distinct element, so shared-memory traffic per FMA is ~3x lower than
+    // the broadcast-heavy register-tile SIMT product (which is shared-bandwidth-bound when all the
+    // CTAs of an SM are in their GEMM phase).  fp64 DMMA shares the FMA datapath on B200 (same
+    // 37 TFLOP/s, see profiles/microbench), so this is about operand bandwidth and issue slots.
+    // The 45x45 operands are used unpadded: rows/columns >= NN read neighbouring data that only
+    // lands in C rows/columns that are never stored; the K tail (k >= NN) is zeroed by predicate.
+    static constexpr int kNW = NTHR / 32;
+    static constexpr bool kDmma = (sizeof(T) == 8) && (NTHR % 32 == 0) && (kNW >= 4);
+    // warp grid of the DMMA product: 2 x 2 (4 warps: 24x24 per warp) or 2 x 3 (>= 6 warps: 24x16)
+    static constexpr int kWR = 2, kWC = (kNW >= 6) ? 3 : 2;
+    template <bool KSIGN, class Epi>
+    __device__ __forceinline__ void mm_dmma_epi(const T* __restrict__ A, const T* __restrict__ B, Epi epi) const {
+        constexpr int NP = (NN + 7) & ~7;                   // padded extent (48)
+        constexpr int TR = NP / 8 / kWR, TC = NP / 8 / kWC; // mma tiles per warp (rows, cols)
+        static_assert(NP / 8 % kWR == 0 && NP / 8 % kWC == 0, "warp tiling");
+        const int warp = tid >> 5, lane = tid & 31;
+        if (warp < kWR * kWC) {
+            const int g = lane >> 2, tg = lane & 3;
+            const int wi = (warp % kWR) * TR * 8, wj = (warp / kWR) * TC * 8;
+            const T* Ab = rebase(A) + wi + g + tg * kLd;      // A[wi+g (+8r)][k0+tg]
+            const T* Bb = rebase(B) + tg + (wj + g) * kLd;    // B[k0+tg][wj+g (+8c)]
+            double c[TR][TC][2];
+#pragma unroll
+            for (int r = 0; r < TR; ++r)
+#pragma unroll
+                for (int q = 0; q < TC; ++q) c[r][q][0] = c[r][q][1] = 0.0;
+#pragma unroll
+            for (int k0 = 0; k0 < NP; k0 += 4) {
+                double a[TR], b[TC];
+                const bool kin = (k0 + 3 < NN) || (k0 + tg < NN);
+                uint32_t mk = 0;
+                if (KSIGN) mk = kin ? dmask[k0 + tg] : 0u;
+#pragma unroll
+                for (int r = 0; r < TR; ++r) {
+                    a[r] = kin ? (double)Ab[r * 8 + k0 * kLd] : 0.0;
+                    if (KSIGN) a[r] = Num<double>::flip(a[r], mk);
+                }
+#pragma unroll
+                for (int q = 0; q < TC; ++q) b[q] = kin ? (double)Bb[k0 + q * 8 * kLd] : 0.0;
+#pragma unroll
+                for (int r = 0; r < TR; ++r)
+#pragma unroll
+                    for (int q = 0; q < TC; ++q)
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                     : "+d"(c[r][q][0]), "+d"(c[r][q][1]) : "d"(a[r]), "d"(b[q]));
+            }
+#pragma unroll
+            for (int r = 0; r < TR; ++r)
+#pragma unroll
+                for (int q = 0; q < TC; ++q)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int i = wi + r * 8 + g, j = wj + q * 8 + 2 * tg + h;
+                        if (i < NN && j < NN) epi(i, j, (T)c[r][q][h]);
+                    }
+        }
+    }
+    template <int MODE>
+    __device__ __forceinline__ void mm_dmma(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C) const {
+        T* Cb = rebase(C);
+        mm_dmma_epi<false>(A, B, [&](int i, int j, T v) {
+            T* p = Cb + i + j * kLd;
+            if (MODE == 1) *p += v;
+            else if (MODE == 2) *p = ((i == j) ? T(1) : T(0)) - v;
+            else *p = v;
+        });
+        sync();
     }
 
     // y = A x (one or two right-hand sides), k split over NTHR/RP segments
@@ -548,6 +636,7 @@ struct OpsFast {
                 const int cur = (k & 1) * NN, nxt = NN - cur;
                 const int d1 = (d + 1 < TMI) ? d + 1 : 0;
                 const int K1 = (d + 1 < TMI) ? K : K + 1;
+                VSM_IT0();
                 T ipv_next = T(0);
                 if (k1 < NN) {         // next pivot and its reciprocal: a thread-local recurrence
                     const T pn = fma(-colb[cur + k1], rowb[cur + k1], diab[cur + k1]);
@@ -581,6 +670,7 @@ struct OpsFast {
 #pragma unroll
                     for (int y = 0; y < TMI; ++y)
                         if (y != d1) m[d1][y] = fma(-c[d1], r[y], m[d1][y]);
+                    VSM_ITICK(0);
                     if (tj == K1) {
 #pragma unroll
                         for (int x = 0; x < TMI; ++x) colb[nxt + i0 + x] = m[x][d1];
@@ -600,7 +690,9 @@ struct OpsFast {
                     }
                 }
                 ipv = ipv_next;
+                VSM_ITICK(1);
                 sync();
+                VSM_ITICK(2);
             }
         }
         if (mybad) *bad = 1;
