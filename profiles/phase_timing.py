@@ -11,7 +11,7 @@ m = vb.synthetic_o2a_model(nSpec=444, aerosol=True)
 ctx = _lib.Context(0)
 prep = rr.prepare(m)
 rr.rt_run(m, ctx, prep)
-buf = (C.c_ulonglong * 24)()
+buf = (C.c_ulonglong * 40)()
 _lib.lib.vsm_debug_phase_cycles(buf, 1)
 rr.rt_run(m, ctx, prep)
 _lib.lib.vsm_debug_phase_cycles(buf, 0)
@@ -28,3 +28,13 @@ iv = np.array(list(buf)[16:19], dtype=np.float64)
 steps = nd * 45
 print("inverse step (thread 0): loads+rcp+first FMAs %.0f | rest of FMAs+stores %.0f | barrier wait %.0f  cycles/step"
       % tuple(iv / steps))
+
+av = np.array(list(buf)[24:34], dtype=np.float64)
+steps11 = 33 * 20 * 444
+an = ["load added layer", "M1 = I - r RB", "inverse 1", "T01, J0- (2 mv)", "X3, RA+=, TD", "M2 = I - RB r", "inverse 2",
+      "T21, J0+ (2 mv)", "TC, Y, RB", "whole interaction step"]
+print("k_adding per layer step (thread 0 cycles):")
+for k, nme in enumerate(an):
+    print(f"  {nme:24s} {av[k] / steps11:9.0f}")
+
+print("inverse calls", buf[16 + 6], "pivoted fallbacks", buf[16 + 7])

@@ -28,9 +28,19 @@ static __device__ unsigned long long vsm_phase_cycles[16];
         if (threadIdx.x == 0) atomicAdd(&vsm_phase_cycles[k], (unsigned long long)(_t1 - _t0)); \
         _t0 = _t1;                                                               \
     } while (0)
+static __device__ unsigned long long vsm_add_cycles[16];
+#define VSM_A0() long long _a0 = clock64()
+#define VSM_ATICK(k)                                                             \
+    do {                                                                         \
+        long long _a1 = clock64();                                               \
+        if (threadIdx.x == 0) atomicAdd(&vsm_add_cycles[k], (unsigned long long)(_a1 - _a0)); \
+        _a0 = _a1;                                                               \
+    } while (0)
 #else
 #define VSM_T0()
 #define VSM_TICK(k)
+#define VSM_A0()
+#define VSM_ATICK(k)
 #endif
 
 // ----------------------------------------------------------------------------
@@ -435,13 +445,17 @@ __device__ __forceinline__ void interact(const Ops& op, int iface, CompPtrs<T>& 
                 at(c.X1, i, j) = (i == j ? T(1) : T(0)) - acc;
             });
         };
+        VSM_A0();
         build1();
         __syncthreads();
+        VSM_ATICK(1);
         op.inverse(c.X1, build1);
+        VSM_ATICK(2);
         op.template mm<false>(c.TD, c.X1, [&](int i, int j, T acc) { at(c.X2, i, j) = acc; });
         // J₀⁻ += T01_inv (r⁻⁺ J₀⁺ + j₀⁻)                                   (:229)
         op.template mv<false>(c.r, J0p, [&](int i, T s) { v1[i] = s + jm[i]; });
         op.template mv<false>(c.X2, v1, [&](int i, T s) { J0m[i] = J0m[i] + s; });
+        VSM_ATICK(3);
         // R⁻⁺ += T01_inv r⁻⁺ T⁺⁺                                          (:237)
         op.template mm<false>(c.X2, c.r, [&](int i, int j, T acc) { at(c.X3, i, j) = acc; });
         __syncthreads();
@@ -455,6 +469,7 @@ __device__ __forceinline__ void interact(const Ops& op, int iface, CompPtrs<T>& 
             });
         }
         __syncthreads();
+        VSM_ATICK(4);
         // temp2 = I - R⁺⁻ r⁻⁺ ; inv ; T21_inv = t⁺⁺ temp1                  (:248-251)
         auto build2 = [&]() {
             op.template mm<false>(c.RB, c.r, [&](int i, int j, T acc) {
@@ -463,7 +478,9 @@ __device__ __forceinline__ void interact(const Ops& op, int iface, CompPtrs<T>& 
         };
         build2();
         __syncthreads();
+        VSM_ATICK(5);
         op.inverse(c.X1, build2);
+        VSM_ATICK(6);
         T* T21;
         if (t_ident) {
             T21 = c.X1;
@@ -474,6 +491,7 @@ __device__ __forceinline__ void interact(const Ops& op, int iface, CompPtrs<T>& 
         // J₀⁺ = j₀⁺ + T21_inv (J₀⁺ + R⁺⁻ j₀⁻)                              (:254)
         op.template mv<false>(c.RB, jm, [&](int i, T s) { v1[i] = J0p[i] + s; });
         op.template mv<false>(T21, v1, [&](int i, T s) { J0p[i] = jp[i] + s; });
+        VSM_ATICK(7);
         // T⁺⁺ = T21_inv T⁺⁺                                               (:262)
         op.template mm<false>(T21, c.TC, [&](int i, int j, T acc) { at(c.X3, i, j) = acc; });
         __syncthreads();
@@ -497,6 +515,7 @@ __device__ __forceinline__ void interact(const Ops& op, int iface, CompPtrs<T>& 
             });
         }
         __syncthreads();
+        VSM_ATICK(8);
     } else if (iface == 1) {
         // J₀⁻ += T⁻⁻ (r⁻⁺ J₀⁺ + j₀⁻) ; J₀⁺ = j₀⁺ + t⁺⁺ J₀⁺                  (:104-105)
         op.template mv<false>(c.r, J0p, [&](int i, T s) { v1[i] = s + jm[i]; });
@@ -615,6 +634,7 @@ __global__ void __launch_bounds__(NTHR) k_adding(ColArgs<T> a, unsigned int tota
         const int m = a.m0 + mi;
         CompPtrs<T> c{mat(0), mat(1), mat(2), mat(3), mat(4), mat(5), mat(6), mat(7), mat(8)};
         for (int iz = 0; iz < a.Nz; ++iz) {
+            VSM_A0();
             const bool sc = a.scatter[iz] != 0;
             T* dr = (iz == 0) ? c.RA : c.r;
             T* dt = (iz == 0) ? c.TC : c.t;
@@ -644,6 +664,7 @@ __global__ void __launch_bounds__(NTHR) k_adding(ColArgs<T> a, unsigned int tota
                 for (int i = threadIdx.x; i < n; i += blockDim.x) { djp[i] = T(0); djm[i] = T(0); }
             }
             __syncthreads();
+            VSM_ATICK(0);
             if (iz == 0) {
                 // copy_added_to_composite! (rt_helpers.jl:204-215)
                 for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
@@ -656,6 +677,7 @@ __global__ void __launch_bounds__(NTHR) k_adding(ColArgs<T> a, unsigned int tota
             } else {
                 interact<T, Ops>(op, a.iface[iz], c, J0p, J0m, jp, jm, v1, !sc, false);
             }
+            VSM_ATICK(9);
         }
         // ---- Lambertian surface (lambertian_surface.jl:41-95) + last interaction (rt_run.jl:459-465)
         const T ts_end = a.p_tausum[(size_t)a.Nz * a.nS + p];

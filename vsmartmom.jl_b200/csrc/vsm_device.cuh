@@ -593,6 +593,203 @@ struct OpsFast {
     // the partial-pivoting routine, so the result is always that of a stable elimination.
     template <class Rebuild>
     __device__ __forceinline__ void inverse(T* M, Rebuild rebuild) const {
+        if constexpr (kDmma) inverse_blk(M, rebuild);
+        else inverse_rank1(M, rebuild);
+    }
+
+    // ---- blocked in-place Gauss-Jordan inverse on the fp64 tensor cores -------------------
+    // The matrix is distributed over the warps as register-resident 8x8 DMMA accumulator tiles
+    // (warp grid kWR x kWC, TR x TC tiles each) for the whole inversion; its shared-memory buffer
+    // is reused as double-buffered staging for the panels.  Block step K (fully unrolled):
+    //   a. owners stage the OLD row panel X_j = M_Kj and column panel C_i = M_iK; the owner warp of
+    //      M_KK inverts it with shuffles (8 rank-1 steps, no CTA barrier) and stages P.     [barrier]
+    //   b. column owners: M_iK <- L_i = -C_i P (staged for everyone); row owners: M_Kj <- P X_j;
+    //      M_KK <- P.                                                                       [barrier]
+    //   c. trailing update of every other tile:  M_ij += L_i X_j   (= M_ij - M_iK P M_Kj).
+    // 6 block steps x 2 barriers replace 45 barrier-separated rank-1 steps and all O(N^3) work is
+    // m8n8k4 products.  Rows/cols >= NN are a virtual identity.  No inter-block pivoting: each pivot
+    // inside a diagonal block is checked against |a_ik| <= 4|a_kk| and each multiplier against
+    // |L_ab| <= 16; on a violation the matrix is rebuilt and inverted with partial pivoting.
+    template <class Rebuild>
+    __device__ __forceinline__ void inverse_blk(T* M, Rebuild rebuild) const {
+        constexpr int NP = (NN + 7) & ~7, NB = NP / 8;
+        constexpr int TR = NB / kWR, TC = NB / kWC;
+        constexpr int RLD = 12, CLD = NP + 4, PLD = 12;            // conflict-free fragment strides
+        constexpr int SET = RLD * NP + CLD * 8;                    // one staging set (row + column panel)
+        static_assert(2 * SET <= NN * (NN | 1), "staging must fit in the matrix buffer");
+        static_assert(2 * PLD * 8 <= 13 * NN, "P staging must fit in vec+part");
+        double* Ms = reinterpret_cast<double*>(rebase(M));
+        double* Pst = reinterpret_cast<double*>(rebase(vec));      // 2 x (8 x 8, ld PLD)
+        int* bad = piv + NN;
+        const int warp = tid >> 5, lane = tid & 31;
+        const int g = lane >> 2, tg = lane & 3;
+        const bool wact = warp < kWR * kWC;
+        const int wr = warp % kWR, wc = warp / kWR;
+        if (tid == 0) *bad = 0;
+        bool mybad = false;
+        auto mma = [](double& c0, double& c1, double a, double b) {
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+        };
+        // ---- load the register tiles (virtual identity outside NN x NN)
+        double c[TR][TC][2];
+        if (wact) {
+#pragma unroll
+            for (int r = 0; r < TR; ++r)
+#pragma unroll
+                for (int q = 0; q < TC; ++q)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int i = (wr * TR + r) * 8 + g, j = (wc * TC + q) * 8 + 2 * tg + h;
+                        c[r][q][h] = (i < NN && j < NN) ? Ms[i + j * kLd] : ((i == j) ? 1.0 : 0.0);
+                    }
+        }
+        sync();                                                    // everyone has read M before staging reuses it
+#pragma unroll
+        for (int K = 0; K < NB; ++K) {
+            double* rowb = Ms + (K & 1) * SET;                     // X: 8 x NP, ld RLD  (element [k][j] at k + j*RLD)
+            double* colb = rowb + RLD * NP;                        // C/L: NP x 8, ld CLD (element [i][k] at i + k*CLD)
+            double* Ps = Pst + (K & 1) * PLD * 8;                  // P: 8 x 8, ld PLD
+            constexpr int KR = 0; (void)KR;
+            const int kr = K / TR, kq = K / TC;                    // warp-grid coordinates of the pivot block
+            const int r0 = K % TR, q0 = K % TC;                    // its position inside the owner warp
+            // ---- a. stage old panels; invert the pivot block
+            if (wact) {
+                if (wr == kr) {                                    // I own tiles (K, j): stage X_j
+#pragma unroll
+                    for (int q = 0; q < TC; ++q) {
+                        const int jo = (wc * TC + q) * 8;
+                        rowb[g + (jo + 2 * tg) * RLD] = c[r0][q][0];
+                        rowb[g + (jo + 2 * tg + 1) * RLD] = c[r0][q][1];
+                    }
+                }
+                if (wc == kq) {                                    // I own tiles (i, K): stage C_i
+#pragma unroll
+                    for (int r = 0; r < TR; ++r) {
+                        const int io = (wr * TR + r) * 8;
+                        colb[io + g + (2 * tg) * CLD] = c[r][q0][0];
+                        colb[io + g + (2 * tg + 1) * CLD] = c[r][q0][1];
+                    }
+                }
+                if (wr == kr && wc == kq) {                        // pivot-block inverse (this warp only)
+                    double d0 = c[r0][q0][0], d1 = c[r0][q0][1];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const double x0 = __shfl_sync(0xffffffffu, d0, 4 * k + tg);          // D[k][2tg]
+                        const double x1 = __shfl_sync(0xffffffffu, d1, 4 * k + tg);          // D[k][2tg+1]
+                        const double cv = __shfl_sync(0xffffffffu, (k & 1) ? d1 : d0, 4 * g + (k >> 1));   // D[g][k]
+                        const double pv = __shfl_sync(0xffffffffu, (k & 1) ? d1 : d0, 4 * k + (k >> 1));   // D[k][k]
+                        const uint32_t kp = Num<double>::key(pv);
+                        if (kp < Num<double>::kKeyMin || kp > Num<double>::kKeyMax) mybad = true;
+                        if (g != k && Num<double>::key(cv) > kp + Num<double>::kKeyTimes4) mybad = true;
+                        const double ipv = Num<double>::rcp(pv);
+                        const double cc = (g == k) ? pv - 1.0 : cv;
+                        const double y0 = (2 * tg == k) ? 1.0 + ipv : x0 * ipv;
+                        const double y1 = (2 * tg + 1 == k) ? 1.0 + ipv : x1 * ipv;
+                        d0 = fma(-cc, y0, d0);
+                        d1 = fma(-cc, y1, d1);
+                    }
+                    c[r0][q0][0] = d0;                             // M_KK <- P
+                    c[r0][q0][1] = d1;
+                    Ps[g + (2 * tg) * PLD] = d0;
+                    Ps[g + (2 * tg + 1) * PLD] = d1;
+                }
+            }
+            sync();
+            // ---- b. panels
+            if (wact) {
+                if (wc == kq) {                                    // L_i = -C_i P   (A = C_i, B = P)
+                    const double pb0 = Ps[tg + g * PLD], pb1 = Ps[4 + tg + g * PLD];
+#pragma unroll
+                    for (int r = 0; r < TR; ++r) {
+                        const int io = (wr * TR + r) * 8;
+                        if (!(wr == kr && r == r0)) {
+                            const double a0 = -colb[io + g + tg * CLD], a1 = -colb[io + g + (4 + tg) * CLD];
+                            double l0 = 0.0, l1 = 0.0;
+                            mma(l0, l1, a0, pb0);
+                            mma(l0, l1, a1, pb1);
+                            if (Num<double>::key(l0) > 0x40300000u || Num<double>::key(l1) > 0x40300000u) mybad = true;
+                            c[r][q0][0] = l0;
+                            c[r][q0][1] = l1;
+                            __syncwarp();
+                            colb[io + g + (2 * tg) * CLD] = l0;    // publish L_i over C_i (rows owned by this warp)
+                            colb[io + g + (2 * tg + 1) * CLD] = l1;
+                        }
+                    }
+                }
+                if (wr == kr) {                                    // M_Kj <- P X_j  (A = P, B = X_j)
+                    const double pa0 = Ps[g + tg * PLD], pa1 = Ps[g + (4 + tg) * PLD];
+#pragma unroll
+                    for (int q = 0; q < TC; ++q) {
+                        const int jo = (wc * TC + q) * 8;
+                        if (!(wc == kq && q == q0)) {
+                            const double b0 = rowb[tg + (jo + g) * RLD], b1 = rowb[4 + tg + (jo + g) * RLD];
+                            double n0 = 0.0, n1 = 0.0;
+                            mma(n0, n1, pa0, b0);
+                            mma(n0, n1, pa1, b1);
+                            c[r0][q][0] = n0;
+                            c[r0][q][1] = n1;
+                        }
+                    }
+                }
+            }
+            sync();
+            // ---- c. trailing update  M_ij += L_i X_j   (i != K, j != K)
+            if (wact) {
+                double la[TR][2], xb[TC][2];
+#pragma unroll
+                for (int r = 0; r < TR; ++r) {
+                    const int io = (wr * TR + r) * 8;
+                    la[r][0] = colb[io + g + tg * CLD];
+                    la[r][1] = colb[io + g + (4 + tg) * CLD];
+                }
+#pragma unroll
+                for (int q = 0; q < TC; ++q) {
+                    const int jo = (wc * TC + q) * 8;
+                    xb[q][0] = rowb[tg + (jo + g) * RLD];
+                    xb[q][1] = rowb[4 + tg + (jo + g) * RLD];
+                }
+#pragma unroll
+                for (int r = 0; r < TR; ++r)
+#pragma unroll
+                    for (int q = 0; q < TC; ++q) {
+                        const bool skip = (wr == kr && r == r0) || (wc == kq && q == q0);
+                        if (!skip) {
+                            mma(c[r][q][0], c[r][q][1], la[r][0], xb[q][0]);
+                            mma(c[r][q][0], c[r][q][1], la[r][1], xb[q][1]);
+                        }
+                    }
+            }
+        }
+        if (mybad) *bad = 1;
+        sync();                                                    // staging no longer read
+        if (wact) {
+#pragma unroll
+            for (int r = 0; r < TR; ++r)
+#pragma unroll
+                for (int q = 0; q < TC; ++q)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int i = (wr * TR + r) * 8 + g, j = (wc * TC + q) * 8 + 2 * tg + h;
+                        if (i < NN && j < NN) Ms[i + j * kLd] = c[r][q][h];
+                    }
+        }
+        sync();
+        if (*bad) {                       // uniform over the group
+#ifdef VSM_PHASE_TIMING
+            if (tid == 0) atomicAdd(&vsm_inv_cycles[7], 1ull);
+#endif
+            rebuild();
+            sync();
+            group_inverse_pivoted(M);
+        }
+#ifdef VSM_PHASE_TIMING
+        if (tid == 0) atomicAdd(&vsm_inv_cycles[6], 1ull);
+#endif
+    }
+
+    template <class Rebuild>
+    __device__ __forceinline__ void inverse_rank1(T* M, Rebuild rebuild) const {
         T* colb = rebase(vec);           // [2][NN]
         T* rowb = colb + 2 * NN;         // [2][NN]
         T* diab = rebase(part);          // [2][NN]  (part is free during the inverse)
