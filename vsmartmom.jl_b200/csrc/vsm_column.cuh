@@ -184,55 +184,82 @@ __device__ __forceinline__ void elemental_fill(const ColArgs<T>& a, int m, int n
                                                const T* __restrict__ Zpp, const T* __restrict__ Zmp,
                                                size_t zstride, const T* __restrict__ F0n,
                                                const uint32_t* __restrict__ dmask,
-                                               T* r, T* t, T* jp, T* jm, T* rowtmp /* >= 3n */) {
+                                               T* r, T* t, T* jp, T* jm, T* rowtmp /* >= 5n */) {
     const int n = NN ? NN : a.N, ld = NN ? (NN | 1) : a.ld, nC = a.nC;
     const T wsc = (m == 0) ? T(0.5) : T(0.25);       // scaled_weights / fourier_weight
     const T eps = Num<T>::eps();
     // per-stream quantities: a_i = dtau/mu_i, e_i = exp(-a_i), em1_i = expm1(-a_i)
-    T* ai = rowtmp; T* ei = rowtmp + n; T* em1 = rowtmp + 2 * n;
+    T* ai = rowtmp; T* ei = rowtmp + n; T* em1 = rowtmp + 2 * n; T* smu = rowtmp + 3 * n; T* swt = rowtmp + 4 * n;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const T x = dtau / a.mu[i];
+        const T mi = a.mu[i];
+        const T x = dtau / mi;
         ai[i] = x;
         ei[i] = Num<T>::exp_(-x);
         em1[i] = Num<T>::expm1_(-x);
+        smu[i] = mi;
+        swt[i] = a.wt[i];
     }
     __syncthreads();
     const T vw = varpi * wsc;
-    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-        const int i = e % n, j = e / n;
-        T zm = T(0), zp = T(0);
-        if (nC == 1) {
-            zm = Zmp[e]; zp = Zpp[e];
-        } else {
-            for (int c = 0; c < nC; ++c) {
-                zm = fma(Wc[c], Zmp[(size_t)c * zstride + e], zm);
-                zp = fma(Wc[c], Zpp[(size_t)c * zstride + e], zp);
-            }
-        }
-        const T wj = a.wt[j] * wsc;
-        T rv, tv;
-        if (wj > eps) {
-            // 1 - exp(-(a_i+a_j)) = -(em1_i + em1_j + em1_i em1_j)      (elemental.jl:298-302)
-            const T xi = em1[i], xj = em1[j];
-            rv = vw * zm * a.geo1[e] * (-(xi + xj + xi * xj));
-            const T mui = a.mu[i], muj = a.mu[j];
-            if (mui == muj) {                                            // (:304-314)
-                tv = (i == j) ? ei[i] * (T(1) + varpi * zp * ai[i] * wj) : ei[j] * (varpi * zp * ai[i] * wj);
+    // element loop, 4 elements per thread per trip: all global (L2) table loads of a trip are issued
+    // before any use so their latency overlaps (the arena leaves almost no L1)
+    constexpr int U = 4;
+    const int nn = n * n;
+    const T w0 = Wc[0], w1 = (nC > 1) ? Wc[1] : T(0);
+    for (int e0 = threadIdx.x; e0 < nn; e0 += U * blockDim.x) {
+        T zmv[U], zpv[U], g1v[U], g2v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = min(e0 + u * (int)blockDim.x, nn - 1);
+            if (nC == 1) {
+                zmv[u] = Zmp[e]; zpv[u] = Zpp[e];
+            } else if (nC == 2) {
+                const T a0 = Zmp[e], a1 = Zmp[zstride + e], b0 = Zpp[e], b1 = Zpp[zstride + e];
+                zmv[u] = fma(w1, a1, fma(w0, a0, T(0)));
+                zpv[u] = fma(w1, b1, fma(w0, b0, T(0)));
             } else {
-                // exp(-a_i) - exp(-a_j) = em1_i - em1_j ; the exact expdiff_neg form (rt_helpers.jl:32-40)
-                // is used for nearly coincident streams where that difference would cancel
-                T dif;
-                if (Num<T>::abs_(mui - muj) > T(1e-3) * muj) dif = xi - xj;
-                else dif = expdiff_neg<T>(ai[i], ai[j]);
-                tv = vw * zp * a.geo2[e] * dif;                          // (:319-323)
+                T zm = T(0), zp = T(0);
+                for (int c = 0; c < nC; ++c) {
+                    zm = fma(Wc[c], Zmp[(size_t)c * zstride + e], zm);
+                    zp = fma(Wc[c], Zpp[(size_t)c * zstride + e], zp);
+                }
+                zmv[u] = zm; zpv[u] = zp;
             }
-        } else {
-            rv = T(0);
-            tv = (i == j) ? ei[i] : T(0);
+            g1v[u] = a.geo1[e];
+            g2v[u] = a.geo2[e];
         }
-        if (nd >= 1) rv = Num<T>::flip(rv, dmask[i]);      // apply_D_elemental!, nd>=1 branch
-        r[i + j * ld] = rv;
-        t[i + j * ld] = tv;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * (int)blockDim.x;
+            if (e < nn) {
+                const int i = e % n, j = e / n;
+                const T zm = zmv[u], zp = zpv[u];
+                const T wj = swt[j] * wsc;
+                T rv, tv;
+                if (wj > eps) {
+                    // 1 - exp(-(a_i+a_j)) = -(em1_i + em1_j + em1_i em1_j)      (elemental.jl:298-302)
+                    const T xi = em1[i], xj = em1[j];
+                    rv = vw * zm * g1v[u] * (-(xi + xj + xi * xj));
+                    const T mui = smu[i], muj = smu[j];
+                    if (mui == muj) {                                            // (:304-314)
+                        tv = (i == j) ? ei[i] * (T(1) + varpi * zp * ai[i] * wj) : ei[j] * (varpi * zp * ai[i] * wj);
+                    } else {
+                        // exp(-a_i) - exp(-a_j) = em1_i - em1_j ; the exact expdiff_neg form (rt_helpers.jl:32-40)
+                        // is used for nearly coincident streams where that difference would cancel
+                        T dif;
+                        if (Num<T>::abs_(mui - muj) > T(1e-3) * muj) dif = xi - xj;
+                        else dif = expdiff_neg<T>(ai[i], ai[j]);
+                        tv = vw * zp * g2v[u] * dif;                             // (:319-323)
+                    }
+                } else {
+                    rv = T(0);
+                    tv = (i == j) ? ei[i] : T(0);
+                }
+                if (nd >= 1) rv = Num<T>::flip(rv, dmask[i]);      // apply_D_elemental!, nd>=1 branch
+                r[i + j * ld] = rv;
+                t[i + j * ld] = tv;
+            }
+        }
     }
     const T wct02 = wsc;
     const T mus = a.mu[a.istart];
