@@ -571,13 +571,60 @@ struct OpsFast {
         }
         sync();
     }
+    // y = A x for one or two right-hand sides on the fp64 tensor cores: X = [x1 x2 0 ...] is the
+    // 8-column B operand; warp w takes row tiles w, w+NWU, ...  Ends with the group synchronised.
+    template <bool KSIGN, int NV, class E1, class E2>
+    __device__ __forceinline__ void mv_dmma(const T* __restrict__ A, const T* __restrict__ x1,
+                                            const T* __restrict__ x2, E1 e1, E2 e2) const {
+        constexpr int NP = (NN + 7) & ~7, NB = NP / 8;
+        constexpr int NWU = (kNW < NB) ? kNW : NB;
+        constexpr int REP = (NB + NWU - 1) / NWU;
+        const int warp = tid >> 5, lane = tid & 31;
+        const int g = lane >> 2, tg = lane & 3;
+        const T* Ab = rebase(A) + g + tg * kLd;
+        const T* xs = rebase((NV == 2 && g == 1) ? x2 : x1);
+        const bool xin = (g < NV);
+        if (warp < NWU) {
+            double c[REP][2];
+#pragma unroll
+            for (int r = 0; r < REP; ++r) c[r][0] = c[r][1] = 0.0;
+#pragma unroll
+            for (int k0 = 0; k0 < NP; k0 += 4) {
+                const bool kin = (k0 + 3 < NN) || (k0 + tg < NN);
+                double b = (xin && kin) ? (double)xs[k0 + tg] : 0.0;
+                if (KSIGN && kin) b = Num<double>::flip(b, dmask[k0 + tg]);
+#pragma unroll
+                for (int r = 0; r < REP; ++r) {
+                    const int io = (warp + r * NWU) * 8;
+                    if (io < NP) {
+                        const double a = kin ? (double)Ab[io + k0 * kLd] : 0.0;
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                     : "+d"(c[r][0]), "+d"(c[r][1]) : "d"(a), "d"(b));
+                    }
+                }
+            }
+            if (tg == 0) {
+#pragma unroll
+                for (int r = 0; r < REP; ++r) {
+                    const int i = (warp + r * NWU) * 8 + g;
+                    if (i < NN) {
+                        e1(i, (T)c[r][0]);
+                        if (NV == 2) e2(i, (T)c[r][1]);
+                    }
+                }
+            }
+        }
+        sync();
+    }
     template <bool KSIGN, class Epi>
     __device__ __forceinline__ void mv(const T* A, const T* x, Epi epi) const {
-        mv_impl<KSIGN, 1>(A, x, x, epi, epi);
+        if constexpr (kDmma) mv_dmma<KSIGN, 1>(A, x, x, epi, epi);
+        else mv_impl<KSIGN, 1>(A, x, x, epi, epi);
     }
     template <class E1, class E2>
     __device__ __forceinline__ void mv2(const T* A, const T* x1, const T* x2, E1 e1, E2 e2) const {
-        mv_impl<false, 2>(A, x1, x2, e1, e2);
+        if constexpr (kDmma) mv_dmma<false, 2>(A, x1, x2, e1, e2);
+        else mv_impl<false, 2>(A, x1, x2, e1, e2);
     }
 
     // In-place inverse.  Register-resident Gauss-Jordan on the diagonal pivots, one
