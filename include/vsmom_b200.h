@@ -54,6 +54,13 @@ const char* vsm_last_error(vsm_ctx* ctx);       /* ctx may be NULL: last create 
 int  vsm_synchronize(vsm_ctx* ctx);             /* Architectures._sync_gpu[] (ext/vSmartMOMCUDAExt.jl:55) */
 /* cap (bytes) on the library-owned scratch used by vsm_rt_column_*; 0 = default */
 int  vsm_set_workspace_limit(vsm_ctx* ctx, uint64_t bytes);
+/* how (I - A)^-1 of doubling (rt_helpers.jl:103-104) and interaction (interaction.jl:220-222,
+ * :248-249) is evaluated by the specialised fp64 kernels.  1 (default): the Frobenius norm nu of
+ * A is measured; if nu^K/(1-nu) < 1e-20 for K in {2,4,8} the Neumann product form
+ * (I+A)(I+A^2)(I+A^4) truncated at order K is summed on the tensor cores (bit-level equivalent to
+ * the elimination at fp64 precision), otherwise blocked Gauss-Jordan.  0: always Gauss-Jordan
+ * (the reference's getrf/getri route, cpu_batched.jl:32-37). */
+int  vsm_set_inverse_mode(vsm_ctx* ctx, int mode);
 /* number of kernels this context has launched since creation (bench bookkeeping) */
 uint64_t vsm_kernel_launches(vsm_ctx* ctx);
 /* roofline denominator: measured register-resident FMA throughput (TFLOP/s) of this

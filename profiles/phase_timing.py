@@ -11,11 +11,11 @@ m = vb.synthetic_o2a_model(nSpec=444, aerosol=True)
 ctx = _lib.Context(0)
 prep = rr.prepare(m)
 rr.rt_run(m, ctx, prep)
-buf = (C.c_ulonglong * 40)()
+buf = (C.c_ulonglong * 56)()
 _lib.lib.vsm_debug_phase_cycles(buf, 1)
 rr.rt_run(m, ctx, prep)
 _lib.lib.vsm_debug_phase_cycles(buf, 0)
-names = ["elemental", "mm r*r (+j1)", "inverse", "mm t*G", "mv2 x2", "mm r*t", "mm r+=tt*Y", "mm tt*t", "doubling loop total", "store"]
+names = ["elemental", "(unused)", "(I - r r)^-1", "mm t*G", "mv2 x2", "mm r*t", "mm r+=tt*Y", "mm tt*t", "doubling loop total", "store"]
 v = np.array(list(buf)[:10], dtype=np.float64)
 nd = prep.ctl.ndoubl.sum() * 20 * 444
 items = 34 * 20 * 444
@@ -24,10 +24,12 @@ for k, nme in enumerate(names):
     per = v[k] / (nd if 1 <= k <= 7 else items)
     print(f"{nme:22s} total {v[k]:.3e} cyc   per {'doubling' if 1 <= k <= 7 else 'item'}: {per:9.0f} cyc")
 
-iv = np.array(list(buf)[16:19], dtype=np.float64)
-steps = nd * 45
-print("inverse step (thread 0): loads+rcp+first FMAs %.0f | rest of FMAs+stores %.0f | barrier wait %.0f  cycles/step"
-      % tuple(iv / steps))
+inames = ["load tiles + sync", "a: stage + pivot block", "a: barrier wait", "b: panels", "b: barrier wait", "c: trailing update"]
+for lbl, off, calls in (("k_layer", 16, nd), ("k_adding2 (per group)", 40, 2 * 33 * 20 * 444)):
+    iv = np.array(list(buf)[off:off + 6], dtype=np.float64) / max(calls, 1)
+    print(f"blocked inverse in {lbl}: thread-0 cycles per call, total {iv.sum():.0f}")
+    for k, nme in enumerate(inames):
+        print(f"  {nme:26s} {iv[k]:9.0f}")
 
 av = np.array(list(buf)[24:34], dtype=np.float64)
 steps11 = 33 * 20 * 444
@@ -37,4 +39,5 @@ print("k_adding per layer step (thread 0 cycles):")
 for k, nme in enumerate(an):
     print(f"  {nme:24s} {av[k] / steps11:9.0f}")
 
-print("inverse calls", buf[16 + 6], "pivoted fallbacks", buf[16 + 7])
+print("inverse calls", buf[16 + 6] + buf[40 + 6], "pivoted fallbacks", buf[16 + 7] + buf[40 + 7])
+print("(I - A)^-1 routes  [K=2, K=4, K=8, Gauss-Jordan]:  k_layer", list(buf[48:52]), " k_adding2", list(buf[52:56]))

@@ -58,6 +58,40 @@ def test_o2a_vector_config_f64(ctx, aerosol, nspec, nref):
     assert_close(out, ref, F64_TOL, sel=slice(0, nref))
 
 
+def thick_o2a_model(nspec, scale):
+    """configs[1] shape with the scattering optical depths scaled up so that ||r r|| and ||r R|| of
+    the doubling / adding steps span every route of the adaptive inverse (Neumann K=2,4,8 and
+    Gauss-Jordan)."""
+    m = vb.synthetic_o2a_model(nSpec=nspec, aerosol=True, albedo=0.8)
+    m.tau_rayl = m.tau_rayl * scale
+    m.tau_aer = m.tau_aer * scale
+    # a 12-point grid sits in a line wing that the generator normalises to tau_abs = 100;
+    # spread the column absorption over 1e-3 .. 30 instead
+    m.tau_abs = m.tau_abs * np.logspace(-5.0, -0.5, nspec)[:, None]
+    return m
+
+
+@pytest.mark.parametrize("scale", [1.0, 8.0, 40.0])
+def test_inverse_routes_match_oracle_and_each_other(ctx, scale):
+    # vsm_set_inverse_mode: 1 = adaptive Neumann / Gauss-Jordan (default), 0 = Gauss-Jordan only
+    m = thick_o2a_model(12, scale)
+    ref = orc.rt_run(to_oracle(m))
+    try:
+        ctx.set_inverse_mode(0)
+        gj = run_gpu(m, ctx)
+        ctx.set_inverse_mode(1)
+        ad = run_gpu(m, ctx)
+    finally:
+        ctx.set_inverse_mode(1)
+    assert_close(gj, ref, F64_TOL)
+    assert_close(ad, ref, F64_TOL)
+    # the two routes differ by rounding only: on this (albedo 0.8, up to 16 doublings) problem the
+    # fp64 LAPACK oracle itself sits 6e-12..3e-11 from an 80-bit evaluation, and so do both routes
+    # (oracle/check_inverse_routes_longdouble.py)
+    for k in KEYS:
+        assert relerr(ad[k], gj[k]) <= 5e-10, k
+
+
 @pytest.mark.parametrize("pol", ["Stokes_I", "Stokes_IQ", "Stokes_IQUV"])
 def test_other_polarisations(ctx, pol):
     m = vb.synthetic_o2a_model(nSpec=8, nstreams=4, polarization_type=pol, aerosol=True)

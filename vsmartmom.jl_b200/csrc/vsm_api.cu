@@ -28,6 +28,7 @@ struct vsm_ctx {
     int num_sms = 0;
     int max_smem_optin = 0;
     uint64_t ws_limit = 0;
+    int inverse_mode = 1;   // 1: adaptive Neumann / Gauss-Jordan, 0: Gauss-Jordan only
     uint64_t launches = 0;
     std::string err;
     // grow-only scratch
@@ -137,6 +138,12 @@ extern "C" int vsm_synchronize(vsm_ctx* ctx) {
 extern "C" int vsm_set_workspace_limit(vsm_ctx* ctx, uint64_t bytes) {
     if (!ctx) return VSM_ERR_INVALID_ARG;
     ctx->ws_limit = bytes;
+    return VSM_OK;
+}
+
+extern "C" int vsm_set_inverse_mode(vsm_ctx* ctx, int mode) {
+    if (!ctx || (mode != 0 && mode != 1)) return VSM_ERR_INVALID_ARG;
+    ctx->inverse_mode = mode;
     return VSM_OK;
 }
 
@@ -521,7 +528,7 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
         memset(&a, 0, sizeof a);
         a.N = N; a.nStokes = nSt; a.Nz = Nz; a.nC = nC; a.nVZA = nV; a.ld = ld;
         a.istart = (d->imu0 - 1) * nSt;
-        a.nS = nS; a.n_sched_layers = nSched; a.z_spectral = 0; a.mz0 = 0;
+        a.nS = nS; a.n_sched_layers = nSched; a.z_spectral = 0; a.mz0 = 0; a.neumann = ctx->inverse_mode;
         a.mu0 = (T)d->mu0; a.albedo = (T)d->albedo;
         a.mu = cT + o_mu; a.wt = cT + o_wt;
         a.ndoubl = cI + o_nd; a.scatter = cI + o_sc; a.iface = cI + o_if; a.layer_order = cI + o_ord;
@@ -676,7 +683,7 @@ static int rt_layer_impl(vsm_ctx* ctx, const vsm_layer_desc* d) {
         memset(&a, 0, sizeof a);
         a.N = N; a.nStokes = nSt; a.Nz = 1; a.nC = 1; a.nVZA = 0; a.ld = ld;
         a.istart = (d->imu0 - 1) * nSt; a.nS = nSpec; a.m0 = d->m; a.Mb = 1; a.n_sched_layers = 1;
-        a.n_smem_mats = l_mats; a.z_spectral = d->z_is_spectral ? 1 : 0; a.mz0 = d->m;
+        a.n_smem_mats = l_mats; a.z_spectral = d->z_is_spectral ? 1 : 0; a.mz0 = d->m; a.neumann = ctx->inverse_mode;
         a.mu0 = (T)d->mu0; a.albedo = T(0);
         a.mu = (const T*)d->mu; a.wt = (const T*)d->wt;
         a.ndoubl = cI; a.scatter = cI + 1; a.iface = cI + 2; a.layer_order = cI + 3;

@@ -136,6 +136,7 @@ struct ColArgs {
     int n_smem_mats;
     int z_spectral;          // L1 only: Z given per spectral point
     int mz0;                 // moment index of the first Z table (0 for L2; m for L1)
+    int neumann;             // 1: adaptive Neumann/Gauss-Jordan inverse (OpsFast fp64), 0: elimination only
     T mu0, albedo;
     const T* mu; const T* wt;                         // [N]
     const int* ndoubl; const int* scatter; const int* iface; const int* layer_order;  // [Nz]
@@ -303,49 +304,22 @@ __device__ __forceinline__ void elemental_fill(const ColArgs<T>& a, int m, int n
 template <typename T, class Ops>
 __device__ __forceinline__ void doubling_loop(const Ops& op, int nd, T expk, T*& r, T*& t, T*& X1,
                                               T* X2, T* jp, T* jm, T* j1p, T* j1m, T* v1, T* v2) {
-    const int n = op.N();
+    const int n = op.N(), ld = op.LD();
     for (int it = 0; it < nd; ++it) {
         VSM_T0();
         for (int i = op.tid; i < n; i += op.nthreads()) {                 // doubling_source_update!, :131-132
             j1p[i] = jp[i] * expk;
             j1m[i] = jm[i] * expk;
         }
-#if defined(VSM_DBL_DMMA)
-        auto build = [&]() { op.template mm_dmma<2>(r, r, X1); };
-#elif defined(VSM_DBL_LAMBDA)
-        const int ld = op.LD();
-        auto build = [&]() {
-            op.template mm<false>(r, r, [&](int i, int j, T acc) { X1[i + j * ld] = (i == j ? T(1) : T(0)) - acc; });
-            op.sync();
-        };
-#else
-        auto build = [&]() { op.template mmC<false, 2>(r, r, X1); };     // X1 = I - r r   (rt_helpers.jl:103)
-#endif
-        build();
-        VSM_TICK(1);
-        op.inverse(X1, build);                                            // :104
+        op.inv_one_minus(r, r, X1, X2);                                   // X1 = (I - r r)^-1  (rt_helpers.jl:103-104)
         VSM_TICK(2);
-#if defined(VSM_DBL_DMMA)
-        op.template mm_dmma<0>(t, X1, X2);
-#elif defined(VSM_DBL_LAMBDA)
-        op.template mm<false>(t, X1, [&](int i, int j, T acc) { X2[i + j * ld] = acc; });
-#else
-        op.template mmC<false, 0>(t, X1, X2);                             // X2 = t gp      (:105)
-#endif
+        op.template mm<false>(t, X1, [&](int i, int j, T acc) { X2[i + j * ld] = acc; });   // X2 = t gp (:105)
         VSM_TICK(3);
         // v1 = j1m + r jp ; v2 = jp + r j1m ; jm += tt v1 ; jp = j1p + tt v2          (:133-134)
         op.mv2(r, jp, j1m, [&](int i, T s) { v1[i] = j1m[i] + s; }, [&](int i, T s) { v2[i] = jp[i] + s; });
         op.mv2(X2, v1, v2, [&](int i, T s) { jm[i] = jm[i] + s; }, [&](int i, T s) { jp[i] = j1p[i] + s; });
         VSM_TICK(4);
         // doubling_rt_update! (:162-163)
-#if defined(VSM_DBL_DMMA)
-        op.template mm_dmma<0>(r, t, X1);
-        VSM_TICK(5);
-        op.template mm_dmma<1>(X2, X1, r);
-        VSM_TICK(6);
-        op.template mm_dmma<0>(X2, t, X1);
-        VSM_TICK(7);
-#elif defined(VSM_DBL_LAMBDA)
         op.template mm<false>(r, t, [&](int i, int j, T acc) { X1[i + j * ld] = acc; });
         op.sync();
         VSM_TICK(5);
@@ -355,14 +329,6 @@ __device__ __forceinline__ void doubling_loop(const Ops& op, int nd, T expk, T*&
         op.template mm<false>(X2, t, [&](int i, int j, T acc) { X1[i + j * ld] = acc; });
         op.sync();
         VSM_TICK(7);
-#else
-        op.template mmC<false, 0>(r, t, X1);                              // X1 = r t
-        VSM_TICK(5);
-        op.template mmC<false, 1>(X2, X1, r);                             // r += tt (r t)
-        VSM_TICK(6);
-        op.template mmC<false, 0>(X2, t, X1);                             // X1 = tt t
-        VSM_TICK(7);
-#endif
         T* tmp = t; t = X1; X1 = tmp;
         expk = expk * expk;                                               // :164
     }
@@ -392,6 +358,7 @@ __global__ void __launch_bounds__(NTHR, MINB) k_layer(ColArgs<T> a, unsigned int
     Ops op;
     if constexpr (NN == 0) { op.n = n; op.ld = ld; }
     op.vec = vec; op.part = part; op.piv = piv; op.dmask = dmask; op.tid = threadIdx.x; op.bar = 0;
+    op.neumann = a.neumann;
 
     for (int i = threadIdx.x; i < n; i += blockDim.x) dmask[i] = dmask_of(i, a.nStokes);
     unsigned int nextv = 0;
@@ -644,6 +611,7 @@ __global__ void __launch_bounds__(NTHR) k_adding(ColArgs<T> a, unsigned int tota
     Ops op;
     if constexpr (NN == 0) { op.n = n; op.ld = ld; }
     op.vec = vec; op.part = part; op.piv = piv; op.dmask = dmask; op.tid = threadIdx.x; op.bar = 0;
+    op.neumann = a.neumann;
 
     for (int i = threadIdx.x; i < n; i += blockDim.x) dmask[i] = dmask_of(i, a.nStokes);
     unsigned int nextv = 0;
@@ -759,11 +727,12 @@ __global__ void __launch_bounds__(NTHR) k_adding(ColArgs<T> a, unsigned int tota
 // :248-265 "plus" half: T21, J0+, T++, R+-) only read the pre-step composite, so two
 // 96-thread groups run them concurrently on named barriers; the plus half writes its
 // results to spare buffers and the pointers are rotated at the end of the step.
-// Arena: RA RB TC TD r t | X1a X2a | X1b X2b X3b  (11 matrices, all shared memory).
+// Arena: RA RB TC TD | X1a X2a | X1b X2b X3b | r0 t0 r1 t1  (13 matrices, all shared memory).
+// The added layer iz+1 is fetched with cp.async into the spare (r,t,j+,j-) set while step iz runs.
 // ----------------------------------------------------------------------------
-constexpr int kAdd2Mats = 11;
-// vector scratch of k_adding2 in units of n: 6 shared vectors + 2 groups x (v1 + vec(5) + part(8))
-constexpr int kAdd2VecUnits = 6 + 2 * 14;
+constexpr int kAdd2Mats = 13;
+// vector scratch of k_adding2 in units of n: 8 shared vectors + 2 groups x (v1 + vec(5) + part(8))
+constexpr int kAdd2VecUnits = 8 + 2 * 14;
 
 template <typename T, int NN, int TM, int GT>
 struct Add2Ctx {
@@ -787,12 +756,7 @@ __device__ __noinline__ void add2_step11(Add2Ctx<T, NN, TM, GT>& c, bool rpm_zer
         const auto& op = c.opA;
         T* r = c.r; T* RB = c.RB; T* X1a = c.X1a; T* X2a = c.X2a; T* TD = c.TD; T* TC = c.TC; T* RA = c.RA;
         T* t = c.t; T* J0m = c.J0m; T* v1A = c.v1A; const T* jm = c.jm; const T* J0pc = c.J0pc;
-        auto build1 = [&]() {
-            op.template mm<false>(r, RB, [&](int i, int j, T acc) { at(X1a, i, j) = (i == j ? T(1) : T(0)) - acc; });
-        };
-        build1();
-        op.sync();
-        op.inverse(X1a, build1);                                                     // (:220-222)
+        op.inv_one_minus(r, RB, X1a, X2a);                                           // (:220-222)
         op.template mm<false>(TD, X1a, [&](int i, int j, T acc) { at(X2a, i, j) = acc; });    // T01_inv (:226)
         op.template mv<false>(r, J0pc, [&](int i, T s) { v1A[i] = s + jm[i]; });      // (:229)
         op.template mv<false>(X2a, v1A, [&](int i, T s) { J0m[i] = J0m[i] + s; });
@@ -805,12 +769,7 @@ __device__ __noinline__ void add2_step11(Add2Ctx<T, NN, TM, GT>& c, bool rpm_zer
         const auto& op = c.opB;
         T* r = c.r; T* RB = c.RB; T* X1b = c.X1b; T* X2b = c.X2b; T* X3b = c.X3b; T* TC = c.TC; T* t = c.t;
         T* v1B = c.v1B; T* J0pnew = c.J0pnew; const T* jm = c.jm; const T* jp = c.jp; const T* J0pc = c.J0pc;
-        auto build2 = [&]() {
-            op.template mm<false>(RB, r, [&](int i, int j, T acc) { at(X1b, i, j) = (i == j ? T(1) : T(0)) - acc; });
-        };
-        build2();
-        op.sync();
-        op.inverse(X1b, build2);                                                     // (:248-249)
+        op.inv_one_minus(RB, r, X1b, X2b);                                           // (:248-249)
         T* T21 = X1b;
         if (!t_ident) {
             op.template mm<false>(t, X1b, [&](int i, int j, T acc) { at(X2b, i, j) = acc; });     // T21_inv (:251)
@@ -861,8 +820,8 @@ __global__ void __launch_bounds__(2 * GT, 1) k_adding2(ColArgs<T> a, unsigned in
     constexpr int n = NN, ld = NN | 1, msz = ld * n;
     T* sm = reinterpret_cast<T*>(vsm_smem);
     T* vb = sm + kAdd2Mats * msz;
-    T* J0p = vb;            T* J0m = J0p + n;   T* J0pn = J0m + n;  T* jp = J0pn + n;
-    T* jm = jp + n;         T* hv = jm + n;
+    T* J0p = vb;            T* J0m = J0p + n;   T* J0pn = J0m + n;  T* jpb = J0pn + n;   // jpb: 2 x n
+    T* jmb = jpb + 2 * n;   T* hv = jmb + 2 * n;                                          // jmb: 2 x n
     T* v1A = hv + n;        T* vecA = v1A + n;  T* partA = vecA + 5 * n;
     T* v1B = partA + 8 * n; T* vecB = v1B + n;  T* partB = vecB + 5 * n;
     uint32_t* dmask = reinterpret_cast<uint32_t*>(partB + 8 * n);
@@ -875,9 +834,43 @@ __global__ void __launch_bounds__(2 * GT, 1) k_adding2(ColArgs<T> a, unsigned in
     c.opA.vec = vecA; c.opA.part = partA; c.opA.piv = pivA; c.opA.dmask = dmask; c.opA.tid = c.gtid; c.opA.bar = 1;
     c.opB.vec = vecB; c.opB.part = partB; c.opB.piv = pivB; c.opB.dmask = dmask; c.opB.tid = c.gtid; c.opB.bar = 2;
     c.opC.vec = vecA; c.opC.part = partA; c.opC.piv = pivA; c.opC.dmask = dmask; c.opC.tid = tid;   c.opC.bar = 0;
-    c.J0m = J0m; c.jp = jp; c.jm = jm; c.v1A = v1A; c.v1B = v1B;
+    c.opA.neumann = c.opB.neumann = c.opC.neumann = a.neumann;
+    c.J0m = J0m; c.v1A = v1A; c.v1B = v1B;
     const size_t zstride = (size_t)n * n;
     const int nOut = a.nVZA * a.nStokes;
+    T* const lbuf = sm + 9 * msz;   // r0 t0 r1 t1
+
+    // fill (r, t, j+, j-) of layer iz: scattering layers asynchronously from the k_layer
+    // hand-off, the others in place.  Destination must not be read by anyone until the
+    // next cp_async_wait + __syncthreads.
+    auto fetch_layer = [&](int iz, int p, int mi, T* dr, T* dt, T* djp, T* djm) {
+        if (a.scatter[iz] != 0) {
+            const size_t slot = ((size_t)mi * a.Nz + iz) * a.nS + p;
+            const T* gr = a.add_r + slot * zstride;
+            const T* gt = a.add_t + slot * zstride;
+            if (ld == n) {
+                for (int e = tid; e < n * n; e += 2 * GT) { cp_async_elem(dr + e, gr + e); cp_async_elem(dt + e, gt + e); }
+            } else {
+                for (int e = tid; e < n * n; e += 2 * GT) {
+                    const int i = e % n, j = e / n;
+                    cp_async_elem(dr + i + j * ld, gr + e);
+                    cp_async_elem(dt + i + j * ld, gt + e);
+                }
+            }
+            for (int i = tid; i < n; i += 2 * GT) {
+                cp_async_elem(djp + i, a.add_jp + slot * n + i);
+                cp_async_elem(djm + i, a.add_jm + slot * n + i);
+            }
+        } else {
+            const T tau = a.p_tau[(size_t)iz * a.nS + p];
+            for (int e = tid; e < n * n; e += 2 * GT) {
+                const int i = e % n, j = e / n;
+                dr[i + j * ld] = T(0);
+                dt[i + j * ld] = (i == j) ? Num<T>::exp_(-tau / a.mu[i]) : T(0);
+            }
+            for (int i = tid; i < n; i += 2 * GT) { djp[i] = T(0); djm[i] = T(0); }
+        }
+    };
 
     for (int i = tid; i < n; i += blockDim.x) dmask[i] = dmask_of(i, a.nStokes);
     unsigned int nextv = 0;
@@ -894,54 +887,43 @@ __global__ void __launch_bounds__(2 * GT, 1) k_adding2(ColArgs<T> a, unsigned in
         const int mi = item / a.nS;
         const int m = a.m0 + mi;
         c.RA = sm;             c.RB = sm + msz;      c.TC = sm + 2 * msz;  c.TD = sm + 3 * msz;
-        c.r = sm + 4 * msz;    c.t = sm + 5 * msz;   c.X1a = sm + 6 * msz; c.X2a = sm + 7 * msz;
-        c.X1b = sm + 8 * msz;  c.X2b = sm + 9 * msz; c.X3b = sm + 10 * msz;
+        c.X1a = sm + 4 * msz;  c.X2a = sm + 5 * msz;
+        c.X1b = sm + 6 * msz;  c.X2b = sm + 7 * msz; c.X3b = sm + 8 * msz;
         c.J0pc = J0p; c.J0pnew = J0pn;
+        auto set_buf = [&](int b) {
+            c.r = lbuf + (2 * b) * msz; c.t = lbuf + (2 * b + 1) * msz; c.jp = jpb + b * n; c.jm = jmb + b * n;
+        };
 
-        for (int iz = 0; iz < a.Nz; ++iz) {
-            const bool sc = a.scatter[iz] != 0;
-            T* dr = (iz == 0) ? c.RA : c.r;
-            T* dt = (iz == 0) ? c.TC : c.t;
-            T* djp = (iz == 0) ? c.J0pc : jp;
-            T* djm = (iz == 0) ? J0m : jm;
-            if (sc) {
-                const size_t slot = ((size_t)mi * a.Nz + iz) * a.nS + p;
-                const T* gr = a.add_r + slot * zstride;
-                const T* gt = a.add_t + slot * zstride;
-                for (int e = tid; e < n * n; e += blockDim.x) {
-                    const int i = e % n, j = e / n;
-                    dr[i + j * ld] = gr[e];
-                    dt[i + j * ld] = gt[e];
-                }
-                for (int i = tid; i < n; i += blockDim.x) {
-                    djp[i] = a.add_jp[slot * n + i];
-                    djm[i] = a.add_jm[slot * n + i];
-                }
-            } else {
-                const T tau = a.p_tau[(size_t)iz * a.nS + p];
-                for (int e = tid; e < n * n; e += blockDim.x) {
-                    const int i = e % n, j = e / n;
-                    dr[i + j * ld] = T(0);
-                    dt[i + j * ld] = (i == j) ? Num<T>::exp_(-tau / a.mu[i]) : T(0);
-                }
-                for (int i = tid; i < n; i += blockDim.x) { djp[i] = T(0); djm[i] = T(0); }
+        fetch_layer(0, p, mi, c.RA, c.TC, c.J0pc, J0m);
+        if (a.Nz > 1) { set_buf(1); fetch_layer(1, p, mi, c.r, c.t, c.jp, c.jm); }
+        cp_async_wait_all();
+        __syncthreads();
+        {
+            const bool sc = a.scatter[0] != 0;
+            T* RA = c.RA; T* RB = c.RB; T* TC = c.TC; T* TD = c.TD;
+            for (int e = tid; e < n * n; e += blockDim.x) {
+                const int i = e % n, j = e / n;
+                const uint32_t sg = dmask[i] ^ dmask[j];
+                RB[i + j * ld] = sc ? Num<T>::flip(RA[i + j * ld], sg) : T(0);
+                TD[i + j * ld] = Num<T>::flip(TC[i + j * ld], sg);
             }
             __syncthreads();
-            if (iz == 0) {
-                T* RA = c.RA; T* RB = c.RB; T* TC = c.TC; T* TD = c.TD;
-                for (int e = tid; e < n * n; e += blockDim.x) {
-                    const int i = e % n, j = e / n;
-                    const uint32_t sg = dmask[i] ^ dmask[j];
-                    RB[i + j * ld] = sc ? Num<T>::flip(RA[i + j * ld], sg) : T(0);
-                    TD[i + j * ld] = Num<T>::flip(TC[i + j * ld], sg);
-                }
-                __syncthreads();
-            } else if (a.iface[iz] == 3) {
-                add2_step11<T, NN, TM, GT>(c, !sc, false);
-            } else {
-                add2_step_other<T, NN, TM, GT>(c, a.iface[iz], !sc, false);
-            }
         }
+        for (int iz = 1; iz < a.Nz; ++iz) {
+            const bool sc = a.scatter[iz] != 0;
+            // layer iz is complete in buffer iz&1 (waited + synchronised); start on iz+1
+            if (iz + 1 < a.Nz) {
+                set_buf((iz + 1) & 1);
+                fetch_layer(iz + 1, p, mi, c.r, c.t, c.jp, c.jm);
+            }
+            set_buf(iz & 1);
+            if (a.iface[iz] == 3) add2_step11<T, NN, TM, GT>(c, !sc, false);
+            else add2_step_other<T, NN, TM, GT>(c, a.iface[iz], !sc, false);
+            cp_async_wait_all();
+            __syncthreads();
+        }
+        set_buf(a.Nz & 1);
+        T* jp = c.jp; T* jm = c.jm;
         // ---- Lambertian surface + last interaction
         const T ts_end = a.p_tausum[(size_t)a.Nz * a.nS + p];
         T jps_sun = T(0);

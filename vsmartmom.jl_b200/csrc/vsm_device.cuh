@@ -264,6 +264,8 @@ struct OpsGeneric {
     int* piv;                // >= n+4
     const uint32_t* dmask;
     int tid, bar;            // whole CTA: tid = threadIdx.x
+    int neumann = 0;         // (OpsFast only)
+    static constexpr bool kDmma = false;
     __device__ __forceinline__ int N() const { return n; }
     __device__ __forceinline__ int LD() const { return ld; }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
@@ -296,6 +298,15 @@ struct OpsGeneric {
     __device__ __forceinline__ void inverse(T* M, Rebuild) const {
         cta_inverse<T>(n, M, ld, vec, piv, nullptr);
     }
+    // X = (I - P Q)^-1 ; ends with the CTA synchronised (S: unused scratch)
+    __device__ __forceinline__ void inv_one_minus(const T* P, const T* Q, T* X, T*) const {
+        const int l = ld;
+        cta_mm<T, TM, TM, false>(n, P, ld, Q, ld, dmask, [&](int i, int j, T acc) {
+            X[i + j * l] = (i == j ? T(1) : T(0)) - acc;
+        });
+        __syncthreads();
+        cta_inverse<T>(n, X, ld, vec, piv, nullptr);
+    }
 };
 
 // The dynamic shared-memory arena of the fused kernels.  OpsFast re-bases every operand on
@@ -309,18 +320,35 @@ __device__ __forceinline__ T* rebase(const T* p) {
     return smem_base<T>() + (int)(p - smem_base<T>());
 }
 
+// One-element asynchronous global -> shared copy (LDGSTS; 4 or 8 bytes, natural alignment
+// only, which is all the (N*N)-strided hand-off slots guarantee) and the matching wait.
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T* dst_smem, const T* src_gmem) {
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "cp.async element size");
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(rebase(dst_smem));
+    if (sizeof(T) == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src_gmem) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 #ifdef VSM_PHASE_TIMING
-static __device__ unsigned long long vsm_inv_cycles[8];
+static __device__ unsigned long long vsm_inv_cycles[24];   // [0..7] CTA-wide callers, [8..15] named-barrier groups
+#define VSM_NCOUNT(k) do { if (tid == 0) atomicAdd(&vsm_inv_cycles[16 + (k) + (BAR ? 4 : 0)], 1ull); } while (0)
 #define VSM_IT0() long long _it0 = clock64()
 #define VSM_ITICK(k)                                                             \
     do {                                                                         \
         long long _it1 = clock64();                                              \
-        if (tid == 0) atomicAdd(&vsm_inv_cycles[k], (unsigned long long)(_it1 - _it0)); \
+        if (tid == 0) atomicAdd(&vsm_inv_cycles[(k) + (BAR ? 8 : 0)], (unsigned long long)(_it1 - _it0)); \
         _it0 = _it1;                                                             \
     } while (0)
 #else
 #define VSM_IT0()
 #define VSM_ITICK(k)
+#define VSM_NCOUNT(k)
 #endif
 
 // Named barrier over the NTHR threads of one Ops group (bar 0 == __syncthreads when
@@ -466,18 +494,21 @@ struct OpsFast {
     static constexpr bool kDmma = (sizeof(T) == 8) && (NTHR % 32 == 0) && (kNW >= 4);
     // warp grid of the DMMA product: 2 x 2 (4 warps: 24x24 per warp) or 2 x 3 (>= 6 warps: 24x16)
     static constexpr int kWR = 2, kWC = (kNW >= 6) ? 3 : 2;
-    template <bool KSIGN, class Epi>
+    // SYNC_EPI: a group barrier between the last operand read and the epilogue, so that the
+    // epilogue may overwrite A or B (each thread only touches the elements it owns).
+    template <bool KSIGN, class Epi, bool SYNC_EPI = false>
     __device__ __forceinline__ void mm_dmma_epi(const T* __restrict__ A, const T* __restrict__ B, Epi epi) const {
         constexpr int NP = (NN + 7) & ~7;                   // padded extent (48)
         constexpr int TR = NP / 8 / kWR, TC = NP / 8 / kWC; // mma tiles per warp (rows, cols)
         static_assert(NP / 8 % kWR == 0 && NP / 8 % kWC == 0, "warp tiling");
         const int warp = tid >> 5, lane = tid & 31;
-        if (warp < kWR * kWC) {
-            const int g = lane >> 2, tg = lane & 3;
-            const int wi = (warp % kWR) * TR * 8, wj = (warp / kWR) * TC * 8;
+        const int g = lane >> 2, tg = lane & 3;
+        const int wi = (warp % kWR) * TR * 8, wj = (warp / kWR) * TC * 8;
+        const bool wact = warp < kWR * kWC;
+        double c[TR][TC][2];
+        if (wact) {
             const T* Ab = rebase(A) + wi + g + tg * kLd;      // A[wi+g (+8r)][k0+tg]
             const T* Bb = rebase(B) + tg + (wj + g) * kLd;    // B[k0+tg][wj+g (+8c)]
-            double c[TR][TC][2];
 #pragma unroll
             for (int r = 0; r < TR; ++r)
 #pragma unroll
@@ -502,6 +533,9 @@ struct OpsFast {
                         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                                      : "+d"(c[r][q][0]), "+d"(c[r][q][1]) : "d"(a[r]), "d"(b[q]));
             }
+        }
+        if (SYNC_EPI) sync();
+        if (wact) {
 #pragma unroll
             for (int r = 0; r < TR; ++r)
 #pragma unroll
@@ -627,6 +661,78 @@ struct OpsFast {
         else mv_impl<false, 2>(A, x1, x2, e1, e2);
     }
 
+    // X = (I - P Q)^-1 with S as scratch; ends with the group synchronised.
+    // fp64 tensor-core path: A = P Q is formed first together with its Frobenius norm nu (a
+    // sub-multiplicative bound of the spectral radius).  When nu is small the Neumann series
+    //   (I - A)^-1 = (I + A)(I + A^2)(I + A^4)...      remainder  <= nu^K / (1 - nu)
+    // is summed on the tensor cores up to the order K whose remainder is below 1e-20 -- i.e. far
+    // below fp64 rounding of the O(1) diagonal -- (K = 2: no product at all, K = 4: two products,
+    // K = 8: four), replacing the latency-bound pivot chain of the elimination by dense products.
+    // Thin layers (the vast majority of doubling and adding steps of a real atmosphere) take the
+    // K = 2 exit.  Otherwise, or when `neumann` is 0, the blocked Gauss-Jordan inverse runs.
+    int neumann = 1;
+    __device__ __forceinline__ void inv_one_minus(const T* P, const T* Q, T* X, T* S) const {
+        auto at = [](T* M, int i, int j) -> T& { return M[i + j * kLd]; };
+        auto rebuild = [&]() {
+            mm<false>(P, Q, [&](int i, int j, T acc) { at(X, i, j) = (i == j ? T(1) : T(0)) - acc; });
+            sync();
+        };
+        if constexpr (kDmma) {
+            if (neumann) {
+                double ss = 0.0;
+                mm_dmma_epi<false>(P, Q, [&](int i, int j, T acc) { at(X, i, j) = acc; ss = fma((double)acc, (double)acc, ss); });
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                double* np = reinterpret_cast<double*>(part);
+                if ((tid & 31) == 0) np[tid >> 5] = ss;
+                sync();
+                double nu2 = 0.0;
+#pragma unroll
+                for (int w = 0; w < kWR * kWC; ++w) nu2 += np[w];
+                if (nu2 <= 1e-20) {                                   // K = 2:  G = I + A
+                    VSM_NCOUNT(0);
+                    if (tid < NN) at(X, tid, tid) += T(1);
+                    sync();
+                    return;
+                }
+                if (nu2 <= 1e-10) {                                   // K = 4:  G = I + A + A^2 + A A^2
+                    VSM_NCOUNT(1);
+                    mm_dmma_epi<false>(X, X, [&](int i, int j, T acc) { at(S, i, j) = acc; });
+                    sync();
+                    auto e = [&](int i, int j, T acc) { at(X, i, j) = ((i == j ? T(1) : T(0)) + at(X, i, j)) + (at(S, i, j) + acc); };
+                    mm_dmma_epi<false, decltype(e), true>(X, S, e);
+                    sync();
+                    return;
+                }
+                if (nu2 <= 9e-6) {                                    // K = 8:  ... (I + A^4)
+                    VSM_NCOUNT(2);
+                    mm_dmma_epi<false>(X, X, [&](int i, int j, T acc) { at(S, i, j) = acc; });
+                    sync();
+                    auto e1 = [&](int i, int j, T acc) { at(X, i, j) = ((i == j ? T(1) : T(0)) + at(X, i, j)) + (at(S, i, j) + acc); };
+                    mm_dmma_epi<false, decltype(e1), true>(X, S, e1);
+                    sync();
+                    auto e2 = [&](int i, int j, T acc) { at(S, i, j) = acc; };
+                    mm_dmma_epi<false, decltype(e2), true>(S, S, e2);
+                    sync();
+                    auto e3 = [&](int i, int j, T acc) { at(X, i, j) += acc; };
+                    mm_dmma_epi<false, decltype(e3), true>(X, S, e3);
+                    sync();
+                    return;
+                }
+                VSM_NCOUNT(3);
+                for (int e = tid; e < NN * NN; e += NTHR) {           // X = I - A, then eliminate
+                    const int i = e % NN, j = e / NN;
+                    at(X, i, j) = (i == j ? T(1) : T(0)) - at(X, i, j);
+                }
+                sync();
+                inverse(X, rebuild);
+                return;
+            }
+        }
+        rebuild();
+        inverse(X, rebuild);
+    }
+
     // In-place inverse.  Register-resident Gauss-Jordan on the diagonal pivots, one
     // barrier per step.  Step k is the rank-1 update  M <- M - c' r'^T  with
     //   c'_i = a_ik (i != k), c'_k = a_kk - 1 ;  r'_j = a_kj / a_kk (j != k), r'_k = 1 + 1/a_kk
@@ -674,6 +780,7 @@ struct OpsFast {
         const int wr = warp % kWR, wc = warp / kWR;
         if (tid == 0) *bad = 0;
         bool mybad = false;
+        VSM_IT0();
         auto mma = [](double& c0, double& c1, double a, double b) {
             asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                          : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -692,6 +799,7 @@ struct OpsFast {
                     }
         }
         sync();                                                    // everyone has read M before staging reuses it
+        VSM_ITICK(0);
 #pragma unroll
         for (int K = 0; K < NB; ++K) {
             double* rowb = Ms + (K & 1) * SET;                     // X: 8 x NP, ld RLD  (element [k][j] at k + j*RLD)
@@ -742,7 +850,9 @@ struct OpsFast {
                     Ps[g + (2 * tg + 1) * PLD] = d1;
                 }
             }
+            VSM_ITICK(1);
             sync();
+            VSM_ITICK(2);
             // ---- b. panels
             if (wact) {
                 if (wc == kq) {                                    // L_i = -C_i P   (A = C_i, B = P)
@@ -780,7 +890,9 @@ struct OpsFast {
                     }
                 }
             }
+            VSM_ITICK(3);
             sync();
+            VSM_ITICK(4);
             // ---- c. trailing update  M_ij += L_i X_j   (i != K, j != K)
             if (wact) {
                 double la[TR][2], xb[TC][2];
@@ -807,6 +919,7 @@ struct OpsFast {
                         }
                     }
             }
+            VSM_ITICK(5);
         }
         if (mybad) *bad = 1;
         sync();                                                    // staging no longer read
@@ -824,14 +937,14 @@ struct OpsFast {
         sync();
         if (*bad) {                       // uniform over the group
 #ifdef VSM_PHASE_TIMING
-            if (tid == 0) atomicAdd(&vsm_inv_cycles[7], 1ull);
+            if (tid == 0) atomicAdd(&vsm_inv_cycles[7 + (BAR ? 8 : 0)], 1ull);
 #endif
             rebuild();
             sync();
             group_inverse_pivoted(M);
         }
 #ifdef VSM_PHASE_TIMING
-        if (tid == 0) atomicAdd(&vsm_inv_cycles[6], 1ull);
+        if (tid == 0) atomicAdd(&vsm_inv_cycles[6 + (BAR ? 8 : 0)], 1ull);
 #endif
     }
 

@@ -4,7 +4,7 @@
 #define VSM_NN 45
 #define VSM_MINB 3
 #define VSM_LTHR 128
-#define VSM_ATHR 512
+#define VSM_ATHR 384
 #define VSM_ADD2 1
 #define VSM_LTMI 5
 #define VSM_LKS 1

@@ -47,7 +47,7 @@ class ColumnDesc(C.Structure):
 
 EXPORTS = [
     "vsm_version", "vsm_create", "vsm_destroy", "vsm_last_error", "vsm_synchronize",
-    "vsm_set_workspace_limit", "vsm_kernel_launches", "vsm_measure_fma_peak",
+    "vsm_set_workspace_limit", "vsm_set_inverse_mode", "vsm_kernel_launches", "vsm_measure_fma_peak",
     "vsm_batched_mul_f64", "vsm_batched_mul_f32", "vsm_batch_inv_f64", "vsm_batch_inv_f32",
     "vsm_batch_solve_f64", "vsm_batch_solve_f32",
     "vsm_rt_layer_f64", "vsm_rt_layer_f32", "vsm_rt_column_f64", "vsm_rt_column_f32",
@@ -61,6 +61,7 @@ lib.vsm_last_error.argtypes = [c_void_p]
 lib.vsm_last_error.restype = C.c_char_p
 lib.vsm_synchronize.argtypes = [c_void_p]
 lib.vsm_set_workspace_limit.argtypes = [c_void_p, C.c_uint64]
+lib.vsm_set_inverse_mode.argtypes = [c_void_p, C.c_int]
 lib.vsm_kernel_launches.argtypes = [c_void_p]
 lib.vsm_kernel_launches.restype = C.c_uint64
 lib.vsm_measure_fma_peak.argtypes = [c_void_p, c_int, C.POINTER(c_double)]
@@ -100,6 +101,10 @@ class Context:
 
     def set_workspace_limit(self, nbytes: int):
         self.check(lib.vsm_set_workspace_limit(self.handle, int(nbytes)))
+
+    def set_inverse_mode(self, mode: int):
+        """1: adaptive Neumann / Gauss-Jordan (default); 0: Gauss-Jordan only."""
+        self.check(lib.vsm_set_inverse_mode(self.handle, int(mode)))
 
     @property
     def kernel_launches(self) -> int:
