@@ -56,7 +56,7 @@ int  vsm_synchronize(vsm_ctx* ctx);             /* Architectures._sync_gpu[] (ex
 int  vsm_set_workspace_limit(vsm_ctx* ctx, uint64_t bytes);
 /* how (I - A)^-1 of doubling (rt_helpers.jl:103-104) and interaction (interaction.jl:220-222,
  * :248-249) is evaluated by the specialised fp64 kernels.  1 (default): the Frobenius norm nu of
- * A is measured; if nu^K/(1-nu) < 1e-20 for K in {2,4,8} the Neumann product form
+ * A is measured; if nu^K/(1-nu) < 1e-20 for K in {2,3,4,8} the Neumann series / product form
  * (I+A)(I+A^2)(I+A^4) truncated at order K is summed on the tensor cores (bit-level equivalent to
  * the elimination at fp64 precision), otherwise blocked Gauss-Jordan.  0: always Gauss-Jordan
  * (the reference's getrf/getri route, cpu_batched.jl:32-37). */

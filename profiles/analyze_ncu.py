@@ -37,7 +37,12 @@ want = ["Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "lau
         "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio"]
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_selected_per_issue_active.ratio"]
 print(f"# ncu summary: {os.path.basename(rep)}\n", file=out)
 for k in want:
     if k in M:

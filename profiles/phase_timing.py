@@ -31,13 +31,13 @@ for lbl, off, calls in (("k_layer", 16, nd), ("k_adding2 (per group)", 40, 2 * 3
     for k, nme in enumerate(inames):
         print(f"  {nme:26s} {iv[k]:9.0f}")
 
-av = np.array(list(buf)[24:34], dtype=np.float64)
+av = np.array(list(buf)[24:40], dtype=np.float64)
 steps11 = 33 * 20 * 444
-an = ["load added layer", "M1 = I - r RB", "inverse 1", "T01, J0- (2 mv)", "X3, RA+=, TD", "M2 = I - RB r", "inverse 2",
-      "T21, J0+ (2 mv)", "TC, Y, RB", "whole interaction step"]
-print("k_adding per layer step (thread 0 cycles):")
+an = ["(I - A)^-1 (+ vector)", "T01 / T21 product", "2nd product(s) + sync", "last product(s)", "wait for the other group",
+      "issue prefetch of next layer", "whole step (call)", "cp.async wait + barrier"]
+print("k_adding2 per layer step (cycles; thread 0 of group 0 | group 1):")
 for k, nme in enumerate(an):
-    print(f"  {nme:24s} {av[k] / steps11:9.0f}")
+    print(f"  {nme:30s} {av[k] / steps11:9.0f} {av[8 + k] / steps11:9.0f}")
 
 print("inverse calls", buf[16 + 6] + buf[40 + 6], "pivoted fallbacks", buf[16 + 7] + buf[40 + 7])
-print("(I - A)^-1 routes  [K=2, K=4, K=8, Gauss-Jordan]:  k_layer", list(buf[48:52]), " k_adding2", list(buf[52:56]))
+print("(I - A)^-1 routes  [K=2, K=3, K=4, K=8 | Gauss-Jordan]:  k_layer", list(buf[48:52]), buf[16 + 6], " k_adding2", list(buf[52:56]), buf[40 + 6])

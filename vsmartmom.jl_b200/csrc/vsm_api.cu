@@ -438,7 +438,7 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
     FastCfg fc{cfg.threads, cfg.threads, 0};
     if (fast) fc = fast_cfg<T, 45>();
     // the two-group adding kernel has its own arena (11 matrices)
-    const size_t a2_smem = (size_t)kAdd2Mats * msz + (size_t)kAdd2VecUnits * N * sizeof(T) + ((size_t)3 * N + 8) * 4;
+    const size_t a2_smem = (size_t)kAdd2Mats * msz + 64 + (size_t)kAdd2VecUnits * N * sizeof(T) + ((size_t)3 * N + 8 + Nz) * 4;
     if (fast && fc.adding_two_group && a2_smem > smax) fast = false;
     if (fast && !fc.adding_two_group && a_mats != kAddMats) fast = false;
 

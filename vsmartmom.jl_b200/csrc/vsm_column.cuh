@@ -36,11 +36,21 @@ static __device__ unsigned long long vsm_add_cycles[16];
         if (threadIdx.x == 0) atomicAdd(&vsm_add_cycles[k], (unsigned long long)(_a1 - _a0)); \
         _a0 = _a1;                                                               \
     } while (0)
+// per-group phases of add2_step11: slots [0..7] group 0, [8..15] group 1
+#define VSM_G0() long long _g0 = clock64()
+#define VSM_GTICK(k)                                                             \
+    do {                                                                         \
+        long long _g1 = clock64();                                               \
+        if (c.gtid == 0) atomicAdd(&vsm_add_cycles[(k) + 8 * c.group], (unsigned long long)(_g1 - _g0)); \
+        _g0 = _g1;                                                               \
+    } while (0)
 #else
 #define VSM_T0()
 #define VSM_TICK(k)
 #define VSM_A0()
 #define VSM_ATICK(k)
+#define VSM_G0()
+#define VSM_GTICK(k)
 #endif
 
 // ----------------------------------------------------------------------------
@@ -305,32 +315,42 @@ template <typename T, class Ops>
 __device__ __forceinline__ void doubling_loop(const Ops& op, int nd, T expk, T*& r, T*& t, T*& X1,
                                               T* X2, T* jp, T* jm, T* j1p, T* j1m, T* v1, T* v2) {
     const int n = op.N(), ld = op.LD();
-    for (int it = 0; it < nd; ++it) {
-        VSM_T0();
-        for (int i = op.tid; i < n; i += op.nthreads()) {                 // doubling_source_update!, :131-132
+    // the matrix-vector products of the source update ride along with the matrix products that
+    // share their left operand (one extra 8-column tile on the tensor-core path)
+    auto attenuate = [&]() {                                              // doubling_source_update!, :131-132
+        for (int i = op.tid; i < n; i += op.nthreads()) {
             j1p[i] = jp[i] * expk;
             j1m[i] = jm[i] * expk;
         }
-        op.inv_one_minus(r, r, X1, X2);                                   // X1 = (I - r r)^-1  (rt_helpers.jl:103-104)
+    };
+    if (nd > 0) {
+        attenuate();
+        op.sync();
+    }
+    for (int it = 0; it < nd; ++it) {
+        VSM_T0();
+        // X1 = (I - r r)^-1 (rt_helpers.jl:103-104) ; v1 = j1m + r jp ; v2 = jp + r j1m  (:133-134)
+        op.template inv_one_minus_v<2>(r, r, X1, X2, jp, j1m,
+                                       [&](int i, T s) { v1[i] = j1m[i] + s; }, [&](int i, T s) { v2[i] = jp[i] + s; });
         VSM_TICK(2);
         op.template mm<false>(t, X1, [&](int i, int j, T acc) { X2[i + j * ld] = acc; });   // X2 = t gp (:105)
+        op.sync();
         VSM_TICK(3);
-        // v1 = j1m + r jp ; v2 = jp + r j1m ; jm += tt v1 ; jp = j1p + tt v2          (:133-134)
-        op.mv2(r, jp, j1m, [&](int i, T s) { v1[i] = j1m[i] + s; }, [&](int i, T s) { v2[i] = jp[i] + s; });
-        op.mv2(X2, v1, v2, [&](int i, T s) { jm[i] = jm[i] + s; }, [&](int i, T s) { jp[i] = j1p[i] + s; });
-        VSM_TICK(4);
         // doubling_rt_update! (:162-163)
         op.template mm<false>(r, t, [&](int i, int j, T acc) { X1[i + j * ld] = acc; });
         op.sync();
         VSM_TICK(5);
-        op.template mm<false>(X2, X1, [&](int i, int j, T acc) { r[i + j * ld] += acc; });
+        // r += tt (r t) ; jm += tt v1 ; jp = j1p + tt v2
+        op.template mmv<2>(X2, X1, [&](int i, int j, T acc) { r[i + j * ld] += acc; }, v1, v2,
+                           [&](int i, T s) { jm[i] = jm[i] + s; }, [&](int i, T s) { jp[i] = j1p[i] + s; });
         op.sync();
         VSM_TICK(6);
+        expk = expk * expk;                                               // :164
         op.template mm<false>(X2, t, [&](int i, int j, T acc) { X1[i + j * ld] = acc; });
+        if (it + 1 < nd) attenuate();
         op.sync();
         VSM_TICK(7);
         T* tmp = t; t = X1; X1 = tmp;
-        expk = expk * expk;                                               // :164
     }
 }
 
@@ -748,39 +768,53 @@ struct Add2Ctx {
 
 // one ScatteringInterface_11 step on two groups; ends with the whole CTA synchronised
 template <typename T, int NN, int TM, int GT>
-__device__ __noinline__ void add2_step11(Add2Ctx<T, NN, TM, GT>& c, bool rpm_zero, bool t_ident) {
+__device__ __forceinline__ void add2_step11(Add2Ctx<T, NN, TM, GT>& c, bool rpm_zero, bool t_ident) {
     constexpr int n = NN, ld = NN | 1;
     const uint32_t* dmask = c.dmask;
     auto at = [](T* M, int i, int j) -> T& { return M[i + j * ld]; };
+    VSM_G0();
     if (c.group == 0) {
         const auto& op = c.opA;
-        T* r = c.r; T* RB = c.RB; T* X1a = c.X1a; T* X2a = c.X2a; T* TD = c.TD; T* TC = c.TC; T* RA = c.RA;
-        T* t = c.t; T* J0m = c.J0m; T* v1A = c.v1A; const T* jm = c.jm; const T* J0pc = c.J0pc;
-        op.inv_one_minus(r, RB, X1a, X2a);                                           // (:220-222)
+        // (re-based on the shared-memory symbol so that the epilogues use LDS/STS, not generic accesses)
+        T* r = rebase(c.r); T* RB = rebase(c.RB); T* X1a = rebase(c.X1a); T* X2a = rebase(c.X2a);
+        T* TD = rebase(c.TD); T* TC = rebase(c.TC); T* RA = rebase(c.RA); T* t = rebase(c.t);
+        T* J0m = rebase(c.J0m); T* v1A = rebase(c.v1A); const T* jm = rebase(c.jm); const T* J0pc = rebase(c.J0pc);
+        // (:220-222) with v1A = r J0+ + j0-  (:229) as a by-product
+        op.template inv_one_minus_v<1>(r, RB, X1a, X2a, J0pc, J0pc, [&](int i, T s) { v1A[i] = s + jm[i]; }, [](int, T) {});
+        VSM_GTICK(0);
         op.template mm<false>(TD, X1a, [&](int i, int j, T acc) { at(X2a, i, j) = acc; });    // T01_inv (:226)
-        op.template mv<false>(r, J0pc, [&](int i, T s) { v1A[i] = s + jm[i]; });      // (:229)
-        op.template mv<false>(X2a, v1A, [&](int i, T s) { J0m[i] = J0m[i] + s; });
-        op.template mm<false>(X2a, r, [&](int i, int j, T acc) { at(X1a, i, j) = acc; });
         op.sync();
+        VSM_GTICK(1);
+        op.template mmv<1>(X2a, r, [&](int i, int j, T acc) { at(X1a, i, j) = acc; }, v1A, v1A,
+                           [&](int i, T s) { J0m[i] = J0m[i] + s; }, [](int, T) {});
+        op.sync();
+        VSM_GTICK(2);
         op.template mm<false>(X1a, TC, [&](int i, int j, T acc) { at(RA, i, j) += acc; });    // (:237)
         if (!t_ident)
             op.template mm<true>(X2a, t, [&](int i, int j, T acc) { at(TD, i, j) = Num<T>::flip(acc, dmask[j]); });  // (:240)
+        VSM_GTICK(3);
     } else {
         const auto& op = c.opB;
-        T* r = c.r; T* RB = c.RB; T* X1b = c.X1b; T* X2b = c.X2b; T* X3b = c.X3b; T* TC = c.TC; T* t = c.t;
-        T* v1B = c.v1B; T* J0pnew = c.J0pnew; const T* jm = c.jm; const T* jp = c.jp; const T* J0pc = c.J0pc;
-        op.inv_one_minus(RB, r, X1b, X2b);                                           // (:248-249)
+        T* r = rebase(c.r); T* RB = rebase(c.RB); T* X1b = rebase(c.X1b); T* X2b = rebase(c.X2b);
+        T* X3b = rebase(c.X3b); T* TC = rebase(c.TC); T* t = rebase(c.t);
+        T* v1B = rebase(c.v1B); T* J0pnew = rebase(c.J0pnew); const T* jm = rebase(c.jm); const T* jp = rebase(c.jp);
+        const T* J0pc = rebase(c.J0pc);
+        // (:248-249) with v1B = J0+ + R+- j0-  (:254) as a by-product
+        op.template inv_one_minus_v<1>(RB, r, X1b, X2b, jm, jm, [&](int i, T s) { v1B[i] = J0pc[i] + s; }, [](int, T) {});
+        VSM_GTICK(0);
         T* T21 = X1b;
         if (!t_ident) {
             op.template mm<false>(t, X1b, [&](int i, int j, T acc) { at(X2b, i, j) = acc; });     // T21_inv (:251)
+            op.sync();
             T21 = X2b;
         }
-        op.template mv<false>(RB, jm, [&](int i, T s) { v1B[i] = J0pc[i] + s; });     // (:254)
-        op.template mv<false>(T21, v1B, [&](int i, T s) { J0pnew[i] = jp[i] + s; });
+        VSM_GTICK(1);
         T* TCn = t_ident ? X2b : X1b;
-        op.template mm<false>(T21, TC, [&](int i, int j, T acc) { at(TCn, i, j) = acc; });        // (:262)
+        op.template mmv<1>(T21, TC, [&](int i, int j, T acc) { at(TCn, i, j) = acc; }, v1B, v1B,      // (:262)
+                           [&](int i, T s) { J0pnew[i] = jp[i] + s; }, [](int, T) {});
         op.template mm<false>(T21, RB, [&](int i, int j, T acc) { at(X3b, i, j) = acc; });
         op.sync();
+        VSM_GTICK(2);
         if (t_ident) {                                                                // (:265)
             if (!rpm_zero)
                 for (int e = c.gtid; e < n * n; e += GT) {
@@ -793,8 +827,10 @@ __device__ __noinline__ void add2_step11(Add2Ctx<T, NN, TM, GT>& c, bool rpm_zer
                 at(X2b, i, j) = rpm + Num<T>::flip(acc, dmask[j]);
             });
         }
+        VSM_GTICK(3);
     }
     __syncthreads();
+    VSM_GTICK(4);
     T* tmp;
     if (t_ident) {
         tmp = c.TD; c.TD = c.X2a; c.X2a = tmp;
@@ -809,7 +845,7 @@ __device__ __noinline__ void add2_step11(Add2Ctx<T, NN, TM, GT>& c, bool rpm_zer
 
 // the rare interfaces (non-scattering layers) run on the whole CTA
 template <typename T, int NN, int TM, int GT>
-__device__ __noinline__ void add2_step_other(Add2Ctx<T, NN, TM, GT>& c, int iface, bool rpm_zero, bool t_ident) {
+__device__ __forceinline__ void add2_step_other(Add2Ctx<T, NN, TM, GT>& c, int iface, bool rpm_zero, bool t_ident) {
     CompPtrs<T> q{c.RA, c.RB, c.TC, c.TD, c.r, c.t, c.X1a, c.X2a, c.X1b};
     interact<T, typename Add2Ctx<T, NN, TM, GT>::OpsC>(c.opC, iface, q, c.J0pc, c.J0m, c.jp, c.jm, c.v1A, rpm_zero, t_ident);
     c.RA = q.RA; c.RB = q.RB; c.TC = q.TC; c.TD = q.TD; c.X1a = q.X1; c.X2a = q.X2; c.X1b = q.X3;
@@ -818,8 +854,10 @@ __device__ __noinline__ void add2_step_other(Add2Ctx<T, NN, TM, GT>& c, int ifac
 template <typename T, int NN, int TM, int GT>
 __global__ void __launch_bounds__(2 * GT, 1) k_adding2(ColArgs<T> a, unsigned int total) {
     constexpr int n = NN, ld = NN | 1, msz = ld * n;
+    constexpr int EPV = 16 / (int)sizeof(T);          // elements per 16-byte cp.async
+    constexpr int LB = msz + EPV - 1;                 // layer-buffer stride: room to match the source's 16-B phase
     T* sm = reinterpret_cast<T*>(vsm_smem);
-    T* vb = sm + kAdd2Mats * msz;
+    T* vb = sm + 9 * msz + 4 * LB;
     T* J0p = vb;            T* J0m = J0p + n;   T* J0pn = J0m + n;  T* jpb = J0pn + n;   // jpb: 2 x n
     T* jmb = jpb + 2 * n;   T* hv = jmb + 2 * n;                                          // jmb: 2 x n
     T* v1A = hv + n;        T* vecA = v1A + n;  T* partA = vecA + 5 * n;
@@ -827,6 +865,7 @@ __global__ void __launch_bounds__(2 * GT, 1) k_adding2(ColArgs<T> a, unsigned in
     uint32_t* dmask = reinterpret_cast<uint32_t*>(partB + 8 * n);
     int* pivA = reinterpret_cast<int*>(dmask + n);
     int* pivB = pivA + n + 4;
+    int* lflag = pivB + n + 4;        // [Nz] scatter | iface << 1, staged once (global reads would sit on the step's critical path)
     __shared__ unsigned int sh_item;
     const int tid = threadIdx.x;
     Add2Ctx<T, NN, TM, GT> c;
@@ -838,24 +877,68 @@ __global__ void __launch_bounds__(2 * GT, 1) k_adding2(ColArgs<T> a, unsigned in
     c.J0m = J0m; c.v1A = v1A; c.v1B = v1B;
     const size_t zstride = (size_t)n * n;
     const int nOut = a.nVZA * a.nStokes;
-    T* const lbuf = sm + 9 * msz;   // r0 t0 r1 t1
+    T* const lbuf = sm + 9 * msz;   // r0 t0 r1 t1, stride LB
+    static_assert(kAdd2Mats == 13, "arena: 9 matrices + 4 layer buffers");
 
-    // fill (r, t, j+, j-) of layer iz: scattering layers asynchronously from the k_layer
-    // hand-off, the others in place.  Destination must not be read by anyone until the
-    // next cp_async_wait + __syncthreads.
-    auto fetch_layer = [&](int iz, int p, int mi, T* dr, T* dt, T* djp, T* djm) {
-        if (a.scatter[iz] != 0) {
+    // One matrix of the k_layer hand-off -> shared memory as one TMA bulk copy.  The slots are only
+    // element-aligned ((N*N)-strided), so the destination is shifted by up to EPV-1 elements to the
+    // source's 16-byte phase; the few head/tail elements go by element-wise cp.async.  Thread 0 issues
+    // the bulk copy on `bar` (expect_tx already posted).  Returns the shifted destination.
+    __shared__ __align__(8) unsigned long long mbar[2];
+    auto matrix_bulk_bytes = [&](const T* g) -> unsigned {
+        const int ps = (int)((reinterpret_cast<uintptr_t>(g) / sizeof(T)) % EPV);
+        return (unsigned)(((n * n - (EPV - ps) % EPV) / EPV) * 16);
+    };
+    auto copy_matrix = [&](T* dbase, const T* g, unsigned long long* bar) -> T* {
+        const int ps = (int)((reinterpret_cast<uintptr_t>(g) / sizeof(T)) % EPV);
+        const int pd = (int)((dbase - sm) % EPV);
+        T* d = dbase + ((ps - pd + EPV) % EPV);
+        const int head = (EPV - ps) % EPV;
+        const int nvec = (n * n - head) / EPV;
+        const int tail0 = head + nvec * EPV;
+        if (tid == 0) bulk_g2s(d + head, g + head, (unsigned)nvec * 16u, bar);
+        if (tid >= 32 && tid - 32 < head) cp_async_elem(d + tid - 32, g + tid - 32);
+        if (tid >= 64 && tid - 64 < n * n - tail0) cp_async_elem(d + tail0 + tid - 64, g + tail0 + tid - 64);
+        return d;
+    };
+    // fill (r, t, j+, j-) of layer iz into layer buffer b (or, for iz == 0, into the composite):
+    // scattering layers asynchronously from the k_layer hand-off, the others in place.  The
+    // destination must not be read by anyone until the next cp_async_wait + __syncthreads.
+    T* lr0 = lbuf; T* lt0 = lbuf + LB; T* lr1 = lbuf + 2 * LB; T* lt1 = lbuf + 3 * LB;
+    bool pend0 = false, pend1 = false;       // a bulk copy is in flight on mbar[b]   (CTA-uniform)
+    unsigned par0 = 0, par1 = 0;             // phase parity the next wait on mbar[b] expects
+    // everything fetched into buffer b has landed and is visible to the whole CTA
+    auto layer_ready = [&](int b) {
+        cp_async_wait_all();
+        if (b ? pend1 : pend0) {
+            mbar_wait(&mbar[b], b ? par1 : par0);
+            if (b) { par1 ^= 1u; pend1 = false; } else { par0 ^= 1u; pend0 = false; }
+        }
+        __syncthreads();
+    };
+    auto fetch_layer = [&](int iz, int p, int mi, int b, T* dr0, T* dt0, T* djp, T* djm) {
+        T* dr = dr0 ? dr0 : lbuf + (2 * b) * LB;
+        T* dt = dt0 ? dt0 : lbuf + (2 * b + 1) * LB;
+        if (lflag[iz] & 1) {
             const size_t slot = ((size_t)mi * a.Nz + iz) * a.nS + p;
             const T* gr = a.add_r + slot * zstride;
             const T* gt = a.add_t + slot * zstride;
-            if (ld == n) {
-                for (int e = tid; e < n * n; e += 2 * GT) { cp_async_elem(dr + e, gr + e); cp_async_elem(dt + e, gt + e); }
-            } else {
+            if (dr0 || ld != n) {                        // fixed destination / padded layout: element copies
                 for (int e = tid; e < n * n; e += 2 * GT) {
                     const int i = e % n, j = e / n;
                     cp_async_elem(dr + i + j * ld, gr + e);
                     cp_async_elem(dt + i + j * ld, gt + e);
                 }
+            } else {
+                // ld == n: the buffer is a dense copy of the slot.  The buffer was last touched through the
+                // generic proxy (reads of the step before last, ordered by the CTA barrier): fence, then TMA.
+                if (tid == 0) {
+                    fence_proxy_async();
+                    mbar_expect_tx(&mbar[b], matrix_bulk_bytes(gr) + matrix_bulk_bytes(gt));
+                }
+                dr = copy_matrix(dr, gr, &mbar[b]);
+                dt = copy_matrix(dt, gt, &mbar[b]);
+                if (b) pend1 = true; else pend0 = true;
             }
             for (int i = tid; i < n; i += 2 * GT) {
                 cp_async_elem(djp + i, a.add_jp + slot * n + i);
@@ -870,9 +953,18 @@ __global__ void __launch_bounds__(2 * GT, 1) k_adding2(ColArgs<T> a, unsigned in
             }
             for (int i = tid; i < n; i += 2 * GT) { djp[i] = T(0); djm[i] = T(0); }
         }
+        if (!dr0) {
+            if (b) { lr1 = dr; lt1 = dt; } else { lr0 = dr; lt0 = dt; }
+        }
     };
 
     for (int i = tid; i < n; i += blockDim.x) dmask[i] = dmask_of(i, a.nStokes);
+    for (int i = tid; i < a.Nz; i += blockDim.x) lflag[i] = (a.scatter[i] != 0 ? 1 : 0) | (a.iface[i] << 1);
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     unsigned int nextv = 0;
     if (tid == 0) nextv = atomicAdd(a.counter, 1u);
 
@@ -891,15 +983,38 @@ __global__ void __launch_bounds__(2 * GT, 1) k_adding2(ColArgs<T> a, unsigned in
         c.X1b = sm + 6 * msz;  c.X2b = sm + 7 * msz; c.X3b = sm + 8 * msz;
         c.J0pc = J0p; c.J0pnew = J0pn;
         auto set_buf = [&](int b) {
-            c.r = lbuf + (2 * b) * msz; c.t = lbuf + (2 * b + 1) * msz; c.jp = jpb + b * n; c.jm = jmb + b * n;
+            c.r = b ? lr1 : lr0; c.t = b ? lt1 : lt0; c.jp = jpb + b * n; c.jm = jmb + b * n;
         };
 
-        fetch_layer(0, p, mi, c.RA, c.TC, c.J0pc, J0m);
-        if (a.Nz > 1) { set_buf(1); fetch_layer(1, p, mi, c.r, c.t, c.jp, c.jm); }
-        cp_async_wait_all();
-        __syncthreads();
+        // Lambertian surface (lambertian_surface.jl:41-95) as the "layer" below the last one; only m = 0
+        // has one.  Written in place into layer buffer b.
+        T jps_sun = T(0);
+        auto fill_surface = [&](int b) {
+            const T ts_end = a.p_tausum[(size_t)a.Nz * a.nS + p];
+            const T rho = T(2) * a.albedo;
+            const T att = Num<T>::exp_(-ts_end / a.mu0);
+            T* r = lbuf + (2 * b) * LB;
+            T* sjp = jpb + b * n; T* sjm = jmb + b * n;
+            for (int e = tid; e < n * n; e += blockDim.x) {
+                const int i = e % n, j = e / n;
+                const bool ii = (i % a.nStokes) == 0 && (j % a.nStokes) == 0;
+                r[i + j * ld] = ii ? rho * (a.mu[j] * a.wt[j]) : T(0);
+            }
+            for (int i = tid; i < n; i += blockDim.x) {
+                sjp[i] = (i == a.istart) ? att : T(0);
+                sjm[i] = ((i % a.nStokes) == 0) ? a.mu0 * rho * att : T(0);
+            }
+            if (b) lr1 = r; else lr0 = r;
+            jps_sun = att;
+        };
+        const int nsteps = a.Nz + (m == 0 ? 1 : 0);       // step Nz = the surface
+
+        fetch_layer(0, p, mi, 0, c.RA, c.TC, c.J0pc, J0m);
+        if (a.Nz > 1) fetch_layer(1, p, mi, 1, nullptr, nullptr, jpb + n, jmb + n);
+        else if (m == 0) fill_surface(1);
+        layer_ready(1);                       // layer 0 (element copies) and layer 1
         {
-            const bool sc = a.scatter[0] != 0;
+            const bool sc = (lflag[0] & 1) != 0;
             T* RA = c.RA; T* RB = c.RB; T* TC = c.TC; T* TD = c.TD;
             for (int e = tid; e < n * n; e += blockDim.x) {
                 const int i = e % n, j = e / n;
@@ -909,42 +1024,27 @@ __global__ void __launch_bounds__(2 * GT, 1) k_adding2(ColArgs<T> a, unsigned in
             }
             __syncthreads();
         }
-        for (int iz = 1; iz < a.Nz; ++iz) {
-            const bool sc = a.scatter[iz] != 0;
+        // one call site for the (large, inlined) interaction step: the composite's pointers stay in registers
+        for (int iz = 1; iz < nsteps; ++iz) {
+            const bool surf = (iz == a.Nz);
+            const int fl = lflag[surf ? a.Nz - 1 : iz];
+            const bool nosrc = surf || (fl & 1) == 0;     // the added layer has r+- = 0
+            const int itf = fl >> 1;
+            VSM_G0();
             // layer iz is complete in buffer iz&1 (waited + synchronised); start on iz+1
-            if (iz + 1 < a.Nz) {
-                set_buf((iz + 1) & 1);
-                fetch_layer(iz + 1, p, mi, c.r, c.t, c.jp, c.jm);
-            }
+            const int nb = (iz + 1) & 1;
+            if (iz + 1 < a.Nz) fetch_layer(iz + 1, p, mi, nb, nullptr, nullptr, jpb + nb * n, jmb + nb * n);
+            else if (iz + 1 == a.Nz && m == 0) fill_surface(nb);
             set_buf(iz & 1);
-            if (a.iface[iz] == 3) add2_step11<T, NN, TM, GT>(c, !sc, false);
-            else add2_step_other<T, NN, TM, GT>(c, a.iface[iz], !sc, false);
-            cp_async_wait_all();
-            __syncthreads();
+            VSM_GTICK(5);
+            if (itf == 3) add2_step11<T, NN, TM, GT>(c, nosrc, surf);
+            else add2_step_other<T, NN, TM, GT>(c, itf, nosrc, surf);
+            VSM_GTICK(6);
+            layer_ready(nb);
+            VSM_GTICK(7);
         }
-        set_buf(a.Nz & 1);
-        T* jp = c.jp; T* jm = c.jm;
-        // ---- Lambertian surface + last interaction
-        const T ts_end = a.p_tausum[(size_t)a.Nz * a.nS + p];
-        T jps_sun = T(0);
-        if (m == 0) {
-            const T rho = T(2) * a.albedo;
-            const T att = Num<T>::exp_(-ts_end / a.mu0);
-            T* r = c.r;
-            for (int e = tid; e < n * n; e += blockDim.x) {
-                const int i = e % n, j = e / n;
-                const bool ii = (i % a.nStokes) == 0 && (j % a.nStokes) == 0;
-                r[i + j * ld] = ii ? rho * (a.mu[j] * a.wt[j]) : T(0);
-            }
-            for (int i = tid; i < n; i += blockDim.x) {
-                jp[i] = (i == a.istart) ? att : T(0);
-                jm[i] = ((i % a.nStokes) == 0) ? a.mu0 * rho * att : T(0);
-            }
-            jps_sun = att;
-            __syncthreads();
-            if (a.iface[a.Nz - 1] == 3) add2_step11<T, NN, TM, GT>(c, true, true);
-            else add2_step_other<T, NN, TM, GT>(c, a.iface[a.Nz - 1], true, true);
-            const T* J0pc = c.J0pc;
+        if (m == 0) {                         // hdr source: R_surf J0+ + j0-(surf)   (interaction_hdrf!)
+            const T* J0pc = c.J0pc; const T* jm = c.jm;
             c.opC.template mv<false>(c.r, J0pc, [&](int i, T s) { hv[i] = s + jm[i]; });
         } else {
             for (int i = tid; i < n; i += blockDim.x) hv[i] = T(0);

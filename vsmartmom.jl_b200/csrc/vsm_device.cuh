@@ -298,6 +298,19 @@ struct OpsGeneric {
     __device__ __forceinline__ void inverse(T* M, Rebuild) const {
         cta_inverse<T>(n, M, ld, vec, piv, nullptr);
     }
+    template <int NV, class Epi, class E1, class E2>
+    __device__ __forceinline__ void mmv(const T* A, const T* B, Epi epi, const T* x1, const T* x2, E1 e1, E2 e2) const {
+        cta_mm<T, TM, TM, false>(n, A, ld, B, ld, dmask, epi);
+        if (NV >= 1) cta_mv<T, false>(n, A, ld, x1, dmask, part, e1);
+        if (NV >= 2) cta_mv<T, false>(n, A, ld, x2, dmask, part, e2);
+    }
+    template <int NV, class E1, class E2>
+    __device__ __forceinline__ void inv_one_minus_v(const T* P, const T* Q, T* X, T* S, const T* x1, const T* x2,
+                                                    E1 e1, E2 e2) const {
+        if (NV >= 1) cta_mv<T, false>(n, P, ld, x1, dmask, part, e1);
+        if (NV >= 2) cta_mv<T, false>(n, P, ld, x2, dmask, part, e2);
+        inv_one_minus(P, Q, X, S);
+    }
     // X = (I - P Q)^-1 ; ends with the CTA synchronised (S: unused scratch)
     __device__ __forceinline__ void inv_one_minus(const T* P, const T* Q, T* X, T*) const {
         const int l = ld;
@@ -330,6 +343,34 @@ __device__ __forceinline__ void cp_async_elem(T* dst_smem, const T* src_gmem) {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src_gmem) : "memory");
     else
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src_gmem) : "memory");
+}
+template <typename T>
+__device__ __forceinline__ void cp_async_16(T* dst_smem, const T* src_gmem) {     // both 16-byte aligned
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(rebase(dst_smem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src_gmem) : "memory");
+}
+// TMA bulk copy global -> shared (cp.async.bulk), completion counted on an mbarrier.  Source,
+// destination and size are multiples of 16 bytes.  One thread issues; nothing blocks at issue.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -418,6 +459,18 @@ struct OpsFast {
         }
     }
 
+    // mm plus the side products y_v = A x_v (v < NV), see mm_dmma_v.  Ends WITHOUT a barrier on the
+    // tensor-core path and with one on the SIMT path; callers synchronise before using any result.
+    template <int NV, class Epi, class E1, class E2>
+    __device__ __forceinline__ void mmv(const T* A, const T* B, Epi epi, const T* x1, const T* x2, E1 e1, E2 e2) const {
+        if constexpr (kDmma) {
+            mm_dmma_v<false, NV, false>(A, B, epi, x1, x2, e1, e2);
+        } else {
+            mm<false>(A, B, epi);
+            mv_impl<false, NV>(A, x1, x2, e1, e2);
+        }
+    }
+
     // C = f(A*B) with the result written to (or accumulated into) C itself; the k range is
     // split over KS thread sets whose partial tiles are combined through C.
     //   MODE 0: C = acc      MODE 1: C += acc      MODE 2: C = I - acc
@@ -496,23 +549,38 @@ struct OpsFast {
     static constexpr int kWR = 2, kWC = (kNW >= 6) ? 3 : 2;
     // SYNC_EPI: a group barrier between the last operand read and the epilogue, so that the
     // epilogue may overwrite A or B (each thread only touches the elements it owns).
+    // NV > 0: the product also yields y_v = A x_v for NV (1 or 2) vectors as one extra 8-column B
+    // tile [x1 x2 0 ...] whose row tiles are dealt to the warps that already hold the A fragments;
+    // e1(i, y1_i) / e2(i, y2_i) receive the result.  x1/x2 must not be written by e1/e2.
     template <bool KSIGN, class Epi, bool SYNC_EPI = false>
     __device__ __forceinline__ void mm_dmma_epi(const T* __restrict__ A, const T* __restrict__ B, Epi epi) const {
+        auto none = [](int, T) {};
+        mm_dmma_v<KSIGN, 0, SYNC_EPI>(A, B, epi, A, A, none, none);
+    }
+    template <bool KSIGN, int NV, bool SYNC_EPI, class Epi, class E1, class E2>
+    __device__ __forceinline__ void mm_dmma_v(const T* __restrict__ A, const T* __restrict__ B, Epi epi,
+                                              const T* __restrict__ x1, const T* __restrict__ x2, E1 e1, E2 e2) const {
         constexpr int NP = (NN + 7) & ~7;                   // padded extent (48)
         constexpr int TR = NP / 8 / kWR, TC = NP / 8 / kWC; // mma tiles per warp (rows, cols)
+        constexpr int VS = (NV > 0) ? (TR + kWC - 1) / kWC : 1;   // vector-tile slots per warp
         static_assert(NP / 8 % kWR == 0 && NP / 8 % kWC == 0, "warp tiling");
         const int warp = tid >> 5, lane = tid & 31;
         const int g = lane >> 2, tg = lane & 3;
-        const int wi = (warp % kWR) * TR * 8, wj = (warp / kWR) * TC * 8;
+        const int wr = warp % kWR, wc = warp / kWR;
+        const int wi = wr * TR * 8, wj = wc * TC * 8;
         const bool wact = warp < kWR * kWC;
         double c[TR][TC][2];
+        double cv[VS][2];
         if (wact) {
             const T* Ab = rebase(A) + wi + g + tg * kLd;      // A[wi+g (+8r)][k0+tg]
             const T* Bb = rebase(B) + tg + (wj + g) * kLd;    // B[k0+tg][wj+g (+8c)]
+            const T* xs = rebase((NV == 2 && g == 1) ? x2 : x1) + tg;
 #pragma unroll
             for (int r = 0; r < TR; ++r)
 #pragma unroll
                 for (int q = 0; q < TC; ++q) c[r][q][0] = c[r][q][1] = 0.0;
+#pragma unroll
+            for (int v = 0; v < VS; ++v) cv[v][0] = cv[v][1] = 0.0;
 #pragma unroll
             for (int k0 = 0; k0 < NP; k0 += 4) {
                 double a[TR], b[TC];
@@ -526,12 +594,26 @@ struct OpsFast {
                 }
 #pragma unroll
                 for (int q = 0; q < TC; ++q) b[q] = kin ? (double)Bb[k0 + q * 8 * kLd] : 0.0;
+                double bx = 0.0;
+                if (NV > 0) bx = (g < NV && kin) ? (double)xs[k0] : 0.0;
 #pragma unroll
                 for (int r = 0; r < TR; ++r)
 #pragma unroll
                     for (int q = 0; q < TC; ++q)
                         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                                      : "+d"(c[r][q][0]), "+d"(c[r][q][1]) : "d"(a[r]), "d"(b[q]));
+                if (NV > 0) {
+#pragma unroll
+                    for (int v = 0; v < VS; ++v) {
+                        double av = a[0];
+#pragma unroll
+                        for (int r = 1; r < TR; ++r)
+                            if (r / kWC == v) av = (r % kWC == wc) ? a[r] : av;
+                        if (v * kWC + wc < TR)                 // warp-uniform
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                         : "+d"(cv[v][0]), "+d"(cv[v][1]) : "d"(av), "d"(bx));
+                    }
+                }
             }
         }
         if (SYNC_EPI) sync();
@@ -545,6 +627,17 @@ struct OpsFast {
                         const int i = wi + r * 8 + g, j = wj + q * 8 + 2 * tg + h;
                         if (i < NN && j < NN) epi(i, j, (T)c[r][q][h]);
                     }
+            if (NV > 0 && tg == 0) {
+#pragma unroll
+                for (int v = 0; v < VS; ++v) {
+                    const int r = v * kWC + wc;
+                    const int i = wi + r * 8 + g;
+                    if (r < TR && i < NN) {
+                        e1(i, (T)cv[v][0]);
+                        if (NV == 2) e2(i, (T)cv[v][1]);
+                    }
+                }
+            }
         }
     }
     template <int MODE>
@@ -666,12 +759,19 @@ struct OpsFast {
     // sub-multiplicative bound of the spectral radius).  When nu is small the Neumann series
     //   (I - A)^-1 = (I + A)(I + A^2)(I + A^4)...      remainder  <= nu^K / (1 - nu)
     // is summed on the tensor cores up to the order K whose remainder is below 1e-20 -- i.e. far
-    // below fp64 rounding of the O(1) diagonal -- (K = 2: no product at all, K = 4: two products,
+    // below fp64 rounding of the O(1) diagonal -- (K = 2: no product at all, K = 3: one, K = 4: two,
     // K = 8: four), replacing the latency-bound pivot chain of the elimination by dense products.
     // Thin layers (the vast majority of doubling and adding steps of a real atmosphere) take the
     // K = 2 exit.  Otherwise, or when `neumann` is 0, the blocked Gauss-Jordan inverse runs.
     int neumann = 1;
     __device__ __forceinline__ void inv_one_minus(const T* P, const T* Q, T* X, T* S) const {
+        auto none = [](int, T) {};
+        inv_one_minus_v<0>(P, Q, X, S, P, P, none, none);
+    }
+    // ... and y_v = P x_v as a by-product of forming P Q (see mmv)
+    template <int NV, class E1, class E2>
+    __device__ __forceinline__ void inv_one_minus_v(const T* P, const T* Q, T* X, T* S, const T* x1, const T* x2,
+                                                    E1 e1, E2 e2) const {
         auto at = [](T* M, int i, int j) -> T& { return M[i + j * kLd]; };
         auto rebuild = [&]() {
             mm<false>(P, Q, [&](int i, int j, T acc) { at(X, i, j) = (i == j ? T(1) : T(0)) - acc; });
@@ -680,7 +780,8 @@ struct OpsFast {
         if constexpr (kDmma) {
             if (neumann) {
                 double ss = 0.0;
-                mm_dmma_epi<false>(P, Q, [&](int i, int j, T acc) { at(X, i, j) = acc; ss = fma((double)acc, (double)acc, ss); });
+                mm_dmma_v<false, NV, false>(P, Q, [&](int i, int j, T acc) { at(X, i, j) = acc; ss = fma((double)acc, (double)acc, ss); },
+                                            x1, x2, e1, e2);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
                 double* np = reinterpret_cast<double*>(part);
@@ -695,8 +796,15 @@ struct OpsFast {
                     sync();
                     return;
                 }
-                if (nu2 <= 1e-10) {                                   // K = 4:  G = I + A + A^2 + A A^2
+                if (nu2 <= 4.6e-14) {                                 // K = 3:  G = I + A + A^2   (nu^3 <= 1e-20)
                     VSM_NCOUNT(1);
+                    auto e = [&](int i, int j, T acc) { at(X, i, j) = ((i == j ? T(1) : T(0)) + at(X, i, j)) + acc; };
+                    mm_dmma_epi<false, decltype(e), true>(X, X, e);
+                    sync();
+                    return;
+                }
+                if (nu2 <= 1e-10) {                                   // K = 4:  G = I + A + A^2 + A A^2
+                    VSM_NCOUNT(2);
                     mm_dmma_epi<false>(X, X, [&](int i, int j, T acc) { at(S, i, j) = acc; });
                     sync();
                     auto e = [&](int i, int j, T acc) { at(X, i, j) = ((i == j ? T(1) : T(0)) + at(X, i, j)) + (at(S, i, j) + acc); };
@@ -705,7 +813,7 @@ struct OpsFast {
                     return;
                 }
                 if (nu2 <= 9e-6) {                                    // K = 8:  ... (I + A^4)
-                    VSM_NCOUNT(2);
+                    VSM_NCOUNT(3);
                     mm_dmma_epi<false>(X, X, [&](int i, int j, T acc) { at(S, i, j) = acc; });
                     sync();
                     auto e1 = [&](int i, int j, T acc) { at(X, i, j) = ((i == j ? T(1) : T(0)) + at(X, i, j)) + (at(S, i, j) + acc); };
@@ -719,7 +827,6 @@ struct OpsFast {
                     sync();
                     return;
                 }
-                VSM_NCOUNT(3);
                 for (int e = tid; e < NN * NN; e += NTHR) {           // X = I - A, then eliminate
                     const int i = e % NN, j = e / NN;
                     at(X, i, j) = (i == j ? T(1) : T(0)) - at(X, i, j);
@@ -729,7 +836,8 @@ struct OpsFast {
                 return;
             }
         }
-        rebuild();
+        mmv<NV>(P, Q, [&](int i, int j, T acc) { at(X, i, j) = (i == j ? T(1) : T(0)) - acc; }, x1, x2, e1, e2);
+        sync();
         inverse(X, rebuild);
     }
 
