@@ -24,6 +24,8 @@ for k, nme in enumerate(names):
     per = v[k] / (nd if 1 <= k <= 7 else items)
     print(f"{nme:22s} total {v[k]:.3e} cyc   per {'doubling' if 1 <= k <= 7 else 'item'}: {per:9.0f} cyc")
 
+ev = np.array(list(buf)[10:13], dtype=np.float64) / items
+print("elemental split (thread 0 cycles per item): per-stream exp/expm1 + barrier %.0f | element loop %.0f | source vectors %.0f" % tuple(ev))
 inames = ["load tiles + sync", "a: stage + pivot block", "a: barrier wait", "b: panels", "b: barrier wait", "c: trailing update"]
 for lbl, off, calls in (("k_layer", 16, nd), ("k_adding2 (per group)", 40, 2 * 33 * 20 * 444)):
     iv = np.array(list(buf)[off:off + 6], dtype=np.float64) / max(calls, 1)

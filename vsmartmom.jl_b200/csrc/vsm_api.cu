@@ -416,9 +416,12 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
     CK(cudaStreamSynchronize(ctx->stream));   // fT/fI are stack-owned vectors
     const T* cT = (const T*)ctx->consts.p;
     const int* cI = (const int*)((char*)ctx->consts.p + offI);
-    if ((rc = ensure(ctx, ctx->geom, (size_t)2 * N * N * sizeof(T)))) return rc;
+    if ((rc = ensure(ctx, ctx->geom, ((size_t)2 * N * N + 2 * N) * sizeof(T) + (size_t)N * N + N))) return rc;
     T* geo1 = (T*)ctx->geom.p; T* geo2 = geo1 + (size_t)N * N;
-    k_geom<T><<<(N * N + 255) / 256, 256, 0, ctx->stream>>>(N, cT + o_mu, cT + o_wt, geo1, geo2);
+    T* gs1 = geo2 + (size_t)N * N; T* gs2 = gs1 + N;
+    unsigned char* gcls = (unsigned char*)(gs2 + N);
+    k_geom<T><<<(N * N + 255) / 256, 256, 0, ctx->stream>>>(N, nSt, (d->imu0 - 1) * nSt, cT + o_mu, cT + o_wt, geo1, geo2,
+                                                            gs1, gs2, gcls);
     ctx->launches++;
     CK(cudaGetLastError());
 
@@ -535,7 +538,7 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
         a.Zpp = (const T*)d->Zpp; a.Zmp = (const T*)d->Zmp;
         a.p_tau = pa.tau; a.p_varpi = pa.varpi; a.p_tausum = pa.tausum; a.p_W = pa.W;
         a.F0 = (const T*)d->F0; a.F0_off = (size_t)n0;
-        a.geo1 = geo1; a.geo2 = geo2;
+        a.geo1 = geo1; a.geo2 = geo2; a.gs1 = gs1; a.gs2 = gs2; a.gcls = gcls;
         a.counter = (unsigned int*)ctx->counter.p;
         a.vza_row = cI + o_vrow; a.vza_w = cT + o_vw;
         a.part_R = part; a.part_T = part + (size_t)nM * per_m; a.part_H = part + (size_t)2 * nM * per_m;
@@ -674,9 +677,12 @@ static int rt_layer_impl(vsm_ctx* ctx, const vsm_layer_desc* d) {
     CK(cudaMemcpyAsync(ctx->consts.p, ctl, sizeof ctl, cudaMemcpyHostToDevice, ctx->stream));
     const int* cI = (const int*)ctx->consts.p;
     if (d->scatter) {
-        if ((rc = ensure(ctx, ctx->geom, (size_t)2 * N * N * sizeof(T)))) return rc;
+        if ((rc = ensure(ctx, ctx->geom, ((size_t)2 * N * N + 2 * N) * sizeof(T) + (size_t)N * N + N))) return rc;
         T* geo1 = (T*)ctx->geom.p; T* geo2 = geo1 + (size_t)N * N;
-        k_geom<T><<<(N * N + 255) / 256, 256, 0, ctx->stream>>>(N, (const T*)d->mu, (const T*)d->wt, geo1, geo2);
+        T* gs1 = geo2 + (size_t)N * N; T* gs2 = gs1 + N;
+        unsigned char* gcls = (unsigned char*)(gs2 + N);
+        k_geom<T><<<(N * N + 255) / 256, 256, 0, ctx->stream>>>(N, nSt, (d->imu0 - 1) * nSt, (const T*)d->mu,
+                                                                (const T*)d->wt, geo1, geo2, gs1, gs2, gcls);
         ctx->launches++;
         CK(cudaGetLastError());
         ColArgs<T> a;
@@ -691,7 +697,7 @@ static int rt_layer_impl(vsm_ctx* ctx, const vsm_layer_desc* d) {
         a.p_tau = (const T*)d->tau; a.p_varpi = (const T*)d->varpi; a.p_tausum = (const T*)d->tau_sum;
         a.p_W = (const T*)d->tau;                      // nC == 1: weights unused
         a.F0 = (const T*)d->F0; a.F0_off = 0;
-        a.geo1 = geo1; a.geo2 = geo2;
+        a.geo1 = geo1; a.geo2 = geo2; a.gs1 = gs1; a.gs2 = gs2; a.gcls = gcls;
         a.add_r = add_r; a.add_t = add_t; a.add_jp = add_jp; a.add_jm = add_jm;
         a.slab = (T*)ctx->slabs.p; a.slab_stride = l_slab / sizeof(T);
         a.counter = (unsigned int*)ctx->counter.p;

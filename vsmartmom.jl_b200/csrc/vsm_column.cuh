@@ -154,6 +154,8 @@ struct ColArgs {
     const T* p_tau; const T* p_varpi; const T* p_tausum; const T* p_W;   // k_props outputs
     const T* F0; size_t F0_off;                       // (nStokes, nSpec) ; column offset of chunk
     const T* geo1; const T* geo2;                     // k_geom tables (N,N)
+    const T* gs1; const T* gs2;                       // k_geom solar-stream factors [N]
+    const unsigned char* gcls;                        // k_geom branch classes (N,N) + [N]
     // added-layer scratch: slot = (mi*Nz + iz)*nS + p
     T* add_r; T* add_t; T* add_jp; T* add_jm;
     // spill slabs and the work counter
@@ -176,91 +178,124 @@ __device__ inline unsigned int next_item(unsigned int* counter, unsigned int* sh
 // ----------------------------------------------------------------------------
 // elemental r⁻⁺/t⁺⁺ and solar sources into the arena  (elemental.jl:289-392)
 // ----------------------------------------------------------------------------
-// geometric factors of the elemental formulas, shared by every point / layer / moment:
+// geometry of the elemental formulas, shared by every point / layer / moment (built once per call):
 //   geo1[i,j] = mu_j/(mu_i+mu_j) * w_j ,  geo2[i,j] = mu_j/(mu_i-mu_j) * w_j  (0 where mu_i == mu_j)
+//   gcls[i,j] = kind | wflags<<2 : kind 0 distinct streams, 1 nearly coincident (|dmu| <= 1e-3 mu_j: the
+//               exact expdiff_neg form is needed), 2 mu_i == mu_j ; wflags bit0/1 = (w_j*0.5 > eps) /
+//               (w_j*0.25 > eps), the `wct > eps` test of elemental.jl:296 for m == 0 / m > 0
+//   and against the solar stream s = istart:  gs1[i] = mu_s/(mu_i+mu_s), gs2[i] = mu_s/(mu_i-mu_s)
+//   (0 inside the solar block), gcls[n*n + i] = 0 distinct / 1 nearly coincident / 2 solar block.
 template <typename T>
-__global__ void k_geom(int n, const T* __restrict__ mu, const T* __restrict__ wt, T* __restrict__ geo1,
-                       T* __restrict__ geo2) {
+__global__ void k_geom(int n, int nStokes, int istart, const T* __restrict__ mu, const T* __restrict__ wt,
+                       T* __restrict__ geo1, T* __restrict__ geo2, T* __restrict__ gs1, T* __restrict__ gs2,
+                       unsigned char* __restrict__ gcls) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n * n) return;
     const int i = e % n, j = e / n;
-    const T mui = mu[i], muj = mu[j];
-    geo1[e] = (muj / (mui + muj)) * wt[j];
-    geo2[e] = (mui == muj) ? T(0) : (muj / (mui - muj)) * wt[j];
+    const T mui = mu[i], muj = mu[j], wj = wt[j];
+    const T eps = Num<T>::eps();
+    const int kind = (mui == muj) ? 2 : ((Num<T>::abs_(mui - muj) > T(1e-3) * muj) ? 0 : 1);
+    geo1[e] = (muj / (mui + muj)) * wj;
+    geo2[e] = (kind == 2) ? T(0) : (muj / (mui - muj)) * wj;
+    gcls[e] = (unsigned char)(kind | ((wj * T(0.5) > eps) ? 4 : 0) | ((wj * T(0.25) > eps) ? 8 : 0));
+    if (e < n) {
+        const T mus = mu[istart];
+        const bool sun = (e >= istart && e < istart + nStokes);
+        const T me = mu[e];
+        gs1[e] = mus / (me + mus);
+        gs2[e] = sun ? T(0) : mus / (me - mus);
+        gcls[n * n + e] = (unsigned char)(sun ? 2 : ((Num<T>::abs_(me - mus) > T(1e-3) * mus) ? 0 : 1));
+    }
 }
 
+// Scratch: rowtmp >= 3n + 1 (a_i, e_i, em1_i, att) ; cap >= 2*nStokes*n (the solar columns of the mixed,
+// scaled Z matrices, captured in the element loop for the source vectors).
 template <typename T, int NN>
 __device__ __forceinline__ void elemental_fill(const ColArgs<T>& a, int m, int nd, T dtau, T varpi,
                                                T tausum, const T* __restrict__ Wc,
                                                const T* __restrict__ Zpp, const T* __restrict__ Zmp,
                                                size_t zstride, const T* __restrict__ F0n,
                                                const uint32_t* __restrict__ dmask,
-                                               T* r, T* t, T* jp, T* jm, T* rowtmp /* >= 5n */) {
+                                               T* r, T* t, T* jp, T* jm, T* rowtmp, T* cap) {
     const int n = NN ? NN : a.N, ld = NN ? (NN | 1) : a.ld, nC = a.nC;
+    const int nn = n * n;
     const T wsc = (m == 0) ? T(0.5) : T(0.25);       // scaled_weights / fourier_weight
-    const T eps = Num<T>::eps();
-    // per-stream quantities: a_i = dtau/mu_i, e_i = exp(-a_i), em1_i = expm1(-a_i)
-    T* ai = rowtmp; T* ei = rowtmp + n; T* em1 = rowtmp + 2 * n; T* smu = rowtmp + 3 * n; T* swt = rowtmp + 4 * n;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const T mi = a.mu[i];
-        const T x = dtau / mi;
-        ai[i] = x;
-        ei[i] = Num<T>::exp_(-x);
-        em1[i] = Num<T>::expm1_(-x);
-        smu[i] = mi;
-        swt[i] = a.wt[i];
+    const unsigned wbit = (m == 0) ? 4u : 8u;
+    // per-stream quantities: a_i = dtau/mu_i, e_i = exp(-a_i), em1_i = expm1(-a_i); solar attenuation
+    T* ai = rowtmp; T* ei = rowtmp + n; T* em1 = rowtmp + 2 * n; T* satt = rowtmp + 3 * n;
+    T* zps = cap; T* zms = cap + a.nStokes * n;
+    VSM_T0();
+    for (int q = threadIdx.x; q < 2 * n + 1; q += blockDim.x) {
+        if (q < n) {
+            const T x = dtau / a.mu[q];
+            ai[q] = x;
+            em1[q] = Num<T>::expm1_(-x);
+        } else if (q < 2 * n) {
+            ei[q - n] = Num<T>::exp_(-(dtau / a.mu[q - n]));
+        } else {
+            satt[0] = Num<T>::exp_(-tausum / a.mu[a.istart]);
+        }
     }
     __syncthreads();
+    VSM_TICK(10);
+    // All the fp64 work below competes with the tensor-core products of the co-resident CTAs for
+    // the one fp64 datapath, so the element formulas are kept to a minimum of fp64 instructions:
+    // the mixing weights carry varpi * w_scale, the geometry and the branch classes are tabulated.
     const T vw = varpi * wsc;
+    const T w0 = (nC > 1) ? vw * Wc[0] : vw, w1 = (nC > 1) ? vw * Wc[1] : T(0);   // nC == 1: Z is used as it is
     // element loop, 4 elements per thread per trip: all global (L2) table loads of a trip are issued
     // before any use so their latency overlaps (the arena leaves almost no L1)
     constexpr int U = 4;
-    const int nn = n * n;
-    const T w0 = Wc[0], w1 = (nC > 1) ? Wc[1] : T(0);
     for (int e0 = threadIdx.x; e0 < nn; e0 += U * blockDim.x) {
         T zmv[U], zpv[U], g1v[U], g2v[U];
+        unsigned clv[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int e = min(e0 + u * (int)blockDim.x, nn - 1);
             if (nC == 1) {
-                zmv[u] = Zmp[e]; zpv[u] = Zpp[e];
+                zmv[u] = w0 * Zmp[e]; zpv[u] = w0 * Zpp[e];
             } else if (nC == 2) {
                 const T a0 = Zmp[e], a1 = Zmp[zstride + e], b0 = Zpp[e], b1 = Zpp[zstride + e];
-                zmv[u] = fma(w1, a1, fma(w0, a0, T(0)));
-                zpv[u] = fma(w1, b1, fma(w0, b0, T(0)));
+                zmv[u] = fma(w1, a1, w0 * a0);
+                zpv[u] = fma(w1, b1, w0 * b0);
             } else {
                 T zm = T(0), zp = T(0);
                 for (int c = 0; c < nC; ++c) {
                     zm = fma(Wc[c], Zmp[(size_t)c * zstride + e], zm);
                     zp = fma(Wc[c], Zpp[(size_t)c * zstride + e], zp);
                 }
-                zmv[u] = zm; zpv[u] = zp;
+                zmv[u] = vw * zm; zpv[u] = vw * zp;
             }
             g1v[u] = a.geo1[e];
             g2v[u] = a.geo2[e];
+            clv[u] = a.gcls[e];
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int e = e0 + u * (int)blockDim.x;
             if (e < nn) {
                 const int i = e % n, j = e / n;
-                const T zm = zmv[u], zp = zpv[u];
-                const T wj = swt[j] * wsc;
+                const T zm = zmv[u], zp = zpv[u];          // varpi * w_scale * Z
+                const unsigned cl = clv[u];
+                if (j >= a.istart && j < a.istart + a.nStokes) {          // solar column: keep for the sources
+                    zps[(j - a.istart) * n + i] = zp;
+                    zms[(j - a.istart) * n + i] = zm;
+                }
                 T rv, tv;
-                if (wj > eps) {
+                if (cl & wbit) {                                                 // wct > eps (elemental.jl:296)
                     // 1 - exp(-(a_i+a_j)) = -(em1_i + em1_j + em1_i em1_j)      (elemental.jl:298-302)
                     const T xi = em1[i], xj = em1[j];
-                    rv = vw * zm * g1v[u] * (-(xi + xj + xi * xj));
-                    const T mui = smu[i], muj = smu[j];
-                    if (mui == muj) {                                            // (:304-314)
-                        tv = (i == j) ? ei[i] * (T(1) + varpi * zp * ai[i] * wj) : ei[j] * (varpi * zp * ai[i] * wj);
-                    } else {
-                        // exp(-a_i) - exp(-a_j) = em1_i - em1_j ; the exact expdiff_neg form (rt_helpers.jl:32-40)
-                        // is used for nearly coincident streams where that difference would cancel
-                        T dif;
-                        if (Num<T>::abs_(mui - muj) > T(1e-3) * muj) dif = xi - xj;
-                        else dif = expdiff_neg<T>(ai[i], ai[j]);
-                        tv = vw * zp * g2v[u] * dif;                             // (:319-323)
+                    rv = zm * g1v[u] * (-fma(xi, xj, xi + xj));
+                    const unsigned kind = cl & 3u;
+                    if (kind == 0) {
+                        // exp(-a_i) - exp(-a_j) = em1_i - em1_j                    (:319-323)
+                        tv = zp * g2v[u] * (xi - xj);
+                    } else if (kind == 1) {
+                        // nearly coincident streams: the exact expdiff_neg form (rt_helpers.jl:32-40)
+                        tv = zp * g2v[u] * expdiff_neg<T>(ai[i], ai[j]);
+                    } else {                                                     // mu_i == mu_j (:304-314)
+                        const T q = zp * ai[i] * a.wt[j];
+                        tv = (i == j) ? ei[i] * (T(1) + q) : ei[j] * q;
                     }
                 } else {
                     rv = T(0);
@@ -272,36 +307,32 @@ __device__ __forceinline__ void elemental_fill(const ColArgs<T>& a, int m, int n
             }
         }
     }
-    const T wct02 = wsc;
-    const T mus = a.mu[a.istart];
-    const T att = Num<T>::exp_(-tausum / mus);
+    __syncthreads();
+    VSM_TICK(11);
+    // solar sources j0+ / j0- (elemental.jl:343-392) from the captured columns
+    const T att = satt[0];
+    const T xs = em1[a.istart], as = ai[a.istart];
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         T zpI = T(0), zmI = T(0);
         for (int s = 0; s < a.nStokes; ++s) {
-            const size_t e = (size_t)i + (size_t)(a.istart + s) * n;
-            T zp = T(0), zm = T(0);
-            if (nC == 1) { zp = Zpp[e]; zm = Zmp[e]; }
-            else for (int c = 0; c < nC; ++c) {
-                zp = fma(Wc[c], Zpp[(size_t)c * zstride + e], zp);
-                zm = fma(Wc[c], Zmp[(size_t)c * zstride + e], zm);
-            }
-            zpI += zp * F0n[s];
-            zmI += zm * F0n[s];
+            const T f = F0n[s];
+            zpI = fma(zps[s * n + i], f, zpI);
+            zmI = fma(zms[s * n + i], f, zmI);
         }
-        const T mui = a.mu[i];
+        const unsigned sc = a.gcls[nn + i];
+        const T xi = em1[i];
         T vp;
-        if (i >= a.istart && i < a.istart + a.nStokes)
-            vp = wct02 * varpi * zpI * (dtau / mui) * Num<T>::exp_(-dtau / mui);
-        else
-            vp = wct02 * varpi * zpI * (mus / (mui - mus)) * expdiff_neg<T>(dtau / mui, dtau / mus);
-        T vm = wct02 * varpi * zmI * (mus / (mui + mus)) *
-               (-Num<T>::expm1_(-dtau * ((T(1) / mui) + (T(1) / mus))));
+        if (sc == 2) vp = zpI * ai[i] * ei[i];
+        else vp = zpI * a.gs2[i] * ((sc == 0) ? (xi - xs) : expdiff_neg<T>(ai[i], as));
+        // -expm1(-dtau (1/mu_i + 1/mu_s)) = -(em1_i + em1_s + em1_i em1_s)
+        T vm = zmI * a.gs1[i] * (-fma(xi, xs, xi + xs));
         vp *= att;
         vm *= att;
         if (nd >= 1) vm = Num<T>::flip(vm, dmask[i]);
         jp[i] = vp;
         jm[i] = vm;
     }
+    VSM_TICK(12);
 }
 
 // ----------------------------------------------------------------------------
@@ -409,7 +440,7 @@ __global__ void __launch_bounds__(NTHR, MINB) k_layer(ColArgs<T> a, unsigned int
         const T* Zmp = a.Zmp + (size_t)(m - a.mz0) * a.nC * zstride + (a.z_spectral ? p * zstride : 0);
         VSM_T0();
         elemental_fill<T, NN>(a, m, nd, dtau, varpi, tausum, Wc, Zpp, Zmp, zstride,
-                              a.F0 + (a.F0_off + p) * a.nStokes, dmask, r, t, jp, jm, part);
+                              a.F0 + (a.F0_off + p) * a.nStokes, dmask, r, t, jp, jm, part, j1p);
         __syncthreads();
         VSM_TICK(0);
         doubling_loop<T, Ops>(op, nd, expk, r, t, X1, X2, jp, jm, j1p, j1m, v1, v2);

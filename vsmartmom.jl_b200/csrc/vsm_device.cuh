@@ -563,6 +563,11 @@ struct OpsFast {
         constexpr int NP = (NN + 7) & ~7;                   // padded extent (48)
         constexpr int TR = NP / 8 / kWR, TC = NP / 8 / kWC; // mma tiles per warp (rows, cols)
         constexpr int VS = (NV > 0) ? (TR + kWC - 1) / kWC : 1;   // vector-tile slots per warp
+        // k tail: a last k-step with only 1 or 2 valid k (45 = 11*4 + 1) would spend a full DMMA per
+        // tile on zeros; it is done as rank-1 DFMA updates on the accumulator fragments instead
+        // (same datapath, 1/4 of the issue cycles per valid k).
+        constexpr int KT = ((NN & 3) == 1 || (NN & 3) == 2) ? (NN & 3) : 0;
+        constexpr int KM = KT ? (NN - KT) : ((NN + 3) & ~3);        // k range of the DMMA loop
         static_assert(NP / 8 % kWR == 0 && NP / 8 % kWC == 0, "warp tiling");
         const int warp = tid >> 5, lane = tid & 31;
         const int g = lane >> 2, tg = lane & 3;
@@ -582,7 +587,7 @@ struct OpsFast {
 #pragma unroll
             for (int v = 0; v < VS; ++v) cv[v][0] = cv[v][1] = 0.0;
 #pragma unroll
-            for (int k0 = 0; k0 < NP; k0 += 4) {
+            for (int k0 = 0; k0 < KM; k0 += 4) {
                 double a[TR], b[TC];
                 const bool kin = (k0 + 3 < NN) || (k0 + tg < NN);
                 uint32_t mk = 0;
@@ -612,6 +617,45 @@ struct OpsFast {
                         if (v * kWC + wc < TR)                 // warp-uniform
                             asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                                          : "+d"(cv[v][0]), "+d"(cv[v][1]) : "d"(av), "d"(bx));
+                    }
+                }
+            }
+            if (KT > 0) {
+                // accumulator fragment: lane (g, tg) holds C[g][2tg], C[g][2tg+1] of each tile
+                const T* At = rebase(A) + wi + g;             // A[wi + 8r + g][k]
+                const T* Bt = rebase(B) + (wj + 2 * tg) * kLd;  // B[k][wj + 8q + 2tg + h]
+#pragma unroll
+                for (int k = KM; k < NN; ++k) {
+                    double a[TR], b[TC][2];
+#pragma unroll
+                    for (int r = 0; r < TR; ++r) {
+                        a[r] = (double)At[r * 8 + k * kLd];
+                        if (KSIGN) a[r] = Num<double>::flip(a[r], dmask[k]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < TC; ++q) {
+                        b[q][0] = (double)Bt[k + q * 8 * kLd];
+                        b[q][1] = (double)Bt[k + (q * 8 + 1) * kLd];
+                    }
+#pragma unroll
+                    for (int r = 0; r < TR; ++r)
+#pragma unroll
+                        for (int q = 0; q < TC; ++q) {
+                            c[r][q][0] = fma(a[r], b[q][0], c[r][q][0]);
+                            c[r][q][1] = fma(a[r], b[q][1], c[r][q][1]);
+                        }
+                    if (NV > 0) {
+                        const double xk1 = (double)rebase(x1)[k];
+                        const double xk2 = (NV == 2) ? (double)rebase(x2)[k] : 0.0;
+#pragma unroll
+                        for (int v = 0; v < VS; ++v) {
+                            double av = a[0];
+#pragma unroll
+                            for (int r = 1; r < TR; ++r)
+                                if (r / kWC == v) av = (r % kWC == wc) ? a[r] : av;
+                            cv[v][0] = fma(av, xk1, cv[v][0]);       // only the tg == 0 lanes' values are used
+                            cv[v][1] = fma(av, xk2, cv[v][1]);
+                        }
                     }
                 }
             }
