@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-aerosol", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gj-compare", action="store_true",
+                    help="skip the extra Gauss-Jordan-only steps (used for ncu launch lists)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
 
@@ -207,6 +209,8 @@ def run_b200(args):
     Rg = torch.empty((world * nS, n, nV), dtype=tdt, device=dev) if world > 1 else None
     Tg = torch.empty_like(Rg) if world > 1 else None
 
+    done = torch.cuda.Event(blocking=True)
+
     def step_device():
         R, T, _, _, _ = rr.rt_column_device(ctx, prep, tr_d, ta_d, f0_d, want_hdr=False)
         if world > 1:                                  # the single gather of R/T at the end of rt_run
@@ -223,9 +227,14 @@ def run_b200(args):
             dist.all_gather_into_tensor(Tg, T)
             R, T = Rg, Tg
         R_h.copy_(R, non_blocking=True); T_h.copy_(T, non_blocking=True)
-        torch.cuda.synchronize()
+        done.record()
+        done.synchronize()          # blocking wait (the host thread sleeps instead of spinning)
 
     def barrier():
+        # sleep on a blocking event first: a host thread that spins for seconds in
+        # cudaDeviceSynchronize eats the container's CPU quota and gets descheduled afterwards
+        done.record()
+        done.synchronize()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -268,7 +277,7 @@ def run_b200(args):
     # the same step with the adaptive inverse switched off (Gauss-Jordan elimination for every
     # (I - A)^-1, the reference's getrf/getri route): reported beside the headline, not as it
     gj = None
-    if world == 1 and FT == np.float64:
+    if world == 1 and FT == np.float64 and not args.no_gj_compare:
         ctx.set_inverse_mode(0)
         step_device()
         barrier()

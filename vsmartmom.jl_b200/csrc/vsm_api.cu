@@ -39,6 +39,10 @@ struct vsm_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> seg_layer, seg_add;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
+    // pinned staging of the per-call constant blob (so that the upload never blocks the host)
+    void* stage = nullptr;
+    size_t stage_cap = 0;
+    cudaEvent_t stage_done = nullptr;
 };
 
 #define CK(call)                                                                  \
@@ -122,6 +126,8 @@ extern "C" int vsm_destroy(vsm_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->consts, &ctx->props, &ctx->added, &ctx->slabs, &ctx->partial, &ctx->counter, &ctx->l0tmp, &ctx->geom};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->stage) cudaFreeHost(ctx->stage);
+    if (ctx->stage_done) cudaEventDestroy(ctx->stage_done);
     delete ctx;
     return VSM_OK;
 }
@@ -410,10 +416,20 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
     const size_t offI = (bytesT + 15) & ~size_t(15);
     int rc = ensure(ctx, ctx->consts, offI + bytesI);
     if (rc) return rc;
-    // the previous call on this stream may still read the blob: order the copy on the stream
-    CK(cudaMemcpyAsync(ctx->consts.p, fT.data(), bytesT, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync((char*)ctx->consts.p + offI, fI.data(), bytesI, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));   // fT/fI are stack-owned vectors
+    // The previous call on this stream may still read the device blob: the copy is ordered on the
+    // stream.  It goes through a pinned staging buffer owned by the context so that nothing here
+    // waits for the GPU (the staging buffer is reused only after its last upload has completed).
+    if (ctx->stage_cap < offI + bytesI) {
+        if (ctx->stage) { CK(cudaStreamSynchronize(ctx->stream)); cudaFreeHost(ctx->stage); ctx->stage = nullptr; ctx->stage_cap = 0; }
+        CK(cudaMallocHost(&ctx->stage, (offI + bytesI) * 2));
+        ctx->stage_cap = (offI + bytesI) * 2;
+    }
+    if (!ctx->stage_done) CK(cudaEventCreateWithFlags(&ctx->stage_done, cudaEventDisableTiming));
+    else CK(cudaEventSynchronize(ctx->stage_done));
+    memcpy(ctx->stage, fT.data(), bytesT);
+    memcpy((char*)ctx->stage + offI, fI.data(), bytesI);
+    CK(cudaMemcpyAsync(ctx->consts.p, ctx->stage, offI + bytesI, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->stage_done, ctx->stream));
     const T* cT = (const T*)ctx->consts.p;
     const int* cI = (const int*)((char*)ctx->consts.p + offI);
     if ((rc = ensure(ctx, ctx->geom, ((size_t)2 * N * N + 2 * N) * sizeof(T) + (size_t)N * N + N))) return rc;

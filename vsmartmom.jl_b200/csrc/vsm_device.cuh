@@ -420,17 +420,20 @@ struct OpsFast {
     __device__ __forceinline__ void sync() const { group_sync<NTHR, BAR>(); }
     __device__ __forceinline__ int nthreads() const { return NTHR; }
 
-    template <bool KSIGN, class Epi>
+    // SYNC_EPI: a group barrier between the last operand read and the epilogue, so that the
+    // epilogue may overwrite A or B (each thread only touches the elements it owns).
+    template <bool KSIGN, class Epi, bool SYNC_EPI = false>
     __device__ __forceinline__ void mm(const T* __restrict__ A, const T* __restrict__ B, Epi epi) const {
         if constexpr (sizeof(T) == 8 && (NTHR % 32 == 0) && (NTHR / 32 >= 4)) {
-            mm_dmma_epi<KSIGN>(A, B, epi);
+            mm_dmma_epi<KSIGN, Epi, SYNC_EPI>(A, B, epi);
             return;
         }
-        if (tid < NT * NT) {
-            const int i0 = (tid % NT) * TM, j0 = (tid / NT) * TM;
+        const bool act = tid < NT * NT;
+        const int i0 = (tid % NT) * TM, j0 = (tid / NT) * TM;
+        T acc[TM][TM];
+        if (act) {
             const T* Ap = rebase(A) + i0;
             const T* Bp = rebase(B) + j0 * kLd;
-            T acc[TM][TM];
 #pragma unroll
             for (int x = 0; x < TM; ++x)
 #pragma unroll
@@ -452,6 +455,9 @@ struct OpsFast {
 #pragma unroll
                     for (int y = 0; y < TM; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
             }
+        }
+        if (SYNC_EPI) sync();
+        if (act) {
 #pragma unroll
             for (int y = 0; y < TM; ++y)
 #pragma unroll
@@ -467,7 +473,7 @@ struct OpsFast {
             mm_dmma_v<false, NV, false>(A, B, epi, x1, x2, e1, e2);
         } else {
             mm<false>(A, B, epi);
-            mv_impl<false, NV>(A, x1, x2, e1, e2);
+            if constexpr (NV > 0) mv_impl<false, NV>(A, x1, x2, e1, e2);
         }
     }
 
@@ -799,11 +805,11 @@ struct OpsFast {
     }
 
     // X = (I - P Q)^-1 with S as scratch; ends with the group synchronised.
-    // fp64 tensor-core path: A = P Q is formed first together with its Frobenius norm nu (a
-    // sub-multiplicative bound of the spectral radius).  When nu is small the Neumann series
+    // A = P Q is formed first together with its Frobenius norm nu (a sub-multiplicative bound of
+    // the spectral radius).  When nu is small the Neumann series
     //   (I - A)^-1 = (I + A)(I + A^2)(I + A^4)...      remainder  <= nu^K / (1 - nu)
-    // is summed on the tensor cores up to the order K whose remainder is below 1e-20 -- i.e. far
-    // below fp64 rounding of the O(1) diagonal -- (K = 2: no product at all, K = 3: one, K = 4: two,
+    // is summed (fp64: on the tensor cores) up to the order K whose remainder is below 1e-20
+    // (fp32: 1e-10) -- i.e. far below the rounding of the O(1) diagonal -- (K = 2: no product at all, K = 3: one, K = 4: two,
     // K = 8: four), replacing the latency-bound pivot chain of the elimination by dense products.
     // Thin layers (the vast majority of doubling and adding steps of a real atmosphere) take the
     // K = 2 exit.  Otherwise, or when `neumann` is 0, the blocked Gauss-Jordan inverse runs.
@@ -821,64 +827,67 @@ struct OpsFast {
             mm<false>(P, Q, [&](int i, int j, T acc) { at(X, i, j) = (i == j ? T(1) : T(0)) - acc; });
             sync();
         };
-        if constexpr (kDmma) {
-            if (neumann) {
-                double ss = 0.0;
-                mm_dmma_v<false, NV, false>(P, Q, [&](int i, int j, T acc) { at(X, i, j) = acc; ss = fma((double)acc, (double)acc, ss); },
-                                            x1, x2, e1, e2);
+        if (neumann) {
+            // remainder bound nu^K <= tol, a few hundred times below the rounding of the O(1) diagonal
+            constexpr double tol = (sizeof(T) == 8) ? 1e-20 : 1e-10;
+            constexpr T kNu2K2 = (T)tol;                                       // nu^2 <= tol
+            constexpr T kNu2K3 = (T)((sizeof(T) == 8) ? 4.6e-14 : 2.1e-7);    // nu^3 <= tol
+            constexpr T kNu2K4 = (T)((sizeof(T) == 8) ? 1e-10 : 1e-5);        // nu^4 <= tol
+            constexpr T kNu2K8 = (T)((sizeof(T) == 8) ? 9e-6 : 3e-3);         // nu^8 <= tol
+            T ss = T(0);
+            mmv<NV>(P, Q, [&](int i, int j, T acc) { at(X, i, j) = acc; ss = fma(acc, acc, ss); }, x1, x2, e1, e2);
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                double* np = reinterpret_cast<double*>(part);
-                if ((tid & 31) == 0) np[tid >> 5] = ss;
-                sync();
-                double nu2 = 0.0;
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            T* np = part;
+            if ((tid & 31) == 0) np[tid >> 5] = ss;
+            sync();
+            T nu2 = T(0);
 #pragma unroll
-                for (int w = 0; w < kWR * kWC; ++w) nu2 += np[w];
-                if (nu2 <= 1e-20) {                                   // K = 2:  G = I + A
-                    VSM_NCOUNT(0);
-                    if (tid < NN) at(X, tid, tid) += T(1);
-                    sync();
-                    return;
-                }
-                if (nu2 <= 4.6e-14) {                                 // K = 3:  G = I + A + A^2   (nu^3 <= 1e-20)
-                    VSM_NCOUNT(1);
-                    auto e = [&](int i, int j, T acc) { at(X, i, j) = ((i == j ? T(1) : T(0)) + at(X, i, j)) + acc; };
-                    mm_dmma_epi<false, decltype(e), true>(X, X, e);
-                    sync();
-                    return;
-                }
-                if (nu2 <= 1e-10) {                                   // K = 4:  G = I + A + A^2 + A A^2
-                    VSM_NCOUNT(2);
-                    mm_dmma_epi<false>(X, X, [&](int i, int j, T acc) { at(S, i, j) = acc; });
-                    sync();
-                    auto e = [&](int i, int j, T acc) { at(X, i, j) = ((i == j ? T(1) : T(0)) + at(X, i, j)) + (at(S, i, j) + acc); };
-                    mm_dmma_epi<false, decltype(e), true>(X, S, e);
-                    sync();
-                    return;
-                }
-                if (nu2 <= 9e-6) {                                    // K = 8:  ... (I + A^4)
-                    VSM_NCOUNT(3);
-                    mm_dmma_epi<false>(X, X, [&](int i, int j, T acc) { at(S, i, j) = acc; });
-                    sync();
-                    auto e1 = [&](int i, int j, T acc) { at(X, i, j) = ((i == j ? T(1) : T(0)) + at(X, i, j)) + (at(S, i, j) + acc); };
-                    mm_dmma_epi<false, decltype(e1), true>(X, S, e1);
-                    sync();
-                    auto e2 = [&](int i, int j, T acc) { at(S, i, j) = acc; };
-                    mm_dmma_epi<false, decltype(e2), true>(S, S, e2);
-                    sync();
-                    auto e3 = [&](int i, int j, T acc) { at(X, i, j) += acc; };
-                    mm_dmma_epi<false, decltype(e3), true>(X, S, e3);
-                    sync();
-                    return;
-                }
-                for (int e = tid; e < NN * NN; e += NTHR) {           // X = I - A, then eliminate
-                    const int i = e % NN, j = e / NN;
-                    at(X, i, j) = (i == j ? T(1) : T(0)) - at(X, i, j);
-                }
+            for (int w = 0; w < (NTHR + 31) / 32; ++w) nu2 += np[w];
+            if (nu2 <= kNu2K2) {                                  // K = 2:  G = I + A
+                VSM_NCOUNT(0);
+                if (tid < NN) at(X, tid, tid) += T(1);
                 sync();
-                inverse(X, rebuild);
                 return;
             }
+            if (nu2 <= kNu2K3) {                                  // K = 3:  G = I + A + A^2
+                VSM_NCOUNT(1);
+                auto e = [&](int i, int j, T acc) { at(X, i, j) = ((i == j ? T(1) : T(0)) + at(X, i, j)) + acc; };
+                mm<false, decltype(e), true>(X, X, e);
+                sync();
+                return;
+            }
+            if (nu2 <= kNu2K4) {                                  // K = 4:  G = I + A + A^2 + A A^2
+                VSM_NCOUNT(2);
+                mm<false>(X, X, [&](int i, int j, T acc) { at(S, i, j) = acc; });
+                sync();
+                auto e = [&](int i, int j, T acc) { at(X, i, j) = ((i == j ? T(1) : T(0)) + at(X, i, j)) + (at(S, i, j) + acc); };
+                mm<false, decltype(e), true>(X, S, e);
+                sync();
+                return;
+            }
+            if (nu2 <= kNu2K8) {                                  // K = 8:  ... (I + A^4)
+                VSM_NCOUNT(3);
+                mm<false>(X, X, [&](int i, int j, T acc) { at(S, i, j) = acc; });
+                sync();
+                auto e1 = [&](int i, int j, T acc) { at(X, i, j) = ((i == j ? T(1) : T(0)) + at(X, i, j)) + (at(S, i, j) + acc); };
+                mm<false, decltype(e1), true>(X, S, e1);
+                sync();
+                auto e2 = [&](int i, int j, T acc) { at(S, i, j) = acc; };
+                mm<false, decltype(e2), true>(S, S, e2);
+                sync();
+                auto e3 = [&](int i, int j, T acc) { at(X, i, j) += acc; };
+                mm<false, decltype(e3), true>(X, S, e3);
+                sync();
+                return;
+            }
+            for (int e = tid; e < NN * NN; e += NTHR) {           // X = I - A, then eliminate
+                const int i = e % NN, j = e / NN;
+                at(X, i, j) = (i == j ? T(1) : T(0)) - at(X, i, j);
+            }
+            sync();
+            inverse(X, rebuild);
+            return;
         }
         mmv<NV>(P, Q, [&](int i, int j, T acc) { at(X, i, j) = (i == j ? T(1) : T(0)) - acc; }, x1, x2, e1, e2);
         sync();
