@@ -43,6 +43,8 @@ extern "C" {
 
 /* surface kinds handled natively by vsm_rt_column_* */
 #define VSM_SURFACE_LAMBERTIAN_SCALAR 0   /* src/CoreRT/Surfaces/lambertian_surface.jl:41-95 */
+#define VSM_SURFACE_BRDF_FOURIER      1   /* create_surface_layer!(::AbstractSurfaceType), rpv_surface.jl:51-97:
+                                            the caller supplies the Fourier moments of R_surf */
 
 typedef struct vsm_ctx vsm_ctx;   /* opaque; one per (device, host task) */
 
@@ -161,6 +163,11 @@ typedef struct vsm_column_desc {
     const void* Zpp;         /* (N,N,1+nAer,n_moments); component 0 = Rayleigh
                                 (Scattering.compute_Z_moments, compute_Z_matrices.jl:26-110) */
     const void* Zmp;
+    /* device, FT -- only read when surface_kind == VSM_SURFACE_BRDF_FOURIER (and struct_size covers it):
+     * (N,N,n_moments), moment m = the reference's R_surf before the Diagonal(qp_μN.*wt_μN) scaling, i.e.
+     * 2*reflectance(brdf,pol_type,qp_μ,0) for m = 0 and reflectance(brdf,pol_type,qp_μ,m) otherwise
+     * (rpv_surface.jl:69-75).  Spectrally constant, like the reference's. */
+    const void* surf_rho;
 } vsm_column_desc;
 /* outputs: device; R_SFI/T_SFI/hdr (nVZA,nStokes,nSpec); bhr_* (nStokes,nSpec);
  * hdr/bhr_uw/bhr_dw may be NULL.  Outputs are overwritten (not accumulated).  */

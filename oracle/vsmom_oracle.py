@@ -346,6 +346,8 @@ class Model:
     dtau_min_floor: Optional[float] = None   # None -> 1024*eps(FT)
     F0: Optional[np.ndarray] = None          # (pol_n, nSpec); default unit Stokes-I
     FT: type = np.float64
+    # BRDF surface: Fourier moments of R_surf, (m_max+1, N, N) -- see brdf_surface(); None = Lambertian
+    surface_rho: Optional[np.ndarray] = None
 
     @property
     def nSpec(self):
@@ -720,6 +722,66 @@ def lambertian_surface(model: Model, m: int, tau_sum_end):
 
 
 # --------------------------------------------------------------------------
+# BRDF surfaces   src/CoreRT/Surfaces/rpv_surface.jl:51-97 (layer), :113-165 (RPV)
+# --------------------------------------------------------------------------
+def brdf_surface(model: Model, m: int, tau_sum_end):
+    """create_surface_layer!(::AbstractSurfaceType, ...) (rpv_surface.jl:51-97) with the
+    Fourier moment R_surf = model.surface_rho[m] (already carrying the factor 2 of m == 0,
+    :69-73).  Unlike the Lambertian case every moment has a reflecting surface."""
+    FT = model.FT
+    q = model.quad
+    pol_n = model.pol_n
+    N = q.qp_muN.size
+    nS = tau_sum_end.shape[0]
+    I = np.eye(N, dtype=FT)
+    t = np.broadcast_to(I, (nS, N, N))
+    zeros = np.zeros((nS, N, N), FT)
+    R_surf = np.asarray(model.surface_rho[m], FT)
+    I0 = np.zeros(N, FT)
+    I0[pol_n * q.imu0] = 1
+    att = np.exp(-tau_sum_end / FT(q.mu0))[:, None]
+    j0p = (I0[None, :] * att).astype(FT)
+    j0m = (FT(q.mu0) * (R_surf @ I0)[None, :] * att).astype(FT)
+    r_mp = R_surf * (q.qp_muN * q.wt_muN).astype(FT)[None, :]
+    r_mp = np.broadcast_to(r_mp, (nS, N, N))
+    return r_mp, zeros, t, t, j0p, j0m
+
+
+def rpv_reflectance(rho0, rho_c, k, theta_hs, mu_i, mu_r, dphi):
+    """Scalar RPV BRDF (Rahman, Pinty, Verstraete 1993) with the reference's sign
+    conventions, rpv_surface.jl:113-144."""
+    th_i = math.acos(mu_i)
+    th_r = math.acos(mu_r)
+    cosg = -mu_i * mu_r + math.sin(th_i) * math.sin(th_r) * math.cos(dphi)
+    G = math.sqrt(math.tan(th_i) ** 2 + math.tan(th_r) ** 2 + 2 * math.tan(th_i) * math.tan(th_r) * math.cos(dphi))
+    M = (mu_i * mu_r) ** (k - 1) / (mu_i + mu_r) ** (1 - k)
+    th = -theta_hs
+    F = (1 - th * th) / (1 + th * th + 2 * th * cosg) ** 1.5
+    H = 1 + (1 - rho_c) / (1 + G)
+    return rho0 * M * F * H
+
+
+def rpv_surface_rho(quad: QuadPoints, m_max: int, rho0, rho_c, k, theta_hs, nquad: int = 100):
+    """Fourier moments of the RPV reflectance matrix, reflectance(brdf, pol_type, mu, m)
+    (rpv_surface.jl:166-196: 100-point Gauss-Legendre in azimuth over [0, pi], only the
+    Stokes-I block is non-zero) times the factor 2 that create_surface_layer! applies to
+    m == 0 (:69-73; for m > 0 the 2 is `ff`).  Pure-Python loops: small cases only."""
+    pol_n = quad.pol_n
+    mu = np.asarray(quad.qp_mu, float)
+    nq = mu.size
+    phi, w = gauleg(nquad, 0.0, math.pi)
+    out = np.zeros((m_max + 1, nq * pol_n, nq * pol_n))
+    for m in range(m_max + 1):
+        for i in range(nq):
+            for j in range(nq):
+                c = 0.0
+                for x, wx in zip(phi, w):
+                    c += wx * rpv_reflectance(rho0, rho_c, k, theta_hs, mu[i], mu[j], x) * math.cos(m * x)
+                out[m, i * pol_n, j * pol_n] = 2.0 * c / math.pi
+    return out
+
+
+# --------------------------------------------------------------------------
 # rt_run (noRS, SFI)   src/CoreRT/rt_run.jl:238-539, rt_kernel.jl:175-250
 # --------------------------------------------------------------------------
 def rt_kernel_layer(model: Model, m: int, iz: int, ctl: BandControl, props: CoreProps,
@@ -804,7 +866,10 @@ def rt_run(model: Model, sel=slice(None), return_streams: bool = False, prep: Op
             C = rt_kernel_layer(model, m, iz, ctl, props[iz], C, F0,
                                 ctl.tau_sum[idx, iz])
         # surface + final interaction (rt_run.jl:423-465)
-        s = lambertian_surface(model, m, ctl.tau_sum[idx, -1])
+        if model.surface_rho is not None:
+            s = brdf_surface(model, m, ctl.tau_sum[idx, -1])
+        else:
+            s = lambertian_surface(model, m, ctl.tau_sum[idx, -1])
         r_mp_s, r_pm_s, t_s, t_mm_s, j0p_s, j0m_s = s
         C = interaction(ctl.interface[-1], C, r_mp_s, r_pm_s, t_s, t_mm_s, j0p_s, j0m_s)
         # interaction_hdrf!, interaction_hdrf.jl:4-42

@@ -30,7 +30,8 @@ def to_oracle(model: vb.RTModel) -> orc.Model:
                      greek_rayleigh=g(model.greek_rayleigh), albedo=model.albedo, m_max=model.m_max,
                      varpi_cabannes=model.varpi_cabannes,
                      dtau_max_threshold=model.numerics.dtau_max_threshold,
-                     dtau_min_floor=model.numerics.dtau_min_floor, FT=model.float_type)
+                     dtau_min_floor=model.numerics.dtau_min_floor, FT=model.float_type,
+                     surface_rho=model.surface_rho)
 
 
 def rayleigh_slab_model(pol, nstreams, sza, vza, vaz, tau, albedo, FT=np.float64, nSpec=2, depol=0.0):

@@ -34,9 +34,10 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_header_layout():
     from vsmom_b200 import _lib
-    # 12 int32 + 1 double + 20 pointers ; 10 int32 + 3 double + 16 pointers
+    # 12 int32 + 1 double + 20 pointers ; 10 int32 + 3 double + 17 pointers (16 before surf_rho)
     assert ctypes.sizeof(_lib.LayerDesc) == 12 * 4 + 8 + 20 * 8
-    assert ctypes.sizeof(_lib.ColumnDesc) == 10 * 4 + 3 * 8 + 16 * 8
+    assert ctypes.sizeof(_lib.ColumnDesc) == 10 * 4 + 3 * 8 + 17 * 8
+    assert _lib.ColumnDesc.surf_rho.offset == 10 * 4 + 3 * 8 + 16 * 8      # the pre-BRDF descriptor size, still accepted
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -92,6 +92,31 @@ def test_inverse_routes_match_oracle_and_each_other(ctx, scale):
         assert relerr(ad[k], gj[k]) <= 5e-10, k
 
 
+def test_brdf_surface_matches_oracle(ctx):
+    # create_surface_layer!(::AbstractSurfaceType) (rpv_surface.jl:51-97): an RPV surface, every Fourier
+    # moment reflects.  configs[1] shape (N=45, specialised kernels) and a small generic-N scene.
+    for kw in (dict(nSpec=10, aerosol=True), dict(nSpec=6, nstreams=4, polarization_type="Stokes_IQUV", aerosol=True)):
+        m = vb.synthetic_o2a_model(**kw)
+        m.tau_abs = m.tau_abs * np.logspace(-5.0, -1.0, m.nSpec)[:, None]
+        m.surface_rho = vb.rpv_surface_rho(m.quad_points, m.pol_n, m.m_max, rho0=0.2, rho_c=0.7, k=0.8, theta_hs=-0.1)
+        assert_close(run_gpu(m, ctx), orc.rt_run(to_oracle(m)), F64_TOL)
+
+
+def test_degenerate_rpv_is_lambertian(ctx):
+    # rho0 = albedo, k = 1, Theta = 0, rho_c = 1  ->  rho == albedo: the BRDF path must give the Lambertian result
+    m = vb.synthetic_o2a_model(nSpec=8, aerosol=True, albedo=0.3)
+    m.tau_abs = m.tau_abs * np.logspace(-5.0, -1.0, 8)[:, None]
+    lam = run_gpu(m, ctx)
+    m.surface_rho = vb.rpv_surface_rho(m.quad_points, m.pol_n, m.m_max, rho0=0.3, rho_c=1.0, k=1.0, theta_hs=0.0)
+    brdf = run_gpu(m, ctx)
+    # (the m > 0 moments of the BRDF are quadrature noise ~1e-17, not exact zeros.)  T_SFI is left out:
+    # create_surface_layer!(::AbstractSurfaceType) injects the direct beam j0+ = I0 exp(-tau/mu0) for every
+    # m (rpv_surface.jl:83), the Lambertian one only for m = 0, so T at a VZA that shares the solar stream
+    # differs by construction.
+    for k in ("R_SFI", "hdr", "bhr_uw", "bhr_dw"):
+        assert relerr(brdf[k], lam[k]) <= F64_TOL, k
+
+
 @pytest.mark.parametrize("pol", ["Stokes_I", "Stokes_IQ", "Stokes_IQUV"])
 def test_other_polarisations(ctx, pol):
     m = vb.synthetic_o2a_model(nSpec=8, nstreams=4, polarization_type=pol, aerosol=True)

@@ -73,3 +73,18 @@ def test_synthetic_scene_shape():
     col = m.tau_abs.sum(axis=1)
     assert col.max() <= 100.0 * 1.01 and col.min() > 0
     assert abs(m.tau_aer.sum() - 0.3) < 1e-12
+
+
+def test_rpv_fourier_moments_match_oracle_restatement():
+    # host mirror (vectorised) against the oracle's loop restatement of rpv_surface.jl:113-196
+    import vsmom_oracle as orc
+    from helpers import to_oracle
+    m = vb.synthetic_o2a_model(nSpec=2, nstreams=3, polarization_type="Stokes_IQU", aerosol=False)
+    got = vb.rpv_surface_rho(m.quad_points, m.pol_n, 3, rho0=0.2, rho_c=0.7, k=0.8, theta_hs=-0.1)
+    ref = orc.rpv_surface_rho(to_oracle(m).quad, 3, 0.2, 0.7, 0.8, -0.1)
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref)) <= 1e-13 * np.max(np.abs(ref))
+    # degenerate RPV = Lambertian: 2*albedo in the Stokes-I block of m = 0, nothing else
+    lam = vb.rpv_surface_rho(m.quad_points, m.pol_n, 2, rho0=0.3, rho_c=1.0, k=1.0, theta_hs=0.0)
+    assert np.allclose(lam[0, ::3, ::3], 0.6, atol=1e-13) and np.abs(lam[1:]).max() < 1e-13
+    assert np.abs(lam[0, 1::3]).max() == 0 and np.abs(lam[0, :, 1::3]).max() == 0

@@ -1,6 +1,7 @@
 // vsm_api.cu -- C-ABI (include/vsmom_b200.h): context, workspace planning, launches.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
@@ -356,8 +357,11 @@ template <typename T>
 static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T_SFI, T* hdr,
                           T* bhr_uw, T* bhr_dw) {
     if (!ctx) return VSM_ERR_INVALID_ARG;
-    if (!d || d->struct_size != (int)sizeof(vsm_column_desc))
+    // struct_size versions the descriptor: the layout up to Zmp (Lambertian only) or the full one
+    if (!d || (d->struct_size != (int)sizeof(vsm_column_desc) && d->struct_size != (int)offsetof(vsm_column_desc, surf_rho)))
         return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column: descriptor NULL or struct_size mismatch");
+    const void* surf_rho = (d->struct_size == (int)sizeof(vsm_column_desc) && d->surface_kind == VSM_SURFACE_BRDF_FOURIER)
+                               ? d->surf_rho : nullptr;
     if (d->nSpec == 0) return VSM_OK;            // empty shard: nothing to do
     if (!R_SFI || !T_SFI) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column: R_SFI/T_SFI NULL");
     const int N = d->N, nSt = d->nStokes, Nz = d->Nz, nAer = d->nAer, nV = d->nVZA, nM = d->n_moments;
@@ -365,8 +369,10 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
     if (N <= 0 || nSt < 1 || nSt > 4 || N % nSt != 0 || Nz <= 0 || nAer < 0 || nAer + 1 > kMaxComp ||
         nV <= 0 || nM <= 0 || nSpec < 0 || d->imu0 < 1 || d->imu0 * nSt > N)
         return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column: bad dimensions");
-    if (d->surface_kind != VSM_SURFACE_LAMBERTIAN_SCALAR)
-        return fail(ctx, VSM_ERR_UNSUPPORTED, "rt_column: only LambertianSurfaceScalar is handled natively");
+    if (d->surface_kind != VSM_SURFACE_LAMBERTIAN_SCALAR && d->surface_kind != VSM_SURFACE_BRDF_FOURIER)
+        return fail(ctx, VSM_ERR_UNSUPPORTED, "rt_column: surface_kind must be LAMBERTIAN_SCALAR or BRDF_FOURIER");
+    if (d->surface_kind == VSM_SURFACE_BRDF_FOURIER && !surf_rho)
+        return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column: BRDF_FOURIER needs surf_rho (and the full descriptor)");
     if (!d->mu || !d->wt || !d->vza_weight || !d->ndoubl || !d->scatter || !d->iface ||
         !d->rayl_allzero || !d->vza_stream || !d->tau_rayl || !d->tau_abs || !d->F0 || !d->Zpp ||
         !d->Zmp || (nAer > 0 && (!d->aer_omega || !d->aer_ft || !d->tau_aer)))
@@ -548,7 +554,7 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
         a.N = N; a.nStokes = nSt; a.Nz = Nz; a.nC = nC; a.nVZA = nV; a.ld = ld;
         a.istart = (d->imu0 - 1) * nSt;
         a.nS = nS; a.n_sched_layers = nSched; a.z_spectral = 0; a.mz0 = 0; a.neumann = ctx->inverse_mode;
-        a.mu0 = (T)d->mu0; a.albedo = (T)d->albedo;
+        a.mu0 = (T)d->mu0; a.albedo = (T)d->albedo; a.surf_rho = (const T*)surf_rho;
         a.mu = cT + o_mu; a.wt = cT + o_wt;
         a.ndoubl = cI + o_nd; a.scatter = cI + o_sc; a.iface = cI + o_if; a.layer_order = cI + o_ord;
         a.Zpp = (const T*)d->Zpp; a.Zmp = (const T*)d->Zmp;

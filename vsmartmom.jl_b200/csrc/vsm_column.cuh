@@ -148,6 +148,7 @@ struct ColArgs {
     int mz0;                 // moment index of the first Z table (0 for L2; m for L1)
     int neumann;             // 1: adaptive Neumann/Gauss-Jordan inverse (OpsFast fp64), 0: elimination only
     T mu0, albedo;
+    const T* surf_rho;       // BRDF surface: Fourier moments of R_surf (N,N,n_moments), or null = Lambertian(albedo)
     const T* mu; const T* wt;                         // [N]
     const int* ndoubl; const int* scatter; const int* iface; const int* layer_order;  // [Nz]
     const T* Zpp; const T* Zmp;                       // (N,N,nC,n_moments)
@@ -725,20 +726,24 @@ __global__ void __launch_bounds__(NTHR) k_adding(ColArgs<T> a, unsigned int tota
             }
             VSM_ATICK(9);
         }
-        // ---- Lambertian surface (lambertian_surface.jl:41-95) + last interaction (rt_run.jl:459-465)
+        // ---- surface (lambertian_surface.jl:41-95 / create_surface_layer!(::AbstractSurfaceType),
+        //      rpv_surface.jl:51-97) + last interaction (rt_run.jl:459-465)
         const T ts_end = a.p_tausum[(size_t)a.Nz * a.nS + p];
         T jps_sun = T(0);
-        if (m == 0) {
-            const T rho = T(2) * a.albedo;
+        if (m == 0 || a.surf_rho) {
             const T att = Num<T>::exp_(-ts_end / a.mu0);
+            const T* rho_m = a.surf_rho ? a.surf_rho + (size_t)m * n * n : nullptr;
+            const T rho_l = T(2) * a.albedo;
             for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
                 const int i = e % n, j = e / n;
                 const bool ii = (i % a.nStokes) == 0 && (j % a.nStokes) == 0;
-                c.r[i + j * ld] = ii ? rho * (a.mu[j] * a.wt[j]) : T(0);
+                const T rho = rho_m ? rho_m[e] : (ii ? rho_l : T(0));
+                c.r[i + j * ld] = rho * (a.mu[j] * a.wt[j]);
             }
             for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const T rho = rho_m ? rho_m[i + (size_t)a.istart * n] : (((i % a.nStokes) == 0) ? rho_l : T(0));
                 jp[i] = (i == a.istart) ? att : T(0);
-                jm[i] = ((i % a.nStokes) == 0) ? a.mu0 * rho * att : T(0);
+                jm[i] = a.mu0 * rho * att;
             }
             jps_sun = att;
             __syncthreads();
@@ -1017,32 +1022,37 @@ __global__ void __launch_bounds__(2 * GT, 1) k_adding2(ColArgs<T> a, unsigned in
             c.r = b ? lr1 : lr0; c.t = b ? lt1 : lt0; c.jp = jpb + b * n; c.jm = jmb + b * n;
         };
 
-        // Lambertian surface (lambertian_surface.jl:41-95) as the "layer" below the last one; only m = 0
-        // has one.  Written in place into layer buffer b.
+        // The surface as the "layer" below the last one, written in place into layer buffer b:
+        // Lambertian (lambertian_surface.jl:41-95; only m = 0 has one) or a BRDF given by the Fourier
+        // moments of R_surf (create_surface_layer!(::AbstractSurfaceType), rpv_surface.jl:51-97).
         T jps_sun = T(0);
+        const bool has_surf = (m == 0) || (a.surf_rho != nullptr);
         auto fill_surface = [&](int b) {
             const T ts_end = a.p_tausum[(size_t)a.Nz * a.nS + p];
-            const T rho = T(2) * a.albedo;
             const T att = Num<T>::exp_(-ts_end / a.mu0);
+            const T* rho_m = a.surf_rho ? a.surf_rho + (size_t)m * n * n : nullptr;
+            const T rho_l = T(2) * a.albedo;
             T* r = lbuf + (2 * b) * LB;
             T* sjp = jpb + b * n; T* sjm = jmb + b * n;
             for (int e = tid; e < n * n; e += blockDim.x) {
                 const int i = e % n, j = e / n;
                 const bool ii = (i % a.nStokes) == 0 && (j % a.nStokes) == 0;
-                r[i + j * ld] = ii ? rho * (a.mu[j] * a.wt[j]) : T(0);
+                const T rho = rho_m ? rho_m[e] : (ii ? rho_l : T(0));
+                r[i + j * ld] = rho * (a.mu[j] * a.wt[j]);
             }
             for (int i = tid; i < n; i += blockDim.x) {
+                const T rho = rho_m ? rho_m[i + (size_t)a.istart * n] : (((i % a.nStokes) == 0) ? rho_l : T(0));
                 sjp[i] = (i == a.istart) ? att : T(0);
-                sjm[i] = ((i % a.nStokes) == 0) ? a.mu0 * rho * att : T(0);
+                sjm[i] = a.mu0 * rho * att;
             }
             if (b) lr1 = r; else lr0 = r;
             jps_sun = att;
         };
-        const int nsteps = a.Nz + (m == 0 ? 1 : 0);       // step Nz = the surface
+        const int nsteps = a.Nz + (has_surf ? 1 : 0);     // step Nz = the surface
 
         fetch_layer(0, p, mi, 0, c.RA, c.TC, c.J0pc, J0m);
         if (a.Nz > 1) fetch_layer(1, p, mi, 1, nullptr, nullptr, jpb + n, jmb + n);
-        else if (m == 0) fill_surface(1);
+        else if (has_surf) fill_surface(1);
         layer_ready(1);                       // layer 0 (element copies) and layer 1
         {
             const bool sc = (lflag[0] & 1) != 0;
@@ -1065,7 +1075,7 @@ __global__ void __launch_bounds__(2 * GT, 1) k_adding2(ColArgs<T> a, unsigned in
             // layer iz is complete in buffer iz&1 (waited + synchronised); start on iz+1
             const int nb = (iz + 1) & 1;
             if (iz + 1 < a.Nz) fetch_layer(iz + 1, p, mi, nb, nullptr, nullptr, jpb + nb * n, jmb + nb * n);
-            else if (iz + 1 == a.Nz && m == 0) fill_surface(nb);
+            else if (iz + 1 == a.Nz && has_surf) fill_surface(nb);
             set_buf(iz & 1);
             VSM_GTICK(5);
             if (itf == 3) add2_step11<T, NN, TM, GT>(c, nosrc, surf);
@@ -1074,7 +1084,7 @@ __global__ void __launch_bounds__(2 * GT, 1) k_adding2(ColArgs<T> a, unsigned in
             layer_ready(nb);
             VSM_GTICK(7);
         }
-        if (m == 0) {                         // hdr source: R_surf J0+ + j0-(surf)   (interaction_hdrf!)
+        if (has_surf) {                       // hdr source: R_surf J0+ + j0-(surf)   (interaction_hdrf!)
             const T* J0pc = c.J0pc; const T* jm = c.jm;
             c.opC.template mv<false>(c.r, J0pc, [&](int i, T s) { hv[i] = s + jm[i]; });
         } else {

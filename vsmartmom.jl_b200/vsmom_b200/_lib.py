@@ -42,7 +42,8 @@ class ColumnDesc(C.Structure):
                 ("mu", f64p), ("wt", f64p), ("aer_omega", f64p), ("aer_ft", f64p), ("tau_aer", f64p),
                 ("vza_weight", f64p),
                 ("ndoubl", i32p), ("scatter", i32p), ("iface", i32p), ("rayl_allzero", i32p), ("vza_stream", i32p),
-                ("tau_rayl", c_void_p), ("tau_abs", c_void_p), ("F0", c_void_p), ("Zpp", c_void_p), ("Zmp", c_void_p)]
+                ("tau_rayl", c_void_p), ("tau_abs", c_void_p), ("F0", c_void_p), ("Zpp", c_void_p), ("Zmp", c_void_p),
+                ("surf_rho", c_void_p)]
 
 
 EXPORTS = [

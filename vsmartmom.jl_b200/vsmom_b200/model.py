@@ -229,6 +229,10 @@ class RTModel:
     numerics: RTNumericalParameters = field(default_factory=RTNumericalParameters)
     float_type: type = np.float64
     spec_grid: Optional[np.ndarray] = None
+    # BRDF surface (any AbstractSurfaceType of the reference other than the scalar Lambertian): Fourier
+    # moments of R_surf, shape (m_max+1, N, N) as built by create_surface_layer! before the
+    # Diagonal(qp_muN.*wt_muN) scaling (rpv_surface.jl:69-75).  None -> Lambertian(albedo).
+    surface_rho: Optional[np.ndarray] = None
 
     @property
     def pol_n(self) -> int:
@@ -401,3 +405,36 @@ def synthetic_o2a_model(nSpec: int = 10000, nstreams: int = 10, polarization_typ
     return RTModel(polarization_type, q, sza, list(vza), list(vaz), tau_rayl.astype(FT), tau_abs.astype(FT),
                    tau_aer, aerosols, get_greek_rayleigh(depol), albedo, derive_m_max(aerosols, nstreams),
                    1.0, RTNumericalParameters(), FT, nu)
+
+
+# ----------------------------------------------------------------------------
+# BRDF surfaces: host-side Fourier moments (the reference computes them on the host too,
+# rpv_surface.jl:166-196); the device consumes them through RTModel.surface_rho.
+# ----------------------------------------------------------------------------
+def rpv_surface_rho(quad: QuadPoints, pol_n: int, m_max: int, rho0: float, rho_c: float, k: float,
+                    theta_hs: float, nquad: int = 100) -> np.ndarray:
+    """Fourier moments 0..m_max of the RPV (Rahman-Pinty-Verstraete) reflectance matrix,
+    ``(m_max+1, N, N)``: ``reflectance(rpv, n, mu_i, mu_r, dphi)`` (rpv_surface.jl:113-144, with the
+    reference's sign conventions) integrated over azimuth with a 100-point Gauss-Legendre rule
+    on [0, pi] (:166-196; only the Stokes-I block is non-zero), times the overall factor 2
+    (``ff`` for m > 0, the explicit ``2*`` of create_surface_layer! for m = 0, :69-73)."""
+    mu = np.asarray(quad.qp_mu, np.float64)
+    x, w = np.polynomial.legendre.leggauss(nquad)
+    phi = 0.5 * math.pi * (x + 1.0)
+    w = 0.5 * math.pi * w
+    mi, mr = mu[:, None, None], mu[None, :, None]
+    cphi = np.cos(phi)[None, None, :]
+    ti, tr = np.arccos(mi), np.arccos(mr)
+    cosg = -mi * mr + np.sin(ti) * np.sin(tr) * cphi
+    G = np.sqrt(np.tan(ti) ** 2 + np.tan(tr) ** 2 + 2 * np.tan(ti) * np.tan(tr) * cphi)
+    M = (mi * mr) ** (k - 1) / (mi + mr) ** (1 - k)
+    th = -theta_hs
+    F = (1 - th * th) / (1 + th * th + 2 * th * cosg) ** 1.5
+    H = 1 + (1 - rho_c) / (1 + G)
+    rho = rho0 * M * F * H                                      # (Nquad, Nquad, nquad)
+    nq = mu.size
+    out = np.zeros((m_max + 1, nq * pol_n, nq * pol_n))
+    for m in range(m_max + 1):
+        c = (rho * (w * np.cos(m * phi))[None, None, :]).sum(axis=2)
+        out[m, ::pol_n, ::pol_n] = 2.0 * c / math.pi
+    return out

@@ -30,6 +30,7 @@ class PreparedColumn:
     ctl: object
     vza_stream: np.ndarray
     vza_weight: np.ndarray
+    surf_rho: Optional[torch.Tensor] = None      # (n_moments, N, N), memory order == Julia (N,N,n_moments)
 
 
 def z_tables(model: RTModel) -> tuple[np.ndarray, np.ndarray]:
@@ -52,8 +53,16 @@ def z_tables(model: RTModel) -> tuple[np.ndarray, np.ndarray]:
 def prepare(model: RTModel, device: torch.device | str = "cuda:0") -> PreparedColumn:
     Zpp, Zmp = z_tables(model)
     stream, w = vza_tables(model)
+    rho = None
+    if model.surface_rho is not None:
+        N = model.quad_points.qp_muN.size
+        sr = np.asarray(model.surface_rho)
+        if sr.shape != (model.m_max + 1, N, N):
+            raise ValueError(f"surface_rho must have shape (m_max+1, N, N) = {(model.m_max + 1, N, N)}, got {sr.shape}")
+        # [m, j, i] <- rho_m[i, j]: column-major (N, N, n_moments) for the library
+        rho = torch.from_numpy(np.ascontiguousarray(sr.transpose(0, 2, 1).astype(model.float_type))).to(device)
     return PreparedColumn(model, torch.from_numpy(Zpp).to(device), torch.from_numpy(Zmp).to(device),
-                          layer_control(model), stream, np.ascontiguousarray(w, dtype=np.float64))
+                          layer_control(model), stream, np.ascontiguousarray(w, dtype=np.float64), rho)
 
 
 def _f64p(a: np.ndarray):
@@ -96,7 +105,8 @@ def rt_column_device(ctx: _lib.Context, prep: PreparedColumn, tau_rayl: torch.Te
     d = _lib.ColumnDesc()
     d.struct_size = C.sizeof(_lib.ColumnDesc)
     d.N, d.nStokes, d.nSpec, d.Nz, d.nAer, d.nVZA = q.qp_muN.size, n, nS, Nz, nAer, nV
-    d.n_moments, d.imu0, d.surface_kind = model.m_max + 1, q.imu0, 0
+    d.n_moments, d.imu0, d.surface_kind = model.m_max + 1, q.imu0, (1 if prep.surf_rho is not None else 0)
+    d.surf_rho = prep.surf_rho.data_ptr() if prep.surf_rho is not None else None
     d.mu0, d.albedo, d.varpi_cabannes = float(q.mu0), float(model.albedo), float(model.varpi_cabannes)
     d.mu, d.wt, d.aer_omega, d.aer_ft, d.tau_aer = _f64p(mu), _f64p(wt), _f64p(om), _f64p(ft), _f64p(taer)
     d.vza_weight = _f64p(prep.vza_weight)
