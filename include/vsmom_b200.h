@@ -175,6 +175,14 @@ int vsm_rt_column_f64(vsm_ctx*, const vsm_column_desc*, double* R_SFI, double* T
                       double* hdr, double* bhr_uw, double* bhr_dw);
 int vsm_rt_column_f32(vsm_ctx*, const vsm_column_desc*, float* R_SFI, float* T_SFI,
                       float* hdr, float* bhr_uw, float* bhr_dw);
+/* The same column with the rt_run_streams export (rt_run.jl:107-193, StreamRTResult): per Fourier moment
+ * the composite after the surface step at ALL quadrature streams, device arrays, each may be NULL:
+ *   Rmp, Tpp  (N,N,nSpec,n_moments)   composite_layer.R⁻⁺ / T⁺⁺
+ *   Jm,  Jp   (N,nSpec,n_moments)     composite_layer.J₀⁻ / J₀⁺  (the reference's (N,1,nSpec) per moment) */
+int vsm_rt_column_streams_f64(vsm_ctx*, const vsm_column_desc*, double* R_SFI, double* T_SFI, double* hdr,
+                              double* bhr_uw, double* bhr_dw, double* Rmp, double* Tpp, double* Jm, double* Jp);
+int vsm_rt_column_streams_f32(vsm_ctx*, const vsm_column_desc*, float* R_SFI, float* T_SFI, float* hdr,
+                              float* bhr_uw, float* bhr_dw, float* Rmp, float* Tpp, float* Jm, float* Jp);
 /* device time (ms) of the most recent vsm_rt_column_* call, measured with CUDA
  * events on the context's stream; blocks until that call has finished.        */
 int vsm_last_column_ms(vsm_ctx*, float* total_ms, float* doubling_ms, float* adding_ms);

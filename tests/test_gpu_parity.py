@@ -117,6 +117,35 @@ def test_degenerate_rpv_is_lambertian(ctx):
         assert relerr(brdf[k], lam[k]) <= F64_TOL, k
 
 
+def test_rt_run_streams_matches_oracle_and_resynthesises(ctx):
+    # rt_run_streams (rt_run.jl:107-193): composite R-+, T++, J0-+ per Fourier moment at all streams; and the
+    # reference's self-consistency KAT (test/test_CoreRT.jl:45-108): Fourier re-synthesis from the per-m J-
+    # equals rt_run, atol 1e-12.  configs[1] shape (specialised kernels) and a generic-N scene.
+    from vsmom_b200 import rt_run as rr
+    for kw in (dict(nSpec=6, aerosol=True), dict(nSpec=5, nstreams=4, polarization_type="Stokes_IQUV", aerosol=True)):
+        m = vb.synthetic_o2a_model(**kw)
+        m.tau_abs = m.tau_abs * np.logspace(-5.0, -1.0, m.nSpec)[:, None]
+        out = rr.rt_run(m, ctx, return_streams=True)
+        ref = orc.rt_run(to_oracle(m), return_streams=True)
+        st = out["streams"]
+        for mi, C in enumerate(ref["streams"]):
+            for got, want, name in ((st["Rmp"][mi], C.Rmp, "Rmp"), (st["Tpp"][mi], C.Tpp, "Tpp"),
+                                    (st["Jm"][mi], C.J0m, "Jm"), (st["Jp"][mi], C.J0p, "Jp")):
+                assert relerr(got, want) <= F64_TOL, (mi, name, relerr(got, want))
+        q, n = m.quad_points, m.pol_n
+        R = np.zeros_like(out["R_SFI"])
+        for mi in range(m.m_max + 1):
+            wgt = (0.5 if mi == 0 else 1.0) / math.pi
+            for iv, (vza, vaz) in enumerate(zip(m.vza, m.vaz)):
+                imu = orc.nearest_point(q.qp_mu, orc.cosd(vza))
+                c, s = orc.cosd(mi * vaz), orc.sind(mi * vaz)
+                wv = wgt * np.array([c, c, s, s][:n])
+                R[iv] += wv[:, None] * st["Jm"][mi][:, imu * n:(imu + 1) * n].T
+        assert np.max(np.abs(R - out["R_SFI"])) <= 1e-12
+    s = rr.rt_run_streams(m, ctx)
+    assert s.Rmp_per_m.shape == (m.m_max + 1, m.nSpec, q.qp_muN.size, q.qp_muN.size) and s.weight[0] == 0.5 / np.pi
+
+
 @pytest.mark.parametrize("pol", ["Stokes_I", "Stokes_IQ", "Stokes_IQUV"])
 def test_other_polarisations(ctx, pol):
     m = vb.synthetic_o2a_model(nSpec=8, nstreams=4, polarization_type=pol, aerosol=True)

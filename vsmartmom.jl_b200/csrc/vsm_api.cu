@@ -355,7 +355,8 @@ static int occupancy(const void* kern, int threads, size_t smem) {
 // ---------------------------------------------------------------------------
 template <typename T>
 static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T_SFI, T* hdr,
-                          T* bhr_uw, T* bhr_dw) {
+                          T* bhr_uw, T* bhr_dw, T* st_Rmp = nullptr, T* st_Tpp = nullptr, T* st_Jm = nullptr,
+                          T* st_Jp = nullptr) {
     if (!ctx) return VSM_ERR_INVALID_ARG;
     // struct_size versions the descriptor: the layout up to Zmp (Lambertian only) or the full one
     if (!d || (d->struct_size != (int)sizeof(vsm_column_desc) && d->struct_size != (int)offsetof(vsm_column_desc, surf_rho)))
@@ -565,6 +566,8 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
         a.vza_row = cI + o_vrow; a.vza_w = cT + o_vw;
         a.part_R = part; a.part_T = part + (size_t)nM * per_m; a.part_H = part + (size_t)2 * nM * per_m;
         a.bhr_uw = cb_uw; a.bhr_dw = cb_dw;
+        a.st_Rmp = st_Rmp; a.st_Tpp = st_Tpp; a.st_Jm = st_Jm; a.st_Jp = st_Jp;
+        a.st_off = (size_t)n0; a.st_nspec = (size_t)nSpec;
 
         for (int m0 = 0; m0 < nM; m0 += Mb) {
             const int mb = std::min(Mb, nM - m0);
@@ -619,6 +622,14 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
 
 extern "C" int vsm_rt_column_f64(vsm_ctx* c, const vsm_column_desc* d, double* R, double* T_, double* hdr, double* uw, double* dw) { return rt_column_impl<double>(c, d, R, T_, hdr, uw, dw); }
 extern "C" int vsm_rt_column_f32(vsm_ctx* c, const vsm_column_desc* d, float* R, float* T_, float* hdr, float* uw, float* dw) { return rt_column_impl<float>(c, d, R, T_, hdr, uw, dw); }
+extern "C" int vsm_rt_column_streams_f64(vsm_ctx* c, const vsm_column_desc* d, double* R, double* T_, double* hdr, double* uw,
+                                         double* dw, double* Rmp, double* Tpp, double* Jm, double* Jp) {
+    return rt_column_impl<double>(c, d, R, T_, hdr, uw, dw, Rmp, Tpp, Jm, Jp);
+}
+extern "C" int vsm_rt_column_streams_f32(vsm_ctx* c, const vsm_column_desc* d, float* R, float* T_, float* hdr, float* uw,
+                                         float* dw, float* Rmp, float* Tpp, float* Jm, float* Jp) {
+    return rt_column_impl<float>(c, d, R, T_, hdr, uw, dw, Rmp, Tpp, Jm, Jp);
+}
 
 extern "C" int vsm_last_column_ms(vsm_ctx* ctx, float* total_ms, float* doubling_ms, float* adding_ms) {
     if (!ctx) return VSM_ERR_INVALID_ARG;

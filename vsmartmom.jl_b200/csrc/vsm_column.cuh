@@ -167,6 +167,10 @@ struct ColArgs {
     const T* vza_w;          // (nStokes,nVZA,n_moments)
     T* part_R; T* part_T; T* part_H;   // [(m*nS + p)*nOut + o]
     T* bhr_uw; T* bhr_dw;              // (nStokes, nS) chunk-local, may be null
+    // rt_run_streams export (rt_run.jl:107-193), all optional: the composite after the surface step,
+    // per moment, at all streams: (N,N,nSpec_total,n_moments) / (N,nSpec_total,n_moments)
+    T* st_Rmp; T* st_Tpp; T* st_Jm; T* st_Jp;
+    size_t st_off, st_nspec;           // first spectral index of this chunk, spectral extent of the arrays
 };
 
 __device__ inline unsigned int next_item(unsigned int* counter, unsigned int* sh) {
@@ -467,6 +471,25 @@ __global__ void __launch_bounds__(NTHR, MINB) k_layer(ColArgs<T> a, unsigned int
     }
 }
 
+// rt_run_streams export: composite R-+ / T++ / J0- / J0+ of point p, moment m to global memory
+template <typename T>
+__device__ __forceinline__ void export_streams(const ColArgs<T>& a, int m, int p, int n, int ld, const T* RA,
+                                               const T* TC, const T* J0m, const T* J0p) {
+    if (!a.st_Rmp && !a.st_Tpp && !a.st_Jm && !a.st_Jp) return;
+    const size_t s = (size_t)m * a.st_nspec + a.st_off + p;
+    if (a.st_Rmp || a.st_Tpp) {
+        for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+            const int i = e % n, j = e / n;
+            if (a.st_Rmp) a.st_Rmp[s * n * n + e] = RA[i + j * ld];
+            if (a.st_Tpp) a.st_Tpp[s * n * n + e] = TC[i + j * ld];
+        }
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (a.st_Jm) a.st_Jm[s * n + i] = J0m[i];
+        if (a.st_Jp) a.st_Jp[s * n + i] = J0p[i];
+    }
+}
+
 // ----------------------------------------------------------------------------
 // interaction!  (interaction.jl:52-266) on arena-resident composite + added layer.
 // Composite: RA=R⁻⁺ RB=R⁺⁻ TC=T⁺⁺ TD=T⁻⁻ ; added: r=r⁻⁺ t=t⁺⁺ (r⁺⁻ = D r D, t⁻⁻ = D t D
@@ -754,6 +777,8 @@ __global__ void __launch_bounds__(NTHR) k_adding(ColArgs<T> a, unsigned int tota
             for (int i = threadIdx.x; i < n; i += blockDim.x) hv[i] = T(0);
             __syncthreads();
         }
+        // ---- rt_run_streams export (streams_callback, rt_run.jl:467-480)
+        export_streams<T>(a, m, p, n, ld, c.RA, c.TC, J0m, J0p);
         // ---- postprocessing_vza! into per-moment partials
         const size_t pbase = ((size_t)m * a.nS + p) * nOut;
         for (int o = threadIdx.x; o < nOut; o += blockDim.x) {
@@ -1093,6 +1118,7 @@ __global__ void __launch_bounds__(2 * GT, 1) k_adding2(ColArgs<T> a, unsigned in
         }
         const size_t pbase = ((size_t)m * a.nS + p) * nOut;
         const T* J0pc = c.J0pc;
+        export_streams<T>(a, m, p, n, ld, c.RA, c.TC, J0m, J0pc);
         for (int o = tid; o < nOut; o += blockDim.x) {
             const int iv = o % a.nVZA, s = o / a.nVZA;
             const T w = a.vza_w[s + a.nStokes * (iv + (size_t)a.nVZA * m)];

@@ -52,6 +52,7 @@ EXPORTS = [
     "vsm_batched_mul_f64", "vsm_batched_mul_f32", "vsm_batch_inv_f64", "vsm_batch_inv_f32",
     "vsm_batch_solve_f64", "vsm_batch_solve_f32",
     "vsm_rt_layer_f64", "vsm_rt_layer_f32", "vsm_rt_column_f64", "vsm_rt_column_f32",
+    "vsm_rt_column_streams_f64", "vsm_rt_column_streams_f32",
     "vsm_last_column_ms", "vsm_last_column_launches",
 ]
 
@@ -72,6 +73,7 @@ for _s in ("f64", "f32"):
     getattr(lib, f"vsm_batch_solve_{_s}").argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]
     getattr(lib, f"vsm_rt_layer_{_s}").argtypes = [c_void_p, C.POINTER(LayerDesc)]
     getattr(lib, f"vsm_rt_column_{_s}").argtypes = [c_void_p, C.POINTER(ColumnDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    getattr(lib, f"vsm_rt_column_streams_{_s}").argtypes = [c_void_p, C.POINTER(ColumnDesc)] + [c_void_p] * 9
 lib.vsm_last_column_ms.argtypes = [c_void_p, C.POINTER(c_float), C.POINTER(c_float), C.POINTER(c_float)]
 lib.vsm_last_column_launches.argtypes = [c_void_p, C.POINTER(c_int), C.POINTER(c_int)]
 

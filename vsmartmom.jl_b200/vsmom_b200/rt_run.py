@@ -74,11 +74,15 @@ def _i32p(a: np.ndarray):
 
 
 def rt_column_device(ctx: _lib.Context, prep: PreparedColumn, tau_rayl: torch.Tensor, tau_abs: torch.Tensor,
-                     F0: torch.Tensor, want_hdr: bool = True):
+                     F0: torch.Tensor, want_hdr: bool = True, streams: Optional[dict] = None):
     """Device-resident entry: ``tau_rayl``/``tau_abs`` are (Nz, nS) torch CUDA tensors
     (memory order == Julia (nSpec, Nz)); ``F0`` is (nS, pol_n).  Returns device
     tensors R_SFI, T_SFI, hdr of shape (nS, pol_n, nVZA) (memory order == Julia
-    (nVZA, pol_n, nSpec)) and bhr_uw, bhr_dw of shape (nS, pol_n)."""
+    (nVZA, pol_n, nSpec)) and bhr_uw, bhr_dw of shape (nS, pol_n).
+    ``streams``: pass an empty dict to also get the per-moment composite at all streams
+    (``rt_run_streams``): it is filled with device tensors ``Rmp``, ``Tpp`` of shape
+    (n_moments, nS, N, N) [memory order == Julia (N,N,nSpec) per moment] and ``Jm``, ``Jp``
+    of shape (n_moments, nS, N)."""
     model = prep.model
     FT = model.float_type
     dt = _tdtype(FT)
@@ -113,20 +117,32 @@ def rt_column_device(ctx: _lib.Context, prep: PreparedColumn, tau_rayl: torch.Te
     d.ndoubl, d.scatter, d.iface, d.rayl_allzero, d.vza_stream = _i32p(nd), _i32p(sc), _i32p(itf), _i32p(rz), _i32p(vs)
     d.tau_rayl, d.tau_abs, d.F0 = tau_rayl.data_ptr(), tau_abs.data_ptr(), F0.data_ptr()
     d.Zpp, d.Zmp = prep.Zpp.data_ptr(), prep.Zmp.data_ptr()
-    fn = _lib.lib.vsm_rt_column_f64 if FT == np.float64 else _lib.lib.vsm_rt_column_f32
-    ctx.check(fn(ctx.handle, C.byref(d), R.data_ptr(), T.data_ptr(),
-                 H.data_ptr() if want_hdr else None, uw.data_ptr() if want_hdr else None,
-                 dw.data_ptr() if want_hdr else None))
+    hp = (H.data_ptr() if want_hdr else None, uw.data_ptr() if want_hdr else None, dw.data_ptr() if want_hdr else None)
+    if streams is not None:
+        N, nM = q.qp_muN.size, model.m_max + 1
+        streams["Rmp"] = torch.empty((nM, nS, N, N), dtype=dt, device=dev)
+        streams["Tpp"] = torch.empty((nM, nS, N, N), dtype=dt, device=dev)
+        streams["Jm"] = torch.empty((nM, nS, N), dtype=dt, device=dev)
+        streams["Jp"] = torch.empty((nM, nS, N), dtype=dt, device=dev)
+        fn = _lib.lib.vsm_rt_column_streams_f64 if FT == np.float64 else _lib.lib.vsm_rt_column_streams_f32
+        ctx.check(fn(ctx.handle, C.byref(d), R.data_ptr(), T.data_ptr(), *hp, streams["Rmp"].data_ptr(),
+                     streams["Tpp"].data_ptr(), streams["Jm"].data_ptr(), streams["Jp"].data_ptr()))
+    else:
+        fn = _lib.lib.vsm_rt_column_f64 if FT == np.float64 else _lib.lib.vsm_rt_column_f32
+        ctx.check(fn(ctx.handle, C.byref(d), R.data_ptr(), T.data_ptr(), *hp))
     return R, T, H, uw, dw
 
 
 def rt_run(model: RTModel, ctx: Optional[_lib.Context] = None, prep: Optional[PreparedColumn] = None,
-           device: str = "cuda:0", sel: slice = slice(None), F0: Optional[np.ndarray] = None):
+           device: str = "cuda:0", sel: slice = slice(None), F0: Optional[np.ndarray] = None,
+           return_streams: bool = False):
     """Host-buffer entry, the call a user makes: NumPy in, NumPy out, like the
     reference's ``rt_run(model)``.  Returns a dict with ``R_SFI``, ``T_SFI``,
     ``hdr`` of shape (nVZA, pol_n, nSpec) and ``bhr_uw``, ``bhr_dw`` (nSpec,).
     ``sel`` restricts the spectral axis (a shard); control flow always comes from
-    the full band."""
+    the full band.  ``return_streams`` adds ``streams``: per Fourier moment the composite
+    ``Rmp``, ``Tpp`` (n_moments, nSpec, N, N) [row i, column j] and ``Jm``, ``Jp``
+    (n_moments, nSpec, N) at all quadrature streams (the reference's ``rt_run_streams``)."""
     if not torch.cuda.is_available():
         raise RuntimeError("vsmom_b200.rt_run needs a CUDA device (B200); there is no CPU fallback")
     own = ctx is None
@@ -148,11 +164,16 @@ def rt_run(model: RTModel, ctx: Optional[_lib.Context] = None, prep: Optional[Pr
         d_tr = torch.from_numpy(tr).pin_memory().to(device, non_blocking=True)
         d_ta = torch.from_numpy(ta).pin_memory().to(device, non_blocking=True)
         d_f0 = torch.from_numpy(f0).to(device)
-        R, T, H, uw, dw = rt_column_device(ctx, prep, d_tr, d_ta, d_f0)
+        st = {} if return_streams else None
+        R, T, H, uw, dw = rt_column_device(ctx, prep, d_tr, d_ta, d_f0, streams=st)
         ctx.synchronize()
         out = dict(R_SFI=R.cpu().numpy().transpose(2, 1, 0), T_SFI=T.cpu().numpy().transpose(2, 1, 0),
                    hdr=H.cpu().numpy().transpose(2, 1, 0), bhr_uw=uw.cpu().numpy()[:, 0].copy(),
                    bhr_dw=dw.cpu().numpy()[:, 0].copy())
+        if return_streams:      # device memory is (m, s, j, i): hand out [m, s, i, j]
+            out["streams"] = dict(Rmp=st["Rmp"].cpu().numpy().transpose(0, 1, 3, 2),
+                                  Tpp=st["Tpp"].cpu().numpy().transpose(0, 1, 3, 2),
+                                  Jm=st["Jm"].cpu().numpy(), Jp=st["Jp"].cpu().numpy())
     if own:
         ctx.close()
     return out
@@ -194,3 +215,32 @@ def rt_run_sharded(model: RTModel, ctx: Optional[_lib.Context] = None, device: O
     if own:
         ctx.close()
     return out
+
+
+@dataclass
+class StreamRTResult:
+    """Mirror of the reference's ``StreamRTResult`` (rt_run.jl:60-131): per-Fourier-moment result
+    at all internal quadrature streams."""
+    qp_mu: np.ndarray
+    imu0: int                 # 1-based, as in the reference
+    mu0: float
+    pol_n: int
+    weight: np.ndarray        # 0.5/pi for m = 0, 1/pi otherwise
+    Rmp_per_m: np.ndarray     # (n_moments, nSpec, N, N)
+    Tpp_per_m: np.ndarray
+    Jm_per_m: np.ndarray      # (n_moments, nSpec, N)
+    Jp_per_m: np.ndarray
+    tau_total: np.ndarray     # (nSpec, Nz) = tau_rayl + tau_abs (aerosol not included, as in the reference)
+    tau_rayl: np.ndarray
+    tau_abs: np.ndarray
+
+
+def rt_run_streams(model: RTModel, ctx: Optional[_lib.Context] = None, device: str = "cuda:0") -> StreamRTResult:
+    """``rt_run_streams(model)`` (rt_run.jl:133-193)."""
+    out = rt_run(model, ctx, device=device, return_streams=True)
+    s = out["streams"]
+    q = model.quad_points
+    nM = model.m_max + 1
+    w = np.array([0.5 / np.pi] + [1.0 / np.pi] * (nM - 1), model.float_type)
+    return StreamRTResult(np.asarray(q.qp_mu), q.imu0, float(q.mu0), model.pol_n, w, s["Rmp"], s["Tpp"], s["Jm"], s["Jp"],
+                          np.asarray(model.tau_rayl + model.tau_abs), np.asarray(model.tau_rayl), np.asarray(model.tau_abs))
