@@ -1,6 +1,6 @@
 """Developer check: where does the end-to-end step spend time beyond the device-timed step?"""
 import os, sys, time
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "vsmartmom.jl_b200"))
 import numpy as np, torch
 import vsmom_b200 as vb

@@ -1,7 +1,7 @@
 """Developer script: quick GPU-vs-oracle parity + timing on a few configurations."""
 import sys, os, time, math
 import numpy as np
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in ("vsmartmom.jl_b200", "oracle", "tests"):
     sys.path.insert(0, os.path.join(ROOT, p))
 import torch

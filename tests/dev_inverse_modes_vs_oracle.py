@@ -1,6 +1,6 @@
 """Developer check: errors of the two inverse modes against the oracle (run on the GPU box)."""
 import sys, os
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in ("vsmartmom.jl_b200", "oracle", "tests"):
     sys.path.insert(0, os.path.join(ROOT, p))
 import numpy as np

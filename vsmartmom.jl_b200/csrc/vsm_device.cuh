@@ -274,17 +274,6 @@ struct OpsGeneric {
     __device__ __forceinline__ void mm(const T* A, const T* B, Epi epi) const {
         cta_mm<T, TM, TM, KSIGN>(n, A, ld, B, ld, dmask, epi);
     }
-    template <bool KSIGN, int MODE>
-    __device__ __forceinline__ void mmC(const T* A, const T* B, T* C) const {
-        const int l = ld;
-        cta_mm<T, TM, TM, KSIGN>(n, A, ld, B, ld, dmask, [&](int i, int j, T acc) {
-            T* c = C + i + j * l;
-            if (MODE == 1) *c += acc;
-            else if (MODE == 2) *c = (i == j ? T(1) : T(0)) - acc;
-            else *c = acc;
-        });
-        __syncthreads();
-    }
     template <bool KSIGN, class Epi>
     __device__ __forceinline__ void mv(const T* A, const T* x, Epi epi) const {
         cta_mv<T, KSIGN>(n, A, ld, x, dmask, part, epi);
@@ -477,72 +466,7 @@ struct OpsFast {
         }
     }
 
-    // C = f(A*B) with the result written to (or accumulated into) C itself; the k range is
-    // split over KS thread sets whose partial tiles are combined through C.
-    //   MODE 0: C = acc      MODE 1: C += acc      MODE 2: C = I - acc
-    // Ends with the group synchronised.
-    template <bool KSIGN, int MODE>
-    __device__ __forceinline__ void mmC(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C) const {
-        constexpr int TILES = NT * NT;
-        constexpr int KL = (NN + KS - 1) / KS;
-        const int tile = tid % TILES, kp = tid / TILES;
-        const bool act = tid < TILES * KS;
-        const int i0 = (tile % NT) * TM, j0 = (tile / NT) * TM;
-        T acc[TM][TM];
-#pragma unroll
-        for (int x = 0; x < TM; ++x)
-#pragma unroll
-            for (int y = 0; y < TM; ++y) acc[x][y] = T(0);
-        if (act) {
-            const int k0 = kp * KL;
-            const T* Ap = rebase(A) + i0 + k0 * kLd;
-            const T* Bp = rebase(B) + j0 * kLd + k0;
-#pragma unroll 5
-            for (int kk = 0; kk < KL; ++kk) {
-                if (k0 + kk < NN) {
-                    T a[TM], b[TM];
-#pragma unroll
-                    for (int x = 0; x < TM; ++x) a[x] = Ap[kk * kLd + x];
-#pragma unroll
-                    for (int y = 0; y < TM; ++y) b[y] = Bp[y * kLd + kk];
-                    if (KSIGN) {
-                        const uint32_t mk = dmask[k0 + kk];
-#pragma unroll
-                        for (int x = 0; x < TM; ++x) a[x] = Num<T>::flip(a[x], mk);
-                    }
-#pragma unroll
-                    for (int x = 0; x < TM; ++x)
-#pragma unroll
-                        for (int y = 0; y < TM; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
-                }
-            }
-        }
-        // combine: sets KS-1 .. 1 deposit / add their partials, set 0 finishes
-#pragma unroll
-        for (int p = KS - 1; p >= 0; --p) {
-            if (act && kp == p) {
-#pragma unroll
-                for (int y = 0; y < TM; ++y)
-#pragma unroll
-                    for (int x = 0; x < TM; ++x) {
-                        T* c = rebase(C) + (i0 + x) + (j0 + y) * kLd;
-                        if (MODE == 1) {
-                            *c += acc[x][y];
-                        } else if (p == KS - 1 && KS > 1) {
-                            *c = acc[x][y];
-                        } else if (p > 0) {
-                            *c += acc[x][y];
-                        } else {
-                            const T tot = (KS > 1) ? acc[x][y] + *c : acc[x][y];
-                            *c = (MODE == 2) ? ((i0 + x == j0 + y) ? T(1) : T(0)) - tot : tot;
-                        }
-                    }
-            }
-            sync();
-        }
-    }
-
-    // fp64 tensor-core GEMM (mma.sync m8n8k4): C = f(A*B), same MODEs as mmC.  Every lane of a
+    // fp64 tensor-core GEMM (mma.sync m8n8k4): epi(i, j, (A*B)_ij).  Every lane of a
     // fragment load reads a distinct element, so shared-memory traffic per FMA is ~3x lower than
     // the broadcast-heavy register-tile SIMT product (which is shared-bandwidth-bound when all the
     // CTAs of an SM are in their GEMM phase).  fp64 DMMA shares the FMA datapath on B200 (same
@@ -690,18 +614,6 @@ struct OpsFast {
             }
         }
     }
-    template <int MODE>
-    __device__ __forceinline__ void mm_dmma(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C) const {
-        T* Cb = rebase(C);
-        mm_dmma_epi<false>(A, B, [&](int i, int j, T v) {
-            T* p = Cb + i + j * kLd;
-            if (MODE == 1) *p += v;
-            else if (MODE == 2) *p = ((i == j) ? T(1) : T(0)) - v;
-            else *p = v;
-        });
-        sync();
-    }
-
     // y = A x (one or two right-hand sides), k split over NTHR/RP segments
     template <bool KSIGN, int NV, class E1, class E2>
     __device__ __forceinline__ void mv_impl(const T* __restrict__ A, const T* __restrict__ x1,
