@@ -507,30 +507,39 @@ struct OpsFast {
         double c[TR][TC][2];
         double cv[VS][2];
         if (wact) {
-            const T* Ab = rebase(A) + wi + g + tg * kLd;      // A[wi+g (+8r)][k0+tg]
-            const T* Bb = rebase(B) + tg + (wj + g) * kLd;    // B[k0+tg][wj+g (+8c)]
-            const T* xs = rebase((NV == 2 && g == 1) ? x2 : x1) + tg;
 #pragma unroll
             for (int r = 0; r < TR; ++r)
 #pragma unroll
                 for (int q = 0; q < TC; ++q) c[r][q][0] = c[r][q][1] = 0.0;
 #pragma unroll
             for (int v = 0; v < VS; ++v) cv[v][0] = cv[v][1] = 0.0;
+            // k of lane tg in DMMA step `st`: inside a block of 16 consecutive k the four lanes of a
+            // fragment row take k = kb + s + 4*tg (s = 0..3 over four steps) instead of kb + 4s + tg.  Any
+            // assignment works as long as A and B agree; with the odd leading dimension 45 this one
+            // makes the 16 lanes of every half-warp hit 16 different 8-byte bank pairs for both
+            // fragments (4*ld = 4 or 12 mod 16 for odd ld), where consecutive k gives 2-way conflicts on every load.
+            constexpr int KB16 = (kLd & 1) ? (KM / 16) * 16 : 0;       // any odd leading dimension
+            constexpr int NSTEP = (KM + 3) / 4;
+            const T* Ar = rebase(A) + wi + g;                 // A[wi+g (+8r)][k]
+            const T* Br = rebase(B) + (wj + g) * kLd;         // B[k][wj+g (+8c)]
+            const T* xr = rebase((NV == 2 && g == 1) ? x2 : x1);
 #pragma unroll
-            for (int k0 = 0; k0 < KM; k0 += 4) {
+            for (int st = 0; st < NSTEP; ++st) {
+                const int k0 = st * 4;
+                const int k = (k0 < KB16) ? ((k0 & ~15) + ((k0 >> 2) & 3) + 4 * tg) : (k0 + tg);
                 double a[TR], b[TC];
-                const bool kin = (k0 + 3 < NN) || (k0 + tg < NN);
+                const bool kin = (k0 + 3 < NN) || (k < NN);
                 uint32_t mk = 0;
-                if (KSIGN) mk = kin ? dmask[k0 + tg] : 0u;
+                if (KSIGN) mk = kin ? dmask[k] : 0u;
 #pragma unroll
                 for (int r = 0; r < TR; ++r) {
-                    a[r] = kin ? (double)Ab[r * 8 + k0 * kLd] : 0.0;
+                    a[r] = kin ? (double)Ar[r * 8 + k * kLd] : 0.0;
                     if (KSIGN) a[r] = Num<double>::flip(a[r], mk);
                 }
 #pragma unroll
-                for (int q = 0; q < TC; ++q) b[q] = kin ? (double)Bb[k0 + q * 8 * kLd] : 0.0;
+                for (int q = 0; q < TC; ++q) b[q] = kin ? (double)Br[k + q * 8 * kLd] : 0.0;
                 double bx = 0.0;
-                if (NV > 0) bx = (g < NV && kin) ? (double)xs[k0] : 0.0;
+                if (NV > 0) bx = (g < NV && kin) ? (double)xr[k] : 0.0;
 #pragma unroll
                 for (int r = 0; r < TR; ++r)
 #pragma unroll
