@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-aerosol", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-sample-ms", type=int, default=1000, help="nvidia-smi polling period during the timed region")
     ap.add_argument("--no-gj-compare", action="store_true",
                     help="skip the extra Gauss-Jordan-only steps (used for ncu launch lists)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -122,13 +123,13 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index, period_ms=1000):
+        self.index, self.proc, self.lines, self.period_ms = index, None, [], int(period_ms)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", str(self.period_ms), "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -244,7 +245,8 @@ def run_b200(args):
         step_device()
     barrier()
     launches0 = ctx.kernel_launches
-    sampler = ClockSampler(local)
+    # (each NVML poll stalls the GPU's work submission for ~10 ms: 200 ms polling cost 3-6 % of the step)
+    sampler = ClockSampler(local, args.clock_sample_ms)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

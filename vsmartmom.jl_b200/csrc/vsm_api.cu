@@ -431,7 +431,7 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
         CK(cudaMallocHost(&ctx->stage, (offI + bytesI) * 2));
         ctx->stage_cap = (offI + bytesI) * 2;
     }
-    if (!ctx->stage_done) CK(cudaEventCreateWithFlags(&ctx->stage_done, cudaEventDisableTiming));
+    if (!ctx->stage_done) CK(cudaEventCreateWithFlags(&ctx->stage_done, cudaEventDisableTiming | cudaEventBlockingSync));
     else CK(cudaEventSynchronize(ctx->stage_done));
     memcpy(ctx->stage, fT.data(), bytesT);
     memcpy((char*)ctx->stage + offI, fI.data(), bytesI);
