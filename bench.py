@@ -345,7 +345,7 @@ def run_b200(args):
                 "adding_kernel": {"achieved": f_add * nS / (t_add * 1e-3) / 1e12, "ms_per_step": t_add},
             },
         }
-        line["config"]["inverse_mode"] = "adaptive (Neumann order 2/4/8 when ||A||_F^K < 1e-20, else blocked Gauss-Jordan)"
+        line["config"]["inverse_mode"] = "adaptive (Neumann order 2/3/4/8 when ||A||_F^K < 1e-20, else blocked Gauss-Jordan)"
         if gj is not None:
             gj["roofline_frac"] = (f_layer * nS / (gj.pop("layer_ms") * 1e-3) / 1e12) / peak_tf if peak_tf else None
             gj["adding_ms"] = gj["adding_ms"]

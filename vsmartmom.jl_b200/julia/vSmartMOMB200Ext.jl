@@ -81,7 +81,12 @@ function CoreRT.rt_kernel!(RS::CoreRT.noRS{FT}, pol_type, SFI, added, comp,
 end
 
 # ---- L2: vsm_rt_column_* replaces the m / iz loops of rt_run(::noRS, model, iBand)
-# (rt_run.jl:383-517) for Lambertian-scalar surfaces; the descriptor is filled from
+# (rt_run.jl:383-517).  Surfaces: LambertianSurfaceScalar natively (surface_kind 0), every other
+# AbstractSurfaceType through the Fourier moments of R_surf that create_surface_layer! builds on
+# the host anyway (surface_kind 1, surf_rho = (m == 0 ? 2 : 1) * reflectance(brdf, pol_type, qp_μ, m),
+# rpv_surface.jl:69-75).  vsm_rt_column_streams_* additionally fills the StreamRTResult arrays of
+# rt_run_streams (rt_run.jl:107-193).  vsm_set_inverse_mode(ctx, 0) forces the elimination route
+# for every (I - A)^-1 (default 1: adaptive Neumann / Gauss-Jordan).  The descriptor is filled from
 # model.τ_rayl/τ_abs/τ_aer, Scattering.compute_Z_moments for m = 0:m_max, the full-band
 # get_dtau_ndoubl / extractEffectiveProps control flow and _precompute_vza_weights --
 # exactly what vsmom_b200/rt_run.py::rt_column_device does; see INTEGRATION.md §3.
