@@ -722,6 +722,139 @@ def lambertian_surface(model: Model, m: int, tau_sum_end):
 
 
 # --------------------------------------------------------------------------
+# Linearized doubling / interaction (config 4, LinMode): the tangent-linear rules of
+# src/CoreRT/CoreKernel/doubling_lin.jl:216-335 and interaction_lin.jl:54-331.
+# Derivative arrays carry a leading parameter axis P: (P, nS, N, N) / (P, nS, N).
+# Pinned by central finite differences of the forward functions above
+# (tests/test_oracle_lin.py), the way the reference pins its own LinMode
+# (analytic vs FD, test/test_forward_lin.jl:167-244).  Not yet used by a CUDA path.
+# --------------------------------------------------------------------------
+def _mvp(A, x):
+    """A (..., N, N) times x (..., N), batched with broadcasting over leading axes."""
+    return np.einsum('...ij,...j->...i', A, x)
+
+
+def doubling_lin(model: Model, ndoubl: int, expk, r, t, j0p, j0m, dr, dt, dj0p, dj0m, dtau_dot):
+    """doubling_allparams_helper! (doubling_lin.jl:216-335).  Forward inputs as doubling();
+    dr, dt (P,nS,N,N), dj0p, dj0m (P,nS,N): per-parameter derivatives of the elemental
+    layer; dtau_dot (P,nS): d(dtau)/dp, which drives d(expk)/dp = -expk/mu0 * dtau_dot (:257-259).
+    Returns (forward tuple as doubling(), derivative tuple (dr_mp, dt_pp, dr_pm, dt_mm, djp, djm))."""
+    FT = model.FT
+    N = r.shape[1]
+    I = np.eye(N, dtype=FT)[None]
+    expk = expk.copy()
+    dexpk = -(expk / FT(model.quad.mu0))[None, :] * dtau_dot
+    r, t, jp, jm = r.copy(), t.copy(), j0p.copy(), j0m.copy()
+    dr, dt, djp, djm = dr.copy(), dt.copy(), dj0p.copy(), dj0m.copy()
+    for _ in range(ndoubl):
+        gp = np.linalg.inv(I - r @ r)                                   # :268
+        tt = t @ gp
+        dgp = gp[None] @ (dr @ r[None] + r[None] @ dr) @ gp[None]        # :273
+        dtt = dt @ gp[None] + t[None] @ dgp                             # :274
+        e = expk[:, None]
+        j1p, j1m = jp * e, jm * e                                       # :283-284
+        a_m = j1m + _mvp(r, jp)                                         # :287
+        a_p = jp + _mvp(r, j1m)                                         # :288
+        dj1p = djp * e[None] + jp[None] * dexpk[:, :, None]             # :291
+        dj1m = djm * e[None] + jm[None] * dexpk[:, :, None]             # :292
+        dexpk = 2 * expk[None, :] * dexpk                               # :294
+        djm_new = djm + _mvp(dtt, a_m[None]) + _mvp(tt[None], dj1m + _mvp(dr, jp[None]) + _mvp(r[None], djp))   # :296-298
+        djp_new = dj1p + _mvp(dtt, a_p[None]) + _mvp(tt[None], djp + _mvp(dr, j1m[None]) + _mvp(r[None], dj1m))  # :299-301
+        djm, djp = djm_new, djp_new
+        jm, jp = jm + _mvp(tt, a_m), j1p + _mvp(tt, a_p)                # :305-306
+        expk = expk ** 2
+        rt = r @ t                                                      # :310
+        dr_new = dr + dtt @ rt[None] + tt[None] @ (dr @ t[None] + r[None] @ dt)   # :314-317
+        dt_new = dtt @ t[None] + tt[None] @ dt                          # :318-319
+        dr, dt = dr_new, dt_new
+        r, t = r + tt @ rt, tt @ t                                      # :323-324
+    Dd = _D_diag(model.pol_n, model.quad.Nquad, FT)
+    if model.pol_n == 1:
+        return (r, t, r.copy(), t.copy(), jp, jm), (dr, dt, dr.copy(), dt.copy(), djp, djm)
+    sgn = (Dd[:, None] * Dd[None, :])
+    r = Dd[None, :, None] * r                                           # apply_D_matrix! (:330-333)
+    dr = Dd[None, None, :, None] * dr
+    jm = Dd[None, :] * jm                                               # apply_D_matrix_SFI! (:334)
+    djm = Dd[None, None, :] * djm
+    return (r, t, sgn[None] * r, sgn[None] * t, jp, jm), (dr, dt, sgn[None, None] * dr, sgn[None, None] * dt, djp, djm)
+
+
+def interaction_lin(itf: int, C: Composite, dC: Composite, r_mp, r_pm, t_pp, t_mm, j0p, j0m,
+                    dr_mp, dr_pm, dt_pp, dt_mm, dj0p, dj0m):
+    """interaction_helper!(::ScatteringInterface_xx, ...) of LinMode (interaction_lin.jl:54-331).
+    C / dC: composite layer and its per-parameter derivatives (fields (P,nS,...)); both are
+    updated and returned."""
+    FT = C.Rmp.dtype
+    N = C.Rmp.shape[1]
+    I = np.eye(N, dtype=FT)[None]
+    b = lambda x: x[None]
+    if itf == 0:     # :54-87
+        dJ0p = dj0p + _mvp(b(t_pp), dC.J0p) + _mvp(dt_pp, b(C.J0p))
+        dJ0m = dC.J0m + _mvp(b(C.Tmm), dj0m) + _mvp(dC.Tmm, b(j0m))
+        J0p = j0p + _mvp(t_pp, C.J0p)
+        J0m = C.J0m + _mvp(C.Tmm, j0m)
+        dTmm = dt_mm @ b(C.Tmm) + b(t_mm) @ dC.Tmm
+        dTpp = dt_pp @ b(C.Tpp) + b(t_pp) @ dC.Tpp
+        C.Tmm, C.Tpp = t_mm @ C.Tmm, t_pp @ C.Tpp
+        C.J0p, C.J0m, dC.J0p, dC.J0m, dC.Tmm, dC.Tpp = J0p, J0m, dJ0p, dJ0m, dTmm, dTpp
+    elif itf == 1:   # :96-141
+        x = _mvp(r_mp, C.J0p) + j0m
+        dJ0m = dC.J0m + _mvp(dC.Tmm, b(x)) + _mvp(b(C.Tmm), _mvp(dr_mp, b(C.J0p)) + _mvp(b(r_mp), dC.J0p) + dj0m)
+        dJ0p = dj0p + _mvp(dt_pp, b(C.J0p)) + _mvp(b(t_pp), dC.J0p)
+        J0m = C.J0m + _mvp(C.Tmm, x)
+        J0p = j0p + _mvp(t_pp, C.J0p)
+        dRmp = dC.Tmm @ b(r_mp) @ b(C.Tpp) + b(C.Tmm) @ dr_mp @ b(C.Tpp) + b(C.Tmm) @ b(r_mp) @ dC.Tpp
+        dTpp = dt_pp @ b(C.Tpp) + b(t_pp) @ dC.Tpp
+        dTmm = dC.Tmm @ b(t_mm) + b(C.Tmm) @ dt_mm
+        C.Rmp = (C.Tmm @ r_mp) @ C.Tpp
+        C.Rpm = r_pm.copy()
+        C.Tpp, C.Tmm = t_pp @ C.Tpp, C.Tmm @ t_mm
+        C.J0p, C.J0m = J0p, J0m
+        dC.Rmp, dC.Rpm, dC.Tpp, dC.Tmm, dC.J0p, dC.J0m = dRmp, dr_pm.copy(), dTpp, dTmm, dJ0p, dJ0m
+    elif itf == 2:   # :150-196
+        y = C.J0p + _mvp(C.Rpm, j0m)
+        dJ0p = dj0p + _mvp(dt_pp, b(y)) + _mvp(b(t_pp), dC.J0p + _mvp(dC.Rpm, b(j0m)) + _mvp(b(C.Rpm), dj0m))
+        dJ0m = dC.J0m + _mvp(dC.Tmm, b(j0m)) + _mvp(b(C.Tmm), dj0m)
+        J0p = j0p + _mvp(t_pp, y)
+        J0m = C.J0m + _mvp(C.Tmm, j0m)
+        dTpp = dt_pp @ b(C.Tpp) + b(t_pp) @ dC.Tpp
+        dTmm = dC.Tmm @ b(t_mm) + b(C.Tmm) @ dt_mm
+        dRpm = dt_pp @ b(C.Rpm) @ b(t_mm) + b(t_pp) @ dC.Rpm @ b(t_mm) + b(t_pp) @ b(C.Rpm) @ dt_mm
+        C.Tpp, C.Tmm = t_pp @ C.Tpp, C.Tmm @ t_mm
+        C.Rpm = (t_pp @ C.Rpm) @ t_mm
+        C.J0p, C.J0m = J0p, J0m
+        dC.Tpp, dC.Tmm, dC.Rpm, dC.J0p, dC.J0m = dTpp, dTmm, dRpm, dJ0p, dJ0m
+    else:            # :217-331
+        g1 = np.linalg.inv(I - r_mp @ C.Rpm)
+        T01 = C.Tmm @ g1
+        rT = r_mp @ C.Tpp
+        dg1 = b(g1) @ (dr_mp @ b(C.Rpm) + b(r_mp) @ dC.Rpm) @ b(g1)                      # :247
+        dT01 = dC.Tmm @ b(g1) + b(C.Tmm) @ dg1                                           # :248
+        dRmp = dC.Rmp + dT01 @ b(rT) + b(T01) @ (dr_mp @ b(C.Tpp) + b(r_mp) @ dC.Tpp)    # :250-253
+        dTmm = dT01 @ b(t_mm) + b(T01) @ dt_mm                                           # :256
+        x = _mvp(r_mp, C.J0p) + j0m
+        dJ0m = dC.J0m + _mvp(dT01, b(x)) + _mvp(b(T01), _mvp(dr_mp, b(C.J0p)) + _mvp(b(r_mp), dC.J0p) + dj0m)   # :265-267
+        J0m = C.J0m + _mvp(T01, x)
+        Rmp = C.Rmp + T01 @ rT
+        Tmm = T01 @ t_mm
+        g2 = np.linalg.inv(I - C.Rpm @ r_mp)
+        T21 = t_pp @ g2
+        Rt = C.Rpm @ t_mm
+        dg2 = b(g2) @ (b(C.Rpm) @ dr_mp + dC.Rpm @ b(r_mp)) @ b(g2)                      # :288
+        dT21 = dt_pp @ b(g2) + b(t_pp) @ dg2                                             # :289
+        dTpp = dT21 @ b(C.Tpp) + b(T21) @ dC.Tpp                                         # :292
+        dRpm = dr_pm + dT21 @ b(Rt) + b(T21) @ (dC.Rpm @ b(t_mm) + b(C.Rpm) @ dt_mm)     # :295-296
+        y = C.J0p + _mvp(C.Rpm, j0m)
+        dJ0p = dj0p + _mvp(dT21, b(y)) + _mvp(b(T21), dC.J0p + _mvp(dC.Rpm, b(j0m)) + _mvp(b(C.Rpm), dj0m))      # :301-306
+        J0p = j0p + _mvp(T21, y)
+        Tpp = T21 @ C.Tpp
+        Rpm = r_pm + T21 @ Rt
+        C.J0m, C.Rmp, C.Tmm, C.J0p, C.Tpp, C.Rpm = J0m, Rmp, Tmm, J0p, Tpp, Rpm
+        dC.J0m, dC.Rmp, dC.Tmm, dC.J0p, dC.Tpp, dC.Rpm = dJ0m, dRmp, dTmm, dJ0p, dTpp, dRpm
+    return C, dC
+
+
+# --------------------------------------------------------------------------
 # BRDF surfaces   src/CoreRT/Surfaces/rpv_surface.jl:51-97 (layer), :113-165 (RPV)
 # --------------------------------------------------------------------------
 def brdf_surface(model: Model, m: int, tau_sum_end):

@@ -1,0 +1,88 @@
+"""Oracle-only (CPU) tests of the tangent-linear doubling / interaction restatement
+(doubling_lin.jl:216-335, interaction_lin.jl:54-331) against central finite differences of
+the forward oracle -- the reference pins its own LinMode the same way
+(test/test_forward_lin.jl:167-244, analytic vs FD)."""
+import copy
+
+import numpy as np
+import pytest
+
+import vsmom_oracle as orc
+import vsmom_b200 as vb
+from helpers import to_oracle
+
+
+def _layer(nS=3, seed=0):
+    """A physically plausible homogeneous layer (elemental r, t, j) from the forward oracle."""
+    m = vb.synthetic_o2a_model(nSpec=nS, nstreams=3, polarization_type="Stokes_IQU", aerosol=True)
+    om = to_oracle(m)
+    ctl = orc.band_control(om, 0)
+    props = orc.construct_core_optical_properties(om, 0)
+    iz = int(np.argmax(ctl.ndoubl))
+    nd = int(ctl.ndoubl[iz])
+    p = props[iz]
+    dtau = p.tau / 2.0 ** nd
+    F0 = np.zeros((om.pol_n, nS)); F0[0] = 1
+    r, t, _, _, j0p, j0m = orc.elemental(om, 0, nd, dtau, p.varpi, p.Zpp, p.Zmp, ctl.tau_sum[:, iz], F0)
+    return om, nd, dtau, r, t, j0p, j0m
+
+
+def _rand_like(rng, x, P, scale):
+    return scale * rng.standard_normal((P,) + x.shape) * (np.abs(x).max() + 1e-30)
+
+
+def test_doubling_lin_matches_finite_differences():
+    om, nd, dtau, r, t, j0p, j0m = _layer()
+    nd = min(nd, 6)
+    rng = np.random.default_rng(5)
+    P = 2
+    dr, dt = _rand_like(rng, r, P, 0.3), _rand_like(rng, t, P, 1e-3)
+    djp, djm = _rand_like(rng, j0p, P, 0.3), _rand_like(rng, j0m, P, 0.3)
+    dtd = 0.2 * rng.standard_normal((P, dtau.size)) * dtau[None]
+    mu0 = om.quad.mu0
+    fwd, lin = orc.doubling_lin(om, nd, np.exp(-dtau / mu0), r, t, j0p, j0m, dr, dt, djp, djm, dtd)
+    ref = orc.doubling(om, nd, np.exp(-dtau / mu0), r, t, j0p, j0m)
+    for a, b in zip(fwd, ref):
+        assert np.max(np.abs(a - b)) <= 1e-14 * max(np.abs(b).max(), 1e-300)
+    h = 1e-6
+    for ip in range(P):
+        out = []
+        for sg in (+1, -1):
+            e = np.exp(-(dtau + sg * h * dtd[ip]) / mu0)
+            out.append(orc.doubling(om, nd, e, r + sg * h * dr[ip], t + sg * h * dt[ip], j0p + sg * h * djp[ip],
+                                    j0m + sg * h * djm[ip]))
+        for k, (up, dn) in enumerate(zip(*out)):
+            fd = (up - dn) / (2 * h)
+            scale = max(np.abs(fd).max(), 1e-300)
+            assert np.max(np.abs(lin[k][ip] - fd)) <= 2e-7 * scale, (ip, k)
+
+
+@pytest.mark.parametrize("itf", [0, 1, 2, 3])
+def test_interaction_lin_matches_finite_differences(itf):
+    om, nd, dtau, r, t, j0p, j0m = _layer(seed=1)
+    mu0 = om.quad.mu0
+    e = np.exp(-dtau / mu0)
+    a = orc.doubling(om, min(nd, 5), e, r, t, j0p, j0m)            # added layer (r-+, t++, r+-, t--, j+, j-)
+    A = (a[0], a[2], a[1], a[3], a[4], a[5])                       # interaction() order: r-+, r+-, t++, t--, j+, j-
+    B = orc.doubling(om, min(nd, 4), e, 0.7 * r, t, 0.5 * j0p, 0.8 * j0m)   # stands in for the composite
+    rng = np.random.default_rng(11 + itf)
+    P = 2
+    dA = [_rand_like(rng, x, P, 0.2 if k not in (2, 3) else 1e-3) for k, x in enumerate(A)]
+    C0 = orc.Composite(B[0].copy(), B[2].copy(), B[1].copy(), B[3].copy(), B[4].copy(), B[5].copy())
+    dC0 = orc.Composite(*[_rand_like(rng, x, P, 0.2) for x in (C0.Rmp, C0.Rpm, C0.Tpp, C0.Tmm, C0.J0p, C0.J0m)])
+    C1, dC1 = orc.interaction_lin(itf, copy.deepcopy(C0), copy.deepcopy(dC0), *A, *dA)
+    Cf = orc.interaction(itf, copy.deepcopy(C0), *A)
+    fields = ("Rmp", "Rpm", "Tpp", "Tmm", "J0p", "J0m")
+    for f in fields:
+        assert np.max(np.abs(getattr(C1, f) - getattr(Cf, f))) <= 1e-14 * max(np.abs(getattr(Cf, f)).max(), 1e-300), f
+    h = 1e-6
+    for ip in range(P):
+        res = []
+        for sg in (+1, -1):
+            Cp = orc.Composite(*[getattr(C0, f) + sg * h * getattr(dC0, f)[ip] for f in fields])
+            Ap = [x + sg * h * dx[ip] for x, dx in zip(A, dA)]
+            res.append(orc.interaction(itf, Cp, *Ap))
+        for f in fields:
+            fd = (getattr(res[0], f) - getattr(res[1], f)) / (2 * h)
+            scale = max(np.abs(fd).max(), 1e-300)
+            assert np.max(np.abs(getattr(dC1, f)[ip] - fd)) <= 2e-7 * scale, (itf, ip, f)
