@@ -275,7 +275,7 @@ def _dd(batch, n, dtype, seed=0):
     return A.to(dtype).cuda()
 
 
-@pytest.mark.parametrize("n,batch", [(4, 6), (15, 33), (45, 200), (112, 7), (200, 3), (45, 1)])
+@pytest.mark.parametrize("n,batch", [(4, 6), (15, 33), (45, 200), (112, 7), (200, 3), (45, 1), (45, 3001)])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_batch_inv_matches_lapack(ctx, n, batch, dtype):
     from vsmom_b200 import batched
@@ -290,7 +290,7 @@ def test_batch_inv_matches_lapack(ctx, n, batch, dtype):
     assert (info == 0).all()
 
 
-@pytest.mark.parametrize("m,k,nc,batch", [(4, 4, 4, 6), (45, 45, 45, 100), (45, 45, 1, 100), (112, 112, 112, 5),
+@pytest.mark.parametrize("m,k,nc,batch", [(4, 4, 4, 6), (45, 45, 45, 100), (45, 45, 45, 3001), (45, 45, 1, 100), (112, 112, 112, 5),
                                            (200, 200, 200, 2), (45, 45, 45, 1), (7, 13, 5, 9)])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_batched_mul_matches_matmul(ctx, m, k, nc, batch, dtype):

@@ -214,6 +214,17 @@ static int bmm_impl(vsm_ctx* ctx, T* C, const T* A, const T* B, int M, int K, in
     if (M <= 0 || K <= 0 || Nc <= 0 || batch < 0) return fail(ctx, VSM_ERR_INVALID_ARG, "batched_mul: bad dims");
     if (batch == 0) return VSM_OK;
     CK(cudaSetDevice(ctx->device));
+    if (sizeof(T) == 8 && M == kL0N && K == kL0N && Nc == kL0N) {          // the hot-path shape: tensor-core path
+        // (+2 KB: the fragment loads of the padded 48x48 tiles read up to 3 columns = 1.1 KB past the end of
+        //  an operand; harmless inside the arena of the fused kernels, but the last stage needs the room here)
+        const size_t smem = (size_t)4 * kL0LB * sizeof(double) + 2048;
+        CK(cudaFuncSetAttribute(k_bmm_f64_n45, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_bmm_f64_n45<<<std::min(batch, ctx->num_sms * 3), 128, smem, ctx->stream>>>((double*)C, (const double*)A,
+                                                                                    (const double*)B, batch);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return VSM_OK;
+    }
     const size_t sm = ((size_t)(M | 1) * K + (size_t)(K | 1) * Nc) * sizeof(T);
     const int stage = sm <= (size_t)ctx->max_smem_optin ? 1 : 0;
     const size_t smem = stage ? sm : 0;
@@ -243,6 +254,14 @@ static int binv_impl(vsm_ctx* ctx, T* X, T* A, int N, int batch, int* info) {
     if (N <= 0 || batch < 0) return fail(ctx, VSM_ERR_INVALID_ARG, "batch_inv: bad dims");
     if (batch == 0) return VSM_OK;
     CK(cudaSetDevice(ctx->device));
+    if (sizeof(T) == 8 && N == kL0N) {                                     // the hot-path shape: tensor-core path
+        const size_t smem = ((size_t)kL0LB + 13 * kL0N) * sizeof(double) + (kL0N + 4) * sizeof(int);
+        CK(cudaFuncSetAttribute(k_binv_f64_n45, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_binv_f64_n45<<<std::min(batch, ctx->num_sms * 3), 128, smem, ctx->stream>>>((double*)X, (const double*)A, batch, info);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return VSM_OK;
+    }
     const size_t vecb = (size_t)3 * N * sizeof(T) + (size_t)N * sizeof(int);
     const size_t full = (size_t)(N | 1) * N * sizeof(T) + vecb;
     const int stage = full <= (size_t)ctx->max_smem_optin ? 1 : 0;
