@@ -729,6 +729,99 @@ def lambertian_surface(model: Model, m: int, tau_sum_end):
 # (tests/test_oracle_lin.py), the way the reference pins its own LinMode
 # (analytic vs FD, test/test_forward_lin.jl:167-244).  Not yet used by a CUDA path.
 # --------------------------------------------------------------------------
+def elemental_lin(model: Model, m: int, ndoubl: int, dtau, varpi, Zpp, Zmp, tau_sum, F0,
+                  dtau_dot, varpi_dot, Zpp_dot, Zmp_dot, tausum_dot):
+    """Per-parameter derivatives of the elemental layer: the fused chain rule of the LinMode
+    elemental! (elemental_lin.jl:77-206 with lin_added_layer_all_params!,
+    lin_added_layer_all_params.jl:1-136): d/dp = (d/d dtau) dtau_dot + (d/d varpi) varpi_dot +
+    (d/dZ) Z_dot, and d(exp(-tau_sum/mu0))/dp for the solar sources.
+    dtau_dot, varpi_dot, tausum_dot: (P,nS);  Zpp_dot, Zmp_dot: (P,nS,N,N) or (P,N,N).
+    Returns (dr_mp, dt_pp, dr_pm, dt_mm, dj0p, dj0m), each with a leading P axis, with the same
+    D-matrix conventions as elemental()."""
+    FT = model.FT
+    q = model.quad
+    pol_n = model.pol_n
+    mu = q.qp_muN.astype(FT)
+    eps = np.finfo(FT).eps
+    wct02 = FT(0.5 if m == 0 else 0.25)
+    wct = (q.wt_muN / 2 if m == 0 else q.wt_muN / 4).astype(FT)
+    nS, N, P = dtau.shape[0], mu.size, dtau_dot.shape[0]
+    if Zpp.ndim == 2:
+        Zpp = np.broadcast_to(Zpp, (nS, N, N)); Zmp = np.broadcast_to(Zmp, (nS, N, N))
+    if Zpp_dot.ndim == 3:
+        Zpp_dot = np.broadcast_to(Zpp_dot[:, None], (P, nS, N, N)); Zmp_dot = np.broadcast_to(Zmp_dot[:, None], (P, nS, N, N))
+    mui, muj = mu[None, :, None], mu[None, None, :]
+    w_j = wct[None, None, :]
+    w, d = varpi[:, None, None], dtau[:, None, None]
+    wd, dd_ = varpi_dot[:, :, None, None], dtau_dot[:, :, None, None]
+    c = (1 / mui) + (1 / muj)
+    g1 = (muj / (mui + muj)) * w_j
+    E1, dE1 = -np.expm1(-d * c), c * np.exp(-d * c)
+    # r-+ = w Zmp g1 E1(d)
+    dr = (wd * Zmp[None] + w[None] * Zmp_dot) * (g1 * E1)[None] + (w * Zmp * g1 * dE1)[None] * dd_
+    with np.errstate(divide='ignore', invalid='ignore'):
+        g2 = (muj / (mui - muj)) * w_j
+        E2 = expdiff_neg(d / mui, d / muj)
+        dE2 = -np.exp(-d / mui) / mui + np.exp(-d / muj) / muj
+        dt_off = (wd * Zpp[None] + w[None] * Zpp_dot) * (g2 * E2)[None] + (w * Zpp * g2 * dE2)[None] * dd_
+    eye = np.eye(N, dtype=bool)[None]
+    same = (mui == muj)
+    wi = wct[None, :, None]
+    ei, ej = np.exp(-d / mui), np.exp(-d / muj)
+    # exp(-d/mu_i) (1 + w Zpp (d/mu_i) wct_i)
+    dt_sd = (ei * (d / mui) * wi)[None] * (wd * Zpp[None] + w[None] * Zpp_dot) \
+        + (-(1 / mui) * ei * (1 + w * Zpp * (d / mui) * wi) + ei * w * Zpp * wi / mui)[None] * dd_
+    # exp(-d/mu_j) w Zpp (d/mu_i) w_j
+    dt_so = (ej * (d / mui) * w_j)[None] * (wd * Zpp[None] + w[None] * Zpp_dot) \
+        + (-(1 / muj) * ej * w * Zpp * (d / mui) * w_j + ej * w * Zpp * w_j / mui)[None] * dd_
+    dt = np.where(same[None], np.where(eye[None], dt_sd, dt_so), dt_off)
+    active = (wct > eps)[None, None, None, :]
+    dr = np.where(active, dr, 0).astype(FT)
+    dt_beer = np.where(eye[None], (-ei / mui)[None] * dd_, 0)
+    dt = np.where(active, dt, dt_beer).astype(FT)
+    # solar sources
+    i_start = pol_n * q.imu0
+    i_end = i_start + pol_n
+    F = F0.astype(FT)
+    ZppI = np.einsum('nik,kn->ni', Zpp[:, :, i_start:i_end], F)
+    ZmpI = np.einsum('nik,kn->ni', Zmp[:, :, i_start:i_end], F)
+    dZppI = np.einsum('pnik,kn->pni', Zpp_dot[:, :, :, i_start:i_end], F)
+    dZmpI = np.einsum('pnik,kn->pni', Zmp_dot[:, :, :, i_start:i_end], F)
+    mu_i, mu_s = mu[None, :], mu[i_start]
+    dd, ww = dtau[:, None], varpi[:, None]
+    ddp, wwp = dtau_dot[:, :, None], varpi_dot[:, :, None]
+    insun = np.zeros(N, bool); insun[i_start:i_end] = True
+    e_i = np.exp(-dd / mu_i)
+    f_in, df_in = (dd / mu_i) * e_i, e_i / mu_i - (dd / mu_i) * e_i / mu_i
+    with np.errstate(divide='ignore', invalid='ignore'):
+        gs2 = mu_s / (mu_i - mu_s)
+        f_out = gs2 * expdiff_neg(dd / mu_i, dd / mu_s)
+        df_out = gs2 * (-np.exp(-dd / mu_i) / mu_i + np.exp(-dd / mu_s) / mu_s)
+    fp = np.where(insun[None, :], f_in, f_out)
+    dfp = np.where(insun[None, :], df_in, df_out)
+    cs = (1 / mu_i) + (1 / mu_s)
+    fm = (mu_s / (mu_i + mu_s)) * (-np.expm1(-dd * cs))
+    dfm = (mu_s / (mu_i + mu_s)) * cs * np.exp(-dd * cs)
+    att = np.exp(-tau_sum / mu_s)[:, None]
+    datt = -(att / mu_s)[None] * tausum_dot[:, :, None]
+    jp0 = wct02 * ww * ZppI * fp
+    jm0 = wct02 * ww * ZmpI * fm
+    djp0 = wct02 * ((wwp * ZppI[None] + ww[None] * dZppI) * fp[None] + (ww * ZppI * dfp)[None] * ddp)
+    djm0 = wct02 * ((wwp * ZmpI[None] + ww[None] * dZmpI) * fm[None] + (ww * ZmpI * dfm)[None] * ddp)
+    dj0p = (djp0 * att[None] + jp0[None] * datt).astype(FT)
+    dj0m = (djm0 * att[None] + jm0[None] * datt).astype(FT)
+    Dd = _D_diag(pol_n, q.Nquad, FT)
+    if ndoubl >= 1:
+        dj0m = Dd[None, None, :] * dj0m
+    dr_pm = dt_mm = None
+    if ndoubl < 1:
+        sgn = (Dd[:, None] * Dd[None, :])[None, None]
+        dr_pm, dt_mm = sgn * dr, sgn * dt
+    else:
+        dr = Dd[None, None, :, None] * dr
+    return dr, dt, dr_pm, dt_mm, dj0p, dj0m
+
+
 def _mvp(A, x):
     """A (..., N, N) times x (..., N), batched with broadcasting over leading axes."""
     return np.einsum('...ij,...j->...i', A, x)

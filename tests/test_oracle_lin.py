@@ -86,3 +86,39 @@ def test_interaction_lin_matches_finite_differences(itf):
             fd = (getattr(res[0], f) - getattr(res[1], f)) / (2 * h)
             scale = max(np.abs(fd).max(), 1e-300)
             assert np.max(np.abs(getattr(dC1, f)[ip] - fd)) <= 2e-7 * scale, (itf, ip, f)
+
+
+@pytest.mark.parametrize("nd_mode", ["doubled", "nd0"])
+def test_elemental_lin_matches_finite_differences(nd_mode):
+    m = vb.synthetic_o2a_model(nSpec=3, nstreams=3, polarization_type="Stokes_IQU", aerosol=True)
+    om = to_oracle(m)
+    ctl = orc.band_control(om, 1)
+    props = orc.construct_core_optical_properties(om, 1)
+    iz = int(np.argmax(ctl.ndoubl))
+    nd = int(ctl.ndoubl[iz]) if nd_mode == "doubled" else 0
+    p = props[iz]
+    nS = 3
+    dtau = p.tau / 2.0 ** max(nd, 4)
+    F0 = np.zeros((om.pol_n, nS)); F0[0] = 1; F0[1] = 0.1
+    tsum = ctl.tau_sum[:, iz] + 0.05
+    rng = np.random.default_rng(3)
+    P = 2
+    N = om.quad.qp_muN.size
+    Zpp = np.broadcast_to(p.Zpp, (nS, N, N)).copy(); Zmp = np.broadcast_to(p.Zmp, (nS, N, N)).copy()
+    dd = 0.3 * rng.standard_normal((P, nS)) * dtau[None]
+    dw = 0.3 * rng.standard_normal((P, nS)) * p.varpi[None]
+    dZp = 0.3 * rng.standard_normal((P, nS, N, N)) * np.abs(Zpp).max()
+    dZm = 0.3 * rng.standard_normal((P, nS, N, N)) * np.abs(Zmp).max()
+    dts = 0.3 * rng.standard_normal((P, nS)) * tsum[None]
+    lin = orc.elemental_lin(om, 1, nd, dtau, p.varpi, Zpp, Zmp, tsum, F0, dd, dw, dZp, dZm, dts)
+    h = 1e-6
+    for ip in range(P):
+        res = [orc.elemental(om, 1, nd, dtau + sg * h * dd[ip], p.varpi + sg * h * dw[ip], Zpp + sg * h * dZp[ip],
+                             Zmp + sg * h * dZm[ip], tsum + sg * h * dts[ip], F0) for sg in (+1, -1)]
+        for k, (up, dn) in enumerate(zip(*res)):
+            if up is None:
+                assert lin[k] is None
+                continue
+            fd = (up - dn) / (2 * h)
+            scale = max(np.abs(fd).max(), 1e-300)
+            assert np.max(np.abs(lin[k][ip] - fd)) <= 5e-7 * scale, (nd_mode, ip, k)
