@@ -1126,6 +1126,121 @@ def rt_run(model: Model, sel=slice(None), return_streams: bool = False, prep: Op
     return out
 
 
+# --------------------------------------------------------------------------
+# Linearized column (config 4 subset): rt_run(model, lin_model, ...) of rt_run_lin.jl:102-326
+# for parameters that act through the layer optical depths and the Lambertian albedo.
+# --------------------------------------------------------------------------
+def core_props_lin(model: Model, m: int, dtau_rayl, dtau_abs, dtau_aer, ztab=None):
+    """Per-layer derivatives (tau_dot, varpi_dot, Zpp_dot, Zmp_dot) of the mixed layer properties
+    (constructCoreOpticalProperties of LinMode, compEffectiveLayerProperties_lin.jl) for P
+    parameters given as derivatives of the inputs: dtau_rayl, dtau_abs (P,nSpec,Nz), dtau_aer
+    (P,nAer,Nz).  With S = sum_c tau_c varpi_c:  varpi = S/tau,  Z = sum_c tau_c varpi_c Z_c / S."""
+    FT = model.FT
+    (Zpp_r, Zmp_r), aerZ = ztab if ztab is not None else z_tables(model, m)
+    P = dtau_abs.shape[0]
+    out = []
+    for iz in range(model.Nz):
+        comps = [(model.tau_rayl[:, iz].astype(FT), FT(model.varpi_cabannes), Zpp_r, Zmp_r, dtau_rayl[:, :, iz])]
+        for ia, a in enumerate(model.aerosols):
+            k = FT(1 - a.ft * a.omega)
+            comps.append((np.full(model.nSpec, k * model.tau_aer[ia, iz], FT), FT((1 - a.ft) * a.omega / (1 - a.ft * a.omega)),
+                          aerZ[ia][0], aerZ[ia][1], np.broadcast_to((k * dtau_aer[:, ia, iz])[:, None], (P, model.nSpec))))
+        tau = sum(c[0] for c in comps) + model.tau_abs[:, iz].astype(FT)
+        S = sum(c[0] * c[1] for c in comps)
+        dtau = sum(c[4] for c in comps) + dtau_abs[:, :, iz]
+        dS = sum(c[4] * c[1] for c in comps)
+        safe_tau = np.where(tau > 0, tau, 1)
+        safe_S = np.where(S > 0, S, 1)
+        varpi = S / safe_tau
+        dvarpi = (dS - varpi[None] * dtau) / safe_tau[None]
+        Zpp = sum((c[0] * c[1])[:, None, None] * c[2][None] for c in comps) / safe_S[:, None, None]
+        Zmp = sum((c[0] * c[1])[:, None, None] * c[3][None] for c in comps) / safe_S[:, None, None]
+        dZpp = (sum((c[4] * c[1])[:, :, None, None] * c[2][None, None] for c in comps) - dS[:, :, None, None] * Zpp[None]) / safe_S[None, :, None, None]
+        dZmp = (sum((c[4] * c[1])[:, :, None, None] * c[3][None, None] for c in comps) - dS[:, :, None, None] * Zmp[None]) / safe_S[None, :, None, None]
+        out.append((dtau, dvarpi, dZpp, dZmp))
+    return out
+
+
+def rt_run_lin(model: Model, dtau_rayl, dtau_abs, dtau_aer, dalbedo):
+    """Forward result and Jacobian dR_SFI/dp, dT_SFI/dp (P,nVZA,pol_n,nSpec) for P parameters that
+    perturb tau_rayl, tau_abs (P,nSpec,Nz), tau_aer (P,nAer,Nz) and the Lambertian albedo (P,).
+    The layer loop of rt_run_lin.jl:102-326 with rt_kernel! of rt_kernel_lin.jl:50-180; control
+    flow (ndoubl, interfaces) is that of the unperturbed band, as in the reference."""
+    FT = model.FT
+    q = model.quad
+    pol_n = model.pol_n
+    nS, nV, N = model.nSpec, len(model.vza), q.qp_muN.size
+    P = dtau_abs.shape[0]
+    R = np.zeros((nV, pol_n, nS), FT); T = np.zeros_like(R)
+    dR = np.zeros((P, nV, pol_n, nS), FT); dT = np.zeros_like(dR)
+    F0 = model.F0
+    if F0 is None:
+        F0 = np.zeros((pol_n, nS), FT); F0[0, :] = 1
+    for m in range(model.m_max + 1):
+        weight = FT(0.5 / math.pi) if m == 0 else FT(1.0 / math.pi)
+        ztab = z_tables(model, m)
+        ctl = band_control(model, m, ztab)
+        props = construct_core_optical_properties(model, m, ztab=ztab)
+        lprops = core_props_lin(model, m, dtau_rayl, dtau_abs, dtau_aer, ztab)
+        dtausum = np.zeros((P, nS), FT)
+        C = dC = None
+        for iz in range(model.Nz):
+            pr = props[iz]
+            dtl, dvl, dZp, dZm = lprops[iz]
+            if ctl.scatter[iz]:
+                nd = ctl.ndoubl[iz]
+                sc = FT(2 ** nd)
+                dtau = (pr.tau / sc).astype(FT)
+                expk = np.exp(-dtau / FT(q.mu0))
+                Zpp = np.broadcast_to(pr.Zpp, (nS, N, N)); Zmp = np.broadcast_to(pr.Zmp, (nS, N, N))
+                a = elemental(model, m, nd, dtau, pr.varpi, Zpp, Zmp, ctl.tau_sum[:, iz], F0)
+                da = elemental_lin(model, m, nd, dtau, pr.varpi, Zpp, Zmp, ctl.tau_sum[:, iz], F0,
+                                   dtl / sc, dvl, dZp, dZm, dtausum)
+                if nd > 0:
+                    a, da = doubling_lin(model, nd, expk, a[0], a[1], a[4], a[5], da[0], da[1], da[4], da[5], dtl / sc)
+                r, t, r_pm, t_mm, j0p, j0m = a
+                dr, dt, dr_pm, dt_mm, dj0p, dj0m = da
+            else:       # zero_added_noscat! and its derivative: t = diag(exp(-tau/mu))
+                tb = np.exp(-pr.tau[:, None] / q.qp_muN.astype(FT)[None, :])
+                idx = np.arange(N)
+                r = np.zeros((nS, N, N), FT); r_pm = r.copy(); t = r.copy(); t[:, idx, idx] = tb; t_mm = t.copy()
+                j0p = np.zeros((nS, N), FT); j0m = j0p.copy()
+                dr = np.zeros((P, nS, N, N), FT); dr_pm = dr.copy(); dt = dr.copy()
+                dt[:, :, idx, idx] = -(tb / q.qp_muN.astype(FT)[None, :])[None] * dtl[:, :, None]
+                dt_mm = dt.copy()
+                dj0p = np.zeros((P, nS, N), FT); dj0m = dj0p.copy()
+            if iz == 0:
+                C = Composite(r.copy(), r_pm.copy(), t.copy(), t_mm.copy(), j0p.copy(), j0m.copy())
+                dC = Composite(dr.copy(), dr_pm.copy(), dt.copy(), dt_mm.copy(), dj0p.copy(), dj0m.copy())
+            else:
+                C, dC = interaction_lin(ctl.interface[iz], C, dC, r, r_pm, t, t_mm, j0p, j0m, dr, dr_pm, dt, dt_mm, dj0p, dj0m)
+            dtausum = dtausum + dtl
+        # Lambertian surface and its derivative (lambertian_surface_lin.jl)
+        r_s, rpm_s, t_s, tmm_s, j0p_s, j0m_s = lambertian_surface(model, m, ctl.tau_sum[:, -1])
+        dr_s = np.zeros((P, nS, N, N), FT); dj0p_s = np.zeros((P, nS, N), FT); dj0m_s = np.zeros((P, nS, N), FT)
+        if m == 0:
+            att_d = -(1 / FT(q.mu0)) * dtausum                                  # d att / att
+            dj0p_s = j0p_s[None] * att_d[:, :, None]
+            dj0m_s = j0m_s[None] * att_d[:, :, None]
+            if model.albedo != 0:
+                rel = (np.asarray(dalbedo, FT) / FT(model.albedo))[:, None, None]
+                dr_s = dr_s + r_s[None] * rel[:, :, :, None]
+                dj0m_s = dj0m_s + j0m_s[None] * rel
+        z4 = np.zeros((P, nS, N, N), FT)
+        C, dC = interaction_lin(ctl.interface[-1], C, dC, r_s, rpm_s, t_s, tmm_s, j0p_s, j0m_s,
+                                dr_s, z4, z4.copy(), z4.copy(), dj0p_s, dj0m_s)
+        for i in range(nV):      # postprocessing_vza! (lin: postprocessing_vza_lin.jl:1-48)
+            imu = nearest_point(q.qp_mu, FT(cosd(model.vza[i])))
+            ist = imu * pol_n
+            c, sn = cosd(m * model.vaz[i]), sind(m * model.vaz[i])
+            wv = (weight * np.array([c, c, sn, sn][:pol_n])).astype(FT)
+            R[i] += wv[:, None] * C.J0m[:, ist:ist + pol_n].T
+            T[i] += wv[:, None] * C.J0p[:, ist:ist + pol_n].T
+            dR[:, i] += wv[None, :, None] * np.swapaxes(dC.J0m[:, :, ist:ist + pol_n], 1, 2)
+            dT[:, i] += wv[None, :, None] * np.swapaxes(dC.J0p[:, :, ist:ist + pol_n], 1, 2)
+    return dict(R_SFI=R, T_SFI=T, dR_SFI=dR, dT_SFI=dT)
+
+
 def rt_run_threaded(model: Model, idx: np.ndarray, threads: int, chunk: int = 8,
                     prep: Optional[Prepared] = None):
     """CPU baseline driver: the reference threads its per-slice BLAS/LAPACK calls

@@ -122,3 +122,39 @@ def test_elemental_lin_matches_finite_differences(nd_mode):
             fd = (up - dn) / (2 * h)
             scale = max(np.abs(fd).max(), 1e-300)
             assert np.max(np.abs(lin[k][ip] - fd)) <= 5e-7 * scale, (nd_mode, ip, k)
+
+
+def test_rt_run_lin_jacobian_matches_finite_differences_of_rt_run():
+    """Column-level Jacobian (gas column, aerosol optical depth, Rayleigh scaling, Lambertian albedo)
+    against central differences of the forward oracle; tolerance far inside the reference's own
+    analytic-vs-FD bounds (1 % - 20 %, test/test_forward_lin.jl:167-244)."""
+    m = vb.synthetic_o2a_model(nSpec=4, nstreams=3, polarization_type="Stokes_IQU", aerosol=True, albedo=0.2)
+    m.tau_abs = m.tau_abs * np.logspace(-4.0, -1.5, 4)[:, None]
+    om = to_oracle(m)
+    nS, Nz, nAer = om.nSpec, om.Nz, len(om.aerosols)
+    P = 4
+    z3 = np.zeros((P, nS, Nz)); za = np.zeros((P, nAer, Nz))
+    d_rayl, d_abs, d_aer, d_alb = z3.copy(), z3.copy(), za.copy(), np.zeros(P)
+    d_abs[0] = om.tau_abs            # p0: gas column scaling
+    d_aer[1] = om.tau_aer            # p1: aerosol optical depth scaling
+    d_rayl[2] = om.tau_rayl          # p2: Rayleigh scaling
+    d_alb[3] = 1.0                   # p3: albedo
+    lin = orc.rt_run_lin(om, d_rayl, d_abs, d_aer, d_alb)
+    fwd = orc.rt_run(om)
+    for k in ("R_SFI", "T_SFI"):
+        assert np.max(np.abs(lin[k] - fwd[k])) <= 1e-13 * np.abs(fwd[k]).max()
+    h = 1e-5
+    for ip in range(P):
+        res = []
+        for sg in (+1, -1):
+            mp = copy.deepcopy(om)
+            mp.tau_abs = om.tau_abs + sg * h * d_abs[ip]
+            mp.tau_aer = om.tau_aer + sg * h * d_aer[ip]
+            mp.tau_rayl = om.tau_rayl + sg * h * d_rayl[ip]
+            mp.albedo = om.albedo + sg * h * d_alb[ip]
+            res.append(orc.rt_run(mp))
+        for k in ("R_SFI", "T_SFI"):
+            fd = (res[0][k] - res[1][k]) / (2 * h)
+            scale = max(np.abs(fd).max(), 1e-300)
+            err = np.max(np.abs(lin["d" + k][ip] - fd)) / scale
+            assert err <= 1e-6, (ip, k, err)
