@@ -88,3 +88,17 @@ def test_rpv_fourier_moments_match_oracle_restatement():
     lam = vb.rpv_surface_rho(m.quad_points, m.pol_n, 2, rho0=0.3, rho_c=1.0, k=1.0, theta_hs=0.0)
     assert np.allclose(lam[0, ::3, ::3], 0.6, atol=1e-13) and np.abs(lam[1:]).max() < 1e-13
     assert np.abs(lam[0, 1::3]).max() == 0 and np.abs(lam[0, :, 1::3]).max() == 0
+
+
+def test_prepare_rejects_wrong_surface_rho_shape():
+    from vsmom_b200 import rt_run as rr
+    m = vb.synthetic_o2a_model(nSpec=2, nstreams=3, polarization_type="Stokes_I", aerosol=False)
+    N = m.quad_points.qp_muN.size
+    m.surface_rho = np.zeros((m.m_max + 1, N, N + 1))
+    with pytest.raises(ValueError):
+        rr.prepare(m, "cpu")
+    m.surface_rho = np.zeros((m.m_max + 1, N, N))
+    p = rr.prepare(m, "cpu")             # host-side preparation needs no GPU
+    assert p.surf_rho is not None and tuple(p.surf_rho.shape) == (m.m_max + 1, N, N)
+    m.surface_rho = None
+    assert rr.prepare(m, "cpu").surf_rho is None
