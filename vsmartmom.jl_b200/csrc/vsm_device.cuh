@@ -250,11 +250,15 @@ __device__ __forceinline__ void cta_inverse(int n, T* __restrict__ M, int ld,
 
 // ==========================================================================
 // Ops policies.  The fused kernels are written against an Ops object providing
-//   mm<KSIGN>(A, B, epi), mv<KSIGN>(A, x, epi), mv2(A, x1, x2, epi1, epi2),
-//   inverse(M, rebuild)
-// OpsGeneric: run-time N, generic (shared-or-global) pointers, any size.
-// OpsFast   : compile-time N (NN), exact TMxTM tiling with one register tile per
-//             thread, everything in shared memory.
+//   mm<KSIGN>(A, B, epi)                       epi(i, j, (A B)_ij)
+//   mmv<NV>(A, B, epi, x1, x2, e1, e2)         ... plus y_v = A x_v as a by-product
+//   mv<KSIGN>(A, x, epi), mv2(A, x1, x2, e1, e2)
+//   inverse(M, rebuild)                        in place; rebuild() re-creates M for a pivoted retry
+//   inv_one_minus_v<NV>(P, Q, X, S, x1, x2, e1, e2)    X = (I - P Q)^-1 (+ y_v = P x_v)
+// OpsGeneric: run-time N, generic (shared-or-global) pointers, any size, SIMT.
+// OpsFast   : compile-time N (NN), everything in shared memory; fp64: tensor-core (DMMA) products
+//             and blocked Gauss-Jordan, adaptive Neumann inverse; fp32: one TMxTM register tile per
+//             thread (SIMT) and the rank-1 register-resident Gauss-Jordan.
 // ==========================================================================
 template <typename T, int TM>
 struct OpsGeneric {
