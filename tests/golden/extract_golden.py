@@ -10,6 +10,8 @@ Sources (numeric tables only; no reference code is copied):
   test/benchmarks/6SV1_R_trues.jl                      6SV1 scalar Rayleigh reflectances (6 cases)
   test/vlidort_baseline/reference_data/siewert2000_IIA_greek.jl   Siewert (2000) problem IIA Greek constants
   test/vlidort_baseline/reference_data/siewert2000_IIA_truth.jl   VLIDORT 2.8.3 tables 2-9
+  test/benchmarks/natraj_cds/CDS/{I,Q,U}_{UP,DN}_TAU_*   Natraj et al. (2009) improved Coulson-Dave-Sekera tables
+                                                        (a subset -> tests/golden/natraj_cds_subset.json)
 """
 import json
 import os
@@ -48,7 +50,51 @@ def nested_brackets(text: str):
     return json.loads(s)
 
 
+CDS_TAUS = ["0.1", "0.5", "1"]
+CDS_ALBEDOS = [0.0, 0.25, 0.8]
+CDS_MU0S = [0.2, 0.6, 1.0]
+
+
+def parse_cds(path):
+    """{(albedo, mu0, mu): [7 azimuth values]} from one CDS table file (format: 00README)."""
+    tab, alb = {}, None
+    for ln in open(path):
+        mt = re.match(r"\s*albedo\s*=\s*(" + _num + ")", ln)
+        if mt:
+            alb = float(mt.group(1))
+            continue
+        parts = ln.split()
+        if len(parts) == 9 and alb is not None:
+            try:
+                v = [float(x) for x in parts]
+            except ValueError:
+                continue
+            tab[(alb, v[0], v[1])] = v[2:]
+    return tab
+
+
+def extract_cds():
+    """Subset of the CDS tables used by test/benchmarks/benchmark_natraj_cds.jl: 3 optical depths x 3 albedos
+    x 3 solar cosines, all 16 mu x 7 phi, I/Q/U, upwelling (TOA) and downwelling (BOA)."""
+    d = os.path.join(REF, "test/benchmarks/natraj_cds/CDS")
+    mus = [0.02, 0.06, 0.1, 0.16, 0.2, 0.28, 0.32, 0.4, 0.52, 0.64, 0.72, 0.84, 0.92, 0.96, 0.98, 1.0]
+    out = {"tau": [float(t) for t in CDS_TAUS], "albedo": CDS_ALBEDOS, "mu0": CDS_MU0S, "mu": mus,
+           "phi": [0.0, 30.0, 60.0, 90.0, 120.0, 150.0, 180.0], "nstreams": 11, "depol": 0.0, "tables": {}}
+    for st in "IQU":
+        for di in ("UP", "DN"):
+            arr = []
+            for t in CDS_TAUS:
+                tab = parse_cds(os.path.join(d, f"{st}_{di}_TAU_{t}"))
+                arr.append([[[tab[(a, m0, mu)] for mu in mus] for m0 in CDS_MU0S] for a in CDS_ALBEDOS])
+            out["tables"][f"{st}_{di}"] = arr          # [tau][albedo][mu0][mu][phi]
+    path = os.path.join(os.path.dirname(OUT), "natraj_cds_subset.json")
+    with open(path, "w") as f:
+        json.dump(out, f)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def main():
+    extract_cds()
     out = {}
     t = open(os.path.join(REF, "test/benchmarks/natraj_trues.jl")).read()
     out["natraj"] = {

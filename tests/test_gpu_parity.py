@@ -196,6 +196,18 @@ def test_6sv1_golden_on_gpu(ctx):
     assert worst < d["tol"]
 
 
+def test_natraj_cds_tables_on_gpu(ctx):
+    # one (albedo, mu0) slice of the CDS subset straight against the published tables and against the oracle:
+    # N = 112, generic kernels, reflecting surface, upwelling and downwelling
+    from helpers import CDS_TOL, cds_errors, cds_golden, cds_model
+    d = cds_golden()
+    m = cds_model(d, d["albedo"][1], d["mu0"][1])
+    out = run_gpu(m, ctx)
+    for st, (ae, re_) in cds_errors(d, out, 1, 1).items():
+        assert ae <= CDS_TOL["abs"] and re_ <= CDS_TOL[st], (st, ae, re_)
+    assert_close(out, orc.rt_run(to_oracle(m)), F64_TOL)
+
+
 def test_siewert_golden_on_gpu(ctx):
     # aerosol-only slab with supplied Greek coefficients: Rayleigh weight all-zero branch (types.jl:1279)
     m = siewert_model(90.0)

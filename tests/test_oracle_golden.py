@@ -92,3 +92,15 @@ def test_float32_oracle_close_to_float64():
     r64 = orc.rt_run(to_oracle(m64))["R_SFI"]
     r32 = orc.rt_run(to_oracle(m32))["R_SFI"]
     assert np.max(np.abs(r32[:, 0] - r64[:, 0]) / np.abs(r64[:, 0])) < 1e-2
+
+
+@pytest.mark.parametrize("ia", range(3))
+@pytest.mark.parametrize("i0", range(3))
+def test_natraj_cds_tables_up_and_down(ia, i0):
+    # test/benchmarks/benchmark_natraj_cds.jl against test/benchmarks/natraj_cds/CDS: I/Q/U, TOA upwelling and BOA
+    # downwelling, Lambertian albedo 0 / 0.25 / 0.8, mu0 0.2 / 0.6 / 1, tau 0.1 / 0.5 / 1, 16 mu x 7 phi each
+    from helpers import CDS_TOL, cds_errors, cds_golden, cds_model
+    d = cds_golden()
+    out = orc.rt_run(to_oracle(cds_model(d, d["albedo"][ia], d["mu0"][i0])))
+    for st, (ae, re_) in cds_errors(d, out, ia, i0).items():
+        assert ae <= CDS_TOL["abs"] and re_ <= CDS_TOL[st], (st, ae, re_)
