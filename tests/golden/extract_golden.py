@@ -10,6 +10,8 @@ Sources (numeric tables only; no reference code is copied):
   test/benchmarks/6SV1_R_trues.jl                      6SV1 scalar Rayleigh reflectances (6 cases)
   test/vlidort_baseline/reference_data/siewert2000_IIA_greek.jl   Siewert (2000) problem IIA Greek constants
   test/vlidort_baseline/reference_data/siewert2000_IIA_truth.jl   VLIDORT 2.8.3 tables 2-9
+  test/vlidort_baseline/reference_data/solar_tester_{atmosphere,truth}.jl   VLIDORT 2.8.3 solar_tester (23 layers,
+                                                        Rayleigh + gas + HG aerosol), task 1, TOA up / BOA down
   test/benchmarks/natraj_cds/CDS/{I,Q,U}_{UP,DN}_TAU_*   Natraj et al. (2009) improved Coulson-Dave-Sekera tables
                                                         (a subset -> tests/golden/natraj_cds_subset.json)
 """
@@ -93,9 +95,33 @@ def extract_cds():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def extract_solar_tester():
+    """VLIDORT solar_tester scalar case as used by test/vlidort_baseline/cases/case_B_solar_tester.jl: the
+    23-layer atmosphere and the task-1 (plane-parallel, no delta-M) Stokes-I at TOA (upwelling) and BOA
+    (downwelling) for all 36 geometries."""
+    d = os.path.join(REF, "test/vlidort_baseline/reference_data")
+    ta = open(os.path.join(d, "solar_tester_atmosphere.jl")).read()
+    tt = open(os.path.join(d, "solar_tester_truth.jl")).read()
+    vals = {}
+    for mt in re.finditer(r"^\s*(" + _num + r"),?\s*#\s*geom=(\d+)\s+level=(\d+)\s+dir=(\d+)\s+task=(\d+)", tt, re.M):
+        v, g, lv, di, tk = float(mt.group(1)), *(int(mt.group(k)) for k in range(2, 6))
+        vals[(g, lv, di, tk)] = v
+    levels = julia_vector(tt, "SOLAR_TESTER_TAU_LEVELS")
+    return {
+        "height_km": julia_vector(ta, "SOLAR_TESTER_HEIGHT_KM"), "molext": julia_vector(ta, "SOLAR_TESTER_MOLEXT"),
+        "molomg": julia_vector(ta, "SOLAR_TESTER_MOLOMG"),
+        "sza": julia_vector(tt, "SOLAR_TESTER_SZA_DEG"), "vza": julia_vector(tt, "SOLAR_TESTER_VZA_DEG"),
+        "raz": julia_vector(tt, "SOLAR_TESTER_RAZ_DEG"), "albedo": 0.05, "depol": 0.01072, "nstreams": 8,
+        "aerosol": {"g": 0.8, "omega": 0.95, "tau_total": 0.5, "nmoments": 15, "layers": 6},   # case_B_solar_tester.jl:19-22,44-54
+        "toa_up": [vals[(g, 1, 1, 1)] for g in range(1, 37)],               # geom = (isza*3 + ivza)*3 + iraz
+        "boa_dn": [vals[(g, len(levels), 2, 1)] for g in range(1, 37)],
+        "rtol": 1e-3,                                                       # case_B_solar_tester.jl:166-170
+    }
+
+
 def main():
     extract_cds()
-    out = {}
+    out = {"solar_tester": extract_solar_tester()}
     t = open(os.path.join(REF, "test/benchmarks/natraj_trues.jl")).read()
     out["natraj"] = {
         "mu": [0.02, 0.06, 0.10, 0.16, 0.20, 0.28, 0.32, 0.40, 0.52, 0.64, 0.72,

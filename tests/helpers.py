@@ -95,3 +95,35 @@ def cds_errors(d, out, ia, i0):
 # measured over the whole subset: abs <= 9.2e-5; rel I 3.7e-4, Q 3.3e-3, U 1.8e-4 (the reference's own Natraj
 # limits at tau = 0.5, mu0 = 0.2 are 5e-4 / 2.5e-3 / 5e-4, test/test_CoreRT.jl:153-155)
 CDS_TOL = {"abs": 1.5e-4, "I": 6e-4, "Q": 5e-3, "U": 6e-4}
+
+
+def solar_tester_model(st, sza, raz):
+    """VLIDORT 2.8.3 solar_tester scene as test/vlidort_baseline/cases/case_B_solar_tester.jl builds it: 23 layers
+    (tau_rayl = molomg*molext, tau_abs = (1-molomg)*molext), HG aerosol g = 0.8, omega = 0.95, total tau 0.5 spread
+    over the bottom 6 layers by geometric thickness, 16 phase moments, Stokes_I, 8 Gauss streams, Lambertian 0.05,
+    two identical spectral points."""
+    a = st["aerosol"]
+    L = a["nmoments"]
+    beta = np.array([(2 * l + 1) * a["g"] ** l for l in range(L + 1)])
+    z = np.zeros(L + 1)
+    aer = vb.AerosolOptics(vb.GreekCoefs(z.copy(), beta, z.copy(), z.copy(), z.copy(), z.copy()), a["omega"], 0.0)
+    h = np.array([60.0] + list(st["height_km"]))
+    n6 = 23 - a["layers"]
+    parcel = a["tau_total"] / (h[n6] - h[-1])
+    aerext = np.zeros(23)
+    aerext[n6:] = parcel * (h[n6:-1] - h[n6 + 1:])
+    ext, ssa = np.array(st["molext"]), np.array(st["molomg"])
+    q = vb.rt_set_streams(st["nstreams"], sza, st["vza"], 1, np.float64)
+    return vb.RTModel("Stokes_I", q, sza, list(st["vza"]), [raz] * len(st["vza"]), np.tile(ssa * ext, (2, 1)),
+                      np.tile((1 - ssa) * ext, (2, 1)), aerext[None, :], [aer], vb.get_greek_rayleigh(st["depol"]),
+                      st["albedo"], vb.derive_m_max([aer], st["nstreams"]), 1.0, vb.RTNumericalParameters(), np.float64)
+
+
+def solar_tester_errors(st, out, isza, iraz):
+    """Worst relative deviation of R_SFI (TOA up) and T_SFI (BOA down) from VLIDORT task 1 over the VZAs."""
+    up = dn = 0.0
+    for ivza in range(len(st["vza"])):
+        g = (isza * 3 + ivza) * 3 + iraz
+        up = max(up, abs(out["R_SFI"][ivza, 0, 0] - st["toa_up"][g]) / st["toa_up"][g])
+        dn = max(dn, abs(out["T_SFI"][ivza, 0, 0] - st["boa_dn"][g]) / st["boa_dn"][g])
+    return up, dn

@@ -208,6 +208,17 @@ def test_natraj_cds_tables_on_gpu(ctx):
     assert_close(out, orc.rt_run(to_oracle(m)), F64_TOL)
 
 
+def test_vlidort_solar_tester_on_gpu(ctx):
+    # 23 layers, Rayleigh + gas + HG aerosol, Stokes_I, 16 moments: straight against VLIDORT and against the oracle
+    from helpers import solar_tester_errors, solar_tester_model
+    st = golden()["solar_tester"]
+    m = solar_tester_model(st, st["sza"][0], st["raz"][1])
+    out = run_gpu(m, ctx)
+    up, dn = solar_tester_errors(st, out, 0, 1)
+    assert up < st["rtol"] and dn < st["rtol"], (up, dn)
+    assert_close(out, orc.rt_run(to_oracle(m)), F64_TOL)
+
+
 def test_siewert_golden_on_gpu(ctx):
     # aerosol-only slab with supplied Greek coefficients: Rayleigh weight all-zero branch (types.jl:1279)
     m = siewert_model(90.0)
