@@ -119,9 +119,32 @@ def extract_solar_tester():
     }
 
 
+def extract_solar_tester_vector():
+    """VLIDORT solar_tester, NSTOKES = 3 with the Problem III Mie aerosol, as used by
+    test/vlidort_baseline/cases/case_C_solar_tester_vector.jl: first 16 expansion moments of the F-matrix and the
+    task-1 I/Q/U at TOA (up) and BOA (down) for all 36 geometries."""
+    d = os.path.join(REF, "test/vlidort_baseline/reference_data")
+    ta = open(os.path.join(d, "solar_tester_problemIII_aerosol.jl")).read()
+    tt = open(os.path.join(d, "solar_tester_vector_truth.jl")).read()
+    out = {"moms": {k: julia_vector(ta, "PROBLEMIII_" + k)[:16] for k in ("a1", "b1", "a2", "a3", "b2", "a4")},
+           "omega": 0.99999, "tau_total": 0.5, "layers": 6, "nstreams": 8, "albedo": 0.05,
+           "sza": julia_vector(tt, "SOLAR_TESTER_VECTOR_SZA_DEG"), "vza": julia_vector(tt, "SOLAR_TESTER_VECTOR_VZA_DEG"),
+           "raz": julia_vector(tt, "SOLAR_TESTER_VECTOR_RAZ_DEG"), "rtol_up": 1e-3, "rtol_dn": 2e-3}
+    for st in "IQU":
+        a = tt.index(f"const SOLAR_TESTER_VECTOR_{st} = reshape(")
+        b = tt.index("], ", a) if "], " in tt[a:a + 400000] else len(tt)
+        blk = tt[a:tt.index("const SOLAR_TESTER_VECTOR_", a + 10)]
+        vals = {}
+        for mt in re.finditer(r"^\s*(" + _num + r"),?\s*#\s*geom=(\d+)\s+level=(\d+)\s+dir=(\d+)\s+task=(\d+)", blk, re.M):
+            vals[tuple(int(mt.group(k)) for k in range(2, 6))] = float(mt.group(1))
+        out[st + "_toa_up"] = [vals[(g, 1, 1, 1)] for g in range(1, 37)]
+        out[st + "_boa_dn"] = [vals[(g, 5, 2, 1)] for g in range(1, 37)]
+    return out
+
+
 def main():
     extract_cds()
-    out = {"solar_tester": extract_solar_tester()}
+    out = {"solar_tester": extract_solar_tester(), "solar_tester_vector": extract_solar_tester_vector()}
     t = open(os.path.join(REF, "test/benchmarks/natraj_trues.jl")).read()
     out["natraj"] = {
         "mu": [0.02, 0.06, 0.10, 0.16, 0.20, 0.28, 0.32, 0.40, 0.52, 0.64, 0.72,

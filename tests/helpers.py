@@ -127,3 +127,37 @@ def solar_tester_errors(st, out, isza, iraz):
         up = max(up, abs(out["R_SFI"][ivza, 0, 0] - st["toa_up"][g]) / st["toa_up"][g])
         dn = max(dn, abs(out["T_SFI"][ivza, 0, 0] - st["boa_dn"][g]) / st["boa_dn"][g])
     return up, dn
+
+
+def solar_tester_vector_model(st, sv, sza, raz):
+    """The NSTOKES = 3 variant (test/vlidort_baseline/cases/case_C_solar_tester_vector.jl): same 23-layer atmosphere,
+    Problem III Mie aerosol (first 16 F-matrix moments: a1->beta, b1->gamma, a2->alpha, a3->zeta, b2->-epsilon,
+    a4->delta), omega 0.99999, Stokes_IQU."""
+    mo = sv["moms"]
+    g = vb.GreekCoefs(np.array(mo["a2"]), np.array(mo["a1"]), np.array(mo["b1"]), np.array(mo["a4"]),
+                      -np.array(mo["b2"]), np.array(mo["a3"]))
+    aer = vb.AerosolOptics(g, sv["omega"], 0.0)
+    h = np.array([60.0] + list(st["height_km"]))
+    n6 = 23 - sv["layers"]
+    parcel = sv["tau_total"] / (h[n6] - h[-1])
+    aerext = np.zeros(23)
+    aerext[n6:] = parcel * (h[n6:-1] - h[n6 + 1:])
+    ext, ssa = np.array(st["molext"]), np.array(st["molomg"])
+    q = vb.rt_set_streams(sv["nstreams"], sza, sv["vza"], 3, np.float64)
+    return vb.RTModel("Stokes_IQU", q, sza, list(sv["vza"]), [raz] * len(sv["vza"]), np.tile(ssa * ext, (2, 1)),
+                      np.tile((1 - ssa) * ext, (2, 1)), aerext[None, :], [aer], vb.get_greek_rayleigh(st["depol"]),
+                      sv["albedo"], vb.derive_m_max([aer], sv["nstreams"]), 1.0, vb.RTNumericalParameters(), np.float64)
+
+
+def solar_tester_vector_errors(sv, out, isza, iraz):
+    """Worst relative deviation per direction over I/Q/U and the VZAs; VLIDORT's Q and U carry the opposite sign
+    (case_C_solar_tester_vector.jl:163-166)."""
+    up = dn = 0.0
+    for si, s in enumerate("IQU"):
+        sgn = 1.0 if s == "I" else -1.0
+        for ivza in range(len(sv["vza"])):
+            g = (isza * 3 + ivza) * 3 + iraz
+            tu, td = sgn * sv[s + "_toa_up"][g], sgn * sv[s + "_boa_dn"][g]
+            up = max(up, abs(out["R_SFI"][ivza, si, 0] - tu) / abs(tu))
+            dn = max(dn, abs(out["T_SFI"][ivza, si, 0] - td) / abs(td))
+    return up, dn

@@ -219,6 +219,18 @@ def test_vlidort_solar_tester_on_gpu(ctx):
     assert_close(out, orc.rt_run(to_oracle(m)), F64_TOL)
 
 
+def test_vlidort_solar_tester_vector_on_gpu(ctx):
+    # polarized 23-layer case with the Problem III Mie aerosol (N = 36): against VLIDORT and against the oracle
+    from helpers import solar_tester_vector_errors, solar_tester_vector_model
+    G = golden()
+    st, sv = G["solar_tester"], G["solar_tester_vector"]
+    m = solar_tester_vector_model(st, sv, sv["sza"][0], sv["raz"][0])
+    out = run_gpu(m, ctx)
+    up, dn = solar_tester_vector_errors(sv, out, 0, 0)
+    assert up < sv["rtol_up"] and dn < sv["rtol_dn"], (up, dn)
+    assert_close(out, orc.rt_run(to_oracle(m)), F64_TOL)
+
+
 def test_siewert_golden_on_gpu(ctx):
     # aerosol-only slab with supplied Greek coefficients: Rayleigh weight all-zero branch (types.jl:1279)
     m = siewert_model(90.0)
