@@ -987,6 +987,42 @@ def rpv_reflectance(rho0, rho_c, k, theta_hs, mu_i, mu_r, dphi):
     return rho0 * M * F * H
 
 
+def rossli_reflectance(fiso, fvol, fgeo, mu_i, mu_r, dphi):
+    """Scalar Ross-Li BRDF (rossli_surface.jl: reflectance + RossLi_K_vol + RossLi_K_geo, RAMI defaults
+    h/b = 2, b/r = 1)."""
+    dphi = math.pi - dphi
+    th_i, th_r = math.acos(mu_i), math.acos(mu_r)
+    xi = math.acos(max(-1.0, min(1.0, math.cos(th_i) * math.cos(th_r) + math.sin(th_i) * math.sin(th_r) * math.cos(dphi))))
+    k_vol = ((math.pi / 2 - xi) * math.cos(xi) + math.sin(xi)) / (math.cos(th_i) + math.cos(th_r)) - math.pi / 4
+    tip, trp = math.atan(math.tan(th_i) * 1.0), math.atan(math.tan(th_r) * 1.0)
+    xip = math.acos(max(-1.0, min(1.0, math.cos(tip) * math.cos(trp) + math.sin(tip) * math.sin(trp) * math.cos(dphi))))
+    D = math.sqrt(max(0.0, math.tan(tip) ** 2 + math.tan(trp) ** 2 - 2 * math.tan(tip) * math.tan(trp) * math.cos(dphi)))
+    sec = 1 / math.cos(tip) + 1 / math.cos(trp)
+    ct = 2.0 * math.sqrt(D * D + (math.tan(tip) * math.tan(trp) * math.sin(dphi)) ** 2) / sec
+    ct = max(-1.0, min(1.0, ct))
+    t = math.acos(ct)
+    O = (1 / math.pi) * (t - math.sin(t) * math.cos(t)) * sec
+    k_geo = O - sec + 0.5 * (1 + math.cos(xip)) / (math.cos(tip) * math.cos(trp))
+    return fiso + fvol * k_vol + fgeo * k_geo
+
+
+def brdf_surface_rho(quad: QuadPoints, m_max: int, fn, nquad: int = 100):
+    """reflectance(brdf, pol_type, mu, m) (rpv_surface.jl:166-196) for a scalar BRDF fn(mu_i, mu_r, dphi), with
+    the factor 2 of create_surface_layer! (:69-73).  Pure-Python loops: small cases only."""
+    pol_n = quad.pol_n
+    mu = np.asarray(quad.qp_mu, float)
+    nq = mu.size
+    phi, w = gauleg(nquad, 0.0, math.pi)
+    out = np.zeros((m_max + 1, nq * pol_n, nq * pol_n))
+    for i in range(nq):
+        for j in range(nq):
+            vals = [fn(mu[i], mu[j], x) for x in phi]
+            for m in range(m_max + 1):
+                c = sum(wx * v * math.cos(m * x) for x, wx, v in zip(phi, w, vals))
+                out[m, i * pol_n, j * pol_n] = 2.0 * c / math.pi
+    return out
+
+
 def rpv_surface_rho(quad: QuadPoints, m_max: int, rho0, rho_c, k, theta_hs, nquad: int = 100):
     """Fourier moments of the RPV reflectance matrix, reflectance(brdf, pol_type, mu, m)
     (rpv_surface.jl:166-196: 100-point Gauss-Legendre in azimuth over [0, pi], only the

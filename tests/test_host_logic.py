@@ -102,3 +102,18 @@ def test_prepare_rejects_wrong_surface_rho_shape():
     assert p.surf_rho is not None and tuple(p.surf_rho.shape) == (m.m_max + 1, N, N)
     m.surface_rho = None
     assert rr.prepare(m, "cpu").surf_rho is None
+
+
+def test_rossli_fourier_moments_match_oracle_restatement():
+    # host mirror (vectorised) against the oracle's loop restatement of rossli_surface.jl
+    import vsmom_oracle as orc
+    from helpers import to_oracle
+    m = vb.synthetic_o2a_model(nSpec=2, nstreams=3, polarization_type="Stokes_IQ", aerosol=False)
+    got = vb.rossli_surface_rho(m.quad_points, m.pol_n, 3, fiso=0.1, fvol=0.05, fgeo=0.02)
+    ref = orc.brdf_surface_rho(to_oracle(m).quad, 3, lambda a, b, p: orc.rossli_reflectance(0.1, 0.05, 0.02, a, b, p))
+    assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref))
+    # reciprocity of the kernels: rho(mu_i, mu_r) == rho(mu_r, mu_i) -> symmetric Stokes-I block
+    assert np.max(np.abs(got[:, ::2, ::2] - got[:, ::2, ::2].transpose(0, 2, 1))) <= 1e-12
+    # isotropic only == Lambertian: 2*fiso at m = 0
+    iso = vb.rossli_surface_rho(m.quad_points, m.pol_n, 2, fiso=0.25, fvol=0.0, fgeo=0.0)
+    assert np.allclose(iso[0, ::2, ::2], 0.5, atol=1e-13) and np.abs(iso[1:]).max() < 1e-13

@@ -411,30 +411,66 @@ def synthetic_o2a_model(nSpec: int = 10000, nstreams: int = 10, polarization_typ
 # BRDF surfaces: host-side Fourier moments (the reference computes them on the host too,
 # rpv_surface.jl:166-196); the device consumes them through RTModel.surface_rho.
 # ----------------------------------------------------------------------------
-def rpv_surface_rho(quad: QuadPoints, pol_n: int, m_max: int, rho0: float, rho_c: float, k: float,
-                    theta_hs: float, nquad: int = 100) -> np.ndarray:
-    """Fourier moments 0..m_max of the RPV (Rahman-Pinty-Verstraete) reflectance matrix,
-    ``(m_max+1, N, N)``: ``reflectance(rpv, n, mu_i, mu_r, dphi)`` (rpv_surface.jl:113-144, with the
-    reference's sign conventions) integrated over azimuth with a 100-point Gauss-Legendre rule
-    on [0, pi] (:166-196; only the Stokes-I block is non-zero), times the overall factor 2
-    (``ff`` for m > 0, the explicit ``2*`` of create_surface_layer! for m = 0, :69-73)."""
+def brdf_fourier_moments(quad: QuadPoints, pol_n: int, m_max: int, rho, nquad: int = 100) -> np.ndarray:
+    """Fourier moments 0..m_max of a scalar BRDF ``rho(mu_i, mu_r, dphi)`` (NumPy-broadcasting callable) as the
+    reference's ``reflectance(brdf, pol_type, mu, m)`` builds them (rpv_surface.jl:166-196): 100-point
+    Gauss-Legendre rule in azimuth over [0, pi], only the Stokes-I block is filled, times the overall factor 2
+    (``ff`` for m > 0, the explicit ``2*`` of create_surface_layer! for m = 0, :69-73).  Shape (m_max+1, N, N),
+    ready for ``RTModel.surface_rho``."""
     mu = np.asarray(quad.qp_mu, np.float64)
     x, w = np.polynomial.legendre.leggauss(nquad)
     phi = 0.5 * math.pi * (x + 1.0)
     w = 0.5 * math.pi * w
-    mi, mr = mu[:, None, None], mu[None, :, None]
-    cphi = np.cos(phi)[None, None, :]
-    ti, tr = np.arccos(mi), np.arccos(mr)
-    cosg = -mi * mr + np.sin(ti) * np.sin(tr) * cphi
-    G = np.sqrt(np.tan(ti) ** 2 + np.tan(tr) ** 2 + 2 * np.tan(ti) * np.tan(tr) * cphi)
-    M = (mi * mr) ** (k - 1) / (mi + mr) ** (1 - k)
-    th = -theta_hs
-    F = (1 - th * th) / (1 + th * th + 2 * th * cosg) ** 1.5
-    H = 1 + (1 - rho_c) / (1 + G)
-    rho = rho0 * M * F * H                                      # (Nquad, Nquad, nquad)
+    r = rho(mu[:, None, None], mu[None, :, None], phi[None, None, :])          # (Nquad, Nquad, nquad)
     nq = mu.size
     out = np.zeros((m_max + 1, nq * pol_n, nq * pol_n))
     for m in range(m_max + 1):
-        c = (rho * (w * np.cos(m * phi))[None, None, :]).sum(axis=2)
+        c = (r * (w * np.cos(m * phi))[None, None, :]).sum(axis=2)
         out[m, ::pol_n, ::pol_n] = 2.0 * c / math.pi
     return out
+
+
+def rpv_reflectance(rho0: float, rho_c: float, k: float, theta_hs: float):
+    """RPV (Rahman-Pinty-Verstraete) BRDF with the reference's sign conventions (rpv_surface.jl:113-144)."""
+    def rho(mi, mr, dphi):
+        ti, tr = np.arccos(mi), np.arccos(mr)
+        cosg = -mi * mr + np.sin(ti) * np.sin(tr) * np.cos(dphi)
+        G = np.sqrt(np.tan(ti) ** 2 + np.tan(tr) ** 2 + 2 * np.tan(ti) * np.tan(tr) * np.cos(dphi))
+        M = (mi * mr) ** (k - 1) / (mi + mr) ** (1 - k)
+        th = -theta_hs
+        F = (1 - th * th) / (1 + th * th + 2 * th * cosg) ** 1.5
+        H = 1 + (1 - rho_c) / (1 + G)
+        return rho0 * M * F * H
+    return rho
+
+
+def rossli_reflectance(fiso: float, fvol: float, fgeo: float):
+    """Ross-Li BRDF: isotropic + Ross-thick volumetric + Li-sparse geometric kernels with the RAMI defaults
+    h/b = 2, b/r = 1 (rossli_surface.jl: reflectance, RossLi_K_vol, RossLi_K_geo)."""
+    def rho(mi, mr, dphi):
+        dphi = math.pi - dphi
+        ti, tr = np.arccos(mi), np.arccos(mr)
+        xi = np.arccos(np.clip(np.cos(ti) * np.cos(tr) + np.sin(ti) * np.sin(tr) * np.cos(dphi), -1.0, 1.0))
+        kvol = ((math.pi / 2 - xi) * np.cos(xi) + np.sin(xi)) / (np.cos(ti) + np.cos(tr)) - math.pi / 4
+        tip, trp = np.arctan(np.tan(ti) * 1.0), np.arctan(np.tan(tr) * 1.0)
+        xip = np.arccos(np.clip(np.cos(tip) * np.cos(trp) + np.sin(tip) * np.sin(trp) * np.cos(dphi), -1.0, 1.0))
+        D = np.sqrt(np.maximum(np.tan(tip) ** 2 + np.tan(trp) ** 2 - 2 * np.tan(tip) * np.tan(trp) * np.cos(dphi), 0.0))
+        sec = 1 / np.cos(tip) + 1 / np.cos(trp)
+        ct = np.clip(2.0 * np.sqrt(D ** 2 + (np.tan(tip) * np.tan(trp) * np.sin(dphi)) ** 2) / sec, -1.0, 1.0)
+        t = np.arccos(ct)
+        O = (1 / math.pi) * (t - np.sin(t) * np.cos(t)) * sec
+        kgeo = O - sec + 0.5 * (1 + np.cos(xip)) / (np.cos(tip) * np.cos(trp))
+        return fiso + fvol * kvol + fgeo * kgeo
+    return rho
+
+
+def rossli_surface_rho(quad: QuadPoints, pol_n: int, m_max: int, fiso: float, fvol: float, fgeo: float,
+                       nquad: int = 100) -> np.ndarray:
+    """Fourier moments of the Ross-Li reflectance matrix, shape (m_max+1, N, N)."""
+    return brdf_fourier_moments(quad, pol_n, m_max, rossli_reflectance(fiso, fvol, fgeo), nquad)
+
+
+def rpv_surface_rho(quad: QuadPoints, pol_n: int, m_max: int, rho0: float, rho_c: float, k: float,
+                    theta_hs: float, nquad: int = 100) -> np.ndarray:
+    """Fourier moments of the RPV reflectance matrix, shape (m_max+1, N, N)."""
+    return brdf_fourier_moments(quad, pol_n, m_max, rpv_reflectance(rho0, rho_c, k, theta_hs), nquad)
