@@ -250,6 +250,23 @@ def test_nonscattering_layers_all_interfaces(ctx):
     assert_close(run_gpu(m, ctx), orc.rt_run(to_oracle(m)), F64_TOL)
 
 
+def test_nonscattering_layers_fresh_context():
+    # the added-layer hand-off is sized from the SCATTERING layers and indexed by their compact position
+    # (sched_idx); a fresh context (grow-only buffers still empty) as first call catches any extent mismatch
+    from vsmom_b200 import _lib
+    m = vb.synthetic_o2a_model(nSpec=6, nstreams=8, polarization_type="Stokes_IQU", aerosol=False,
+                               p_half=np.array([1., 50., 200., 400., 600., 800., 1000.]))
+    m.tau_rayl[:, 0] = 0; m.tau_rayl[:, 1] = 0; m.tau_rayl[:, 3] = 0
+    m.tau_abs[:, 0] += 0.05; m.tau_abs[:, 3] += 0.2
+    assert list(vb.layer_control(m).scatter) == [0, 0, 1, 0, 1, 1]
+    c = _lib.Context(0)
+    try:
+        out = run_gpu(m, c)
+    finally:
+        c.close()
+    assert_close(out, orc.rt_run(to_oracle(m)), F64_TOL)
+
+
 def test_single_point_and_empty(ctx):
     m = vb.synthetic_o2a_model(nSpec=1, nstreams=4, aerosol=True)
     assert_close(run_gpu(m, ctx), orc.rt_run(to_oracle(m)), F64_TOL)      # batch == 1 must work

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -31,6 +32,8 @@ struct vsm_ctx {
     uint64_t ws_limit = 0;
     int inverse_mode = 1;   // 1: adaptive Neumann / Gauss-Jordan, 0: Gauss-Jordan only
     uint64_t launches = 0;
+    int dbg_layer_ctas = 0;                 // VSM_DEBUG_LAYER_CTAS_PER_SM, read once at vsm_create
+    std::map<const void*, int> smem_set;    // largest dynamic shared-memory size already granted per kernel
     std::string err;
     // grow-only scratch
     DevBuf consts, props, added, slabs, partial, counter, l0tmp, geom;
@@ -54,6 +57,15 @@ struct vsm_ctx {
             return VSM_ERR_CUDA;                                                  \
         }                                                                         \
     } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize, issued once per (kernel, size) instead of per call
+static cudaError_t set_smem(vsm_ctx* ctx, const void* kern, size_t bytes) {
+    auto it = ctx->smem_set.find(kern);
+    if (it != ctx->smem_set.end() && it->second >= (int)bytes) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) ctx->smem_set[kern] = (int)bytes;
+    return e;
+}
 
 static int fail(vsm_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg; else g_create_error = msg;
@@ -80,14 +92,22 @@ static int ensure(vsm_ctx* ctx, DevBuf& b, size_t bytes) {
     return VSM_OK;
 }
 
+// nullptr (and ctx->err set) when the event cannot be created
 static cudaEvent_t get_event(vsm_ctx* ctx) {
     if (ctx->ev_used == ctx->ev_pool.size()) {
-        cudaEvent_t e;
-        cudaEventCreate(&e);
+        cudaEvent_t e = nullptr;
+        const cudaError_t rc = cudaEventCreate(&e);
+        if (rc != cudaSuccess) {
+            ctx->err = std::string("cudaEventCreate: ") + cudaGetErrorString(rc);
+            return nullptr;
+        }
         ctx->ev_pool.push_back(e);
     }
     return ctx->ev_pool[ctx->ev_used++];
 }
+#define GET_EVENT(var)                                  \
+    cudaEvent_t var = get_event(ctx);                   \
+    if (!var) return VSM_ERR_CUDA
 
 extern "C" int vsm_version(void) { return 100; }
 
@@ -116,6 +136,7 @@ extern "C" int vsm_create(vsm_ctx** out, int device, void* cuda_stream) {
     ctx->num_sms = prop.multiProcessorCount;
     ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     ctx->ws_limit = 0;
+    if (const char* e = getenv("VSM_DEBUG_LAYER_CTAS_PER_SM")) ctx->dbg_layer_ctas = atoi(e);
     *out = ctx;
     return VSM_OK;
 }
@@ -218,7 +239,7 @@ static int bmm_impl(vsm_ctx* ctx, T* C, const T* A, const T* B, int M, int K, in
         // (+2 KB: the fragment loads of the padded 48x48 tiles read up to 3 columns = 1.1 KB past the end of
         //  an operand; harmless inside the arena of the fused kernels, but the last stage needs the room here)
         const size_t smem = (size_t)4 * kL0LB * sizeof(double) + 2048;
-        CK(cudaFuncSetAttribute(k_bmm_f64_n45, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(set_smem(ctx, (const void*)k_bmm_f64_n45, smem));
         k_bmm_f64_n45<<<std::min(batch, ctx->num_sms * 3), 128, smem, ctx->stream>>>((double*)C, (const double*)A,
                                                                                     (const double*)B, batch);
         ctx->launches++;
@@ -232,15 +253,15 @@ static int bmm_impl(vsm_ctx* ctx, T* C, const T* A, const T* B, int M, int K, in
     const bool vec = (Nc == 1);
     if (vec) {
         auto kern = k_bmm<T, 1, 1>;
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(set_smem(ctx, (const void*)kern, smem));
         kern<<<grid, 128, smem, ctx->stream>>>(C, A, B, M, K, Nc, batch, stage);
     } else if (M <= 24) {
         auto kern = k_bmm<T, 2, 2>;
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(set_smem(ctx, (const void*)kern, smem));
         kern<<<grid, 128, smem, ctx->stream>>>(C, A, B, M, K, Nc, batch, stage);
     } else {
         auto kern = k_bmm<T, 4, 4>;
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(set_smem(ctx, (const void*)kern, smem));
         kern<<<grid, 256, smem, ctx->stream>>>(C, A, B, M, K, Nc, batch, stage);
     }
     ctx->launches++;
@@ -256,7 +277,7 @@ static int binv_impl(vsm_ctx* ctx, T* X, T* A, int N, int batch, int* info) {
     CK(cudaSetDevice(ctx->device));
     if (sizeof(T) == 8 && N == kL0N) {                                     // the hot-path shape: tensor-core path
         const size_t smem = ((size_t)kL0LB + 13 * kL0N) * sizeof(double) + (kL0N + 4) * sizeof(int);
-        CK(cudaFuncSetAttribute(k_binv_f64_n45, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(set_smem(ctx, (const void*)k_binv_f64_n45, smem));
         k_binv_f64_n45<<<std::min(batch, ctx->num_sms * 3), 128, smem, ctx->stream>>>((double*)X, (const double*)A, batch, info);
         ctx->launches++;
         CK(cudaGetLastError());
@@ -267,7 +288,7 @@ static int binv_impl(vsm_ctx* ctx, T* X, T* A, int N, int batch, int* info) {
     const int stage = full <= (size_t)ctx->max_smem_optin ? 1 : 0;
     const size_t smem = stage ? full : vecb;
     auto kern = k_binv<T>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(set_smem(ctx, (const void*)kern, smem));
     const int grid = std::min(batch, ctx->num_sms * 8);
     const int threads = N <= 8 ? 64 : (N <= 24 ? 128 : 256);
     kern<<<grid, threads, smem, ctx->stream>>>(X, A, N, batch, info, stage);
@@ -279,7 +300,9 @@ static int binv_impl(vsm_ctx* ctx, T* X, T* A, int N, int batch, int* info) {
 template <typename T>
 static int bsolve_impl(vsm_ctx* ctx, T* X, T* A, const T* B, int N, int Nc, int batch) {
     if (!ctx || !X || !A || !B) return fail(ctx, VSM_ERR_INVALID_ARG, "batch_solve: NULL argument");
+    if (N <= 0 || Nc <= 0 || batch < 0) return fail(ctx, VSM_ERR_INVALID_ARG, "batch_solve: bad dims");
     if (batch == 0) return VSM_OK;
+    CK(cudaSetDevice(ctx->device));
     int rc = ensure(ctx, ctx->l0tmp, (size_t)N * N * batch * sizeof(T));
     if (rc) return rc;
     T* inv = (T*)ctx->l0tmp.p;
@@ -429,6 +452,10 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
     std::vector<int> order_pad(order);
     order_pad.resize(Nz, 0);
     const size_t o_ord = pushI(order_pad.data(), Nz);
+    std::vector<int> sched_idx(Nz, 0);          // compact hand-off slot of every scattering layer
+    for (int k = 0; k < nSched; ++k) sched_idx[order[k]] = k;
+    const size_t o_sidx = pushI(sched_idx.data(), Nz);
+    const int nSl = std::max(1, nSched);
     std::vector<int> vrow(nV);
     for (int i = 0; i < nV; ++i) {
         if (d->vza_stream[i] < 1 || d->vza_stream[i] * nSt > N) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column: vza_stream out of range");
@@ -490,18 +517,18 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
     if (fast && fc.adding_two_group) a_smem = a2_smem;
     const void* kl = nullptr; const void* ka = nullptr;
     get_kernel_ptrs<T>(cfg.tm, fast, N, &kl, &ka);
-    CK(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l_smem));
-    CK(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
+    CK(set_smem(ctx, (const void*)kl, l_smem));
+    CK(set_smem(ctx, (const void*)ka, a_smem));
     // CTA sizes: the specialised kernels fix theirs at compile time
     const int l_threads = fast ? fc.layer_threads : cfg.threads;
     const int a_threads = fast ? fc.adding_threads : cfg.threads;
     const int l_occ = occupancy<T>(kl, l_threads, l_smem);
     const int a_occ = occupancy<T>(ka, a_threads, a_smem);
     int l_grid_max = ctx->num_sms * l_occ, a_grid_max = ctx->num_sms * a_occ;
-    if (const char* e = getenv("VSM_DEBUG_LAYER_CTAS_PER_SM")) l_grid_max = ctx->num_sms * std::max(1, std::min(l_occ, atoi(e)));
+    if (ctx->dbg_layer_ctas > 0) l_grid_max = ctx->num_sms * std::max(1, std::min(l_occ, ctx->dbg_layer_ctas));
 
     // ---- workspace plan: chunk over spectral points and moments
-    const size_t add_item = (size_t)std::max(1, nSched) * ((size_t)2 * N * N + 2 * N) * sizeof(T);
+    const size_t add_item = (size_t)nSl * ((size_t)2 * N * N + 2 * N) * sizeof(T);
     const size_t props_pt = ((size_t)Nz * (2 + nC) + (Nz + 1)) * sizeof(T);
     const size_t part_pt = (size_t)3 * nM * nOut * sizeof(T);
     uint64_t limit = ctx->ws_limit ? ctx->ws_limit : (uint64_t)24 << 30;
@@ -543,7 +570,8 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
     ctx->ev_used = 0;
     ctx->seg_layer.clear();
     ctx->seg_add.clear();
-    cudaEvent_t ev_begin = get_event(ctx), ev_end = get_event(ctx);
+    GET_EVENT(ev_begin);
+    GET_EVENT(ev_end);
     CK(cudaEventRecord(ev_begin, ctx->stream));
 
     const size_t NN = (size_t)N * N;
@@ -573,10 +601,11 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
         memset(&a, 0, sizeof a);
         a.N = N; a.nStokes = nSt; a.Nz = Nz; a.nC = nC; a.nVZA = nV; a.ld = ld;
         a.istart = (d->imu0 - 1) * nSt;
-        a.nS = nS; a.n_sched_layers = nSched; a.z_spectral = 0; a.mz0 = 0; a.neumann = ctx->inverse_mode;
+        a.nS = nS; a.n_sched_layers = nSl; a.z_spectral = 0; a.mz0 = 0; a.neumann = ctx->inverse_mode;
         a.mu0 = (T)d->mu0; a.albedo = (T)d->albedo; a.surf_rho = (const T*)surf_rho;
         a.mu = cT + o_mu; a.wt = cT + o_wt;
         a.ndoubl = cI + o_nd; a.scatter = cI + o_sc; a.iface = cI + o_if; a.layer_order = cI + o_ord;
+        a.sched_idx = cI + o_sidx;
         a.Zpp = (const T*)d->Zpp; a.Zmp = (const T*)d->Zmp;
         a.p_tau = pa.tau; a.p_varpi = pa.varpi; a.p_tausum = pa.tausum; a.p_W = pa.W;
         a.F0 = (const T*)d->F0; a.F0_off = (size_t)n0;
@@ -592,7 +621,7 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
             const int mb = std::min(Mb, nM - m0);
             a.m0 = m0; a.Mb = mb;
             T* ad = (T*)ctx->added.p;
-            const size_t slots = (size_t)mb * Nz * nS;
+            const size_t slots = (size_t)mb * nSl * nS;
             a.add_r = ad; a.add_t = ad + slots * NN; a.add_jp = ad + 2 * slots * NN; a.add_jm = a.add_jp + slots * N;
             // --- k_layer
             if (nSched > 0) {
@@ -600,7 +629,8 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
                 const int grid = (int)std::min<size_t>(total, (size_t)l_grid_max);
                 a.n_smem_mats = l_mats; a.slab = (T*)ctx->slabs.p; a.slab_stride = l_slab / sizeof(T);
                 CK(cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
-                cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+                GET_EVENT(e0);
+                GET_EVENT(e1);
                 CK(cudaEventRecord(e0, ctx->stream));
                 rc = do_launch<T>(ctx, true, cfg.tm, fast, N, a, total, grid, l_threads, l_smem);
                 if (rc) return rc;
@@ -615,7 +645,8 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
                 a.slab = (T*)ctx->slabs.p + ((size_t)l_slab * l_grid_max) / sizeof(T);
                 a.slab_stride = a_slab / sizeof(T);
                 CK(cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
-                cudaEvent_t e0 = get_event(ctx), e1 = get_event(ctx);
+                GET_EVENT(e0);
+                GET_EVENT(e1);
                 CK(cudaEventRecord(e0, ctx->stream));
                 rc = do_launch<T>(ctx, false, cfg.tm, fast, N, a, total, grid, a_threads, a_smem);
                 if (rc) return rc;
@@ -708,8 +739,8 @@ static int rt_layer_impl(vsm_ctx* ctx, const vsm_layer_desc* d) {
         case 3: ks = step_kernel_ptr<T, 3>(); break;
         default: ks = step_kernel_ptr<T, 4>(); break;
     }
-    CK(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l_smem));
-    CK(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
+    CK(set_smem(ctx, (const void*)kl, l_smem));
+    CK(set_smem(ctx, (const void*)ks, a_smem));
     const int l_grid_max = ctx->num_sms * occupancy<T>(kl, cfg.threads, l_smem);
     const int s_grid_max = ctx->num_sms * occupancy<T>(ks, cfg.threads, a_smem);
     const size_t NN2 = (size_t)N * N;
@@ -744,7 +775,7 @@ static int rt_layer_impl(vsm_ctx* ctx, const vsm_layer_desc* d) {
         a.n_smem_mats = l_mats; a.z_spectral = d->z_is_spectral ? 1 : 0; a.mz0 = d->m; a.neumann = ctx->inverse_mode;
         a.mu0 = (T)d->mu0; a.albedo = T(0);
         a.mu = (const T*)d->mu; a.wt = (const T*)d->wt;
-        a.ndoubl = cI; a.scatter = cI + 1; a.iface = cI + 2; a.layer_order = cI + 3;
+        a.ndoubl = cI; a.scatter = cI + 1; a.iface = cI + 2; a.layer_order = cI + 3; a.sched_idx = cI + 3;
         a.Zpp = (const T*)d->Zpp; a.Zmp = (const T*)d->Zmp;
         a.p_tau = (const T*)d->tau; a.p_varpi = (const T*)d->varpi; a.p_tausum = (const T*)d->tau_sum;
         a.p_W = (const T*)d->tau;                      // nC == 1: weights unused

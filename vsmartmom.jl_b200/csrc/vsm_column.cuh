@@ -151,13 +151,14 @@ struct ColArgs {
     const T* surf_rho;       // BRDF surface: Fourier moments of R_surf (N,N,n_moments), or null = Lambertian(albedo)
     const T* mu; const T* wt;                         // [N]
     const int* ndoubl; const int* scatter; const int* iface; const int* layer_order;  // [Nz]
+    const int* sched_idx;    // [Nz] position of layer iz in layer_order (scattering layers only)
     const T* Zpp; const T* Zmp;                       // (N,N,nC,n_moments)
     const T* p_tau; const T* p_varpi; const T* p_tausum; const T* p_W;   // k_props outputs
     const T* F0; size_t F0_off;                       // (nStokes, nSpec) ; column offset of chunk
     const T* geo1; const T* geo2;                     // k_geom tables (N,N)
     const T* gs1; const T* gs2;                       // k_geom solar-stream factors [N]
     const unsigned char* gcls;                        // k_geom branch classes (N,N) + [N]
-    // added-layer scratch: slot = (mi*Nz + iz)*nS + p
+    // added-layer scratch: slot = (mi*n_sched_layers + sched_idx[iz])*nS + p   (scattering layers only)
     T* add_r; T* add_t; T* add_jp; T* add_jm;
     // spill slabs and the work counter
     T* slab; size_t slab_stride;
@@ -185,7 +186,7 @@ __device__ inline unsigned int next_item(unsigned int* counter, unsigned int* sh
 // ----------------------------------------------------------------------------
 // geometry of the elemental formulas, shared by every point / layer / moment (built once per call):
 //   geo1[i,j] = mu_j/(mu_i+mu_j) * w_j ,  geo2[i,j] = mu_j/(mu_i-mu_j) * w_j  (0 where mu_i == mu_j)
-//   gcls[i,j] = kind | wflags<<2 : kind 0 distinct streams, 1 nearly coincident (|dmu| <= 1e-3 mu_j: the
+//   gcls[i,j] = kind | wflags<<2 : kind 0 distinct streams, 1 nearly coincident (|dmu| <= 1e-3 mu_j, fp32 5e-2: the
 //               exact expdiff_neg form is needed), 2 mu_i == mu_j ; wflags bit0/1 = (w_j*0.5 > eps) /
 //               (w_j*0.25 > eps), the `wct > eps` test of elemental.jl:296 for m == 0 / m > 0
 //   and against the solar stream s = istart:  gs1[i] = mu_s/(mu_i+mu_s), gs2[i] = mu_s/(mu_i-mu_s)
@@ -199,7 +200,10 @@ __global__ void k_geom(int n, int nStokes, int istart, const T* __restrict__ mu,
     const int i = e % n, j = e / n;
     const T mui = mu[i], muj = mu[j], wj = wt[j];
     const T eps = Num<T>::eps();
-    const int kind = (mui == muj) ? 2 : ((Num<T>::abs_(mui - muj) > T(1e-3) * muj) ? 0 : 1);
+    // em1_i - em1_j loses ~mu/|dmu| ulps to cancellation: negligible in fp64 below 1e3 eps, but fp32 keeps the
+    // exact expdiff_neg form (the reference's, elemental.jl:319-323) for every pair closer than 5 %
+    const T near = (sizeof(T) == 8) ? T(1e-3) : T(5e-2);
+    const int kind = (mui == muj) ? 2 : ((Num<T>::abs_(mui - muj) > near * muj) ? 0 : 1);
     geo1[e] = (muj / (mui + muj)) * wj;
     geo2[e] = (kind == 2) ? T(0) : (muj / (mui - muj)) * wj;
     gcls[e] = (unsigned char)(kind | ((wj * T(0.5) > eps) ? 4 : 0) | ((wj * T(0.25) > eps) ? 8 : 0));
@@ -209,7 +213,7 @@ __global__ void k_geom(int n, int nStokes, int istart, const T* __restrict__ mu,
         const T me = mu[e];
         gs1[e] = mus / (me + mus);
         gs2[e] = sun ? T(0) : mus / (me - mus);
-        gcls[n * n + e] = (unsigned char)(sun ? 2 : ((Num<T>::abs_(me - mus) > T(1e-3) * mus) ? 0 : 1));
+        gcls[n * n + e] = (unsigned char)(sun ? 2 : ((Num<T>::abs_(me - mus) > near * mus) ? 0 : 1));
     }
 }
 
@@ -430,7 +434,8 @@ __global__ void __launch_bounds__(NTHR, MINB) k_layer(ColArgs<T> a, unsigned int
         const int p = item % a.nS;
         const unsigned int rest = item / a.nS;
         const int mi = rest % a.Mb;
-        const int iz = a.layer_order[rest / a.Mb];
+        const int si = rest / a.Mb;
+        const int iz = a.layer_order[si];
         const int m = a.m0 + mi;
         const int nd = a.ndoubl[iz];
         const size_t pi = (size_t)iz * a.nS + p;
@@ -451,7 +456,7 @@ __global__ void __launch_bounds__(NTHR, MINB) k_layer(ColArgs<T> a, unsigned int
         doubling_loop<T, Ops>(op, nd, expk, r, t, X1, X2, jp, jm, j1p, j1m, v1, v2);
         VSM_TICK(8);
         // apply_D_matrix! / apply_D_matrix_SFI! (doubling.jl:178-216): r⁻⁺ <- D r*, j₀⁻ <- D j*
-        const size_t slot = ((size_t)mi * a.Nz + iz) * a.nS + p;
+        const size_t slot = ((size_t)mi * a.n_sched_layers + si) * a.nS + p;
         T* gr = a.add_r + slot * zstride;
         T* gt = a.add_t + slot * zstride;
         for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
@@ -711,7 +716,7 @@ __global__ void __launch_bounds__(NTHR) k_adding(ColArgs<T> a, unsigned int tota
             T* djp = (iz == 0) ? J0p : jp;
             T* djm = (iz == 0) ? J0m : jm;
             if (sc) {
-                const size_t slot = ((size_t)mi * a.Nz + iz) * a.nS + p;
+                const size_t slot = ((size_t)mi * a.n_sched_layers + a.sched_idx[iz]) * a.nS + p;
                 const T* gr = a.add_r + slot * zstride;
                 const T* gt = a.add_t + slot * zstride;
                 for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
@@ -981,7 +986,7 @@ __global__ void __launch_bounds__(2 * GT, 1) k_adding2(ColArgs<T> a, unsigned in
         T* dr = dr0 ? dr0 : lbuf + (2 * b) * LB;
         T* dt = dt0 ? dt0 : lbuf + (2 * b + 1) * LB;
         if (lflag[iz] & 1) {
-            const size_t slot = ((size_t)mi * a.Nz + iz) * a.nS + p;
+            const size_t slot = ((size_t)mi * a.n_sched_layers + a.sched_idx[iz]) * a.nS + p;
             const T* gr = a.add_r + slot * zstride;
             const T* gt = a.add_t + slot * zstride;
             if (dr0 || ld != n) {                        // fixed destination / padded layout: element copies
