@@ -168,6 +168,11 @@ typedef struct vsm_column_desc {
      * 2*reflectance(brdf,pol_type,qp_μ,0) for m = 0 and reflectance(brdf,pol_type,qp_μ,m) otherwise
      * (rpv_surface.jl:69-75).  Spectrally constant, like the reference's. */
     const void* surf_rho;
+    /* host, double, may be NULL -- only read when struct_size covers it: (nVZA,nStokes) geometry factor of the
+     * Cox-Munk TMS single-scattering correction, M_exact[si,1] - M_fourier[si,1] per viewing geometry
+     * (apply_ss_correction!, Surfaces/coxmunk_surface.jl:509-555, called at rt_run.jl:520-524).  The library adds
+     * R_SFI[iv,si,s] += mu0 * exp(-tau_sum_all[s,end]/mu0) * ss_correction[iv,si] in its output reduction. */
+    const double* ss_correction;
 } vsm_column_desc;
 /* outputs: device; R_SFI/T_SFI/hdr (nVZA,nStokes,nSpec); bhr_* (nStokes,nSpec);
  * hdr/bhr_uw/bhr_dw may be NULL.  Outputs are overwritten (not accumulated).  */

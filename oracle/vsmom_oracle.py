@@ -348,6 +348,9 @@ class Model:
     FT: type = np.float64
     # BRDF surface: Fourier moments of R_surf, (m_max+1, N, N) -- see brdf_surface(); None = Lambertian
     surface_rho: Optional[np.ndarray] = None
+    # Cox-Munk TMS correction (apply_ss_correction!, rt_run.jl:520-524): (nVZA, pol_n) geometry factor from
+    # coxmunk_ss_correction(); None = no correction (any surface other than CoxMunkSurface)
+    ss_correction: Optional[np.ndarray] = None
 
     @property
     def nSpec(self):
@@ -1044,6 +1047,182 @@ def rpv_surface_rho(quad: QuadPoints, m_max: int, rho0, rho_c, k, theta_hs, nqua
 
 
 # --------------------------------------------------------------------------
+# Cox-Munk ocean surface   src/CoreRT/Surfaces/coxmunk_surface.jl, fresnel.jl
+# (scalar restatement, pure-Python loops: small quadratures only)
+# --------------------------------------------------------------------------
+# water_refractive_index(550 nm) (water_refraction.jl: Segelstein 1981 table row 550 nm).  Every reference call
+# site evaluates the default `n_water = _get_n_water(surf, FT(550))` (coxmunk_surface.jl:262,465,514).
+N_WATER_550 = complex(1.328, 5.69e-9)
+
+
+@dataclass
+class CoxMunk:
+    """CoxMunkSurface (types.jl:525-536)."""
+    wind_speed: float
+    n_water: complex = N_WATER_550
+    whitecap_albedo: float = 0.22
+    include_whitecaps: bool = True
+    shadowing: bool = True
+
+
+def wind_to_sigma2(U):                                   # coxmunk_surface.jl:22
+    return 0.003 + 0.00512 * U
+
+
+def cox_munk_pdf(zx, zy, s2):                            # :25-27
+    return math.exp(-(zx * zx + zy * zy) / (2 * s2)) / (2 * math.pi * s2)
+
+
+def whitecap_fraction(U):                                # :30-33
+    return 0.0 if U <= 0 else 2.95e-6 * U ** 3.52
+
+
+def smith_lambda(mu, s2):                                # :41-50
+    if mu <= 0:
+        return 1e10
+    sig = math.sqrt(s2)
+    cot = mu / math.sqrt(max(1e-30, 1.0 - mu * mu))
+    nu = cot / (math.sqrt(2.0) * sig)
+    lam = (math.exp(-nu * nu) / (math.sqrt(2 * math.pi) * nu) - math.erfc(nu)) / 2
+    return max(0.0, lam)
+
+
+def shadow_factor(mu_i, mu_r, s2):                       # :53-55
+    return 1.0 / (1.0 + smith_lambda(mu_i, s2) + smith_lambda(mu_r, s2))
+
+
+def fresnel_coefficients(n_rel: complex, cos_i: float):  # fresnel.jl:25-33
+    import cmath
+    sin2 = max(0.0, 1.0 - cos_i * cos_i)
+    cos_t = cmath.sqrt(1.0 - sin2 / (n_rel * n_rel))
+    r_s = (cos_i - n_rel * cos_t) / (cos_i + n_rel * cos_t)
+    r_p = (n_rel * cos_i - cos_t) / (n_rel * cos_i + cos_t)
+    return r_s, r_p
+
+
+def fresnel_mueller(r_s: complex, r_p: complex, n: int) -> np.ndarray:   # fresnel.jl:50-88
+    rs2, rp2 = abs(r_s) ** 2, abs(r_p) ** 2
+    rsp = r_s * r_p.conjugate()
+    M = np.zeros((4, 4))
+    M[0, 0] = M[1, 1] = (rs2 + rp2) / 2
+    M[0, 1] = M[1, 0] = (rs2 - rp2) / 2
+    M[2, 2] = M[3, 3] = rsp.real
+    M[2, 3] = rsp.imag
+    M[3, 2] = -rsp.imag
+    return M[:n, :n]
+
+
+def stokes_rotation_matrix(phi: float, n: int) -> np.ndarray:            # fresnel.jl:104-132
+    c2, s2 = math.cos(2 * phi), math.sin(2 * phi)
+    L = np.eye(4)
+    L[1, 1] = c2; L[1, 2] = s2
+    L[2, 1] = -s2; L[2, 2] = c2
+    return L[:n, :n]
+
+
+def coxmunk_geometry(mu_i, mu_r, dphi):                  # coxmunk_surface.jl:124-250
+    sin_i = math.sqrt(max(0.0, 1 - mu_i * mu_i))
+    sin_r = math.sqrt(max(0.0, 1 - mu_r * mu_r))
+    cd, sd = math.cos(dphi), math.sin(dphi)
+    nx = -sin_i + sin_r * cd
+    ny = sin_r * sd
+    nz = mu_i + mu_r
+    nn = math.sqrt(nx * nx + ny * ny + nz * nz)
+    if nn < 1e-15:
+        return 1.0, 1.0, 0.0, 0.0, 0.0, 0.0
+    nx, ny, nz = nx / nn, ny / nn, nz / nn
+    cos_b = max(1e-10, nz)
+    cos_loc = min(max((mu_i + mu_r) / (2 * cos_b), 0.0), 1.0)
+    zx, zy = -nx / cos_b, -ny / cos_b
+    cosT = -mu_i * mu_r + sin_i * sin_r * cd
+    sinT = math.sqrt(max(0.0, 1 - cosT * cosT))
+    a1 = a2 = 0.0
+    if sinT >= 1e-12:
+        sp = np.array([-mu_i * sin_r * sd, mu_i * sin_r * cd - sin_i * mu_r, -sin_i * sin_r * sd])
+        ip = np.array([mu_i * ny, -mu_i * nx - sin_i * nz, sin_i * ny])
+        msp, mip = math.sqrt(sp @ sp), math.sqrt(ip @ ip)
+        if not (msp < 1e-15 or mip < 1e-15):
+            c = min(max((sp @ ip) / (msp * mip), -1.0), 1.0)
+            cr = np.cross(sp, ip)
+            sg = sin_i * cr[0] + (-mu_i) * cr[2]
+            a1 = math.acos(c) if sg >= 0 else -math.acos(c)
+        rp = np.array([(-sin_r * sd) * nz - mu_r * ny, mu_r * nx - (-sin_r * cd) * nz,
+                       (-sin_r * cd) * ny - (-sin_r * sd) * nx])
+        mrp = math.sqrt(rp @ rp)
+        if not (msp < 1e-15 or mrp < 1e-15):
+            c = min(max((sp @ rp) / (msp * mrp), -1.0), 1.0)
+            cr = np.cross(sp, rp)
+            sg = (-sin_r * cd) * cr[0] + (-sin_r * sd) * cr[1] + mu_r * cr[2]
+            a2 = math.acos(c) if sg >= 0 else -math.acos(c)
+    return cos_b, cos_loc, zx, zy, a1, a2
+
+
+def coxmunk_brdf_mueller(surf: CoxMunk, n: int, mu_i, mu_r, dphi) -> np.ndarray:   # :259-301
+    """(first argument pair as the reference's: its callers pass (reflected, incident) = (mu[i], mu[j]))"""
+    s2 = wind_to_sigma2(surf.wind_speed)
+    cos_b, cos_loc, zx, zy, a1, a2 = coxmunk_geometry(mu_i, mu_r, dphi)
+    P = cox_munk_pdf(zx, zy, s2)
+    r_s, r_p = fresnel_coefficients(surf.n_water, cos_loc)
+    M = stokes_rotation_matrix(a2, n) @ fresnel_mueller(r_s, r_p, n) @ stokes_rotation_matrix(-a1, n)
+    pre = P / (4 * mu_i * mu_r * cos_b ** 4)
+    if surf.shadowing:
+        pre *= shadow_factor(mu_i, mu_r, s2)
+    rho = pre * M
+    if surf.include_whitecaps:
+        f = whitecap_fraction(surf.wind_speed)
+        wc = np.zeros((n, n))
+        wc[0, 0] = surf.whitecap_albedo / math.pi
+        return (1 - f) * rho + f * wc
+    return rho
+
+
+def _azimuthal_kernel(si: int, sj: int, m: int, dphi: float) -> float:    # :444-452 (0-based si, sj)
+    return math.cos(m * dphi) if ((si <= 1) == (sj <= 1)) else math.sin(m * dphi)
+
+
+def coxmunk_surface_rho(quad: QuadPoints, m_max: int, surf: CoxMunk, nquad: int = 100) -> np.ndarray:
+    """reflectance(surf::CoxMunkSurface, pol_type, mu, m) (:464-498) for m = 0..m_max with the factor 2 of
+    create_surface_layer! at m = 0 (rpv_surface.jl:69-73; `ff` supplies it for m > 0): (m_max+1, N, N)."""
+    n = quad.pol_n
+    mu = np.asarray(quad.qp_mu, float)
+    nq = mu.size
+    phi, w = gauleg(nquad, 0.0, math.pi)
+    out = np.zeros((m_max + 1, nq * n, nq * n))
+    for x, wx in zip(phi, w):
+        for j in range(nq):
+            for i in range(nq):
+                M = coxmunk_brdf_mueller(surf, n, mu[i], mu[j], x)
+                for m in range(m_max + 1):
+                    cm, sm = math.cos(m * x), math.sin(m * x)
+                    for sj in range(n):
+                        for si in range(n):
+                            az = cm if ((si <= 1) == (sj <= 1)) else sm
+                            out[m, i * n + si, j * n + sj] += wx * M[si, sj] * az
+    return 2.0 * out / math.pi
+
+
+def coxmunk_ss_correction(surf: CoxMunk, pol_n: int, vza, vaz, mu0: float, m_max: int, nquad: int = 100) -> np.ndarray:
+    """The geometry factor of apply_ss_correction! (:509-555): (nVZA, pol_n) array of
+    M_exact[si,1] - M_fourier[si,1]; R_SFI[iv,si,s] += mu0 exp(-tau_total[s]/mu0) * that."""
+    phi, w = gauleg(nquad, 0.0, math.pi)
+    out = np.zeros((len(vza), pol_n))
+    for iv in range(len(vza)):
+        mu_v = cosd(vza[iv])
+        dphi = math.radians(vaz[iv])
+        Mex = coxmunk_brdf_mueller(surf, pol_n, mu_v, mu0, dphi)
+        Ms = [coxmunk_brdf_mueller(surf, pol_n, mu_v, mu0, x) for x in phi]
+        for si in range(pol_n):
+            four = 0.0
+            for m in range(m_max + 1):
+                wm = 0.5 if m == 0 else 1.0
+                ff = 1.0 if m == 0 else 2.0
+                coeff = ff * sum(wx * M[si, 0] * _azimuthal_kernel(si, 0, m, x) for x, wx, M in zip(phi, w, Ms)) / math.pi
+                four += wm * _azimuthal_kernel(si, 0, m, dphi) * coeff
+            out[iv, si] = Mex[si, 0] - four
+    return out
+
+
+# --------------------------------------------------------------------------
 # rt_run (noRS, SFI)   src/CoreRT/rt_run.jl:238-539, rt_kernel.jl:175-250
 # --------------------------------------------------------------------------
 def rt_kernel_layer(model: Model, m: int, iz: int, ctl: BandControl, props: CoreProps,
@@ -1156,6 +1335,10 @@ def rt_run(model: Model, sel=slice(None), return_streams: bool = False, prep: Op
             hdr[i] += wv[:, None] * hdr_J0m[:, ist:ist + pol_n].T
         if return_streams:
             streams.append(C)
+    if model.ss_correction is not None:                 # apply_ss_correction! (coxmunk_surface.jl:544-552)
+        ctl0 = prep.ctl if prep is not None else band_control(model, 0)
+        atten = (FT(q.mu0) * np.exp(-ctl0.tau_sum[idx, -1] / FT(q.mu0))).astype(FT)
+        R_SFI += np.asarray(model.ss_correction, FT)[:, :, None] * atten[None, None, :]
     out = dict(R_SFI=R_SFI, T_SFI=T_SFI, hdr=hdr, bhr_uw=bhr_uw[0], bhr_dw=bhr_dw[0])
     if return_streams:
         out['streams'] = streams

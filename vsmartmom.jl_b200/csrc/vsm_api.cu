@@ -401,14 +401,18 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
                           T* st_Jp = nullptr) {
     if (!ctx) return VSM_ERR_INVALID_ARG;
     // struct_size versions the descriptor: the layout up to Zmp (Lambertian only) or the full one
-    if (!d || (d->struct_size != (int)sizeof(vsm_column_desc) && d->struct_size != (int)offsetof(vsm_column_desc, surf_rho)))
+    // (Lambertian only), up to surf_rho (BRDF moments), or the full one (+ Cox-Munk TMS correction)
+    if (!d || (d->struct_size != (int)sizeof(vsm_column_desc) && d->struct_size != (int)offsetof(vsm_column_desc, surf_rho) &&
+               d->struct_size != (int)offsetof(vsm_column_desc, ss_correction)))
         return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column: descriptor NULL or struct_size mismatch");
-    const void* surf_rho = (d->struct_size == (int)sizeof(vsm_column_desc) && d->surface_kind == VSM_SURFACE_BRDF_FOURIER)
+    const void* surf_rho = (d->struct_size >= (int)offsetof(vsm_column_desc, ss_correction) && d->surface_kind == VSM_SURFACE_BRDF_FOURIER)
                                ? d->surf_rho : nullptr;
+    const double* ss_corr = (d->struct_size == (int)sizeof(vsm_column_desc)) ? d->ss_correction : nullptr;
     if (d->nSpec == 0) return VSM_OK;            // empty shard: nothing to do
     if (!R_SFI || !T_SFI) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column: R_SFI/T_SFI NULL");
     const int N = d->N, nSt = d->nStokes, Nz = d->Nz, nAer = d->nAer, nV = d->nVZA, nM = d->n_moments;
     const int nSpec = d->nSpec;
+    const int nOut = nV * nSt;
     if (N <= 0 || nSt < 1 || nSt > 4 || N % nSt != 0 || Nz <= 0 || nAer < 0 || nAer + 1 > kMaxComp ||
         nV <= 0 || nM <= 0 || nSpec < 0 || d->imu0 < 1 || d->imu0 * nSt > N)
         return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column: bad dimensions");
@@ -423,7 +427,6 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
     if (nSpec == 0) return VSM_OK;
     CK(cudaSetDevice(ctx->device));
     const int nC = nAer + 1;
-    const int nOut = nV * nSt;
 
     // ---- small constant tables -> one device blob
     std::vector<T> fT;
@@ -441,6 +444,7 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
     const size_t o_taumod = pushT(taumod.data(), taumod.size());
     const size_t o_varmod = pushT(varmod.data(), varmod.size());
     const size_t o_vw = pushT(d->vza_weight, (size_t)nSt * nV * nM);
+    const size_t o_ss = ss_corr ? pushT(ss_corr, (size_t)nOut) : 0;
     auto pushI = [&](const int32_t* p, size_t n) { size_t o = fI.size(); for (size_t i = 0; i < n; ++i) fI.push_back(p[i]); return o; };
     const size_t o_nd = pushI(d->ndoubl, Nz), o_sc = pushI(d->scatter, Nz), o_if = pushI(d->iface, Nz);
     const size_t o_rz = pushI(d->rayl_allzero, Nz);
@@ -657,7 +661,8 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
         // --- k_reduce into the caller's outputs (chunk window)
         k_reduce<T><<<(unsigned)((per_m + 255) / 256), 256, 0, ctx->stream>>>(
             nM, per_m, a.part_R, a.part_T, hdr ? a.part_H : (const T*)nullptr,
-            R_SFI + (size_t)n0 * nOut, T_SFI + (size_t)n0 * nOut, hdr ? hdr + (size_t)n0 * nOut : (T*)nullptr);
+            R_SFI + (size_t)n0 * nOut, T_SFI + (size_t)n0 * nOut, hdr ? hdr + (size_t)n0 * nOut : (T*)nullptr,
+            ss_corr ? cT + o_ss : (const T*)nullptr, pa.tausum + (size_t)Nz * nS, (T)d->mu0, nOut);
         ctx->launches++;
         CK(cudaGetLastError());
         if (bhr_uw) CK(cudaMemcpyAsync(bhr_uw + (size_t)n0 * nSt, cb_uw, (size_t)nSt * nS * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));

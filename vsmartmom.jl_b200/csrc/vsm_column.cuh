@@ -1250,11 +1250,13 @@ __global__ void __launch_bounds__(256) k_interact_step(StepArgs<T> a, unsigned i
     }
 }
 
-// out[o + nOut*p] = sum_m part[(m*nS + p)*nOut + o]   (m ascending, as the Fourier loop)
+// out[o + nOut*p] = sum_m part[(m*nS + p)*nOut + o]   (m ascending, as the Fourier loop), then the Cox-Munk
+// TMS correction R += mu0 exp(-tau_total/mu0) ss[o] (apply_ss_correction!, coxmunk_surface.jl:544-552) when given
 template <typename T>
 __global__ void k_reduce(int n_moments, size_t per_m, const T* __restrict__ pR,
                          const T* __restrict__ pT, const T* __restrict__ pH, T* __restrict__ R,
-                         T* __restrict__ Tt, T* __restrict__ H) {
+                         T* __restrict__ Tt, T* __restrict__ H, const T* __restrict__ ss,
+                         const T* __restrict__ tau_total, T mu0, int nOut) {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= per_m) return;
     T r = T(0), t = T(0), h = T(0);
@@ -1263,6 +1265,7 @@ __global__ void k_reduce(int n_moments, size_t per_m, const T* __restrict__ pR,
         t += pT[(size_t)m * per_m + e];
         if (H) h += pH[(size_t)m * per_m + e];
     }
+    if (ss) r += (mu0 * Num<T>::exp_(-tau_total[e / nOut] / mu0)) * ss[e % nOut];
     R[e] = r;
     Tt[e] = t;
     if (H) H[e] = h;

@@ -233,6 +233,9 @@ class RTModel:
     # moments of R_surf, shape (m_max+1, N, N) as built by create_surface_layer! before the
     # Diagonal(qp_muN.*wt_muN) scaling (rpv_surface.jl:69-75).  None -> Lambertian(albedo).
     surface_rho: Optional[np.ndarray] = None
+    # Cox-Munk TMS correction (apply_ss_correction!, rt_run.jl:520-524): (nVZA, pol_n) geometry factor from
+    # coxmunk.coxmunk_ss_correction(); None for every other surface
+    ss_correction: Optional[np.ndarray] = None
 
     @property
     def pol_n(self) -> int:
@@ -369,6 +372,29 @@ def hg_greek(g: float, nterms: int) -> GreekCoefs:
     return GreekCoefs(a, beta, np.zeros(nterms), beta.copy(), np.zeros(nterms), a.copy())
 
 
+def _synthetic_absorption(nu: np.ndarray, p_half: np.ndarray, seed: int, nu_lo: float, nu_hi: float,
+                          col_max: float, nlines: int = 60) -> np.ndarray:
+    """(nSpec, Nz) absorption optical depths of `nlines` pressure-broadened Lorentz pseudo-lines with centres
+    uniform in [nu_lo, nu_hi] and strengths log-uniform over four decades, scaled to a largest column optical
+    depth `col_max`, plus a 1e-4 continuum."""
+    dp = np.diff(p_half)
+    pbar = 0.5 * (p_half[1:] + p_half[:-1])
+    rng = np.random.default_rng(seed)
+    nu_l = rng.uniform(nu_lo, nu_hi, nlines)
+    a_l = 10.0 ** rng.uniform(-3.0, 1.0, nlines)
+    wz = dp * pbar
+    wz = wz / wz.sum()
+    tau_abs = np.zeros((nu.size, len(dp)))
+    for iz in range(len(dp)):
+        gam = 0.05 * pbar[iz] / 1013.0 + 0.002
+        lor = (gam / math.pi) / ((nu[:, None] - nu_l[None, :]) ** 2 + gam * gam)
+        tau_abs[:, iz] = wz[iz] * (lor * a_l[None, :]).sum(axis=1)
+    col = tau_abs.sum(axis=1)
+    tau_abs *= col_max / max(col.max(), 1e-300)
+    tau_abs += 1e-4 * wz[None, :]
+    return tau_abs
+
+
 def synthetic_o2a_model(nSpec: int = 10000, nstreams: int = 10, polarization_type: str = "Stokes_IQU",
                         aerosol: bool = True, float_type=np.float64, sza: float = 60.0,
                         vza=DEFAULT_VZA, vaz=DEFAULT_VAZ, albedo: float = 0.15,
@@ -383,20 +409,7 @@ def synthetic_o2a_model(nSpec: int = 10000, nstreams: int = 10, polarization_typ
     pbar = 0.5 * (p_half[1:] + p_half[:-1])
     tau_R = bodhaine_tau_rayleigh(wl, p_half[-1])
     tau_rayl = tau_R[:, None] * (dp / dp.sum())[None, :]
-    rng = np.random.default_rng(seed)
-    nlines = 60
-    nu_l = rng.uniform(12900.0, 13180.0, nlines)
-    a_l = 10.0 ** rng.uniform(-3.0, 1.0, nlines)
-    wz = dp * pbar
-    wz = wz / wz.sum()
-    tau_abs = np.zeros((nSpec, len(dp)))
-    for iz in range(len(dp)):
-        gam = 0.05 * pbar[iz] / 1013.0 + 0.002
-        lor = (gam / math.pi) / ((nu[:, None] - nu_l[None, :]) ** 2 + gam * gam)
-        tau_abs[:, iz] = wz[iz] * (lor * a_l[None, :]).sum(axis=1)
-    col = tau_abs.sum(axis=1)
-    tau_abs *= 100.0 / max(col.max(), 1e-300)
-    tau_abs += 1e-4 * wz[None, :]
+    tau_abs = _synthetic_absorption(nu, p_half, seed, 12900.0, 13180.0, 100.0)
     aerosols, tau_aer = [], np.zeros((0, len(dp)))
     if aerosol:
         aerosols = [AerosolOptics(hg_greek(0.7, 2 * nstreams), 0.95, 0.0)]
@@ -405,6 +418,49 @@ def synthetic_o2a_model(nSpec: int = 10000, nstreams: int = 10, polarization_typ
     return RTModel(polarization_type, q, sza, list(vza), list(vaz), tau_rayl.astype(FT), tau_abs.astype(FT),
                    tau_aer, aerosols, get_greek_rayleigh(depol), albedo, derive_m_max(aerosols, nstreams),
                    1.0, RTNumericalParameters(), FT, nu)
+
+
+# config/ocean_coxmunk.yaml: atmospheric_profile.p (34 half levels -> 33 layers), geometry
+OCEAN_P_HALF = np.array([0.14, 0.22, 0.30, 0.39, 0.53, 0.71, 0.96, 1.28, 1.70, 2.27, 3.03, 4.03, 5.44, 7.26, 9.67, 12.90,
+                         17.23, 23.30, 31.00, 42.07, 56.09, 74.78, 99.69, 131.00, 176.85, 236.64, 314.58, 418.87,
+                         557.76, 735.00, 800.12, 849.00, 912.00, 980.00])
+OCEAN_VZA = (60.0, 45.0, 30.0, 15.0, 0.0, 15.0, 30.0, 45.0, 60.0)
+OCEAN_VAZ = (180.0, 180.0, 180.0, 180.0, 0.0, 0.0, 0.0, 0.0, 0.0)
+
+
+def synthetic_ocean_model(nSpec: int = 1000, nstreams: int = 20, polarization_type: str = "Stokes_IQU",
+                          aerosol: bool = True, wind_speed: float = 5.0, float_type=np.float64,
+                          ss_correction: bool = True, seed: int = 20251017) -> RTModel:
+    """BASELINE.json configs[2]: the scene of ``config/ocean_coxmunk.yaml`` (geometry sza 30, the nine viewing
+    angles, the 33-layer profile, a CoxMunkSurface at 5 m/s with whitecaps and shadowing, band around
+    19417.5 cm^-1 = 515 nm) with the polarized + aerosol, 20-stream settings of the benchmark row: 20 + 5
+    zero-weight nodes -> Nquad = 25 -> N = 75 (IQU) / 100 (IQUV), Fourier loop to 2*nstreams - 1 (Cox-Munk runs
+    to the stream cap, component_m_max.jl:72).  The spectral axis is a synthetic nSpec-point grid across the band
+    with pseudo-line absorption (column 1e-4 .. 3) so that layers differ spectrally."""
+    from .coxmunk import CoxMunkSurface, coxmunk_ss_correction, coxmunk_surface_rho
+    FT = float_type
+    pol_n = POL_N[polarization_type]
+    q = rt_set_streams(nstreams, 30.0, OCEAN_VZA, pol_n, FT)
+    nu = 19417.0 + np.arange(nSpec) / max(nSpec, 1)
+    wl = 1e4 / nu
+    dp = np.diff(OCEAN_P_HALF)
+    pbar = 0.5 * (OCEAN_P_HALF[1:] + OCEAN_P_HALF[:-1])
+    tau_R = bodhaine_tau_rayleigh(wl, OCEAN_P_HALF[-1])
+    tau_rayl = tau_R[:, None] * (dp / dp.sum())[None, :]
+    tau_abs = _synthetic_absorption(nu, OCEAN_P_HALF, seed, 19416.8, 19418.2, 3.0, nlines=24)
+    aerosols, tau_aer = [], np.zeros((0, len(dp)))
+    if aerosol:
+        aerosols = [AerosolOptics(hg_greek(0.7, 2 * nstreams), 0.95, 0.0)]
+        prof = np.exp(-0.5 * ((pbar - 900.0) / 50.0) ** 2) * dp
+        tau_aer = (0.3 * prof / prof.sum())[None, :]
+    m_max = 2 * nstreams - 1
+    surf = CoxMunkSurface(wind_speed)
+    model = RTModel(polarization_type, q, 30.0, list(OCEAN_VZA), list(OCEAN_VAZ), tau_rayl.astype(FT), tau_abs.astype(FT),
+                    tau_aer, aerosols, get_greek_rayleigh(0.0279), 0.0, m_max, 1.0, RTNumericalParameters(), FT, nu)
+    model.surface_rho = coxmunk_surface_rho(q, pol_n, m_max, surf)
+    if ss_correction:
+        model.ss_correction = coxmunk_ss_correction(surf, pol_n, OCEAN_VZA, OCEAN_VAZ, float(q.mu0), m_max)
+    return model
 
 
 # ----------------------------------------------------------------------------

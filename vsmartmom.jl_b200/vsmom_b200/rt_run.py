@@ -31,6 +31,7 @@ class PreparedColumn:
     vza_stream: np.ndarray
     vza_weight: np.ndarray
     surf_rho: Optional[torch.Tensor] = None      # (n_moments, N, N), memory order == Julia (N,N,n_moments)
+    ss_correction: Optional[np.ndarray] = None   # (pol_n, nVZA) float64, memory order == (nVZA, nStokes) column-major
 
 
 def z_tables(model: RTModel) -> tuple[np.ndarray, np.ndarray]:
@@ -61,8 +62,14 @@ def prepare(model: RTModel, device: torch.device | str = "cuda:0") -> PreparedCo
             raise ValueError(f"surface_rho must have shape (m_max+1, N, N) = {(model.m_max + 1, N, N)}, got {sr.shape}")
         # [m, j, i] <- rho_m[i, j]: column-major (N, N, n_moments) for the library
         rho = torch.from_numpy(np.ascontiguousarray(sr.transpose(0, 2, 1).astype(model.float_type))).to(device)
+    ss = None
+    if model.ss_correction is not None:
+        sc = np.asarray(model.ss_correction, np.float64)
+        if sc.shape != (len(model.vza), model.pol_n):
+            raise ValueError(f"ss_correction must have shape (nVZA, pol_n) = {(len(model.vza), model.pol_n)}, got {sc.shape}")
+        ss = np.ascontiguousarray(sc.T)
     return PreparedColumn(model, torch.from_numpy(Zpp).to(device), torch.from_numpy(Zmp).to(device),
-                          layer_control(model), stream, np.ascontiguousarray(w, dtype=np.float64), rho)
+                          layer_control(model), stream, np.ascontiguousarray(w, dtype=np.float64), rho, ss)
 
 
 def _f64p(a: np.ndarray):
@@ -111,6 +118,7 @@ def rt_column_device(ctx: _lib.Context, prep: PreparedColumn, tau_rayl: torch.Te
     d.N, d.nStokes, d.nSpec, d.Nz, d.nAer, d.nVZA = q.qp_muN.size, n, nS, Nz, nAer, nV
     d.n_moments, d.imu0, d.surface_kind = model.m_max + 1, q.imu0, (1 if prep.surf_rho is not None else 0)
     d.surf_rho = prep.surf_rho.data_ptr() if prep.surf_rho is not None else None
+    d.ss_correction = _f64p(prep.ss_correction) if prep.ss_correction is not None else None
     d.mu0, d.albedo, d.varpi_cabannes = float(q.mu0), float(model.albedo), float(model.varpi_cabannes)
     d.mu, d.wt, d.aer_omega, d.aer_ft, d.tau_aer = _f64p(mu), _f64p(wt), _f64p(om), _f64p(ft), _f64p(taer)
     d.vza_weight = _f64p(prep.vza_weight)
