@@ -9,11 +9,13 @@
 #include <algorithm>
 #include <map>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/vsmom_b200.h"
 #include "vsm_launch.cuh"
 #include "vsm_l0.cuh"
+#include "vsm_stream.cuh"
 
 using namespace vsm;
 
@@ -36,7 +38,8 @@ struct vsm_ctx {
     std::map<const void*, int> smem_set;    // largest dynamic shared-memory size already granted per kernel
     std::string err;
     // grow-only scratch
-    DevBuf consts, props, added, slabs, partial, counter, l0tmp, geom;
+    DevBuf consts, props, added, slabs, partial, counter, l0tmp, geom, surfpad;
+    int use_stream = 1;                     // streamed-operand kernels for N = 60 / 75 / 100 (VSM_DISABLE_STREAM=1 turns them off)
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float t_total = 0, t_layer = 0, t_add = 0;
     bool timing_valid = false;
@@ -137,6 +140,7 @@ extern "C" int vsm_create(vsm_ctx** out, int device, void* cuda_stream) {
     ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     ctx->ws_limit = 0;
     if (const char* e = getenv("VSM_DEBUG_LAYER_CTAS_PER_SM")) ctx->dbg_layer_ctas = atoi(e);
+    if (const char* e = getenv("VSM_DISABLE_STREAM")) ctx->use_stream = atoi(e) ? 0 : 1;
     *out = ctx;
     return VSM_OK;
 }
@@ -145,7 +149,7 @@ extern "C" int vsm_destroy(vsm_ctx* ctx) {
     if (!ctx) return VSM_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->consts, &ctx->props, &ctx->added, &ctx->slabs, &ctx->partial, &ctx->counter, &ctx->l0tmp, &ctx->geom};
+    DevBuf* bufs[] = {&ctx->consts, &ctx->props, &ctx->added, &ctx->slabs, &ctx->partial, &ctx->counter, &ctx->l0tmp, &ctx->geom, &ctx->surfpad};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->stage) cudaFreeHost(ctx->stage);
@@ -371,6 +375,24 @@ static int do_launch(vsm_ctx* ctx, bool layer, int tm, bool fast, int N, const C
     return VSM_OK;
 }
 
+// the streamed kernels when a descriptor is given (fp64 only), else the shared-memory-arena kernels
+template <typename T>
+static int launch_col(vsm_ctx* ctx, const StreamDesc* sd, bool layer, int tm, bool fast, int N, const ColArgs<T>& a,
+                      unsigned total, int grid, int threads, size_t smem) {
+    if constexpr (std::is_same<T, double>::value) {
+        if (sd) {
+            const cudaError_t e = layer ? sd->launch_layer(ctx->stream, a, total, grid) : sd->launch_adding(ctx->stream, a, total, grid);
+            ctx->launches++;
+            if (e != cudaSuccess) {
+                ctx->err = std::string(layer ? "k_layer_stream launch: " : "k_adding_stream launch: ") + cudaGetErrorString(e);
+                return VSM_ERR_CUDA;
+            }
+            return VSM_OK;
+        }
+    }
+    return do_launch<T>(ctx, layer, tm, fast, N, a, total, grid, threads, smem);
+}
+
 template <typename T>
 static void get_kernel_ptrs(int tm, bool fast, int N, const void** kl, const void** ka) {
     if (fast && N == 45) { kernel_ptrs<T, 0, 45>(kl, ka); return; }
@@ -507,10 +529,19 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
     if (lv + 1024 > smax) return fail(ctx, VSM_ERR_UNSUPPORTED, "rt_column: N too large");
     int l_mats = (int)std::min<size_t>(kLayerMats, (smax - lv) / msz);
     int a_mats = (int)std::min<size_t>(kAddMats, (smax - av) / msz);
-    const size_t l_smem = lv + (size_t)l_mats * msz;
+    size_t l_smem = lv + (size_t)l_mats * msz;
     size_t a_smem = av + (size_t)a_mats * msz;
-    const size_t l_slab = (size_t)(kLayerMats - l_mats) * msz, a_slab = (size_t)(kAddMats - a_mats) * msz;
-    bool fast = has_fast(N) && l_mats == kLayerMats;
+    size_t l_slab = (size_t)(kLayerMats - l_mats) * msz, a_slab = (size_t)(kAddMats - a_mats) * msz;
+    // streamed-operand kernels (vsm_stream.cuh): fp64, N = 60 / 75 / 100; every matrix in a zero-padded slab
+    const StreamDesc* sd = (std::is_same<T, double>::value && ctx->use_stream) ? stream_desc(N) : nullptr;
+    size_t mstride = (size_t)N * N;                       // elements per hand-off matrix
+    if (sd) {
+        l_smem = a_smem = sd->smem;
+        l_slab = (size_t)kStreamLayerMats * sd->MSZ * sizeof(T);
+        a_slab = (size_t)kStreamAddMats * sd->MSZ * sizeof(T);
+        mstride = (size_t)sd->MSZ;
+    }
+    bool fast = !sd && has_fast(N) && l_mats == kLayerMats;
     FastCfg fc{cfg.threads, cfg.threads, 0};
     if (fast) fc = fast_cfg<T, 45>();
     // the two-group adding kernel has its own arena (11 matrices)
@@ -520,19 +551,20 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
 
     if (fast && fc.adding_two_group) a_smem = a2_smem;
     const void* kl = nullptr; const void* ka = nullptr;
-    get_kernel_ptrs<T>(cfg.tm, fast, N, &kl, &ka);
+    if (sd) { kl = sd->k_layer; ka = sd->k_adding; }
+    else get_kernel_ptrs<T>(cfg.tm, fast, N, &kl, &ka);
     CK(set_smem(ctx, (const void*)kl, l_smem));
     CK(set_smem(ctx, (const void*)ka, a_smem));
     // CTA sizes: the specialised kernels fix theirs at compile time
-    const int l_threads = fast ? fc.layer_threads : cfg.threads;
-    const int a_threads = fast ? fc.adding_threads : cfg.threads;
+    const int l_threads = sd ? sd->threads : (fast ? fc.layer_threads : cfg.threads);
+    const int a_threads = sd ? sd->threads : (fast ? fc.adding_threads : cfg.threads);
     const int l_occ = occupancy<T>(kl, l_threads, l_smem);
     const int a_occ = occupancy<T>(ka, a_threads, a_smem);
     int l_grid_max = ctx->num_sms * l_occ, a_grid_max = ctx->num_sms * a_occ;
     if (ctx->dbg_layer_ctas > 0) l_grid_max = ctx->num_sms * std::max(1, std::min(l_occ, ctx->dbg_layer_ctas));
 
     // ---- workspace plan: chunk over spectral points and moments
-    const size_t add_item = (size_t)nSl * ((size_t)2 * N * N + 2 * N) * sizeof(T);
+    const size_t add_item = (size_t)nSl * ((size_t)2 * mstride + 2 * N) * sizeof(T);
     const size_t props_pt = ((size_t)Nz * (2 + nC) + (Nz + 1)) * sizeof(T);
     const size_t part_pt = (size_t)3 * nM * nOut * sizeof(T);
     uint64_t limit = ctx->ws_limit ? ctx->ws_limit : (uint64_t)24 << 30;
@@ -569,6 +601,20 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
     if ((rc = ensure(ctx, ctx->partial, (size_t)part_pt * chunk + (size_t)2 * nSt * chunk * sizeof(T)))) return rc;
     if ((rc = ensure(ctx, ctx->slabs, (size_t)std::max<uint64_t>(slab_bytes, 16)))) return rc;
     if ((rc = ensure(ctx, ctx->counter, 256))) return rc;
+    T* surf_pad = nullptr;
+    if (sd) {
+        // the padding of every slab matrix is an invariant of the streamed kernels: start from zeros
+        CK(cudaMemsetAsync(ctx->slabs.p, 0, (size_t)slab_bytes, ctx->stream));
+        if (surf_rho) {
+            if ((rc = ensure(ctx, ctx->surfpad, (size_t)nM * sd->MSZ * sizeof(T)))) return rc;
+            surf_pad = (T*)ctx->surfpad.p;
+            const size_t ne = (size_t)nM * sd->MSZ;
+            k_surf_pad<T><<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(N, sd->LD, sd->MSZ, nM, (const T*)surf_rho,
+                                                                                cT + o_mu, cT + o_wt, surf_pad);
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
+    }
 
     // timing events
     ctx->ev_used = 0;
@@ -578,7 +624,6 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
     GET_EVENT(ev_end);
     CK(cudaEventRecord(ev_begin, ctx->stream));
 
-    const size_t NN = (size_t)N * N;
     for (int n0 = 0; n0 < nSpec; n0 += chunk) {
         const int nS = std::min(chunk, nSpec - n0);
         // --- k_props
@@ -620,13 +665,14 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
         a.bhr_uw = cb_uw; a.bhr_dw = cb_dw;
         a.st_Rmp = st_Rmp; a.st_Tpp = st_Tpp; a.st_Jm = st_Jm; a.st_Jp = st_Jp;
         a.st_off = (size_t)n0; a.st_nspec = (size_t)nSpec;
+        a.add_mstride = mstride; a.surf_pad = surf_pad;
 
         for (int m0 = 0; m0 < nM; m0 += Mb) {
             const int mb = std::min(Mb, nM - m0);
             a.m0 = m0; a.Mb = mb;
             T* ad = (T*)ctx->added.p;
             const size_t slots = (size_t)mb * nSl * nS;
-            a.add_r = ad; a.add_t = ad + slots * NN; a.add_jp = ad + 2 * slots * NN; a.add_jm = a.add_jp + slots * N;
+            a.add_r = ad; a.add_t = ad + slots * mstride; a.add_jp = ad + 2 * slots * mstride; a.add_jm = a.add_jp + slots * N;
             // --- k_layer
             if (nSched > 0) {
                 const unsigned total = (unsigned)((size_t)nSched * mb * nS);
@@ -636,7 +682,7 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
                 GET_EVENT(e0);
                 GET_EVENT(e1);
                 CK(cudaEventRecord(e0, ctx->stream));
-                rc = do_launch<T>(ctx, true, cfg.tm, fast, N, a, total, grid, l_threads, l_smem);
+                rc = launch_col<T>(ctx, sd, true, cfg.tm, fast, N, a, total, grid, l_threads, l_smem);
                 if (rc) return rc;
                 CK(cudaEventRecord(e1, ctx->stream));
                 ctx->seg_layer.push_back({e0, e1});
@@ -652,7 +698,7 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
                 GET_EVENT(e0);
                 GET_EVENT(e1);
                 CK(cudaEventRecord(e0, ctx->stream));
-                rc = do_launch<T>(ctx, false, cfg.tm, fast, N, a, total, grid, a_threads, a_smem);
+                rc = launch_col<T>(ctx, sd, false, cfg.tm, fast, N, a, total, grid, a_threads, a_smem);
                 if (rc) return rc;
                 CK(cudaEventRecord(e1, ctx->stream));
                 ctx->seg_add.push_back({e0, e1});

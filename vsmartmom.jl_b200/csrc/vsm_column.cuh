@@ -160,6 +160,8 @@ struct ColArgs {
     const unsigned char* gcls;                        // k_geom branch classes (N,N) + [N]
     // added-layer scratch: slot = (mi*n_sched_layers + sched_idx[iz])*nS + p   (scattering layers only)
     T* add_r; T* add_t; T* add_jp; T* add_jm;
+    size_t add_mstride;      // elements per hand-off matrix: N*N (dense) or LD*NP (streamed kernels, padded layout)
+    const T* surf_pad;       // streamed kernels: R_surf Diagonal(mu w) per moment in the padded layout, or null
     // spill slabs and the work counter
     T* slab; size_t slab_stride;
     unsigned int* counter;
@@ -219,14 +221,14 @@ __global__ void k_geom(int n, int nStokes, int istart, const T* __restrict__ mu,
 
 // Scratch: rowtmp >= 3n + 1 (a_i, e_i, em1_i, att) ; cap >= 2*nStokes*n (the solar columns of the mixed,
 // scaled Z matrices, captured in the element loop for the source vectors).
-template <typename T, int NN>
+template <typename T, int NN, int LDO = 0>
 __device__ __forceinline__ void elemental_fill(const ColArgs<T>& a, int m, int nd, T dtau, T varpi,
                                                T tausum, const T* __restrict__ Wc,
                                                const T* __restrict__ Zpp, const T* __restrict__ Zmp,
                                                size_t zstride, const T* __restrict__ F0n,
                                                const uint32_t* __restrict__ dmask,
                                                T* r, T* t, T* jp, T* jm, T* rowtmp, T* cap) {
-    const int n = NN ? NN : a.N, ld = NN ? (NN | 1) : a.ld, nC = a.nC;
+    const int n = NN ? NN : a.N, ld = LDO ? LDO : (NN ? (NN | 1) : a.ld), nC = a.nC;
     const int nn = n * n;
     const T wsc = (m == 0) ? T(0.5) : T(0.25);       // scaled_weights / fourier_weight
     const unsigned wbit = (m == 0) ? 4u : 8u;

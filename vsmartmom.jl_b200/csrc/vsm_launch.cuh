@@ -24,6 +24,22 @@ struct FastCfg {
 template <typename T, int NN>
 FastCfg fast_cfg();
 
+// streamed-operand kernels (vsm_stream.cuh), fp64 only: one descriptor per instantiated N
+struct StreamDesc {
+    int N, LD, NP, MSZ;            // padded layout of every matrix (slab and hand-off): LD x NP elements
+    int threads, layer_minb;
+    size_t smem;
+    const void* k_layer; const void* k_adding;
+    cudaError_t (*launch_layer)(cudaStream_t, const ColArgs<double>&, unsigned total, int grid);
+    cudaError_t (*launch_adding)(cudaStream_t, const ColArgs<double>&, unsigned total, int grid);
+};
+const StreamDesc* stream_desc_60();
+const StreamDesc* stream_desc_75();
+const StreamDesc* stream_desc_100();
+inline const StreamDesc* stream_desc(int N) {
+    return N == 60 ? stream_desc_60() : N == 75 ? stream_desc_75() : N == 100 ? stream_desc_100() : nullptr;
+}
+
 template <typename T, int TM, int NN, int NTHR, int TMI = TM, int KS = 1>
 struct OpsSel { using type = OpsFast<T, TM, NN, NTHR, 0, TMI, KS>; };
 template <typename T, int TM, int NTHR, int TMI, int KS>
