@@ -4,15 +4,23 @@
     python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun)
     python bench.py --impl reference ...                      (CPU arm: the oracle port of the
                                                                reference's CPU path, all host cores)
+    python bench.py --config 3 [--pol IQUV] [--nspec 1000]    (BASELINE.json configs[2]: ocean_coxmunk, N = 75 / 100)
+    python bench.py --scaling strong --nspec-total 80000      (fixed band cut into N shards)
 
-A "step" is one rt_run over one batch of synthetic spectral points: every Fourier
-moment, every layer, surface, post-processing.  The workload is BASELINE.json
-configs[1]: default_parameters() geometry/profile, Stokes_IQU, 10 streams, 34
-layers, Rayleigh + one aerosol + Lambertian surface, ~10k spectral points per GPU.
-Weak scaling: every rank gets its own nSpec-point shard of one nSpec*N band; the
-layer control flow (ndoubl / scatter / interface) is reduced over the FULL band on
-the host, each rank runs its shard with no data-path collective, and one NCCL
-all-gather of R_SFI/T_SFI closes the step.
+A "step" is one rt_run over one batch of synthetic spectral points: every Fourier moment, every
+layer, surface, post-processing.  Default workload = BASELINE.json configs[1]: default_parameters()
+geometry/profile, Stokes_IQU, 10 streams (N = 45), 34 layers, Rayleigh + one aerosol + Lambertian
+surface, 10k spectral points per GPU.
+
+Scaling.  The layer control flow (ndoubl / scatter / interface) is a reduction over the FULL band,
+so it is computed once on the host and every rank runs its shard with no data-path collective; ONE
+NCCL all-gather of the packed (R_SFI, T_SFI) closes the step.  Weak scaling tiles the single-GPU
+band N times (every rank gets the same points, so the sum of doublings and the per-rank work are
+independent of N -- the round-1 bench extended the band instead, which made the work per point grow
+with N).  --scaling strong cuts one fixed band into N shards.
+
+After the timed loop the benchmarked output itself is verified: random points of every rank's
+shard (after the gather) are recomputed by the CPU oracle -> "parity_check".
 """
 import argparse
 import json
@@ -31,6 +39,7 @@ import numpy as np
 
 METRIC = "spectral points/sec in rt_run (O2-A band, vector I/Q/U)"
 UNIT = "spectral_points/s"
+INVERSE_MODE = "adaptive (Neumann order 2/3/4/8 when ||A||_F^K < 1e-20, else Gauss-Jordan elimination)"
 
 
 def parse():
@@ -39,39 +48,98 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--nspec", type=int, default=10000, help="spectral points per GPU")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3],
+                    help="2: BASELINE configs[1] (O2-A, N=45); 3: configs[2] (ocean_coxmunk, 20 streams, N=75/100)")
+    ap.add_argument("--pol", default=None, choices=["IQU", "IQUV"], help="config 3 polarization (default IQU -> N=75)")
+    ap.add_argument("--nspec", type=int, default=None, help="spectral points per GPU (default 10000 / config 3: 1000)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--nspec-total", type=int, default=None, help="--scaling strong: size of the fixed band")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-aerosol", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--parity-points", type=int, default=None, help="points recomputed by the oracle (default 64 / config 3: 16)")
     ap.add_argument("--clock-sample-ms", type=int, default=1000, help="nvidia-smi polling period during the timed region")
     ap.add_argument("--no-gj-compare", action="store_true",
                     help="skip the extra Gauss-Jordan-only steps (used for ncu launch lists)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.nspec is None:
+        a.nspec = 10000 if a.config == 2 else 1000
+    if a.pol is None:
+        a.pol = "IQU"
+    if a.parity_points is None:
+        a.parity_points = 64 if a.config == 2 else 16
+    return a
 
 
-def workload_config(args, world):
-    return {"workload": "configs[1]: default_parameters() O2-A band, Stokes_IQU, nstreams=10 (N=45), 34 layers, "
-                        "Rayleigh+1 aerosol (HG g=0.7, 20 Greek terms -> 20 Fourier moments), Lambertian 0.15",
-            "nSpec_per_gpu": args.nspec, "nSpec_total": args.nspec * world, "N": 45, "Nz": 34,
-            "n_moments": 3 if args.no_aerosol else 20, "parallelism": f"nSpec-shard x{world}",
-            "l2": "working set (added-layer scratch, GBs per moment) >> 126 MB L2; a 256 MiB buffer is also "
+def build_model(args, nspec, FT):
+    import vsmom_b200 as vb
+    if args.config == 2:
+        return vb.synthetic_o2a_model(nSpec=nspec, aerosol=not args.no_aerosol, float_type=FT)
+    return vb.synthetic_ocean_model(nSpec=nspec, nstreams=20, polarization_type="Stokes_" + args.pol,
+                                    aerosol=not args.no_aerosol, float_type=FT)
+
+
+def tile_model(model, reps):
+    """The same band `reps` times along the spectral axis (weak scaling with constant work per point)."""
+    import copy
+    if reps == 1:
+        return model
+    m = copy.copy(model)
+    m.tau_rayl = np.tile(model.tau_rayl, (reps, 1))
+    m.tau_abs = np.tile(model.tau_abs, (reps, 1))
+    if model.spec_grid is not None:
+        m.spec_grid = np.tile(model.spec_grid, reps)
+    return m
+
+
+def workload_config(args, world, model=None):
+    if args.config == 2:
+        w = ("configs[1]: default_parameters() O2-A band, Stokes_IQU, nstreams=10 (N=45), 34 layers, "
+             "Rayleigh+1 aerosol (HG g=0.7, 20 Greek terms -> 20 Fourier moments), Lambertian 0.15")
+        N, Nz, nM = 45, 34, (3 if args.no_aerosol else 20)
+    else:
+        N = 75 if args.pol == "IQU" else 100
+        w = (f"configs[2]: ocean_coxmunk.yaml scene (sza 30, 9 viewing angles, 33 layers, CoxMunkSurface 5 m/s with "
+             f"whitecaps + shadowing + TMS correction), Stokes_{args.pol}, nstreams=20 (N={N}), Rayleigh+1 aerosol, "
+             "40 Fourier moments")
+        Nz, nM = 33, 40
+    total = args.nspec_total if (args.scaling == "strong" and args.nspec_total) else args.nspec * world
+    return {"workload": w, "nSpec_per_gpu": total // world if args.scaling == "strong" else args.nspec,
+            "nSpec_total": total, "N": N, "Nz": Nz, "n_moments": nM, "parallelism": f"nSpec-shard x{world}",
+            "scaling_mode": ("weak: the single-GPU band tiled x%d (constant sum of doublings)" % world)
+            if args.scaling == "weak" else "strong: one fixed band cut into contiguous shards",
+            "inverse_mode": INVERSE_MODE,
+            "l2": "working set (added-layer hand-off, GBs per moment batch) >> 126 MB L2; a 256 MiB buffer is also "
                   "rewritten between timed iterations"}
 
 
 # ----------------------------------------------------------------------------
-# CPU arm / cpu_baseline: the oracle port on all host cores (the only place bench.py
+# CPU arm / cpu_baseline / parity check: the oracle port on all host cores (the only place bench.py
 # touches oracle/)
 # ----------------------------------------------------------------------------
-def cpu_points_per_sec(model, seconds, steps=1, warmup=0, log=None):
+def _oracle_pool(model):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import vsmom_oracle as orc
     from helpers import to_oracle
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     om = to_oracle(model)
-    prep = orc.prepare(om)
-    pool = orc.ProcessPoolBaseline(om, cores, prep)
-    chunk = 8
+    return orc.ProcessPoolBaseline(om, cores, orc.prepare(om)), cores
+
+
+def _blas_vendor():
+    try:
+        from threadpoolctl import threadpool_info
+        return ", ".join(sorted({f"{i.get('internal_api')} {i.get('version')}" for i in threadpool_info()
+                                 if i.get("user_api") == "blas"})) or "unknown"
+    except Exception:
+        return "unknown"
+
+
+def cpu_points_per_sec(model, seconds, steps=1, warmup=0):
+    pool, cores = _oracle_pool(model)
+    chunk = 8 if model.quad_points.qp_muN.size <= 48 else 1
     rng = np.random.default_rng(0)
     pick = lambda n: np.sort(rng.choice(model.nSpec, size=min(n, model.nSpec), replace=False))
     t0 = time.perf_counter()
@@ -88,11 +156,31 @@ def cpu_points_per_sec(model, seconds, steps=1, warmup=0, log=None):
         times.append(time.perf_counter() - t0)
     pool.close()
     total = sum(times)
-    return {"value": n * steps / total, "unit": UNIT, "cores": cores, "kind": "port",
+    v = n * steps / total
+    return {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "per_core": v / cores, "blas": _blas_vendor(),
             "sample": f"{n} of {model.nSpec} spectral points per step (random subset of the same band, all "
-                      f"{model.m_max + 1} moments, {model.Nz} layers), {steps} step(s), {total:.1f} s; NumPy/OpenBLAS "
-                      f"oracle, one forked worker per core, BLAS threads=1, dtype {np.dtype(model.float_type).name}",
+                      f"{model.m_max + 1} moments, {model.Nz} layers), {steps} step(s), {total:.1f} s; NumPy oracle "
+                      f"(per-slice gemm + getrf/getri), one forked worker per core, BLAS threads=1, dtype "
+                      f"{np.dtype(model.float_type).name}",
             "ms_per_step": 1e3 * total / steps, "points_per_step": n}
+
+
+def parity_check(model, R, T, npts, tol):
+    """Recompute `npts` random points of the benchmarked band with the CPU oracle and compare with the
+    benchmarked output R, T (nVZA, pol_n, nSpec): max|d|/max|ref| per array."""
+    pool, _ = _oracle_pool(model)
+    rng = np.random.default_rng(12345)
+    idx = np.sort(rng.choice(model.nSpec, size=min(npts, model.nSpec), replace=False))
+    t0 = time.perf_counter()
+    Rr, Tr = pool.run(idx, 1)
+    dt = time.perf_counter() - t0
+    pool.close()
+    eR = float(np.max(np.abs(R[..., idx] - Rr)) / np.max(np.abs(Rr)))
+    eT = float(np.max(np.abs(T[..., idx] - Tr)) / np.max(np.abs(Tr)))
+    return {"max_rel": max(eR, eT), "max_rel_R_SFI": eR, "max_rel_T_SFI": eT, "n": int(idx.size), "tol": tol,
+            "ok": bool(max(eR, eT) <= tol and np.isfinite(R).all() and np.isfinite(T).all()),
+            "what": "random points of the benchmarked band (all ranks' shards, after the gather) vs the CPU oracle",
+            "oracle_s": round(dt, 1)}
 
 
 def run_reference(args):
@@ -100,18 +188,19 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    import vsmom_b200 as vb
     FT = np.float64 if args.dtype == "f64" else np.float32
-    model = vb.synthetic_o2a_model(nSpec=args.nspec, aerosol=not args.no_aerosol, float_type=FT)
+    model = build_model(args, args.nspec, FT)
     r = cpu_points_per_sec(model, args.cpu_seconds, steps=args.steps, warmup=min(args.warmup, 1))
+    cfg = workload_config(args, world)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": workload_config(args, world),
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "scaling": args.scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": cfg,
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "per_core", "blas")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference arm = CPU port of the reference's rt_run hot path (the reference is pure Julia and "
-                    "cannot run here); each step is a bounded sample of the workload"}
+                    "cannot run here); each step is a bounded sample of the workload; the CPU port always inverts "
+                    "with LAPACK getrf/getri (config.inverse_mode describes the B200 arm)"}
     print(json.dumps(line), flush=True)
 
 
@@ -166,12 +255,13 @@ class ClockSampler:
 # ----------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------
-def alg_flops(N, nd_sum, n_scat, n_adds11, n_moments, surface_adds=1):
+def alg_flops(N, nd_sum, n_scat, n_adds11, n_moments, surface_moments):
     """Algorithmic flops per spectral point: doubling (12N^3+8N^2)/iteration,
-    _11 interaction (24N^3+12N^2), elemental ~40 N^2 per layer."""
+    _11 interaction (24N^3+12N^2), elemental ~40 N^2 per layer; the surface adds one interaction per
+    moment that has a reflecting surface (Lambertian: m = 0 only; BRDF: every moment)."""
     layer = (12 * N ** 3 + 8 * N ** 2) * nd_sum + 40 * N ** 2 * n_scat
     add = (24 * N ** 3 + 12 * N ** 2) * n_adds11
-    return n_moments * layer, n_moments * add + surface_adds * (24 * N ** 3 + 12 * N ** 2)
+    return n_moments * layer, n_moments * add + surface_moments * (24 * N ** 3 + 12 * N ** 2)
 
 
 def run_b200(args):
@@ -179,6 +269,7 @@ def run_b200(args):
     import torch.distributed as dist
     import vsmom_b200 as vb
     from vsmom_b200 import _lib, rt_run as rr
+    from vsmom_b200.sharding import shard_bounds
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -192,44 +283,59 @@ def run_b200(args):
     FT = np.float64 if args.dtype == "f64" else np.float32
     tdt = torch.float64 if FT == np.float64 else torch.float32
 
-    # one band of nspec*world points; control flow from the FULL band, then shard
-    full = vb.synthetic_o2a_model(nSpec=args.nspec * world, aerosol=not args.no_aerosol, float_type=FT)
+    # the band: weak = the single-GPU band tiled `world` times; strong = one fixed band
+    if args.scaling == "strong":
+        total = args.nspec_total or args.nspec * world
+        full = build_model(args, total, FT)
+    else:
+        full = tile_model(build_model(args, args.nspec, FT), world)
+        total = full.nSpec
+    bounds = shard_bounds(total, world)
+    lo, hi = bounds[rank]
+    nS, n, nV = hi - lo, full.pol_n, len(full.vza)
+    nmax = max(b[1] - b[0] for b in bounds)
     prep = rr.prepare(full, dev)                       # Z tables + full-band layer control
-    lo, hi = rank * args.nspec, (rank + 1) * args.nspec
-    nS, n, nV = args.nspec, full.pol_n, len(full.vza)
     tr_h = torch.from_numpy(np.ascontiguousarray(full.tau_rayl[lo:hi].T)).pin_memory()
     ta_h = torch.from_numpy(np.ascontiguousarray(full.tau_abs[lo:hi].T)).pin_memory()
     f0 = np.zeros((nS, n), FT); f0[:, 0] = 1
     f0_h = torch.from_numpy(f0).pin_memory()
-    R_h = torch.empty((nS * world, n, nV), dtype=tdt).pin_memory()
-    T_h = torch.empty((nS * world, n, nV), dtype=tdt).pin_memory()
+    k = n * nV
 
     ctx = _lib.Context(local, torch.cuda.current_stream().cuda_stream)
     tr_d, ta_d, f0_d = tr_h.to(dev), ta_h.to(dev), f0_h.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    Rg = torch.empty((world * nS, n, nV), dtype=tdt, device=dev) if world > 1 else None
-    Tg = torch.empty_like(Rg) if world > 1 else None
-
+    pack = torch.zeros((nmax, 2 * k), dtype=tdt, device=dev)          # this rank's (R_SFI | T_SFI), padded to the largest shard
+    gathered = torch.empty((world * nmax, 2 * k), dtype=tdt, device=dev) if world > 1 else None
     done = torch.cuda.Event(blocking=True)
 
     def step_device():
         R, T, _, _, _ = rr.rt_column_device(ctx, prep, tr_d, ta_d, f0_d, want_hdr=False)
         if world > 1:                                  # the single gather of R/T at the end of rt_run
-            dist.all_gather_into_tensor(Rg, R)
-            dist.all_gather_into_tensor(Tg, T)
-            return Rg, Tg
+            pack[:nS, :k] = R.reshape(nS, k)
+            pack[:nS, k:] = T.reshape(nS, k)
+            dist.all_gather_into_tensor(gathered, pack)
+            return gathered
+        return R, T
+
+    def full_output():
+        """(nVZA, pol_n, nSpec_total) R_SFI, T_SFI of the whole band from the last step (host)."""
+        out = step_device()
+        torch.cuda.synchronize()
+        if world > 1:
+            g = out.cpu().numpy().reshape(world, nmax, 2 * k)
+            rows = np.concatenate([g[r, :bounds[r][1] - bounds[r][0]] for r in range(world)], axis=0)
+        else:
+            rows = torch.cat([out[0].reshape(nS, k), out[1].reshape(nS, k)], dim=1).cpu().numpy()
+        R = rows[:, :k].reshape(-1, n, nV).transpose(2, 1, 0)
+        T = rows[:, k:].reshape(-1, n, nV).transpose(2, 1, 0)
         return R, T
 
     def step_e2e():
-        a = tr_h.to(dev, non_blocking=True); b = ta_h.to(dev, non_blocking=True); c = f0_h.to(dev, non_blocking=True)
-        R, T, _, _, _ = rr.rt_column_device(ctx, prep, a, b, c, want_hdr=False)
+        # the public call: NumPy model in, NumPy out -- prepare() (Z tables, full-band control flow), pageable/pinned
+        # H2D of this rank's shard, the column, the gather, D2H
         if world > 1:
-            dist.all_gather_into_tensor(Rg, R)
-            dist.all_gather_into_tensor(Tg, T)
-            R, T = Rg, Tg
-        R_h.copy_(R, non_blocking=True); T_h.copy_(T, non_blocking=True)
-        done.record()
-        done.synchronize()          # blocking wait (the host thread sleeps instead of spinning)
+            return rr.rt_run_sharded(full, ctx, device=str(dev))
+        return rr.rt_run(full, ctx, device=str(dev))
 
     def barrier():
         # sleep on a blocking event first: a host thread that spins for seconds in
@@ -256,15 +362,27 @@ def run_b200(args):
     e1.record()
     barrier()
     clocks = sampler.stop()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    my_ms = float(e0.elapsed_time(e1))
+    all_ms = torch.tensor([my_ms], device=dev, dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
+        lst = [torch.zeros_like(all_ms) for _ in range(world)]
+        dist.all_gather(lst, all_ms)
+        rank_ms = [float(x.item()) for x in lst]
+    else:
+        rank_ms = [my_ms]
+    ms = max(rank_ms)
     launches = ctx.kernel_launches - launches0
     t_total, t_layer, t_add = ctx.last_column_ms()
     n_layer_launches, n_add_launches = ctx.last_column_launches()
+    col_ms = torch.tensor([t_total, t_layer, t_add], device=dev, dtype=torch.float64)
+    if world > 1:
+        lst = [torch.zeros_like(col_ms) for _ in range(world)]
+        dist.all_gather(lst, col_ms)
+        col_all = [[float(v) for v in x.tolist()] for x in lst]
+    else:
+        col_all = [[t_total, t_layer, t_add]]
 
-    # e2e through the public host-buffer path
+    # e2e through the public host-buffer call
     step_e2e()
     barrier()
     t0 = time.perf_counter()
@@ -277,7 +395,7 @@ def run_b200(args):
     e2e_s = float(e2e_s.item())
 
     # the same step with the adaptive inverse switched off (Gauss-Jordan elimination for every
-    # (I - A)^-1, the reference's getrf/getri route): reported beside the headline, not as it
+    # (I - A)^-1, the reference's getrf/getri route): reported inside `roofline`, not as the headline
     gj = None
     if world == 1 and FT == np.float64 and not args.no_gj_compare:
         ctx.set_inverse_mode(0)
@@ -295,12 +413,16 @@ def run_b200(args):
         gj = {"value": nS / (gms * 1e-3), "ms_per_step": gms, "layer_ms": gt[1], "adding_ms": gt[2]}
         ctx.set_inverse_mode(1)
 
+    # the benchmarked output itself, gathered
+    R_full, T_full = full_output()
+
     if rank == 0:
         ctl = prep.ctl
         N = full.quad_points.qp_muN.size
         nM = full.m_max + 1
         n11 = int(np.sum(np.asarray(ctl.iface)[1:] == 3))
-        f_layer, f_add = alg_flops(N, int(ctl.ndoubl.sum()), int(ctl.scatter.sum()), n11, nM)
+        f_layer, f_add = alg_flops(N, int(ctl.ndoubl.sum()), int(ctl.scatter.sum()), n11, nM,
+                                   nM if full.surface_rho is not None else 1)
         esz = 8 if FT == np.float64 else 4
         peak_tf = ctx.measure_fma_peak(0 if FT == np.float64 else 1)
         ach = f_layer * nS / n_layer_launches / (t_layer / n_layer_launches * 1e-3) / 1e12
@@ -312,21 +434,30 @@ def run_b200(args):
         traffic = None
         try:   # dram bytes of the dominant kernel from the committed ncu --set full capture, scaled to this launch
             tj = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
-            traffic = tj["bytes_per_point_moment"] * nS * nM / n_layer_launches
+            key = "bytes_per_point_moment" if args.config == 2 else f"bytes_per_point_moment_config3_{args.pol}"
+            traffic = tj[key] * nS * nM / n_layer_launches
         except Exception:
             pass
-        value = nS * world * args.steps / (ms * 1e-3)
+        value = total * args.steps / (ms * 1e-3)
+        h2d = int(full.tau_rayl[lo:hi].size + full.tau_abs[lo:hi].size + f0.size) * esz
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, world),
             "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": nS * world * args.steps / e2e_s, "unit": UNIT,
-                    "h2d_bytes_per_step": int(tr_h.numel() + ta_h.numel() + f0_h.numel()) * esz,
-                    "d2h_bytes_per_step": int(R_h.numel() + T_h.numel()) * esz,
-                    "path": "pinned host tau_rayl/tau_abs/F0 -> H2D -> vsm_rt_column -> (all-gather) -> D2H R_SFI/T_SFI"},
+            "e2e": {"value": total * args.steps / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": int(total * (3 * k + 2 * n)) * esz,
+                    "path": "vsmom_b200.rt_run(model) / rt_run_sharded(model): prepare() (Z-moment tables + full-band layer "
+                            "control on the host) -> H2D tau_rayl/tau_abs/F0 -> vsm_rt_column -> (one all-gather) -> D2H "
+                            "R_SFI/T_SFI/hdr/bhr -> NumPy"},
+            "per_rank": {"step_ms_min": min(rank_ms) / args.steps, "step_ms_max": max(rank_ms) / args.steps,
+                         "column_ms": [c[0] for c in col_all], "layer_ms": [c[1] for c in col_all],
+                         "adding_ms": [c[2] for c in col_all],
+                         "note": "step = column + gather; the step time is the slowest rank's"},
             "roofline": {
-                "bound": "tensor", "kernel": "k_layer (elemental + doubling, fused)",
+                "bound": "tensor", "kernel": "k_layer (elemental + doubling, fused)" if args.config == 2 else
+                "k_layer_stream (elemental + doubling, operands streamed from L2-resident slabs)",
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
                 "traffic": traffic,
                 "peak_source": f"fp{esz * 8} FMA issue-rate microbenchmark measured live on this GPU "
@@ -336,23 +467,27 @@ def run_b200(args):
                 "flop_accounting": "algorithmic = the reference algorithm (every (I-A)^-1 counted as one 2N^3 "
                                    "inverse). With inverse_mode=adaptive the kernels execute 0 / 4N^3 / 8N^3 flops "
                                    "for it instead when ||A||_F allows a Neumann sum of order 2 / 4 / 8 "
-                                   "(remainder < 1e-20), and 21% more on every product for the 45->48 tile padding.",
+                                   "(remainder < 1e-20), and up to 21% more on every product for the padding to 8x8 tiles.",
                 "alg_flops_per_point": f_layer + f_add, "alg_flops_per_launch": f_layer * nS / n_layer_launches,
                 "launch_ms": t_layer / n_layer_launches, "launches_per_step": n_layer_launches,
                 "kernel_share_of_step": t_layer / t_total,
+                "whole_step_frac": ((f_layer + f_add) * nS / (t_total * 1e-3) / 1e12) / peak_tf if peak_tf else None,
                 "hbm_frac_of_measured": (nS * (full.Nz * 2 + nV * n * 2) * esz / (t_total * 1e-3) / 1e9) / peaks["hbm_gbs"]
                 if peaks.get("hbm_gbs") else None,
-                "adding_kernel": {"achieved": f_add * nS / (t_add * 1e-3) / 1e12, "ms_per_step": t_add},
+                "adding_kernel": {"achieved": f_add * nS / (t_add * 1e-3) / 1e12, "ms_per_step": t_add,
+                                  "frac": (f_add * nS / (t_add * 1e-3) / 1e12) / peak_tf if peak_tf else None},
             },
         }
-        line["config"]["inverse_mode"] = "adaptive (Neumann order 2/3/4/8 when ||A||_F^K < 1e-20, else blocked Gauss-Jordan)"
         if gj is not None:
-            gj["roofline_frac"] = (f_layer * nS / (gj.pop("layer_ms") * 1e-3) / 1e12) / peak_tf if peak_tf else None
-            gj["adding_ms"] = gj["adding_ms"]
-            line["gauss_jordan_only"] = gj
+            gj["frac"] = (f_layer * nS / (gj.pop("layer_ms") * 1e-3) / 1e12) / peak_tf if peak_tf else None
+            gj["what"] = "the same step with vsm_set_inverse_mode(0): every (I-A)^-1 by elimination (no Neumann exit)"
+            line["roofline"]["gauss_jordan_only"] = gj
+        if not args.no_parity_check:
+            tol = 1e-9 if FT == np.float64 else 1e-2
+            line["parity_check"] = parity_check(full, R_full, T_full, args.parity_points, tol)
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_points_per_sec(full, args.cpu_seconds)
-            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"] = {k_: r[k_] for k_ in ("value", "unit", "cores", "kind", "sample", "per_core", "blas")}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

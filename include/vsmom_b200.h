@@ -188,6 +188,27 @@ int vsm_rt_column_streams_f64(vsm_ctx*, const vsm_column_desc*, double* R_SFI, d
                               double* bhr_uw, double* bhr_dw, double* Rmp, double* Tpp, double* Jm, double* Jp);
 int vsm_rt_column_streams_f32(vsm_ctx*, const vsm_column_desc*, float* R_SFI, float* T_SFI, float* hdr,
                               float* bhr_uw, float* bhr_dw, float* Rmp, float* Tpp, float* Jm, float* Jp);
+/* -- L2, LinMode: forward R_SFI/T_SFI and the analytic Jacobians for P parameters -- drop-in for the body of
+ * rt_run(model, lin_model, ...) src/CoreRT/rt_run_lin.jl:102-326 with rt_kernel! of CoreKernel/rt_kernel_lin.jl:50-180
+ * (lin elemental!, doubling_allparams!, lin interaction_helper!, lin postprocessing_vza!).  A parameter p is given
+ * by the derivatives of the column inputs with respect to it (the reference's chain rule from its
+ * 7*NAer + NGas + NSurf parameter vector, parameter_layout.jl:32-34, to tau-dot / varpi-dot / Z-dot per layer is
+ * evaluated on the device from these): parameters that act through the layer optical depths -- Rayleigh, gas
+ * absorption (per-layer VMR scalings), aerosol optical depth (tau_ref) -- and through the Lambertian albedo.
+ * Parameters that change the phase matrix itself (aerosol microphysics) and BRDF shape parameters are not covered.
+ * fp64 only; every layer must scatter (all interfaces _11), as in any Rayleigh atmosphere. */
+typedef struct vsm_lin_desc {
+    int32_t struct_size;      /* sizeof(vsm_lin_desc) */
+    int32_t n_params;         /* P, 1..16 */
+    const double* dtau_aer;   /* host (nAer,Nz,P) d tau_aer / dp, or NULL */
+    const double* dalbedo;    /* host [P] d albedo / dp, or NULL */
+    const void*   dtau_rayl;  /* device (nSpec,Nz,P) d tau_rayl / dp, or NULL */
+    const void*   dtau_abs;   /* device (nSpec,Nz,P) d tau_abs / dp, or NULL */
+} vsm_lin_desc;
+/* outputs: device; R_SFI/T_SFI (nVZA,nStokes,nSpec); dR/dT (nVZA,nStokes,nSpec,P) as rt_run_lin.jl:185-190 */
+int vsm_rt_column_lin_f64(vsm_ctx*, const vsm_column_desc*, const vsm_lin_desc*, double* R_SFI, double* T_SFI,
+                          double* dR, double* dT);
+
 /* device time (ms) of the most recent vsm_rt_column_* call, measured with CUDA
  * events on the context's stream; blocks until that call has finished.        */
 int vsm_last_column_ms(vsm_ctx*, float* total_ms, float* doubling_ms, float* adding_ms);

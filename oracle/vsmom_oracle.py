@@ -1434,14 +1434,19 @@ def rt_run_lin(model: Model, dtau_rayl, dtau_abs, dtau_aer, dalbedo):
             else:
                 C, dC = interaction_lin(ctl.interface[iz], C, dC, r, r_pm, t, t_mm, j0p, j0m, dr, dr_pm, dt, dt_mm, dj0p, dj0m)
             dtausum = dtausum + dtl
-        # Lambertian surface and its derivative (lambertian_surface_lin.jl)
-        r_s, rpm_s, t_s, tmm_s, j0p_s, j0m_s = lambertian_surface(model, m, ctl.tau_sum[:, -1])
+        # surface and its derivative: Lambertian (lambertian_surface_lin.jl: albedo and attenuation), or a BRDF given by
+        # its Fourier moments (no surface parameter here: only the attenuation of the direct beam varies)
+        brdf = model.surface_rho is not None
+        if brdf:
+            r_s, rpm_s, t_s, tmm_s, j0p_s, j0m_s = brdf_surface(model, m, ctl.tau_sum[:, -1])
+        else:
+            r_s, rpm_s, t_s, tmm_s, j0p_s, j0m_s = lambertian_surface(model, m, ctl.tau_sum[:, -1])
         dr_s = np.zeros((P, nS, N, N), FT); dj0p_s = np.zeros((P, nS, N), FT); dj0m_s = np.zeros((P, nS, N), FT)
-        if m == 0:
+        if m == 0 or brdf:
             att_d = -(1 / FT(q.mu0)) * dtausum                                  # d att / att
             dj0p_s = j0p_s[None] * att_d[:, :, None]
             dj0m_s = j0m_s[None] * att_d[:, :, None]
-            if model.albedo != 0:
+            if not brdf and model.albedo != 0:
                 rel = (np.asarray(dalbedo, FT) / FT(model.albedo))[:, None, None]
                 dr_s = dr_s + r_s[None] * rel[:, :, :, None]
                 dj0m_s = dj0m_s + j0m_s[None] * rel

@@ -25,13 +25,15 @@ def run(pol, nstreams, nspec, mmax=None, noscat=False):
     t = time.time(); out = rr.rt_run(m, ctx); t2 = time.time() - t
     ms = ctx.last_column_ms()
     ctx.close()
-    os.environ["VSM_DISABLE_STREAM"] = "1"
-    ctx = _lib.Context(0)
-    gen = rr.rt_run(m, ctx); msg = ctx.last_column_ms(); ctx.close()
-    del os.environ["VSM_DISABLE_STREAM"]
-    line = f"{pol} nstreams={nstreams} N={N} nSpec={nspec} moments={m.m_max+1}: stream ms={ms} generic ms={msg} "
-    for k in ("R_SFI", "T_SFI", "hdr"):
-        line += f"| {k} vs generic {relerr(out[k], gen[k]):.2e} "
+    line = f"{pol} nstreams={nstreams} N={N} nSpec={nspec} moments={m.m_max+1}: stream ms={ms} "
+    if nspec <= 4 or os.environ.get("DEV_GENERIC"):
+        os.environ["VSM_DISABLE_STREAM"] = "1"
+        ctx = _lib.Context(0)
+        gen = rr.rt_run(m, ctx); msg = ctx.last_column_ms(); ctx.close()
+        del os.environ["VSM_DISABLE_STREAM"]
+        line += f"generic ms={msg} "
+        for k in ("R_SFI", "T_SFI", "hdr"):
+            line += f"| {k} vs generic {relerr(out[k], gen[k]):.2e} "
     print(line, flush=True)
     if nspec <= 4:
         t = time.time(); ref = orc.rt_run(to_oracle(m)); t3 = time.time() - t
@@ -44,7 +46,11 @@ if __name__ == "__main__":
         run("Stokes_IQUV", 20, 2, mmax=3)
         run("Stokes_IQUV", 11, 2, mmax=3)
         run("Stokes_IQU", 20, 2, mmax=2, noscat=True)
+    elif what == "prof":
+        run("Stokes_IQUV", 20, 148, mmax=0)
+        run("Stokes_IQU", 20, 296, mmax=0)
     else:
-        run("Stokes_IQU", 20, 296)
-        run("Stokes_IQUV", 20, 148)
-        run("Stokes_IQUV", 11, 296)
+        mm = int(os.environ.get("DEV_MMAX", "9"))
+        run("Stokes_IQU", 20, 296, mmax=mm)
+        run("Stokes_IQUV", 20, 148, mmax=mm)
+        run("Stokes_IQUV", 11, 296, mmax=mm)

@@ -436,3 +436,83 @@ def test_rt_layer_entry_matches_oracle(ctx, dtype, pol, nstreams):
         rpm = added.rpm.cpu().numpy().transpose(0, 2, 1)
         if np.abs(rmp).max() > 0:
             assert np.allclose(rpm, Dd[None, :, None] * rmp * Dd[None, None, :], rtol=0, atol=0)
+
+
+# ----------------------------------------------------------------------------
+# BASELINE.json configs[2]: ocean_coxmunk.yaml scene (polarized Cox-Munk glint + aerosol), N = 60 / 75 / 100:
+# the streamed-operand kernels (vsm_stream.cuh)
+# ----------------------------------------------------------------------------
+def trim_moments(m, mmax):
+    """Shorten the Fourier loop (keeps the oracle run short): m_max, the surface moments and the aerosol
+    Greek coefficients are cut consistently for both sides."""
+    m.m_max = mmax
+    m.surface_rho = m.surface_rho[:mmax + 1]
+    for a in m.aerosol_optics:
+        g = a.greek_coefs
+        for f in ("alpha", "beta", "gamma", "delta", "epsilon", "zeta"):
+            setattr(g, f, getattr(g, f)[:mmax + 1])
+    return m
+
+
+@pytest.mark.parametrize("pol,nstreams,N,mmax", [("Stokes_IQU", 20, 75, None), ("Stokes_IQUV", 20, 100, 7),
+                                                  ("Stokes_IQUV", 11, 60, 9)])
+def test_ocean_coxmunk_config3_matches_oracle(ctx, pol, nstreams, N, mmax):
+    m = vb.synthetic_ocean_model(nSpec=2, nstreams=nstreams, polarization_type=pol)
+    assert m.quad_points.qp_muN.size == N
+    if mmax is not None:
+        trim_moments(m, mmax)
+    else:
+        assert m.m_max == 2 * nstreams - 1           # the full 40-moment Fourier loop of the benchmark row
+    out = run_gpu(m, ctx)
+    assert_close(out, orc.rt_run(to_oracle(m)), F64_TOL)
+    # the TMS correction is in: switching it off changes R_SFI by exactly mu0 exp(-tau/mu0) * factor
+    ss = m.ss_correction
+    m.ss_correction = None
+    off = run_gpu(m, ctx)
+    tau = (m.tau_rayl + m.tau_abs).sum(axis=1) + m.tau_aer.sum()
+    mu0 = m.quad_points.mu0
+    want = ss[:, :, None] * (mu0 * np.exp(-tau / mu0))[None, None, :]
+    assert np.allclose(out["R_SFI"] - off["R_SFI"], want, rtol=1e-8, atol=1e-15)
+
+
+def test_ocean_streamed_equals_generic_many_points(ctx):
+    # several work items per CTA (slab reuse), every CTA busy: streamed kernels == the generic shared-memory/slab
+    # kernels to rounding on 600 points, and spot points equal the oracle
+    import os
+    from vsmom_b200 import _lib
+    m = trim_moments(vb.synthetic_ocean_model(nSpec=600, nstreams=20, polarization_type="Stokes_IQU"), 2)
+    out = run_gpu(m, ctx)
+    os.environ["VSM_DISABLE_STREAM"] = "1"
+    try:
+        c = _lib.Context(0)
+    finally:
+        del os.environ["VSM_DISABLE_STREAM"]
+    try:
+        gen = run_gpu(m, c)
+    finally:
+        c.close()
+    for k in KEYS:
+        assert relerr(out[k], gen[k]) <= 1e-10, k
+    idx = np.array([0, 233, 599])
+    ref = orc.rt_run(to_oracle(m), idx)
+    for k in ("R_SFI", "T_SFI", "hdr"):
+        assert relerr(out[k][..., idx], ref[k]) <= F64_TOL, k
+
+
+@pytest.mark.parametrize("scale", [8.0, 40.0])
+def test_ocean_streamed_inverse_routes(ctx, scale):
+    # thick, bright scene: Neumann orders 2..8 and the staged partial-pivoting elimination all occur; the
+    # elimination-only mode must agree
+    m = trim_moments(vb.synthetic_ocean_model(nSpec=6, nstreams=20, polarization_type="Stokes_IQU"), 3)
+    m.tau_rayl = m.tau_rayl * scale
+    m.tau_aer = m.tau_aer * scale
+    m.tau_abs = m.tau_abs * np.logspace(-3.0, 0.0, 6)[:, None]
+    ref = orc.rt_run(to_oracle(m))
+    try:
+        ctx.set_inverse_mode(0)
+        gj = run_gpu(m, ctx)
+    finally:
+        ctx.set_inverse_mode(1)
+    ad = run_gpu(m, ctx)
+    assert_close(gj, ref, F64_TOL)
+    assert_close(ad, ref, F64_TOL)

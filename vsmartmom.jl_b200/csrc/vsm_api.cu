@@ -16,6 +16,7 @@
 #include "vsm_launch.cuh"
 #include "vsm_l0.cuh"
 #include "vsm_stream.cuh"
+#include "vsm_lin.cuh"
 
 using namespace vsm;
 
@@ -38,7 +39,7 @@ struct vsm_ctx {
     std::map<const void*, int> smem_set;    // largest dynamic shared-memory size already granted per kernel
     std::string err;
     // grow-only scratch
-    DevBuf consts, props, added, slabs, partial, counter, l0tmp, geom, surfpad;
+    DevBuf consts, props, added, slabs, partial, counter, l0tmp, geom, surfpad, linprops;
     int use_stream = 1;                     // streamed-operand kernels for N = 60 / 75 / 100 (VSM_DISABLE_STREAM=1 turns them off)
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float t_total = 0, t_layer = 0, t_add = 0;
@@ -149,7 +150,7 @@ extern "C" int vsm_destroy(vsm_ctx* ctx) {
     if (!ctx) return VSM_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->consts, &ctx->props, &ctx->added, &ctx->slabs, &ctx->partial, &ctx->counter, &ctx->l0tmp, &ctx->geom, &ctx->surfpad};
+    DevBuf* bufs[] = {&ctx->consts, &ctx->props, &ctx->added, &ctx->slabs, &ctx->partial, &ctx->counter, &ctx->l0tmp, &ctx->geom, &ctx->surfpad, &ctx->linprops};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->stage) cudaFreeHost(ctx->stage);
@@ -730,6 +731,230 @@ extern "C" int vsm_rt_column_streams_f64(vsm_ctx* c, const vsm_column_desc* d, d
 extern "C" int vsm_rt_column_streams_f32(vsm_ctx* c, const vsm_column_desc* d, float* R, float* T_, float* hdr, float* uw,
                                          float* dw, float* Rmp, float* Tpp, float* Jm, float* Jp) {
     return rt_column_impl<float>(c, d, R, T_, hdr, uw, dw, Rmp, Tpp, Jm, Jp);
+}
+
+// ---------------------------------------------------------------------------
+// L2 LinMode: forward + Jacobians (rt_run_lin.jl:102-326)
+// ---------------------------------------------------------------------------
+static int rt_column_lin_impl(vsm_ctx* ctx, const vsm_column_desc* d, const vsm_lin_desc* ld_, double* R_SFI, double* T_SFI,
+                              double* dR, double* dT) {
+    using T = double;
+    if (!ctx) return VSM_ERR_INVALID_ARG;
+    if (!d || d->struct_size < (int)offsetof(vsm_column_desc, ss_correction))
+        return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_lin: descriptor NULL or struct_size mismatch");
+    if (!ld_ || ld_->struct_size != (int)sizeof(vsm_lin_desc) || ld_->n_params < 1 || ld_->n_params > kMaxParams)
+        return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_lin: lin descriptor NULL / struct_size mismatch / n_params not in 1..16");
+    const void* surf_rho = (d->surface_kind == VSM_SURFACE_BRDF_FOURIER) ? d->surf_rho : nullptr;
+    if (d->nSpec == 0) return VSM_OK;
+    if (!R_SFI || !T_SFI || !dR || !dT) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_lin: output NULL");
+    const int N = d->N, nSt = d->nStokes, Nz = d->Nz, nAer = d->nAer, nV = d->nVZA, nM = d->n_moments, nSpec = d->nSpec;
+    const int P = ld_->n_params, nOut = nV * nSt, nC = nAer + 1;
+    if (N <= 0 || nSt < 1 || nSt > 4 || N % nSt != 0 || Nz <= 0 || nAer < 0 || nC > kMaxComp || nV <= 0 || nM <= 0 ||
+        d->imu0 < 1 || d->imu0 * nSt > N)
+        return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_lin: bad dimensions");
+    if (d->surface_kind == VSM_SURFACE_BRDF_FOURIER && !surf_rho) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_lin: BRDF_FOURIER needs surf_rho");
+    if (!d->mu || !d->wt || !d->vza_weight || !d->ndoubl || !d->scatter || !d->iface || !d->vza_stream || !d->tau_rayl ||
+        !d->tau_abs || !d->F0 || !d->Zpp || !d->Zmp || (nAer > 0 && (!d->aer_omega || !d->aer_ft || !d->tau_aer)))
+        return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_lin: NULL input array");
+    for (int iz = 0; iz < Nz; ++iz) {
+        if (!d->scatter[iz] || (iz > 0 && d->iface[iz] != VSM_IFACE_11))
+            return fail(ctx, VSM_ERR_UNSUPPORTED, "rt_column_lin: every layer must scatter (ScatteringInterface_11 throughout)");
+        if (d->ndoubl[iz] < 0 || d->ndoubl[iz] > 60) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_lin: ndoubl out of range");
+    }
+    CK(cudaSetDevice(ctx->device));
+    // ---- constant tables (as rt_column_impl) + the parameter tables
+    std::vector<T> fT;
+    std::vector<int> fI;
+    auto pushT = [&](const double* p, size_t n) { size_t o = fT.size(); for (size_t i = 0; i < n; ++i) fT.push_back((T)p[i]); return o; };
+    auto pushI = [&](const int32_t* p, size_t n) { size_t o = fI.size(); for (size_t i = 0; i < n; ++i) fI.push_back(p[i]); return o; };
+    const size_t o_mu = pushT(d->mu, N), o_wt = pushT(d->wt, N);
+    std::vector<double> taumod((size_t)std::max(1, nAer * Nz)), varmod((size_t)std::max(1, nAer)), dtaumod((size_t)std::max(1, nAer * Nz * P), 0.0);
+    for (int c = 0; c < nAer; ++c) {
+        const T ft = (T)d->aer_ft[c], om = (T)d->aer_omega[c];
+        varmod[c] = (T(1) - ft) * om / (T(1) - ft * om);
+        for (int iz = 0; iz < Nz; ++iz) {
+            taumod[c + (size_t)nAer * iz] = (T(1) - ft * om) * (T)d->tau_aer[c + (size_t)nAer * iz];
+            if (ld_->dtau_aer)
+                for (int p = 0; p < P; ++p)      // d tau_mod: [(p*Nz + iz)*nAer + c] <- host (nAer,Nz,P)
+                    dtaumod[((size_t)p * Nz + iz) * nAer + c] = (T(1) - ft * om) * ld_->dtau_aer[c + (size_t)nAer * (iz + (size_t)Nz * p)];
+        }
+    }
+    const size_t o_taumod = pushT(taumod.data(), taumod.size()), o_varmod = pushT(varmod.data(), varmod.size());
+    const size_t o_dtaumod = pushT(dtaumod.data(), dtaumod.size());
+    std::vector<double> dalb(P, 0.0);
+    if (ld_->dalbedo) for (int p = 0; p < P; ++p) dalb[p] = ld_->dalbedo[p];
+    const size_t o_dalb = pushT(dalb.data(), P);
+    const size_t o_vw = pushT(d->vza_weight, (size_t)nSt * nV * nM);
+    const size_t o_nd = pushI(d->ndoubl, Nz), o_sc = pushI(d->scatter, Nz), o_if = pushI(d->iface, Nz);
+    std::vector<int> rz(Nz, 0);
+    if (d->rayl_allzero) for (int iz = 0; iz < Nz; ++iz) rz[iz] = d->rayl_allzero[iz];
+    const size_t o_rz = pushI(rz.data(), Nz);
+    std::vector<int> order(Nz);
+    for (int iz = 0; iz < Nz; ++iz) order[iz] = iz;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return d->ndoubl[x] > d->ndoubl[y]; });
+    std::vector<int> sidx(Nz);
+    for (int k = 0; k < Nz; ++k) sidx[order[k]] = k;
+    const size_t o_ord = pushI(order.data(), Nz), o_sidx = pushI(sidx.data(), Nz);
+    std::vector<int> vrow(nV);
+    for (int i = 0; i < nV; ++i) {
+        if (d->vza_stream[i] < 1 || d->vza_stream[i] * nSt > N) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_lin: vza_stream out of range");
+        vrow[i] = (d->vza_stream[i] - 1) * nSt;
+    }
+    const size_t o_vrow = pushI(vrow.data(), nV);
+    const size_t bytesT = fT.size() * sizeof(T), bytesI = fI.size() * sizeof(int);
+    const size_t offI = (bytesT + 15) & ~size_t(15);
+    int rc = ensure(ctx, ctx->consts, offI + bytesI);
+    if (rc) return rc;
+    // (synchronous upload from pageable memory: this entry is not on the latency-critical path)
+    std::vector<char> blob(offI + bytesI);
+    memcpy(blob.data(), fT.data(), bytesT);
+    memcpy(blob.data() + offI, fI.data(), bytesI);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(ctx->consts.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const T* cT = (const T*)ctx->consts.p;
+    const int* cI = (const int*)((char*)ctx->consts.p + offI);
+
+    // ---- kernels and layout
+    const LinDesc* ldsc = ctx->use_stream ? lin_desc_stream(N) : nullptr;
+    if (!ldsc) ldsc = lin_desc_generic(N <= 24 ? 2 : 4);
+    const int mld = ldsc->ld ? ldsc->ld : (N | 1), mcols = ldsc->ld ? ldsc->ncols : N;
+    const size_t msz = (size_t)mld * mcols;
+    const int vs = ldsc->ld ? ldsc->ncols : N;
+    const size_t smem = ldsc->smem ? ldsc->smem : ((size_t)13 * N + kMaxComp) * sizeof(T) + ((size_t)2 * N + 8) * 4;
+    if (smem > (size_t)ctx->max_smem_optin) return fail(ctx, VSM_ERR_UNSUPPORTED, "rt_column_lin: N too large");
+    CK(set_smem(ctx, ldsc->k_layer, smem));
+    CK(set_smem(ctx, ldsc->k_adding, smem));
+    const int l_grid_max = ctx->num_sms * occupancy<T>(ldsc->k_layer, ldsc->threads, smem);
+    const int a_grid_max = ctx->num_sms * occupancy<T>(ldsc->k_adding, ldsc->threads, smem);
+    const size_t dsz = (size_t)(1 + P) * msz, dv = (size_t)(1 + P) * vs;
+    const size_t l_slab = ((size_t)kLinLayerDuals * dsz + kLinSingles * msz + kLinLayerVecs * dv + (size_t)2 * (1 + P) * nSt * N + 16) * sizeof(T);
+    const size_t a_slab = ((size_t)kLinAddDuals * dsz + kLinSingles * msz + kLinAddVecs * dv + 16) * sizeof(T);
+    const uint64_t slab_bytes = (uint64_t)l_slab * l_grid_max + (uint64_t)a_slab * a_grid_max;
+
+    // ---- workspace plan: one moment at a time, chunks of spectral points
+    const size_t add_item = (size_t)Nz * (1 + P) * ((size_t)2 * msz + 2 * N) * sizeof(T);
+    const size_t props_pt = ((size_t)Nz * (2 + nC) + (Nz + 1)) * sizeof(T);
+    const size_t lprops_pt = (size_t)P * ((size_t)Nz * (2 + nC) + (Nz + 1)) * sizeof(T);
+    const size_t part_pt = (size_t)2 * nM * nOut * (1 + P) * sizeof(T) + (size_t)nM * nOut * sizeof(T);
+    uint64_t limit = ctx->ws_limit ? ctx->ws_limit : (uint64_t)24 << 30;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t avail = (uint64_t)free_b + ctx->added.cap + ctx->props.cap + ctx->partial.cap + ctx->slabs.cap + ctx->linprops.cap;
+    limit = std::min<uint64_t>(limit, avail * 8 / 10);
+    const uint64_t per_pt = (uint64_t)add_item + props_pt + lprops_pt + part_pt;
+    if (limit < slab_bytes + per_pt) return fail(ctx, VSM_ERR_NOMEM, "rt_column_lin: workspace limit too small for one spectral point");
+    const int chunk = (int)std::min<uint64_t>((uint64_t)nSpec, std::max<uint64_t>(1, (limit - slab_bytes) / per_pt));
+    if ((rc = ensure(ctx, ctx->added, (size_t)add_item * chunk))) return rc;
+    if ((rc = ensure(ctx, ctx->props, (size_t)props_pt * chunk))) return rc;
+    if ((rc = ensure(ctx, ctx->linprops, (size_t)lprops_pt * chunk))) return rc;
+    if ((rc = ensure(ctx, ctx->partial, (size_t)part_pt * chunk))) return rc;
+    if ((rc = ensure(ctx, ctx->slabs, (size_t)std::max<uint64_t>(slab_bytes, 16)))) return rc;
+    if ((rc = ensure(ctx, ctx->counter, 256))) return rc;
+    CK(cudaMemsetAsync(ctx->slabs.p, 0, (size_t)slab_bytes, ctx->stream));      // zero padding is an invariant of the streamed products
+
+    ctx->ev_used = 0; ctx->seg_layer.clear(); ctx->seg_add.clear();
+    GET_EVENT(ev_begin);
+    GET_EVENT(ev_end);
+    CK(cudaEventRecord(ev_begin, ctx->stream));
+    for (int n0 = 0; n0 < nSpec; n0 += chunk) {
+        const int nS = std::min(chunk, nSpec - n0);
+        T* pw = (T*)ctx->props.p;
+        PropsArgs<T> pa;
+        pa.nS = nS; pa.Nz = Nz; pa.nAer = nAer; pa.ldspec = (size_t)nSpec;
+        pa.tau_rayl = (const T*)d->tau_rayl + n0; pa.tau_abs = (const T*)d->tau_abs + n0;
+        pa.varpi_cab = (T)d->varpi_cabannes;
+        pa.aer_tau_mod = cT + o_taumod; pa.aer_varpi_mod = cT + o_varmod; pa.rayl_allzero = cI + o_rz;
+        pa.tau = pw; pa.varpi = pw + (size_t)Nz * nS; pa.tausum = pw + (size_t)2 * Nz * nS; pa.W = pw + (size_t)(3 * Nz + 1) * nS;
+        k_props<T><<<(nS + 127) / 128, 128, 0, ctx->stream>>>(pa);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        T* lw = (T*)ctx->linprops.p;
+        PropsLinArgs<T> pl;
+        pl.nS = nS; pl.Nz = Nz; pl.nAer = nAer; pl.P = P; pl.ldspec = (size_t)nSpec;
+        pl.tau_rayl = pa.tau_rayl; pl.tau_abs = pa.tau_abs;
+        pl.dtau_rayl = ld_->dtau_rayl ? (const T*)ld_->dtau_rayl + n0 : nullptr;
+        pl.dtau_abs = ld_->dtau_abs ? (const T*)ld_->dtau_abs + n0 : nullptr;
+        pl.varpi_cab = pa.varpi_cab; pl.aer_tau_mod = pa.aer_tau_mod; pl.aer_varpi_mod = pa.aer_varpi_mod;
+        pl.daer_tau_mod = (nAer > 0 && ld_->dtau_aer) ? cT + o_dtaumod : nullptr;
+        pl.d_tau = lw; pl.d_varpi = lw + (size_t)P * Nz * nS; pl.d_tausum = lw + (size_t)2 * P * Nz * nS;
+        pl.d_W = lw + ((size_t)2 * P * Nz + (size_t)P * (Nz + 1)) * nS;
+        k_props_lin<T><<<(nS + 127) / 128, 128, 0, ctx->stream>>>(pl);
+        ctx->launches++;
+        CK(cudaGetLastError());
+
+        T* part = (T*)ctx->partial.p;
+        const size_t per_m = (size_t)nS * nOut;
+        ColArgs<T> a;
+        memset(&a, 0, sizeof a);
+        a.N = N; a.nStokes = nSt; a.Nz = Nz; a.nC = nC; a.nVZA = nV; a.ld = mld;
+        a.istart = (d->imu0 - 1) * nSt; a.nS = nS; a.n_sched_layers = Nz; a.neumann = ctx->inverse_mode;
+        a.mu0 = (T)d->mu0; a.albedo = (T)d->albedo; a.surf_rho = (const T*)surf_rho;
+        a.mu = cT + o_mu; a.wt = cT + o_wt;
+        a.ndoubl = cI + o_nd; a.scatter = cI + o_sc; a.iface = cI + o_if; a.layer_order = cI + o_ord; a.sched_idx = cI + o_sidx;
+        a.Zpp = (const T*)d->Zpp; a.Zmp = (const T*)d->Zmp;
+        a.p_tau = pa.tau; a.p_varpi = pa.varpi; a.p_tausum = pa.tausum; a.p_W = pa.W;
+        a.F0 = (const T*)d->F0; a.F0_off = (size_t)n0;
+        a.counter = (unsigned int*)ctx->counter.p;
+        a.vza_row = cI + o_vrow; a.vza_w = cT + o_vw;
+        a.part_R = part; a.part_T = part + (size_t)nM * per_m; a.part_H = part + (size_t)2 * nM * per_m;
+        a.add_mstride = msz;
+        LinArgs<T> l;
+        memset(&l, 0, sizeof l);
+        l.P = P; l.msz = msz; l.vstride = vs;
+        l.d_tau = pl.d_tau; l.d_varpi = pl.d_varpi; l.d_tausum = pl.d_tausum; l.d_W = pl.d_W; l.dalbedo = cT + o_dalb;
+        l.part_dR = part + (size_t)3 * nM * per_m; l.part_dT = l.part_dR + (size_t)nM * per_m * P;
+        T* ad = (T*)ctx->added.p;
+        const size_t slots = (size_t)Nz * nS * (1 + P);
+        l.add_r = ad; l.add_t = ad + slots * msz; l.add_jp = ad + 2 * slots * msz; l.add_jm = l.add_jp + slots * N;
+        for (int m0 = 0; m0 < nM; ++m0) {
+            a.m0 = m0; a.Mb = 1;
+            {
+                const unsigned total = (unsigned)((size_t)Nz * nS);
+                const int grid = (int)std::min<size_t>(total, (size_t)l_grid_max);
+                a.slab = (T*)ctx->slabs.p; a.slab_stride = l_slab / sizeof(T);
+                CK(cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
+                GET_EVENT(e0);
+                GET_EVENT(e1);
+                CK(cudaEventRecord(e0, ctx->stream));
+                const cudaError_t e = ldsc->launch_layer(ctx->stream, a, l, total, grid, smem);
+                ctx->launches++;
+                if (e != cudaSuccess) return fail(ctx, VSM_ERR_CUDA, std::string("k_layer_lin launch: ") + cudaGetErrorString(e));
+                CK(cudaEventRecord(e1, ctx->stream));
+                ctx->seg_layer.push_back({e0, e1});
+            }
+            {
+                const unsigned total = (unsigned)nS;
+                const int grid = (int)std::min<size_t>(total, (size_t)a_grid_max);
+                a.slab = (T*)ctx->slabs.p + ((size_t)l_slab * l_grid_max) / sizeof(T); a.slab_stride = a_slab / sizeof(T);
+                CK(cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
+                GET_EVENT(e0);
+                GET_EVENT(e1);
+                CK(cudaEventRecord(e0, ctx->stream));
+                const cudaError_t e = ldsc->launch_adding(ctx->stream, a, l, total, grid, smem);
+                ctx->launches++;
+                if (e != cudaSuccess) return fail(ctx, VSM_ERR_CUDA, std::string("k_adding_lin launch: ") + cudaGetErrorString(e));
+                CK(cudaEventRecord(e1, ctx->stream));
+                ctx->seg_add.push_back({e0, e1});
+            }
+        }
+        k_reduce<T><<<(unsigned)((per_m + 255) / 256), 256, 0, ctx->stream>>>(
+            nM, per_m, a.part_R, a.part_T, (const T*)nullptr, R_SFI + (size_t)n0 * nOut, T_SFI + (size_t)n0 * nOut, (T*)nullptr,
+            (const T*)nullptr, pa.tausum + (size_t)Nz * nS, (T)d->mu0, nOut);
+        const size_t per_ml = per_m * P;
+        k_reduce_lin<T><<<(unsigned)((per_ml + 255) / 256), 256, 0, ctx->stream>>>(nM, nS, P, nOut, (size_t)nSpec, (size_t)n0,
+                                                                               l.part_dR, l.part_dT, dR, dT);
+        ctx->launches += 2;
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(ev_end, ctx->stream));
+    ctx->ev[0] = ev_begin; ctx->ev[1] = ev_end; ctx->timing_valid = true;
+    return VSM_OK;
+}
+
+extern "C" int vsm_rt_column_lin_f64(vsm_ctx* c, const vsm_column_desc* d, const vsm_lin_desc* l, double* R, double* T_, double* dR,
+                                     double* dT) {
+    return rt_column_lin_impl(c, d, l, R, T_, dR, dT);
 }
 
 extern "C" int vsm_last_column_ms(vsm_ctx* ctx, float* total_ms, float* doubling_ms, float* adding_ms) {

@@ -270,6 +270,7 @@ struct OpsGeneric {
     int tid, bar;            // whole CTA: tid = threadIdx.x
     int neumann = 0;         // (OpsFast only)
     static constexpr bool kDmma = false;
+    static constexpr bool kIsStream = false;
     __device__ __forceinline__ int N() const { return n; }
     __device__ __forceinline__ int LD() const { return ld; }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
@@ -404,6 +405,7 @@ struct OpsFast {
     static constexpr int NTI = NN / TMI;          // inverse tiles per dimension
     static_assert(NT * NT * KS <= NTHR && NTI * NTI <= NTHR, "one register tile per thread");
     static constexpr int kLd = NN | 1;
+    static constexpr bool kIsStream = false;
     static constexpr int RP = (NN + 31) & ~31;    // rows padded to whole warps for mv
     T* vec;                  // >= 5*NN : colb[2][NN] rowb[2][NN] ipv[2]
     T* part;                 // >= 8*NN

@@ -40,6 +40,25 @@ inline const StreamDesc* stream_desc(int N) {
     return N == 60 ? stream_desc_60() : N == 75 ? stream_desc_75() : N == 100 ? stream_desc_100() : nullptr;
 }
 
+// LinMode kernels (vsm_lin.cuh), fp64: generic (run-time N, SIMT products on slab-resident matrices) and the
+// streamed instantiations
+template <typename T> struct LinArgs;
+struct LinDesc {
+    int ld, ncols;                 // slab / hand-off layout of one matrix: ld x ncols elements (0: N|1 x N, run-time)
+    int threads;
+    size_t smem;                   // 0: computed from N by the host (generic kernels)
+    const void* k_layer; const void* k_adding;
+    cudaError_t (*launch_layer)(cudaStream_t, const ColArgs<double>&, const LinArgs<double>&, unsigned total, int grid, size_t smem);
+    cudaError_t (*launch_adding)(cudaStream_t, const ColArgs<double>&, const LinArgs<double>&, unsigned total, int grid, size_t smem);
+};
+const LinDesc* lin_desc_generic(int tm);        // tm = 2 (128 threads) or 4 (256 threads)
+const LinDesc* lin_desc_60();
+const LinDesc* lin_desc_75();
+const LinDesc* lin_desc_100();
+inline const LinDesc* lin_desc_stream(int N) {
+    return N == 60 ? lin_desc_60() : N == 75 ? lin_desc_75() : N == 100 ? lin_desc_100() : nullptr;
+}
+
 template <typename T, int TM, int NN, int NTHR, int TMI = TM, int KS = 1>
 struct OpsSel { using type = OpsFast<T, TM, NN, NTHR, 0, TMI, KS>; };
 template <typename T, int TM, int NTHR, int TMI, int KS>

@@ -45,12 +45,60 @@ struct StreamCfg {
     }
 };
 
+// cp.async ring state (uniform over the CTA)
+struct StreamRing {
+    unsigned committed = 0;          // groups committed so far; group G lives in stage G % NST
+    const double* pfA = nullptr;     // operands of the announced next product ...
+    const double* pfB = nullptr;
+    unsigned pfG0 = 0;               // ... the group of its panel 0 and the panels already issued
+    int pfN = 0;
+};
+
+// Position of a warp in the WR x WC warp grid.  A warp's DMMA work is (its row tiles) x (its column tiles) and the
+// tile counts differ by one when the grid does not divide NT; warps w, w+4, w+8, ... share an SM sub-partition
+// (one DMMA pipe), so the grid is laid over the warps such that every sub-partition gets a balanced mix.
+template <int WR, int WC>
+__device__ __forceinline__ void stream_warp_coords(int warp, int& wr, int& wc) {
+    if (WR == 4 && WC == 4) { wc = warp >> 2; wr = (warp + wc) & 3; }          // each sub-partition: every row and column once
+    else if (WR == 2 && WC == 4) { wr = warp >> 2; wc = wr ? 3 - (warp & 3) : (warp & 3); }   // large row half with small column
+    else { wr = warp % WR; wc = warp / WR; }
+}
+
+template <class CF>
+__device__ __forceinline__ void stream_issue_panel(double* stages, int tid, unsigned G, const double* __restrict__ A,
+                                                   const double* __restrict__ B, int kp) {
+    constexpr int NP = CF::NP, kLd = CF::LD, KP = CF::KP, NTHR = CF::NTHR;
+    double* sA = stages + (G % CF::NST) * CF::STAGE;
+    double* sB = sA + CF::A_STAGE;
+    const int k0 = kp * KP;
+    const int kc = (NP - k0 < KP) ? (NP - k0) : KP;               // multiple of 8
+    const double* gA = A + (size_t)k0 * kLd;                      // kc contiguous columns of A
+    for (int c = tid; c < kc * kLd / 2; c += NTHR) cp_async_16(sA + 2 * c, gA + 2 * c);
+    // B panel: kc consecutive k (kc/2 16-byte chunks) of every column
+    if (kc == KP) {
+        constexpr int CPC = KP / 2;
+        for (int c = tid; c < NP * CPC; c += NTHR) {
+            const int j = c / CPC, q = c % CPC;
+            cp_async_16(sB + j * CF::LDB + 2 * q, B + j * kLd + k0 + 2 * q);
+        }
+    } else {
+        const int cpc = kc / 2;
+        for (int c = tid; c < NP * cpc; c += NTHR) {
+            const int j = c / cpc, q = c - j * cpc;
+            cp_async_16(sB + j * CF::LDB + 2 * q, B + j * kLd + k0 + 2 * q);
+        }
+    }
+    cp_async_commit();
+}
+
 template <class CF>
 struct OpsStream {
     using T = double;
     static constexpr int NN = CF::NN, NP = CF::NP, kLd = CF::LD, NTHR = CF::NTHR;
     static constexpr int WR = CF::WR, WC = CF::WC, TR = CF::TR, TC = CF::TC, NST = CF::NST, KP = CF::KP;
     static constexpr bool kDmma = true;
+    static constexpr bool kIsStream = true;
+    using Cfg = CF;
     T* stages;               // NST * STAGE
     T* vec;                  // >= 5 NP (elimination fallback)
     T* part;                 // >= 8 NP
@@ -58,47 +106,20 @@ struct OpsStream {
     const uint32_t* dmask;   // [NP], 0 beyond NN
     int tid, bar;
     int neumann = 1;
-    // cp.async ring state (uniform over the CTA)
-    mutable unsigned committed = 0;          // groups committed so far; group G lives in stage G % NST
-    mutable const T* pfA = nullptr;          // operands of the announced next product ...
-    mutable const T* pfB = nullptr;
-    mutable unsigned pfG0 = 0;               // ... the group of its panel 0 and the panels already issued
-    mutable int pfN = 0;
+    mutable StreamRing ring;
 
     __device__ __forceinline__ constexpr int N() const { return NN; }
     __device__ __forceinline__ constexpr int LD() const { return kLd; }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
     __device__ __forceinline__ int nthreads() const { return NTHR; }
 
-    // first tile and tile count of warp-grid row wr / column wc (balanced split of NT tiles)
+    // first tile of warp-grid row wr / column wc (balanced split of NT tiles)
     static __device__ __forceinline__ int t0(int w, int W) { return (CF::NT * w) / W; }
 
-    __device__ __forceinline__ void issue_panel(unsigned G, const T* __restrict__ A, const T* __restrict__ B, int kp) const {
-        T* sA = stages + (G % NST) * CF::STAGE;
-        T* sB = sA + CF::A_STAGE;
-        const int k0 = kp * KP;
-        const int kc = (NP - k0 < KP) ? (NP - k0) : KP;               // multiple of 8
-        const T* gA = A + (size_t)k0 * kLd;                           // kc contiguous columns of A
-        for (int c = tid; c < kc * kLd / 2; c += NTHR) cp_async_16(sA + 2 * c, gA + 2 * c);
-        const int cpc = kc / 2;                                       // 16-byte chunks per column of the B panel
-        for (int c = tid; c < NP * cpc; c += NTHR) {
-            const int j = c / cpc, q = c - j * cpc;
-            cp_async_16(sB + j * CF::LDB + 2 * q, B + (size_t)j * kLd + k0 + 2 * q);
-        }
-        cp_async_commit();
-    }
-    // all of this thread's copies of group G have landed
-    __device__ __forceinline__ void wait_group_of(unsigned G) const {
-        const int allow = (int)(committed - 1u - G);
-        if (allow <= 0) cp_async_wait_group<0>();
-        else if (allow == 1) cp_async_wait_group<1>();
-        else if (allow == 2) cp_async_wait_group<2>();
-        else cp_async_wait_group<3>();
-    }
     // nothing in flight, nothing announced (before the ring memory is used for anything else)
     __device__ __forceinline__ void drain() const {
         cp_async_wait_all();
-        pfN = 0; pfA = pfB = nullptr;
+        ring.pfN = 0; ring.pfA = ring.pfB = nullptr;
         __syncthreads();
     }
 
@@ -113,22 +134,34 @@ struct OpsStream {
                                               const T* nA, const T* nB) const {
         const int warp = tid >> 5, lane = tid & 31;
         const int g = lane >> 2, tg = lane & 3;
-        const int wr = warp % WR, wc = warp / WR;
+        int wr, wc;
+        stream_warp_coords<WR, WC>(warp, wr, wc);
         const int tr0 = t0(wr, WR), trn = t0(wr + 1, WR) - tr0;
         const int tc0 = t0(wc, WC), tcn = t0(wc + 1, WC) - tc0;
         const int wi = tr0 * 8, wj = tc0 * 8;
         const bool vown = (NV > 0) && (wc == 0);
+        // A warp with one tile row / column less than the largest block recomputes its last one in the spare slot
+        // (discarded by the epilogue): the k loop then carries no per-tile predicate -- a predicate around mma.sync
+        // costs ~10 instructions (BSSY / WARPSYNC / ...) per DMMA, the spare DMMAs cost nothing the slowest warp of
+        // the panel barrier does not already pay.
+        int aoff[TR], boff[TC];
+#pragma unroll
+        for (int r = 0; r < TR; ++r) aoff[r] = (r < trn ? r : trn - 1) * 8;
+#pragma unroll
+        for (int q = 0; q < TC; ++q) boff[q] = (q < tcn ? q : tcn - 1) * 8 * CF::LDB;
+        StreamRing& rs = ring;
         unsigned g0;
         int issued;
-        if (pfN > 0 && pfA == A && pfB == B) {
-            g0 = pfG0; issued = pfN;                   // announced: its first panels are already in flight
+        if (rs.pfN > 0 && rs.pfA == A && rs.pfB == B) {
+            g0 = rs.pfG0; issued = rs.pfN;             // announced: its first panels are already in flight
         } else {
-            if (pfN > 0) cp_async_wait_all();          // an announcement that did not come true
+            if (rs.pfN > 0) cp_async_wait_all();       // an announcement that did not come true
             __syncthreads();                           // every stage is free
-            g0 = committed; issued = 0;
-            for (; issued < NST - 1 && issued < CF::NPAN; ++issued, ++committed) issue_panel(committed, A, B, issued);
+            g0 = rs.committed; issued = 0;
+            for (; issued < NST - 1 && issued < CF::NPAN; ++issued, ++rs.committed)
+                stream_issue_panel<CF>(stages, tid, rs.committed, A, B, issued);
         }
-        pfN = 0; pfA = nA; pfB = nB;
+        rs.pfN = 0; rs.pfA = nA; rs.pfB = nB;
         double c[TR][TC][2];
         double cv[TR][2];
 #pragma unroll
@@ -141,27 +174,34 @@ struct OpsStream {
 #pragma unroll 1
         for (int kp = 0; kp < CF::NPAN; ++kp) {
             const unsigned G = g0 + (unsigned)kp;
-            wait_group_of(G);
+            {   // all of this thread's copies of group G have landed
+                const int allow = (int)(rs.committed - 1u - G);
+                if (allow <= 0) cp_async_wait_group<0>();
+                else if (allow == 1) cp_async_wait_group<1>();
+                else if (allow == 2) cp_async_wait_group<2>();
+                else cp_async_wait_group<3>();
+            }
             __syncthreads();                           // panel kp visible to all; everyone is done with group G - 1
             // top up the ring: stage (G - 1) % NST is free now -> groups up to G + NST - 1, this product's panels
             // first, then the announced product's
-            while (committed < G + (unsigned)NST) {
+            while (rs.committed < G + (unsigned)NST) {
                 if (issued < CF::NPAN) {
-                    issue_panel(committed, A, B, issued);
+                    stream_issue_panel<CF>(stages, tid, rs.committed, A, B, issued);
                     ++issued;
-                } else if (pfA && pfN < CF::NPAN) {
-                    if (pfN == 0) pfG0 = committed;
-                    issue_panel(committed, pfA, pfB, pfN);
-                    ++pfN;
+                } else if (rs.pfA && rs.pfN < CF::NPAN) {
+                    if (rs.pfN == 0) rs.pfG0 = rs.committed;
+                    stream_issue_panel<CF>(stages, tid, rs.committed, rs.pfA, rs.pfB, rs.pfN);
+                    ++rs.pfN;
                 } else {
                     break;
                 }
-                ++committed;
+                ++rs.committed;
             }
             const T* sA = stages + (G % NST) * CF::STAGE;
             const T* sB = sA + CF::A_STAGE;
             const int k0 = kp * KP;
-            const int kc = (NP - k0 < KP) ? (NP - k0) : KP;
+            constexpr int K4 = (NN + 3) & ~3;          // k >= K4 only meets zero padding
+            const int kc = (K4 - k0 < KP) ? (K4 - k0) : KP;
             const T* Ar = rebase(sA) + wi + g + tg * kLd;
             const T* Br = rebase(sB) + tg + (wj + g) * CF::LDB;
 #pragma unroll 2
@@ -171,27 +211,25 @@ struct OpsStream {
                 if (KSIGN) mk = dmask[k0 + ks * 4 + tg];
 #pragma unroll
                 for (int r = 0; r < TR; ++r) {
-                    a[r] = (r < trn) ? Ar[r * 8 + ks * 4 * kLd] : 0.0;
+                    a[r] = Ar[aoff[r] + ks * 4 * kLd];
                     if (KSIGN) a[r] = Num<double>::flip(a[r], mk);
                 }
 #pragma unroll
-                for (int q = 0; q < TC; ++q) b[q] = (q < tcn) ? Br[ks * 4 + q * 8 * CF::LDB] : 0.0;
+                for (int q = 0; q < TC; ++q) b[q] = Br[ks * 4 + boff[q]];
 #pragma unroll
                 for (int r = 0; r < TR; ++r)
 #pragma unroll
                     for (int q = 0; q < TC; ++q)
-                        if (r < trn && q < tcn)
-                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                                         : "+d"(c[r][q][0]), "+d"(c[r][q][1]) : "d"(a[r]), "d"(b[q]));
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                     : "+d"(c[r][q][0]), "+d"(c[r][q][1]) : "d"(a[r]), "d"(b[q]));
                 if (NV > 0) {
                     if (vown) {
                         const int k = k0 + ks * 4 + tg;
                         const double bx = (g < NV && k < NN) ? xr[k] : 0.0;
 #pragma unroll
                         for (int r = 0; r < TR; ++r)
-                            if (r < trn)
-                                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                                             : "+d"(cv[r][0]), "+d"(cv[r][1]) : "d"(a[r]), "d"(bx));
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                         : "+d"(cv[r][0]), "+d"(cv[r][1]) : "d"(a[r]), "d"(bx));
                     }
                 }
             }

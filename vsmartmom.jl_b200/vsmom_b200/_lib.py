@@ -46,13 +46,18 @@ class ColumnDesc(C.Structure):
                 ("surf_rho", c_void_p), ("ss_correction", f64p)]
 
 
+class LinDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("n_params", C.c_int32), ("dtau_aer", f64p), ("dalbedo", f64p),
+                ("dtau_rayl", c_void_p), ("dtau_abs", c_void_p)]
+
+
 EXPORTS = [
     "vsm_version", "vsm_create", "vsm_destroy", "vsm_last_error", "vsm_synchronize",
     "vsm_set_workspace_limit", "vsm_set_inverse_mode", "vsm_kernel_launches", "vsm_measure_fma_peak",
     "vsm_batched_mul_f64", "vsm_batched_mul_f32", "vsm_batch_inv_f64", "vsm_batch_inv_f32",
     "vsm_batch_solve_f64", "vsm_batch_solve_f32",
     "vsm_rt_layer_f64", "vsm_rt_layer_f32", "vsm_rt_column_f64", "vsm_rt_column_f32",
-    "vsm_rt_column_streams_f64", "vsm_rt_column_streams_f32",
+    "vsm_rt_column_streams_f64", "vsm_rt_column_streams_f32", "vsm_rt_column_lin_f64",
     "vsm_last_column_ms", "vsm_last_column_launches",
 ]
 
@@ -74,6 +79,7 @@ for _s in ("f64", "f32"):
     getattr(lib, f"vsm_rt_layer_{_s}").argtypes = [c_void_p, C.POINTER(LayerDesc)]
     getattr(lib, f"vsm_rt_column_{_s}").argtypes = [c_void_p, C.POINTER(ColumnDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     getattr(lib, f"vsm_rt_column_streams_{_s}").argtypes = [c_void_p, C.POINTER(ColumnDesc)] + [c_void_p] * 9
+lib.vsm_rt_column_lin_f64.argtypes = [c_void_p, C.POINTER(ColumnDesc), C.POINTER(LinDesc)] + [c_void_p] * 4
 lib.vsm_last_column_ms.argtypes = [c_void_p, C.POINTER(c_float), C.POINTER(c_float), C.POINTER(c_float)]
 lib.vsm_last_column_launches.argtypes = [c_void_p, C.POINTER(c_int), C.POINTER(c_int)]
 

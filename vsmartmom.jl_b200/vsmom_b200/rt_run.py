@@ -80,6 +80,37 @@ def _i32p(a: np.ndarray):
     return a.ctypes.data_as(_lib.i32p)
 
 
+def _column_desc(prep: PreparedColumn, tau_rayl: torch.Tensor, tau_abs: torch.Tensor, F0: torch.Tensor):
+    """The vsm_column_desc of one call plus the host arrays it points to (which must stay alive)."""
+    model = prep.model
+    q = model.quad_points
+    Nz, nS = tau_rayl.shape
+    nV, n = len(model.vza), model.pol_n
+    mu = np.ascontiguousarray(q.qp_muN, dtype=np.float64)
+    wt = np.ascontiguousarray(q.wt_muN, dtype=np.float64)
+    nAer = len(model.aerosol_optics)
+    om = np.array([a.omega for a in model.aerosol_optics] or [0.0], np.float64)
+    ft = np.array([a.ft for a in model.aerosol_optics] or [0.0], np.float64)
+    taer = np.ascontiguousarray(model.tau_aer.T if nAer else np.zeros((1, 1)), dtype=np.float64)  # (Nz, nAer) mem == Julia (nAer,Nz)
+    ctl = prep.ctl
+    nd = np.ascontiguousarray(ctl.ndoubl, np.int32); sc = np.ascontiguousarray(ctl.scatter, np.int32)
+    itf = np.ascontiguousarray(ctl.iface, np.int32); rz = np.ascontiguousarray(ctl.rayl_allzero, np.int32)
+    vs = np.ascontiguousarray(prep.vza_stream, np.int32)
+    d = _lib.ColumnDesc()
+    d.struct_size = C.sizeof(_lib.ColumnDesc)
+    d.N, d.nStokes, d.nSpec, d.Nz, d.nAer, d.nVZA = q.qp_muN.size, n, nS, Nz, nAer, nV
+    d.n_moments, d.imu0, d.surface_kind = model.m_max + 1, q.imu0, (1 if prep.surf_rho is not None else 0)
+    d.surf_rho = prep.surf_rho.data_ptr() if prep.surf_rho is not None else None
+    d.ss_correction = _f64p(prep.ss_correction) if prep.ss_correction is not None else None
+    d.mu0, d.albedo, d.varpi_cabannes = float(q.mu0), float(model.albedo), float(model.varpi_cabannes)
+    d.mu, d.wt, d.aer_omega, d.aer_ft, d.tau_aer = _f64p(mu), _f64p(wt), _f64p(om), _f64p(ft), _f64p(taer)
+    d.vza_weight = _f64p(prep.vza_weight)
+    d.ndoubl, d.scatter, d.iface, d.rayl_allzero, d.vza_stream = _i32p(nd), _i32p(sc), _i32p(itf), _i32p(rz), _i32p(vs)
+    d.tau_rayl, d.tau_abs, d.F0 = tau_rayl.data_ptr(), tau_abs.data_ptr(), F0.data_ptr()
+    d.Zpp, d.Zmp = prep.Zpp.data_ptr(), prep.Zmp.data_ptr()
+    return d, (mu, wt, om, ft, taer, nd, sc, itf, rz, vs)
+
+
 def rt_column_device(ctx: _lib.Context, prep: PreparedColumn, tau_rayl: torch.Tensor, tau_abs: torch.Tensor,
                      F0: torch.Tensor, want_hdr: bool = True, streams: Optional[dict] = None):
     """Device-resident entry: ``tau_rayl``/``tau_abs`` are (Nz, nS) torch CUDA tensors
@@ -103,28 +134,7 @@ def rt_column_device(ctx: _lib.Context, prep: PreparedColumn, tau_rayl: torch.Te
     H = torch.empty_like(R) if want_hdr else None
     uw = torch.empty((nS, n), dtype=dt, device=dev) if want_hdr else None
     dw = torch.empty((nS, n), dtype=dt, device=dev) if want_hdr else None
-    mu = np.ascontiguousarray(q.qp_muN, dtype=np.float64)
-    wt = np.ascontiguousarray(q.wt_muN, dtype=np.float64)
-    nAer = len(model.aerosol_optics)
-    om = np.array([a.omega for a in model.aerosol_optics] or [0.0], np.float64)
-    ft = np.array([a.ft for a in model.aerosol_optics] or [0.0], np.float64)
-    taer = np.ascontiguousarray(model.tau_aer.T if nAer else np.zeros((1, 1)), dtype=np.float64)  # (Nz, nAer) mem == Julia (nAer,Nz)
-    ctl = prep.ctl
-    nd = np.ascontiguousarray(ctl.ndoubl, np.int32); sc = np.ascontiguousarray(ctl.scatter, np.int32)
-    itf = np.ascontiguousarray(ctl.iface, np.int32); rz = np.ascontiguousarray(ctl.rayl_allzero, np.int32)
-    vs = np.ascontiguousarray(prep.vza_stream, np.int32)
-    d = _lib.ColumnDesc()
-    d.struct_size = C.sizeof(_lib.ColumnDesc)
-    d.N, d.nStokes, d.nSpec, d.Nz, d.nAer, d.nVZA = q.qp_muN.size, n, nS, Nz, nAer, nV
-    d.n_moments, d.imu0, d.surface_kind = model.m_max + 1, q.imu0, (1 if prep.surf_rho is not None else 0)
-    d.surf_rho = prep.surf_rho.data_ptr() if prep.surf_rho is not None else None
-    d.ss_correction = _f64p(prep.ss_correction) if prep.ss_correction is not None else None
-    d.mu0, d.albedo, d.varpi_cabannes = float(q.mu0), float(model.albedo), float(model.varpi_cabannes)
-    d.mu, d.wt, d.aer_omega, d.aer_ft, d.tau_aer = _f64p(mu), _f64p(wt), _f64p(om), _f64p(ft), _f64p(taer)
-    d.vza_weight = _f64p(prep.vza_weight)
-    d.ndoubl, d.scatter, d.iface, d.rayl_allzero, d.vza_stream = _i32p(nd), _i32p(sc), _i32p(itf), _i32p(rz), _i32p(vs)
-    d.tau_rayl, d.tau_abs, d.F0 = tau_rayl.data_ptr(), tau_abs.data_ptr(), F0.data_ptr()
-    d.Zpp, d.Zmp = prep.Zpp.data_ptr(), prep.Zmp.data_ptr()
+    d, _keep = _column_desc(prep, tau_rayl, tau_abs, F0)
     hp = (H.data_ptr() if want_hdr else None, uw.data_ptr() if want_hdr else None, dw.data_ptr() if want_hdr else None)
     if streams is not None:
         N, nM = q.qp_muN.size, model.m_max + 1
@@ -220,6 +230,68 @@ def rt_run_sharded(model: RTModel, ctx: Optional[_lib.Context] = None, device: O
                T_SFI=full[:, k:2 * k].reshape(-1, n, nV).transpose(2, 1, 0),
                hdr=full[:, 2 * k:3 * k].reshape(-1, n, nV).transpose(2, 1, 0),
                bhr_uw=full[:, 3 * k].copy(), bhr_dw=full[:, 3 * k + n].copy())
+    if own:
+        ctx.close()
+    return out
+
+
+def rt_run_lin(model: RTModel, dtau_rayl: Optional[np.ndarray] = None, dtau_abs: Optional[np.ndarray] = None,
+               dtau_aer: Optional[np.ndarray] = None, dalbedo: Optional[np.ndarray] = None,
+               ctx: Optional[_lib.Context] = None, device: str = "cuda:0"):
+    """LinMode: forward ``R_SFI``, ``T_SFI`` (nVZA, pol_n, nSpec) and the analytic Jacobians ``dR_SFI``, ``dT_SFI``
+    (P, nVZA, pol_n, nSpec) -- the reference's ``rt_run(model, lin_model, ...)`` (rt_run_lin.jl:102-326, outputs
+    :185-190) for P parameters given by the derivatives of the column inputs: ``dtau_rayl``, ``dtau_abs``
+    (P, nSpec, Nz), ``dtau_aer`` (P, nAer, Nz), ``dalbedo`` (P,); any may be None (= 0).  fp64."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("vsmom_b200.rt_run_lin needs a CUDA device (B200); there is no CPU fallback")
+    if model.float_type != np.float64:
+        raise ValueError("rt_run_lin is fp64 only")
+    given = [x for x in (dtau_rayl, dtau_abs, dtau_aer, dalbedo) if x is not None]
+    if not given:
+        raise ValueError("rt_run_lin: no parameter given")
+    P = int(np.asarray(given[0]).shape[0])
+    own = ctx is None
+    if own:
+        ctx = _lib.Context(torch.device(device).index or 0)
+    prep = prepare(model, device)
+    nS, Nz, n, nV = model.nSpec, model.Nz, model.pol_n, len(model.vza)
+    dev = torch.device(device)
+
+    def spectral(x):        # (P, nSpec, Nz) -> memory (P, Nz, nSpec) == Julia (nSpec, Nz, P)
+        if x is None:
+            return None
+        x = np.asarray(x, np.float64)
+        assert x.shape == (P, nS, Nz), x.shape
+        return torch.from_numpy(np.ascontiguousarray(x.transpose(0, 2, 1))).to(dev)
+    d_tr, d_ta = spectral(dtau_rayl), spectral(dtau_abs)
+    tr = torch.from_numpy(np.ascontiguousarray(model.tau_rayl.T)).to(dev)
+    ta = torch.from_numpy(np.ascontiguousarray(model.tau_abs.T)).to(dev)
+    f0 = np.zeros((nS, n)); f0[:, 0] = 1
+    F0 = torch.from_numpy(f0).to(dev)
+    d, _keep = _column_desc(prep, tr, ta, F0)
+    ld = _lib.LinDesc()
+    ld.struct_size, ld.n_params = C.sizeof(_lib.LinDesc), P
+    aer = None
+    if dtau_aer is not None and len(model.aerosol_optics):
+        aer = np.ascontiguousarray(np.asarray(dtau_aer, np.float64).transpose(0, 2, 1))     # (P, Nz, nAer) mem == (nAer,Nz,P)
+        assert aer.shape == (P, Nz, len(model.aerosol_optics))
+        ld.dtau_aer = _f64p(aer)
+    alb = None
+    if dalbedo is not None:
+        alb = np.ascontiguousarray(np.asarray(dalbedo, np.float64))
+        assert alb.shape == (P,)
+        ld.dalbedo = _f64p(alb)
+    ld.dtau_rayl = d_tr.data_ptr() if d_tr is not None else None
+    ld.dtau_abs = d_ta.data_ptr() if d_ta is not None else None
+    R = torch.empty((nS, n, nV), dtype=torch.float64, device=dev)
+    T = torch.empty_like(R)
+    dR = torch.empty((P, nS, n, nV), dtype=torch.float64, device=dev)
+    dT = torch.empty_like(dR)
+    ctx.check(_lib.lib.vsm_rt_column_lin_f64(ctx.handle, C.byref(d), C.byref(ld), R.data_ptr(), T.data_ptr(),
+                                             dR.data_ptr(), dT.data_ptr()))
+    ctx.synchronize()
+    out = dict(R_SFI=R.cpu().numpy().transpose(2, 1, 0), T_SFI=T.cpu().numpy().transpose(2, 1, 0),
+               dR_SFI=dR.cpu().numpy().transpose(0, 3, 2, 1), dT_SFI=dT.cpu().numpy().transpose(0, 3, 2, 1))
     if own:
         ctx.close()
     return out
