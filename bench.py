@@ -397,7 +397,7 @@ def run_b200(args):
     # the same step with the adaptive inverse switched off (Gauss-Jordan elimination for every
     # (I - A)^-1, the reference's getrf/getri route): reported inside `roofline`, not as the headline
     gj = None
-    if world == 1 and FT == np.float64 and not args.no_gj_compare:
+    if world == 1 and FT == np.float64 and not args.no_gj_compare and args.config == 2:
         ctx.set_inverse_mode(0)
         step_device()
         barrier()

@@ -209,6 +209,27 @@ typedef struct vsm_lin_desc {
 int vsm_rt_column_lin_f64(vsm_ctx*, const vsm_column_desc*, const vsm_lin_desc*, double* R_SFI, double* T_SFI,
                           double* dR, double* dT);
 
+/* -- several GPUs from ONE host process (the reference drives everything from a single Julia process and has no
+ * multi-GPU path: Architectures.jl:42-45 "Run on a single NVIDIA CUDA GPU").  vsm_multi_create opens one context
+ * (own stream) per listed device and an in-process NCCL communicator over them (ncclCommInitAll; NCCL is loaded
+ * with dlopen, VSM_ERR_UNSUPPORTED if libnccl.so.2 is absent).  vsm_rt_column_sharded_* runs the column of
+ * vsm_rt_column_* with the spectral axis cut into contiguous shards, one per device, no data-path collective (the
+ * ndoubl / scatter / iface arrays of the descriptor must come from the FULL band, as always), ONE ncclAllGather of
+ * the packed outputs, and returns the full-band result.  Differences to vsm_rt_column_*: the descriptor's
+ * tau_rayl, tau_abs, F0, Zpp, Zmp and surf_rho and all five outputs are HOST pointers (the library stages the
+ * shards), struct_size must be sizeof(vsm_column_desc), and the call blocks until the result is in host memory.
+ * Results are bit-identical to the single-device call. */
+typedef struct vsm_multi vsm_multi;
+int  vsm_multi_create(vsm_multi** out, const int* devices, int ndev);
+int  vsm_multi_destroy(vsm_multi*);
+const char* vsm_multi_last_error(vsm_multi*);       /* may be NULL: last create error */
+int  vsm_multi_ndev(vsm_multi*);
+vsm_ctx* vsm_multi_ctx(vsm_multi*, int rank);       /* the per-device context (e.g. for vsm_set_inverse_mode) */
+int vsm_rt_column_sharded_f64(vsm_multi*, const vsm_column_desc*, double* R_SFI, double* T_SFI, double* hdr,
+                              double* bhr_uw, double* bhr_dw);
+int vsm_rt_column_sharded_f32(vsm_multi*, const vsm_column_desc*, float* R_SFI, float* T_SFI, float* hdr,
+                              float* bhr_uw, float* bhr_dw);
+
 /* device time (ms) of the most recent vsm_rt_column_* call, measured with CUDA
  * events on the context's stream; blocks until that call has finished.        */
 int vsm_last_column_ms(vsm_ctx*, float* total_ms, float* doubling_ms, float* adding_ms);

@@ -516,3 +516,44 @@ def test_ocean_streamed_inverse_routes(ctx, scale):
     ad = run_gpu(m, ctx)
     assert_close(gj, ref, F64_TOL)
     assert_close(ad, ref, F64_TOL)
+
+
+# ----------------------------------------------------------------------------
+# several GPUs from one process behind the C-ABI (vsm_multi_create / vsm_rt_column_sharded_*)
+# ----------------------------------------------------------------------------
+def _multi_equals_single(devices, ctx, nspec=130):
+    from vsmom_b200 import _lib, rt_run as rr
+    m = vb.synthetic_o2a_model(nSpec=nspec, nstreams=4, aerosol=True)
+    single = run_gpu(m, ctx)
+    mc = _lib.MultiContext(devices)
+    try:
+        multi = rr.rt_run_multi(m, mc)
+        again = rr.rt_run_multi(m, mc)
+    finally:
+        mc.close()
+    for k in KEYS:
+        assert np.array_equal(multi[k], single[k]), k          # sharding changes nothing, bit for bit
+        assert np.array_equal(multi[k], again[k]), k
+
+
+def test_multi_context_one_device(ctx):
+    # the in-library sharded entry with a single device: staging, NCCL communicator of one rank, packing, unpacking
+    _multi_equals_single([0], ctx)
+
+
+def test_multi_context_two_devices_one_process(ctx):
+    # two GPUs driven from this one process (the Julia situation): ragged shards (130 points -> 96 + 34)
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _multi_equals_single([0, 1], ctx)
+    m = vb.synthetic_ocean_model(nSpec=40, nstreams=11, polarization_type="Stokes_IQUV")
+    trim_moments(m, 2)
+    from vsmom_b200 import _lib, rt_run as rr
+    mc = _lib.MultiContext([0, 1])
+    try:
+        multi = rr.rt_run_multi(m, mc)
+    finally:
+        mc.close()
+    single = run_gpu(m, ctx)
+    for k in KEYS:
+        assert np.array_equal(multi[k], single[k]), k

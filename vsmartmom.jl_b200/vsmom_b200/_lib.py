@@ -59,6 +59,8 @@ EXPORTS = [
     "vsm_rt_layer_f64", "vsm_rt_layer_f32", "vsm_rt_column_f64", "vsm_rt_column_f32",
     "vsm_rt_column_streams_f64", "vsm_rt_column_streams_f32", "vsm_rt_column_lin_f64",
     "vsm_last_column_ms", "vsm_last_column_launches",
+    "vsm_multi_create", "vsm_multi_destroy", "vsm_multi_last_error", "vsm_multi_ndev", "vsm_multi_ctx",
+    "vsm_rt_column_sharded_f64", "vsm_rt_column_sharded_f32",
 ]
 
 lib.vsm_version.restype = c_int
@@ -82,6 +84,17 @@ for _s in ("f64", "f32"):
 lib.vsm_rt_column_lin_f64.argtypes = [c_void_p, C.POINTER(ColumnDesc), C.POINTER(LinDesc)] + [c_void_p] * 4
 lib.vsm_last_column_ms.argtypes = [c_void_p, C.POINTER(c_float), C.POINTER(c_float), C.POINTER(c_float)]
 lib.vsm_last_column_launches.argtypes = [c_void_p, C.POINTER(c_int), C.POINTER(c_int)]
+
+
+lib.vsm_multi_create.argtypes = [C.POINTER(c_void_p), i32p, c_int]
+lib.vsm_multi_destroy.argtypes = [c_void_p]
+lib.vsm_multi_last_error.argtypes = [c_void_p]
+lib.vsm_multi_last_error.restype = C.c_char_p
+lib.vsm_multi_ndev.argtypes = [c_void_p]
+lib.vsm_multi_ctx.argtypes = [c_void_p, c_int]
+lib.vsm_multi_ctx.restype = c_void_p
+for _s in ("f64", "f32"):
+    getattr(lib, f"vsm_rt_column_sharded_{_s}").argtypes = [c_void_p, C.POINTER(ColumnDesc)] + [c_void_p] * 5
 
 
 class VsmError(RuntimeError):
@@ -138,6 +151,35 @@ class Context:
     def close(self):
         if getattr(self, "handle", None):
             lib.vsm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiContext:
+    """``vsm_multi``: several GPUs driven from this one process (in-library spectral sharding + one NCCL all-gather)."""
+
+    def __init__(self, devices):
+        import numpy as np
+        dv = np.ascontiguousarray(list(devices), np.int32)
+        h = c_void_p()
+        rc = lib.vsm_multi_create(C.byref(h), dv.ctypes.data_as(i32p), int(dv.size))
+        if rc != 0:
+            raise VsmError(f"vsm_multi_create failed ({rc}): {lib.vsm_multi_last_error(None).decode()}")
+        self.handle = h
+        self.devices = list(map(int, dv))
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise VsmError(f"libvsmom_b200 error {rc}: {lib.vsm_multi_last_error(self.handle).decode()}")
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib.vsm_multi_destroy(self.handle)
             self.handle = None
 
     def __del__(self):

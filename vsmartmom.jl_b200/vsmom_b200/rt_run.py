@@ -235,6 +235,31 @@ def rt_run_sharded(model: RTModel, ctx: Optional[_lib.Context] = None, device: O
     return out
 
 
+def rt_run_multi(model: RTModel, mctx: "_lib.MultiContext"):
+    """``rt_run`` on several GPUs driven from THIS process (``vsm_rt_column_sharded_*``): host arrays in, host arrays
+    out; the library shards the spectral axis over the devices of ``mctx`` and gathers with one NCCL all-gather."""
+    FT = model.float_type
+    Zpp, Zmp = z_tables(model)
+    stream, w = vza_tables(model)
+    prep = PreparedColumn(model, torch.from_numpy(Zpp), torch.from_numpy(Zmp), layer_control(model), stream,
+                          np.ascontiguousarray(w, dtype=np.float64), None,
+                          None if model.ss_correction is None else np.ascontiguousarray(np.asarray(model.ss_correction, np.float64).T))
+    if model.surface_rho is not None:
+        prep.surf_rho = torch.from_numpy(np.ascontiguousarray(np.asarray(model.surface_rho).transpose(0, 2, 1).astype(FT)))
+    nS, n, nV = model.nSpec, model.pol_n, len(model.vza)
+    tr = torch.from_numpy(np.ascontiguousarray(model.tau_rayl.T))       # (Nz, nSpec) mem == Julia (nSpec, Nz), HOST
+    ta = torch.from_numpy(np.ascontiguousarray(model.tau_abs.T))
+    f0 = np.zeros((nS, n), FT); f0[:, 0] = 1
+    F0 = torch.from_numpy(f0)
+    d, _keep = _column_desc(prep, tr, ta, F0)
+    R = np.empty((nS, n, nV), FT); T = np.empty_like(R); H = np.empty_like(R)
+    uw = np.empty((nS, n), FT); dw = np.empty_like(uw)
+    fn = _lib.lib.vsm_rt_column_sharded_f64 if FT == np.float64 else _lib.lib.vsm_rt_column_sharded_f32
+    mctx.check(fn(mctx.handle, C.byref(d), R.ctypes.data, T.ctypes.data, H.ctypes.data, uw.ctypes.data, dw.ctypes.data))
+    return dict(R_SFI=R.transpose(2, 1, 0), T_SFI=T.transpose(2, 1, 0), hdr=H.transpose(2, 1, 0),
+                bhr_uw=uw[:, 0].copy(), bhr_dw=dw[:, 0].copy())
+
+
 def rt_run_lin(model: RTModel, dtau_rayl: Optional[np.ndarray] = None, dtau_abs: Optional[np.ndarray] = None,
                dtau_aer: Optional[np.ndarray] = None, dalbedo: Optional[np.ndarray] = None,
                ctx: Optional[_lib.Context] = None, device: str = "cuda:0"):
