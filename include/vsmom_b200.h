@@ -233,6 +233,11 @@ int vsm_rt_column_sharded_f32(vsm_multi*, const vsm_column_desc*, float* R_SFI, 
 /* device time (ms) of the most recent vsm_rt_column_* call, measured with CUDA
  * events on the context's stream; blocks until that call has finished.        */
 int vsm_last_column_ms(vsm_ctx*, float* total_ms, float* doubling_ms, float* adding_ms);
+/* failure detection for the fused column (the reference allocates cuBLAS' info arrays but never reads them,
+ * gpu_batched_cuda.jl:146-153): the number of R_SFI / T_SFI elements of the most recent vsm_rt_column_* call that
+ * are not finite -- a singular (I - A) or an overflow anywhere in a spectral point's chain ends up there.  Blocks
+ * until that call has finished.  (vsm_batch_inv_* reports per-slice zero pivots through its info array.) */
+int vsm_last_column_status(vsm_ctx*, int* nonfinite_outputs);
 /* number of k_layer (elemental+doubling) and k_adding launches of that call */
 int vsm_last_column_launches(vsm_ctx*, int* layer_launches, int* adding_launches);
 

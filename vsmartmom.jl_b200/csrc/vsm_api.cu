@@ -617,6 +617,7 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
         }
     }
 
+    CK(cudaMemsetAsync((int*)ctx->counter.p + 16, 0, 4, ctx->stream));       // non-finite output counter of this call
     // timing events
     ctx->ev_used = 0;
     ctx->seg_layer.clear();
@@ -709,7 +710,7 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
         k_reduce<T><<<(unsigned)((per_m + 255) / 256), 256, 0, ctx->stream>>>(
             nM, per_m, a.part_R, a.part_T, hdr ? a.part_H : (const T*)nullptr,
             R_SFI + (size_t)n0 * nOut, T_SFI + (size_t)n0 * nOut, hdr ? hdr + (size_t)n0 * nOut : (T*)nullptr,
-            ss_corr ? cT + o_ss : (const T*)nullptr, pa.tausum + (size_t)Nz * nS, (T)d->mu0, nOut);
+            ss_corr ? cT + o_ss : (const T*)nullptr, pa.tausum + (size_t)Nz * nS, (T)d->mu0, nOut, (int*)ctx->counter.p + 16);
         ctx->launches++;
         CK(cudaGetLastError());
         if (bhr_uw) CK(cudaMemcpyAsync(bhr_uw + (size_t)n0 * nSt, cb_uw, (size_t)nSt * nS * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -969,6 +970,15 @@ extern "C" int vsm_last_column_ms(vsm_ctx* ctx, float* total_ms, float* doubling
     if (total_ms) *total_ms = t;
     if (doubling_ms) *doubling_ms = tl;
     if (adding_ms) *adding_ms = ta;
+    return VSM_OK;
+}
+
+extern "C" int vsm_last_column_status(vsm_ctx* ctx, int* nonfinite_outputs) {
+    if (!ctx || !nonfinite_outputs) return VSM_ERR_INVALID_ARG;
+    if (!ctx->timing_valid || !ctx->counter.p) return fail(ctx, VSM_ERR_INVALID_ARG, "vsm_last_column_status: no column call yet");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(nonfinite_outputs, (int*)ctx->counter.p + 16, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return VSM_OK;
 }
 

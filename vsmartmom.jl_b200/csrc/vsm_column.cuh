@@ -1258,7 +1258,7 @@ template <typename T>
 __global__ void k_reduce(int n_moments, size_t per_m, const T* __restrict__ pR,
                          const T* __restrict__ pT, const T* __restrict__ pH, T* __restrict__ R,
                          T* __restrict__ Tt, T* __restrict__ H, const T* __restrict__ ss,
-                         const T* __restrict__ tau_total, T mu0, int nOut) {
+                         const T* __restrict__ tau_total, T mu0, int nOut, int* __restrict__ nonfinite = nullptr) {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= per_m) return;
     T r = T(0), t = T(0), h = T(0);
@@ -1268,6 +1268,8 @@ __global__ void k_reduce(int n_moments, size_t per_m, const T* __restrict__ pR,
         if (H) h += pH[(size_t)m * per_m + e];
     }
     if (ss) r += (mu0 * Num<T>::exp_(-tau_total[e / nOut] / mu0)) * ss[e % nOut];
+    // a singular (I - A) or an overflow anywhere upstream ends up here as Inf / NaN: counted per call
+    if (nonfinite && !(Num<T>::abs_(r) <= T(1e300) && Num<T>::abs_(t) <= T(1e300))) atomicAdd(nonfinite, 1);
     R[e] = r;
     Tt[e] = t;
     if (H) H[e] = h;

@@ -635,8 +635,8 @@ __device__ __forceinline__ void add_step11_stream(const OpsStream<CF>& op, Strea
     tmp = c.J0pc; c.J0pc = c.J0pnew; c.J0pnew = tmp;
 }
 
-template <class CF>
-__global__ void __launch_bounds__(CF::NTHR, 1) k_adding_stream(ColArgs<double> a, unsigned int total) {
+template <class CF, int MINB>
+__global__ void __launch_bounds__(CF::NTHR, MINB) k_adding_stream(ColArgs<double> a, unsigned int total) {
     using T = double;
     constexpr int n = CF::NN, NP = CF::NP, ld = CF::LD;
     StreamSmem<CF> sm;

@@ -58,7 +58,7 @@ EXPORTS = [
     "vsm_batch_solve_f64", "vsm_batch_solve_f32",
     "vsm_rt_layer_f64", "vsm_rt_layer_f32", "vsm_rt_column_f64", "vsm_rt_column_f32",
     "vsm_rt_column_streams_f64", "vsm_rt_column_streams_f32", "vsm_rt_column_lin_f64",
-    "vsm_last_column_ms", "vsm_last_column_launches",
+    "vsm_last_column_ms", "vsm_last_column_launches", "vsm_last_column_status",
     "vsm_multi_create", "vsm_multi_destroy", "vsm_multi_last_error", "vsm_multi_ndev", "vsm_multi_ctx",
     "vsm_rt_column_sharded_f64", "vsm_rt_column_sharded_f32",
 ]
@@ -84,6 +84,7 @@ for _s in ("f64", "f32"):
 lib.vsm_rt_column_lin_f64.argtypes = [c_void_p, C.POINTER(ColumnDesc), C.POINTER(LinDesc)] + [c_void_p] * 4
 lib.vsm_last_column_ms.argtypes = [c_void_p, C.POINTER(c_float), C.POINTER(c_float), C.POINTER(c_float)]
 lib.vsm_last_column_launches.argtypes = [c_void_p, C.POINTER(c_int), C.POINTER(c_int)]
+lib.vsm_last_column_status.argtypes = [c_void_p, C.POINTER(c_int)]
 
 
 lib.vsm_multi_create.argtypes = [C.POINTER(c_void_p), i32p, c_int]
@@ -147,6 +148,12 @@ class Context:
         a, b = c_int(), c_int()
         self.check(lib.vsm_last_column_launches(self.handle, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def last_column_nonfinite(self) -> int:
+        """Number of non-finite R_SFI / T_SFI elements of the most recent column call (0 = healthy)."""
+        v = c_int()
+        self.check(lib.vsm_last_column_status(self.handle, C.byref(v)))
+        return v.value
 
     def close(self):
         if getattr(self, "handle", None):
