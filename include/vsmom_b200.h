@@ -173,6 +173,16 @@ typedef struct vsm_column_desc {
      * (apply_ss_correction!, Surfaces/coxmunk_surface.jl:509-555, called at rt_run.jl:520-524).  The library adds
      * R_SFI[iv,si,s] += mu0 * exp(-tau_sum_all[s,end]/mu0) * ss_correction[iv,si] in its output reduction. */
     const double* ss_correction;
+    /* device, FT, may be NULL -- only read when struct_size covers them: extra sources of the v0.7 source-term
+     * seam (per-source j0 slots, doubling.jl:66-80, interaction.jl:231-259).
+     *  thermal_B (Nz,nSpec): ThermalEmission.B_layer, the Planck radiance of every layer.  At m = 0 each scattering
+     *    elemental layer gets the volume source 2 pi (1-varpi) B (1-exp(-dtau/mu_i)) on its Stokes-I rows
+     *    (contribute!, Sources/thermal_emission.jl:236-316) in its own slot, doubled with expk = 1, then joined
+     *    with the solar slot (the interaction step treats all slots alike and the outputs add, postprocessing_vza.jl:67-80).
+     *  sif0 (nStokes,nSpec): SurfaceSIF.SIF0, injected as 2*SIF0 into the Lambertian surface's j0- at m = 0
+     *    (surface_source_contribute!, Sources/surface_sif.jl:168-178). */
+    const void* thermal_B;
+    const void* sif0;
 } vsm_column_desc;
 /* outputs: device; R_SFI/T_SFI/hdr (nVZA,nStokes,nSpec); bhr_* (nStokes,nSpec);
  * hdr/bhr_uw/bhr_dw may be NULL.  Outputs are overwritten (not accumulated).  */

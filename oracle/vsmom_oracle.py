@@ -351,6 +351,10 @@ class Model:
     # Cox-Munk TMS correction (apply_ss_correction!, rt_run.jl:520-524): (nVZA, pol_n) geometry factor from
     # coxmunk_ss_correction(); None = no correction (any surface other than CoxMunkSurface)
     ss_correction: Optional[np.ndarray] = None
+    # extra sources (rt_run(model; sources = SourceSet(...))): ThermalEmission.B_layer as (nSpec, Nz) and
+    # SurfaceSIF.SIF0 as (nSpec, pol_n); None = absent
+    thermal_B: Optional[np.ndarray] = None
+    sif0: Optional[np.ndarray] = None
 
     @property
     def nSpec(self):
@@ -1225,10 +1229,24 @@ def coxmunk_ss_correction(surf: CoxMunk, pol_n: int, vza, vaz, mu0: float, m_max
 # --------------------------------------------------------------------------
 # rt_run (noRS, SFI)   src/CoreRT/rt_run.jl:238-539, rt_kernel.jl:175-250
 # --------------------------------------------------------------------------
+def thermal_elemental(model: Model, dtau, varpi, B):
+    """contribute!(::PreparedThermalEmission, ...) (Sources/thermal_emission.jl:236-316) at m = 0: the Planck volume
+    source of one elemental layer, 2 pi (1 - varpi) B (1 - exp(-dtau/mu_i)) on the Stokes-I rows of j0+ and j0-."""
+    FT = model.FT
+    q = model.quad
+    mu = q.qp_muN.astype(FT)
+    j = np.zeros((dtau.shape[0], mu.size), FT)
+    rows = np.arange(0, mu.size, model.pol_n)
+    ok = mu[rows] > np.finfo(FT).eps
+    coeff = (FT(2 * math.pi) * (1 - varpi) * B)[:, None]
+    j[:, rows[ok]] = coeff * (-np.expm1(-dtau[:, None] / mu[rows[ok]][None, :]))
+    return j
+
+
 def rt_kernel_layer(model: Model, m: int, iz: int, ctl: BandControl, props: CoreProps,
-                    C: Optional[Composite], F0, tau_sum_iz):
+                    C: Optional[Composite], F0, tau_sum_iz, thermal_B=None):
     """One layer of rt_kernel!(::noRS, ...) for the selected spectral points.
-    Returns the updated composite (created at iz == 0)."""
+    Returns the updated composite (created at iz == 0).  thermal_B: B_layer[iz] of the selected points, or None."""
     FT = model.FT
     q = model.quad
     nS = props.tau.shape[0]
@@ -1239,8 +1257,21 @@ def rt_kernel_layer(model: Model, m: int, iz: int, ctl: BandControl, props: Core
         expk = np.exp(-dtau / FT(q.mu0))
         r, t, r_pm, t_mm, j0p, j0m = elemental(model, m, nd, dtau, props.varpi,
                                                props.Zpp, props.Zmp, tau_sum_iz, F0)
+        if thermal_B is not None and m == 0:
+            # the :thermal slot of j0_by_src (rt_kernel.jl:211-225): its own doubling with expk = ones
+            # (doubling.jl:66-80, apply_D on the slot :92-94); the interaction step then updates every slot with the
+            # same operators (interaction.jl:231-259) and the outputs add (postprocessing_vza.jl:67-80), so the doubled
+            # slot is joined with the solar vectors here
+            jt = thermal_elemental(model, dtau, props.varpi, thermal_B)
+            jtp, jtm = jt, jt.copy()
+            if nd > 0:
+                _, _, _, _, jtp, jtm = doubling(model, nd, np.ones_like(expk), r, t, jtp, jtm)
+        else:
+            jtp = jtm = None
         if nd > 0:
             r, t, r_pm, t_mm, j0p, j0m = doubling(model, nd, expk, r, t, j0p, j0m)
+        if jtp is not None:
+            j0p, j0m = j0p + jtp, j0m + jtm
     else:
         # zero_added_noscat!, rt_helpers.jl:174-180 (j₀⁺ is left untouched by the
         # reference; it is never read by the 00/10 interaction with zero sources
@@ -1305,13 +1336,17 @@ def rt_run(model: Model, sel=slice(None), return_streams: bool = False, prep: Op
         C = None
         for iz in range(model.Nz):
             C = rt_kernel_layer(model, m, iz, ctl, props[iz], C, F0,
-                                ctl.tau_sum[idx, iz])
+                                ctl.tau_sum[idx, iz],
+                                None if model.thermal_B is None else np.asarray(model.thermal_B, FT)[idx, iz])
         # surface + final interaction (rt_run.jl:423-465)
         if model.surface_rho is not None:
             s = brdf_surface(model, m, ctl.tau_sum[idx, -1])
         else:
             s = lambertian_surface(model, m, ctl.tau_sum[idx, -1])
         r_mp_s, r_pm_s, t_s, t_mm_s, j0p_s, j0m_s = s
+        if model.sif0 is not None and model.surface_rho is None and m == 0:
+            # surface_source_contribute!(::PreparedSurfaceSIF, ::Lambertian...) (Sources/surface_sif.jl:168-178)
+            j0m_s = j0m_s + FT(2) * np.tile(np.asarray(model.sif0, FT)[idx], (1, q.Nquad))
         C = interaction(ctl.interface[-1], C, r_mp_s, r_pm_s, t_s, t_mm_s, j0p_s, j0m_s)
         # interaction_hdrf!, interaction_hdrf.jl:4-42
         hdr_J0m = _mv(r_mp_s, C.J0p) + j0m_s

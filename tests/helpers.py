@@ -31,7 +31,8 @@ def to_oracle(model: vb.RTModel) -> orc.Model:
                      varpi_cabannes=model.varpi_cabannes,
                      dtau_max_threshold=model.numerics.dtau_max_threshold,
                      dtau_min_floor=model.numerics.dtau_min_floor, FT=model.float_type,
-                     surface_rho=model.surface_rho, ss_correction=model.ss_correction)
+                     surface_rho=model.surface_rho, ss_correction=model.ss_correction,
+                     thermal_B=model.thermal_B, sif0=model.sif0)
 
 
 def rayleigh_slab_model(pol, nstreams, sza, vza, vaz, tau, albedo, FT=np.float64, nSpec=2, depol=0.0):

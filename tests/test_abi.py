@@ -34,9 +34,10 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_header_layout():
     from vsmom_b200 import _lib
-    # 12 int32 + 1 double + 20 pointers ; 10 int32 + 3 double + 18 pointers (16 before surf_rho, 17 before ss_correction)
+    # 12 int32 + 1 double + 20 pointers ; 10 int32 + 3 double + 20 pointers (16 before surf_rho, 17 before ss_correction, 18 before thermal_B)
     assert ctypes.sizeof(_lib.LayerDesc) == 12 * 4 + 8 + 20 * 8
-    assert ctypes.sizeof(_lib.ColumnDesc) == 10 * 4 + 3 * 8 + 18 * 8
+    assert ctypes.sizeof(_lib.ColumnDesc) == 10 * 4 + 3 * 8 + 20 * 8
+    assert _lib.ColumnDesc.thermal_B.offset == 10 * 4 + 3 * 8 + 18 * 8     # the pre-sources descriptor size, still accepted
     assert _lib.ColumnDesc.surf_rho.offset == 10 * 4 + 3 * 8 + 16 * 8      # the pre-BRDF descriptor size, still accepted
     assert _lib.ColumnDesc.ss_correction.offset == 10 * 4 + 3 * 8 + 17 * 8  # the pre-Cox-Munk descriptor size, still accepted
     assert ctypes.sizeof(_lib.LinDesc) == 2 * 4 + 4 * 8

@@ -425,12 +425,15 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
     if (!ctx) return VSM_ERR_INVALID_ARG;
     // struct_size versions the descriptor: the layout up to Zmp (Lambertian only) or the full one
     // (Lambertian only), up to surf_rho (BRDF moments), or the full one (+ Cox-Munk TMS correction)
+    // + extra sources: thermal emission, surface SIF)
     if (!d || (d->struct_size != (int)sizeof(vsm_column_desc) && d->struct_size != (int)offsetof(vsm_column_desc, surf_rho) &&
-               d->struct_size != (int)offsetof(vsm_column_desc, ss_correction)))
+               d->struct_size != (int)offsetof(vsm_column_desc, ss_correction) && d->struct_size != (int)offsetof(vsm_column_desc, thermal_B)))
         return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column: descriptor NULL or struct_size mismatch");
     const void* surf_rho = (d->struct_size >= (int)offsetof(vsm_column_desc, ss_correction) && d->surface_kind == VSM_SURFACE_BRDF_FOURIER)
                                ? d->surf_rho : nullptr;
-    const double* ss_corr = (d->struct_size == (int)sizeof(vsm_column_desc)) ? d->ss_correction : nullptr;
+    const double* ss_corr = (d->struct_size >= (int)offsetof(vsm_column_desc, thermal_B)) ? d->ss_correction : nullptr;
+    const void* therm_B = (d->struct_size == (int)sizeof(vsm_column_desc)) ? d->thermal_B : nullptr;
+    const void* sif0 = (d->struct_size == (int)sizeof(vsm_column_desc)) ? d->sif0 : nullptr;
     if (d->nSpec == 0) return VSM_OK;            // empty shard: nothing to do
     if (!R_SFI || !T_SFI) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column: R_SFI/T_SFI NULL");
     const int N = d->N, nSt = d->nStokes, Nz = d->Nz, nAer = d->nAer, nV = d->nVZA, nM = d->n_moments;
@@ -668,6 +671,7 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
         a.st_Rmp = st_Rmp; a.st_Tpp = st_Tpp; a.st_Jm = st_Jm; a.st_Jp = st_Jp;
         a.st_off = (size_t)n0; a.st_nspec = (size_t)nSpec;
         a.add_mstride = mstride; a.surf_pad = surf_pad;
+        a.therm_B = (const T*)therm_B; a.sif0 = (const T*)sif0;
 
         for (int m0 = 0; m0 < nM; m0 += Mb) {
             const int mb = std::min(Mb, nM - m0);

@@ -160,6 +160,9 @@ struct ColArgs {
     const unsigned char* gcls;                        // k_geom branch classes (N,N) + [N]
     // added-layer scratch: slot = (mi*n_sched_layers + sched_idx[iz])*nS + p   (scattering layers only)
     T* add_r; T* add_t; T* add_jp; T* add_jm;
+    // extra sources (Sources/thermal_emission.jl, Sources/surface_sif.jl), both optional:
+    const T* therm_B;        // ThermalEmission.B_layer (Nz, nSpec_total): Planck radiance per layer, volume source at m = 0
+    const T* sif0;           // SurfaceSIF.SIF0 (nStokes, nSpec_total): surface emission injected into the surface j0- at m = 0
     size_t add_mstride;      // elements per hand-off matrix: N*N (dense) or LD*NP (streamed kernels, padded layout)
     const T* surf_pad;       // streamed kernels: R_surf Diagonal(mu w) per moment in the padded layout, or null
     // spill slabs and the work counter
@@ -353,9 +356,12 @@ __device__ __forceinline__ void elemental_fill(const ColArgs<T>& a, int m, int n
 // (the reference forms (X2 r) t; the product is re-associated so that one scratch
 //  matrix less is live, which lets a third CTA share the SM).
 // ----------------------------------------------------------------------------
+// sjp / sjm (optional): a per-source slot j0+- with its own expk == 1 (ThermalEmission: the sub-layer's emission is
+// not pre-attenuated, doubling.jl:66-80), doubled alongside the solar vectors with the same operators; sv1 / sv2 scratch.
 template <typename T, class Ops>
 __device__ __forceinline__ void doubling_loop(const Ops& op, int nd, T expk, T*& r, T*& t, T*& X1,
-                                              T* X2, T* jp, T* jm, T* j1p, T* j1m, T* v1, T* v2) {
+                                              T* X2, T* jp, T* jm, T* j1p, T* j1m, T* v1, T* v2,
+                                              T* sjp = nullptr, T* sjm = nullptr, T* sv1 = nullptr, T* sv2 = nullptr) {
     const int n = op.N(), ld = op.LD();
     // the matrix-vector products of the source update ride along with the matrix products that
     // share their left operand (one extra 8-column tile on the tensor-core path)
@@ -377,6 +383,10 @@ __device__ __forceinline__ void doubling_loop(const Ops& op, int nd, T expk, T*&
         VSM_TICK(2);
         op.template mm<false>(t, X1, [&](int i, int j, T acc) { X2[i + j * ld] = acc; });   // X2 = t gp (:105)
         op.sync();
+        if (sjp) {      // doubling_source_update! of the slot (doubling.jl:72-76) with expk = 1: j1 = j
+            op.mv2(r, sjp, sjm, [&](int i, T s) { sv1[i] = sjm[i] + s; }, [&](int i, T s) { sv2[i] = sjp[i] + s; });
+            op.mv2(X2, sv1, sv2, [&](int i, T s) { sjm[i] = sjm[i] + s; }, [&](int i, T s) { sjp[i] = sjp[i] + s; });
+        }
         VSM_TICK(3);
         // doubling_rt_update! (:162-163)
         op.template mm<false>(r, t, [&](int i, int j, T acc) { X1[i + j * ld] = acc; });
@@ -396,10 +406,25 @@ __device__ __forceinline__ void doubling_loop(const Ops& op, int nd, T expk, T*&
     }
 }
 
+// ThermalEmission volume source of one elemental layer (contribute!, Sources/thermal_emission.jl:236-316):
+// j0+-[I rows] = 2 pi (1 - varpi) B_layer[iz, n] (1 - exp(-dtau/mu_i)), zero for Q/U/V rows and zero-mu streams; m = 0 only
+template <typename T>
+__device__ __forceinline__ void thermal_fill(const ColArgs<T>& a, int n, int iz, int p, T dtau, T varpi, T* sjp, T* sjm) {
+    const T B = a.therm_B[iz + (size_t)a.Nz * (a.F0_off + p)];
+    const T coeff = T(6.283185307179586) * (T(1) - varpi) * B;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const T mui = a.mu[i];
+        const T v = ((i % a.nStokes) == 0 && mui > Num<T>::eps()) ? coeff * (-Num<T>::expm1_(-dtau / mui)) : T(0);
+        sjp[i] = v;
+        sjm[i] = v;
+    }
+}
+
 constexpr int kLayerMats = 4;
 constexpr int kAddMats = 9;
-// vector scratch (in units of n elements of T) shared by both kernels: 6 vectors + vec(5) + part(8)
-constexpr int kVecUnits = 19;
+// vector scratch (in units of n elements of T) shared by both kernels: 6 vectors + vec(5) + part(8) + the
+// per-source slot of k_layer (4)
+constexpr int kVecUnits = 23;
 
 template <typename T, class Ops, int NN, int NTHR, int MINB>
 __global__ void __launch_bounds__(NTHR, MINB) k_layer(ColArgs<T> a, unsigned int total) {
@@ -413,7 +438,8 @@ __global__ void __launch_bounds__(NTHR, MINB) k_layer(ColArgs<T> a, unsigned int
     T* vbase = sm + nsm * msz;
     T* jp = vbase;           T* jm = jp + n;     T* j1p = jm + n;   T* j1m = j1p + n;
     T* v1 = j1m + n;         T* v2 = v1 + n;     T* vec = v2 + n;   /* 5n */
-    T* part = vec + 5 * n;   /* 8n */            T* Wc = part + 8 * n;   /* kMaxComp */
+    T* part = vec + 5 * n;   /* 8n */            T* sjp = part + 8 * n;  T* sjm = sjp + n;  T* sv1 = sjm + n;  T* sv2 = sv1 + n;
+    T* Wc = sv2 + n;         /* kMaxComp */
     uint32_t* dmask = reinterpret_cast<uint32_t*>(Wc + kMaxComp);
     int* piv = reinterpret_cast<int*>(dmask + n);
     __shared__ unsigned int sh_item;
@@ -453,9 +479,11 @@ __global__ void __launch_bounds__(NTHR, MINB) k_layer(ColArgs<T> a, unsigned int
         VSM_T0();
         elemental_fill<T, NN>(a, m, nd, dtau, varpi, tausum, Wc, Zpp, Zmp, zstride,
                               a.F0 + (a.F0_off + p) * a.nStokes, dmask, r, t, jp, jm, part, j1p);
+        const bool thermal = (a.therm_B != nullptr) && (m == 0);
+        if (thermal) thermal_fill<T>(a, n, iz, p, dtau, varpi, sjp, sjm);
         __syncthreads();
         VSM_TICK(0);
-        doubling_loop<T, Ops>(op, nd, expk, r, t, X1, X2, jp, jm, j1p, j1m, v1, v2);
+        doubling_loop<T, Ops>(op, nd, expk, r, t, X1, X2, jp, jm, j1p, j1m, v1, v2, thermal ? sjp : nullptr, sjm, sv1, sv2);
         VSM_TICK(8);
         // apply_D_matrix! / apply_D_matrix_SFI! (doubling.jl:178-216): r⁻⁺ <- D r*, j₀⁻ <- D j*
         const size_t slot = ((size_t)mi * a.n_sched_layers + si) * a.nS + p;
@@ -468,10 +496,13 @@ __global__ void __launch_bounds__(NTHR, MINB) k_layer(ColArgs<T> a, unsigned int
             gr[e] = rv;
             gt[e] = t[i + j * ld];
         }
+        // (the interaction step is linear in the sources and treats every slot alike -- interaction.jl:229-259 --
+        //  so the doubled per-source slot joins the solar vectors here)
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            T vm = jm[i];
+            T vm = jm[i], vp = jp[i];
+            if (thermal) { vm += sjm[i]; vp += sjp[i]; }
             if (nd >= 1) vm = Num<T>::flip(vm, dmask[i]);
-            a.add_jp[slot * n + i] = jp[i];
+            a.add_jp[slot * n + i] = vp;
             a.add_jm[slot * n + i] = vm;
         }
         VSM_TICK(9);
@@ -774,6 +805,8 @@ __global__ void __launch_bounds__(NTHR) k_adding(ColArgs<T> a, unsigned int tota
                 const T rho = rho_m ? rho_m[i + (size_t)a.istart * n] : (((i % a.nStokes) == 0) ? rho_l : T(0));
                 jp[i] = (i == a.istart) ? att : T(0);
                 jm[i] = a.mu0 * rho * att;
+                // SurfaceSIF on a Lambertian surface (surface_source_contribute!, Sources/surface_sif.jl:168-178)
+                if (a.sif0 && !rho_m && m == 0) jm[i] += T(2) * a.sif0[(i % a.nStokes) + (size_t)a.nStokes * (a.F0_off + p)];
             }
             jps_sun = att;
             __syncthreads();
@@ -1076,6 +1109,7 @@ __global__ void __launch_bounds__(2 * GT, 1) k_adding2(ColArgs<T> a, unsigned in
                 const T rho = rho_m ? rho_m[i + (size_t)a.istart * n] : (((i % a.nStokes) == 0) ? rho_l : T(0));
                 sjp[i] = (i == a.istart) ? att : T(0);
                 sjm[i] = a.mu0 * rho * att;
+                if (a.sif0 && !rho_m && m == 0) sjm[i] += T(2) * a.sif0[(i % a.nStokes) + (size_t)a.nStokes * (a.F0_off + p)];
             }
             if (b) lr1 = r; else lr0 = r;
             jps_sun = att;

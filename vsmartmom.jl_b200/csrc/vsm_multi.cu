@@ -61,7 +61,7 @@ struct vsm_multi {
     std::vector<cudaStream_t> stream;
     std::vector<ncclComm_t> comm;
     // per-device grow-only buffers: inputs (tau_rayl, tau_abs, F0, Zpp, Zmp, surf_rho), outputs, packed rows, gathered rows
-    std::vector<DBuf> tr, ta, f0, zpp, zmp, rho, out, pack, gath;
+    std::vector<DBuf> tr, ta, f0, zpp, zmp, rho, out, pack, gath, thb, sif;
     std::string err;
 };
 
@@ -90,7 +90,7 @@ extern "C" int vsm_multi_create(vsm_multi** out, const int* devices, int ndev) {
     m->dev.assign(devices, devices + ndev);
     m->ctx.assign(ndev, nullptr); m->stream.assign(ndev, nullptr); m->comm.assign(ndev, nullptr);
     m->tr.resize(ndev); m->ta.resize(ndev); m->f0.resize(ndev); m->zpp.resize(ndev); m->zmp.resize(ndev);
-    m->rho.resize(ndev); m->out.resize(ndev); m->pack.resize(ndev); m->gath.resize(ndev);
+    m->rho.resize(ndev); m->out.resize(ndev); m->pack.resize(ndev); m->gath.resize(ndev); m->thb.resize(ndev); m->sif.resize(ndev);
     for (int r = 0; r < ndev; ++r) {
         if (cudaSetDevice(devices[r]) != cudaSuccess || cudaStreamCreateWithFlags(&m->stream[r], cudaStreamNonBlocking) != cudaSuccess) {
             cudaGetLastError();
@@ -121,7 +121,7 @@ extern "C" int vsm_multi_destroy(vsm_multi* m) {
         if (m->stream[r]) cudaStreamSynchronize(m->stream[r]);
         if (m->comm[r] && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm[r]);
         if (m->ctx[r]) vsm_destroy(m->ctx[r]);
-        for (DBuf* b : {&m->tr[r], &m->ta[r], &m->f0[r], &m->zpp[r], &m->zmp[r], &m->rho[r], &m->out[r], &m->pack[r], &m->gath[r]})
+        for (DBuf* b : {&m->tr[r], &m->ta[r], &m->f0[r], &m->zpp[r], &m->zmp[r], &m->rho[r], &m->out[r], &m->pack[r], &m->gath[r], &m->thb[r], &m->sif[r]})
             if (b->p) cudaFree(b->p);
         if (m->stream[r]) cudaStreamDestroy(m->stream[r]);
     }
@@ -183,6 +183,16 @@ static int column_sharded(vsm_multi* m, const vsm_column_desc* d, T* R, T* Tt, T
         if (brdf) MCK(cudaMemcpyAsync(m->rho[r].p, d->surf_rho, (size_t)N * N * nM * sizeof(T), cudaMemcpyHostToDevice, s));
         vsm_column_desc dd = *d;
         dd.nSpec = nS;
+        if (d->thermal_B) {      // (Nz, nSpec): the shard's columns are contiguous
+            if (grow(m->thb[r], (size_t)nS * Nz * sizeof(T))) return mfail(m, VSM_ERR_NOMEM, "rt_column_sharded: cudaMalloc failed");
+            MCK(cudaMemcpyAsync(m->thb[r].p, (const T*)d->thermal_B + (size_t)lo * Nz, (size_t)nS * Nz * sizeof(T), cudaMemcpyHostToDevice, s));
+            dd.thermal_B = m->thb[r].p;
+        }
+        if (d->sif0) {           // (nStokes, nSpec)
+            if (grow(m->sif[r], (size_t)nS * nSt * sizeof(T))) return mfail(m, VSM_ERR_NOMEM, "rt_column_sharded: cudaMalloc failed");
+            MCK(cudaMemcpyAsync(m->sif[r].p, (const T*)d->sif0 + (size_t)lo * nSt, (size_t)nS * nSt * sizeof(T), cudaMemcpyHostToDevice, s));
+            dd.sif0 = m->sif[r].p;
+        }
         dd.tau_rayl = m->tr[r].p; dd.tau_abs = m->ta[r].p; dd.F0 = m->f0[r].p; dd.Zpp = m->zpp[r].p; dd.Zmp = m->zmp[r].p;
         dd.surf_rho = brdf ? m->rho[r].p : nullptr;
         T* o = (T*)m->out[r].p;

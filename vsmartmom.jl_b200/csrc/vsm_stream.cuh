@@ -415,7 +415,8 @@ struct OpsStream {
 template <class CF>
 __device__ __forceinline__ void doubling_stream(const OpsStream<CF>& op, int nd, double expk, double*& r, double*& t,
                                                 double*& X1, double* X2, double* W, double* jp, double* jm, double* j1p,
-                                                double* j1m, double* v1, double* v2) {
+                                                double* j1m, double* v1, double* v2, double* sjp = nullptr, double* sjm = nullptr,
+                                                double* sv1 = nullptr, double* sv2 = nullptr) {
     using T = double;
     constexpr int n = CF::NN, ld = CF::LD;
     auto at = [](T* M, int i, int j) -> T& { return M[i + (size_t)j * ld]; };
@@ -435,6 +436,10 @@ __device__ __forceinline__ void doubling_stream(const OpsStream<CF>& op, int nd,
         __syncthreads();
         op.template mm_stream<false, 0>(t, X1, [&](int i, int j, T acc) { at(X2, i, j) = acc; }, r, r, none, none, nullptr, nullptr);
         __syncthreads();
+        if (sjp) {      // per-source slot with expk = 1 (ThermalEmission), see doubling_loop
+            op.mv2(r, sjp, sjm, [&](int i, T s) { sv1[i] = sjm[i] + s; }, [&](int i, T s) { sv2[i] = sjp[i] + s; });
+            op.mv2(X2, sv1, sv2, [&](int i, T s) { sjm[i] = sjm[i] + s; }, [&](int i, T s) { sjp[i] = sjp[i] + s; });
+        }
         op.template mm_stream<false, 2>(X2, W, [&](int i, int j, T acc) { at(r, i, j) += acc; }, v1, v2,
                                         [&](int i, T s) { jm[i] = jm[i] + s; }, [&](int i, T s) { jp[i] = j1p[i] + s; },
                                         X2, t);
@@ -510,7 +515,10 @@ __global__ void __launch_bounds__(CF::NTHR, MINB) k_layer_stream(ColArgs<double>
         elemental_fill<T, CF::NN, CF::LD>(a, m, nd, dtau, varpi, tausum, Wc, Zpp, Zmp, zstride,
                                           a.F0 + (a.F0_off + p) * a.nStokes, dmask, r, t, jp, jm, rowtmp, cap);
         __syncthreads();
-        doubling_stream<CF>(op, nd, expk, r, t, X1, X2, W, jp, jm, j1p, j1m, v1, v2);
+        const bool thermal = (a.therm_B != nullptr) && (m == 0);
+        T* sjp = cap; T* sjm = cap + NP; T* sv1 = cap + 2 * NP; T* sv2 = cap + 3 * NP;       // (cap is free after the elemental phase)
+        if (thermal) { thermal_fill<T>(a, n, iz, p, dtau, varpi, sjp, sjm); __syncthreads(); }
+        doubling_stream<CF>(op, nd, expk, r, t, X1, X2, W, jp, jm, j1p, j1m, v1, v2, thermal ? sjp : nullptr, sjm, sv1, sv2);
         // apply_D_matrix! / apply_D_matrix_SFI! (doubling.jl:178-216) on the way out
         const size_t slot = ((size_t)mi * a.n_sched_layers + si) * a.nS + p;
         T* gr = a.add_r + slot * a.add_mstride;
@@ -524,9 +532,10 @@ __global__ void __launch_bounds__(CF::NTHR, MINB) k_layer_stream(ColArgs<double>
             gt[e] = in ? t[e] : 0.0;
         }
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            T vm = jm[i];
+            T vm = jm[i], vp = jp[i];
+            if (thermal) { vm += sjm[i]; vp += sjp[i]; }
             if (nd >= 1) vm = Num<T>::flip(vm, dmask[i]);
-            a.add_jp[slot * n + i] = jp[i];
+            a.add_jp[slot * n + i] = vp;
             a.add_jm[slot * n + i] = vm;
         }
     }
@@ -697,6 +706,7 @@ __global__ void __launch_bounds__(CF::NTHR, MINB) k_adding_stream(ColArgs<double
                                              : (((i % a.nStokes) == 0) ? rho_l : T(0));
                     jps[i] = (i == a.istart) ? att : T(0);
                     jms[i] = a.mu0 * rho * att;
+                    if (a.sif0 && !a.surf_rho && m == 0) jms[i] += T(2) * a.sif0[(i % a.nStokes) + (size_t)a.nStokes * (a.F0_off + p)];
                 }
                 jps_sun = att;
                 t = nullptr; ljp = jps; ljm = jms;

@@ -43,7 +43,8 @@ class ColumnDesc(C.Structure):
                 ("vza_weight", f64p),
                 ("ndoubl", i32p), ("scatter", i32p), ("iface", i32p), ("rayl_allzero", i32p), ("vza_stream", i32p),
                 ("tau_rayl", c_void_p), ("tau_abs", c_void_p), ("F0", c_void_p), ("Zpp", c_void_p), ("Zmp", c_void_p),
-                ("surf_rho", c_void_p), ("ss_correction", f64p)]
+                ("surf_rho", c_void_p), ("ss_correction", f64p),
+                ("thermal_B", c_void_p), ("sif0", c_void_p)]
 
 
 class LinDesc(C.Structure):

@@ -236,6 +236,11 @@ class RTModel:
     # Cox-Munk TMS correction (apply_ss_correction!, rt_run.jl:520-524): (nVZA, pol_n) geometry factor from
     # coxmunk.coxmunk_ss_correction(); None for every other surface
     ss_correction: Optional[np.ndarray] = None
+    # extra sources of the reference's source-term seam (rt_run(model; sources = ...)):
+    #   thermal_B (nSpec, Nz): ThermalEmission.B_layer (Planck radiance per layer; Sources/thermal_emission.jl:92-115)
+    #   sif0 (nSpec, pol_n):   SurfaceSIF.SIF0 (surface fluorescence irradiance; Sources/surface_sif.jl:153-178)
+    thermal_B: Optional[np.ndarray] = None
+    sif0: Optional[np.ndarray] = None
 
     @property
     def pol_n(self) -> int:

@@ -112,7 +112,8 @@ def _column_desc(prep: PreparedColumn, tau_rayl: torch.Tensor, tau_abs: torch.Te
 
 
 def rt_column_device(ctx: _lib.Context, prep: PreparedColumn, tau_rayl: torch.Tensor, tau_abs: torch.Tensor,
-                     F0: torch.Tensor, want_hdr: bool = True, streams: Optional[dict] = None):
+                     F0: torch.Tensor, want_hdr: bool = True, streams: Optional[dict] = None,
+                     thermal_B: Optional[torch.Tensor] = None, sif0: Optional[torch.Tensor] = None):
     """Device-resident entry: ``tau_rayl``/``tau_abs`` are (Nz, nS) torch CUDA tensors
     (memory order == Julia (nSpec, Nz)); ``F0`` is (nS, pol_n).  Returns device
     tensors R_SFI, T_SFI, hdr of shape (nS, pol_n, nVZA) (memory order == Julia
@@ -135,6 +136,12 @@ def rt_column_device(ctx: _lib.Context, prep: PreparedColumn, tau_rayl: torch.Te
     uw = torch.empty((nS, n), dtype=dt, device=dev) if want_hdr else None
     dw = torch.empty((nS, n), dtype=dt, device=dev) if want_hdr else None
     d, _keep = _column_desc(prep, tau_rayl, tau_abs, F0)
+    if thermal_B is not None:           # (nS, Nz) tensor, memory == Julia (Nz, nSpec)
+        assert thermal_B.shape == (nS, Nz) and thermal_B.dtype == dt and thermal_B.is_contiguous()
+        d.thermal_B = thermal_B.data_ptr()
+    if sif0 is not None:                # (nS, pol_n) tensor, memory == Julia (nStokes, nSpec)
+        assert sif0.shape == (nS, n) and sif0.dtype == dt and sif0.is_contiguous()
+        d.sif0 = sif0.data_ptr()
     hp = (H.data_ptr() if want_hdr else None, uw.data_ptr() if want_hdr else None, dw.data_ptr() if want_hdr else None)
     if streams is not None:
         N, nM = q.qp_muN.size, model.m_max + 1
@@ -183,7 +190,9 @@ def rt_run(model: RTModel, ctx: Optional[_lib.Context] = None, prep: Optional[Pr
         d_ta = torch.from_numpy(ta).pin_memory().to(device, non_blocking=True)
         d_f0 = torch.from_numpy(f0).to(device)
         st = {} if return_streams else None
-        R, T, H, uw, dw = rt_column_device(ctx, prep, d_tr, d_ta, d_f0, streams=st)
+        d_th = None if model.thermal_B is None else torch.from_numpy(np.ascontiguousarray(model.thermal_B[sel].astype(FT))).to(device)
+        d_sif = None if model.sif0 is None else torch.from_numpy(np.ascontiguousarray(model.sif0[sel].astype(FT))).to(device)
+        R, T, H, uw, dw = rt_column_device(ctx, prep, d_tr, d_ta, d_f0, streams=st, thermal_B=d_th, sif0=d_sif)
         ctx.synchronize()
         out = dict(R_SFI=R.cpu().numpy().transpose(2, 1, 0), T_SFI=T.cpu().numpy().transpose(2, 1, 0),
                    hdr=H.cpu().numpy().transpose(2, 1, 0), bhr_uw=uw.cpu().numpy()[:, 0].copy(),
@@ -219,7 +228,9 @@ def rt_run_sharded(model: RTModel, ctx: Optional[_lib.Context] = None, device: O
         d_tr = torch.from_numpy(np.ascontiguousarray(model.tau_rayl[lo:hi].T)).to(device)
         d_ta = torch.from_numpy(np.ascontiguousarray(model.tau_abs[lo:hi].T)).to(device)
         f0 = np.zeros((nS, n), FT); f0[:, 0] = 1
-        R, T, H, uw, dw = rt_column_device(ctx, prep, d_tr, d_ta, torch.from_numpy(f0).to(device))
+        d_th = None if model.thermal_B is None else torch.from_numpy(np.ascontiguousarray(model.thermal_B[lo:hi].astype(FT))).to(device)
+        d_sif = None if model.sif0 is None else torch.from_numpy(np.ascontiguousarray(model.sif0[lo:hi].astype(FT))).to(device)
+        R, T, H, uw, dw = rt_column_device(ctx, prep, d_tr, d_ta, torch.from_numpy(f0).to(device), thermal_B=d_th, sif0=d_sif)
     else:
         R = torch.zeros((0, n, nV), dtype=dt, device=device); T = R.clone(); H = R.clone()
         uw = torch.zeros((0, n), dtype=dt, device=device); dw = uw.clone()
@@ -252,6 +263,12 @@ def rt_run_multi(model: RTModel, mctx: "_lib.MultiContext"):
     f0 = np.zeros((nS, n), FT); f0[:, 0] = 1
     F0 = torch.from_numpy(f0)
     d, _keep = _column_desc(prep, tr, ta, F0)
+    th = None if model.thermal_B is None else np.ascontiguousarray(model.thermal_B.astype(FT))       # (nSpec, Nz), HOST
+    sf = None if model.sif0 is None else np.ascontiguousarray(model.sif0.astype(FT))
+    if th is not None:
+        d.thermal_B = th.ctypes.data
+    if sf is not None:
+        d.sif0 = sf.ctypes.data
     R = np.empty((nS, n, nV), FT); T = np.empty_like(R); H = np.empty_like(R)
     uw = np.empty((nS, n), FT); dw = np.empty_like(uw)
     fn = _lib.lib.vsm_rt_column_sharded_f64 if FT == np.float64 else _lib.lib.vsm_rt_column_sharded_f32
