@@ -48,8 +48,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3],
-                    help="2: BASELINE configs[1] (O2-A, N=45); 3: configs[2] (ocean_coxmunk, 20 streams, N=75/100)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
+                    help="2: BASELINE configs[1] (O2-A, N=45); 3: configs[2] (ocean_coxmunk, 20 streams, N=75/100); "
+                         "4: configs[3] (LinMode Jacobians on the config-3 scene; prints its own line, N=1 only)")
+    ap.add_argument("--nparams", type=int, default=4, help="config 4: number of Jacobian parameters")
     ap.add_argument("--pol", default=None, choices=["IQU", "IQUV"], help="config 3 polarization (default IQU -> N=75)")
     ap.add_argument("--nspec", type=int, default=None, help="spectral points per GPU (default 10000 / config 3: 1000)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
@@ -65,7 +67,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     a = ap.parse_args()
     if a.nspec is None:
-        a.nspec = 10000 if a.config == 2 else 1000
+        a.nspec = 10000 if a.config == 2 else (1000 if a.config == 3 else 148)
     if a.pol is None:
         a.pol = "IQU"
     if a.parity_points is None:
@@ -495,9 +497,75 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_lin(args):
+    """BASELINE.json configs[3]: LinMode analytic Jacobians (R, T, dR, dT) on the ocean_coxmunk scene.  One step =
+    one rt_run_lin over the batch: forward + P derivative columns.  Prints one JSON line (spectral points/s with
+    the parameter count stated) and verifies a few points against the FD-pinned oracle."""
+    import torch
+    import vsmom_b200 as vb
+    from vsmom_b200 import _lib, rt_run as rr
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import vsmom_oracle as orc
+    from helpers import to_oracle
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    m = vb.synthetic_ocean_model(nSpec=args.nspec, nstreams=20, polarization_type="Stokes_" + args.pol, ss_correction=False)
+    P, nS, Nz, nA = args.nparams, m.nSpec, m.Nz, len(m.aerosol_optics)
+    rng = np.random.default_rng(5)
+    d_rayl = np.zeros((P, nS, Nz)); d_abs = np.zeros((P, nS, Nz)); d_aer = np.zeros((P, nA, Nz)); d_alb = np.zeros(P)
+    for p in range(P):                     # gas-profile scalings, then Rayleigh and aerosol optical depth
+        if p == P - 1 and nA:
+            d_aer[p] = m.tau_aer
+        elif p == P - 2:
+            d_rayl[p] = m.tau_rayl
+        else:
+            d_abs[p] = m.tau_abs * rng.random(Nz)[None, :]
+    ctx = _lib.Context(0)
+    for _ in range(max(1, args.warmup - 2)):
+        out = rr.rt_run_lin(m, d_rayl, d_abs, d_aer, d_alb, ctx=ctx)
+    times, dev_ms = [], []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        out = rr.rt_run_lin(m, d_rayl, d_abs, d_aer, d_alb, ctx=ctx)
+        times.append(time.perf_counter() - t0)
+        dev_ms.append(ctx.last_column_ms())
+    tot, lay, add = (float(np.mean([d[i] for d in dev_ms])) for i in range(3))
+    # parity on a few points (the oracle carries P derivative columns: small sample)
+    k = min(2, nS)
+    idx = np.sort(rng.choice(nS, size=k, replace=False))
+    import copy
+    om = to_oracle(m)
+    full_ctl = orc.band_control(om, 0)                 # the sample must branch like the full band
+    om2 = copy.copy(om); om2.tau_rayl = om.tau_rayl[idx]; om2.tau_abs = om.tau_abs[idx]
+    ctl = orc.BandControl(full_ctl.scatter, full_ctl.ndoubl, full_ctl.interface, full_ctl.tau_sum[idx])
+    ref = orc.rt_run_lin(om2, d_rayl[:, idx], d_abs[:, idx], d_aer, d_alb, ctl=ctl)
+    errs = {}
+    for key in ("R_SFI", "T_SFI"):
+        errs[key] = float(np.max(np.abs(out[key][..., idx] - ref[key])) / np.max(np.abs(ref[key])))
+    for key in ("dR_SFI", "dT_SFI"):
+        errs[key] = float(max(np.max(np.abs(out[key][p][..., idx] - ref[key][p])) / max(np.max(np.abs(ref[key][p])), 1e-300)
+                              for p in range(P) if np.max(np.abs(ref[key][p])) > 0))
+    N = m.quad_points.qp_muN.size
+    line = {"metric": "spectral points/sec in rt_run_lin (forward + analytic Jacobians)", "value": nS / (tot * 1e-3),
+            "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot,
+            "higher_is_better": True, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"configs[3]: LinMode on the ocean_coxmunk scene, Stokes_{args.pol}, nstreams=20 (N={N}), "
+                                   f"33 layers, 40 Fourier moments, Nparams={P} (gas-profile scalings, Rayleigh, aerosol optical depth)",
+                       "nSpec": nS, "Nparams": P, "N": N},
+            "device_ms": {"total": tot, "layer_lin": lay, "adding_lin": add},
+            "e2e": {"value": nS / float(np.mean(times)), "unit": UNIT, "path": "vsmom_b200.rt_run_lin(model, ...) NumPy in / NumPy out"},
+            "products_per_doubling": 5 + 1 + 14 * P,
+            "parity_check": {"n": int(k), "max_rel": errs, "tol": {"forward": 1e-9, "jacobian": 1e-8},
+                             "ok": bool(errs["R_SFI"] <= 1e-9 and errs["T_SFI"] <= 1e-9 and errs["dR_SFI"] <= 1e-8 and errs["dT_SFI"] <= 1e-8)}}
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.config == 4:
+        run_lin(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_b200(a)

@@ -1415,11 +1415,12 @@ def core_props_lin(model: Model, m: int, dtau_rayl, dtau_abs, dtau_aer, ztab=Non
     return out
 
 
-def rt_run_lin(model: Model, dtau_rayl, dtau_abs, dtau_aer, dalbedo):
+def rt_run_lin(model: Model, dtau_rayl, dtau_abs, dtau_aer, dalbedo, ctl: Optional[BandControl] = None):
     """Forward result and Jacobian dR_SFI/dp, dT_SFI/dp (P,nVZA,pol_n,nSpec) for P parameters that
     perturb tau_rayl, tau_abs (P,nSpec,Nz), tau_aer (P,nAer,Nz) and the Lambertian albedo (P,).
     The layer loop of rt_run_lin.jl:102-326 with rt_kernel! of rt_kernel_lin.jl:50-180; control
-    flow (ndoubl, interfaces) is that of the unperturbed band, as in the reference."""
+    flow (ndoubl, interfaces) is that of the unperturbed band, as in the reference; `ctl` overrides it (a sample of a
+    larger band must branch like the full band)."""
     FT = model.FT
     q = model.quad
     pol_n = model.pol_n
@@ -1430,10 +1431,12 @@ def rt_run_lin(model: Model, dtau_rayl, dtau_abs, dtau_aer, dalbedo):
     F0 = model.F0
     if F0 is None:
         F0 = np.zeros((pol_n, nS), FT); F0[0, :] = 1
+    ctl_given = ctl
     for m in range(model.m_max + 1):
         weight = FT(0.5 / math.pi) if m == 0 else FT(1.0 / math.pi)
         ztab = z_tables(model, m)
-        ctl = band_control(model, m, ztab)
+        if ctl_given is None:
+            ctl = band_control(model, m, ztab)
         props = construct_core_optical_properties(model, m, ztab=ztab)
         lprops = core_props_lin(model, m, dtau_rayl, dtau_abs, dtau_aer, ztab)
         dtausum = np.zeros((P, nS), FT)

@@ -1,5 +1,5 @@
 #define VSM_SNN 100
-#define VSM_SWR 2
+#define VSM_SWR 4
 #define VSM_SWC 4
 #define VSM_SKP 16
 #define VSM_SNST 3

@@ -1,6 +1,6 @@
 #define VSM_SNN 75
 #define VSM_SWR 2
-#define VSM_SWC 4
+#define VSM_SWC 5
 #define VSM_SKP 16
 #define VSM_SNST 3
 #define VSM_SMINB 2

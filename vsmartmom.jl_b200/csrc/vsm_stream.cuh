@@ -140,15 +140,13 @@ struct OpsStream {
         const int tc0 = t0(wc, WC), tcn = t0(wc + 1, WC) - tc0;
         const int wi = tr0 * 8, wj = tc0 * 8;
         const bool vown = (NV > 0) && (wc == 0);
-        // A warp with one tile row / column less than the largest block recomputes its last one in the spare slot
-        // (discarded by the epilogue): the k loop then carries no per-tile predicate -- a predicate around mma.sync
-        // costs ~10 instructions (BSSY / WARPSYNC / ...) per DMMA, the spare DMMAs cost nothing the slowest warp of
-        // the panel barrier does not already pay.
-        int aoff[TR], boff[TC];
-#pragma unroll
-        for (int r = 0; r < TR; ++r) aoff[r] = (r < trn ? r : trn - 1) * 8;
-#pragma unroll
-        for (int q = 0; q < TC; ++q) boff[q] = (q < tcn ? q : tcn - 1) * 8 * CF::LDB;
+        // Tile block of this warp = a core of TRB x TCB tiles that every warp owns (no predicate in its k loop) plus,
+        // when the grid does not divide NT, one extra tile row and / or column: each extra is ONE warp-uniform branch
+        // around a block of DMMAs per k step.  (A predicate around every single mma.sync costs ~10 instructions of
+        // BSSY / WARPSYNC / ISETP per DMMA: ncu showed DMMA at 10 % of the instruction stream that way.)
+        constexpr int TRB = CF::NT / WR, TCB = CF::NT / WC;
+        constexpr bool RU = (CF::NT % WR) != 0, CU = (CF::NT % WC) != 0;
+        const bool xr = RU && (trn > TRB), xc = CU && (tcn > TCB);
         StreamRing& rs = ring;
         unsigned g0;
         int issued;
@@ -170,7 +168,7 @@ struct OpsStream {
 #pragma unroll
             for (int q = 0; q < TC; ++q) c[r][q][0] = c[r][q][1] = 0.0;
         }
-        const T* xr = (NV == 2 && g == 1) ? x2 : x1;
+        const T* xr_ = (NV == 2 && g == 1) ? x2 : x1;
 #pragma unroll 1
         for (int kp = 0; kp < CF::NPAN; ++kp) {
             const unsigned G = g0 + (unsigned)kp;
@@ -211,25 +209,43 @@ struct OpsStream {
                 if (KSIGN) mk = dmask[k0 + ks * 4 + tg];
 #pragma unroll
                 for (int r = 0; r < TR; ++r) {
-                    a[r] = Ar[aoff[r] + ks * 4 * kLd];
+                    a[r] = (r < TRB || xr) ? Ar[r * 8 + ks * 4 * kLd] : 0.0;
                     if (KSIGN) a[r] = Num<double>::flip(a[r], mk);
                 }
 #pragma unroll
-                for (int q = 0; q < TC; ++q) b[q] = Br[ks * 4 + boff[q]];
+                for (int q = 0; q < TC; ++q) b[q] = (q < TCB || xc) ? Br[ks * 4 + q * 8 * CF::LDB] : 0.0;
+                auto mma = [](double& c0, double& c1, double x, double y) {
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(c0), "+d"(c1) : "d"(x), "d"(y));
+                };
 #pragma unroll
-                for (int r = 0; r < TR; ++r)
+                for (int r = 0; r < TRB; ++r)
 #pragma unroll
-                    for (int q = 0; q < TC; ++q)
-                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                                     : "+d"(c[r][q][0]), "+d"(c[r][q][1]) : "d"(a[r]), "d"(b[q]));
+                    for (int q = 0; q < TCB; ++q) mma(c[r][q][0], c[r][q][1], a[r], b[q]);
+                if (RU) {
+                    if (xr) {
+#pragma unroll
+                        for (int q = 0; q < TCB; ++q) mma(c[TR - 1][q][0], c[TR - 1][q][1], a[TR - 1], b[q]);
+                    }
+                }
+                if (CU) {
+                    if (xc) {
+#pragma unroll
+                        for (int r = 0; r < TRB; ++r) mma(c[r][TC - 1][0], c[r][TC - 1][1], a[r], b[TC - 1]);
+                        if (RU) {
+                            if (xr) mma(c[TR - 1][TC - 1][0], c[TR - 1][TC - 1][1], a[TR - 1], b[TC - 1]);
+                        }
+                    }
+                }
                 if (NV > 0) {
                     if (vown) {
                         const int k = k0 + ks * 4 + tg;
-                        const double bx = (g < NV && k < NN) ? xr[k] : 0.0;
+                        const double bx = (g < NV && k < NN) ? xr_[k] : 0.0;
 #pragma unroll
-                        for (int r = 0; r < TR; ++r)
-                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                                         : "+d"(cv[r][0]), "+d"(cv[r][1]) : "d"(a[r]), "d"(bx));
+                        for (int r = 0; r < TRB; ++r) mma(cv[r][0], cv[r][1], a[r], bx);
+                        if (RU) {
+                            if (xr) mma(cv[TR - 1][0], cv[TR - 1][1], a[TR - 1], bx);
+                        }
                     }
                 }
             }
