@@ -16,7 +16,9 @@ def sh(cmd, **kw):
     return subprocess.run(cmd, shell=True, capture_output=True, text=True, **kw).stdout
 
 raw = list(csv.reader(io.StringIO(sh(f"ncu -i {rep} --page raw --csv"))))
-hdr, units, vals = raw[0], raw[1], raw[2]
+hdr, units = raw[0], raw[1]
+iK = hdr.index("Kernel Name")
+vals = next((r for r in raw[2:] if kname in r[iK]), raw[2])      # the launch of the requested kernel
 M = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
 want = ["Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "launch__registers_per_thread",
         "launch__shared_mem_per_block", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
@@ -29,6 +31,7 @@ want = ["Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "lau
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "lts__t_sector_hit_rate.pct",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
@@ -48,8 +51,11 @@ for k in want:
     if k in M:
         print(f"- `{k}` = {M[k][0]} {M[k][1]}", file=out)
 
-src = list(csv.reader(io.StringIO(sh(f"ncu -i {rep} --page source --csv"))))
-h = src[1]; data = src[2:]
+src = list(csv.reader(io.StringIO(sh(f"ncu -i {rep} --page source --csv --kernel-name regex:{kname}"))))
+# the export holds one section per launch / view: "Kernel Name" line, header line, rows; take the first (SASS) one
+starts = [i for i, r in enumerate(src) if r and r[0] == "Kernel Name"]
+end = starts[1] if len(starts) > 1 else len(src)
+h = src[starts[0] + 1]; data = [r for r in src[starts[0] + 2:end] if len(r) == len(h)]
 iS, iI, iA, iSrc = h.index("# Samples"), h.index("Instructions Executed"), h.index("Address"), h.index("Source")
 tot = sum(int(r[iS]) for r in data) or 1
 toti = sum(int(r[iI]) for r in data) or 1

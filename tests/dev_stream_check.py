@@ -47,8 +47,11 @@ if __name__ == "__main__":
         run("Stokes_IQUV", 11, 2, mmax=3)
         run("Stokes_IQU", 20, 2, mmax=2, noscat=True)
     elif what == "prof":
-        run("Stokes_IQUV", 20, 148, mmax=0)
-        run("Stokes_IQU", 20, 296, mmax=0)
+        only = os.environ.get("DEV_ONLY", "")
+        if only in ("", "100"):
+            run("Stokes_IQUV", 20, 148, mmax=0)
+        if only in ("", "75"):
+            run("Stokes_IQU", 20, 296, mmax=0)
     else:
         mm = int(os.environ.get("DEV_MMAX", "9"))
         run("Stokes_IQU", 20, 296, mmax=mm)
