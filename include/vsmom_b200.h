@@ -219,6 +219,38 @@ typedef struct vsm_lin_desc {
 int vsm_rt_column_lin_f64(vsm_ctx*, const vsm_column_desc*, const vsm_lin_desc*, double* R_SFI, double* T_SFI,
                           double* dR, double* dT);
 
+/* -- L2, rotational Raman scattering (RRS): elastic + first-order inelastic radiances -- drop-in for the body of
+ * rt_run(RS_type::RRS, model, iBand) src/CoreRT/rt_run.jl:238-539 with rt_kernel!(::RRS) of
+ * CoreKernel/rt_kernel.jl:352-391: elemental_inelastic! (elemental_inelastic.jl:23-206, 479-603), elemental!,
+ * doubling_helper!(::RRS) (doubling_inelastic.jl:13-164), interaction_helper!(::RRS, ::ScatteringInterface_11)
+ * (interaction_inelastic.jl:319-521), copy_added_to_composite_ie!, postprocessing_vza!(::RRS)
+ * (postprocessing_vza.jl:121-162).  The Raman line physics (getRamanSSProp!, raman_atmo_prop.jl:80-100) is the
+ * caller's: it supplies the shift table i_λ₁λ₀, the normalised weights ϖ_λ₁λ₀ (normalize_raman_weights!,
+ * Inelastic/types.jl:625-629) and the Z moments of greek_raman (computeRamanZλ!, inelastic_helper.jl:917-924).
+ * The column descriptor describes the WHOLE band (nSpec = band length: the donor wavelength n0 = n1 + i_shift[dn]
+ * of every coupling must be addressable); its Zpp/Zmp component 0 must be the Cabannes set and varpi_cabannes
+ * ϖ_Cabannes (compEffectiveLayerProperties.jl:36-41).  The call computes the outputs of the OWNER range
+ * n1 in [n1_begin, n1_begin + n1_count) -- the whole band for a single device, one contiguous shard per device
+ * when the band is sharded: the inelastic terms read only ELASTIC state of other wavelengths, so a shard needs no
+ * communication, just the elastic column of its halo [n1_begin + min shift, n1_end + max shift], which the library
+ * recomputes locally.  Every layer must scatter (rt_kernel.jl:366 hard-codes scatter = true; the
+ * reference has no working _01/_10 RRS interaction).  fp64, N <= 48.  thermal_B / sif0 / ss_correction must be NULL. */
+typedef struct vsm_rrs_desc {
+    int32_t struct_size;        /* sizeof(vsm_rrs_desc) */
+    int32_t n_raman;            /* length of i_λ₁λ₀ */
+    int32_t n1_begin;           /* 0-based first owned band index */
+    int32_t n1_count;           /* number of owned band indices */
+    const int32_t* i_shift;     /* host [n_raman]  RS_type.i_λ₁λ₀ */
+    const double*  varpi_raman; /* host [n_raman]  RS_type.ϖ_λ₁λ₀ after normalize_raman_weights! */
+    const void*    Zpp_raman;   /* device (N,N,n_moments)  RS_type.Z⁺⁺_λ₁λ₀ per Fourier moment */
+    const void*    Zmp_raman;   /* device (N,N,n_moments)  RS_type.Z⁻⁺_λ₁λ₀ */
+} vsm_rrs_desc;
+/* outputs: device, (nVZA,nStokes,n1_count) each, overwritten: the elastic R_SFI/T_SFI and the inelastic
+ * ieR_SFI/ieT_SFI (rt_run.jl:532) of the owner range.  vsm_last_column_ms reports the inelastic-unit kernels as
+ * doubling_ms and the elastic-export kernels as adding_ms. */
+int vsm_rt_column_rrs_f64(vsm_ctx*, const vsm_column_desc*, const vsm_rrs_desc*, double* R_SFI, double* T_SFI,
+                          double* ieR_SFI, double* ieT_SFI);
+
 /* -- several GPUs from ONE host process (the reference drives everything from a single Julia process and has no
  * multi-GPU path: Architectures.jl:42-45 "Run on a single NVIDIA CUDA GPU").  vsm_multi_create opens one context
  * (own stream) per listed device and an in-process NCCL communicator over them (ncclCommInitAll; NCCL is loaded

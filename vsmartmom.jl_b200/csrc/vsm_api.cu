@@ -17,6 +17,7 @@
 #include "vsm_l0.cuh"
 #include "vsm_stream.cuh"
 #include "vsm_lin.cuh"
+#include "vsm_raman_args.h"
 
 using namespace vsm;
 
@@ -39,7 +40,8 @@ struct vsm_ctx {
     std::map<const void*, int> smem_set;    // largest dynamic shared-memory size already granted per kernel
     std::string err;
     // grow-only scratch
-    DevBuf consts, props, added, slabs, partial, counter, l0tmp, geom, surfpad, linprops;
+    DevBuf consts, props, added, slabs, partial, counter, l0tmp, geom, surfpad, linprops, rrs;
+    int rrs_order = 1;                      // unit enumeration of the Raman kernels (VSM_RRS_ORDER): 0 dn-major, 1 donor-major
     int use_stream = 1;                     // streamed-operand kernels for N = 60 / 75 / 100 (VSM_DISABLE_STREAM=1 turns them off)
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float t_total = 0, t_layer = 0, t_add = 0;
@@ -142,6 +144,7 @@ extern "C" int vsm_create(vsm_ctx** out, int device, void* cuda_stream) {
     ctx->ws_limit = 0;
     if (const char* e = getenv("VSM_DEBUG_LAYER_CTAS_PER_SM")) ctx->dbg_layer_ctas = atoi(e);
     if (const char* e = getenv("VSM_DISABLE_STREAM")) ctx->use_stream = atoi(e) ? 0 : 1;
+    if (const char* e = getenv("VSM_RRS_ORDER")) ctx->rrs_order = atoi(e) ? 1 : 0;
     *out = ctx;
     return VSM_OK;
 }
@@ -960,6 +963,223 @@ static int rt_column_lin_impl(vsm_ctx* ctx, const vsm_column_desc* d, const vsm_
 extern "C" int vsm_rt_column_lin_f64(vsm_ctx* c, const vsm_column_desc* d, const vsm_lin_desc* l, double* R, double* T_, double* dR,
                                      double* dT) {
     return rt_column_lin_impl(c, d, l, R, T_, dR, dT);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// L2, rotational Raman (RRS): rt_run(::RRS, model, iBand) rt_run.jl:238-539 with rt_kernel!(::RRS) rt_kernel.jl:352-391
+// ----------------------------------------------------------------------------------------------------------------
+static int rt_column_rrs_impl(vsm_ctx* ctx, const vsm_column_desc* d, const vsm_rrs_desc* rd, double* R_SFI, double* T_SFI,
+                              double* ieR_SFI, double* ieT_SFI) {
+    using T = double;
+    if (!ctx) return VSM_ERR_INVALID_ARG;
+    if (!d || d->struct_size != (int)sizeof(vsm_column_desc))
+        return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_rrs: column descriptor NULL or struct_size mismatch");
+    if (!rd || rd->struct_size != (int)sizeof(vsm_rrs_desc))
+        return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_rrs: rrs descriptor NULL or struct_size mismatch");
+    if (!R_SFI || !T_SFI || !ieR_SFI || !ieT_SFI) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_rrs: output NULL");
+    const int N = d->N, nSt = d->nStokes, Nz = d->Nz, nAer = d->nAer, nV = d->nVZA, nM = d->n_moments;
+    const int nBand = d->nSpec, nR = rd->n_raman;
+    const int nOut = nV * nSt;
+    if (N <= 0 || nSt < 1 || nSt > 4 || N % nSt != 0 || Nz <= 0 || nAer < 0 || nAer + 1 > kMaxComp || nV <= 0 || nM <= 0 ||
+        nBand <= 0 || d->imu0 < 1 || d->imu0 * nSt > N || nR <= 0)
+        return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_rrs: bad dimensions");
+    if (!d->mu || !d->wt || !d->vza_weight || !d->ndoubl || !d->scatter || !d->iface || !d->rayl_allzero || !d->vza_stream ||
+        !d->tau_rayl || !d->tau_abs || !d->F0 || !d->Zpp || !d->Zmp || (nAer > 0 && (!d->aer_omega || !d->aer_ft || !d->tau_aer)) ||
+        !rd->i_shift || !rd->varpi_raman || !rd->Zpp_raman || !rd->Zmp_raman)
+        return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_rrs: NULL input array");
+    if (d->thermal_B || d->sif0 || d->ss_correction)
+        return fail(ctx, VSM_ERR_UNSUPPORTED, "rt_column_rrs: extra sources / TMS correction are not part of the RRS driver");
+    if (d->surface_kind != VSM_SURFACE_LAMBERTIAN_SCALAR && d->surface_kind != VSM_SURFACE_BRDF_FOURIER)
+        return fail(ctx, VSM_ERR_UNSUPPORTED, "rt_column_rrs: surface_kind must be LAMBERTIAN_SCALAR or BRDF_FOURIER");
+    if (d->surface_kind == VSM_SURFACE_BRDF_FOURIER && !d->surf_rho)
+        return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_rrs: BRDF_FOURIER needs surf_rho");
+    int ndmax = 0;
+    for (int iz = 0; iz < Nz; ++iz) {
+        // rt_kernel!(::RRS) hard-codes scatter = true (rt_kernel.jl:366); only the _11 interaction exists for RRS
+        if (!d->scatter[iz] || d->iface[iz] != VSM_IFACE_11)
+            return fail(ctx, VSM_ERR_UNSUPPORTED, "rt_column_rrs: every layer must scatter (ScatteringInterface_11)");
+        if (d->ndoubl[iz] < 0 || d->ndoubl[iz] > 60) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_rrs: ndoubl out of range");
+        ndmax = std::max(ndmax, d->ndoubl[iz]);
+    }
+    const int n1lo = rd->n1_begin, n1cnt = rd->n1_count;
+    if (n1lo < 0 || n1cnt < 0 || n1lo + n1cnt > nBand) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_rrs: owner range outside the band");
+    if (n1cnt == 0) return VSM_OK;
+    const rrs::Desc* kd = rrs::desc(N);
+    if (!kd) return fail(ctx, VSM_ERR_UNSUPPORTED, "rt_column_rrs: N > 48 is not covered by the Raman kernels");
+    const int NP = kd->NP;
+    CK(cudaSetDevice(ctx->device));
+    const int nC = nAer + 1;
+    int smin = 0, smax = 0;
+    for (int k = 0; k < nR; ++k) { smin = std::min(smin, rd->i_shift[k]); smax = std::max(smax, rd->i_shift[k]); }
+    // elastic halo: the owner range plus every donor wavelength it can reach
+    const int e0 = std::max(0, n1lo + smin), e1 = std::min(nBand, n1lo + n1cnt + smax);
+    const int nE = e1 - e0;
+
+    // ---- constant tables
+    std::vector<T> fT;
+    std::vector<int> fI;
+    auto pushT = [&](const double* p, size_t n) { size_t o = fT.size(); for (size_t i = 0; i < n; ++i) fT.push_back(p[i]); return o; };
+    auto pushI = [&](const int32_t* p, size_t n) { size_t o = fI.size(); for (size_t i = 0; i < n; ++i) fI.push_back(p[i]); return o; };
+    std::vector<double> mu_pad(NP, 1.0), wt_pad(NP, 0.0), sgn(NP, 1.0);
+    for (int i = 0; i < N; ++i) { mu_pad[i] = d->mu[i]; wt_pad[i] = d->wt[i]; sgn[i] = ((i % nSt) >= 2) ? -1.0 : 1.0; }
+    const size_t o_mu = pushT(mu_pad.data(), NP), o_wt = pushT(wt_pad.data(), NP), o_sg = pushT(sgn.data(), NP);
+    std::vector<double> taumod((size_t)std::max(1, nAer * Nz)), varmod((size_t)std::max(1, nAer));
+    for (int c = 0; c < nAer; ++c) {
+        const T ft = d->aer_ft[c], om = d->aer_omega[c];
+        varmod[c] = (T(1) - ft) * om / (T(1) - ft * om);
+        for (int iz = 0; iz < Nz; ++iz) taumod[c + (size_t)nAer * iz] = (T(1) - ft * om) * d->tau_aer[c + (size_t)nAer * iz];
+    }
+    const size_t o_taumod = pushT(taumod.data(), taumod.size()), o_varmod = pushT(varmod.data(), varmod.size());
+    const size_t o_vw = pushT(d->vza_weight, (size_t)nSt * nV * nM);
+    const size_t o_wR = pushT(rd->varpi_raman, nR);
+    size_t o_rho = 0;
+    const bool lambertian = d->surface_kind == VSM_SURFACE_LAMBERTIAN_SCALAR;
+    if (lambertian) {
+        // lambertian_surface.jl:59-70: R_surf = 2 albedo on the (I,I) element of every stream pair, m = 0 only
+        std::vector<double> rho((size_t)N * N, 0.0);
+        for (int i = 0; i < N; i += nSt) for (int j = 0; j < N; j += nSt) rho[i + (size_t)j * N] = 2.0 * d->albedo;
+        o_rho = pushT(rho.data(), rho.size());
+    }
+    const size_t o_nd = pushI(d->ndoubl, Nz), o_rz = pushI(d->rayl_allzero, Nz), o_sh = pushI(rd->i_shift, nR);
+    std::vector<int> vrow(nV);
+    for (int i = 0; i < nV; ++i) {
+        if (d->vza_stream[i] < 1 || d->vza_stream[i] * nSt > N) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_rrs: vza_stream out of range");
+        vrow[i] = (d->vza_stream[i] - 1) * nSt;
+    }
+    const size_t o_vrow = pushI(vrow.data(), nV);
+    const size_t bytesT = fT.size() * sizeof(T), bytesI = fI.size() * sizeof(int);
+    const size_t offI = (bytesT + 15) & ~size_t(15);
+    int rc = ensure(ctx, ctx->consts, offI + bytesI);
+    if (rc) return rc;
+    if (ctx->stage_cap < offI + bytesI) {
+        if (ctx->stage) { CK(cudaStreamSynchronize(ctx->stream)); cudaFreeHost(ctx->stage); ctx->stage = nullptr; ctx->stage_cap = 0; }
+        CK(cudaMallocHost(&ctx->stage, (offI + bytesI) * 2));
+        ctx->stage_cap = (offI + bytesI) * 2;
+    }
+    if (!ctx->stage_done) CK(cudaEventCreateWithFlags(&ctx->stage_done, cudaEventDisableTiming | cudaEventBlockingSync));
+    else CK(cudaEventSynchronize(ctx->stage_done));
+    memcpy(ctx->stage, fT.data(), bytesT);
+    memcpy((char*)ctx->stage + offI, fI.data(), bytesI);
+    CK(cudaMemcpyAsync(ctx->consts.p, ctx->stage, offI + bytesI, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->stage_done, ctx->stream));
+    const T* cT = (const T*)ctx->consts.p;
+    const int* cI = (const int*)((char*)ctx->consts.p + offI);
+
+    // ---- workspace (doubles)
+    const size_t U = (size_t)nR * n1cnt;
+    const size_t w_props = ((size_t)Nz * (2 + nC) + Nz + 1) * nE, w_fsc = (size_t)Nz * nE;
+    const size_t w_cE = (size_t)nE * kd->ce, w_cI = U * kd->ci;
+    const size_t w_rec0 = (size_t)std::max(1, ndmax) * nE * kd->rec0, w_rec1 = (size_t)std::max(1, ndmax) * nE * kd->rec1;
+    const size_t w_i0 = (size_t)nE * kd->irec0, w_i1 = (size_t)nE * kd->irec1;
+    const size_t w_uo = U * 2 * nOut;
+    const size_t w_total = w_props + w_fsc + 2 * w_cE + 2 * w_cI + w_rec0 + w_rec1 + w_i0 + w_i1 + w_uo + 64;
+    {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        if (w_total * sizeof(T) > free_b + ctx->rrs.cap) {
+            char buf[200];
+            snprintf(buf, sizeof buf, "rt_column_rrs: needs %.1f GB of workspace (nRaman x n1_count = %zu units); shrink the owner range",
+                     w_total * 8.0 / 1e9, U);
+            return fail(ctx, VSM_ERR_NOMEM, buf);
+        }
+    }
+    if ((rc = ensure(ctx, ctx->rrs, w_total * sizeof(T)))) return rc;
+    if ((rc = ensure(ctx, ctx->counter, 256))) return rc;
+    T* w = (T*)ctx->rrs.p;
+    T* pw = w; w += w_props;
+    T* fsc = w; w += w_fsc;
+    T* cE[2] = {w, w + w_cE}; w += 2 * w_cE;
+    T* cIe[2] = {w, w + w_cI}; w += 2 * w_cI;
+    T* rec0 = w; w += w_rec0;
+    T* rec1 = w; w += w_rec1;
+    T* i0 = w; w += w_i0;
+    T* i1 = w; w += w_i1;
+    T* uo = w;
+
+    CK(cudaMemsetAsync((int*)ctx->counter.p + 16, 0, 4, ctx->stream));
+    const size_t out_bytes = (size_t)nOut * n1cnt * sizeof(T);
+    CK(cudaMemsetAsync(R_SFI, 0, out_bytes, ctx->stream));
+    CK(cudaMemsetAsync(T_SFI, 0, out_bytes, ctx->stream));
+    CK(cudaMemsetAsync(ieR_SFI, 0, out_bytes, ctx->stream));
+    CK(cudaMemsetAsync(ieT_SFI, 0, out_bytes, ctx->stream));
+    ctx->ev_used = 0;
+    ctx->seg_layer.clear();
+    ctx->seg_add.clear();
+    GET_EVENT(ev_begin);
+    GET_EVENT(ev_end);
+    CK(cudaEventRecord(ev_begin, ctx->stream));
+
+    PropsArgs<T> pa;
+    pa.nS = nE; pa.Nz = Nz; pa.nAer = nAer; pa.ldspec = (size_t)nBand;
+    pa.tau_rayl = (const T*)d->tau_rayl + e0;
+    pa.tau_abs = (const T*)d->tau_abs + e0;
+    pa.varpi_cab = d->varpi_cabannes;
+    pa.aer_tau_mod = cT + o_taumod; pa.aer_varpi_mod = cT + o_varmod;
+    pa.rayl_allzero = cI + o_rz;
+    pa.tau = pw; pa.varpi = pw + (size_t)Nz * nE; pa.tausum = pw + (size_t)2 * Nz * nE;
+    pa.W = pw + (size_t)(2 * Nz + Nz + 1) * nE;
+    k_props<T><<<(nE + 127) / 128, 128, 0, ctx->stream>>>(pa);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(rrs::launch_fscatt(ctx->stream, nE, Nz, nAer, (size_t)nBand, (const T*)d->tau_rayl + e0, cT + o_taumod, fsc));
+    ctx->launches++;
+
+    rrs::Args a;
+    memset(&a, 0, sizeof a);
+    a.N = N; a.nStokes = nSt; a.Nz = Nz; a.nC = nC; a.nVZA = nV; a.nM = nM;
+    a.nBand = nBand; a.e0 = e0; a.nE = nE; a.n1lo = n1lo; a.n1cnt = n1cnt; a.nRaman = nR;
+    a.istart = (d->imu0 - 1) * nSt;
+    a.order = ctx->rrs_order;
+    a.u_lo = e0; a.u_n0cnt = nE;
+    a.mu0 = d->mu0;
+    a.mu = cT + o_mu; a.wt = cT + o_wt; a.sgn = cT + o_sg;
+    a.shift = cI + o_sh; a.wR = cT + o_wR; a.ndoubl = cI + o_nd;
+    a.p_tau = pa.tau; a.p_varpi = pa.varpi; a.p_tausum = pa.tausum; a.p_W = pa.W; a.fsc = fsc;
+    a.Zpp = (const T*)d->Zpp; a.Zmp = (const T*)d->Zmp;
+    a.ZppR = (const T*)rd->Zpp_raman; a.ZmpR = (const T*)rd->Zmp_raman;
+    a.F0 = (const T*)d->F0;
+    a.surf_rho = lambertian ? cT + o_rho : (const T*)d->surf_rho;
+    a.lambertian = lambertian ? 1 : 0;
+    a.rec0 = rec0; a.rec1 = rec1; a.irec0 = i0; a.irec1 = i1; a.uout = uo;
+    a.vza_row = cI + o_vrow; a.vza_w = cT + o_vw;
+    a.R_SFI = R_SFI; a.T_SFI = T_SFI;
+    CK(set_smem(ctx, kd->k_elastic, kd->smem_elastic));
+    CK(set_smem(ctx, kd->k_inel, kd->smem_inel));
+    const size_t total_units = (a.order == 0) ? U : (size_t)nE * nR;
+    if (total_units > 0xfffffff0u) return fail(ctx, VSM_ERR_UNSUPPORTED, "rt_column_rrs: too many units for one launch");
+    int be = 0, bi = 0;
+    for (int m = 0; m < nM; ++m) {
+        for (int step = 0; step <= Nz; ++step) {
+            const int mode = (step == Nz) ? 1 : 0;
+            const int iz = mode ? Nz - 1 : step;
+            a.cE_in = cE[be]; a.cE_out = cE[be ^ 1];
+            a.cI_in = cIe[bi]; a.cI_out = cIe[bi ^ 1];
+            GET_EVENT(x0);
+            GET_EVENT(x1);
+            GET_EVENT(x2);
+            CK(cudaEventRecord(x0, ctx->stream));
+            CK(kd->launch_elastic(ctx->stream, a, m, iz, mode));
+            CK(cudaEventRecord(x1, ctx->stream));
+            CK(kd->launch_inel(ctx->stream, a, m, iz, mode, (unsigned int)total_units));
+            CK(cudaEventRecord(x2, ctx->stream));
+            ctx->launches += 2;
+            ctx->seg_add.push_back({x0, x1});
+            ctx->seg_layer.push_back({x1, x2});
+            be ^= 1; bi ^= 1;
+        }
+        CK(rrs::launch_reduce(ctx->stream, a, ieR_SFI, ieT_SFI, (m == nM - 1) ? (int*)ctx->counter.p + 16 : nullptr));
+        ctx->launches++;
+    }
+    CK(cudaEventRecord(ev_end, ctx->stream));
+    ctx->ev[0] = ev_begin;
+    ctx->ev[1] = ev_end;
+    ctx->timing_valid = true;
+    return VSM_OK;
+}
+
+extern "C" int vsm_rt_column_rrs_f64(vsm_ctx* c, const vsm_column_desc* d, const vsm_rrs_desc* r, double* R, double* T_, double* ieR,
+                                     double* ieT) {
+    return rt_column_rrs_impl(c, d, r, R, T_, ieR, ieT);
 }
 
 extern "C" int vsm_last_column_ms(vsm_ctx* ctx, float* total_ms, float* doubling_ms, float* adding_ms) {
