@@ -48,9 +48,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
                     help="2: BASELINE configs[1] (O2-A, N=45); 3: configs[2] (ocean_coxmunk, 20 streams, N=75/100); "
-                         "4: configs[3] (LinMode Jacobians on the config-3 scene; prints its own line, N=1 only)")
+                         "4: configs[3] (LinMode Jacobians on the config-3 scene; prints its own line, N=1 only); "
+                         "5: configs[4] (rotational Raman, N=15, 6837 points, owner-range sharding; prints its own line)")
     ap.add_argument("--nparams", type=int, default=4, help="config 4: number of Jacobian parameters")
     ap.add_argument("--pol", default=None, choices=["IQU", "IQUV"], help="config 3 polarization (default IQU -> N=75)")
     ap.add_argument("--nspec", type=int, default=None, help="spectral points per GPU (default 10000 / config 3: 1000)")
@@ -67,11 +68,11 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     a = ap.parse_args()
     if a.nspec is None:
-        a.nspec = 10000 if a.config == 2 else (1000 if a.config == 3 else 148)
+        a.nspec = {2: 10000, 3: 1000, 4: 148, 5: 6837}[a.config]
     if a.pol is None:
         a.pol = "IQU"
     if a.parity_points is None:
-        a.parity_points = 64 if a.config == 2 else 16
+        a.parity_points = {2: 64, 5: 6}.get(a.config, 16)
     return a
 
 
@@ -561,9 +562,223 @@ def run_lin(args):
     ctx.close()
 
 
+# ----------------------------------------------------------------------------
+# config 5: rotational Raman scattering
+# ----------------------------------------------------------------------------
+def _rrs_oracle_objects(m, rs):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import vsmom_oracle as orc
+    import vsmom_oracle_rrs as orr
+    from helpers import to_oracle
+    g = rs.greek_raman
+    og = orc.GreekCoefs(*(np.asarray(x, float) for x in (g.alpha, g.beta, g.gamma, g.delta, g.epsilon, g.zeta)))
+    return to_oracle(m), orr.RRS(np.asarray(rs.i_shift), np.asarray(rs.varpi_raman), og), orr
+
+
+_RRS_W = {}
+
+
+def _rrs_worker(idx):
+    om, ors, orr = _RRS_W["o"]
+    return orr.rt_run_rrs_points(om, ors, idx)
+
+
+def cpu_rrs_points_per_sec(m, rs, seconds, steps=1):
+    """The oracle port of the RRS path on all host cores, on a bounded sample of output wavelengths (every sampled
+    point carries its full set of Raman couplings, evaluated unit-wise: oracle/vsmom_oracle_rrs.rt_run_rrs_points)."""
+    import multiprocessing as mp
+    _RRS_W["o"] = _rrs_oracle_objects(m, rs)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    rng = np.random.default_rng(0)
+    pick = lambda n: np.sort(rng.choice(m.nSpec, size=min(n, m.nSpec), replace=False))
+    with mp.get_context("fork").Pool(cores) as pool:
+        t0 = time.perf_counter()
+        pool.map(_rrs_worker, [np.array([i]) for i in pick(cores)])
+        rate = cores / (time.perf_counter() - t0)
+        n = int(max(cores, min(m.nSpec, round(rate * seconds / cores) * cores)))
+        times = []
+        for _ in range(steps):
+            idx = pick(n)
+            t0 = time.perf_counter()
+            pool.map(_rrs_worker, np.array_split(idx, cores * max(1, n // (cores * 4))))
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    v = n * steps / total
+    return {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "per_core": v / cores, "blas": _blas_vendor(),
+            "sample": f"{n} of {m.nSpec} output wavelengths per step, each with all its Raman couplings "
+                      f"({len(rs.i_shift)} lines), {m.m_max + 1} moments, {m.Nz} layers, {steps} step(s), {total:.1f} s; NumPy "
+                      "oracle, one forked worker per core, BLAS threads=1, f64",
+            "ms_per_step": 1e3 * total / steps, "points_per_step": n}
+
+
+def run_rrs(args):
+    """BASELINE.json configs[4]: rotational Raman (test_forward_raman config shape: IQU, N = 15, 5 layers, 6837 points
+    on the 0.05 cm^-1 grid).  One step = one rt_run(::RRS) over the band: elastic column + every (n1, dn) inelastic
+    unit, all moments.  The OWNER range of the outputs is cut into contiguous shards (strong scaling: the band is
+    fixed); each rank recomputes the elastic column of its halo; ONE all-gather of (R | T | ieR | ieT)."""
+    import torch
+    import torch.distributed as dist
+    import vsmom_b200 as vb
+    from vsmom_b200 import _lib, raman, rt_run as rr
+    from vsmom_b200.sharding import shard_bounds
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    m = raman.synthetic_rrs_model(nSpec=args.nspec)
+    rs = raman.synthetic_rrs()
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_rrs_points_per_sec(m, rs, args.cpu_seconds, steps=args.steps)
+        print(json.dumps({"impl": "reference", "metric": "spectral points/sec in rt_run(RRS) (elastic + rotational-Raman inelastic)",
+                          "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "f64", "data": "synthetic", "config": {"workload": "configs[4]: RRS", "nSpec_total": m.nSpec,
+                                                                           "n_raman": int(len(rs.i_shift))},
+                          "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "per_core", "blas")},
+                          "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nS, n, nV = m.nSpec, m.pol_n, len(m.vza)
+    bounds = shard_bounds(nS, world)
+    lo, hi = bounds[rank]
+    nmax = max(b[1] - b[0] for b in bounds)
+    k = n * nV
+    prep = rr.prepare(m, dev)
+    ctx = _lib.Context(local, torch.cuda.current_stream().cuda_stream)
+    tr_h = torch.from_numpy(np.ascontiguousarray(m.tau_rayl.T)).pin_memory()
+    ta_h = torch.from_numpy(np.ascontiguousarray(m.tau_abs.T)).pin_memory()
+    f0 = np.zeros((nS, n)); f0[:, 0] = 1
+    tr_d, ta_d, f0_d = tr_h.to(dev), ta_h.to(dev), torch.from_numpy(f0).to(dev)
+    zp, zm = raman.raman_z_tables(m, rs)
+    zp_d, zm_d = torch.from_numpy(zp).to(dev), torch.from_numpy(zm).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    pack = torch.zeros((nmax, 4 * k), dtype=torch.float64, device=dev)
+    gathered = torch.empty((world * nmax, 4 * k), dtype=torch.float64, device=dev) if world > 1 else None
+    done = torch.cuda.Event(blocking=True)
+
+    def step_device():
+        outs = raman.rrs_column_device(ctx, prep, rs, tr_d, ta_d, f0_d, zp_d, zm_d, lo, hi - lo)
+        for i, o in enumerate(outs):
+            pack[:hi - lo, i * k:(i + 1) * k] = o.reshape(hi - lo, k)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, pack)
+            return gathered
+        return pack
+
+    def barrier():
+        done.record(); done.synchronize(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    launches0 = ctx.kernel_launches
+    sampler = ClockSampler(local, args.clock_sample_ms)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        flush.zero_()
+        out = step_device()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    my_ms = float(e0.elapsed_time(e1))
+    t = torch.tensor([my_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        lst = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(lst, t)
+        rank_ms = [float(x.item()) for x in lst]
+    else:
+        rank_ms = [my_ms]
+    ms = max(rank_ms)
+    launches = ctx.kernel_launches - launches0
+    t_total, t_inel, t_el = ctx.last_column_ms()
+    g = out.cpu().numpy().reshape(world, nmax, 4 * k)
+    rows = np.concatenate([g[r, :bounds[r][1] - bounds[r][0]] for r in range(world)], axis=0)
+    res = {name: rows[:, i * k:(i + 1) * k].reshape(-1, n, nV).transpose(2, 1, 0) for i, name in enumerate(("R_SFI", "T_SFI", "ieR_SFI", "ieT_SFI"))}
+    # e2e through the public call
+    e2e_fn = (lambda: raman.rt_run_rrs_sharded(m, rs, ctx, str(dev))) if world > 1 else (lambda: raman.rt_run_rrs(m, rs, ctx, str(dev)))
+    e2e_fn()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_fn()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+    if rank == 0:
+        ctl = prep.ctl
+        N, nM, Nz, nR = m.quad_points.qp_muN.size, m.m_max + 1, m.Nz, len(rs.i_shift)
+        sh = np.asarray(rs.i_shift)
+        n1 = np.arange(lo, hi)
+        units = int(sum(np.count_nonzero((n1 + s >= 0) & (n1 + s < nS)) for s in sh))
+        per_unit = nM * (int(ctl.ndoubl.sum()) * (10 * 2 * N ** 3 + 10 * 2 * N ** 2) + Nz * (18 * 2 * N ** 3 + 8 * 2 * N ** 2) + 60 * N ** 2 * Nz)
+        n_inel = nM * (Nz + 1)
+        peak_tf = ctx.measure_fma_peak(0)
+        ach = per_unit * units / (t_inel * 1e-3) / 1e12
+        rec_bytes = nM * sum((7 * 16 * 16 + 5 * 16) * 8 * int(nd) for nd in ctl.ndoubl)        # level records read per unit
+        value = nS * args.steps / (ms * 1e-3)
+        line = {"metric": "spectral points/sec in rt_run(RRS) (elastic + rotational-Raman inelastic)", "value": value, "unit": UNIT,
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "configs[4]: rotational Raman on the test_forward_raman-shaped scene: O2-A band "
+                                       "(1e7/775):0.05:(1e7/755) cm^-1, Stokes_IQU, 3 streams + VZA + SZA (N=15), 5 layers, Rayleigh "
+                                       "(Cabannes) + pseudo-line absorption, Lambertian 0.05, synthetic N2/O2 rotational line table",
+                           "nSpec_total": nS, "N": N, "Nz": Nz, "n_moments": nM, "n_raman": nR, "units_rank0": units,
+                           "parallelism": f"owner-range shard x{world} (elastic halo recomputed per rank)",
+                           "l2": "unit state + level records (GBs) >> 126 MB L2; a 256 MiB buffer is also rewritten between timed iterations"},
+                "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": nS * args.steps / e2e_s, "unit": UNIT,
+                        "h2d_bytes_per_step": int(m.tau_rayl.size + m.tau_abs.size + f0.size) * 8,
+                        "d2h_bytes_per_step": int(nS * 4 * k * 8),
+                        "path": "vsmom_b200.raman.rt_run_rrs(model, rs) / rt_run_rrs_sharded: prepare() -> H2D -> vsm_rt_column_rrs_f64 -> "
+                                "(one all-gather) -> D2H -> NumPy"},
+                "per_rank": {"step_ms_min": min(rank_ms) / args.steps, "step_ms_max": max(rank_ms) / args.steps},
+                "roofline": {"bound": "tensor", "kernel": "k_rrs_inel (one warp per (n1, dn) unit: inelastic elemental + doubling levels + _11 interaction, DMMA)",
+                             "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
+                             "traffic": None,
+                             "peak_source": "fp64 FMA issue-rate microbenchmark measured live (vsm_measure_fma_peak); fp64 DMMA measures the same",
+                             "flop_accounting": "per unit and moment: 10 N^3-products + 10 mat-vecs per doubling level, 18 products + 8 mat-vecs "
+                                                "per interaction (the reference forms 17 products per level: it recomputes gp t, gp r t per dn), N = 15 "
+                                                "unpadded; executed on 16 x 16 tiles (+21 %)",
+                             "alg_flops_per_unit": per_unit, "units": units, "launches_per_step": n_inel,
+                             "launch_ms": t_inel / n_inel, "kernel_share_of_step": t_inel / t_total,
+                             "elastic_export_ms": t_el,
+                             "l2_record_bytes_per_unit": rec_bytes,
+                             "record_read_GBps": rec_bytes * units / (t_inel * 1e-3) / 1e9}}
+        if not args.no_parity_check:
+            om, ors, orr = _rrs_oracle_objects(m, rs)
+            idx = np.sort(np.random.default_rng(12345).choice(nS, size=min(args.parity_points, nS), replace=False))
+            t0 = time.perf_counter()
+            ref = orr.rt_run_rrs_points(om, ors, idx)
+            errs = {kk: float(np.max(np.abs(res[kk][..., idx] - ref[kk])) / np.max(np.abs(ref[kk]))) for kk in ref}
+            line["parity_check"] = {"n": int(idx.size), "max_rel": errs, "tol": 1e-9, "ok": bool(max(errs.values()) <= 1e-9),
+                                    "what": "random output wavelengths of the benchmarked band (after the gather), every Raman coupling, vs the CPU oracle",
+                                    "oracle_s": round(time.perf_counter() - t0, 1)}
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_rrs_points_per_sec(m, rs, args.cpu_seconds)
+            line["cpu_baseline"] = {k_: r[k_] for k_ in ("value", "unit", "cores", "kind", "sample", "per_core", "blas")}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.config == 4:
+    if a.config == 5:
+        run_rrs(a)
+    elif a.config == 4:
         run_lin(a)
     elif a.impl == "reference":
         run_reference(a)

@@ -323,7 +323,7 @@ def interaction_inelastic_11(rrs: RRS, C: Composite, CI: CompositeIE, r_mp, r_pm
 # --------------------------------------------------------------------------
 # rt_run(::RRS, model, iBand)   rt_run.jl:238-539 with rt_kernel!(::RRS) rt_kernel.jl:352-391
 # --------------------------------------------------------------------------
-def rt_run_rrs(model: Model, rrs: RRS, return_streams: bool = False):
+def rt_run_rrs(model: Model, rrs: RRS, return_streams: bool = False, ctl_override=None):
     """Returns dict(R_SFI, T_SFI, ieR_SFI, ieT_SFI), each (nVZA, pol_n, nSpec).  ``model.greek_rayleigh`` must be
     the Cabannes set and ``model.varpi_cabannes`` ϖ_Cabannes (compEffectiveLayerProperties.jl:36-41)."""
     FT = model.FT
@@ -347,6 +347,8 @@ def rt_run_rrs(model: Model, rrs: RRS, return_streams: bool = False):
         weight = FT(0.5 / math.pi) if m == 0 else FT(1.0 / math.pi)
         Zpp_r, Zmp_r = orc.compute_Z_moments(pol_n, q.qp_mu, rrs.greek_raman, m, FT)     # computeRamanZλ!
         ctl = orc.band_control(model, m)
+        if ctl_override is not None:      # control flow of the FULL band when `model` holds a subset of its points
+            ctl = orc.BandControl(ctl_override.scatter, ctl_override.ndoubl, ctl_override.interface, ctl.tau_sum)
         props = orc.construct_core_optical_properties(model, m)
         if not all(ctl.scatter):
             raise ValueError("RRS: every layer must scatter (rt_kernel.jl:366)")
@@ -393,3 +395,46 @@ def rt_run_rrs(model: Model, rrs: RRS, return_streams: bool = False):
     if return_streams:
         out['streams'] = streams
     return out
+
+
+def rt_run_rrs_points(model: Model, rrs: RRS, idx, F0=None):
+    """The RRS result at the band indices ``idx`` only, without running the whole band: a unit (n1, dn) reads nothing
+    but the spectral points n1 and n0 = n1 + i_shift[dn], and its contribution is linear in ϖ_λ₁λ₀[dn], so every
+    unit is evaluated as the first point of a two-point band [n1, n0] with one Raman line of shift +1 and weight 1
+    (the spurious coupling n0 -> next pair only lands on the odd, ignored outputs).  Control flow from the full band.
+    Returns dict(R_SFI, T_SFI, ieR_SFI, ieT_SFI) of shape (nVZA, pol_n, len(idx)).  Used by bench.py (parity check
+    of the benchmarked band, CPU baseline sample)."""
+    import copy
+    idx = np.asarray(idx, int)
+    nS = model.nSpec
+    ctl_full = orc.band_control(model, 0)
+    pairs, owner, wts = [], [], []
+    for q, n1 in enumerate(idx):
+        for dn, sh in enumerate(rrs.i_shift):
+            n0 = n1 + int(sh)
+            if 0 <= n0 < nS:
+                pairs += [n1, n0]
+                owner.append(q)
+                wts.append(rrs.varpi_raman[dn])
+    if not pairs:                                   # no coupling at all: elastic only
+        pairs = [v for n1 in idx for v in (n1, n1)]
+        owner = list(range(len(idx)))
+        wts = [0.0] * len(idx)
+    pairs = np.asarray(pairs)
+    sub = copy.copy(model)
+    sub.tau_rayl = model.tau_rayl[pairs]
+    sub.tau_abs = model.tau_abs[pairs]
+    Fb = model.F0 if F0 is None else F0
+    sub.F0 = None if Fb is None else np.asarray(Fb)[:, pairs]
+    out = rt_run_rrs(sub, RRS(np.array([1]), np.array([1.0]), rrs.greek_raman), ctl_override=ctl_full)
+    nV, pn = out["R_SFI"].shape[:2]
+    res = {k: np.zeros((nV, pn, len(idx)), model.FT) for k in ("R_SFI", "T_SFI", "ieR_SFI", "ieT_SFI")}
+    seen = set()
+    for u, (q, w) in enumerate(zip(owner, wts)):
+        res["ieR_SFI"][:, :, q] += w * out["ieR_SFI"][:, :, 2 * u]
+        res["ieT_SFI"][:, :, q] += w * out["ieT_SFI"][:, :, 2 * u]
+        if q not in seen:
+            seen.add(q)
+            res["R_SFI"][:, :, q] = out["R_SFI"][:, :, 2 * u]
+            res["T_SFI"][:, :, q] = out["T_SFI"][:, :, 2 * u]
+    return res

@@ -140,3 +140,20 @@ def test_get_n0_n1_matches_reference_ranges():
             continue
         assert (s1.start + 1, s1.stop) == (lo1, hi1)
         assert (s0.start + 1, s0.stop) == (lo1 + d, hi1 + d)
+
+
+def test_pointwise_evaluation_equals_full_band():
+    """rt_run_rrs_points (unit-wise two-point bands) reproduces the full-band oracle at the selected indices."""
+    rng = np.random.default_rng(2)
+    nS, Nz, eps = 30, 3, 0.03
+    m = _flat_model(eps, nS=nS, Nz=Nz, tau=0.05)
+    m.tau_abs = rng.random((nS, Nz)) * 0.2
+    m.tau_rayl = m.tau_rayl * (1 + 0.1 * rng.random((nS, 1)))
+    shifts = np.array([-7, -3, 2, 5, 12])
+    w = rrs.normalize_raman_weights(rng.random(5) + 0.2, 1.0 - eps)
+    r = rrs.RRS(shifts, w, rrs.get_greek_raman(0.1))
+    full = rrs.rt_run_rrs(m, r)
+    idx = np.array([0, 4, 13, 22, 29])
+    part = rrs.rt_run_rrs_points(m, r, idx)
+    for k in full:
+        np.testing.assert_allclose(part[k], full[k][:, :, idx], rtol=1e-11, atol=1e-16)
