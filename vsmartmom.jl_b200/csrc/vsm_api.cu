@@ -1067,7 +1067,8 @@ static int rt_column_rrs_impl(vsm_ctx* ctx, const vsm_column_desc* d, const vsm_
 
     // ---- workspace (doubles)
     const size_t U = (size_t)nR * n1cnt;
-    const size_t w_props = ((size_t)Nz * (2 + nC) + Nz + 1) * nE, w_fsc = (size_t)Nz * nE;
+    auto even = [](size_t x) { return (x + 1) & ~size_t(1); };          // keep every array 16-byte aligned (vector loads)
+    const size_t w_props = even(((size_t)Nz * (2 + nC) + Nz + 1) * nE), w_fsc = even((size_t)Nz * nE);
     const size_t w_cE = (size_t)nE * kd->ce, w_cI = U * kd->ci;
     const size_t w_rec0 = (size_t)std::max(1, ndmax) * nE * kd->rec0, w_rec1 = (size_t)std::max(1, ndmax) * nE * kd->rec1;
     const size_t w_i0 = (size_t)nE * kd->irec0, w_i1 = (size_t)nE * kd->irec1;

@@ -37,12 +37,67 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// element accessors: shared (ld = NP+4), global record (ld = NP), and their D-conjugates  s_i M_ij s_j
-template <int NP> struct SM { const double* p; __device__ __forceinline__ double operator()(int i, int j) const { return p[i + j * (NP + 4)]; } };
-template <int NP> struct GMr { const double* p; __device__ __forceinline__ double operator()(int i, int j) const { return __ldg(p + i + j * NP); } };
-template <int NP> struct GMw { const double* p; __device__ __forceinline__ double operator()(int i, int j) const { return p[i + j * NP]; } };
-template <class M> struct Conj { M m; const double* s; __device__ __forceinline__ double operator()(int i, int j) const { return m(i, j) * s[i] * s[j]; } };
-struct Zero { __device__ __forceinline__ double operator()(int, int) const { return 0.0; } };
+// Operand accessors.  A product C = A B runs its k loop in the order k = 16 kb + 4 tg + s (lane tg, step s): any
+// order is valid as long as both operands use it, and this one lets a lane fetch its four k-values of a global
+// operand as ONE 32-byte run (two 16-byte loads; one fully used sector) instead of four 8-byte gathers:
+//   a4(i, k0, v): v[s] = M(i, k0+s)      b4(k0, j, v): v[s] = M(k0+s, j)      operator()(i, j) = M(i, j)
+//   SM   shared, column-major, ld = NP+1 (== 1 mod 16: a4 / b4 / mat-vec rows are bank-conflict free)
+//   GB   global, column-major ld = NP        -> the B side of a product  (b4 vectorised)
+//   GA   global, stored TRANSPOSED (ld = NP) -> the A side of a product  (a4 vectorised)
+template <int NP> struct SM {
+    const double* p;
+    __device__ __forceinline__ double operator()(int i, int j) const { return p[i + j * (NP + 1)]; }
+    __device__ __forceinline__ void a4(int i, int k0, double (&v)[4]) const {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) v[s] = p[i + (k0 + s) * (NP + 1)];
+    }
+    __device__ __forceinline__ void b4(int k0, int j, double (&v)[4]) const {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) v[s] = p[k0 + s + j * (NP + 1)];
+    }
+};
+template <int NP, bool RO = true> struct GB {
+    const double* p;
+    __device__ __forceinline__ double operator()(int i, int j) const { return RO ? __ldg(p + i + j * NP) : p[i + j * NP]; }
+    __device__ __forceinline__ void a4(int i, int k0, double (&v)[4]) const {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) v[s] = (*this)(i, k0 + s);
+    }
+    __device__ __forceinline__ void b4(int k0, int j, double (&v)[4]) const {
+        const double2* q = reinterpret_cast<const double2*>(p + k0 + j * NP);
+        const double2 x = RO ? __ldg(q) : q[0], y = RO ? __ldg(q + 1) : q[1];
+        v[0] = x.x; v[1] = x.y; v[2] = y.x; v[3] = y.y;
+    }
+};
+template <int NP> struct GA {
+    const double* p;
+    __device__ __forceinline__ double operator()(int i, int j) const { return __ldg(p + j + i * NP); }
+    __device__ __forceinline__ void a4(int i, int k0, double (&v)[4]) const {
+        const double2* q = reinterpret_cast<const double2*>(p + k0 + i * NP);
+        const double2 x = __ldg(q), y = __ldg(q + 1);
+        v[0] = x.x; v[1] = x.y; v[2] = y.x; v[3] = y.y;
+    }
+    __device__ __forceinline__ void b4(int k0, int j, double (&v)[4]) const {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) v[s] = (*this)(k0 + s, j);
+    }
+};
+template <class M> struct Conj {      // D M D
+    M m; const double* s;
+    __device__ __forceinline__ double operator()(int i, int j) const { return m(i, j) * s[i] * s[j]; }
+    __device__ __forceinline__ void a4(int i, int k0, double (&v)[4]) const {
+        m.a4(i, k0, v);
+        const double si = s[i];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] *= si * s[k0 + q];
+    }
+    __device__ __forceinline__ void b4(int k0, int j, double (&v)[4]) const {
+        m.b4(k0, j, v);
+        const double sj = s[j];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] *= sj * s[k0 + q];
+    }
+};
 struct SV { const double* p; __device__ __forceinline__ double operator()(int k) const { return p[k]; } };
 struct GV { const double* p; __device__ __forceinline__ double operator()(int k) const { return __ldg(p + k); } };
 
@@ -54,28 +109,42 @@ __device__ __forceinline__ void czero(double (&c)[NP / 8][NP / 8][2]) {
         for (int q = 0; q < NP / 8; ++q) c[r][q][0] = c[r][q][1] = 0.0;
 }
 
-// c += A B on the fp64 tensor cores; a(i,k), b(k,j) are element accessors over the zero-padded NP x NP operands
+// c += A B on the fp64 tensor cores over the zero-padded NP x NP operands (k order: see above)
 template <int NP, class FA, class FB>
 __device__ __forceinline__ void wmm(double (&c)[NP / 8][NP / 8][2], FA a, FB b, int lane) {
     constexpr int NT = NP / 8;
     const int g = lane >> 2, tg = lane & 3;
-    auto step = [&](int k0) {
-        double af[NT], bf[NT];
-#pragma unroll
-        for (int r = 0; r < NT; ++r) af[r] = a(8 * r + g, k0 + tg);
-#pragma unroll
-        for (int q = 0; q < NT; ++q) bf[q] = b(k0 + tg, 8 * q + g);
-#pragma unroll
-        for (int r = 0; r < NT; ++r)
-#pragma unroll
-            for (int q = 0; q < NT; ++q) dmma(c[r][q][0], c[r][q][1], af[r], bf[q]);
-    };
     if constexpr (NP <= 16) {
 #pragma unroll
-        for (int k0 = 0; k0 < NP; k0 += 4) step(k0);
+        for (int kb = 0; kb < NP; kb += 16) {
+            double af[NT][4], bf[NT][4];
+#pragma unroll
+            for (int r = 0; r < NT; ++r) a.a4(8 * r + g, kb + 4 * tg, af[r]);
+#pragma unroll
+            for (int q = 0; q < NT; ++q) b.b4(kb + 4 * tg, 8 * q + g, bf[q]);
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+#pragma unroll
+                for (int r = 0; r < NT; ++r)
+#pragma unroll
+                    for (int q = 0; q < NT; ++q) dmma(c[r][q][0], c[r][q][1], af[r][s], bf[q][s]);
+        }
     } else {
 #pragma unroll 1
-        for (int k0 = 0; k0 < NP; k0 += 4) step(k0);
+        for (int kb = 0; kb < NP; kb += 16)
+#pragma unroll 1
+            for (int s = 0; s < 4; ++s) {
+                double af[NT], bf[NT];
+                const int k = kb + 4 * tg + s;
+#pragma unroll
+                for (int r = 0; r < NT; ++r) af[r] = a(8 * r + g, k);
+#pragma unroll
+                for (int q = 0; q < NT; ++q) bf[q] = b(k, 8 * q + g);
+#pragma unroll
+                for (int r = 0; r < NT; ++r)
+#pragma unroll
+                    for (int q = 0; q < NT; ++q) dmma(c[r][q][0], c[r][q][1], af[r], bf[q]);
+            }
     }
 }
 
@@ -99,18 +168,51 @@ __device__ __forceinline__ void wmv(double (&y)[NP / 16], FA a, FX x, int lane) 
 #pragma unroll
     for (int b = 0; b < NP / 16; ++b) {
         double s = 0.0;
-#pragma unroll 8
-        for (int k = half * (NP / 2); k < (half + 1) * (NP / 2); ++k) s = fma(a(16 * b + row, k), x(k), s);
+#pragma unroll 2
+        for (int k = half * (NP / 2); k < (half + 1) * (NP / 2); k += 4) {
+            double v[4];
+            a.a4(16 * b + row, k, v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s = fma(v[q], x(k + q), s);
+        }
         s += __shfl_xor_sync(0xffffffffu, s, 16);
         y[b] = s;
     }
+}
+
+// ---- register-resident fragments of a 16 x 16 operand (NP = 16): 8 doubles per lane hold the whole matrix as the A side
+//      (af[r][s] = M(8r+g, 4tg+s)) or as the B side (bf[q][s] = M(4tg+s, 8q+g)), so an operand that enters several
+//      products of a doubling level crosses the L1 data pipe once
+typedef double Frag16[2][4];
+template <class M> __device__ __forceinline__ void lfA(const M& m, Frag16& f, int g, int tg) { m.a4(g, 4 * tg, f[0]); m.a4(8 + g, 4 * tg, f[1]); }
+template <class M> __device__ __forceinline__ void lfB(const M& m, Frag16& f, int g, int tg) { m.b4(4 * tg, g, f[0]); m.b4(4 * tg, 8 + g, f[1]); }
+__device__ __forceinline__ void mmf(double (&c)[2][2][2], const Frag16& a, const Frag16& b) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) dmma(c[r][q][0], c[r][q][1], a[r][s], b[q][s]);
+}
+// two mat-vecs that share the matrix as ONE tensor-core tile: B tile column 0 = x1, column 1 = x2, the rest zero;
+// on return lanes with tg == 0 hold y1[8r+g] = cv[r][0], y2[8r+g] = cv[r][1]
+template <class X1, class X2>
+__device__ __forceinline__ void mvf(double (&cv)[2][2], const Frag16& a, X1 x1, X2 x2, int g, int tg) {
+    double bx[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) bx[s] = (g == 0) ? x1(4 * tg + s) : ((g == 1) ? x2(4 * tg + s) : 0.0);
+    cv[0][0] = cv[0][1] = cv[1][0] = cv[1][1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) dmma(cv[r][0], cv[r][1], a[r][s], bx[s]);
 }
 
 // in-place inverse of the leading n x n block of M (shared, ld = NP+4) by Gauss-Jordan with partial pivoting
 // (the reference's getrf/getri route, cpu_batched.jl:32-37); colk: NP doubles, piv: NP ints of scratch
 template <int NP>
 __device__ __forceinline__ void winv(double* M, int n, double* colk, int* piv, int lane) {
-    constexpr int LDS = NP + 4;
+    constexpr int LDS = NP + 1;
     for (int k = 0; k < n; ++k) {
         __syncwarp();
         double best = -1.0;
@@ -276,7 +378,7 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_elastic(Args a, int m, int iz,
                 const double rv = r[i + j * LDS];
                 R0[e] = rv;
                 R0[MG + e] = t[i + j * LDS];
-                R1[e] = rv;
+                R1[j + i * NP] = rv;
             }
             czero<NP>(c);
             wmm<NP>(c, sr, sr, lane);
@@ -284,7 +386,7 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_elastic(Args a, int m, int iz,
             winv<NP>(Gm, n, colk, piv, lane);
             czero<NP>(c);                                               // tt⁺⁺_gp_refl = t gp
             wmm<NP>(c, st, sG, lane);
-            wepi<NP>(c, [&](int i, int j, double v) { TG[i + j * LDS] = v; R1[MG + i + j * NP] = v; }, lane);
+            wepi<NP>(c, [&](int i, int j, double v) { TG[i + j * LDS] = v; R1[MG + j + i * NP] = v; }, lane);
             czero<NP>(c);                                               // gp t
             wmm<NP>(c, sG, st, lane);
             wepi<NP>(c, [&](int i, int j, double v) { R0[2 * MG + i + j * NP] = v; }, lane);
@@ -373,7 +475,7 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_elastic(Args a, int m, int iz,
     // ---- interaction_helper!(::ScatteringInterface_11) elastic lines (interaction_inelastic.jl:372-373, 402-403,
     //      423-427, 441-442, 463-464, 489-502) with the exports the units need
     const double* Cin = a.cE_in + (size_t)p * G::CE;
-    const GMw<NP> Rmp{Cin}, Rpm{Cin + MG}, Tpp{Cin + 2 * MG}, Tmm{Cin + 3 * MG};
+    const GB<NP, false> Rmp{Cin}, Rpm{Cin + MG}, Tpp{Cin + 2 * MG}, Tmm{Cin + 3 * MG};
     const double* J0p = Cin + 4 * MG; const double* J0m = J0p + NP;
     const bool surf = (mode == 1);
     const Conj<SM<NP>> stmm{st, sg};
@@ -384,7 +486,7 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_elastic(Args a, int m, int iz,
         const int i = e % NP, j = e / NP;
         const double rv = r[i + j * LDS], rpm = Cin[MG + e];
         I0[e] = rpm; I0[MG + e] = Cin[2 * MG + e]; I0[2 * MG + e] = rv; I0[3 * MG + e] = t[i + j * LDS] * sg[i] * sg[j];
-        I1[2 * MG + e] = rv; I1[3 * MG + e] = rpm;
+        I1[2 * MG + j + i * NP] = rv; I1[3 * MG + j + i * NP] = rpm;
     }
     for (int i = lane; i < NP; i += 32) { IV[2 * NP + i] = J0p[i]; IV[3 * NP + i] = jm[i]; }
     double y1[NP / 16], y2[NP / 16];
@@ -395,7 +497,7 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_elastic(Args a, int m, int iz,
     winv<NP>(Gm, n, colk, piv, lane);
     czero<NP>(c);                                                   // T01_inv = T-- inv1
     wmm<NP>(c, Tmm, sG, lane);
-    wepi<NP>(c, [&](int i, int j, double v) { TG[i + j * LDS] = v; I1[i + j * NP] = v; }, lane);
+    wepi<NP>(c, [&](int i, int j, double v) { TG[i + j * LDS] = v; I1[j + i * NP] = v; }, lane);
     czero<NP>(c);                                                   // inv1 r
     wmm<NP>(c, sG, sr, lane);
     wepi<NP>(c, [&](int i, int j, double v) { S[i + j * LDS] = v; }, lane);
@@ -432,7 +534,7 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_elastic(Args a, int m, int iz,
     winv<NP>(Gm, n, colk, piv, lane);
     czero<NP>(c);                                                   // T21_inv = t++ inv2
     wmm<NP>(c, st, sG, lane);
-    wepi<NP>(c, [&](int i, int j, double v) { TG[i + j * LDS] = v; I1[MG + i + j * NP] = v; }, lane);
+    wepi<NP>(c, [&](int i, int j, double v) { TG[i + j * LDS] = v; I1[MG + j + i * NP] = v; }, lane);
     czero<NP>(c);                                                   // E3 = inv2 T++
     wmm<NP>(c, sG, Tpp, lane);
     wepi<NP>(c, [&](int i, int j, double v) { I0[6 * MG + i + j * NP] = v; }, lane);
@@ -482,7 +584,7 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_elastic(Args a, int m, int iz,
 // inelastic units: one warp per (n1, dn)
 // ----------------------------------------------------------------------------------------------------------------
 template <int NP, int WPC>
-__global__ void __launch_bounds__(32 * WPC) k_rrs_inel(Args a, int m, int iz, int mode, unsigned int total) {
+__global__ void __launch_bounds__(32 * WPC, (NP <= 16) ? 4 : 1) k_rrs_inel(Args a, int m, int iz, int mode, unsigned int total) {
     using G = Geo<NP>;
     constexpr int LDS = G::LDS, MS = G::MS, MG = G::MG;
     extern __shared__ __align__(16) unsigned char rrs_smem[];
@@ -497,7 +599,7 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_inel(Args a, int m, int iz, in
     if (n0 < 0 || n0 >= a.nBand) return;                 // get_n₀_n₁ (inelastic_helper.jl:19-26): unit stays zero
     const int p0 = n0 - a.e0, p1 = n1 - a.e0;
     const size_t u = (size_t)dn * a.n1cnt + (n1 - a.n1lo);
-    constexpr int kVecs = 10;
+    constexpr int kVecs = 7;
     double* base = reinterpret_cast<double*>(rrs_smem) + (size_t)warp * (5 * MS + kVecs * NP);
     double* A = base; double* B = A + MS; double* X = B + MS; double* S1 = X + MS; double* S2 = S1 + MS;
     double* jp = S2 + MS; double* jm = jp + NP; double* v1p = jm + NP; double* v1m = v1p + NP;
@@ -519,6 +621,24 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_inel(Args a, int m, int iz, in
         const double wsc = (m == 0) ? 0.5 : 0.25;
         const double* Zpp = a.ZppR + (size_t)m * n * n;
         const double* Zmp = a.ZmpR + (size_t)m * n * n;
+        // Every transcendental of the element formulas depends on one stream at a time: E1_i = expm1(-dτ₁/μ_i),
+        // E0_i = expm1(-dτ₀/μ_i), ED_i = exp(-dτ₁/μ_i) - exp(-dτ₀/μ_i) are evaluated once per row (4 N calls instead of
+        // 3 N²) and combined exactly: -expm1(-(x+y)) = -(u + v + u v), exp(-y) = 1 + v, and exp(-x) - exp(-y) = u - v
+        // unless x and y agree to 1e-3 (then the reference's expdiff_neg itself; cancellation bound 1e3 eps).
+        double* vE1 = v1p; double* vE0 = v1m; double* vED = w3; double* va1 = w4; double* va0 = jp;
+        for (int i = lane; i < NP; i += 32) {
+            const double mui = a.mu[i];
+            const double x1 = d1 / mui, x0 = d0 / mui;
+            va1[i] = x1; va0[i] = x0;
+            vE1[i] = expm1(-x1); vE0[i] = expm1(-x0);
+            vED[i] = expdiff_neg<double>(x1, x0);
+        }
+        __syncwarp();
+        auto ediff = [&](int i, int j) {          // exp(-dτ₁/μ_i) - exp(-dτ₀/μ_j)
+            const double x = va1[i], y = va0[j];
+            if (fabs(x - y) < 1e-3 * fmax(x, y)) return expdiff_neg<double>(x, y);
+            return vE1[i] - vE0[j];
+        };
         for (int e = lane; e < NP * NP; e += 32) {
             const int i = e % NP, j = e / NP;
             double rv = 0.0, tv = 0.0;
@@ -527,14 +647,16 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_inel(Args a, int m, int iz, in
                 if (wct > kWeightTol) {
                     const double mui = a.mu[i], muj = a.mu[j];
                     const double zpp = Zpp[i + (size_t)j * n], zmp = Zmp[i + (size_t)j * n];
-                    rv = fw * zmp * (1.0 / ((mui / muj) + ratio)) * (-expm1(-((d1 / mui) + (d0 / muj)))) * wct;
+                    const double u = vE1[i], v = vE0[j];
+                    const double mr = mui / muj;
+                    rv = fw * zmp * (1.0 / (mr + ratio)) * (-(u + v + u * v)) * wct;
                     if (mui == muj) {
-                        if (fabs(d0 - d1) > kLooseTol) tv = fw * zpp * wct * expdiff_neg<double>(d1 / mui, d0 / muj) / (1.0 - ratio);
-                        else tv = (d0 / mui) * fw * zpp * wct * exp(-d0 / muj);
-                    } else if (fabs((mui / muj) - ratio) < kCloseTol) {
-                        tv = (d0 / mui) * fw * zpp * wct * exp(-d0 / muj);
+                        if (fabs(d0 - d1) > kLooseTol) tv = fw * zpp * wct * vED[i] / (1.0 - ratio);
+                        else tv = va0[i] * fw * zpp * wct * (1.0 + v);
+                    } else if (fabs(mr - ratio) < kCloseTol) {
+                        tv = va0[i] * fw * zpp * wct * (1.0 + v);
                     } else {
-                        tv = fw * zpp * (1.0 / ((mui / muj) - ratio)) * wct * expdiff_neg<double>(d1 / mui, d0 / muj);
+                        tv = fw * zpp * (1.0 / (mr - ratio)) * wct * ediff(i, j);
                     }
                     if (nd >= 1) rv *= sg[i];
                 }
@@ -545,6 +667,8 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_inel(Args a, int m, int iz, in
         {
             const double mus = a.mu[a.istart];
             const double att = exp(-a.p_tausum[(size_t)iz * a.nE + p0] / mus);
+            const double vs = vE0[a.istart], a0s = va0[a.istart];
+            __syncwarp();                // va0 aliases jp: the solar-stream entry is read by every lane before jp is written
             for (int i = lane; i < NP; i += 32) {
                 double vp = 0.0, vm = 0.0;
                 if (i < n) {
@@ -555,15 +679,18 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_inel(Args a, int m, int iz, in
                         zmI = fma(Zmp[i + (size_t)(a.istart + s) * n], f0, zmI);
                     }
                     const double mui = a.mu[i];
+                    const double u = vE1[i];
                     if (i >= a.istart && i < a.istart + a.nStokes) {
-                        if (fabs(d0 - d1) > kCloseTol) vp = fw * zpI * wsc * expdiff_neg<double>(d1 / mui, d0 / mui) / (1.0 - ratio);
-                        else vp = (d0 / mui) * wsc * fw * zpI * exp(-d0 / mui);
+                        if (fabs(d0 - d1) > kCloseTol) vp = fw * zpI * wsc * vED[i] / (1.0 - ratio);
+                        else vp = va0[i] * wsc * fw * zpI * (1.0 + vE0[i]);
                     } else if (fabs((mui / mus) - ratio) < kCloseTol) {
-                        vp = (d0 / mui) * wsc * fw * zpI * exp(-d0 / mus);
+                        vp = va0[i] * wsc * fw * zpI * (1.0 + vs);
                     } else {
-                        vp = wsc * fw * zpI * (1.0 / ((mui / mus) - ratio)) * expdiff_neg<double>(d1 / mui, d0 / mus);
+                        const double x = va1[i];
+                        const double ed = (fabs(x - a0s) < 1e-3 * fmax(x, a0s)) ? expdiff_neg<double>(x, a0s) : (u - vs);
+                        vp = wsc * fw * zpI * (1.0 / ((mui / mus) - ratio)) * ed;
                     }
-                    vm = wsc * fw * zmI * (1.0 / ((mui / mus) + ratio)) * (-expm1(-((d1 / mui) + (d0 / mus))));
+                    vm = wsc * fw * zmI * (1.0 / ((mui / mus) + ratio)) * (-(u + vs + u * vs));
                     vp *= att;
                     vm *= att;
                     if (nd >= 1) vm *= sg[i];
@@ -577,67 +704,148 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_inel(Args a, int m, int iz, in
         for (int l = 0; l < nd; ++l) {
             const double* R0 = a.rec0 + ((size_t)l * a.nE + p0) * G::REC0;
             const double* R1 = a.rec1 + ((size_t)l * a.nE + p1) * G::REC1;
-            const GMr<NP> r0{R0}, t0{R0 + MG}, GT0{R0 + 2 * MG}, GR0{R0 + 3 * MG}, GRT0{R0 + 4 * MG};
-            const GMr<NP> r1{R1}, TG1{R1 + MG};
+            const GB<NP> r0{R0}, t0{R0 + MG}, GT0{R0 + 2 * MG}, GR0{R0 + 3 * MG}, GRT0{R0 + 4 * MG};
+            const GA<NP> r1{R1}, TG1{R1 + MG};
             const double* V0 = R0 + 5 * MG;
             const GV tmp1{V0}, tmp2{V0 + NP}, J0p0{V0 + 2 * NP}, J1m0{V0 + 3 * NP};
             const double e0 = __ldg(V0 + 4 * NP);
-            // X = ier r0 + r1 ier
-            czero<NP>(c);
-            wmm<NP>(c, sA, r0, lane);
-            wmm<NP>(c, r1, sA, lane);
-            wepi<NP>(c, [&](int i, int j, double v) { X[i + j * LDS] = v; }, lane);
-            for (int i = lane; i < NP; i += 32) { v1p[i] = jp[i] * e0; v1m[i] = jm[i] * e0; }
-            __syncwarp();
-            // sources (:74-98)
-            wmv<NP>(y1, r1, SV{v1m}, lane);
-            wmv<NP>(y2, sA, J1m0, lane);
-            wmv<NP>(y3, sX, tmp1, lane);
-            if (lane < 16) for (int b = 0; b < NP / 16; ++b) { const int i = 16 * b + lane; w3[i] = jp[i] + y1[b] + y2[b] + y3[b]; }
-            wmv<NP>(y1, sA, J0p0, lane);
-            wmv<NP>(y2, r1, SV{jp}, lane);
-            wmv<NP>(y3, sX, tmp2, lane);
-            if (lane < 16) for (int b = 0; b < NP / 16; ++b) { const int i = 16 * b + lane; w4[i] = v1m[i] + y1[b] + y2[b] + y3[b]; }
-            __syncwarp();
-            wmv<NP>(y1, TG1, SV{w3}, lane);
-            wmv<NP>(y2, sB, tmp1, lane);
-            wmv<NP>(y3, TG1, SV{w4}, lane);
-            double y4[NP / 16];
-            wmv<NP>(y4, sB, tmp2, lane);
-            __syncwarp();
-            if (lane < 16)
-                for (int b = 0; b < NP / 16; ++b) {
-                    const int i = 16 * b + lane;
-                    jp[i] = v1p[i] + y1[b] + y2[b];
-                    jm[i] = jm[i] + y3[b] + y4[b];
+            if constexpr (NP == 16) {
+                // ---- fragments in registers: every global operand is fetched once per level, the mat-vec pairs ride
+                //      on the tensor pipe with the matrix fragments that are already there
+                const int g = lane >> 2, tg = lane & 3;
+                Frag16 r1A, TG1A, AA, XA, T;
+                double cv1[2][2], cv2[2][2], cv3[2][2];
+                lfA(r1, r1A, g, tg);
+                lfA(TG1, TG1A, g, tg);
+                // X = ier r0 + r1 ier
+                lfA(sA, AA, g, tg);
+                lfB(r0, T, g, tg);
+                czero<NP>(c);
+                mmf(c, AA, T);
+                lfB(sA, T, g, tg);
+                mmf(c, r1A, T);
+                wepi<NP>(c, [&](int i, int j, double v) { X[i + j * LDS] = v; }, lane);
+                if (lane < NP) { v1p[lane] = jp[lane] * e0; v1m[lane] = jm[lane] * e0; }
+                __syncwarp();
+                lfA(sX, XA, g, tg);
+                // sources (:74-98)
+                mvf(cv1, r1A, SV{v1m}, SV{jp}, g, tg);            // r1 ieJ1-          | r1 ieJ0+
+                mvf(cv2, AA, J1m0, J0p0, g, tg);                  // ier J1-[n0]       | ier J0+[n0]
+                mvf(cv3, XA, tmp1, tmp2, g, tg);                  // X tmp1[n0]        | X tmp2[n0]
+                if (tg == 0) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const int i = 8 * r + g;
+                        w3[i] = jp[i] + cv1[r][0] + cv2[r][0] + cv3[r][0];
+                        w4[i] = v1m[i] + cv2[r][1] + cv1[r][1] + cv3[r][1];
+                    }
                 }
-            // S1 = iet + X gp t ; S2 = ier + X gp r
-            czero<NP>(c);
-            wmm<NP>(c, sX, GT0, lane);
-            wepi<NP>(c, [&](int i, int j, double v) { S1[i + j * LDS] = B[i + j * LDS] + v; }, lane);
-            czero<NP>(c);
-            wmm<NP>(c, sX, GR0, lane);
-            wepi<NP>(c, [&](int i, int j, double v) { S2[i + j * LDS] = A[i + j * LDS] + v; }, lane);
-            __syncwarp();
-            // V = r1 iet + S2 t0   (into X)
-            czero<NP>(c);
-            wmm<NP>(c, r1, sB, lane);
-            wmm<NP>(c, sS2, t0, lane);
-            __syncwarp();
-            wepi<NP>(c, [&](int i, int j, double v) { X[i + j * LDS] = v; }, lane);
-            __syncwarp();
-            // ier' = ier + iet (gp r t)0 + tt1 V ;  iet' = tt1 S1 + iet (gp t)0
-            czero<NP>(c);
-            wmm<NP>(c, sB, GRT0, lane);
-            wmm<NP>(c, TG1, sX, lane);
-            wepi<NP>(c, [&](int i, int j, double v) { A[i + j * LDS] += v; }, lane);
-            czero<NP>(c);
-            wmm<NP>(c, TG1, sS1, lane);
-            wmm<NP>(c, sB, GT0, lane);
-            __syncwarp();
-            wepi<NP>(c, [&](int i, int j, double v) { B[i + j * LDS] = v; }, lane);
-            __syncwarp();
+                __syncwarp();
+                Frag16 BA;
+                lfA(sB, BA, g, tg);
+                mvf(cv1, TG1A, SV{w3}, SV{w4}, g, tg);
+                mvf(cv2, BA, tmp1, tmp2, g, tg);
+                if (tg == 0) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const int i = 8 * r + g;
+                        jp[i] = v1p[i] + cv1[r][0] + cv2[r][0];
+                        jm[i] = jm[i] + cv1[r][1] + cv2[r][1];
+                    }
+                }
+                // S1 = iet + X gp t ; S2 = ier + X gp r
+                Frag16 GT0B;
+                lfB(GT0, GT0B, g, tg);
+                czero<NP>(c);
+                mmf(c, XA, GT0B);
+                wepi<NP>(c, [&](int i, int j, double v) { S1[i + j * LDS] = B[i + j * LDS] + v; }, lane);
+                lfB(GR0, T, g, tg);
+                czero<NP>(c);
+                mmf(c, XA, T);
+                wepi<NP>(c, [&](int i, int j, double v) { S2[i + j * LDS] = A[i + j * LDS] + v; }, lane);
+                __syncwarp();
+                // V = r1 iet + S2 t0   (into X)
+                lfB(sB, T, g, tg);
+                czero<NP>(c);
+                mmf(c, r1A, T);
+                lfA(sS2, AA, g, tg);
+                lfB(t0, T, g, tg);
+                mmf(c, AA, T);
+                wepi<NP>(c, [&](int i, int j, double v) { X[i + j * LDS] = v; }, lane);
+                __syncwarp();
+                // ier' = ier + iet (gp r t)0 + tt1 V
+                lfB(GRT0, T, g, tg);
+                czero<NP>(c);
+                mmf(c, BA, T);
+                lfB(sX, T, g, tg);
+                mmf(c, TG1A, T);
+                wepi<NP>(c, [&](int i, int j, double v) { A[i + j * LDS] += v; }, lane);
+                // iet' = tt1 S1 + iet (gp t)0
+                lfB(sS1, T, g, tg);
+                czero<NP>(c);
+                mmf(c, TG1A, T);
+                mmf(c, BA, GT0B);
+                __syncwarp();
+                wepi<NP>(c, [&](int i, int j, double v) { B[i + j * LDS] = v; }, lane);
+                __syncwarp();
+            } else {
+                // X = ier r0 + r1 ier
+                czero<NP>(c);
+                wmm<NP>(c, sA, r0, lane);
+                wmm<NP>(c, r1, sA, lane);
+                wepi<NP>(c, [&](int i, int j, double v) { X[i + j * LDS] = v; }, lane);
+                for (int i = lane; i < NP; i += 32) { v1p[i] = jp[i] * e0; v1m[i] = jm[i] * e0; }
+                __syncwarp();
+                // sources (:74-98)
+                wmv<NP>(y1, r1, SV{v1m}, lane);
+                wmv<NP>(y2, sA, J1m0, lane);
+                wmv<NP>(y3, sX, tmp1, lane);
+                if (lane < 16) for (int b = 0; b < NP / 16; ++b) { const int i = 16 * b + lane; w3[i] = jp[i] + y1[b] + y2[b] + y3[b]; }
+                wmv<NP>(y1, sA, J0p0, lane);
+                wmv<NP>(y2, r1, SV{jp}, lane);
+                wmv<NP>(y3, sX, tmp2, lane);
+                if (lane < 16) for (int b = 0; b < NP / 16; ++b) { const int i = 16 * b + lane; w4[i] = v1m[i] + y1[b] + y2[b] + y3[b]; }
+                __syncwarp();
+                wmv<NP>(y1, TG1, SV{w3}, lane);
+                wmv<NP>(y2, sB, tmp1, lane);
+                wmv<NP>(y3, TG1, SV{w4}, lane);
+                double y4[NP / 16];
+                wmv<NP>(y4, sB, tmp2, lane);
+                __syncwarp();
+                if (lane < 16)
+                    for (int b = 0; b < NP / 16; ++b) {
+                        const int i = 16 * b + lane;
+                        jp[i] = v1p[i] + y1[b] + y2[b];
+                        jm[i] = jm[i] + y3[b] + y4[b];
+                    }
+                // S1 = iet + X gp t ; S2 = ier + X gp r
+                czero<NP>(c);
+                wmm<NP>(c, sX, GT0, lane);
+                wepi<NP>(c, [&](int i, int j, double v) { S1[i + j * LDS] = B[i + j * LDS] + v; }, lane);
+                czero<NP>(c);
+                wmm<NP>(c, sX, GR0, lane);
+                wepi<NP>(c, [&](int i, int j, double v) { S2[i + j * LDS] = A[i + j * LDS] + v; }, lane);
+                __syncwarp();
+                // V = r1 iet + S2 t0   (into X)
+                czero<NP>(c);
+                wmm<NP>(c, r1, sB, lane);
+                wmm<NP>(c, sS2, t0, lane);
+                __syncwarp();
+                wepi<NP>(c, [&](int i, int j, double v) { X[i + j * LDS] = v; }, lane);
+                __syncwarp();
+                // ier' = ier + iet (gp r t)0 + tt1 V ;  iet' = tt1 S1 + iet (gp t)0
+                czero<NP>(c);
+                wmm<NP>(c, sB, GRT0, lane);
+                wmm<NP>(c, TG1, sX, lane);
+                wepi<NP>(c, [&](int i, int j, double v) { A[i + j * LDS] += v; }, lane);
+                czero<NP>(c);
+                wmm<NP>(c, TG1, sS1, lane);
+                wmm<NP>(c, sB, GT0, lane);
+                __syncwarp();
+                wepi<NP>(c, [&](int i, int j, double v) { B[i + j * LDS] = v; }, lane);
+                __syncwarp();
         }
+            }
         // apply_D_IE_RRS! / apply_D_SFI_IE_RRS! (doubling_inelastic.jl:335-358, 396-408)
         if (nd >= 1) {
             for (int e = lane; e < NP * NP; e += 32) { const int i = e % NP, j = e / NP; A[i + j * LDS] *= sg[i]; }
@@ -664,16 +872,20 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_inel(Args a, int m, int iz, in
     }
     // ---- interaction_helper!(::RRS, ::ScatteringInterface_11) inelastic lines (interaction_inelastic.jl:376-420, 446-487)
     const double* Cin = a.cI_in + u * G::CI;
-    const GMr<NP> ieRmp{Cin}, ieRpm{Cin + MG}, ieTpp{Cin + 2 * MG}, ieTmm{Cin + 3 * MG};
+    const GB<NP> ieRmp{Cin}, ieTpp{Cin + 2 * MG}, ieTmm{Cin + 3 * MG};
     const double* cJp = Cin + 4 * MG; const double* cJm = cJp + NP;
     const double* I0 = a.irec0 + (size_t)p0 * G::IREC0;
     const double* I1 = a.irec1 + (size_t)p1 * G::IREC1;
-    const GMr<NP> Rpm0{I0}, Tpp0{I0 + MG}, r0{I0 + 2 * MG}, tmm0{I0 + 3 * MG}, E1{I0 + 4 * MG}, E2{I0 + 5 * MG},
+    const GB<NP> Rpm0{I0}, Tpp0{I0 + MG}, r0{I0 + 2 * MG}, tmm0{I0 + 3 * MG}, E1{I0 + 4 * MG}, E2{I0 + 5 * MG},
         E3{I0 + 6 * MG}, E4{I0 + 7 * MG};
-    const GMr<NP> T01{I1}, T21{I1 + MG}, r1{I1 + 2 * MG}, Rpm1{I1 + 3 * MG};
+    const GA<NP> T01{I1}, T21{I1 + MG}, r1{I1 + 2 * MG}, Rpm1{I1 + 3 * MG};
     const double* IV = I0 + 8 * MG;
     const GV v1{IV}, v2{IV + NP}, J0p0{IV + 2 * NP}, aj0m0{IV + 3 * NP};
     const Conj<SM<NP>> sBc{sB, sg};                    // iet-- = D iet++ D
+    // the unit's composite ieR+- is used on both sides of products: staged once (coalesced) into S2
+    for (int e = lane; e < NP * NP; e += 32) S2[(e % NP) + (e / NP) * LDS] = __ldg(Cin + MG + e);
+    const SM<NP> ieRpm{S2};
+    __syncwarp();
     // Q1 = ier R+-0 + r1 ieR+- ;  P = T01 Q1 + ieT--
     czero<NP>(c);
     wmm<NP>(c, sA, Rpm0, lane);
@@ -779,7 +991,7 @@ __global__ void k_rrs_reduce(Args a, double* __restrict__ ieR, double* __restric
 template <int NP, int WPC>
 constexpr size_t elastic_smem() { return (size_t)WPC * (5 * Geo<NP>::MS + 12 * NP) * sizeof(double) + 64; }
 template <int NP, int WPC>
-constexpr size_t inel_smem() { return (size_t)WPC * (5 * Geo<NP>::MS + 10 * NP) * sizeof(double) + 64; }
+constexpr size_t inel_smem() { return (size_t)WPC * (5 * Geo<NP>::MS + 7 * NP) * sizeof(double) + 64; }
 
 }  // namespace rrs
 }  // namespace vsm

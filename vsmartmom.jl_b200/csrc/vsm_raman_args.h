@@ -10,15 +10,15 @@ namespace rrs {
 template <int NP>
 struct Geo {
     static constexpr int NT = NP / 8;          // 8x8 accumulator tiles per side
-    static constexpr int LDS = NP + 4;         // shared leading dimension (== 4 mod 16 for NP = 16, 48)
+    static constexpr int LDS = NP + 1;         // shared leading dimension (== 1 mod 16 for NP = 16, 48)
     static constexpr int MS = LDS * NP;        // doubles per shared matrix
     static constexpr int MG = NP * NP;         // doubles per global (record) matrix, ld = NP
     static constexpr int VB = NP / 16;         // 16-row blocks of a warp mat-vec
     // record sizes (doubles)
     static constexpr int REC0 = 5 * MG + 5 * NP;   // level, donor side:  r t GT GR GRT | tmp1 tmp2 J0p J1m expk
-    static constexpr int REC1 = 2 * MG;            // level, own side:    r TG
+    static constexpr int REC1 = 2 * MG;            // level, own side:    r' TG'  (stored transposed: A-side operands)
     static constexpr int IREC0 = 8 * MG + 4 * NP;  // interaction, donor: Rpm Tpp r tmm E1 E2 E3 E4 | v1 v2 J0p j0m
-    static constexpr int IREC1 = 4 * MG;           // interaction, own:   T01 T21 r Rpm
+    static constexpr int IREC1 = 4 * MG;           // interaction, own:   T01' T21' r' Rpm'  (transposed)
     static constexpr int CE = 4 * MG + 2 * NP;     // elastic composite:  Rmp Rpm Tpp Tmm | J0p J0m
     static constexpr int CI = 4 * MG + 2 * NP;     // unit composite:     ieRmp ieRpm ieTpp ieTmm | ieJ0p ieJ0m
 };
