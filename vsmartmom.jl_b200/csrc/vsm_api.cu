@@ -41,6 +41,7 @@ struct vsm_ctx {
     std::string err;
     // grow-only scratch
     DevBuf consts, props, added, slabs, partial, counter, l0tmp, geom, surfpad, linprops, rrs;
+    int use_small = 1;                      // warp-per-point column kernel for N <= 16 in fp64 (VSM_DISABLE_SMALL=1 turns it off)
     int rrs_order = 1;                      // unit enumeration of the Raman kernels (VSM_RRS_ORDER): 0 dn-major, 1 donor-major
     int use_stream = 1;                     // streamed-operand kernels for N = 60 / 75 / 100 (VSM_DISABLE_STREAM=1 turns them off)
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -144,6 +145,7 @@ extern "C" int vsm_create(vsm_ctx** out, int device, void* cuda_stream) {
     ctx->ws_limit = 0;
     if (const char* e = getenv("VSM_DEBUG_LAYER_CTAS_PER_SM")) ctx->dbg_layer_ctas = atoi(e);
     if (const char* e = getenv("VSM_DISABLE_STREAM")) ctx->use_stream = atoi(e) ? 0 : 1;
+    if (const char* e = getenv("VSM_DISABLE_SMALL")) ctx->use_small = atoi(e) ? 0 : 1;
     if (const char* e = getenv("VSM_RRS_ORDER")) ctx->rrs_order = atoi(e) ? 1 : 0;
     *out = ctx;
     return VSM_OK;
@@ -548,6 +550,10 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
         a_slab = (size_t)kStreamAddMats * sd->MSZ * sizeof(T);
         mstride = (size_t)sd->MSZ;
     }
+    // small matrices (N <= 16, fp64): one warp per (point, moment) runs the whole column on-chip (vsm_small.cuh); the
+    // per-source thermal slot and the streams export stay on the CTA-per-item kernels
+    const bool small_path = std::is_same<T, double>::value && ctx->use_small && N <= 16 && !therm_B && !st_Rmp && !st_Tpp &&
+                            !st_Jm && !st_Jp;
     bool fast = !sd && has_fast(N) && l_mats == kLayerMats;
     FastCfg fc{cfg.threads, cfg.threads, 0};
     if (fast) fc = fast_cfg<T, 45>();
@@ -571,7 +577,7 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
     if (ctx->dbg_layer_ctas > 0) l_grid_max = ctx->num_sms * std::max(1, std::min(l_occ, ctx->dbg_layer_ctas));
 
     // ---- workspace plan: chunk over spectral points and moments
-    const size_t add_item = (size_t)nSl * ((size_t)2 * mstride + 2 * N) * sizeof(T);
+    const size_t add_item = small_path ? 16 : (size_t)nSl * ((size_t)2 * mstride + 2 * N) * sizeof(T);   // no hand-off on the small path
     const size_t props_pt = ((size_t)Nz * (2 + nC) + (Nz + 1)) * sizeof(T);
     const size_t part_pt = (size_t)3 * nM * nOut * sizeof(T);
     uint64_t limit = ctx->ws_limit ? ctx->ws_limit : (uint64_t)24 << 30;
@@ -682,6 +688,20 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
             T* ad = (T*)ctx->added.p;
             const size_t slots = (size_t)mb * nSl * nS;
             a.add_r = ad; a.add_t = ad + slots * mstride; a.add_jp = ad + 2 * slots * mstride; a.add_jm = a.add_jp + slots * N;
+            if (small_path) {
+                if constexpr (std::is_same<T, double>::value) {
+                    const unsigned total = (unsigned)((size_t)mb * nS);
+                    CK(set_smem(ctx, small::small_kernel(), small::small_smem_bytes()));
+                    GET_EVENT(e0);
+                    GET_EVENT(e1);
+                    CK(cudaEventRecord(e0, ctx->stream));
+                    CK(small::launch_small(ctx->stream, a, total));
+                    ctx->launches++;
+                    CK(cudaEventRecord(e1, ctx->stream));
+                    ctx->seg_add.push_back({e0, e1});
+                }
+                continue;
+            }
             // --- k_layer
             if (nSched > 0) {
                 const unsigned total = (unsigned)((size_t)nSched * mb * nS);
@@ -1131,6 +1151,7 @@ static int rt_column_rrs_impl(vsm_ctx* ctx, const vsm_column_desc* d, const vsm_
     a.nBand = nBand; a.e0 = e0; a.nE = nE; a.n1lo = n1lo; a.n1cnt = n1cnt; a.nRaman = nR;
     a.istart = (d->imu0 - 1) * nSt;
     a.order = ctx->rrs_order;
+    a.neumann = ctx->inverse_mode;
     a.u_lo = e0; a.u_n0cnt = nE;
     a.mu0 = d->mu0;
     a.mu = cT + o_mu; a.wt = cT + o_wt; a.sgn = cT + o_sg;

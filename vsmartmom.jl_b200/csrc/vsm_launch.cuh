@@ -59,6 +59,13 @@ inline const LinDesc* lin_desc_stream(int N) {
     return N == 60 ? lin_desc_60() : N == 75 ? lin_desc_75() : N == 100 ? lin_desc_100() : nullptr;
 }
 
+// small-matrix column kernel (vsm_small.cuh): fp64, N <= 16, one warp per (point, moment), no hand-off
+namespace small {
+size_t small_smem_bytes();
+const void* small_kernel();
+cudaError_t launch_small(cudaStream_t, const ColArgs<double>&, unsigned int total);
+}  // namespace small
+
 template <typename T, int TM, int NN, int NTHR, int TMI = TM, int KS = 1>
 struct OpsSel { using type = OpsFast<T, TM, NN, NTHR, 0, TMI, KS>; };
 template <typename T, int TM, int NTHR, int TMI, int KS>

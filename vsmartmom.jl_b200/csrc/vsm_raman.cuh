@@ -180,6 +180,22 @@ __device__ __forceinline__ void wmv(double (&y)[NP / 16], FA a, FX x, int lane) 
     }
 }
 
+// I + M (identity on the leading n x n block) as an operand
+template <class M> struct IPlus {
+    M m; int n;
+    __device__ __forceinline__ double operator()(int i, int j) const { return m(i, j) + ((i == j && i < n) ? 1.0 : 0.0); }
+    __device__ __forceinline__ void a4(int i, int k0, double (&v)[4]) const {
+        m.a4(i, k0, v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] += (k0 + q == i && i < n) ? 1.0 : 0.0;
+    }
+    __device__ __forceinline__ void b4(int k0, int j, double (&v)[4]) const {
+        m.b4(k0, j, v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] += (k0 + q == j && j < n) ? 1.0 : 0.0;
+    }
+};
+
 // ---- register-resident fragments of a 16 x 16 operand (NP = 16): 8 doubles per lane hold the whole matrix as the A side
 //      (af[r][s] = M(8r+g, 4tg+s)) or as the B side (bf[q][s] = M(4tg+s, 8q+g)), so an operand that enters several
 //      products of a doubling level crosses the L1 data pipe once
@@ -261,8 +277,70 @@ __device__ __forceinline__ void winv(double* M, int n, double* colk, int* piv, i
     }
 }
 
+// Gm = (I - P)^-1 where the accumulators c hold P.  Adaptive like the large kernels (vsm_device.cuh): with nu = ||P||_F,
+// if nu^K / (1 - nu) < 1e-20 the Neumann sum of order K in {2, 4, 8} -- I + P, (I+P)(I+P^2), (I+P)(I+P^2)(I+P^4) --
+// equals the inverse to fp64 rounding and runs on the tensor cores; otherwise (or with neumann == 0) Gauss-Jordan with
+// partial pivoting.  S and TG are scratch matrices.
+template <int NP>
+__device__ __forceinline__ void winv_one_minus(double (&c)[NP / 8][NP / 8][2], double* Gm, double* S, double* TG, int n,
+                                               int neumann, double* colk, int* piv, int lane) {
+    constexpr int LDS = NP + 1;
+    double ss = 0.0;
+#pragma unroll
+    for (int r = 0; r < NP / 8; ++r)
+#pragma unroll
+        for (int q = 0; q < NP / 8; ++q) ss += c[r][q][0] * c[r][q][0] + c[r][q][1] * c[r][q][1];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const double nu = sqrt(ss);
+    int K = 0;
+    if (neumann && nu < 0.25) {
+        const double lim = 1e-20 * (1.0 - nu);
+        const double n2 = nu * nu, n4 = n2 * n2;
+        K = (n2 < lim) ? 2 : ((n4 < lim) ? 4 : ((n4 * n4 < lim) ? 8 : 0));
+    }
+    auto idn = [&](int i, int j) { return (i == j && i < n) ? 1.0 : 0.0; };
+    if (K == 2) {
+        wepi<NP>(c, [&](int i, int j, double v) { Gm[i + j * LDS] = idn(i, j) + v; }, lane);
+        __syncwarp();
+        return;
+    }
+    if (K == 0) {
+        wepi<NP>(c, [&](int i, int j, double v) { Gm[i + j * LDS] = idn(i, j) - v; }, lane);
+        winv<NP>(Gm, n, colk, piv, lane);
+        return;
+    }
+    const SM<NP> sS{S}, sT{TG}, sG{Gm};
+    wepi<NP>(c, [&](int i, int j, double v) { S[i + j * LDS] = v; }, lane);          // S = P
+    __syncwarp();
+    czero<NP>(c);
+    wmm<NP>(c, sS, sS, lane);
+    wepi<NP>(c, [&](int i, int j, double v) { TG[i + j * LDS] = v; }, lane);         // TG = P^2
+    __syncwarp();
+    if (K == 4) {
+        czero<NP>(c);
+        wmm<NP>(c, IPlus<SM<NP>>{sS, n}, IPlus<SM<NP>>{sT, n}, lane);
+        wepi<NP>(c, [&](int i, int j, double v) { Gm[i + j * LDS] = v; }, lane);
+        __syncwarp();
+        return;
+    }
+    czero<NP>(c);
+    wmm<NP>(c, sT, sT, lane);
+    wepi<NP>(c, [&](int i, int j, double v) { Gm[i + j * LDS] = v; }, lane);         // Gm = P^4
+    czero<NP>(c);
+    wmm<NP>(c, IPlus<SM<NP>>{sS, n}, IPlus<SM<NP>>{sT, n}, lane);
+    __syncwarp();
+    wepi<NP>(c, [&](int i, int j, double v) { S[i + j * LDS] = v; }, lane);          // S = (I+P)(I+P^2)
+    __syncwarp();
+    czero<NP>(c);
+    wmm<NP>(c, sS, IPlus<SM<NP>>{sG, n}, lane);
+    __syncwarp();
+    wepi<NP>(c, [&](int i, int j, double v) { Gm[i + j * LDS] = v; }, lane);
+    __syncwarp();
+}
+
 // fScattRayleigh = rayl.τ ./ combo.τ before the absorption is added (compEffectiveLayerProperties.jl:56)
-__global__ void k_rrs_fscatt(int nE, int Nz, int nAer, size_t ldspec, const double* __restrict__ tau_rayl,
+static __global__ void k_rrs_fscatt(int nE, int Nz, int nAer, size_t ldspec, const double* __restrict__ tau_rayl,
                              const double* __restrict__ aer_tau_mod, double* __restrict__ fsc) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= nE) return;
@@ -382,8 +460,7 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_elastic(Args a, int m, int iz,
             }
             czero<NP>(c);
             wmm<NP>(c, sr, sr, lane);
-            wepi<NP>(c, [&](int i, int j, double v) { Gm[i + j * LDS] = ((i == j && i < n) ? 1.0 : 0.0) - v; }, lane);
-            winv<NP>(Gm, n, colk, piv, lane);
+            winv_one_minus<NP>(c, Gm, S, TG, n, a.neumann, colk, piv, lane);
             czero<NP>(c);                                               // tt⁺⁺_gp_refl = t gp
             wmm<NP>(c, st, sG, lane);
             wepi<NP>(c, [&](int i, int j, double v) { TG[i + j * LDS] = v; R1[MG + j + i * NP] = v; }, lane);
@@ -493,8 +570,7 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_elastic(Args a, int m, int iz,
     // inv1 = (I - r-+ R+-)^-1
     czero<NP>(c);
     wmm<NP>(c, sr, Rpm, lane);
-    wepi<NP>(c, [&](int i, int j, double v) { Gm[i + j * LDS] = ((i == j && i < n) ? 1.0 : 0.0) - v; }, lane);
-    winv<NP>(Gm, n, colk, piv, lane);
+    winv_one_minus<NP>(c, Gm, S, TG, n, a.neumann, colk, piv, lane);
     czero<NP>(c);                                                   // T01_inv = T-- inv1
     wmm<NP>(c, Tmm, sG, lane);
     wepi<NP>(c, [&](int i, int j, double v) { TG[i + j * LDS] = v; I1[j + i * NP] = v; }, lane);
@@ -530,8 +606,7 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_elastic(Args a, int m, int iz,
     czero<NP>(c);
     wmm<NP>(c, Rpm, sr, lane);
     __syncwarp();
-    wepi<NP>(c, [&](int i, int j, double v) { Gm[i + j * LDS] = ((i == j && i < n) ? 1.0 : 0.0) - v; }, lane);
-    winv<NP>(Gm, n, colk, piv, lane);
+    winv_one_minus<NP>(c, Gm, S, TG, n, a.neumann, colk, piv, lane);
     czero<NP>(c);                                                   // T21_inv = t++ inv2
     wmm<NP>(c, st, sG, lane);
     wepi<NP>(c, [&](int i, int j, double v) { TG[i + j * LDS] = v; I1[MG + j + i * NP] = v; }, lane);
@@ -970,7 +1045,7 @@ __global__ void __launch_bounds__(32 * WPC, (NP <= 16) ? 4 : 1) k_rrs_inel(Args 
 
 // ieR_SFI[i,:,s] += sum_t w ieJ0-[...,s,t] in the reference's order t = 1..nRaman (postprocessing_vza.jl:143-146);
 // units whose donor wavelength is outside the band hold zeros in the reference and are skipped here
-__global__ void k_rrs_reduce(Args a, double* __restrict__ ieR, double* __restrict__ ieT, int* __restrict__ nonfinite) {
+static __global__ void k_rrs_reduce(Args a, double* __restrict__ ieR, double* __restrict__ ieT, int* __restrict__ nonfinite) {
     const int nOut = a.nVZA * a.nStokes;
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (size_t)a.n1cnt * nOut) return;

@@ -30,6 +30,7 @@ struct Args {
     int n1lo, n1cnt;         // inelastic owner range (band indices)
     int nRaman;
     int istart;              // 0-based first row of the solar stream
+    int neumann;             // 1: adaptive Neumann / Gauss-Jordan inverse in the elastic column, 0: elimination only
     int order;               // unit enumeration: 0 = dn-major (n1 fastest), 1 = donor-major (dn fastest)
     int u_lo, u_n0cnt;       // donor-major enumeration: n0 in [u_lo, u_lo + u_n0cnt)
     double mu0;
