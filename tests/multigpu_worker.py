@@ -17,15 +17,28 @@ local = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 nspec = int(sys.argv[1])
-m = vb.synthetic_o2a_model(nSpec=nspec, nstreams=4, aerosol=True)
+mode = sys.argv[2] if len(sys.argv) > 2 else "elastic"
 ctx = _lib.Context(local)
-out = rr.rt_run_sharded(m, ctx, device=f"cuda:{local}")
 ok = True
-if dist.get_rank() == 0:
-    ref = rr.rt_run(m, ctx, device=f"cuda:{local}")
-    for k in ("R_SFI", "T_SFI", "hdr", "bhr_uw", "bhr_dw"):
-        ok = ok and np.array_equal(out[k], ref[k])
-    print("MULTIGPU_OK" if ok else "MULTIGPU_MISMATCH", flush=True)
+if mode == "rrs":
+    # rotational Raman: owner-range shards with a locally recomputed elastic halo, one all-gather
+    from vsmom_b200 import raman
+    m = raman.synthetic_rrs_model(nSpec=nspec)
+    rs = raman.synthetic_rrs(grid_step=2.0)
+    out = raman.rt_run_rrs_sharded(m, rs, ctx, device=f"cuda:{local}")
+    if dist.get_rank() == 0:
+        ref = raman.rt_run_rrs(m, rs, ctx, device=f"cuda:{local}")
+        for k in ("R_SFI", "T_SFI", "ieR_SFI", "ieT_SFI"):
+            ok = ok and np.array_equal(out[k], ref[k])
+        print("MULTIGPU_OK" if ok else "MULTIGPU_MISMATCH", flush=True)
+else:
+    m = vb.synthetic_o2a_model(nSpec=nspec, nstreams=4, aerosol=True)
+    out = rr.rt_run_sharded(m, ctx, device=f"cuda:{local}")
+    if dist.get_rank() == 0:
+        ref = rr.rt_run(m, ctx, device=f"cuda:{local}")
+        for k in ("R_SFI", "T_SFI", "hdr", "bhr_uw", "bhr_dw"):
+            ok = ok and np.array_equal(out[k], ref[k])
+        print("MULTIGPU_OK" if ok else "MULTIGPU_MISMATCH", flush=True)
 ctx.close()
 dist.barrier()
 dist.destroy_process_group()

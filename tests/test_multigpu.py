@@ -24,3 +24,14 @@ def test_sharded_equals_single_gpu(nspec):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MULTIGPU_OK" in r.stdout
+
+
+def test_raman_owner_shards_equal_single_gpu():
+    """rt_run_rrs_sharded (owner ranges + locally recomputed elastic halo + one all-gather) == single-GPU rt_run_rrs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29543", os.path.join(ROOT, "tests", "multigpu_worker.py"), "300", "rrs"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MULTIGPU_OK" in r.stdout

@@ -992,8 +992,10 @@ static int rt_column_rrs_impl(vsm_ctx* ctx, const vsm_column_desc* d, const vsm_
                               double* ieR_SFI, double* ieT_SFI) {
     using T = double;
     if (!ctx) return VSM_ERR_INVALID_ARG;
-    if (!d || d->struct_size != (int)sizeof(vsm_column_desc))
+    // the column descriptor with or without the trailing extra-source fields (which this driver does not take)
+    if (!d || (d->struct_size != (int)sizeof(vsm_column_desc) && d->struct_size != (int)offsetof(vsm_column_desc, thermal_B)))
         return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_rrs: column descriptor NULL or struct_size mismatch");
+    const bool full_desc = d->struct_size == (int)sizeof(vsm_column_desc);
     if (!rd || rd->struct_size != (int)sizeof(vsm_rrs_desc))
         return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_rrs: rrs descriptor NULL or struct_size mismatch");
     if (!R_SFI || !T_SFI || !ieR_SFI || !ieT_SFI) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_rrs: output NULL");
@@ -1007,7 +1009,7 @@ static int rt_column_rrs_impl(vsm_ctx* ctx, const vsm_column_desc* d, const vsm_
         !d->tau_rayl || !d->tau_abs || !d->F0 || !d->Zpp || !d->Zmp || (nAer > 0 && (!d->aer_omega || !d->aer_ft || !d->tau_aer)) ||
         !rd->i_shift || !rd->varpi_raman || !rd->Zpp_raman || !rd->Zmp_raman)
         return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_rrs: NULL input array");
-    if (d->thermal_B || d->sif0 || d->ss_correction)
+    if ((full_desc && (d->thermal_B || d->sif0)) || d->ss_correction)
         return fail(ctx, VSM_ERR_UNSUPPORTED, "rt_column_rrs: extra sources / TMS correction are not part of the RRS driver");
     if (d->surface_kind != VSM_SURFACE_LAMBERTIAN_SCALAR && d->surface_kind != VSM_SURFACE_BRDF_FOURIER)
         return fail(ctx, VSM_ERR_UNSUPPORTED, "rt_column_rrs: surface_kind must be LAMBERTIAN_SCALAR or BRDF_FOURIER");
@@ -1264,8 +1266,12 @@ static int rt_layer_impl(vsm_ctx* ctx, const vsm_layer_desc* d) {
     const size_t l_smem = lv + (size_t)l_mats * msz, a_smem = av + (size_t)a_mats * msz;
     const size_t l_slab = (size_t)(kLayerMats - l_mats) * msz, a_slab = (size_t)(kAddMats - a_mats) * msz;
     const void* kl = nullptr; const void* ka = nullptr; const void* ks = nullptr;
-    get_kernel_ptrs<T>(cfg.tm, false, N, &kl, &ka);
-    switch (cfg.tm) {
+    // N = 45: the specialised tensor-core kernels of the column path (everything in shared memory)
+    const bool fast = has_fast(N) && l_mats == kLayerMats && a_mats == kAddMats;
+    const int l_threads = fast ? fast_cfg<T, 45>().layer_threads : cfg.threads;
+    get_kernel_ptrs<T>(cfg.tm, fast, N, &kl, &ka);
+    if (fast) ks = step_fast_kernel_ptr<T, 45>();
+    else switch (cfg.tm) {
         case 1: ks = step_kernel_ptr<T, 1>(); break;
         case 2: ks = step_kernel_ptr<T, 2>(); break;
         case 3: ks = step_kernel_ptr<T, 3>(); break;
@@ -1273,8 +1279,8 @@ static int rt_layer_impl(vsm_ctx* ctx, const vsm_layer_desc* d) {
     }
     CK(set_smem(ctx, (const void*)kl, l_smem));
     CK(set_smem(ctx, (const void*)ks, a_smem));
-    const int l_grid_max = ctx->num_sms * occupancy<T>(kl, cfg.threads, l_smem);
-    const int s_grid_max = ctx->num_sms * occupancy<T>(ks, cfg.threads, a_smem);
+    const int l_grid_max = ctx->num_sms * occupancy<T>(kl, l_threads, l_smem);
+    const int s_grid_max = ctx->num_sms * occupancy<T>(ks, l_threads, a_smem);
     const size_t NN2 = (size_t)N * N;
     // AddedLayer storage: the caller's arrays when given, library scratch otherwise
     const bool own_added = !(d->rmp && d->tpp && d->j0p && d->j0m);
@@ -1318,13 +1324,13 @@ static int rt_layer_impl(vsm_ctx* ctx, const vsm_layer_desc* d) {
         a.counter = (unsigned int*)ctx->counter.p;
         CK(cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
         const int grid = (int)std::min<size_t>((size_t)nSpec, (size_t)l_grid_max);
-        if ((rc = do_launch<T>(ctx, true, cfg.tm, false, N, a, (unsigned)nSpec, grid, cfg.threads, l_smem))) return rc;
+        if ((rc = do_launch<T>(ctx, true, cfg.tm, fast, N, a, (unsigned)nSpec, grid, l_threads, l_smem))) return rc;
     }
     {
         StepArgs<T> s;
         memset(&s, 0, sizeof s);
         s.N = N; s.nStokes = nSt; s.nS = nSpec; s.ld = ld; s.n_smem_mats = a_mats;
-        s.iface = d->iface; s.first = (d->iz == 1) ? 1 : 0; s.scatter = d->scatter ? 1 : 0;
+        s.iface = d->iface; s.first = (d->iz == 1) ? 1 : 0; s.scatter = d->scatter ? 1 : 0; s.neumann = ctx->inverse_mode;
         s.tau = (const T*)d->tau; s.mu = (const T*)d->mu;
         s.add_r = add_r; s.add_t = add_t; s.add_jp = add_jp; s.add_jm = add_jm;
         s.Rmp = (T*)d->Rmp; s.Rpm = (T*)d->Rpm; s.Tpp = (T*)d->Tpp; s.Tmm = (T*)d->Tmm;
@@ -1336,7 +1342,8 @@ static int rt_layer_impl(vsm_ctx* ctx, const vsm_layer_desc* d) {
         CK(cudaMemsetAsync(ctx->counter.p, 0, 4, ctx->stream));
         const int grid = (int)std::min<size_t>((size_t)nSpec, (size_t)s_grid_max);
         cudaError_t e;
-        switch (cfg.tm) {
+        if (fast) e = launch_step_fast<T, 45>(ctx->stream, s, (unsigned)nSpec, grid, a_smem);
+        else switch (cfg.tm) {
             case 1: e = launch_step<T, 1>(ctx->stream, s, (unsigned)nSpec, grid, cfg.threads, a_smem); break;
             case 2: e = launch_step<T, 2>(ctx->stream, s, (unsigned)nSpec, grid, cfg.threads, a_smem); break;
             case 3: e = launch_step<T, 3>(ctx->stream, s, (unsigned)nSpec, grid, cfg.threads, a_smem); break;

@@ -1190,6 +1190,7 @@ template <typename T>
 struct StepArgs {
     int N, nStokes, nS, ld, n_smem_mats;
     int iface, first, scatter;          // first: iz == 1 -> copy
+    int neumann;                        // inverse mode of the specialised Ops (vsm_set_inverse_mode)
     const T* tau; const T* mu;          // non-scattering layer: t = diag(exp(-tau/mu))
     const T* add_r; const T* add_t; const T* add_jp; const T* add_jm;   // (N,N,nS)/(N,nS)
     T* Rmp; T* Rpm; T* Tpp; T* Tmm; T* J0p; T* J0m;                     // composite, in/out
@@ -1199,12 +1200,13 @@ struct StepArgs {
     unsigned int* counter;
 };
 
-template <typename T, class Ops>
+// NN > 0: compile-time N with the specialised (tensor-core) Ops of the column kernels, all nine matrices in shared memory
+template <typename T, class Ops, int NN = 0>
 __global__ void __launch_bounds__(256) k_interact_step(StepArgs<T> a, unsigned int total) {
-    const int n = a.N, ld = a.ld;
+    const int n = NN ? NN : a.N, ld = NN ? (NN | 1) : a.ld;
     const int msz = ld * n;
     T* sm = reinterpret_cast<T*>(vsm_smem);
-    const int nsm = a.n_smem_mats;
+    const int nsm = NN ? kAddMats : a.n_smem_mats;
     T* slab = a.slab + (size_t)blockIdx.x * a.slab_stride;
     auto mat = [&](int k) -> T* { return k < nsm ? sm + k * msz : slab + (size_t)(k - nsm) * msz; };
     T* vbase = sm + nsm * msz;
@@ -1215,7 +1217,9 @@ __global__ void __launch_bounds__(256) k_interact_step(StepArgs<T> a, unsigned i
     int* piv = reinterpret_cast<int*>(dmask + n);
     __shared__ unsigned int sh_item;
     Ops op;
-    op.n = n; op.ld = ld; op.vec = vec; op.part = part; op.piv = piv; op.dmask = dmask; op.tid = threadIdx.x; op.bar = 0;
+    if constexpr (NN == 0) { op.n = n; op.ld = ld; }
+    op.vec = vec; op.part = part; op.piv = piv; op.dmask = dmask; op.tid = threadIdx.x; op.bar = 0;
+    op.neumann = a.neumann;
     const size_t NN2 = (size_t)n * n;
     for (int i = threadIdx.x; i < n; i += blockDim.x) dmask[i] = dmask_of(i, a.nStokes);
     for (;;) {

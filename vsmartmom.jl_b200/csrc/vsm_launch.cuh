@@ -16,6 +16,11 @@ template <typename T, int TM>
 cudaError_t launch_step(cudaStream_t s, const StepArgs<T>& a, unsigned total, int grid, int threads, size_t smem);
 template <typename T, int TM>
 const void* step_kernel_ptr();
+// the same step on the specialised Ops of the compile-time-N column kernels (L1 on the tensor-core path)
+template <typename T, int NN>
+cudaError_t launch_step_fast(cudaStream_t s, const StepArgs<T>& a, unsigned total, int grid, size_t smem);
+template <typename T, int NN>
+const void* step_fast_kernel_ptr();
 // launch geometry chosen at compile time by the specialised instantiation
 struct FastCfg {
     int layer_threads, adding_threads;

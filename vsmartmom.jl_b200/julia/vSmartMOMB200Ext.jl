@@ -25,6 +25,7 @@ using vSmartMOM
 using vSmartMOM.Architectures
 using vSmartMOM.CoreRT
 using vSmartMOM.Scattering
+using vSmartMOM.InelasticScattering
 import CUDA.CUDAKernels
 
 const LIB = get(ENV, "VSMOM_B200_LIB", "libvsmom_b200")
@@ -301,6 +302,90 @@ function CoreRT.rt_run(RS_type::CoreRT.noRS{FT}, model::CoreRT.RTModel{<:Archite
     R_SFI, T_SFI, hdr = Array(R_d), Array(T_d), Array(H_d)     # ONE D2H per output instead of one per Fourier moment
     z = zeros(FT, nV, n, nSpec)
     return R_SFI, T_SFI, z, copy(z), hdr, Array(uw_d)[1, :], Array(dw_d)[1, :]     # (R_SFI,T_SFI,ieR_SFI,ieT_SFI,hdr,bhr_uw,bhr_dw), rt_run.jl:535
+end
+
+# ---- L2, rotational Raman: rt_run(RS_type::RRS, model, iBand) (rt_run.jl:238-539, rt_kernel!(::RRS) rt_kernel.jl:352-391)
+mutable struct RrsDesc                                        # == struct vsm_rrs_desc
+    struct_size::Int32; n_raman::Int32; n1_begin::Int32; n1_count::Int32
+    i_shift::Ptr{Int32}; varpi_raman::Ptr{Float64}; Zpp_raman::CuPtr{Cvoid}; Zmp_raman::CuPtr{Cvoid}
+end
+
+function CoreRT.rt_run(RS_type::InelasticScattering.RRS{Float64}, model::CoreRT.RTModel{<:Architectures.GPU,Float64}, iBand;
+                       sources=nothing, streams_callback=nothing)
+    FT = Float64
+    brdf0 = CoreRT.get_surface(model, iBand[1])
+    if CTX[] == C_NULL || !_native(RS_type, model, iBand, sources) || streams_callback !== nothing || brdf0 isa CoreRT.CoxMunkSurface
+        return invoke(CoreRT.rt_run, Tuple{CoreRT.AbstractRamanType,Any,Any}, RS_type, model, iBand;
+                      sources=sources, streams_callback=streams_callback)
+    end
+    iB = iBand[1]
+    InelasticScattering.normalize_raman_weights!(RS_type, model, iBand)          # rt_run.jl:275
+    (; vza, vaz) = model.obs_geom
+    qp = model.quad_points
+    (; qp_μ, qp_μN, wt_μN, μ₀, iμ₀) = qp
+    pol = CoreRT.polarization_type(model)
+    n, N, nV = pol.n, length(qp_μN), length(vza)
+    m_max = CoreRT.m_max_bands(model)[iB]
+    nM = m_max + 1
+    τ_rayl, τ_abs, τ_aer = model.τ_rayl[iB], model.τ_abs[iB], model.τ_aer[iB]
+    nSpec, Nz, nAer = size(τ_abs, 1), size(τ_abs, 2), size(τ_aer, 1)
+    μ = collect(qp_μ)
+    # elastic Z tables with the CABANNES Greek set (compEffectiveLayerProperties.jl:36-41) and the Raman Z moments
+    # (computeRamanZλ!, inelastic_helper.jl:917-924), all Fourier moments at once
+    Zpp = Array{FT}(undef, N, N, 1 + nAer, nM); Zmp = similar(Zpp)
+    ZppR = Array{FT}(undef, N, N, nM); ZmpR = similar(ZppR)
+    grs = CoreRT._rayleigh_greek_source(RS_type, model.greek_rayleigh, model.greek_cabannes)
+    gr = grs isa AbstractVector ? grs[iB] : grs
+    for m in 0:m_max
+        Zpp[:, :, 1, m+1], Zmp[:, :, 1, m+1] = Array.(Scattering.compute_Z_moments(pol, μ, gr, m))
+        for a in 1:nAer
+            Zpp[:, :, 1+a, m+1], Zmp[:, :, 1+a, m+1] =
+                Array.(Scattering.compute_Z_moments(pol, μ, model.aerosol_optics[iB][a].greek_coefs, m))
+        end
+        ZppR[:, :, m+1], ZmpR[:, :, m+1] = Array.(Scattering.compute_Z_moments(pol, μ, RS_type.greek_raman, m))
+    end
+    props, _ = CoreRT.constructCoreOpticalProperties(RS_type, iBand, 0, model)
+    ifaces, _ = CoreRT.extractEffectiveProps(props, qp)
+    scatter = Int32[maximum(p.τ .* p.ϖ) > 2eps(FT) for p in props]
+    all(scatter .== 1) || error("vSmartMOMB200Ext: RRS needs every layer to scatter (rt_kernel.jl:366)")
+    ndoubl = Int32[CoreRT.get_dtau_ndoubl(props[i], qp; dτ_max_threshold=model.numerics.dτ_max_threshold,
+                                          dτ_min_floor=model.numerics.dτ_min_floor)[2] for i in 1:Nz]
+    iface = Int32[iface_tag(x) for x in ifaces]
+    rz = Int32[all(τ_rayl[:, i] .* RS_type.ϖ_Cabannes[iB] .== 0) for i in 1:Nz]
+    vstream = Int32[CoreRT.nearest_point(qp_μ, cosd(v)) for v in vza]
+    vw = Array{Float64}(undef, n, nV, nM)
+    for m in 0:m_max, i in 1:nV
+        w = m == 0 ? 0.5 / π : 1.0 / π
+        c, s = cosd(m * vaz[i]), sind(m * vaz[i])
+        vw[:, i, m+1] .= w .* (c, c, s, s)[1:n]
+    end
+    lamb = brdf0 isa CoreRT.LambertianSurfaceScalar
+    ρ = lamb ? nothing : CuArray{FT}(cat([(m == 0 ? 2 : 1) .* CoreRT.reflectance(brdf0, pol, μ, m) for m in 0:m_max]...; dims=3))
+    ω = Float64[model.aerosol_optics[iB][a].ω̃ for a in 1:nAer]; isempty(ω) && push!(ω, 0.0)
+    ft = Float64[model.aerosol_optics[iB][a].fᵗ for a in 1:nAer]; isempty(ft) && push!(ft, 0.0)
+    τa = nAer > 0 ? Array{Float64}(τ_aer) : zeros(1, 1)
+    μh, wh = Array{Float64}(qp_μN), Array{Float64}(wt_μN)
+    F0 = size(RS_type.F₀) == (n, nSpec) ? RS_type.F₀ : (f = zeros(FT, n, nSpec); f[1, :] .= 1; f)
+    shift = Int32.(RS_type.i_λ₁λ₀); wR = Float64.(RS_type.ϖ_λ₁λ₀)
+    d_τr, d_τa, d_F0, d_Zpp, d_Zmp = CuArray{FT}(τ_rayl), CuArray{FT}(τ_abs), CuArray{FT}(F0), CuArray(Zpp), CuArray(Zmp)
+    d_ZppR, d_ZmpR = CuArray(ZppR), CuArray(ZmpR)
+    R_d = CuArray{FT}(undef, nV, n, nSpec); T_d = similar(R_d); ieR_d = similar(R_d); ieT_d = similar(R_d)
+    GC.@preserve μh wh ω ft τa vw ndoubl scatter iface rz vstream ρ shift wR d_τr d_τa d_F0 d_Zpp d_Zmp d_ZppR d_ZmpR begin
+        d = ColumnDesc(sizeof(ColumnDesc), N, n, nSpec, Nz, nAer, nV, nM, iμ₀, lamb ? 0 : 1,
+            μ₀, lamb ? brdf0.albedo : 0.0, RS_type.ϖ_Cabannes[iB],
+            pointer(μh), pointer(wh), pointer(ω), pointer(ft), pointer(τa), pointer(vw),
+            pointer(ndoubl), pointer(scatter), pointer(iface), pointer(rz), pointer(vstream),
+            _p(d_τr), _p(d_τa), _p(d_F0), _p(d_Zpp), _p(d_Zmp), lamb ? CU_NULL : _p(ρ), Ptr{Float64}(C_NULL))
+        # one device owns the whole band: owner range = 1:nSpec (a multi-GPU driver passes one contiguous range per
+        # device; the library recomputes the elastic halo of the range locally, no communication)
+        rd = RrsDesc(sizeof(RrsDesc), length(shift), 0, nSpec, pointer(shift), pointer(wR), _p(d_ZppR), _p(d_ZmpR))
+        _check(ccall((:vsm_rt_column_rrs_f64, LIB), Cint,
+            (Ptr{Cvoid}, Ref{ColumnDesc}, Ref{RrsDesc}, CuPtr{FT}, CuPtr{FT}, CuPtr{FT}, CuPtr{FT}),
+            CTX[], d, rd, R_d, T_d, ieR_d, ieT_d))
+        Architectures.synchronize_if_gpu()
+    end
+    hdr = zeros(FT, nV, n, nSpec)                              # interaction_hdrf! outputs are not produced on this path
+    return Array(R_d), Array(T_d), Array(ieR_d), Array(ieT_d), hdr, zeros(FT, nSpec), zeros(FT, nSpec)   # rt_run.jl:532
 end
 
 # ---- LinMode: vsm_rt_column_lin_f64 takes the same ColumnDesc plus
