@@ -251,6 +251,15 @@ typedef struct vsm_rrs_desc {
 int vsm_rt_column_rrs_f64(vsm_ctx*, const vsm_column_desc*, const vsm_rrs_desc*, double* R_SFI, double* T_SFI,
                           double* ieR_SFI, double* ieT_SFI);
 
+/* -- L2, single scattering -- drop-in for the body of rt_run_ss(::noRS, model, iBand) src/CoreRT/rt_run.jl:593-755:
+ * rt_kernel_ss!(::noRS{FT}) (CoreKernel/rt_kernel_ss.jl:156-236: elemental! of the whole layer with ndoubl = 0, no
+ * doubling), interaction_ss! (CoreKernel/interaction_ss.jl:14-42), the surface sources, postprocessing_vza! and the
+ * m = 0 hemispheric sums.  Same column descriptor (ndoubl / scatter / iface are not read: the driver hard-codes
+ * scatter = true, rt_kernel_ss.jl:177); thermal_B / sif0 must be NULL.  Outputs: device, R_SFI/T_SFI
+ * (nVZA,nStokes,nSpec), hem_R/hem_T [nSpec] (may be NULL), overwritten. */
+int vsm_rt_column_ss_f64(vsm_ctx*, const vsm_column_desc*, double* R_SFI, double* T_SFI, double* hem_R, double* hem_T);
+int vsm_rt_column_ss_f32(vsm_ctx*, const vsm_column_desc*, float* R_SFI, float* T_SFI, float* hem_R, float* hem_T);
+
 /* -- several GPUs from ONE host process (the reference drives everything from a single Julia process and has no
  * multi-GPU path: Architectures.jl:42-45 "Run on a single NVIDIA CUDA GPU").  vsm_multi_create opens one context
  * (own stream) per listed device and an in-process NCCL communicator over them (ncclCommInitAll; NCCL is loaded

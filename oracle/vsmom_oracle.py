@@ -1556,3 +1556,61 @@ class ProcessPoolBaseline:
     def close(self):
         self.pool.close()
         self.pool.join()
+
+
+# --------------------------------------------------------------------------
+# Single-scattering driver: rt_run_ss(::noRS, model, iBand) rt_run.jl:593-755 with rt_kernel_ss!(::noRS{FT})
+# CoreKernel/rt_kernel_ss.jl:156-236 (elemental! of the WHOLE layer with ndoubl = 0, no doubling) and
+# interaction_ss! CoreKernel/interaction_ss.jl:14-42.  Pinned by the invariants of test/test_forward_ss.jl (finite,
+# positive, SS <= MS on Stokes I, hemispheric bounds) and by the thin-atmosphere limit R_ss -> R_ms
+# (tests/test_oracle_golden.py::test_single_scatter_*).
+# --------------------------------------------------------------------------
+def rt_run_ss(model: Model):
+    FT = model.FT
+    q = model.quad
+    pol_n = model.pol_n
+    nS = model.nSpec
+    nV = len(model.vza)
+    mu = q.qp_muN.astype(FT)
+    R_SFI = np.zeros((nV, pol_n, nS), FT)
+    T_SFI = np.zeros((nV, pol_n, nS), FT)
+    hem_R = np.zeros(nS, FT)
+    hem_T = np.zeros(nS, FT)
+    F0 = model.F0
+    if F0 is None:
+        F0 = np.zeros((pol_n, nS), FT)
+        F0[0, :] = 1
+    for m in range(model.m_max + 1):
+        weight = FT(0.5 / math.pi) if m == 0 else FT(1.0 / math.pi)
+        ctl = band_control(model, m)
+        props = construct_core_optical_properties(model, m)
+        J0p = J0m = None
+        for iz in range(model.Nz):
+            p = props[iz]
+            tau = np.broadcast_to(p.tau, (nS,)).astype(FT)
+            varpi = np.broadcast_to(p.varpi, (nS,)).astype(FT)
+            tsum = ctl.tau_sum[:, iz]
+            _, _, _, _, j0p, j0m = elemental(model, m, 0, tau, varpi, p.Zpp, p.Zmp, tsum, F0)   # ndoubl_ss = 0
+            if iz == 0:
+                J0p, J0m = j0p.copy(), j0m.copy()
+            else:                                                  # get_interaction_ss! (interaction_ss.jl:14-19)
+                J0p = J0p * np.exp(-tau[:, None] / mu[None, :]) + j0p
+                J0m = J0m + j0m * np.exp(-tsum[:, None] / mu[None, :])
+        s = brdf_surface(model, m, ctl.tau_sum[:, -1]) if model.surface_rho is not None \
+            else lambertian_surface(model, m, ctl.tau_sum[:, -1])
+        j0p_s, j0m_s = s[4], s[5]
+        J0p = J0p + j0p_s                                          # τ_surf = 0 (rt_run.jl:713-721)
+        J0m = J0m + j0m_s * np.exp(-ctl.tau_sum[:, -1][:, None] / mu[None, :])
+        for i in range(nV):
+            imu = nearest_point(q.qp_mu, FT(cosd(model.vza[i])))
+            ist = imu * pol_n
+            c = cosd(m * model.vaz[i])
+            sn = sind(m * model.vaz[i])
+            wv = (weight * np.array([c, c, sn, sn][:pol_n])).astype(FT)
+            R_SFI[i] += wv[:, None] * J0m[:, ist:ist + pol_n].T
+            T_SFI[i] += wv[:, None] * J0p[:, ist:ist + pol_n].T
+        if m == 0:                                                 # rt_run.jl:737-748
+            wq = (q.wt_mu * q.qp_mu).astype(FT)
+            hem_R += np.sum(J0m[:, 0::pol_n] * wq[None, :], axis=1)
+            hem_T += np.sum(J0p[:, 0::pol_n] * wq[None, :], axis=1)
+    return dict(R_SFI=R_SFI, T_SFI=T_SFI, hem_R=hem_R, hem_T=hem_T)

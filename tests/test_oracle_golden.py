@@ -5,6 +5,7 @@ import math
 import numpy as np
 import pytest
 
+import vsmom_b200 as vb
 import vsmom_oracle as orc
 from helpers import golden, rayleigh_slab_model, to_oracle
 
@@ -129,3 +130,36 @@ def test_vlidort_solar_tester_vector_problemIII_aerosol(iraz):
     m = solar_tester_vector_model(st, sv, sv["sza"][0], sv["raz"][iraz])
     up, dn = solar_tester_vector_errors(sv, orc.rt_run(to_oracle(m)), 0, iraz)
     assert up < sv["rtol_up"] and dn < sv["rtol_dn"], (up, dn)
+
+
+# ---- single-scattering driver (rt_run_ss): the reference's invariants (test/test_forward_ss.jl:47-76) + the thin limit
+def _ss_model(scale, pol="Stokes_IQU"):
+    m = vb.synthetic_o2a_model(nSpec=12, nstreams=4, polarization_type=pol, aerosol=True)
+    m.tau_rayl = m.tau_rayl * scale
+    m.tau_abs = np.minimum(m.tau_abs, 0.5) * scale
+    m.tau_aer = m.tau_aer * scale
+    m.albedo = 0.0
+    return to_oracle(m)
+
+
+def test_single_scatter_invariants():
+    om = _ss_model(1.0)
+    ss = orc.rt_run_ss(om)
+    ms = orc.rt_run(om)
+    for k in ss:
+        assert np.all(np.isfinite(ss[k]))
+    I_ss, I_ms = ss["R_SFI"][:, 0], ms["R_SFI"][:, 0]
+    assert np.all(I_ss > 0) and I_ss.max() < 1.0
+    assert np.all(np.abs(ss["R_SFI"][:, 1]) <= I_ss + 1e-10)
+    assert np.all(I_ss <= I_ms + 1e-10) and I_ss.max() < I_ms.max()
+    assert np.all(ss["hem_R"] >= 0) and np.all(ss["hem_T"] >= 0) and ss["hem_R"].max() < 1 and ss["hem_T"].max() < 1
+
+
+def test_single_scatter_thin_limit_converges_to_full_solution():
+    """R_ms - R_ss is second order in the optical depth: the relative gap shrinks linearly with the scale."""
+    gaps = []
+    for scale in (1e-2, 5e-3):
+        om = _ss_model(scale)
+        ss, ms = orc.rt_run_ss(om), orc.rt_run(om)
+        gaps.append(np.max(np.abs(ms["R_SFI"][:, 0] - ss["R_SFI"][:, 0]) / ms["R_SFI"][:, 0]))
+    assert gaps[0] < 3e-2 and 1.6 < gaps[0] / gaps[1] < 2.4, gaps

@@ -100,3 +100,23 @@ def test_sources_match_oracle_on_gpu(ctx, kind):
         assert np.isfinite(out[k]).all(), k
         assert relerr(out[k], ref[k]) <= 1e-9, (k, relerr(out[k], ref[k]))
     assert relerr(out["R_SFI"], base["R_SFI"]) > 1e-3          # the sources are really in
+
+
+# ---- single-scattering driver (rt_run_ss)
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,pol,brdf", [(np.float64, "Stokes_IQU", False), (np.float64, "Stokes_I", True), (np.float32, "Stokes_IQU", False)])
+def test_rt_run_ss_matches_oracle(dtype, pol, brdf):
+    import vsmom_oracle as orc
+    from helpers import relerr, to_oracle
+    from vsmom_b200 import rt_run as rr
+    m = vb.synthetic_o2a_model(nSpec=40, nstreams=6, polarization_type=pol, aerosol=True, float_type=dtype)
+    if brdf:
+        N = m.quad_points.qp_muN.size
+        m.surface_rho = 0.1 * np.random.default_rng(0).random((m.m_max + 1, N, N))
+    ref = orc.rt_run_ss(to_oracle(m))
+    out = rr.rt_run_ss(m)
+    tol = 1e-9 if dtype == np.float64 else 1e-3
+    for k in ("R_SFI", "T_SFI", "hem_R", "hem_T"):
+        assert relerr(out[k], ref[k]) <= tol, (k, relerr(out[k], ref[k]))
+    ms = rr.rt_run(m)
+    assert np.all(out["R_SFI"][:, 0] <= ms["R_SFI"][:, 0] * (1 + 1e-5) + 1e-10)      # SS <= MS on Stokes I (test_forward_ss.jl:62-73)

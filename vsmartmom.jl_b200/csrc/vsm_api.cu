@@ -18,6 +18,7 @@
 #include "vsm_stream.cuh"
 #include "vsm_lin.cuh"
 #include "vsm_raman_args.h"
+#include "vsm_ss.cuh"
 
 using namespace vsm;
 
@@ -1205,6 +1206,121 @@ extern "C" int vsm_rt_column_rrs_f64(vsm_ctx* c, const vsm_column_desc* d, const
                                      double* ieT) {
     return rt_column_rrs_impl(c, d, r, R, T_, ieR, ieT);
 }
+
+// ----------------------------------------------------------------------------------------------------------------
+// L2, single scattering: rt_run_ss(::noRS, model, iBand) rt_run.jl:593-755
+// ----------------------------------------------------------------------------------------------------------------
+template <typename T>
+static int rt_column_ss_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T_SFI, T* hem_R, T* hem_T) {
+    if (!ctx) return VSM_ERR_INVALID_ARG;
+    if (!d || (d->struct_size != (int)sizeof(vsm_column_desc) && d->struct_size != (int)offsetof(vsm_column_desc, thermal_B)))
+        return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_ss: descriptor NULL or struct_size mismatch");
+    if (d->struct_size == (int)sizeof(vsm_column_desc) && (d->thermal_B || d->sif0))
+        return fail(ctx, VSM_ERR_UNSUPPORTED, "rt_column_ss: extra sources are not part of this driver");
+    if (d->nSpec == 0) return VSM_OK;
+    if (!R_SFI || !T_SFI) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_ss: R_SFI/T_SFI NULL");
+    const int N = d->N, nSt = d->nStokes, Nz = d->Nz, nAer = d->nAer, nV = d->nVZA, nM = d->n_moments, nSpec = d->nSpec;
+    const int nOut = nV * nSt;
+    if (N <= 0 || nSt < 1 || nSt > 4 || N % nSt != 0 || Nz <= 0 || nAer < 0 || nAer + 1 > kMaxComp || nV <= 0 || nM <= 0 ||
+        nSpec < 0 || d->imu0 < 1 || d->imu0 * nSt > N)
+        return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_ss: bad dimensions");
+    if (!d->mu || !d->wt || !d->vza_weight || !d->rayl_allzero || !d->vza_stream || !d->tau_rayl || !d->tau_abs || !d->F0 ||
+        !d->Zpp || !d->Zmp || (nAer > 0 && (!d->aer_omega || !d->aer_ft || !d->tau_aer)))
+        return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_ss: NULL input array");
+    if (d->surface_kind != VSM_SURFACE_LAMBERTIAN_SCALAR && d->surface_kind != VSM_SURFACE_BRDF_FOURIER)
+        return fail(ctx, VSM_ERR_UNSUPPORTED, "rt_column_ss: surface_kind must be LAMBERTIAN_SCALAR or BRDF_FOURIER");
+    const void* surf_rho = d->surface_kind == VSM_SURFACE_BRDF_FOURIER ? d->surf_rho : nullptr;
+    if (d->surface_kind == VSM_SURFACE_BRDF_FOURIER && !surf_rho) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_ss: BRDF_FOURIER needs surf_rho");
+    CK(cudaSetDevice(ctx->device));
+    const int nC = nAer + 1;
+    std::vector<T> fT;
+    std::vector<int> fI;
+    auto pushT = [&](const double* p, size_t n) { size_t o = fT.size(); for (size_t i = 0; i < n; ++i) fT.push_back((T)p[i]); return o; };
+    const size_t o_mu = pushT(d->mu, N), o_wt = pushT(d->wt, N);
+    std::vector<double> taumod((size_t)std::max(1, nAer * Nz)), varmod((size_t)std::max(1, nAer));
+    for (int c = 0; c < nAer; ++c) {
+        const T ft = (T)d->aer_ft[c], om = (T)d->aer_omega[c];
+        varmod[c] = (double)(T)((T(1) - ft) * om / (T(1) - ft * om));
+        for (int iz = 0; iz < Nz; ++iz) taumod[c + (size_t)nAer * iz] = (double)(T)((T(1) - ft * om) * (T)d->tau_aer[c + (size_t)nAer * iz]);
+    }
+    const size_t o_taumod = pushT(taumod.data(), taumod.size()), o_varmod = pushT(varmod.data(), varmod.size());
+    const size_t o_vw = pushT(d->vza_weight, (size_t)nSt * nV * nM);
+    for (int iz = 0; iz < Nz; ++iz) fI.push_back(d->rayl_allzero[iz]);
+    const size_t o_vrow = fI.size();
+    for (int i = 0; i < nV; ++i) {
+        if (d->vza_stream[i] < 1 || d->vza_stream[i] * nSt > N) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_ss: vza_stream out of range");
+        fI.push_back((d->vza_stream[i] - 1) * nSt);
+    }
+    const size_t bytesT = fT.size() * sizeof(T), bytesI = fI.size() * sizeof(int);
+    const size_t offI = (bytesT + 15) & ~size_t(15);
+    int rc = ensure(ctx, ctx->consts, offI + bytesI);
+    if (rc) return rc;
+    if (ctx->stage_cap < offI + bytesI) {
+        if (ctx->stage) { CK(cudaStreamSynchronize(ctx->stream)); cudaFreeHost(ctx->stage); ctx->stage = nullptr; ctx->stage_cap = 0; }
+        CK(cudaMallocHost(&ctx->stage, (offI + bytesI) * 2));
+        ctx->stage_cap = (offI + bytesI) * 2;
+    }
+    if (!ctx->stage_done) CK(cudaEventCreateWithFlags(&ctx->stage_done, cudaEventDisableTiming | cudaEventBlockingSync));
+    else CK(cudaEventSynchronize(ctx->stage_done));
+    memcpy(ctx->stage, fT.data(), bytesT);
+    memcpy((char*)ctx->stage + offI, fI.data(), bytesI);
+    CK(cudaMemcpyAsync(ctx->consts.p, ctx->stage, offI + bytesI, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->stage_done, ctx->stream));
+    const T* cT = (const T*)ctx->consts.p;
+    const int* cI = (const int*)((char*)ctx->consts.p + offI);
+    const size_t props_pt = ((size_t)Nz * (2 + nC) + (Nz + 1)) * sizeof(T);
+    const size_t part_pt = (size_t)2 * nM * nOut * sizeof(T);
+    if ((rc = ensure(ctx, ctx->props, props_pt * nSpec))) return rc;
+    if ((rc = ensure(ctx, ctx->partial, part_pt * nSpec))) return rc;
+    if ((rc = ensure(ctx, ctx->counter, 256))) return rc;
+    CK(cudaMemsetAsync((int*)ctx->counter.p + 16, 0, 4, ctx->stream));
+    ctx->ev_used = 0;
+    ctx->seg_layer.clear();
+    ctx->seg_add.clear();
+    GET_EVENT(ev_begin);
+    GET_EVENT(ev_end);
+    CK(cudaEventRecord(ev_begin, ctx->stream));
+    T* pw = (T*)ctx->props.p;
+    PropsArgs<T> pa;
+    pa.nS = nSpec; pa.Nz = Nz; pa.nAer = nAer; pa.ldspec = (size_t)nSpec;
+    pa.tau_rayl = (const T*)d->tau_rayl; pa.tau_abs = (const T*)d->tau_abs;
+    pa.varpi_cab = (T)d->varpi_cabannes;
+    pa.aer_tau_mod = cT + o_taumod; pa.aer_varpi_mod = cT + o_varmod; pa.rayl_allzero = cI;
+    pa.tau = pw; pa.varpi = pw + (size_t)Nz * nSpec; pa.tausum = pw + (size_t)2 * Nz * nSpec;
+    pa.W = pw + (size_t)(2 * Nz + Nz + 1) * nSpec;
+    k_props<T><<<(nSpec + 127) / 128, 128, 0, ctx->stream>>>(pa);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    ColArgs<T> a;
+    memset(&a, 0, sizeof a);
+    a.N = N; a.nStokes = nSt; a.Nz = Nz; a.nC = nC; a.nVZA = nV; a.istart = (d->imu0 - 1) * nSt; a.nS = nSpec;
+    a.mu0 = (T)d->mu0; a.albedo = (T)d->albedo; a.surf_rho = (const T*)surf_rho;
+    a.mu = cT + o_mu; a.wt = cT + o_wt;
+    a.Zpp = (const T*)d->Zpp; a.Zmp = (const T*)d->Zmp;
+    a.p_tau = pa.tau; a.p_varpi = pa.varpi; a.p_tausum = pa.tausum; a.p_W = pa.W;
+    a.F0 = (const T*)d->F0; a.F0_off = 0;
+    a.vza_row = cI + o_vrow; a.vza_w = cT + o_vw;
+    T* part = (T*)ctx->partial.p;
+    const size_t per_m = (size_t)nSpec * nOut;
+    a.part_R = part; a.part_T = part + (size_t)nM * per_m;
+    const unsigned total = (unsigned)((size_t)nM * nSpec);
+    k_ss<T><<<(total + 3) / 4, 128, 0, ctx->stream>>>(a, total, hem_R, hem_T);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    k_reduce<T><<<(unsigned)((per_m + 255) / 256), 256, 0, ctx->stream>>>(nM, per_m, a.part_R, a.part_T, (const T*)nullptr, R_SFI, T_SFI,
+                                                                         (T*)nullptr, (const T*)nullptr, pa.tausum + (size_t)Nz * nSpec,
+                                                                         (T)d->mu0, nOut, (int*)ctx->counter.p + 16);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ev_end, ctx->stream));
+    ctx->ev[0] = ev_begin;
+    ctx->ev[1] = ev_end;
+    ctx->timing_valid = true;
+    return VSM_OK;
+}
+
+extern "C" int vsm_rt_column_ss_f64(vsm_ctx* c, const vsm_column_desc* d, double* R, double* T_, double* hR, double* hT) { return rt_column_ss_impl<double>(c, d, R, T_, hR, hT); }
+extern "C" int vsm_rt_column_ss_f32(vsm_ctx* c, const vsm_column_desc* d, float* R, float* T_, float* hR, float* hT) { return rt_column_ss_impl<float>(c, d, R, T_, hR, hT); }
 
 extern "C" int vsm_last_column_ms(vsm_ctx* ctx, float* total_ms, float* doubling_ms, float* adding_ms) {
     if (!ctx) return VSM_ERR_INVALID_ARG;

@@ -206,6 +206,35 @@ def rt_run(model: RTModel, ctx: Optional[_lib.Context] = None, prep: Optional[Pr
     return out
 
 
+def rt_run_ss(model: RTModel, ctx: Optional[_lib.Context] = None, device: str = "cuda:0"):
+    """Single-scattering driver, the reference's ``rt_run_ss(model)`` (rt_run.jl:547-755, noRS): returns ``R_SFI``,
+    ``T_SFI`` (nVZA, pol_n, nSpec) and the hemispheric ``hem_R``, ``hem_T`` (nSpec,)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("vsmom_b200.rt_run_ss needs a CUDA device (B200); there is no CPU fallback")
+    own = ctx is None
+    if own:
+        ctx = _lib.Context(torch.device(device).index or 0)
+    prep = prepare(model, device)
+    FT = model.float_type
+    dt = _tdtype(FT)
+    nS, n, nV = model.nSpec, model.pol_n, len(model.vza)
+    with torch.cuda.device(device):
+        tr = torch.from_numpy(np.ascontiguousarray(model.tau_rayl.T)).to(device)
+        ta = torch.from_numpy(np.ascontiguousarray(model.tau_abs.T)).to(device)
+        f0 = np.zeros((nS, n), FT); f0[:, 0] = 1
+        d, _keep = _column_desc(prep, tr, ta, torch.from_numpy(f0).to(device))
+        R = torch.empty((nS, n, nV), dtype=dt, device=device); T = torch.empty_like(R)
+        hR = torch.empty((nS,), dtype=dt, device=device); hT = torch.empty_like(hR)
+        fn = _lib.lib.vsm_rt_column_ss_f64 if FT == np.float64 else _lib.lib.vsm_rt_column_ss_f32
+        ctx.check(fn(ctx.handle, C.byref(d), R.data_ptr(), T.data_ptr(), hR.data_ptr(), hT.data_ptr()))
+        ctx.synchronize()
+        out = dict(R_SFI=R.cpu().numpy().transpose(2, 1, 0), T_SFI=T.cpu().numpy().transpose(2, 1, 0),
+                   hem_R=hR.cpu().numpy(), hem_T=hT.cpu().numpy())
+    if own:
+        ctx.close()
+    return out
+
+
 def rt_run_sharded(model: RTModel, ctx: Optional[_lib.Context] = None, device: Optional[str] = None):
     """``rt_run`` with the spectral axis sharded over the ranks of the default
     torch.distributed process group (NCCL, one process per GPU).  Every rank passes
