@@ -139,3 +139,14 @@ def test_rrs_config5_shape_invariants():
     part = raman.rt_run_rrs(ms, rs)
     for k in KEYS:
         assert relerr(part[k], ref[k]) <= TOL, (k, relerr(part[k], ref[k]))
+
+
+def test_rrs_with_brdf_surface_moments():
+    """A non-Lambertian surface (Fourier moments of R_surf for every m) under the Raman column."""
+    m, rs = _scene(aerosol=True, seed=21)
+    N = m.quad_points.qp_muN.size
+    m.surface_rho = 0.08 * np.random.default_rng(8).random((m.m_max + 1, N, N))
+    ref = _oracle(m, rs)
+    out = raman.rt_run_rrs(m, rs)
+    for k in KEYS:
+        assert relerr(out[k], ref[k]) <= TOL, (k, relerr(out[k], ref[k]))
