@@ -150,3 +150,16 @@ def test_rrs_with_brdf_surface_moments():
     out = raman.rt_run_rrs(m, rs)
     for k in KEYS:
         assert relerr(out[k], ref[k]) <= TOL, (k, relerr(out[k], ref[k]))
+
+
+def test_rrs_workspace_limit_chunks_owner_range_bit_identically():
+    """A small workspace limit makes the library run the owner range in sub-ranges: same bits."""
+    from vsmom_b200 import _lib
+    m, rs = _scene(nS=48)
+    full = raman.rt_run_rrs(m, rs)
+    ctx = _lib.Context(0)
+    ctx.set_workspace_limit(10 << 20)            # elastic records ~6.3 MB + 135 KB of unit state per owner point -> 2 sub-ranges
+    part = raman.rt_run_rrs(m, rs, ctx=ctx)
+    ctx.close()
+    for k in KEYS:
+        assert np.array_equal(part[k], full[k]), k

@@ -1204,6 +1204,35 @@ static int rt_column_rrs_impl(vsm_ctx* ctx, const vsm_column_desc* d, const vsm_
 
 extern "C" int vsm_rt_column_rrs_f64(vsm_ctx* c, const vsm_column_desc* d, const vsm_rrs_desc* r, double* R, double* T_, double* ieR,
                                      double* ieT) {
+    // The unit state is (nRaman x owner points) x 8.4 KB (NP = 16), double-buffered: when it exceeds the workspace limit the owner
+    // range is cut into sub-ranges that run one after the other (each recomputes the elastic column of its own halo; results are
+    // identical because a unit depends on nothing but the elastic state of n1 and n0).
+    if (c && d && r && r->struct_size == (int)sizeof(vsm_rrs_desc) && r->n1_count > 0 && r->n_raman > 0 && d->N > 0 && d->nVZA > 0) {
+        const rrs::Desc* kd = rrs::desc(d->N);
+        if (kd) {
+            if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, VSM_ERR_CUDA, "cudaSetDevice failed");
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return fail(c, VSM_ERR_CUDA, "cudaMemGetInfo failed");
+            uint64_t limit = c->ws_limit ? c->ws_limit : (uint64_t)48 << 30;
+            limit = std::min<uint64_t>(limit, ((uint64_t)free_b + c->rrs.cap) * 8 / 10);
+            const uint64_t per_pt = (uint64_t)r->n_raman * (2 * kd->ci + 2 * (uint64_t)d->nVZA * d->nStokes) * sizeof(double);
+            int ndm = 1;
+            for (int iz = 0; d->ndoubl && iz < d->Nz; ++iz) ndm = std::max(ndm, d->ndoubl[iz]);
+            const uint64_t elastic = (uint64_t)d->nSpec * ((uint64_t)ndm * (kd->rec0 + kd->rec1) + kd->irec0 + kd->irec1 + 2 * kd->ce + 64) * sizeof(double);
+            if (elastic + per_pt * r->n1_count > limit && limit > elastic + per_pt) {
+                const int chunk = (int)std::max<uint64_t>(1, (limit - elastic) / per_pt);
+                const size_t nOut = (size_t)d->nVZA * d->nStokes;
+                for (int lo = 0; lo < r->n1_count; lo += chunk) {
+                    vsm_rrs_desc sub = *r;
+                    sub.n1_begin = r->n1_begin + lo;
+                    sub.n1_count = std::min(chunk, r->n1_count - lo);
+                    const int rc = rt_column_rrs_impl(c, d, &sub, R + lo * nOut, T_ + lo * nOut, ieR + lo * nOut, ieT + lo * nOut);
+                    if (rc) return rc;
+                }
+                return VSM_OK;
+            }
+        }
+    }
     return rt_column_rrs_impl(c, d, r, R, T_, ieR, ieT);
 }
 
