@@ -224,6 +224,25 @@ __device__ __forceinline__ void mvf(double (&cv)[2][2], const Frag16& a, X1 x1, 
         for (int r = 0; r < 2; ++r) dmma(cv[r][0], cv[r][1], a[r][s], bx[s]);
 }
 
+// y = M x from the A-side fragments of M on the FMA datapath: 8 DFMA + 4 shuffles per lane (a tensor tile with one useful
+// column would spend 8 DMMA = 8x the fp64-pipe time); on return every lane holds y[8r+g] in out[r]
+template <class X>
+__device__ __forceinline__ void mvs(double (&out)[2], const Frag16& a, X x, int tg) {
+    double xs[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) xs[s] = x(4 * tg + s);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        double p = a[r][0] * xs[0];
+        p = fma(a[r][1], xs[1], p);
+        p = fma(a[r][2], xs[2], p);
+        p = fma(a[r][3], xs[3], p);
+        p += __shfl_xor_sync(0xffffffffu, p, 1);
+        p += __shfl_xor_sync(0xffffffffu, p, 2);
+        out[r] = p;
+    }
+}
+
 // in-place inverse of the leading n x n block of M (shared, ld = NP+4) by Gauss-Jordan with partial pivoting
 // (the reference's getrf/getri route, cpu_batched.jl:32-37); colk: NP doubles, piv: NP ints of scratch
 template <int NP>
@@ -804,9 +823,20 @@ __global__ void __launch_bounds__(32 * WPC, (NP <= 16) ? 4 : 1) k_rrs_inel(Args 
                 __syncwarp();
                 lfA(sX, XA, g, tg);
                 // sources (:74-98)
+#ifdef VSM_RRS_MV_TENSOR
                 mvf(cv1, r1A, SV{v1m}, SV{jp}, g, tg);            // r1 ieJ1-          | r1 ieJ0+
                 mvf(cv2, AA, J1m0, J0p0, g, tg);                  // ier J1-[n0]       | ier J0+[n0]
                 mvf(cv3, XA, tmp1, tmp2, g, tg);                  // X tmp1[n0]        | X tmp2[n0]
+#else
+                // mat-vecs from the fragments already in registers, on the FMA datapath (mvs)
+                { double t0[2], t1[2];
+                  mvs(t0, r1A, SV{v1m}, tg); mvs(t1, r1A, SV{jp}, tg);
+                  cv1[0][0] = t0[0]; cv1[1][0] = t0[1]; cv1[0][1] = t1[0]; cv1[1][1] = t1[1];
+                  mvs(t0, AA, J1m0, tg); mvs(t1, AA, J0p0, tg);
+                  cv2[0][0] = t0[0]; cv2[1][0] = t0[1]; cv2[0][1] = t1[0]; cv2[1][1] = t1[1];
+                  mvs(t0, XA, tmp1, tg); mvs(t1, XA, tmp2, tg);
+                  cv3[0][0] = t0[0]; cv3[1][0] = t0[1]; cv3[0][1] = t1[0]; cv3[1][1] = t1[1]; }
+#endif
                 if (tg == 0) {
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {
@@ -818,8 +848,16 @@ __global__ void __launch_bounds__(32 * WPC, (NP <= 16) ? 4 : 1) k_rrs_inel(Args 
                 __syncwarp();
                 Frag16 BA;
                 lfA(sB, BA, g, tg);
+#ifdef VSM_RRS_MV_TENSOR
                 mvf(cv1, TG1A, SV{w3}, SV{w4}, g, tg);
                 mvf(cv2, BA, tmp1, tmp2, g, tg);
+#else
+                { double t0[2], t1[2];
+                  mvs(t0, TG1A, SV{w3}, tg); mvs(t1, TG1A, SV{w4}, tg);
+                  cv1[0][0] = t0[0]; cv1[1][0] = t0[1]; cv1[0][1] = t1[0]; cv1[1][1] = t1[1];
+                  mvs(t0, BA, tmp1, tg); mvs(t1, BA, tmp2, tg);
+                  cv2[0][0] = t0[0]; cv2[1][0] = t0[1]; cv2[0][1] = t1[0]; cv2[1][1] = t1[1]; }
+#endif
                 if (tg == 0) {
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {
@@ -961,73 +999,177 @@ __global__ void __launch_bounds__(32 * WPC, (NP <= 16) ? 4 : 1) k_rrs_inel(Args 
     for (int e = lane; e < NP * NP; e += 32) S2[(e % NP) + (e / NP) * LDS] = __ldg(Cin + MG + e);
     const SM<NP> ieRpm{S2};
     __syncwarp();
-    // Q1 = ier R+-0 + r1 ieR+- ;  P = T01 Q1 + ieT--
-    czero<NP>(c);
-    wmm<NP>(c, sA, Rpm0, lane);
-    wmm<NP>(c, r1, ieRpm, lane);
-    wepi<NP>(c, [&](int i, int j, double v) { X[i + j * LDS] = v; }, lane);
-    __syncwarp();
-    czero<NP>(c);
-    wmm<NP>(c, T01, sX, lane);
-    wepi<NP>(c, [&](int i, int j, double v) { S1[i + j * LDS] = ieTmm(i, j) + v; }, lane);
-    // ieJ0- (:378-398)
-    wmv<NP>(y1, sA, J0p0, lane);
-    wmv<NP>(y2, r1, GV{cJp}, lane);
-    if (lane < 16) for (int b = 0; b < NP / 16; ++b) { const int i = 16 * b + lane; w3[i] = y1[b] + y2[b] + jm[i]; }
-    __syncwarp();
-    wmv<NP>(y1, T01, SV{w3}, lane);
-    wmv<NP>(y2, sS1, v1, lane);
-    if (lane < 16) for (int b = 0; b < NP / 16; ++b) { const int i = 16 * b + lane; Cout[4 * MG + NP + i] = __ldg(cJm + i) + y1[b] + y2[b]; }
-    // Q2 = ier T++0 + r1 ieT++ ;  ieR-+ = ieR-+ + T01 Q2 + P E1
-    czero<NP>(c);
-    wmm<NP>(c, sA, Tpp0, lane);
-    wmm<NP>(c, r1, ieTpp, lane);
-    __syncwarp();
-    wepi<NP>(c, [&](int i, int j, double v) { X[i + j * LDS] = v; }, lane);
-    __syncwarp();
-    czero<NP>(c);
-    wmm<NP>(c, T01, sX, lane);
-    wmm<NP>(c, sS1, E1, lane);
-    wepi<NP>(c, [&](int i, int j, double v) { Cout[i + j * NP] = ieRmp(i, j) + v; }, lane);
-    // ieT-- = T01 iet-- + P E2
-    czero<NP>(c);
-    wmm<NP>(c, T01, sBc, lane);
-    wmm<NP>(c, sS1, E2, lane);
-    wepi<NP>(c, [&](int i, int j, double v) { Cout[3 * MG + i + j * NP] = v; }, lane);
-    // Q3 = ieR+- r0 + R+-1 ier ;  P' = T21 Q3 + iet++
-    czero<NP>(c);
-    wmm<NP>(c, ieRpm, r0, lane);
-    wmm<NP>(c, Rpm1, sA, lane);
-    __syncwarp();
-    wepi<NP>(c, [&](int i, int j, double v) { X[i + j * LDS] = v; }, lane);
-    __syncwarp();
-    czero<NP>(c);
-    wmm<NP>(c, T21, sX, lane);
-    wepi<NP>(c, [&](int i, int j, double v) { S1[i + j * LDS] = B[i + j * LDS] + v; }, lane);
-    // ieJ0+ (:447-459)
-    wmv<NP>(y1, ieRpm, aj0m0, lane);
-    wmv<NP>(y2, Rpm1, SV{jm}, lane);
-    if (lane < 16) for (int b = 0; b < NP / 16; ++b) { const int i = 16 * b + lane; w4[i] = __ldg(cJp + i) + y1[b] + y2[b]; }
-    __syncwarp();
-    wmv<NP>(y1, T21, SV{w4}, lane);
-    wmv<NP>(y2, sS1, v2, lane);
-    if (lane < 16) for (int b = 0; b < NP / 16; ++b) { const int i = 16 * b + lane; Cout[4 * MG + i] = jp[i] + y1[b] + y2[b]; }
-    // ieT++ = T21 ieT++ + P' E3
-    czero<NP>(c);
-    wmm<NP>(c, T21, ieTpp, lane);
-    wmm<NP>(c, sS1, E3, lane);
-    wepi<NP>(c, [&](int i, int j, double v) { Cout[2 * MG + i + j * NP] = v; }, lane);
-    // Q4 = ieR+- t--0 + R+-1 iet-- ;  ieR+- = ier+- + T21 Q4 + P' E4
-    czero<NP>(c);
-    wmm<NP>(c, ieRpm, tmm0, lane);
-    wmm<NP>(c, Rpm1, sBc, lane);
-    __syncwarp();
-    wepi<NP>(c, [&](int i, int j, double v) { X[i + j * LDS] = v; }, lane);
-    __syncwarp();
-    czero<NP>(c);
-    wmm<NP>(c, T21, sX, lane);
-    wmm<NP>(c, sS1, E4, lane);
-    wepi<NP>(c, [&](int i, int j, double v) { Cout[MG + i + j * NP] = A[i + j * LDS] * sg[i] * sg[j] + v; }, lane);
+    if constexpr (NP == 16) {
+        // register-resident fragments: T01 / T21, r1 / R+-1, ier, P / P' and ieR+- enter several products each
+        const int g = lane >> 2, tg = lane & 3;
+        Frag16 TA, RA, AA, PA, T;
+        double ya[2], yb[2];
+        lfA(T01, TA, g, tg);
+        lfA(r1, RA, g, tg);
+        lfA(sA, AA, g, tg);
+        // Q1 = ier R+-0 + r1 ieR+- ;  P = T01 Q1 + ieT--
+        lfB(Rpm0, T, g, tg);
+        czero<NP>(c);
+        mmf(c, AA, T);
+        lfB(ieRpm, T, g, tg);
+        mmf(c, RA, T);
+        wepi<NP>(c, [&](int i, int j, double v) { X[i + j * LDS] = v; }, lane);
+        __syncwarp();
+        lfB(sX, T, g, tg);
+        czero<NP>(c);
+        mmf(c, TA, T);
+        wepi<NP>(c, [&](int i, int j, double v) { S1[i + j * LDS] = ieTmm(i, j) + v; }, lane);
+        // ieJ0- (:378-398)
+        mvs(ya, AA, J0p0, tg);
+        mvs(yb, RA, GV{cJp}, tg);
+        if (tg == 0) { w3[g] = ya[0] + yb[0] + jm[g]; w3[8 + g] = ya[1] + yb[1] + jm[8 + g]; }
+        __syncwarp();
+        lfA(sS1, PA, g, tg);
+        mvs(ya, TA, SV{w3}, tg);
+        mvs(yb, PA, v1, tg);
+        if (tg == 0) {
+            Cout[4 * MG + NP + g] = __ldg(cJm + g) + ya[0] + yb[0];
+            Cout[4 * MG + NP + 8 + g] = __ldg(cJm + 8 + g) + ya[1] + yb[1];
+        }
+        // Q2 = ier T++0 + r1 ieT++ ;  ieR-+ = ieR-+ + T01 Q2 + P E1
+        lfB(Tpp0, T, g, tg);
+        czero<NP>(c);
+        mmf(c, AA, T);
+        lfB(ieTpp, T, g, tg);
+        mmf(c, RA, T);
+        __syncwarp();
+        wepi<NP>(c, [&](int i, int j, double v) { X[i + j * LDS] = v; }, lane);
+        __syncwarp();
+        lfB(sX, T, g, tg);
+        czero<NP>(c);
+        mmf(c, TA, T);
+        lfB(E1, T, g, tg);
+        mmf(c, PA, T);
+        wepi<NP>(c, [&](int i, int j, double v) { Cout[i + j * NP] = ieRmp(i, j) + v; }, lane);
+        // ieT-- = T01 iet-- + P E2
+        lfB(sBc, T, g, tg);
+        czero<NP>(c);
+        mmf(c, TA, T);
+        lfB(E2, T, g, tg);
+        mmf(c, PA, T);
+        wepi<NP>(c, [&](int i, int j, double v) { Cout[3 * MG + i + j * NP] = v; }, lane);
+        // second half: T21, R+-1, ieR+- (A side)
+        lfA(T21, TA, g, tg);
+        lfA(Rpm1, RA, g, tg);
+        lfA(ieRpm, AA, g, tg);
+        // Q3 = ieR+- r0 + R+-1 ier ;  P' = T21 Q3 + iet++
+        lfB(r0, T, g, tg);
+        czero<NP>(c);
+        mmf(c, AA, T);
+        lfB(sA, T, g, tg);
+        mmf(c, RA, T);
+        __syncwarp();
+        wepi<NP>(c, [&](int i, int j, double v) { X[i + j * LDS] = v; }, lane);
+        __syncwarp();
+        lfB(sX, T, g, tg);
+        czero<NP>(c);
+        mmf(c, TA, T);
+        wepi<NP>(c, [&](int i, int j, double v) { S1[i + j * LDS] = B[i + j * LDS] + v; }, lane);
+        // ieJ0+ (:447-459)
+        mvs(ya, AA, aj0m0, tg);
+        mvs(yb, RA, SV{jm}, tg);
+        if (tg == 0) { w4[g] = __ldg(cJp + g) + ya[0] + yb[0]; w4[8 + g] = __ldg(cJp + 8 + g) + ya[1] + yb[1]; }
+        __syncwarp();
+        lfA(sS1, PA, g, tg);
+        mvs(ya, TA, SV{w4}, tg);
+        mvs(yb, PA, v2, tg);
+        if (tg == 0) { Cout[4 * MG + g] = jp[g] + ya[0] + yb[0]; Cout[4 * MG + 8 + g] = jp[8 + g] + ya[1] + yb[1]; }
+        // ieT++ = T21 ieT++ + P' E3
+        lfB(ieTpp, T, g, tg);
+        czero<NP>(c);
+        mmf(c, TA, T);
+        lfB(E3, T, g, tg);
+        mmf(c, PA, T);
+        wepi<NP>(c, [&](int i, int j, double v) { Cout[2 * MG + i + j * NP] = v; }, lane);
+        // Q4 = ieR+- t--0 + R+-1 iet-- ;  ieR+- = ier+- + T21 Q4 + P' E4
+        lfB(tmm0, T, g, tg);
+        czero<NP>(c);
+        mmf(c, AA, T);
+        lfB(sBc, T, g, tg);
+        mmf(c, RA, T);
+        __syncwarp();
+        wepi<NP>(c, [&](int i, int j, double v) { X[i + j * LDS] = v; }, lane);
+        __syncwarp();
+        lfB(sX, T, g, tg);
+        czero<NP>(c);
+        mmf(c, TA, T);
+        lfB(E4, T, g, tg);
+        mmf(c, PA, T);
+        wepi<NP>(c, [&](int i, int j, double v) { Cout[MG + i + j * NP] = A[i + j * LDS] * sg[i] * sg[j] + v; }, lane);
+    } else {
+        // Q1 = ier R+-0 + r1 ieR+- ;  P = T01 Q1 + ieT--
+        czero<NP>(c);
+        wmm<NP>(c, sA, Rpm0, lane);
+        wmm<NP>(c, r1, ieRpm, lane);
+        wepi<NP>(c, [&](int i, int j, double v) { X[i + j * LDS] = v; }, lane);
+        __syncwarp();
+        czero<NP>(c);
+        wmm<NP>(c, T01, sX, lane);
+        wepi<NP>(c, [&](int i, int j, double v) { S1[i + j * LDS] = ieTmm(i, j) + v; }, lane);
+        // ieJ0- (:378-398)
+        wmv<NP>(y1, sA, J0p0, lane);
+        wmv<NP>(y2, r1, GV{cJp}, lane);
+        if (lane < 16) for (int b = 0; b < NP / 16; ++b) { const int i = 16 * b + lane; w3[i] = y1[b] + y2[b] + jm[i]; }
+        __syncwarp();
+        wmv<NP>(y1, T01, SV{w3}, lane);
+        wmv<NP>(y2, sS1, v1, lane);
+        if (lane < 16) for (int b = 0; b < NP / 16; ++b) { const int i = 16 * b + lane; Cout[4 * MG + NP + i] = __ldg(cJm + i) + y1[b] + y2[b]; }
+        // Q2 = ier T++0 + r1 ieT++ ;  ieR-+ = ieR-+ + T01 Q2 + P E1
+        czero<NP>(c);
+        wmm<NP>(c, sA, Tpp0, lane);
+        wmm<NP>(c, r1, ieTpp, lane);
+        __syncwarp();
+        wepi<NP>(c, [&](int i, int j, double v) { X[i + j * LDS] = v; }, lane);
+        __syncwarp();
+        czero<NP>(c);
+        wmm<NP>(c, T01, sX, lane);
+        wmm<NP>(c, sS1, E1, lane);
+        wepi<NP>(c, [&](int i, int j, double v) { Cout[i + j * NP] = ieRmp(i, j) + v; }, lane);
+        // ieT-- = T01 iet-- + P E2
+        czero<NP>(c);
+        wmm<NP>(c, T01, sBc, lane);
+        wmm<NP>(c, sS1, E2, lane);
+        wepi<NP>(c, [&](int i, int j, double v) { Cout[3 * MG + i + j * NP] = v; }, lane);
+        // Q3 = ieR+- r0 + R+-1 ier ;  P' = T21 Q3 + iet++
+        czero<NP>(c);
+        wmm<NP>(c, ieRpm, r0, lane);
+        wmm<NP>(c, Rpm1, sA, lane);
+        __syncwarp();
+        wepi<NP>(c, [&](int i, int j, double v) { X[i + j * LDS] = v; }, lane);
+        __syncwarp();
+        czero<NP>(c);
+        wmm<NP>(c, T21, sX, lane);
+        wepi<NP>(c, [&](int i, int j, double v) { S1[i + j * LDS] = B[i + j * LDS] + v; }, lane);
+        // ieJ0+ (:447-459)
+        wmv<NP>(y1, ieRpm, aj0m0, lane);
+        wmv<NP>(y2, Rpm1, SV{jm}, lane);
+        if (lane < 16) for (int b = 0; b < NP / 16; ++b) { const int i = 16 * b + lane; w4[i] = __ldg(cJp + i) + y1[b] + y2[b]; }
+        __syncwarp();
+        wmv<NP>(y1, T21, SV{w4}, lane);
+        wmv<NP>(y2, sS1, v2, lane);
+        if (lane < 16) for (int b = 0; b < NP / 16; ++b) { const int i = 16 * b + lane; Cout[4 * MG + i] = jp[i] + y1[b] + y2[b]; }
+        // ieT++ = T21 ieT++ + P' E3
+        czero<NP>(c);
+        wmm<NP>(c, T21, ieTpp, lane);
+        wmm<NP>(c, sS1, E3, lane);
+        wepi<NP>(c, [&](int i, int j, double v) { Cout[2 * MG + i + j * NP] = v; }, lane);
+        // Q4 = ieR+- t--0 + R+-1 iet-- ;  ieR+- = ier+- + T21 Q4 + P' E4
+        czero<NP>(c);
+        wmm<NP>(c, ieRpm, tmm0, lane);
+        wmm<NP>(c, Rpm1, sBc, lane);
+        __syncwarp();
+        wepi<NP>(c, [&](int i, int j, double v) { X[i + j * LDS] = v; }, lane);
+        __syncwarp();
+        czero<NP>(c);
+        wmm<NP>(c, T21, sX, lane);
+        wmm<NP>(c, sS1, E4, lane);
+        wepi<NP>(c, [&](int i, int j, double v) { Cout[MG + i + j * NP] = A[i + j * LDS] * sg[i] * sg[j] + v; }, lane);
+    }
     if (mode == 1) {
         // postprocessing_vza!(::RRS) inelastic lines (postprocessing_vza.jl:143-146): this unit's share
         __syncwarp();
