@@ -615,3 +615,37 @@ def test_small_matrix_kernel_equals_generic_kernels():
         ref = orc.rt_run(to_oracle(m))
         for k in ("R_SFI", "T_SFI", "hdr", "bhr_uw", "bhr_dw"):
             assert relerr(res[0][k], ref[k]) <= 1e-9, (k, relerr(res[0][k], ref[k]))
+
+
+@pytest.mark.parametrize("pol,nstreams,expect_N", [("Stokes_IQU", 8, 39), ("Stokes_IQU", 4, 27), ("Stokes_I", 30, 35),
+                                                   ("Stokes_IQUV", 8, 52), ("Stokes_IQUV", 12, 68), ("Stokes_IQU", 23, 81)])
+def test_embedded_sizes_match_oracle_and_generic(pol, nstreams, expect_N):
+    """N between the specialised sizes runs zero-padded as the next one (45 / 60 / 75 / 100) with dummy zero-weight
+    streams; VSM_DISABLE_EMBED=1 keeps the run-time-N generic kernels.  Same results, and both match the oracle."""
+    import os
+    from vsmom_b200 import _lib, rt_run as rr
+    m = vb.synthetic_o2a_model(nSpec=5, nstreams=nstreams, polarization_type=pol, aerosol=True)
+    for a in m.aerosol_optics:                       # short Fourier loop: keeps the oracle run short
+        g = a.greek_coefs
+        for f in ("alpha", "beta", "gamma", "delta", "epsilon", "zeta"):
+            setattr(g, f, getattr(g, f)[:5])
+    m.m_max = 4
+    m.tau_rayl[:, 2] = 0.0
+    m.tau_aer[:, 2] = 0.0                            # one non-scattering layer
+    assert m.quad_points.qp_muN.size == expect_N
+    res = []
+    for dis in (None, "1"):
+        if dis:
+            os.environ["VSM_DISABLE_EMBED"] = dis
+        else:
+            os.environ.pop("VSM_DISABLE_EMBED", None)
+        c = _lib.Context(0)
+        res.append(rr.rt_run(m, ctx=c))
+        c.close()
+    os.environ.pop("VSM_DISABLE_EMBED", None)
+    ref = orc.rt_run(to_oracle(m))
+    for k in ("R_SFI", "T_SFI", "hdr", "bhr_uw", "bhr_dw"):
+        # (two kernel families: the deep-absorption points of this band sit at 1e-50, where exp() arguments of ~115 make
+        #  1e-11 relative differences between any two evaluation orders)
+        assert relerr(res[0][k], res[1][k]) <= 1e-10, (k, relerr(res[0][k], res[1][k]))
+        assert relerr(res[0][k], ref[k]) <= 1e-9, (k, relerr(res[0][k], ref[k]))

@@ -42,6 +42,8 @@ struct vsm_ctx {
     std::string err;
     // grow-only scratch
     DevBuf consts, props, added, slabs, partial, counter, l0tmp, geom, surfpad, linprops, rrs;
+    DevBuf padtab;                          // zero-padded Z / surface tables of an embedded column (see embed_size)
+    int use_embed = 1;                      // run N between the specialised sizes as the next one, zero-padded (VSM_DISABLE_EMBED=1: off)
     int use_small = 1;                      // warp-per-point column kernel for N <= 16 in fp64 (VSM_DISABLE_SMALL=1 turns it off)
     int rrs_order = 1;                      // unit enumeration of the Raman kernels (VSM_RRS_ORDER): 0 dn-major, 1 donor-major
     int use_stream = 1;                     // streamed-operand kernels for N = 60 / 75 / 100 (VSM_DISABLE_STREAM=1 turns them off)
@@ -146,6 +148,7 @@ extern "C" int vsm_create(vsm_ctx** out, int device, void* cuda_stream) {
     ctx->ws_limit = 0;
     if (const char* e = getenv("VSM_DEBUG_LAYER_CTAS_PER_SM")) ctx->dbg_layer_ctas = atoi(e);
     if (const char* e = getenv("VSM_DISABLE_STREAM")) ctx->use_stream = atoi(e) ? 0 : 1;
+    if (const char* e = getenv("VSM_DISABLE_EMBED")) ctx->use_embed = atoi(e) ? 0 : 1;
     if (const char* e = getenv("VSM_DISABLE_SMALL")) ctx->use_small = atoi(e) ? 0 : 1;
     if (const char* e = getenv("VSM_RRS_ORDER")) ctx->rrs_order = atoi(e) ? 1 : 0;
     *out = ctx;
@@ -424,10 +427,40 @@ static int occupancy(const void* kern, int threads, size_t smem) {
 // ---------------------------------------------------------------------------
 // L2: whole column
 // ---------------------------------------------------------------------------
+// ---- embedding: a column whose N lies between the sizes that have tensor-core kernels runs as the next such size with
+// DUMMY streams: zero quadrature weight, zero rows/columns in every Z table and surface moment.  A zero-weight stream is
+// something the algorithm already has (the VZA / SZA streams, elemental.jl:325-332): r = 0 and t = exp(-dτ/μ) on its
+// diagonal; with Z = 0 it neither receives from nor feeds any real stream, so the real N x N block of every operator is
+// unchanged (the sums just carry extra exact zeros) and (Npad/N)^3 more flops still beat the SIMT kernels by 2-7x.
+template <typename T>
+static int embed_size(const vsm_ctx* ctx, int N, bool has_stream_export) {
+    if (!ctx->use_embed || has_stream_export) return N;
+    if (std::is_same<T, double>::value) {
+        if (N >= 23 && N < 45) return 45;
+        if (ctx->use_stream) {
+            if (N > 45 && N < 60) return 60;
+            if (N > 60 && N < 75) return 75;
+            if (N > 75 && N < 100) return 100;
+        }
+    }
+    return N;
+}
+
+// dst (Np,Np,K) <- src (N,N,K), zero outside the leading N x N block
+template <typename T>
+__global__ void k_pad_tables(int N, int Np, size_t K, const T* __restrict__ src, T* __restrict__ dst) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t per = (size_t)Np * Np;
+    if (e >= per * K) return;
+    const size_t k = e / per;
+    const int i = (int)(e % per) % Np, j = (int)(e % per) / Np;
+    dst[e] = (i < N && j < N) ? src[(size_t)i + (size_t)j * N + (size_t)N * N * k] : T(0);
+}
+
 template <typename T>
 static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T_SFI, T* hdr,
                           T* bhr_uw, T* bhr_dw, T* st_Rmp = nullptr, T* st_Tpp = nullptr, T* st_Jm = nullptr,
-                          T* st_Jp = nullptr) {
+                          T* st_Jp = nullptr, bool padded = false) {
     if (!ctx) return VSM_ERR_INVALID_ARG;
     // struct_size versions the descriptor: the layout up to Zmp (Lambertian only) or the full one
     // (Lambertian only), up to surf_rho (BRDF moments), or the full one (+ Cox-Munk TMS correction)
@@ -445,7 +478,7 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
     const int N = d->N, nSt = d->nStokes, Nz = d->Nz, nAer = d->nAer, nV = d->nVZA, nM = d->n_moments;
     const int nSpec = d->nSpec;
     const int nOut = nV * nSt;
-    if (N <= 0 || nSt < 1 || nSt > 4 || N % nSt != 0 || Nz <= 0 || nAer < 0 || nAer + 1 > kMaxComp ||
+    if (N <= 0 || nSt < 1 || nSt > 4 || (N % nSt != 0 && !padded) || Nz <= 0 || nAer < 0 || nAer + 1 > kMaxComp ||
         nV <= 0 || nM <= 0 || nSpec < 0 || d->imu0 < 1 || d->imu0 * nSt > N)
         return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column: bad dimensions");
     if (d->surface_kind != VSM_SURFACE_LAMBERTIAN_SCALAR && d->surface_kind != VSM_SURFACE_BRDF_FOURIER)
@@ -459,6 +492,41 @@ static int rt_column_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T* T
     if (nSpec == 0) return VSM_OK;
     CK(cudaSetDevice(ctx->device));
     const int nC = nAer + 1;
+    if (!padded) {
+        const int Np = embed_size<T>(ctx, N, st_Rmp || st_Tpp || st_Jm || st_Jp);
+        if (Np != N) {
+            // zero-padded Z tables / surface moments on the device, dummy streams on the host side
+            const size_t kz = (size_t)nC * nM, per = (size_t)Np * Np;
+            const size_t need = (2 * kz + (surf_rho ? (size_t)nM : 0)) * per * sizeof(T);
+            int rc0 = ensure(ctx, ctx->padtab, need);
+            if (rc0) return rc0;
+            T* zp = (T*)ctx->padtab.p; T* zm = zp + kz * per; T* rp = zm + kz * per;
+            k_pad_tables<T><<<(unsigned)((kz * per + 255) / 256), 256, 0, ctx->stream>>>(N, Np, kz, (const T*)d->Zpp, zp);
+            k_pad_tables<T><<<(unsigned)((kz * per + 255) / 256), 256, 0, ctx->stream>>>(N, Np, kz, (const T*)d->Zmp, zm);
+            if (surf_rho) k_pad_tables<T><<<(unsigned)(((size_t)nM * per + 255) / 256), 256, 0, ctx->stream>>>(N, Np, (size_t)nM, (const T*)surf_rho, rp);
+            ctx->launches += surf_rho ? 3 : 2;
+            CK(cudaGetLastError());
+            std::vector<double> mu2(d->mu, d->mu + N), wt2(d->wt, d->wt + N);
+            for (int k = 0; k < Np - N; ++k) {
+                // dummy cosines spread over (0.3, 0.9), nudged away from the real ones (only their Beer-law diagonal is used)
+                double m = 0.3 + 0.6 * (k + 0.5) / (Np - N);
+                for (int it = 0; it < 64; ++it) {
+                    bool clash = false;
+                    for (size_t q = 0; q < mu2.size(); ++q) clash = clash || fabs(mu2[q] - m) < 1e-4;
+                    if (!clash) break;
+                    m += 1.7e-4;
+                }
+                mu2.push_back(m);
+                wt2.push_back(0.0);
+            }
+            vsm_column_desc d2;
+            memset(&d2, 0, sizeof d2);
+            memcpy(&d2, d, (size_t)d->struct_size);
+            d2.N = Np; d2.mu = mu2.data(); d2.wt = wt2.data(); d2.Zpp = zp; d2.Zmp = zm;
+            if (surf_rho) d2.surf_rho = rp;
+            return rt_column_impl<T>(ctx, &d2, R_SFI, T_SFI, hdr, bhr_uw, bhr_dw, nullptr, nullptr, nullptr, nullptr, true);
+        }
+    }
 
     // ---- small constant tables -> one device blob
     std::vector<T> fT;
