@@ -11,7 +11,7 @@ from vsmom_b200 import _lib, rt_run as rr
 out = {}
 for name, kw, nS in (("file default with Stokes_IQU: 8 streams -> N = 39 (runs as 45)", dict(nstreams=8, polarization_type="Stokes_IQU"), 2000),
                      ("Stokes_IQU, 4 streams -> N = 27 (runs as 45)", dict(nstreams=4, polarization_type="Stokes_IQU"), 2000),
-                     ("Stokes_IQUV, 11 streams -> N = 64 (runs as 75)", dict(nstreams=11, polarization_type="Stokes_IQUV"), 296)):
+                     ("Stokes_IQUV, 12 streams -> N = 68 (runs as 75)", dict(nstreams=12, polarization_type="Stokes_IQUV"), 296)):
     m = vb.synthetic_o2a_model(nSpec=nS, aerosol=True, **kw)
     res = {}
     for mode in ("embedded", "generic"):

@@ -38,7 +38,6 @@ struct vsm_ctx {
     int inverse_mode = 1;   // 1: adaptive Neumann / Gauss-Jordan, 0: Gauss-Jordan only
     uint64_t launches = 0;
     int dbg_layer_ctas = 0;                 // VSM_DEBUG_LAYER_CTAS_PER_SM, read once at vsm_create
-    std::map<const void*, int> smem_set;    // largest dynamic shared-memory size already granted per kernel
     std::string err;
     // grow-only scratch
     DevBuf consts, props, added, slabs, partial, counter, l0tmp, geom, surfpad, linprops, rrs;
@@ -68,12 +67,19 @@ struct vsm_ctx {
         }                                                                         \
     } while (0)
 
-// cudaFuncAttributeMaxDynamicSharedMemorySize, issued once per (kernel, size) instead of per call
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of (device, kernel) in the PROCESS, not of a context: it is
+// raised here and never lowered -- a second context asking for less (fewer layers, say) must not shrink what a first
+// context was granted, or the first one's next launch fails with "invalid argument".  Issued once per growth, not per call.
+#include <mutex>
 static cudaError_t set_smem(vsm_ctx* ctx, const void* kern, size_t bytes) {
-    auto it = ctx->smem_set.find(kern);
-    if (it != ctx->smem_set.end() && it->second >= (int)bytes) return cudaSuccess;
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, int> granted;
+    std::lock_guard<std::mutex> lock(mu);
+    const auto key = std::make_pair(ctx->device, kern);
+    auto it = granted.find(key);
+    if (it != granted.end() && it->second >= (int)bytes) return cudaSuccess;
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e == cudaSuccess) ctx->smem_set[kern] = (int)bytes;
+    if (e == cudaSuccess) granted[key] = (int)bytes;
     return e;
 }
 
