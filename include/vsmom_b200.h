@@ -281,6 +281,14 @@ int vsm_rt_column_sharded_f64(vsm_multi*, const vsm_column_desc*, double* R_SFI,
 int vsm_rt_column_sharded_f32(vsm_multi*, const vsm_column_desc*, float* R_SFI, float* T_SFI, float* hdr,
                               float* bhr_uw, float* bhr_dw);
 
+/* The Raman column (vsm_rt_column_rrs_f64) on the devices of a vsm_multi from ONE process: every device receives the whole
+ * band and one contiguous owner range of the outputs (n1_begin / n1_count of the descriptor are ignored), recomputes the
+ * elastic column of its halo locally (no data-path collective) and ONE ncclAllGather of the packed (R | T | ieR | ieT)
+ * rows closes the call.  tau_rayl, tau_abs, F0, Zpp, Zmp, surf_rho, Zpp_raman, Zmp_raman and the four outputs
+ * (nVZA,nStokes,nSpec) are HOST pointers; blocks until the result is in host memory; bit-identical to one device. */
+int vsm_rt_column_rrs_sharded_f64(vsm_multi*, const vsm_column_desc*, const vsm_rrs_desc*, double* R_SFI, double* T_SFI,
+                                  double* ieR_SFI, double* ieT_SFI);
+
 /* device time (ms) of the most recent vsm_rt_column_* call, measured with CUDA
  * events on the context's stream; blocks until that call has finished.        */
 int vsm_last_column_ms(vsm_ctx*, float* total_ms, float* doubling_ms, float* adding_ms);

@@ -163,3 +163,21 @@ def test_rrs_workspace_limit_chunks_owner_range_bit_identically():
     ctx.close()
     for k in KEYS:
         assert np.array_equal(part[k], full[k]), k
+
+
+@pytest.mark.parametrize("devices", [[0], [0, 1]])
+def test_rrs_multi_context_in_process_equals_single(devices):
+    """vsm_rt_column_rrs_sharded_f64: several GPUs from ONE process (the Julia situation), bit-identical to one device."""
+    import torch
+    from vsmom_b200 import _lib
+    if torch.cuda.device_count() < len(devices):
+        pytest.skip("needs %d GPUs" % len(devices))
+    m, rs = _scene(nS=70, aerosol=True)
+    single = raman.rt_run_rrs(m, rs)
+    mc = _lib.MultiContext(devices)
+    try:
+        multi = raman.rt_run_rrs_multi(m, rs, mc)
+    finally:
+        mc.close()
+    for k in KEYS:
+        assert np.array_equal(multi[k], single[k]), k

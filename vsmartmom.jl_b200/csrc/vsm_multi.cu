@@ -61,7 +61,7 @@ struct vsm_multi {
     std::vector<cudaStream_t> stream;
     std::vector<ncclComm_t> comm;
     // per-device grow-only buffers: inputs (tau_rayl, tau_abs, F0, Zpp, Zmp, surf_rho), outputs, packed rows, gathered rows
-    std::vector<DBuf> tr, ta, f0, zpp, zmp, rho, out, pack, gath, thb, sif;
+    std::vector<DBuf> tr, ta, f0, zpp, zmp, rho, out, pack, gath, thb, sif, zrp, zrm;
     std::string err;
 };
 
@@ -90,7 +90,7 @@ extern "C" int vsm_multi_create(vsm_multi** out, const int* devices, int ndev) {
     m->dev.assign(devices, devices + ndev);
     m->ctx.assign(ndev, nullptr); m->stream.assign(ndev, nullptr); m->comm.assign(ndev, nullptr);
     m->tr.resize(ndev); m->ta.resize(ndev); m->f0.resize(ndev); m->zpp.resize(ndev); m->zmp.resize(ndev);
-    m->rho.resize(ndev); m->out.resize(ndev); m->pack.resize(ndev); m->gath.resize(ndev); m->thb.resize(ndev); m->sif.resize(ndev);
+    m->rho.resize(ndev); m->out.resize(ndev); m->pack.resize(ndev); m->gath.resize(ndev); m->thb.resize(ndev); m->sif.resize(ndev); m->zrp.resize(ndev); m->zrm.resize(ndev);
     for (int r = 0; r < ndev; ++r) {
         if (cudaSetDevice(devices[r]) != cudaSuccess || cudaStreamCreateWithFlags(&m->stream[r], cudaStreamNonBlocking) != cudaSuccess) {
             cudaGetLastError();
@@ -121,7 +121,7 @@ extern "C" int vsm_multi_destroy(vsm_multi* m) {
         if (m->stream[r]) cudaStreamSynchronize(m->stream[r]);
         if (m->comm[r] && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm[r]);
         if (m->ctx[r]) vsm_destroy(m->ctx[r]);
-        for (DBuf* b : {&m->tr[r], &m->ta[r], &m->f0[r], &m->zpp[r], &m->zmp[r], &m->rho[r], &m->out[r], &m->pack[r], &m->gath[r], &m->thb[r], &m->sif[r]})
+        for (DBuf* b : {&m->tr[r], &m->ta[r], &m->f0[r], &m->zpp[r], &m->zmp[r], &m->rho[r], &m->out[r], &m->pack[r], &m->gath[r], &m->thb[r], &m->sif[r], &m->zrp[r], &m->zrm[r]})
             if (b->p) cudaFree(b->p);
         if (m->stream[r]) cudaStreamDestroy(m->stream[r]);
     }
@@ -237,4 +237,81 @@ extern "C" int vsm_rt_column_sharded_f64(vsm_multi* m, const vsm_column_desc* d,
 }
 extern "C" int vsm_rt_column_sharded_f32(vsm_multi* m, const vsm_column_desc* d, float* R, float* T_, float* hdr, float* uw, float* dw) {
     return column_sharded<float>(m, d, R, T_, hdr, uw, dw, vsm_rt_column_f32, ncclFloat32);
+}
+
+// Rotational Raman from one process on several devices: every device gets the WHOLE band (the donor wavelength of a
+// coupling may lie anywhere in it) and one contiguous OWNER range of the outputs; it recomputes the elastic column of the
+// range's halo locally (vsm_rt_column_rrs_f64), so the data path has no collective; ONE ncclAllGather of the packed
+// (R | T | ieR | ieT) rows closes the call.  Host pointers in (column arrays, Z tables, Raman Z tables), host outputs.
+extern "C" int vsm_rt_column_rrs_sharded_f64(vsm_multi* m, const vsm_column_desc* d, const vsm_rrs_desc* rd, double* R, double* Tt,
+                                             double* ieR, double* ieT) {
+    using T = double;
+    if (!m) return VSM_ERR_INVALID_ARG;
+    if (!d || d->struct_size != (int)sizeof(vsm_column_desc) || !rd || rd->struct_size != (int)sizeof(vsm_rrs_desc))
+        return mfail(m, VSM_ERR_INVALID_ARG, "rt_column_rrs_sharded: descriptor NULL or struct_size mismatch");
+    if (!R || !Tt || !ieR || !ieT) return mfail(m, VSM_ERR_INVALID_ARG, "rt_column_rrs_sharded: output NULL");
+    if (!d->tau_rayl || !d->tau_abs || !d->F0 || !d->Zpp || !d->Zmp || !rd->Zpp_raman || !rd->Zmp_raman)
+        return mfail(m, VSM_ERR_INVALID_ARG, "rt_column_rrs_sharded: NULL input array");
+    const int nSpec = d->nSpec, Nz = d->Nz, nSt = d->nStokes, nV = d->nVZA, N = d->N, nM = d->n_moments, nC = d->nAer + 1;
+    if (nSpec <= 0) return VSM_OK;
+    const int nOut = nV * nSt, W = 4 * nOut;
+    const int world = m->ndev;
+    int per = 0;
+    { int a, b; shard_bounds(nSpec, world, 0, &a, &b, &per); }
+    const size_t zbytes = (size_t)N * N * nC * nM * sizeof(T), zrbytes = (size_t)N * N * nM * sizeof(T);
+    const size_t band = (size_t)nSpec * Nz * sizeof(T);
+    const bool brdf = d->surface_kind == VSM_SURFACE_BRDF_FOURIER && d->surf_rho;
+    for (int r = 0; r < world; ++r) {
+        int lo, hi;
+        shard_bounds(nSpec, world, r, &lo, &hi, nullptr);
+        const int nS = hi - lo;
+        MCK(cudaSetDevice(m->dev[r]));
+        cudaStream_t s = m->stream[r];
+        if (grow(m->pack[r], (size_t)per * W * sizeof(T)) || grow(m->gath[r], (size_t)world * per * W * sizeof(T)))
+            return mfail(m, VSM_ERR_NOMEM, "rt_column_rrs_sharded: cudaMalloc failed");
+        MCK(cudaMemsetAsync(m->pack[r].p, 0, (size_t)per * W * sizeof(T), s));
+        if (nS == 0) continue;
+        if (grow(m->tr[r], band) || grow(m->ta[r], band) || grow(m->f0[r], (size_t)nSpec * nSt * sizeof(T)) || grow(m->zpp[r], zbytes) ||
+            grow(m->zmp[r], zbytes) || grow(m->zrp[r], zrbytes) || grow(m->zrm[r], zrbytes) || grow(m->out[r], (size_t)nS * W * sizeof(T)) ||
+            (brdf && grow(m->rho[r], (size_t)N * N * nM * sizeof(T))))
+            return mfail(m, VSM_ERR_NOMEM, "rt_column_rrs_sharded: cudaMalloc failed");
+        MCK(cudaMemcpyAsync(m->tr[r].p, d->tau_rayl, band, cudaMemcpyHostToDevice, s));
+        MCK(cudaMemcpyAsync(m->ta[r].p, d->tau_abs, band, cudaMemcpyHostToDevice, s));
+        MCK(cudaMemcpyAsync(m->f0[r].p, d->F0, (size_t)nSpec * nSt * sizeof(T), cudaMemcpyHostToDevice, s));
+        MCK(cudaMemcpyAsync(m->zpp[r].p, d->Zpp, zbytes, cudaMemcpyHostToDevice, s));
+        MCK(cudaMemcpyAsync(m->zmp[r].p, d->Zmp, zbytes, cudaMemcpyHostToDevice, s));
+        MCK(cudaMemcpyAsync(m->zrp[r].p, rd->Zpp_raman, zrbytes, cudaMemcpyHostToDevice, s));
+        MCK(cudaMemcpyAsync(m->zrm[r].p, rd->Zmp_raman, zrbytes, cudaMemcpyHostToDevice, s));
+        if (brdf) MCK(cudaMemcpyAsync(m->rho[r].p, d->surf_rho, (size_t)N * N * nM * sizeof(T), cudaMemcpyHostToDevice, s));
+        vsm_column_desc dd = *d;
+        dd.tau_rayl = m->tr[r].p; dd.tau_abs = m->ta[r].p; dd.F0 = m->f0[r].p; dd.Zpp = m->zpp[r].p; dd.Zmp = m->zmp[r].p;
+        dd.surf_rho = brdf ? m->rho[r].p : nullptr;
+        vsm_rrs_desc rr = *rd;
+        rr.n1_begin = lo; rr.n1_count = nS; rr.Zpp_raman = m->zrp[r].p; rr.Zmp_raman = m->zrm[r].p;
+        T* o = (T*)m->out[r].p;
+        T* o4[4] = {o, o + (size_t)nS * nOut, o + (size_t)2 * nS * nOut, o + (size_t)3 * nS * nOut};
+        if (vsm_rt_column_rrs_f64(m->ctx[r], &dd, &rr, o4[0], o4[1], o4[2], o4[3]) != VSM_OK)
+            return mfail(m, VSM_ERR_CUDA, std::string("rt_column_rrs_sharded (device ") + std::to_string(m->dev[r]) + "): " + vsm_last_error(m->ctx[r]));
+        T* pk = (T*)m->pack[r].p;
+        for (int q = 0; q < 4; ++q)
+            MCK(cudaMemcpy2DAsync(pk + q * nOut, (size_t)W * sizeof(T), o4[q], (size_t)nOut * sizeof(T), (size_t)nOut * sizeof(T), nS, cudaMemcpyDeviceToDevice, s));
+    }
+    NCK(g_nccl.GroupStart());
+    for (int r = 0; r < world; ++r)
+        NCK(g_nccl.AllGather(m->pack[r].p, m->gath[r].p, (size_t)per * W, ncclFloat64, m->comm[r], m->stream[r]));
+    NCK(g_nccl.GroupEnd());
+    MCK(cudaSetDevice(m->dev[0]));
+    std::vector<T> host((size_t)world * per * W);
+    MCK(cudaMemcpyAsync(host.data(), m->gath[0].p, host.size() * sizeof(T), cudaMemcpyDeviceToHost, m->stream[0]));
+    for (int r = 0; r < world; ++r) { MCK(cudaSetDevice(m->dev[r])); MCK(cudaStreamSynchronize(m->stream[r])); }
+    double* outs[4] = {R, Tt, ieR, ieT};
+    for (int r = 0; r < world; ++r) {
+        int lo, hi;
+        shard_bounds(nSpec, world, r, &lo, &hi, nullptr);
+        for (int sidx = lo; sidx < hi; ++sidx) {
+            const T* row = host.data() + ((size_t)r * per + (sidx - lo)) * W;
+            for (int q = 0; q < 4; ++q) memcpy(outs[q] + (size_t)sidx * nOut, row + q * nOut, (size_t)nOut * sizeof(T));
+        }
+    }
+    return VSM_OK;
 }

@@ -131,6 +131,33 @@ def rt_run_rrs_sharded(model: RTModel, rs: RRS, ctx: Optional[_lib.Context] = No
             for i, name in enumerate(("R_SFI", "T_SFI", "ieR_SFI", "ieT_SFI"))}
 
 
+def rt_run_rrs_multi(model: RTModel, rs: RRS, mctx: "_lib.MultiContext"):
+    """``rt_run_rrs`` on several GPUs driven from THIS process (``vsm_rt_column_rrs_sharded_f64``): host arrays in, host
+    arrays out; the library gives every device of ``mctx`` one owner range and gathers with one NCCL all-gather."""
+    from .rt_run import PreparedColumn, z_tables
+    from .model import layer_control, vza_tables
+    Zpp, Zmp = z_tables(model)
+    stream, w = vza_tables(model)
+    prep = PreparedColumn(model, torch.from_numpy(Zpp), torch.from_numpy(Zmp), layer_control(model), stream,
+                          np.ascontiguousarray(w, dtype=np.float64), None, None)
+    if model.surface_rho is not None:
+        prep.surf_rho = torch.from_numpy(np.ascontiguousarray(np.asarray(model.surface_rho).transpose(0, 2, 1).astype(np.float64)))
+    nS, n, nV = model.nSpec, model.pol_n, len(model.vza)
+    tr = torch.from_numpy(np.ascontiguousarray(model.tau_rayl.T))          # HOST
+    ta = torch.from_numpy(np.ascontiguousarray(model.tau_abs.T))
+    f0 = np.zeros((nS, n)); f0[:, 0] = 1
+    d, _keep = _column_desc(prep, tr, ta, torch.from_numpy(f0))
+    zp, zm = raman_z_tables(model, rs)
+    sh = np.ascontiguousarray(rs.i_shift, np.int32)
+    wr = np.ascontiguousarray(rs.varpi_raman, np.float64)
+    rd = _lib.RrsDesc()
+    rd.struct_size, rd.n_raman, rd.n1_begin, rd.n1_count = C.sizeof(_lib.RrsDesc), int(sh.size), 0, nS
+    rd.i_shift, rd.varpi_raman, rd.Zpp_raman, rd.Zmp_raman = _i32p(sh), _f64p(wr), zp.ctypes.data, zm.ctypes.data
+    outs = [np.empty((nS, n, nV)) for _ in range(4)]
+    mctx.check(_lib.lib.vsm_rt_column_rrs_sharded_f64(mctx.handle, C.byref(d), C.byref(rd), *[o.ctypes.data for o in outs]))
+    return {k: o.transpose(2, 1, 0) for k, o in zip(("R_SFI", "T_SFI", "ieR_SFI", "ieT_SFI"), outs)}
+
+
 # ---------------------------------------------------------------------------
 # synthetic config 5 (SURVEY.md section 8: test/test_forward_raman.jl -> O2Parameters.yaml): IQU, 3 streams + VZA/SZA
 # -> N = 15, 5 layers, grid (1e7/775):0.05:(1e7/755) = 6837 points
