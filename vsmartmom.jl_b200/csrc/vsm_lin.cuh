@@ -119,6 +119,36 @@ __device__ __forceinline__ void dual_mm(const Ops& op, int P, const Dual<T>& A, 
             *e = acc ? *e + v : v;
         };
     };
+    if constexpr (Ops::kIsStream) {
+        // Streamed operands: the products of one dual product are known in advance and none of them writes an operand of
+        // another (C is distinct from A and B), so every product ANNOUNCES the next one -- its first panels are in flight
+        // while the current epilogue runs and it starts warm instead of refilling the cp.async ring from cold.
+        const int per_q = (a_const ? 0 : 1) + (b_const ? 0 : 1);
+        const int total = P * per_q + 1;
+        auto operands = [&](int k, const T*& pa, const T*& pb) {
+            if (k >= total - 1) { pa = A.f; pb = B.f; return; }
+            const int q = k / per_q;
+            const bool first_of_q = (k % per_q) == 0;
+            if (first_of_q && !a_const) { pa = A.d(q); pb = B.f; }
+            else { pa = A.f; pb = B.d(q); }
+        };
+        auto none = [](int, T) {};
+        if (per_q == 0) {
+            for (int q = 0; q < P; ++q)
+                for (int e = op.tid; e < op.N() * op.N(); e += op.nthreads()) C.d(q)[(e % op.N()) + (size_t)(e / op.N()) * ld] = T(0);
+            op.sync();
+        }
+        for (int k = 0; k < total; ++k) {
+            const T *pa, *pb, *na = nullptr, *nb = nullptr;
+            operands(k, pa, pb);
+            if (k + 1 < total) operands(k + 1, na, nb);
+            const bool last = (k == total - 1);
+            T* dst = last ? C.f : C.d(k / per_q);
+            const bool acc = last ? ACC : (ACC || (k % per_q) != 0);
+            op.template mm_stream<KSIGN, 0>(pa, pb, put(dst, acc), pa, pa, none, none, na, nb);
+            op.sync();
+        }
+    } else {
     for (int q = 0; q < P; ++q) {                         // derivatives first: they read the old forward C only if ACC
         bool first = !ACC;
         if (!a_const) { op.template mm<KSIGN>(A.d(q), B.f, put(C.d(q), !first)); first = false; op.sync(); }
@@ -130,6 +160,7 @@ __device__ __forceinline__ void dual_mm(const Ops& op, int P, const Dual<T>& A, 
     }
     op.template mm<KSIGN>(A.f, B.f, put(C.f, ACC));
     op.sync();
+    }
 }
 
 // y = A x on duals (vectors: forward at v, derivative q at v + (q+1)*vs); epi(q, i, value) with q = -1 forward
@@ -153,6 +184,27 @@ __device__ __forceinline__ void dual_inv_one_minus(const Ops& op, int P, const D
                                                    T* S1, T* S2) {
     const int ld = op.LD();
     op.inv_one_minus(A.f, B.f, G.f, S1);
+    if constexpr (Ops::kIsStream) {
+        // as in dual_mm: a product whose operands are complete is announced one product ahead (A'B -> AB', and the last
+        // product of parameter q -> the first of q+1); G S1 and S2 G read what the previous product wrote and start cold
+        auto none = [](int, T) {};
+        for (int q = 0; q < P; ++q) {
+            op.template mm_stream<false, 0>(A.d(q), B.f, [&](int i, int j, T v) { S1[i + (size_t)j * ld] = v; }, A.f, A.f, none, none,
+                                            A.f, B.d(q));
+            op.sync();
+            op.template mm_stream<false, 0>(A.f, B.d(q), [&](int i, int j, T v) { S1[i + (size_t)j * ld] += v; }, A.f, A.f, none, none,
+                                            nullptr, nullptr);
+            op.sync();
+            op.template mm_stream<false, 0>(G.f, S1, [&](int i, int j, T v) { S2[i + (size_t)j * ld] = v; }, A.f, A.f, none, none,
+                                            nullptr, nullptr);
+            op.sync();
+            T* Gq = G.d(q);
+            const bool more = q + 1 < P;
+            op.template mm_stream<false, 0>(S2, G.f, [&](int i, int j, T v) { Gq[i + (size_t)j * ld] = v; }, A.f, A.f, none, none,
+                                            more ? A.d(q + 1) : nullptr, more ? B.f : nullptr);
+            op.sync();
+        }
+    } else {
     for (int q = 0; q < P; ++q) {
         op.template mm<false>(A.d(q), B.f, [&](int i, int j, T v) { S1[i + (size_t)j * ld] = v; });
         op.sync();
@@ -163,6 +215,7 @@ __device__ __forceinline__ void dual_inv_one_minus(const Ops& op, int P, const D
         T* Gq = G.d(q);
         op.template mm<false>(S2, G.f, [&](int i, int j, T v) { Gq[i + (size_t)j * ld] = v; });
         op.sync();
+    }
     }
 }
 
@@ -313,8 +366,8 @@ constexpr int kLinLayerDuals = 7, kLinAddDuals = 13, kLinSingles = 2;
 // dual vectors per CTA (each (1+P)*vstride): layer: jp jm j1p j1m am ap + tmp ; adding: J0p J0m J0pn jp jm v1 v2 + tmp
 constexpr int kLinLayerVecs = 7, kLinAddVecs = 8;
 
-template <typename T, class Ops, int NN, int NTHR>
-__global__ void __launch_bounds__(NTHR, 1) k_layer_lin(ColArgs<T> a, LinArgs<T> l, unsigned int total) {
+template <typename T, class Ops, int NN, int NTHR, int MINB = 1>
+__global__ void __launch_bounds__(NTHR, MINB) k_layer_lin(ColArgs<T> a, LinArgs<T> l, unsigned int total) {
     const int n = NN ? NN : a.N;
     T* smv = reinterpret_cast<T*>(vsm_smem);
     Ops op;
@@ -437,8 +490,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_layer_lin(ColArgs<T> a, LinArgs<T> 
 // interaction_helper!(::ScatteringInterface_11), the surface (Lambertian with its albedo derivative, or BRDF moments),
 // and the lin postprocessing_vza!.  Only all-scattering columns (every interface _11): the host rejects others.
 // ----------------------------------------------------------------------------
-template <typename T, class Ops, int NN, int NTHR>
-__global__ void __launch_bounds__(NTHR, 1) k_adding_lin(ColArgs<T> a, LinArgs<T> l, unsigned int total) {
+template <typename T, class Ops, int NN, int NTHR, int MINB = 1>
+__global__ void __launch_bounds__(NTHR, MINB) k_adding_lin(ColArgs<T> a, LinArgs<T> l, unsigned int total) {
     const int n = NN ? NN : a.N;
     T* smv = reinterpret_cast<T*>(vsm_smem);
     Ops op;
