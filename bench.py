@@ -643,7 +643,7 @@ def run_rrs(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     nS, n, nV = m.nSpec, m.pol_n, len(m.vza)
-    bounds = shard_bounds(nS, world)
+    bounds = raman.rrs_shard_bounds(nS, rs, world)      # equal numbers of (n1, dn) units per rank
     lo, hi = bounds[rank]
     nmax = max(b[1] - b[0] for b in bounds)
     k = n * nV
@@ -734,7 +734,7 @@ def run_rrs(args):
                                        "(1e7/775):0.05:(1e7/755) cm^-1, Stokes_IQU, 3 streams + VZA + SZA (N=15), 5 layers, Rayleigh "
                                        "(Cabannes) + pseudo-line absorption, Lambertian 0.05, synthetic N2/O2 rotational line table",
                            "nSpec_total": nS, "N": N, "Nz": Nz, "n_moments": nM, "n_raman": nR, "units_rank0": units,
-                           "parallelism": f"owner-range shard x{world} (elastic halo recomputed per rank)",
+                           "parallelism": f"owner-range shard x{world}, ranges balanced by unit count (elastic halo recomputed per rank)",
                            "l2": "unit state + level records (GBs) >> 126 MB L2; a 256 MiB buffer is also rewritten between timed iterations"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": nS * args.steps / e2e_s, "unit": UNIT,

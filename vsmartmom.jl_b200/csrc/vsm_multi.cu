@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -243,6 +244,25 @@ extern "C" int vsm_rt_column_sharded_f32(vsm_multi* m, const vsm_column_desc* d,
 // coupling may lie anywhere in it) and one contiguous OWNER range of the outputs; it recomputes the elastic column of the
 // range's halo locally (vsm_rt_column_rrs_f64), so the data path has no collective; ONE ncclAllGather of the packed
 // (R | T | ieR | ieT) rows closes the call.  Host pointers in (column arrays, Z tables, Raman Z tables), host outputs.
+// owner ranges with equal numbers of (n1, dn) units (band-edge wavelengths have fewer in-band donors) -- the same rule as
+// vsmom_b200/raman.py::rrs_shard_bounds: weight(n1) = 2 + #{dn : 0 <= n1 + shift[dn] < nSpec}
+static std::vector<int> rrs_cuts(int nSpec, const vsm_rrs_desc* rd, int world) {
+    std::vector<double> c((size_t)nSpec + 1, 0.0);
+    for (int n1 = 0; n1 < nSpec; ++n1) {
+        double w = 2.0;
+        for (int k = 0; k < rd->n_raman; ++k) { const int n0 = n1 + rd->i_shift[k]; w += (n0 >= 0 && n0 < nSpec) ? 1.0 : 0.0; }
+        c[n1 + 1] = c[n1] + w;
+    }
+    std::vector<int> cuts(world + 1, nSpec);
+    cuts[0] = 0;
+    for (int r = 1; r < world; ++r) {
+        const double target = c[nSpec] * r / world;
+        cuts[r] = (int)(std::lower_bound(c.begin(), c.end(), target) - c.begin());
+        cuts[r] = std::min(std::max(cuts[r], cuts[r - 1]), nSpec);
+    }
+    return cuts;
+}
+
 extern "C" int vsm_rt_column_rrs_sharded_f64(vsm_multi* m, const vsm_column_desc* d, const vsm_rrs_desc* rd, double* R, double* Tt,
                                              double* ieR, double* ieT) {
     using T = double;
@@ -256,14 +276,15 @@ extern "C" int vsm_rt_column_rrs_sharded_f64(vsm_multi* m, const vsm_column_desc
     if (nSpec <= 0) return VSM_OK;
     const int nOut = nV * nSt, W = 4 * nOut;
     const int world = m->ndev;
-    int per = 0;
-    { int a, b; shard_bounds(nSpec, world, 0, &a, &b, &per); }
+    if (!rd->i_shift || rd->n_raman <= 0) return mfail(m, VSM_ERR_INVALID_ARG, "rt_column_rrs_sharded: shift table missing");
+    const std::vector<int> cuts = rrs_cuts(nSpec, rd, world);
+    int per = 1;
+    for (int r = 0; r < world; ++r) per = std::max(per, cuts[r + 1] - cuts[r]);
     const size_t zbytes = (size_t)N * N * nC * nM * sizeof(T), zrbytes = (size_t)N * N * nM * sizeof(T);
     const size_t band = (size_t)nSpec * Nz * sizeof(T);
     const bool brdf = d->surface_kind == VSM_SURFACE_BRDF_FOURIER && d->surf_rho;
     for (int r = 0; r < world; ++r) {
-        int lo, hi;
-        shard_bounds(nSpec, world, r, &lo, &hi, nullptr);
+        const int lo = cuts[r], hi = cuts[r + 1];
         const int nS = hi - lo;
         MCK(cudaSetDevice(m->dev[r]));
         cudaStream_t s = m->stream[r];
@@ -306,8 +327,7 @@ extern "C" int vsm_rt_column_rrs_sharded_f64(vsm_multi* m, const vsm_column_desc
     for (int r = 0; r < world; ++r) { MCK(cudaSetDevice(m->dev[r])); MCK(cudaStreamSynchronize(m->stream[r])); }
     double* outs[4] = {R, Tt, ieR, ieT};
     for (int r = 0; r < world; ++r) {
-        int lo, hi;
-        shard_bounds(nSpec, world, r, &lo, &hi, nullptr);
+        const int lo = cuts[r], hi = cuts[r + 1];
         for (int sidx = lo; sidx < hi; ++sidx) {
             const T* row = host.data() + ((size_t)r * per + (sidx - lo)) * W;
             for (int q = 0; q < 4; ++q) memcpy(outs[q] + (size_t)sidx * nOut, row + q * nOut, (size_t)nOut * sizeof(T));

@@ -109,23 +109,39 @@ def rt_run_rrs(model: RTModel, rs: RRS, ctx: Optional[_lib.Context] = None, devi
     return res
 
 
+def rrs_unit_weights(nSpec: int, rs: RRS, elastic_cost: float = 2.0) -> np.ndarray:
+    """Work per output wavelength: its number of in-band donors (get_n0_n1, inelastic_helper.jl:19-26) plus the elastic column."""
+    n1 = np.arange(nSpec)
+    w = np.full(nSpec, float(elastic_cost))
+    for s in np.asarray(rs.i_shift):
+        w += ((n1 + s >= 0) & (n1 + s < nSpec))
+    return w
+
+
+def rrs_shard_bounds(nSpec: int, rs: RRS, world: int):
+    """Owner ranges with equal numbers of (n1, dn) units per rank (band-edge wavelengths have fewer in-band donors)."""
+    from .sharding import shard_bounds_weighted
+    return shard_bounds_weighted(rrs_unit_weights(nSpec, rs), world)
+
+
 def rt_run_rrs_sharded(model: RTModel, rs: RRS, ctx: Optional[_lib.Context] = None, device: Optional[str] = None):
     """``rt_run_rrs`` with the OWNER range sharded over the ranks of the default process group (one process per
     GPU): each rank recomputes the elastic column of its halo locally (no data-path collective) and ONE all-gather
     of the packed (R | T | ieR | ieT) rows closes the run.  Every rank gets the full band."""
     import torch.distributed as dist
-    from .sharding import gather_spectral, shard_bounds
+    from .sharding import gather_spectral
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     device = device or f"cuda:{torch.cuda.current_device()}"
-    lo, hi = shard_bounds(model.nSpec, world)[rank]
+    bounds = rrs_shard_bounds(model.nSpec, rs, world)
+    lo, hi = bounds[rank]
     n, nV = model.pol_n, len(model.vza)
     if hi > lo:
         r = rt_run_rrs(model, rs, ctx, device, owner=(lo, hi))
         packed = np.concatenate([r[k].transpose(2, 1, 0).reshape(hi - lo, -1) for k in ("R_SFI", "T_SFI", "ieR_SFI", "ieT_SFI")], axis=1)
     else:
         packed = np.zeros((0, 4 * n * nV))
-    full = gather_spectral(torch.from_numpy(np.ascontiguousarray(packed)).to(device), model.nSpec, world, rank).cpu().numpy()
+    full = gather_spectral(torch.from_numpy(np.ascontiguousarray(packed)).to(device), model.nSpec, world, rank, bounds=bounds).cpu().numpy()
     k = n * nV
     return {name: full[:, i * k:(i + 1) * k].reshape(-1, n, nV).transpose(2, 1, 0)
             for i, name in enumerate(("R_SFI", "T_SFI", "ieR_SFI", "ieT_SFI"))}

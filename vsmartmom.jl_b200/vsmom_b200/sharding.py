@@ -24,12 +24,31 @@ def shard_bounds(nSpec: int, world: int, align: int = 32) -> List[Tuple[int, int
     return out
 
 
-def gather_spectral(local: torch.Tensor, nSpec: int, world: int, rank: int, align: int = 32) -> torch.Tensor:
+def shard_bounds_weighted(weights, world: int) -> List[Tuple[int, int]]:
+    """Contiguous [lo, hi) per rank with (nearly) equal total WEIGHT instead of equal length -- the Raman path, where the
+    work of an output wavelength is its number of in-band donor wavelengths (fewer near the band edges)."""
+    import numpy as np
+    w = np.asarray(weights, dtype=np.float64)
+    n = w.size
+    c = np.concatenate([[0.0], np.cumsum(w)])
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(c, c[-1] * r / world, side="left")))
+    cuts.append(n)
+    cuts = [min(max(x, 0), n) for x in cuts]
+    for i in range(1, len(cuts)):
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def gather_spectral(local: torch.Tensor, nSpec: int, world: int, rank: int, align: int = 32, bounds=None) -> torch.Tensor:
     """All-gather shards whose FIRST dimension is the spectral axis into the full
-    band (every rank gets the result).  Shards may be ragged / empty."""
+    band (every rank gets the result).  Shards may be ragged / empty.  ``bounds``: explicit [lo, hi) per rank
+    (default: ``shard_bounds``)."""
     if world == 1:
         return local
-    bounds = shard_bounds(nSpec, world, align)
+    if bounds is None:
+        bounds = shard_bounds(nSpec, world, align)
     per = max(hi - lo for lo, hi in bounds)
     pad = local.new_zeros((per,) + tuple(local.shape[1:]))
     pad[: local.shape[0]] = local
