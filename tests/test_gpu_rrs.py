@@ -181,3 +181,16 @@ def test_rrs_multi_context_in_process_equals_single(devices):
         mc.close()
     for k in KEYS:
         assert np.array_equal(multi[k], single[k]), k
+
+
+def test_rrs_no_donor_in_band_gives_elastic_only():
+    """Every Raman shift points outside a short band: no unit is valid, the inelastic outputs are exactly zero and the
+    elastic ones match the oracle (get_n0_n1 returns empty ranges, inelastic_helper.jl:19-26)."""
+    m, rs = _scene(nS=6)
+    rs = raman.RRS(np.array([-9, 7, 11], np.int32), rs.varpi_raman[:3], rs.greek_raman)
+    ref = _oracle(m, rs)
+    out = raman.rt_run_rrs(m, rs)
+    assert np.all(out["ieR_SFI"] == 0) and np.all(out["ieT_SFI"] == 0)
+    assert np.all(ref["ieR_SFI"] == 0)
+    for k in ("R_SFI", "T_SFI"):
+        assert relerr(out[k], ref[k]) <= TOL

@@ -388,6 +388,13 @@ function CoreRT.rt_run(RS_type::InelasticScattering.RRS{Float64}, model::CoreRT.
     return Array(R_d), Array(T_d), Array(ieR_d), Array(ieT_d), hdr, zeros(FT, nSpec), zeros(FT, nSpec)   # rt_run.jl:532
 end
 
+# ---- single scattering: rt_run_ss(::noRS, model, iBand) (rt_run.jl:593-755) is ONE call on the same ColumnDesc:
+#   ccall((:vsm_rt_column_ss_f64, LIB), Cint, (Ptr{Cvoid}, Ref{ColumnDesc}, CuPtr{FT}, CuPtr{FT}, CuPtr{FT}, CuPtr{FT}),
+#         CTX[], d, R_d, T_d, hemR_d, hemT_d)        # R_SFI/T_SFI (nVZA,n,nSpec), hem_R/hem_T [nSpec]
+# with `d` filled exactly as in rt_run(::noRS) above (ndoubl / scatter / iface are not read by this driver); the method
+#   CoreRT.rt_run_ss(RS_type::CoreRT.noRS{FT}, model::CoreRT.RTModel{<:Architectures.GPU,FT}, iBand; kwargs...)
+# returns (Array(R_d), Array(T_d), zeros, zeros, Array(hemR_d), Array(hemT_d)) -- rt_run.jl:754.
+#
 # ---- LinMode: vsm_rt_column_lin_f64 takes the same ColumnDesc plus
 #   mutable struct LinDesc; struct_size::Int32; n_params::Int32; dtau_aer::Ptr{Float64}; dalbedo::Ptr{Float64};
 #                           dtau_rayl::CuPtr{Cvoid}; dtau_abs::CuPtr{Cvoid}; end
