@@ -12,6 +12,7 @@ static cudaError_t le(cudaStream_t s, const Args& a, int m, int iz, int mode) {
 }
 template <int NP, int WPC>
 static cudaError_t li(cudaStream_t s, const Args& a, int m, int iz, int mode, unsigned int total) {
+    if (total == 0) return cudaSuccess;                    // no donor of this owner range lies inside the band
     const unsigned int grid = (total + WPC - 1) / WPC;
     k_rrs_inel<NP, WPC><<<grid, 32 * WPC, inel_smem<NP, WPC>(), s>>>(a, m, iz, mode, total);
     return cudaGetLastError();

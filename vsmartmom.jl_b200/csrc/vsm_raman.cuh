@@ -686,7 +686,8 @@ __global__ void __launch_bounds__(32 * WPC, (NP <= 16) ? 4 : 1) k_rrs_inel(Args 
     const unsigned int item = blockIdx.x * WPC + warp;
     if (item >= total) return;
     int dn, n1;
-    if (a.order == 0) { dn = item / a.n1cnt; n1 = a.n1lo + item % a.n1cnt; }
+    if (a.units) { const int2 un = a.units[item]; n1 = un.x; dn = un.y; }      // donor-major, valid units only
+    else if (a.order == 0) { dn = item / a.n1cnt; n1 = a.n1lo + item % a.n1cnt; }
     else { dn = item % a.nRaman; n1 = a.u_lo + (int)(item / a.nRaman) - a.shift[dn]; }
     if (n1 < a.n1lo || n1 >= a.n1lo + a.n1cnt) return;
     const int n0 = n1 + a.shift[dn];

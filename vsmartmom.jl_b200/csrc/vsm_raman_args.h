@@ -33,6 +33,7 @@ struct Args {
     int neumann;             // 1: adaptive Neumann / Gauss-Jordan inverse in the elastic column, 0: elimination only
     int order;               // unit enumeration: 0 = dn-major (n1 fastest), 1 = donor-major (dn fastest)
     int u_lo, u_n0cnt;       // donor-major enumeration: n0 in [u_lo, u_lo + u_n0cnt)
+    const int2* units;       // order 1: the valid (n1, dn) units of the owner range sorted by donor wavelength (host-built), or null
     double mu0;
     const double* mu; const double* wt; const double* sgn;     // [NP] (sgn: +1 I,Q rows / -1 U,V rows; pad +1)
     const int* shift; const double* wR;                        // [nRaman]
