@@ -117,3 +117,37 @@ def test_rossli_fourier_moments_match_oracle_restatement():
     # isotropic only == Lambertian: 2*fiso at m = 0
     iso = vb.rossli_surface_rho(m.quad_points, m.pol_n, 2, fiso=0.25, fvol=0.0, fgeo=0.0)
     assert np.allclose(iso[0, ::2, ::2], 0.5, atol=1e-13) and np.abs(iso[1:]).max() < 1e-13
+
+
+# ---- Raman host logic (vsmom_b200/raman.py)
+def test_raman_host_helpers():
+    from vsmom_b200 import raman
+    rs = raman.synthetic_rrs()
+    # normalize_raman_weights! (Inelastic/types.jl:625-629): the weights sum to the Raman fraction 1 - ϖ_Cabannes
+    assert abs(rs.varpi_raman.sum() - 0.04) < 1e-15 and np.all(rs.varpi_raman > 0)
+    assert len(set(rs.i_shift.tolist())) == len(rs.i_shift) and 0 not in rs.i_shift
+    assert rs.i_shift.min() < 0 < rs.i_shift.max()                 # Stokes and anti-Stokes branches
+    g = raman.get_greek_raman(0.75 * 0.1)                          # inelastic_helper.jl:862-880
+    assert g.beta[0] == 1.0 and g.alpha[2] == pytest.approx(3 * (1 - 0.075) / (1 + 0.0375))
+    m = raman.synthetic_rrs_model(nSpec=50)
+    assert m.quad_points.qp_muN.size == 15 and m.Nz == 5 and m.m_max == 2      # config 5 shape
+    zp, zm = raman.raman_z_tables(m, rs)
+    assert zp.shape == (3, 15, 15) and zm.shape == (3, 15, 15)
+
+
+def test_raman_owner_ranges_are_balanced_by_units():
+    from vsmom_b200 import raman
+    rs = raman.synthetic_rrs()
+    n = 6837
+    w = raman.rrs_unit_weights(n, rs)
+    for world in (1, 2, 3, 8):
+        b = raman.rrs_shard_bounds(n, rs, world)
+        assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+        loads = [w[lo:hi].sum() for lo, hi in b]
+        assert max(loads) - min(loads) <= 2 * w.max()              # equal up to one wavelength's worth of units
+    # band-edge wavelengths have fewer in-band donors -> the edge ranges are longer
+    b8 = raman.rrs_shard_bounds(n, rs, 8)
+    assert (b8[0][1] - b8[0][0]) > (b8[3][1] - b8[3][0])
+    # degenerate: more ranks than points still covers the band
+    b = raman.rrs_shard_bounds(3, rs, 8)
+    assert b[0][0] == 0 and b[-1][1] == 3 and all(lo <= hi for lo, hi in b)
