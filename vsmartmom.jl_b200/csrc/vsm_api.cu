@@ -170,7 +170,8 @@ extern "C" int vsm_destroy(vsm_ctx* ctx) {
     if (!ctx) return VSM_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->consts, &ctx->props, &ctx->added, &ctx->slabs, &ctx->partial, &ctx->counter, &ctx->l0tmp, &ctx->geom, &ctx->surfpad, &ctx->linprops};
+    DevBuf* bufs[] = {&ctx->consts, &ctx->props, &ctx->added, &ctx->slabs, &ctx->partial, &ctx->counter, &ctx->l0tmp, &ctx->geom, &ctx->surfpad, &ctx->linprops,
+                      &ctx->rrs, &ctx->rrsunits, &ctx->padtab};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->stage) cudaFreeHost(ctx->stage);
