@@ -260,6 +260,14 @@ int vsm_rt_column_rrs_f64(vsm_ctx*, const vsm_column_desc*, const vsm_rrs_desc*,
 int vsm_rt_column_ss_f64(vsm_ctx*, const vsm_column_desc*, double* R_SFI, double* T_SFI, double* hem_R, double* hem_T);
 int vsm_rt_column_ss_f32(vsm_ctx*, const vsm_column_desc*, float* R_SFI, float* T_SFI, float* hem_R, float* hem_T);
 
+/* The same driver with rotational Raman: rt_run_ss(RS_type::RRS, model, iBand) -- rt_kernel_ss!(::RRS)
+ * (CoreKernel/rt_kernel_ss.jl:240-331: elemental_inelastic! and elemental! of the whole layer with ndoubl = 0) and
+ * interaction_ss! / get_interaction_ss_RRS! (CoreKernel/interaction_ss.jl:14-19, 70-90).  The rrs descriptor as for
+ * vsm_rt_column_rrs_f64 with the owner range = the whole band (n1_begin = 0, n1_count = nSpec).  Outputs: device,
+ * R_SFI/T_SFI/ieR_SFI/ieT_SFI (nVZA,nStokes,nSpec), hem_R/hem_T [nSpec] (may be NULL). */
+int vsm_rt_column_ss_rrs_f64(vsm_ctx*, const vsm_column_desc*, const vsm_rrs_desc*, double* R_SFI, double* T_SFI,
+                             double* ieR_SFI, double* ieT_SFI, double* hem_R, double* hem_T);
+
 /* -- several GPUs from ONE host process (the reference drives everything from a single Julia process and has no
  * multi-GPU path: Architectures.jl:42-45 "Run on a single NVIDIA CUDA GPU").  vsm_multi_create opens one context
  * (own stream) per listed device and an in-process NCCL communicator over them (ncclCommInitAll; NCCL is loaded

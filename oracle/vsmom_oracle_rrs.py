@@ -438,3 +438,57 @@ def rt_run_rrs_points(model: Model, rrs: RRS, idx, F0=None):
             res["R_SFI"][:, :, q] = out["R_SFI"][:, :, 2 * u]
             res["T_SFI"][:, :, q] = out["T_SFI"][:, :, 2 * u]
     return res
+
+
+# --------------------------------------------------------------------------
+# rt_run_ss(::RRS, model, iBand)   rt_run.jl:593-755 with rt_kernel_ss!(::RRS) CoreKernel/rt_kernel_ss.jl:240-331 (elemental_inelastic!
+# and elemental! of the WHOLE layer with ndoubl = 0) and interaction_ss! / get_interaction_ss_RRS! (CoreKernel/interaction_ss.jl:14-19, 70-90)
+# --------------------------------------------------------------------------
+def rt_run_ss_rrs(model: Model, rrs: RRS):
+    """Single-scattering driver with rotational Raman: dict(R_SFI, T_SFI, ieR_SFI, ieT_SFI, hem_R, hem_T)."""
+    FT = model.FT
+    q = model.quad
+    pol_n = model.pol_n
+    nS = model.nSpec
+    nV = len(model.vza)
+    nR = len(rrs.i_shift)
+    mu = q.qp_muN.astype(FT)
+    el = orc.rt_run_ss(model)
+    ieR = np.zeros((nV, pol_n, nS), FT)
+    ieT = np.zeros((nV, pol_n, nS), FT)
+    F0 = model.F0
+    if F0 is None:
+        F0 = np.zeros((pol_n, nS), FT)
+        F0[0, :] = 1
+    fsc = fscatt_rayleigh(model)
+    valid = np.zeros((nR, nS), bool)
+    for dn in range(nR):
+        _, s1 = get_n0_n1(nS, int(rrs.i_shift[dn]))
+        valid[dn, s1] = True
+    for m in range(model.m_max + 1):
+        weight = FT(0.5 / math.pi) if m == 0 else FT(1.0 / math.pi)
+        Zpp_r, Zmp_r = orc.compute_Z_moments(pol_n, q.qp_mu, rrs.greek_raman, m, FT)
+        ctl = orc.band_control(model, m)
+        props = orc.construct_core_optical_properties(model, m)
+        Jp = Jm = None
+        for iz in range(model.Nz):
+            tau = np.broadcast_to(props[iz].tau, (nS,)).astype(FT)
+            tsum = ctl.tau_sum[:, iz]
+            _, _, _, _, jp, jm = elemental_inelastic(model, rrs, m, 0, tau, fsc[:, iz], tsum, F0, Zpp_r, Zmp_r)
+            if iz == 0:
+                Jp, Jm = jp.copy(), jm.copy()
+            else:                                          # get_interaction_ss_RRS!: attenuation at the OUTPUT wavelength n1
+                upd_p = Jp * np.exp(-tau[None, :, None] / mu[None, None, :]) + jp
+                upd_m = Jm + jm * np.exp(-tsum[None, :, None] / mu[None, None, :])
+                Jp = np.where(valid[:, :, None], upd_p, Jp)
+                Jm = np.where(valid[:, :, None], upd_m, Jm)
+        for i in range(nV):
+            imu = nearest_point(q.qp_mu, FT(cosd(model.vza[i])))
+            ist = imu * pol_n
+            c = cosd(m * model.vaz[i])
+            sn = sind(m * model.vaz[i])
+            wv = (weight * np.array([c, c, sn, sn][:pol_n])).astype(FT)
+            for dn in range(nR):
+                ieR[i] += wv[:, None] * Jm[dn, :, ist:ist + pol_n].T
+                ieT[i] += wv[:, None] * Jp[dn, :, ist:ist + pol_n].T
+    return dict(R_SFI=el["R_SFI"], T_SFI=el["T_SFI"], ieR_SFI=ieR, ieT_SFI=ieT, hem_R=el["hem_R"], hem_T=el["hem_T"])

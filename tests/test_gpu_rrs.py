@@ -194,3 +194,19 @@ def test_rrs_no_donor_in_band_gives_elastic_only():
     assert np.all(ref["ieR_SFI"] == 0)
     for k in ("R_SFI", "T_SFI"):
         assert relerr(out[k], ref[k]) <= TOL
+
+
+@pytest.mark.parametrize("aerosol", [False, True])
+def test_rt_run_ss_rrs_matches_oracle(aerosol):
+    """Single scattering with rotational Raman (rt_run_ss(::RRS)): all six outputs vs the oracle; SS inelastic <= full inelastic."""
+    import vsmom_oracle as orc
+    import vsmom_oracle_rrs as orr
+    m, rs = _scene(aerosol=aerosol, seed=13)
+    g = rs.greek_raman
+    og = orc.GreekCoefs(*(np.asarray(x, float) for x in (g.alpha, g.beta, g.gamma, g.delta, g.epsilon, g.zeta)))
+    ref = orr.rt_run_ss_rrs(to_oracle(m), orr.RRS(np.asarray(rs.i_shift), np.asarray(rs.varpi_raman), og))
+    out = raman.rt_run_ss_rrs(m, rs)
+    for k in ("R_SFI", "T_SFI", "ieR_SFI", "ieT_SFI", "hem_R", "hem_T"):
+        assert relerr(out[k], ref[k]) <= TOL, (k, relerr(out[k], ref[k]))
+    full = raman.rt_run_rrs(m, rs)
+    assert np.all(out["ieR_SFI"][:, 0] <= full["ieR_SFI"][:, 0] * (1 + 1e-9) + 1e-14)

@@ -157,3 +157,27 @@ def test_pointwise_evaluation_equals_full_band():
     part = rrs.rt_run_rrs_points(m, r, idx)
     for k in full:
         np.testing.assert_allclose(part[k], full[k][:, :, idx], rtol=1e-11, atol=1e-16)
+
+
+def test_single_scatter_rrs_closure_and_thin_limit():
+    """rt_run_ss(::RRS): (i) in the flat-spectrum case elastic + inelastic single scattering equals the elastic single
+    scattering of the mixed phase matrix EXACTLY (single scattering is linear in the phase matrix: no O(eps^2) remainder);
+    (ii) for a thin atmosphere the inelastic part converges to the full RRS solution (gap linear in the optical depth)."""
+    eps = 2e-2
+    m = _flat_model(eps, albedo=0.0, tau=0.02)
+    gr = rrs.get_greek_raman(0.1)
+    r = rrs.RRS(SHIFTS, rrs.normalize_raman_weights(WEIGHTS, 1.0 - eps), gr)
+    ss = rrs.rt_run_ss_rrs(m, r)
+    tot = _flat_model(eps, albedo=0.0, tau=0.02, greek_cab=_greek_mix(m.greek_rayleigh, gr, eps))
+    tot.varpi_cabannes = 1.0
+    ref = orc.rt_run_ss(tot)
+    inner = slice(4, m.nSpec - 4)
+    for a, b in (("R_SFI", "ieR_SFI"), ("T_SFI", "ieT_SFI")):
+        np.testing.assert_allclose(ss[a][:, :, inner] + ss[b][:, :, inner], ref[a][:, :, inner], rtol=1e-11, atol=1e-16)
+    gaps = []
+    for tau in (4e-3, 2e-3):
+        mm = _flat_model(eps, albedo=0.0, tau=tau)
+        full = rrs.rt_run_rrs(mm, r)
+        s1 = rrs.rt_run_ss_rrs(mm, r)
+        gaps.append(np.max(np.abs(full["ieR_SFI"][:, 0, inner] - s1["ieR_SFI"][:, 0, inner]) / np.abs(full["ieR_SFI"][:, 0, inner])))
+    assert gaps[0] < 5e-2 and 1.6 < gaps[0] / gaps[1] < 2.4, gaps

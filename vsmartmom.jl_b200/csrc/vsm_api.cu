@@ -1453,6 +1453,89 @@ static int rt_column_ss_impl(vsm_ctx* ctx, const vsm_column_desc* d, T* R_SFI, T
 extern "C" int vsm_rt_column_ss_f64(vsm_ctx* c, const vsm_column_desc* d, double* R, double* T_, double* hR, double* hT) { return rt_column_ss_impl<double>(c, d, R, T_, hR, hT); }
 extern "C" int vsm_rt_column_ss_f32(vsm_ctx* c, const vsm_column_desc* d, float* R, float* T_, float* hR, float* hT) { return rt_column_ss_impl<float>(c, d, R, T_, hR, hT); }
 
+// ----------------------------------------------------------------------------------------------------------------
+// L2, single scattering with rotational Raman: rt_run_ss(::RRS, model, iBand) rt_run.jl:593-755
+// ----------------------------------------------------------------------------------------------------------------
+static int rt_column_ss_rrs_impl(vsm_ctx* ctx, const vsm_column_desc* d, const vsm_rrs_desc* rd, double* R_SFI, double* T_SFI,
+                                 double* ieR_SFI, double* ieT_SFI, double* hem_R, double* hem_T) {
+    using T = double;
+    if (!ctx) return VSM_ERR_INVALID_ARG;
+    if (!rd || rd->struct_size != (int)sizeof(vsm_rrs_desc) || rd->n_raman <= 0 || !rd->i_shift || !rd->varpi_raman || !rd->Zpp_raman ||
+        !rd->Zmp_raman)
+        return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_ss_rrs: rrs descriptor NULL / incomplete");
+    if (!ieR_SFI || !ieT_SFI) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_ss_rrs: output NULL");
+    if (!d) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_ss_rrs: descriptor NULL");
+    if (rd->n1_begin != 0 || rd->n1_count != d->nSpec)
+        return fail(ctx, VSM_ERR_UNSUPPORTED, "rt_column_ss_rrs: the owner range must be the whole band");
+    // elastic single scattering (validates the column descriptor; leaves tau / tau_sum of the band in ctx->props)
+    int rc = rt_column_ss_impl<T>(ctx, d, R_SFI, T_SFI, hem_R, hem_T);
+    if (rc) return rc;
+    const int N = d->N, nSt = d->nStokes, Nz = d->Nz, nAer = d->nAer, nV = d->nVZA, nM = d->n_moments, nBand = d->nSpec, nR = rd->n_raman;
+    if (nBand == 0) return VSM_OK;
+    const size_t nOut = (size_t)nV * nSt;
+    // constants of this stage + fScattRayleigh in the Raman workspace (ctx->consts is still read by the elastic kernels)
+    std::vector<T> fT;
+    std::vector<int> fI;
+    for (int i = 0; i < N; ++i) fT.push_back(d->mu[i]);
+    const size_t o_wR = fT.size();
+    for (int k = 0; k < nR; ++k) fT.push_back(rd->varpi_raman[k]);
+    const size_t o_tm = fT.size();
+    std::vector<T> taumod((size_t)std::max(1, nAer * Nz));
+    for (int c = 0; c < nAer; ++c)
+        for (int iz = 0; iz < Nz; ++iz) taumod[c + (size_t)nAer * iz] = (T(1) - d->aer_ft[c] * d->aer_omega[c]) * d->tau_aer[c + (size_t)nAer * iz];
+    for (T v : taumod) fT.push_back(v);
+    const size_t o_vw = fT.size();
+    for (size_t i = 0; i < (size_t)nSt * nV * nM; ++i) fT.push_back(d->vza_weight[i]);
+    for (int k = 0; k < nR; ++k) fI.push_back(rd->i_shift[k]);
+    const size_t o_vrow = fI.size();
+    for (int i = 0; i < nV; ++i) fI.push_back((d->vza_stream[i] - 1) * nSt);
+    const size_t bytesT = ((fT.size() * sizeof(T)) + 15) & ~size_t(15), bytesI = ((fI.size() * sizeof(int)) + 15) & ~size_t(15);
+    const size_t fsc_bytes = (size_t)Nz * nBand * sizeof(T);
+    if ((rc = ensure(ctx, ctx->rrs, bytesT + bytesI + fsc_bytes + 64))) return rc;
+    if (ctx->stage_cap < bytesT + bytesI) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->stage) { cudaFreeHost(ctx->stage); ctx->stage = nullptr; ctx->stage_cap = 0; }
+        CK(cudaMallocHost(&ctx->stage, (bytesT + bytesI) * 2));
+        ctx->stage_cap = (bytesT + bytesI) * 2;
+    }
+    CK(cudaEventSynchronize(ctx->stage_done));               // the elastic stage's constant upload has left the pinned buffer
+    memcpy(ctx->stage, fT.data(), fT.size() * sizeof(T));
+    memcpy((char*)ctx->stage + bytesT, fI.data(), fI.size() * sizeof(int));
+    CK(cudaMemcpyAsync(ctx->rrs.p, ctx->stage, bytesT + bytesI, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->stage_done, ctx->stream));
+    const T* cT = (const T*)ctx->rrs.p;
+    const int* cI = (const int*)((char*)ctx->rrs.p + bytesT);
+    T* fsc = (T*)((char*)ctx->rrs.p + bytesT + bytesI);
+    CK(rrs::launch_fscatt(ctx->stream, nBand, Nz, nAer, (size_t)nBand, (const T*)d->tau_rayl, cT + o_tm, fsc));
+    ctx->launches++;
+    const size_t out_bytes = nOut * nBand * sizeof(T);
+    CK(cudaMemsetAsync(ieR_SFI, 0, out_bytes, ctx->stream));
+    CK(cudaMemsetAsync(ieT_SFI, 0, out_bytes, ctx->stream));
+    const T* pw = (const T*)ctx->props.p;                     // k_props layout of rt_column_ss_impl: tau | varpi | tausum | W
+    rrs::SsArgs a;
+    memset(&a, 0, sizeof a);
+    a.N = N; a.nStokes = nSt; a.Nz = Nz; a.nVZA = nV; a.nBand = nBand; a.nRaman = nR; a.istart = (d->imu0 - 1) * nSt;
+    a.mu = cT; a.shift = cI; a.wR = cT + o_wR;
+    a.p_tau = pw; a.p_tausum = pw + (size_t)2 * Nz * nBand; a.fsc = fsc;
+    a.ZppR = (const T*)rd->Zpp_raman; a.ZmpR = (const T*)rd->Zmp_raman;
+    a.F0 = (const T*)d->F0;
+    a.vza_row = cI + o_vrow; a.vza_w = cT + o_vw;
+    a.ieR = ieR_SFI; a.ieT = ieT_SFI;
+    for (int m = 0; m < nM; ++m) {
+        CK(rrs::launch_ss_rrs(ctx->stream, a, m, (unsigned int)nBand));
+        ctx->launches++;
+    }
+    GET_EVENT(ev_end2);
+    CK(cudaEventRecord(ev_end2, ctx->stream));
+    ctx->ev[1] = ev_end2;
+    return VSM_OK;
+}
+
+extern "C" int vsm_rt_column_ss_rrs_f64(vsm_ctx* c, const vsm_column_desc* d, const vsm_rrs_desc* r, double* R, double* T_, double* ieR,
+                                        double* ieT, double* hR, double* hT) {
+    return rt_column_ss_rrs_impl(c, d, r, R, T_, ieR, ieT, hR, hT);
+}
+
 extern "C" int vsm_last_column_ms(vsm_ctx* ctx, float* total_ms, float* doubling_ms, float* adding_ms) {
     if (!ctx) return VSM_ERR_INVALID_ARG;
     if (!ctx->timing_valid) return fail(ctx, VSM_ERR_INVALID_ARG, "vsm_last_column_ms: no column call yet");

@@ -35,6 +35,10 @@ cudaError_t launch_fscatt(cudaStream_t s, int nE, int Nz, int nAer, size_t ldspe
     k_rrs_fscatt<<<(nE + 127) / 128, 128, 0, s>>>(nE, Nz, nAer, ldspec, tau_rayl, aer_tau_mod, fsc);
     return cudaGetLastError();
 }
+cudaError_t launch_ss_rrs(cudaStream_t s, const SsArgs& a, int m, unsigned int nBand) {
+    k_ss_rrs<<<(nBand + 3) / 4, 128, 0, s>>>(a, m, nBand);
+    return cudaGetLastError();
+}
 cudaError_t launch_reduce(cudaStream_t s, const Args& a, double* ieR, double* ieT, int* nonfinite) {
     const size_t tot = (size_t)a.n1cnt * a.nVZA * a.nStokes;
     k_rrs_reduce<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(a, ieR, ieT, nonfinite);

@@ -1206,6 +1206,73 @@ static __global__ void k_rrs_reduce(Args a, double* __restrict__ ieR, double* __
     if (nonfinite && (!isfinite(ieR[e]) || !isfinite(ieT[e]) || !isfinite(a.R_SFI[e]) || !isfinite(a.T_SFI[e]))) atomicAdd(nonfinite, 1);
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// single scattering with rotational Raman: rt_kernel_ss!(::RRS) (CoreKernel/rt_kernel_ss.jl:240-331: elemental_inelastic! of the
+// WHOLE layer with ndoubl = 0) + get_interaction_ss_RRS! (CoreKernel/interaction_ss.jl:70-90).  Only source vectors: one warp
+// per (output wavelength, moment), lanes over the stream rows, the Raman lines in the reference's order.
+// ----------------------------------------------------------------------------------------------------------------
+
+static __global__ void __launch_bounds__(128) k_ss_rrs(SsArgs a, int m, unsigned int total) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned int n1 = blockIdx.x * 4 + warp;
+    if (n1 >= total) return;
+    const int n = a.N;
+    const double wsc = (m == 0) ? 0.5 : 0.25;
+    const double* Zpp = a.ZppR + (size_t)m * n * n;
+    const double* Zmp = a.ZmpR + (size_t)m * n * n;
+    const double mus = a.mu[a.istart];
+    const int nOut = a.nVZA * a.nStokes;
+    for (int i = lane; i < n; i += 32) {
+        const double mui = a.mu[i];
+        const bool insun = (i >= a.istart && i < a.istart + a.nStokes);
+        double sumP = 0.0, sumM = 0.0;
+        for (int dn = 0; dn < a.nRaman; ++dn) {
+            const int n0 = (int)n1 + a.shift[dn];
+            if (n0 < 0 || n0 >= a.nBand) continue;
+            double zpI = 0.0, zmI = 0.0;
+            for (int s = 0; s < a.nStokes; ++s) {
+                const double f0 = a.F0[s + (size_t)a.nStokes * n0];
+                zpI = fma(Zpp[i + (size_t)(a.istart + s) * n], f0, zpI);
+                zmI = fma(Zmp[i + (size_t)(a.istart + s) * n], f0, zmI);
+            }
+            double Jp = 0.0, Jm = 0.0;
+            for (int iz = 0; iz < a.Nz; ++iz) {
+                const double d1 = a.p_tau[(size_t)iz * a.nBand + n1], d0 = a.p_tau[(size_t)iz * a.nBand + n0];
+                const double fw = a.fsc[(size_t)iz * a.nBand + n0] * a.wR[dn];
+                const double ratio = d1 / d0;
+                double vp;
+                if (insun) {
+                    if (fabs(d0 - d1) > kCloseTol) vp = fw * zpI * wsc * expdiff_neg<double>(d1 / mui, d0 / mui) / (1.0 - ratio);
+                    else vp = (d0 / mui) * wsc * fw * zpI * exp(-d0 / mui);
+                } else if (fabs((mui / mus) - ratio) < kCloseTol) {
+                    vp = (d0 / mui) * wsc * fw * zpI * exp(-d0 / mus);
+                } else {
+                    vp = wsc * fw * zpI * (1.0 / ((mui / mus) - ratio)) * expdiff_neg<double>(d1 / mui, d0 / mus);
+                }
+                double vm = wsc * fw * zmI * (1.0 / ((mui / mus) + ratio)) * (-expm1(-((d1 / mui) + (d0 / mus))));
+                const double att = exp(-a.p_tausum[(size_t)iz * a.nBand + n0] / mus);
+                vp *= att;
+                vm *= att;
+                if (iz == 0) { Jp = vp; Jm = vm; }
+                else {
+                    Jp = Jp * exp(-d1 / mui) + vp;
+                    Jm = Jm + vm * exp(-a.p_tausum[(size_t)iz * a.nBand + n1] / mui);
+                }
+            }
+            sumP += Jp;
+            sumM += Jm;
+        }
+        for (int iv = 0; iv < a.nVZA; ++iv) {
+            const int s = i - a.vza_row[iv];
+            if (s >= 0 && s < a.nStokes) {
+                const double w = a.vza_w[s + a.nStokes * (iv + (size_t)a.nVZA * m)];
+                a.ieR[(size_t)n1 * nOut + iv + a.nVZA * s] += w * sumM;
+                a.ieT[(size_t)n1 * nOut + iv + a.nVZA * s] += w * sumP;
+            }
+        }
+    }
+}
+
 template <int NP, int WPC>
 constexpr size_t elastic_smem() { return (size_t)WPC * (5 * Geo<NP>::MS + 12 * NP) * sizeof(double) + 64; }
 template <int NP, int WPC>

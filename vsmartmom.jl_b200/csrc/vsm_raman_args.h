@@ -66,6 +66,19 @@ struct Desc {
 const Desc* desc(int N);          // nullptr when N is not covered (N > 48)
 cudaError_t launch_fscatt(cudaStream_t, int nE, int Nz, int nAer, size_t ldspec, const double* tau_rayl,
                           const double* aer_tau_mod, double* fsc);
+// argument block of the Raman single-scattering kernel (k_ss_rrs)
+struct SsArgs {
+    int N, nStokes, Nz, nVZA, nBand, nRaman, istart;
+    const double* mu;                            // [N]
+    const int* shift; const double* wR;          // [nRaman]
+    const double* p_tau; const double* p_tausum; // [iz*nBand + n]
+    const double* fsc;                           // [iz*nBand + n]
+    const double* ZppR; const double* ZmpR;      // (N,N,nM)
+    const double* F0;                            // (nStokes, nBand)
+    const int* vza_row; const double* vza_w;     // [nVZA] ; (nStokes,nVZA,nM)
+    double* ieR; double* ieT;                    // (nVZA,nStokes,nBand), accumulated over m
+};
+cudaError_t launch_ss_rrs(cudaStream_t, const SsArgs&, int m, unsigned int nBand);
 cudaError_t launch_reduce(cudaStream_t, const Args&, double* ieR, double* ieT, int* nonfinite);
 
 }  // namespace rrs

@@ -63,7 +63,7 @@ EXPORTS = [
     "vsm_batched_mul_f64", "vsm_batched_mul_f32", "vsm_batch_inv_f64", "vsm_batch_inv_f32",
     "vsm_batch_solve_f64", "vsm_batch_solve_f32",
     "vsm_rt_layer_f64", "vsm_rt_layer_f32", "vsm_rt_column_f64", "vsm_rt_column_f32",
-    "vsm_rt_column_streams_f64", "vsm_rt_column_streams_f32", "vsm_rt_column_lin_f64", "vsm_rt_column_rrs_f64", "vsm_rt_column_ss_f64", "vsm_rt_column_ss_f32",
+    "vsm_rt_column_streams_f64", "vsm_rt_column_streams_f32", "vsm_rt_column_lin_f64", "vsm_rt_column_rrs_f64", "vsm_rt_column_ss_f64", "vsm_rt_column_ss_f32", "vsm_rt_column_ss_rrs_f64",
     "vsm_last_column_ms", "vsm_last_column_launches", "vsm_last_column_status",
     "vsm_multi_create", "vsm_multi_destroy", "vsm_multi_last_error", "vsm_multi_ndev", "vsm_multi_ctx",
     "vsm_rt_column_sharded_f64", "vsm_rt_column_sharded_f32", "vsm_rt_column_rrs_sharded_f64",
@@ -106,6 +106,7 @@ lib.vsm_multi_ctx.restype = c_void_p
 for _s in ("f64", "f32"):
     getattr(lib, f"vsm_rt_column_sharded_{_s}").argtypes = [c_void_p, C.POINTER(ColumnDesc)] + [c_void_p] * 5
 
+lib.vsm_rt_column_ss_rrs_f64.argtypes = [c_void_p, C.POINTER(ColumnDesc), C.POINTER(RrsDesc)] + [c_void_p] * 6
 lib.vsm_rt_column_rrs_sharded_f64.argtypes = [c_void_p, C.POINTER(ColumnDesc), C.POINTER(RrsDesc)] + [c_void_p] * 4
 
 

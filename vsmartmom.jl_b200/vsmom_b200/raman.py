@@ -100,10 +100,45 @@ def rt_run_rrs(model: RTModel, rs: RRS, ctx: Optional[_lib.Context] = None, devi
         else:
             f0 = np.ascontiguousarray(np.asarray(F0, np.float64).T)
         zp, zm = raman_z_tables(model, rs)
-        outs = rrs_column_device(ctx, prep, rs, tr, ta, torch.from_numpy(f0).to(device), torch.from_numpy(zp).to(device),
-                                 torch.from_numpy(zm).to(device), lo, hi - lo)
+        f0_d, zp_d, zm_d = torch.from_numpy(f0).to(device), torch.from_numpy(zp).to(device), torch.from_numpy(zm).to(device)
+        outs = rrs_column_device(ctx, prep, rs, tr, ta, f0_d, zp_d, zm_d, lo, hi - lo)     # inputs stay alive until the sync
         ctx.synchronize()
         res = {k: o.cpu().numpy().transpose(2, 1, 0) for k, o in zip(("R_SFI", "T_SFI", "ieR_SFI", "ieT_SFI"), outs)}
+    if own:
+        ctx.close()
+    return res
+
+
+def rt_run_ss_rrs(model: RTModel, rs: RRS, ctx: Optional[_lib.Context] = None, device: str = "cuda:0"):
+    """Single-scattering driver with rotational Raman, the reference's ``rt_run_ss(RS_type::RRS, model, iBand)``
+    (rt_run.jl:593-755): ``R_SFI``, ``T_SFI``, ``ieR_SFI``, ``ieT_SFI`` (nVZA, pol_n, nSpec), ``hem_R``, ``hem_T`` (nSpec,)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("vsmom_b200.rt_run_ss_rrs needs a CUDA device (B200); there is no CPU fallback")
+    own = ctx is None
+    if own:
+        ctx = _lib.Context(torch.device(device).index or 0)
+    prep = prepare(model, device)
+    nS, n, nV = model.nSpec, model.pol_n, len(model.vza)
+    with torch.cuda.device(device):
+        tr = torch.from_numpy(np.ascontiguousarray(model.tau_rayl.T)).to(device)
+        ta = torch.from_numpy(np.ascontiguousarray(model.tau_abs.T)).to(device)
+        f0 = np.zeros((nS, n)); f0[:, 0] = 1
+        f0_d = torch.from_numpy(f0).to(device)            # (kept alive: the descriptor holds its raw pointer)
+        d, _keep = _column_desc(prep, tr, ta, f0_d)
+        zp, zm = raman_z_tables(model, rs)
+        zp_d, zm_d = torch.from_numpy(zp).to(device), torch.from_numpy(zm).to(device)
+        sh = np.ascontiguousarray(rs.i_shift, np.int32)
+        wr = np.ascontiguousarray(rs.varpi_raman, np.float64)
+        rd = _lib.RrsDesc()
+        rd.struct_size, rd.n_raman, rd.n1_begin, rd.n1_count = C.sizeof(_lib.RrsDesc), int(sh.size), 0, nS
+        rd.i_shift, rd.varpi_raman, rd.Zpp_raman, rd.Zmp_raman = _i32p(sh), _f64p(wr), zp_d.data_ptr(), zm_d.data_ptr()
+        outs = [torch.empty((nS, n, nV), dtype=torch.float64, device=device) for _ in range(4)]
+        hR = torch.empty((nS,), dtype=torch.float64, device=device); hT = torch.empty_like(hR)
+        ctx.check(_lib.lib.vsm_rt_column_ss_rrs_f64(ctx.handle, C.byref(d), C.byref(rd), *[o.data_ptr() for o in outs],
+                                                    hR.data_ptr(), hT.data_ptr()))
+        ctx.synchronize()
+        res = {k: o.cpu().numpy().transpose(2, 1, 0) for k, o in zip(("R_SFI", "T_SFI", "ieR_SFI", "ieT_SFI"), outs)}
+        res["hem_R"], res["hem_T"] = hR.cpu().numpy(), hT.cpu().numpy()
     if own:
         ctx.close()
     return res

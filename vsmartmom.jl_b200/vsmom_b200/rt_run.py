@@ -222,7 +222,8 @@ def rt_run_ss(model: RTModel, ctx: Optional[_lib.Context] = None, device: str = 
         tr = torch.from_numpy(np.ascontiguousarray(model.tau_rayl.T)).to(device)
         ta = torch.from_numpy(np.ascontiguousarray(model.tau_abs.T)).to(device)
         f0 = np.zeros((nS, n), FT); f0[:, 0] = 1
-        d, _keep = _column_desc(prep, tr, ta, torch.from_numpy(f0).to(device))
+        f0_d = torch.from_numpy(f0).to(device)            # (kept alive: the descriptor holds its raw pointer)
+        d, _keep = _column_desc(prep, tr, ta, f0_d)
         R = torch.empty((nS, n, nV), dtype=dt, device=device); T = torch.empty_like(R)
         hR = torch.empty((nS,), dtype=dt, device=device); hT = torch.empty_like(hR)
         fn = _lib.lib.vsm_rt_column_ss_f64 if FT == np.float64 else _lib.lib.vsm_rt_column_ss_f32
@@ -259,7 +260,9 @@ def rt_run_sharded(model: RTModel, ctx: Optional[_lib.Context] = None, device: O
         f0 = np.zeros((nS, n), FT); f0[:, 0] = 1
         d_th = None if model.thermal_B is None else torch.from_numpy(np.ascontiguousarray(model.thermal_B[lo:hi].astype(FT))).to(device)
         d_sif = None if model.sif0 is None else torch.from_numpy(np.ascontiguousarray(model.sif0[lo:hi].astype(FT))).to(device)
-        R, T, H, uw, dw = rt_column_device(ctx, prep, d_tr, d_ta, torch.from_numpy(f0).to(device), thermal_B=d_th, sif0=d_sif)
+        d_f0 = torch.from_numpy(f0).to(device)             # inputs stay alive until the gather has synchronised
+        R, T, H, uw, dw = rt_column_device(ctx, prep, d_tr, d_ta, d_f0, thermal_B=d_th, sif0=d_sif)
+        ctx.synchronize()
     else:
         R = torch.zeros((0, n, nV), dtype=dt, device=device); T = R.clone(); H = R.clone()
         uw = torch.zeros((0, n), dtype=dt, device=device); dw = uw.clone()
