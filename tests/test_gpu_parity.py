@@ -617,7 +617,7 @@ def test_small_matrix_kernel_equals_generic_kernels():
             assert relerr(res[0][k], ref[k]) <= 1e-9, (k, relerr(res[0][k], ref[k]))
 
 
-@pytest.mark.parametrize("pol,nstreams,expect_N", [("Stokes_IQU", 8, 39), ("Stokes_IQU", 4, 27), ("Stokes_I", 30, 35),
+@pytest.mark.parametrize("pol,nstreams,expect_N", [("Stokes_I", 12, 17), ("Stokes_I", 16, 21), ("Stokes_IQU", 8, 39), ("Stokes_IQU", 4, 27), ("Stokes_I", 30, 35),
                                                    ("Stokes_IQUV", 8, 52), ("Stokes_IQUV", 12, 68), ("Stokes_IQU", 23, 81)])
 def test_embedded_sizes_match_oracle_and_generic(pol, nstreams, expect_N):
     """N between the specialised sizes runs zero-padded as the next one (45 / 60 / 75 / 100) with dummy zero-weight

@@ -45,6 +45,8 @@ struct vsm_ctx {
     std::vector<int> rrs_key;               // nBand, n1lo, n1cnt, shifts...
     size_t rrs_nunits = 0;
     DevBuf padtab;                          // zero-padded Z / surface tables of an embedded column (see embed_size)
+    int embed_min = 17;                     // smallest N that runs embedded in the N = 45 kernels (VSM_EMBED_MIN); measured: even N = 17
+                                            // is 2.05x faster padded to 45 than on the run-time-N SIMT kernels
     int use_embed = 1;                      // run N between the specialised sizes as the next one, zero-padded (VSM_DISABLE_EMBED=1: off)
     int use_small = 1;                      // warp-per-point column kernel for N <= 16 in fp64 (VSM_DISABLE_SMALL=1 turns it off)
     int rrs_order = 1;                      // unit enumeration of the Raman kernels (VSM_RRS_ORDER): 1 donor-major over a host-built list of
@@ -160,6 +162,7 @@ extern "C" int vsm_create(vsm_ctx** out, int device, void* cuda_stream) {
     if (const char* e = getenv("VSM_DEBUG_LAYER_CTAS_PER_SM")) ctx->dbg_layer_ctas = atoi(e);
     if (const char* e = getenv("VSM_DISABLE_STREAM")) ctx->use_stream = atoi(e) ? 0 : 1;
     if (const char* e = getenv("VSM_DISABLE_EMBED")) ctx->use_embed = atoi(e) ? 0 : 1;
+    if (const char* e = getenv("VSM_EMBED_MIN")) ctx->embed_min = std::max(17, atoi(e));
     if (const char* e = getenv("VSM_DISABLE_SMALL")) ctx->use_small = atoi(e) ? 0 : 1;
     if (const char* e = getenv("VSM_RRS_ORDER")) ctx->rrs_order = atoi(e) ? 1 : 0;
     *out = ctx;
@@ -443,12 +446,12 @@ static int occupancy(const void* kern, int threads, size_t smem) {
 // DUMMY streams: zero quadrature weight, zero rows/columns in every Z table and surface moment.  A zero-weight stream is
 // something the algorithm already has (the VZA / SZA streams, elemental.jl:325-332): r = 0 and t = exp(-dτ/μ) on its
 // diagonal; with Z = 0 it neither receives from nor feeds any real stream, so the real N x N block of every operator is
-// unchanged (the sums just carry extra exact zeros) and (Npad/N)^3 more flops still beat the SIMT kernels by 2-7x.
+// unchanged (the sums just carry extra exact zeros) and (Npad/N)^3 more flops still beat the SIMT kernels by 2-13x.
 template <typename T>
 static int embed_size(const vsm_ctx* ctx, int N, bool has_stream_export) {
     if (!ctx->use_embed || has_stream_export) return N;
     if (std::is_same<T, double>::value) {
-        if (N >= 23 && N < 45) return 45;
+        if (N >= ctx->embed_min && N < 45) return 45;
         if (ctx->use_stream) {
             if (N > 45 && N < 60) return 60;
             if (N > 60 && N < 75) return 75;
