@@ -649,3 +649,30 @@ def test_embedded_sizes_match_oracle_and_generic(pol, nstreams, expect_N):
         #  1e-11 relative differences between any two evaluation orders)
         assert relerr(res[0][k], res[1][k]) <= 1e-10, (k, relerr(res[0][k], res[1][k]))
         assert relerr(res[0][k], ref[k]) <= 1e-9, (k, relerr(res[0][k], ref[k]))
+
+
+def test_embedded_size_fp32():
+    """fp32: N = 39 runs embedded in the compile-time N = 45 kernels; <= 1e-2 vs the fp64 oracle (test_float32.jl:64) and
+    close to the fp32 generic kernels."""
+    import os
+    from vsmom_b200 import _lib, rt_run as rr
+    m = vb.synthetic_o2a_model(nSpec=6, nstreams=8, polarization_type="Stokes_IQU", aerosol=True, float_type=np.float32)
+    assert m.quad_points.qp_muN.size == 39
+    sc = np.logspace(-5.0, -1.0, 6)[:, None]         # (as in test_o2a_vector_config_f32: keep T_SFI above the fp32 underflow)
+    m.tau_abs = (m.tau_abs * sc).astype(np.float32)
+    res = []
+    for dis in (None, "1"):
+        if dis:
+            os.environ["VSM_DISABLE_EMBED"] = dis
+        else:
+            os.environ.pop("VSM_DISABLE_EMBED", None)
+        c = _lib.Context(0)
+        res.append(rr.rt_run(m, ctx=c))
+        c.close()
+    os.environ.pop("VSM_DISABLE_EMBED", None)
+    m64 = vb.synthetic_o2a_model(nSpec=6, nstreams=8, polarization_type="Stokes_IQU", aerosol=True)
+    m64.tau_abs = m64.tau_abs * sc
+    ref = orc.rt_run(to_oracle(m64))
+    for k in ("R_SFI", "T_SFI"):
+        assert relerr(res[0][k], ref[k]) <= 1e-2, (k, relerr(res[0][k], ref[k]))
+        assert relerr(res[0][k], res[1][k]) <= 2e-3, (k, relerr(res[0][k], res[1][k]))

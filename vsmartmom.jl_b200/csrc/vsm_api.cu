@@ -450,8 +450,8 @@ static int occupancy(const void* kern, int threads, size_t smem) {
 template <typename T>
 static int embed_size(const vsm_ctx* ctx, int N, bool has_stream_export) {
     if (!ctx->use_embed || has_stream_export) return N;
+    if (N >= ctx->embed_min && N < 45) return 45;            // fp64 (tensor-core kernels) and fp32 (compile-time-N SIMT kernels)
     if (std::is_same<T, double>::value) {
-        if (N >= ctx->embed_min && N < 45) return 45;
         if (ctx->use_stream) {
             if (N > 45 && N < 60) return 60;
             if (N > 60 && N < 75) return 75;
