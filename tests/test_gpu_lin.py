@@ -96,3 +96,18 @@ def test_lin_streamed_ocean_n60(ctx):
     assert m.quad_points.qp_muN.size == 60
     out, ref = check(m, ctx)
     assert np.abs(out["dR_SFI"][3]).max() == 0
+
+
+def test_lin_embedded_n45_runs_on_the_streamed_kernels(ctx):
+    # config-2 shape with Jacobians: N = 45 (IQU, 10 streams) has no LinMode tensor-core kernel of its own; it runs
+    # zero-padded on the N = 60 streamed kernels (dummy zero-weight streams).  Lambertian albedo parameter included.
+    m = vb.synthetic_o2a_model(nSpec=3, nstreams=10, polarization_type="Stokes_IQU", aerosol=True, albedo=0.2,
+                               p_half=np.array([1.0, 200.0, 500.0, 800.0, 1000.0]))
+    m.tau_abs = m.tau_abs * np.logspace(-3.0, -1.0, 3)[:, None]
+    for a in m.aerosol_optics:
+        g = a.greek_coefs
+        for f in ("alpha", "beta", "gamma", "delta", "epsilon", "zeta"):
+            setattr(g, f, getattr(g, f)[:4])
+    m.m_max = 3
+    assert m.quad_points.qp_muN.size == 45
+    check(m, ctx)

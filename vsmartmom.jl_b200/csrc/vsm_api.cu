@@ -849,7 +849,7 @@ extern "C" int vsm_rt_column_streams_f32(vsm_ctx* c, const vsm_column_desc* d, f
 // L2 LinMode: forward + Jacobians (rt_run_lin.jl:102-326)
 // ---------------------------------------------------------------------------
 static int rt_column_lin_impl(vsm_ctx* ctx, const vsm_column_desc* d, const vsm_lin_desc* ld_, double* R_SFI, double* T_SFI,
-                              double* dR, double* dT) {
+                              double* dR, double* dT, bool padded = false) {
     using T = double;
     if (!ctx) return VSM_ERR_INVALID_ARG;
     if (!d || d->struct_size < (int)offsetof(vsm_column_desc, ss_correction))
@@ -861,7 +861,7 @@ static int rt_column_lin_impl(vsm_ctx* ctx, const vsm_column_desc* d, const vsm_
     if (!R_SFI || !T_SFI || !dR || !dT) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_lin: output NULL");
     const int N = d->N, nSt = d->nStokes, Nz = d->Nz, nAer = d->nAer, nV = d->nVZA, nM = d->n_moments, nSpec = d->nSpec;
     const int P = ld_->n_params, nOut = nV * nSt, nC = nAer + 1;
-    if (N <= 0 || nSt < 1 || nSt > 4 || N % nSt != 0 || Nz <= 0 || nAer < 0 || nC > kMaxComp || nV <= 0 || nM <= 0 ||
+    if (N <= 0 || nSt < 1 || nSt > 4 || (N % nSt != 0 && !padded) || Nz <= 0 || nAer < 0 || nC > kMaxComp || nV <= 0 || nM <= 0 ||
         d->imu0 < 1 || d->imu0 * nSt > N)
         return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_lin: bad dimensions");
     if (d->surface_kind == VSM_SURFACE_BRDF_FOURIER && !surf_rho) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_lin: BRDF_FOURIER needs surf_rho");
@@ -874,6 +874,42 @@ static int rt_column_lin_impl(vsm_ctx* ctx, const vsm_column_desc* d, const vsm_
         if (d->ndoubl[iz] < 0 || d->ndoubl[iz] > 60) return fail(ctx, VSM_ERR_INVALID_ARG, "rt_column_lin: ndoubl out of range");
     }
     CK(cudaSetDevice(ctx->device));
+    if (!padded && ctx->use_embed && ctx->use_stream) {
+        // embedding (see embed_size): the LinMode tensor-core kernels exist for N = 60 / 75 / 100; a smaller N runs as the next
+        // of them with dummy zero-weight streams (the derivative Z tables are mixed on the device from the same padded base
+        // tables), measured 2.0x over the run-time-N SIMT LinMode kernels at N = 45; taken from N = 40 on ((60/40)^3 = 3.4x the flops)
+        const int Np = (N >= 40 && N < 60) ? 60 : (N > 60 && N < 75) ? 75 : (N > 75 && N < 100) ? 100 : N;
+        if (Np != N) {
+            const size_t kz = (size_t)nC * nM, per = (size_t)Np * Np;
+            const size_t need = (2 * kz + (surf_rho ? (size_t)nM : 0)) * per * sizeof(T);
+            int rc0 = ensure(ctx, ctx->padtab, need);
+            if (rc0) return rc0;
+            T* zp = (T*)ctx->padtab.p; T* zm = zp + kz * per; T* rp = zm + kz * per;
+            k_pad_tables<T><<<(unsigned)((kz * per + 255) / 256), 256, 0, ctx->stream>>>(N, Np, kz, (const T*)d->Zpp, zp);
+            k_pad_tables<T><<<(unsigned)((kz * per + 255) / 256), 256, 0, ctx->stream>>>(N, Np, kz, (const T*)d->Zmp, zm);
+            if (surf_rho) k_pad_tables<T><<<(unsigned)(((size_t)nM * per + 255) / 256), 256, 0, ctx->stream>>>(N, Np, (size_t)nM, (const T*)surf_rho, rp);
+            ctx->launches += surf_rho ? 3 : 2;
+            CK(cudaGetLastError());
+            std::vector<double> mu2(d->mu, d->mu + N), wt2(d->wt, d->wt + N);
+            for (int k = 0; k < Np - N; ++k) {
+                double mk = 0.3 + 0.6 * (k + 0.5) / (Np - N);
+                for (int it = 0; it < 64; ++it) {
+                    bool clash = false;
+                    for (size_t q = 0; q < mu2.size(); ++q) clash = clash || fabs(mu2[q] - mk) < 1e-4;
+                    if (!clash) break;
+                    mk += 1.7e-4;
+                }
+                mu2.push_back(mk);
+                wt2.push_back(0.0);
+            }
+            vsm_column_desc d2;
+            memset(&d2, 0, sizeof d2);
+            memcpy(&d2, d, (size_t)std::min<int>(d->struct_size, (int)sizeof d2));
+            d2.N = Np; d2.mu = mu2.data(); d2.wt = wt2.data(); d2.Zpp = zp; d2.Zmp = zm;
+            if (surf_rho) d2.surf_rho = rp;
+            return rt_column_lin_impl(ctx, &d2, ld_, R_SFI, T_SFI, dR, dT, true);
+        }
+    }
     // ---- constant tables (as rt_column_impl) + the parameter tables
     std::vector<T> fT;
     std::vector<int> fI;
