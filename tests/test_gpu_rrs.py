@@ -66,10 +66,11 @@ def test_rrs_matches_oracle_structured_solar_spectrum_and_dark_surface():
         assert relerr(out[k], ref[k]) <= TOL, (k, relerr(out[k], ref[k]))
 
 
-def test_rrs_matches_oracle_N30_wide_kernels():
-    """8 Gauss streams + VZA + SZA -> 10 streams, IQU -> N = 30: the NP = 48 instantiation."""
-    m, rs = _scene(nstreams=8, nS=24, Nz=2, aerosol=True)
-    assert 16 < m.quad_points.qp_muN.size <= 48
+@pytest.mark.parametrize("nstreams,lo,hi", [(8, 16, 32), (12, 32, 48)])
+def test_rrs_matches_oracle_wide_kernels(nstreams, lo, hi):
+    """8 Gauss streams + VZA + SZA -> 10 streams, IQU -> N = 30: the NP = 32 instantiation; 12 streams -> N = 42: NP = 48."""
+    m, rs = _scene(nstreams=nstreams, nS=24, Nz=2, aerosol=True)
+    assert lo < m.quad_points.qp_muN.size <= hi
     ref = _oracle(m, rs)
     out = raman.rt_run_rrs(m, rs)
     for k in KEYS:

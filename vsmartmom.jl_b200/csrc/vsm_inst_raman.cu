@@ -1,4 +1,4 @@
-// rotational-Raman kernels (vsm_raman.cuh): NP = 16 (N <= 16: config 5, N = 15) and NP = 48 (N <= 48)
+// rotational-Raman kernels (vsm_raman.cuh): NP = 16 (N <= 16: config 5, N = 15), NP = 32 (N <= 32) and NP = 48 (N <= 48)
 #include "vsm_raman.cuh"
 
 namespace vsm {
@@ -27,6 +27,7 @@ static const Desc* make() {
 }
 const Desc* desc(int N) {
     if (N <= 16) return make<16, 4>();
+    if (N <= 32) return make<32, 4>();
     if (N <= 48) return make<48, 2>();
     return nullptr;
 }
