@@ -541,7 +541,11 @@ struct CompPtrs {
 
 template <typename T, class Ops>
 __device__ __forceinline__ void interact(const Ops& op, int iface, CompPtrs<T>& c, T* J0p, T* J0m,
-                                         const T* jp, const T* jm, T* v1, bool rpm_zero, bool t_ident) {
+                                         const T* jp, const T* jm, T* v1, bool rpm_zero, bool t_ident,
+                                         bool full = true) {
+    // full == false (ScatteringInterface_11 only): the composite R-+ and T++ are not advanced.  They enter no
+    // J0+- / T-- / R+- of this or any later step, so every rt_run output is unchanged; callers that hand the
+    // composite matrices out (rt_run_streams, the L1 entry) keep full == true.
     const int n = op.N(), ld = op.LD();
     const uint32_t* dmask = op.dmask;
     auto at = [ld](T* M, int i, int j) -> T& { return M[i + j * ld]; };
@@ -564,9 +568,11 @@ __device__ __forceinline__ void interact(const Ops& op, int iface, CompPtrs<T>& 
         op.template mv<false>(c.X2, v1, [&](int i, T s) { J0m[i] = J0m[i] + s; });
         VSM_ATICK(3);
         // R⁻⁺ += T01_inv r⁻⁺ T⁺⁺                                          (:237)
-        op.template mm<false>(c.X2, c.r, [&](int i, int j, T acc) { at(c.X3, i, j) = acc; });
-        __syncthreads();
-        op.template mm<false>(c.X3, c.TC, [&](int i, int j, T acc) { at(c.RA, i, j) += acc; });
+        if (full) {
+            op.template mm<false>(c.X2, c.r, [&](int i, int j, T acc) { at(c.X3, i, j) = acc; });
+            __syncthreads();
+            op.template mm<false>(c.X3, c.TC, [&](int i, int j, T acc) { at(c.RA, i, j) += acc; });
+        }
         // T⁻⁻ = T01_inv t⁻⁻                                               (:240)
         if (t_ident) {
             T* tmp = c.TD; c.TD = c.X2; c.X2 = tmp;
@@ -600,9 +606,11 @@ __device__ __forceinline__ void interact(const Ops& op, int iface, CompPtrs<T>& 
         op.template mv<false>(T21, v1, [&](int i, T s) { J0p[i] = jp[i] + s; });
         VSM_ATICK(7);
         // T⁺⁺ = T21_inv T⁺⁺                                               (:262)
-        op.template mm<false>(T21, c.TC, [&](int i, int j, T acc) { at(c.X3, i, j) = acc; });
-        __syncthreads();
-        { T* tmp = c.TC; c.TC = c.X3; c.X3 = tmp; }
+        if (full) {
+            op.template mm<false>(T21, c.TC, [&](int i, int j, T acc) { at(c.X3, i, j) = acc; });
+            __syncthreads();
+            T* tmp = c.TC; c.TC = c.X3; c.X3 = tmp;
+        }
         // R⁺⁻ = r⁺⁻ + T21_inv R⁺⁻ t⁻⁻                                      (:265)
         op.template mm<false>(T21, c.RB, [&](int i, int j, T acc) { at(c.X3, i, j) = acc; });
         __syncthreads();
@@ -783,7 +791,7 @@ __global__ void __launch_bounds__(NTHR) k_adding(ColArgs<T> a, unsigned int tota
                 }
                 __syncthreads();
             } else {
-                interact<T, Ops>(op, a.iface[iz], c, J0p, J0m, jp, jm, v1, !sc, false);
+                interact<T, Ops>(op, a.iface[iz], c, J0p, J0m, jp, jm, v1, !sc, false, a.st_Rmp || a.st_Tpp);
             }
             VSM_ATICK(9);
         }
@@ -810,7 +818,7 @@ __global__ void __launch_bounds__(NTHR) k_adding(ColArgs<T> a, unsigned int tota
             }
             jps_sun = att;
             __syncthreads();
-            interact<T, Ops>(op, a.iface[a.Nz - 1], c, J0p, J0m, jp, jm, v1, true, true);
+            interact<T, Ops>(op, a.iface[a.Nz - 1], c, J0p, J0m, jp, jm, v1, true, true, a.st_Rmp || a.st_Tpp);
             // interaction_hdrf!: hdr_J₀⁻ = r⁻⁺ J₀⁺ + j₀⁻
             op.template mv<false>(c.r, J0p, [&](int i, T s) { hv[i] = s + jm[i]; });
         } else {
@@ -869,7 +877,7 @@ struct Add2Ctx {
 
 // one ScatteringInterface_11 step on two groups; ends with the whole CTA synchronised
 template <typename T, int NN, int TM, int GT>
-__device__ __forceinline__ void add2_step11(Add2Ctx<T, NN, TM, GT>& c, bool rpm_zero, bool t_ident) {
+__device__ __forceinline__ void add2_step11(Add2Ctx<T, NN, TM, GT>& c, bool rpm_zero, bool t_ident, bool full) {
     constexpr int n = NN, ld = NN | 1;
     const uint32_t* dmask = c.dmask;
     auto at = [](T* M, int i, int j) -> T& { return M[i + j * ld]; };
@@ -886,11 +894,18 @@ __device__ __forceinline__ void add2_step11(Add2Ctx<T, NN, TM, GT>& c, bool rpm_
         op.template mm<false>(TD, X1a, [&](int i, int j, T acc) { at(X2a, i, j) = acc; });    // T01_inv (:226)
         op.sync();
         VSM_GTICK(1);
-        op.template mmv<1>(X2a, r, [&](int i, int j, T acc) { at(X1a, i, j) = acc; }, v1A, v1A,
-                           [&](int i, T s) { J0m[i] = J0m[i] + s; }, [](int, T) {});
-        op.sync();
-        VSM_GTICK(2);
-        op.template mm<false>(X1a, TC, [&](int i, int j, T acc) { at(RA, i, j) += acc; });    // (:237)
+        if (full) {
+            op.template mmv<1>(X2a, r, [&](int i, int j, T acc) { at(X1a, i, j) = acc; }, v1A, v1A,
+                               [&](int i, T s) { J0m[i] = J0m[i] + s; }, [](int, T) {});
+            op.sync();
+            VSM_GTICK(2);
+            op.template mm<false>(X1a, TC, [&](int i, int j, T acc) { at(RA, i, j) += acc; });    // (:237)
+        } else {
+            // R-+ (and T++ below) of the composite feed no J0+- / T-- / R+- of any later step: without the
+            // rt_run_streams export only the source line of (:229) is needed here
+            op.template mv<false>(X2a, v1A, [&](int i, T s) { J0m[i] = J0m[i] + s; });
+            VSM_GTICK(2);
+        }
         if (!t_ident)
             op.template mm<true>(X2a, t, [&](int i, int j, T acc) { at(TD, i, j) = Num<T>::flip(acc, dmask[j]); });  // (:240)
         VSM_GTICK(3);
@@ -911,9 +926,14 @@ __device__ __forceinline__ void add2_step11(Add2Ctx<T, NN, TM, GT>& c, bool rpm_
         }
         VSM_GTICK(1);
         T* TCn = t_ident ? X2b : X1b;
-        op.template mmv<1>(T21, TC, [&](int i, int j, T acc) { at(TCn, i, j) = acc; }, v1B, v1B,      // (:262)
-                           [&](int i, T s) { J0pnew[i] = jp[i] + s; }, [](int, T) {});
-        op.template mm<false>(T21, RB, [&](int i, int j, T acc) { at(X3b, i, j) = acc; });
+        if (full) {
+            op.template mmv<1>(T21, TC, [&](int i, int j, T acc) { at(TCn, i, j) = acc; }, v1B, v1B,      // (:262)
+                               [&](int i, T s) { J0pnew[i] = jp[i] + s; }, [](int, T) {});
+            op.template mm<false>(T21, RB, [&](int i, int j, T acc) { at(X3b, i, j) = acc; });
+        } else {
+            op.template mmv<1>(T21, RB, [&](int i, int j, T acc) { at(X3b, i, j) = acc; }, v1B, v1B,     // (:254)
+                               [&](int i, T s) { J0pnew[i] = jp[i] + s; }, [](int, T) {});
+        }
         op.sync();
         VSM_GTICK(2);
         if (t_ident) {                                                                // (:265)
@@ -935,10 +955,10 @@ __device__ __forceinline__ void add2_step11(Add2Ctx<T, NN, TM, GT>& c, bool rpm_
     T* tmp;
     if (t_ident) {
         tmp = c.TD; c.TD = c.X2a; c.X2a = tmp;
-        tmp = c.TC; c.TC = c.X2b; c.X2b = tmp;
+        if (full) { tmp = c.TC; c.TC = c.X2b; c.X2b = tmp; }
         tmp = c.RB; c.RB = c.X3b; c.X3b = tmp;
     } else {
-        tmp = c.TC; c.TC = c.X1b; c.X1b = tmp;
+        if (full) { tmp = c.TC; c.TC = c.X1b; c.X1b = tmp; }
         tmp = c.RB; c.RB = c.X2b; c.X2b = tmp;
     }
     tmp = c.J0pc; c.J0pc = c.J0pnew; c.J0pnew = tmp;
@@ -1115,6 +1135,7 @@ __global__ void __launch_bounds__(2 * GT, 1) k_adding2(ColArgs<T> a, unsigned in
             jps_sun = att;
         };
         const int nsteps = a.Nz + (has_surf ? 1 : 0);     // step Nz = the surface
+        const bool full = a.st_Rmp || a.st_Tpp;           // composite R-+ / T++ wanted (rt_run_streams)
 
         fetch_layer(0, p, mi, 0, c.RA, c.TC, c.J0pc, J0m);
         if (a.Nz > 1) fetch_layer(1, p, mi, 1, nullptr, nullptr, jpb + n, jmb + n);
@@ -1144,7 +1165,7 @@ __global__ void __launch_bounds__(2 * GT, 1) k_adding2(ColArgs<T> a, unsigned in
             else if (iz + 1 == a.Nz && has_surf) fill_surface(nb);
             set_buf(iz & 1);
             VSM_GTICK(5);
-            if (itf == 3) add2_step11<T, NN, TM, GT>(c, nosrc, surf);
+            if (itf == 3) add2_step11<T, NN, TM, GT>(c, nosrc, surf, full);
             else add2_step_other<T, NN, TM, GT>(c, itf, nosrc, surf);
             VSM_GTICK(6);
             layer_ready(nb);

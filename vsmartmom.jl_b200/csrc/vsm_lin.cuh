@@ -516,9 +516,10 @@ __global__ void __launch_bounds__(NTHR, MINB) k_adding_lin(ColArgs<T> a, LinArgs
     const int P = l.P, vs = l.vstride, tid = threadIdx.x;
     const size_t msz = l.msz, dsz = (size_t)(1 + P) * msz;
     T* slab = a.slab + (size_t)blockIdx.x * a.slab_stride;
-    Dual<T> RA{slab, msz}, RB{slab + dsz, msz}, TC{slab + 2 * dsz, msz}, TD{slab + 3 * dsz, msz}, G{slab + 4 * dsz, msz},
-        T01{slab + 5 * dsz, msz}, X{slab + 6 * dsz, msz}, T21{slab + 7 * dsz, msz}, Y{slab + 8 * dsz, msz},
-        N1{slab + 9 * dsz, msz}, N2{slab + 10 * dsz, msz}, N3{slab + 11 * dsz, msz}, SR{slab + 12 * dsz, msz};
+    // (slots 0, 2, 6 and 10 of the slab held the composite R-+ / T++ and their scratch; they are not advanced, see below)
+    Dual<T> RB{slab + dsz, msz}, TD{slab + 3 * dsz, msz}, G{slab + 4 * dsz, msz},
+        T01{slab + 5 * dsz, msz}, T21{slab + 7 * dsz, msz}, Y{slab + 8 * dsz, msz},
+        N1{slab + 9 * dsz, msz}, N3{slab + 11 * dsz, msz}, SR{slab + 12 * dsz, msz};
     T* S1 = slab + 13 * dsz; T* S2 = S1 + msz;
     const size_t dv = (size_t)(1 + P) * vs;
     T* J0p = S2 + msz; T* J0m = J0p + dv; T* J0pn = J0m + dv; T* jp = J0pn + dv; T* jm = jp + dv;
@@ -538,7 +539,7 @@ __global__ void __launch_bounds__(NTHR, MINB) k_adding_lin(ColArgs<T> a, LinArgs
         const int sp = item % a.nS;
         const int mi = item / a.nS;
         const int m = a.m0 + mi;
-        Dual<T> cRA = RA, cRB = RB, cTC = TC, cTD = TD, nTD = N1, nTC = N2, nRB = N3;
+        Dual<T> cRB = RB, cTD = TD, nTD = N1, nRB = N3;
         T* cJ0p = J0p; T* cJ0pn = J0pn;
         const bool has_surf = (m == 0) || (a.surf_rho != nullptr);
         const int nsteps = a.Nz + (has_surf ? 1 : 0);
@@ -548,14 +549,12 @@ __global__ void __launch_bounds__(NTHR, MINB) k_adding_lin(ColArgs<T> a, LinArgs
             for (int q = 0; q <= P; ++q) {
                 const T* gr = l.add_r + (slot * (1 + P) + q) * msz;
                 const T* gt = l.add_t + (slot * (1 + P) + q) * msz;
-                T* ra = cRA.f + (size_t)q * msz; T* rb = cRB.f + (size_t)q * msz;
-                T* tc = cTC.f + (size_t)q * msz; T* td = cTD.f + (size_t)q * msz;
+                T* rb = cRB.f + (size_t)q * msz; T* td = cTD.f + (size_t)q * msz;
                 for (int e = tid; e < n * n; e += blockDim.x) {
                     const int i = e % n, j = e / n;
                     const size_t o = i + (size_t)j * ld;
                     const uint32_t sg = dmask[i] ^ dmask[j];
                     const T rv = gr[o], tv = gt[o];
-                    ra[o] = rv; tc[o] = tv;
                     rb[o] = Num<T>::flip(rv, sg); td[o] = Num<T>::flip(tv, sg);
                 }
                 for (int i = tid; i < n; i += blockDim.x) {
@@ -611,11 +610,9 @@ __global__ void __launch_bounds__(NTHR, MINB) k_adding_lin(ColArgs<T> a, LinArgs
             dual_mm<T, Ops, false, false>(op, P, cTD, G, T01);                       // T01 = T-- G1
             dual_mv<T, Ops>(op, P, r, cJ0p, vs, tmpv, [&](int q, int i, T s) { v1[(q + 1) * vs + i] = s + jm[(q + 1) * vs + i]; });
             dual_mv<T, Ops>(op, P, T01, v1, vs, tmpv, [&](int q, int i, T s) { J0m[(q + 1) * vs + i] += s; });
-            if (!surf) {        // (after the surface step only J0+- are read: its matrix updates are skipped)
-                dual_mm<T, Ops, false, false>(op, P, T01, r, X);                     // X = T01 r
-                dual_mm<T, Ops, false, true>(op, P, X, cTC, cRA);                    // R-+ += X T++
-                dual_mm<T, Ops, true, false>(op, P, T01, t, nTD);                    // T--' = T01 t--
-            }
+            // (after the surface step only J0+- are read: its matrix updates are skipped.  The composite R-+ and
+            //  T++ (:252-255, :296) enter no J0+- / T-- / R+- of any later step, i.e. no LinMode output: not advanced.)
+            if (!surf) dual_mm<T, Ops, true, false>(op, P, T01, t, nTD);             // T--' = T01 t--
             // ---- plus half (:280-306)
             dual_inv_one_minus<T, Ops>(op, P, cRB, r, G, S1, S2);                    // G2 = (I - R+- r)^-1
             Dual<T> T21u = G;                                                        // (surface: t = I)
@@ -623,7 +620,6 @@ __global__ void __launch_bounds__(NTHR, MINB) k_adding_lin(ColArgs<T> a, LinArgs
             dual_mv<T, Ops>(op, P, cRB, jm, vs, tmpv, [&](int q, int i, T s) { v2[(q + 1) * vs + i] = cJ0p[(q + 1) * vs + i] + s; });
             dual_mv<T, Ops>(op, P, T21u, v2, vs, tmpv, [&](int q, int i, T s) { cJ0pn[(q + 1) * vs + i] = jp[(q + 1) * vs + i] + s; });
             if (!surf) {
-                dual_mm<T, Ops, false, false>(op, P, T21u, cTC, nTC);                // T++' = T21 T++
                 dual_mm<T, Ops, false, false>(op, P, T21u, cRB, Y);                  // Y = T21 R+-
                 dual_mm<T, Ops, true, false>(op, P, Y, t, nRB);                      // R+-' = r+- + Y t--
                 for (int q = 0; q <= P; ++q) {
@@ -636,7 +632,6 @@ __global__ void __launch_bounds__(NTHR, MINB) k_adding_lin(ColArgs<T> a, LinArgs
                 __syncthreads();
                 Dual<T> sw;
                 sw = cTD; cTD = nTD; nTD = sw;
-                sw = cTC; cTC = nTC; nTC = sw;
                 sw = cRB; cRB = nRB; nRB = sw;
             }
             { T* sw = cJ0p; cJ0p = cJ0pn; cJ0pn = sw; }

@@ -63,13 +63,8 @@ __global__ void __launch_bounds__(32 * WPC) k_small(ColArgs<double> a, unsigned 
             __syncwarp();
             wmv<NP>(y2, sTG, SV{a1}, lane);
             if (lane < 16) for (int b = 0; b < NP / 16; ++b) J0m[16 * b + lane] += y2[b];
-            czero<NP>(c);                                            // R-+ += (T01 r) T++
-            wmm<NP>(c, sTG, sr, lane);
-            wepi<NP>(c, [&](int i, int j, double v) { S[i + j * LDS] = v; }, lane);
-            __syncwarp();
-            czero<NP>(c);
-            wmm<NP>(c, sS, sTpp, lane);
-            wepi<NP>(c, [&](int i, int j, double v) { Rmp[i + j * LDS] += v; }, lane);
+            // (R-+ += T01 r T++ (:237) and T++ = T21 T++ (:262) are not advanced: the composite R-+ / T++ enter no
+            //  J0+- / T-- / R+- of any later step, and this kernel never exports them)
             czero<NP>(c);                                            // T-- = T01 t--
             wmm<NP>(c, sTG, stmm, lane);
             wepi<NP>(c, [&](int i, int j, double v) { Tmm[i + j * LDS] = v; }, lane);
@@ -85,10 +80,6 @@ __global__ void __launch_bounds__(32 * WPC) k_small(ColArgs<double> a, unsigned 
             __syncwarp();
             wmv<NP>(y2, sTG, SV{a2}, lane);
             if (lane < 16) for (int b = 0; b < NP / 16; ++b) J0p[16 * b + lane] = jp[16 * b + lane] + y2[b];
-            czero<NP>(c);                                            // T++ = T21 T++
-            wmm<NP>(c, sTG, sTpp, lane);
-            __syncwarp();
-            wepi<NP>(c, [&](int i, int j, double v) { Tpp[i + j * LDS] = v; }, lane);
             czero<NP>(c);                                            // R+- = r+- + (T21 R+-) t--
             wmm<NP>(c, sTG, sRpm, lane);
             wepi<NP>(c, [&](int i, int j, double v) { S[i + j * LDS] = v; }, lane);

@@ -575,7 +575,7 @@ struct StreamComp {
 template <class CF>
 __device__ __forceinline__ void add_step11_stream(const OpsStream<CF>& op, StreamComp<CF>& c, const double* r, const double* t,
                                                   const double* jp, const double* jm, bool rpm_zero, bool t_ident,
-                                                  const double* next_r) {
+                                                  const double* next_r, bool full) {
     using T = double;
     constexpr int n = CF::NN, ld = CF::LD;
     const uint32_t* dmask = op.dmask;
@@ -584,6 +584,61 @@ __device__ __forceinline__ void add_step11_stream(const OpsStream<CF>& op, Strea
     auto none = [](int, T) {};
     T* J0m = c.J0m; T* v1A = c.v1A; T* v1B = c.v1B; T* J0pc = c.J0pc; T* J0pn = c.J0pnew;
     T ssa = 0.0, ssb = 0.0;
+    if (!full) {
+        // The composite R-+ and T++ enter no J0+- / T-- / R+- of this or any later step: without the rt_run_streams
+        // export M4 and the matrix halves of M3 / P3 are dropped and the two source lines ride on M5 / P4:
+        //   P1 X1b = R+- r (+ R+- j-)      M1 X1a = r R+- (+ r J+)       -> both inverses
+        //   P2 X2b = t X1b (T21)           M2 X2a = T-- X1a
+        //   P4 X3b = T21 R+- (+ J+')       M5 T--' = (X2a D t) D (+ J-)  P5 R+-' = r+- + (X3b D t) D
+        // Every product but the step's first is announced by the one before it (its operands are complete by then).
+        op.template mm_stream<false, 1>(c.RB, r, [&](int i, int j, T acc) { at(c.X1b, i, j) = acc; ssb = fma(acc, acc, ssb); },
+                                        jm, jm, [&](int i, T s) { v1B[i] = J0pc[i] + s; }, none, r, c.RB);
+        op.finish_inverse(op.neumann_order(op.block_sum(ssb)), c.X1b, c.X2b);
+        // v1A is kept D-flipped: the source line of M5 runs through its D-signed k loop
+        op.template mm_stream<false, 1>(r, c.RB, [&](int i, int j, T acc) { at(c.X1a, i, j) = acc; ssa = fma(acc, acc, ssa); },
+                                        J0pc, J0pc, [&](int i, T s) { v1A[i] = Num<T>::flip(s + jm[i], dmask[i]); }, none,
+                                        t_ident ? nullptr : t, t_ident ? nullptr : c.X1b);
+        op.finish_inverse(op.neumann_order(op.block_sum(ssa)), c.X1a, c.X2a);
+        const T* T21 = c.X1b;
+        if (!t_ident) {
+            op.template mm_stream<false, 0>(t, c.X1b, [&](int i, int j, T acc) { at(c.X2b, i, j) = acc; }, r, r, none, none,
+                                            c.TD, c.X1a);
+            __syncthreads();
+            T21 = c.X2b;
+        }
+        op.template mm_stream<false, 0>(c.TD, c.X1a, [&](int i, int j, T acc) { at(c.X2a, i, j) = acc; }, r, r, none, none,
+                                        T21, c.RB);
+        __syncthreads();
+        op.template mm_stream<false, 1>(T21, c.RB, [&](int i, int j, T acc) { at(c.X3b, i, j) = acc; }, v1B, v1B,
+                                        [&](int i, T s) { J0pn[i] = jp[i] + s; }, none,
+                                        t_ident ? nullptr : c.X2a, t_ident ? nullptr : t);
+        __syncthreads();
+        T* tmp;
+        if (t_ident) {
+            op.template mv<true>(c.X2a, v1A, [&](int i, T s) { J0m[i] = J0m[i] + s; });
+            if (!rpm_zero) {
+                for (int e = op.tid; e < n * n; e += CF::NTHR) {
+                    const int i = e % n, j = e / n;
+                    at(c.X3b, i, j) += Num<T>::flip(rd(r, i, j), dmask[i] ^ dmask[j]);
+                }
+                __syncthreads();
+            }
+            tmp = c.TD; c.TD = c.X2a; c.X2a = tmp;
+            tmp = c.RB; c.RB = c.X3b; c.X3b = tmp;
+        } else {
+            op.template mm_stream<true, 1>(c.X2a, t, [&](int i, int j, T acc) { at(c.TD, i, j) = Num<T>::flip(acc, dmask[j]); },
+                                           v1A, v1A, [&](int i, T s) { J0m[i] = J0m[i] + s; }, none, c.X3b, t);
+            __syncthreads();
+            op.template mm_stream<true, 0>(c.X3b, t, [&](int i, int j, T acc) {
+                const T rpm = rpm_zero ? 0.0 : Num<T>::flip(rd(r, i, j), dmask[i] ^ dmask[j]);
+                at(c.X1b, i, j) = rpm + Num<T>::flip(acc, dmask[j]);
+            }, r, r, none, none, nullptr, nullptr);
+            __syncthreads();
+            tmp = c.RB; c.RB = c.X1b; c.X1b = tmp;
+        }
+        tmp = c.J0pc; c.J0pc = c.J0pnew; c.J0pnew = tmp;
+        return;
+    }
     // M1, then its inverse (K = 2: the diagonal only, the announcement of P1 stays valid)
     op.template mm_stream<false, 1>(r, c.RB, [&](int i, int j, T acc) { at(c.X1a, i, j) = acc; ssa = fma(acc, acc, ssa); },
                                     J0pc, J0pc, [&](int i, T s) { v1A[i] = s + jm[i]; }, none, c.RB, r);
@@ -779,7 +834,7 @@ __global__ void __launch_bounds__(CF::NTHR, MINB) k_adding_stream(ColArgs<double
             layer(iz, r, t, ljp, ljm);
             __syncthreads();
             if (itf == 3) {
-                add_step11_stream<CF>(op, c, r, t, ljp, ljm, nosrc, surf, next_r_of(iz + 1));
+                add_step11_stream<CF>(op, c, r, t, ljp, ljm, nosrc, surf, next_r_of(iz + 1), a.st_Rmp || a.st_Tpp);
             } else {
                 op.drain();
                 CompPtrs<T> q{c.RA, c.RB, c.TC, c.TD, const_cast<T*>(r), const_cast<T*>(t), c.X1a, c.X2a, c.X1b};
