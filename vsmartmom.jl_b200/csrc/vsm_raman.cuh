@@ -563,15 +563,18 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_elastic(Args a, int m, int iz,
         for (int e = lane; e < NP * NP; e += 32) {
             const int i = e % NP, j = e / NP;
             const double rv = r[i + j * LDS], tv = t[i + j * LDS], s2 = sg[i] * sg[j];
-            Cout[e] = rv; Cout[MG + e] = rv * s2; Cout[2 * MG + e] = tv; Cout[3 * MG + e] = tv * s2;
+            Cout[MG + e] = rv * s2; Cout[3 * MG + e] = tv * s2;
         }
         for (int i = lane; i < NP; i += 32) { Cout[4 * MG + i] = jp[i]; Cout[4 * MG + NP + i] = jm[i]; }
         return;
     }
+    // The composite R-+ / T++ (elastic: interaction_inelastic.jl:489-502, inelastic: ieR-+ / ieT++) enter no J0+- / T-- / R+-
+    // line of this or any later step, elastic or inelastic: they are not advanced (slots 0 and 2 MG of the composite and
+    // slots 1, 4, 6 MG of the interaction record stay unused), and neither are the products that only feed them.
     // ---- interaction_helper!(::ScatteringInterface_11) elastic lines (interaction_inelastic.jl:372-373, 402-403,
     //      423-427, 441-442, 463-464, 489-502) with the exports the units need
     const double* Cin = a.cE_in + (size_t)p * G::CE;
-    const GB<NP, false> Rmp{Cin}, Rpm{Cin + MG}, Tpp{Cin + 2 * MG}, Tmm{Cin + 3 * MG};
+    const GB<NP, false> Rpm{Cin + MG}, Tmm{Cin + 3 * MG};
     const double* J0p = Cin + 4 * MG; const double* J0m = J0p + NP;
     const bool surf = (mode == 1);
     const Conj<SM<NP>> stmm{st, sg};
@@ -581,7 +584,7 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_elastic(Args a, int m, int iz,
     for (int e = lane; e < NP * NP; e += 32) {
         const int i = e % NP, j = e / NP;
         const double rv = r[i + j * LDS], rpm = Cin[MG + e];
-        I0[e] = rpm; I0[MG + e] = Cin[2 * MG + e]; I0[2 * MG + e] = rv; I0[3 * MG + e] = t[i + j * LDS] * sg[i] * sg[j];
+        I0[e] = rpm; I0[2 * MG + e] = rv; I0[3 * MG + e] = t[i + j * LDS] * sg[i] * sg[j];
         I1[2 * MG + j + i * NP] = rv; I1[3 * MG + j + i * NP] = rpm;
     }
     for (int i = lane; i < NP; i += 32) { IV[2 * NP + i] = J0p[i]; IV[3 * NP + i] = jm[i]; }
@@ -593,13 +596,6 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_elastic(Args a, int m, int iz,
     czero<NP>(c);                                                   // T01_inv = T-- inv1
     wmm<NP>(c, Tmm, sG, lane);
     wepi<NP>(c, [&](int i, int j, double v) { TG[i + j * LDS] = v; I1[j + i * NP] = v; }, lane);
-    czero<NP>(c);                                                   // inv1 r
-    wmm<NP>(c, sG, sr, lane);
-    wepi<NP>(c, [&](int i, int j, double v) { S[i + j * LDS] = v; }, lane);
-    __syncwarp();
-    czero<NP>(c);                                                   // E1 = inv1 r T++
-    wmm<NP>(c, sS, Tpp, lane);
-    wepi<NP>(c, [&](int i, int j, double v) { I0[4 * MG + i + j * NP] = v; }, lane);
     czero<NP>(c);                                                   // E2 = inv1 t--
     wmm<NP>(c, sG, stmm, lane);
     wepi<NP>(c, [&](int i, int j, double v) { I0[5 * MG + i + j * NP] = v; }, lane);
@@ -610,14 +606,6 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_elastic(Args a, int m, int iz,
     wmv<NP>(y2, sTG, SV{a1}, lane);                                 // J0- += T01 b1
     if (lane < 16)
         for (int b = 0; b < NP / 16; ++b) { const int i = 16 * b + lane; IV[i] = y1[b]; Cout[4 * MG + NP + i] = J0m[i] + y2[b]; }
-    czero<NP>(c);                                                   // R-+ += (T01 r) T++
-    wmm<NP>(c, sTG, sr, lane);
-    __syncwarp();
-    wepi<NP>(c, [&](int i, int j, double v) { S[i + j * LDS] = v; }, lane);
-    __syncwarp();
-    czero<NP>(c);
-    wmm<NP>(c, sS, Tpp, lane);
-    wepi<NP>(c, [&](int i, int j, double v) { Cout[i + j * NP] = Rmp(i, j) + v; }, lane);
     czero<NP>(c);                                                   // T-- = T01 t--
     wmm<NP>(c, sTG, stmm, lane);
     wepi<NP>(c, [&](int i, int j, double v) { Cout[3 * MG + i + j * NP] = v; }, lane);
@@ -629,9 +617,6 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_elastic(Args a, int m, int iz,
     czero<NP>(c);                                                   // T21_inv = t++ inv2
     wmm<NP>(c, st, sG, lane);
     wepi<NP>(c, [&](int i, int j, double v) { TG[i + j * LDS] = v; I1[MG + j + i * NP] = v; }, lane);
-    czero<NP>(c);                                                   // E3 = inv2 T++
-    wmm<NP>(c, sG, Tpp, lane);
-    wepi<NP>(c, [&](int i, int j, double v) { I0[6 * MG + i + j * NP] = v; }, lane);
     czero<NP>(c);                                                   // inv2 R+-
     wmm<NP>(c, sG, Rpm, lane);
     wepi<NP>(c, [&](int i, int j, double v) { S[i + j * LDS] = v; }, lane);
@@ -646,9 +631,6 @@ __global__ void __launch_bounds__(32 * WPC) k_rrs_elastic(Args a, int m, int iz,
     wmv<NP>(y2, sTG, SV{a2}, lane);                                 // J0+ = j0+ + T21 b2
     if (lane < 16)
         for (int b = 0; b < NP / 16; ++b) { const int i = 16 * b + lane; IV[NP + i] = y1[b]; Cout[4 * MG + i] = jp[i] + y2[b]; }
-    czero<NP>(c);                                                   // T++ = T21 T++
-    wmm<NP>(c, sTG, Tpp, lane);
-    wepi<NP>(c, [&](int i, int j, double v) { Cout[2 * MG + i + j * NP] = v; }, lane);
     czero<NP>(c);                                                   // R+- = r+- + (T21 R+-) t--
     wmm<NP>(c, sTG, Rpm, lane);
     __syncwarp();
@@ -979,19 +961,19 @@ __global__ void __launch_bounds__(32 * WPC, (NP <= 16) ? 4 : 1) k_rrs_inel(Args 
         for (int e = lane; e < NP * NP; e += 32) {
             const int i = e % NP, j = e / NP;
             const double rv = A[i + j * LDS], tv = B[i + j * LDS], s2 = sg[i] * sg[j];
-            Cout[e] = rv; Cout[MG + e] = rv * s2; Cout[2 * MG + e] = tv; Cout[3 * MG + e] = tv * s2;
+            Cout[MG + e] = rv * s2; Cout[3 * MG + e] = tv * s2;
         }
         for (int i = lane; i < NP; i += 32) { Cout[4 * MG + i] = jp[i]; Cout[4 * MG + NP + i] = jm[i]; }
         return;
     }
+    // (ieR-+ (:400-420) and ieT++ (:461-487) are not advanced, see k_rrs_elastic: nothing reads them back)
     // ---- interaction_helper!(::RRS, ::ScatteringInterface_11) inelastic lines (interaction_inelastic.jl:376-420, 446-487)
     const double* Cin = a.cI_in + u * G::CI;
-    const GB<NP> ieRmp{Cin}, ieTpp{Cin + 2 * MG}, ieTmm{Cin + 3 * MG};
+    const GB<NP> ieTmm{Cin + 3 * MG};
     const double* cJp = Cin + 4 * MG; const double* cJm = cJp + NP;
     const double* I0 = a.irec0 + (size_t)p0 * G::IREC0;
     const double* I1 = a.irec1 + (size_t)p1 * G::IREC1;
-    const GB<NP> Rpm0{I0}, Tpp0{I0 + MG}, r0{I0 + 2 * MG}, tmm0{I0 + 3 * MG}, E1{I0 + 4 * MG}, E2{I0 + 5 * MG},
-        E3{I0 + 6 * MG}, E4{I0 + 7 * MG};
+    const GB<NP> Rpm0{I0}, r0{I0 + 2 * MG}, tmm0{I0 + 3 * MG}, E2{I0 + 5 * MG}, E4{I0 + 7 * MG};
     const GA<NP> T01{I1}, T21{I1 + MG}, r1{I1 + 2 * MG}, Rpm1{I1 + 3 * MG};
     const double* IV = I0 + 8 * MG;
     const GV v1{IV}, v2{IV + NP}, J0p0{IV + 2 * NP}, aj0m0{IV + 3 * NP};
@@ -1032,21 +1014,6 @@ __global__ void __launch_bounds__(32 * WPC, (NP <= 16) ? 4 : 1) k_rrs_inel(Args 
             Cout[4 * MG + NP + g] = __ldg(cJm + g) + ya[0] + yb[0];
             Cout[4 * MG + NP + 8 + g] = __ldg(cJm + 8 + g) + ya[1] + yb[1];
         }
-        // Q2 = ier T++0 + r1 ieT++ ;  ieR-+ = ieR-+ + T01 Q2 + P E1
-        lfB(Tpp0, T, g, tg);
-        czero<NP>(c);
-        mmf(c, AA, T);
-        lfB(ieTpp, T, g, tg);
-        mmf(c, RA, T);
-        __syncwarp();
-        wepi<NP>(c, [&](int i, int j, double v) { X[i + j * LDS] = v; }, lane);
-        __syncwarp();
-        lfB(sX, T, g, tg);
-        czero<NP>(c);
-        mmf(c, TA, T);
-        lfB(E1, T, g, tg);
-        mmf(c, PA, T);
-        wepi<NP>(c, [&](int i, int j, double v) { Cout[i + j * NP] = ieRmp(i, j) + v; }, lane);
         // ieT-- = T01 iet-- + P E2
         lfB(sBc, T, g, tg);
         czero<NP>(c);
@@ -1080,13 +1047,6 @@ __global__ void __launch_bounds__(32 * WPC, (NP <= 16) ? 4 : 1) k_rrs_inel(Args 
         mvs(ya, TA, SV{w4}, tg);
         mvs(yb, PA, v2, tg);
         if (tg == 0) { Cout[4 * MG + g] = jp[g] + ya[0] + yb[0]; Cout[4 * MG + 8 + g] = jp[8 + g] + ya[1] + yb[1]; }
-        // ieT++ = T21 ieT++ + P' E3
-        lfB(ieTpp, T, g, tg);
-        czero<NP>(c);
-        mmf(c, TA, T);
-        lfB(E3, T, g, tg);
-        mmf(c, PA, T);
-        wepi<NP>(c, [&](int i, int j, double v) { Cout[2 * MG + i + j * NP] = v; }, lane);
         // Q4 = ieR+- t--0 + R+-1 iet-- ;  ieR+- = ier+- + T21 Q4 + P' E4
         lfB(tmm0, T, g, tg);
         czero<NP>(c);
@@ -1120,17 +1080,6 @@ __global__ void __launch_bounds__(32 * WPC, (NP <= 16) ? 4 : 1) k_rrs_inel(Args 
         wmv<NP>(y1, T01, SV{w3}, lane);
         wmv<NP>(y2, sS1, v1, lane);
         if (lane < 16) for (int b = 0; b < NP / 16; ++b) { const int i = 16 * b + lane; Cout[4 * MG + NP + i] = __ldg(cJm + i) + y1[b] + y2[b]; }
-        // Q2 = ier T++0 + r1 ieT++ ;  ieR-+ = ieR-+ + T01 Q2 + P E1
-        czero<NP>(c);
-        wmm<NP>(c, sA, Tpp0, lane);
-        wmm<NP>(c, r1, ieTpp, lane);
-        __syncwarp();
-        wepi<NP>(c, [&](int i, int j, double v) { X[i + j * LDS] = v; }, lane);
-        __syncwarp();
-        czero<NP>(c);
-        wmm<NP>(c, T01, sX, lane);
-        wmm<NP>(c, sS1, E1, lane);
-        wepi<NP>(c, [&](int i, int j, double v) { Cout[i + j * NP] = ieRmp(i, j) + v; }, lane);
         // ieT-- = T01 iet-- + P E2
         czero<NP>(c);
         wmm<NP>(c, T01, sBc, lane);
@@ -1154,11 +1103,6 @@ __global__ void __launch_bounds__(32 * WPC, (NP <= 16) ? 4 : 1) k_rrs_inel(Args 
         wmv<NP>(y1, T21, SV{w4}, lane);
         wmv<NP>(y2, sS1, v2, lane);
         if (lane < 16) for (int b = 0; b < NP / 16; ++b) { const int i = 16 * b + lane; Cout[4 * MG + i] = jp[i] + y1[b] + y2[b]; }
-        // ieT++ = T21 ieT++ + P' E3
-        czero<NP>(c);
-        wmm<NP>(c, T21, ieTpp, lane);
-        wmm<NP>(c, sS1, E3, lane);
-        wepi<NP>(c, [&](int i, int j, double v) { Cout[2 * MG + i + j * NP] = v; }, lane);
         // Q4 = ieR+- t--0 + R+-1 iet-- ;  ieR+- = ier+- + T21 Q4 + P' E4
         czero<NP>(c);
         wmm<NP>(c, ieRpm, tmm0, lane);
