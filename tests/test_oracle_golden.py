@@ -163,3 +163,34 @@ def test_single_scatter_thin_limit_converges_to_full_solution():
         ss, ms = orc.rt_run_ss(om), orc.rt_run(om)
         gaps.append(np.max(np.abs(ms["R_SFI"][:, 0] - ss["R_SFI"][:, 0]) / ms["R_SFI"][:, 0]))
     assert gaps[0] < 3e-2 and 1.6 < gaps[0] / gaps[1] < 2.4, gaps
+
+
+@pytest.mark.parametrize("nonscattering", [False, True])
+def test_outputs_do_not_read_composite_Rmp_Tpp(monkeypatch, nonscattering):
+    """in interaction! (interaction.jl:52-266) the composite R-+ and T++ feed only themselves, so every
+    rt_run output is unchanged -- bit for bit -- when they are overwritten with noise after every interaction.  This is what
+    lets the column kernels leave them out unless rt_run_streams asks for them."""
+    if nonscattering:       # interfaces _00, _01, _10 and _11
+        m = vb.synthetic_o2a_model(nSpec=6, nstreams=4, aerosol=False, p_half=np.array([1., 50., 200., 400., 600., 800., 1000.]))
+        m.tau_rayl[:, 0] = 0; m.tau_rayl[:, 1] = 0; m.tau_rayl[:, 3] = 0
+        m.tau_abs[:, 0] += 0.05; m.tau_abs[:, 3] += 0.2
+    else:
+        m = vb.synthetic_o2a_model(nSpec=6, nstreams=4, polarization_type="Stokes_IQU", aerosol=True)
+    om = to_oracle(m)
+    ref = orc.rt_run(om)
+    plain = orc.interaction
+    rng = np.random.default_rng(3)
+    calls = []
+
+    def poisoned(itf, C, *args):
+        C = plain(itf, C, *args)
+        C.Rmp = rng.standard_normal(C.Rmp.shape)
+        C.Tpp = rng.standard_normal(C.Tpp.shape)
+        calls.append(itf)
+        return C
+
+    monkeypatch.setattr(orc, "interaction", poisoned)
+    out = orc.rt_run(om)
+    assert len(calls) > 0 and (not nonscattering or {0, 1, 2, 3} <= set(calls))
+    for k in ("R_SFI", "T_SFI", "hdr", "bhr_uw", "bhr_dw"):
+        assert np.array_equal(out[k], ref[k]), k

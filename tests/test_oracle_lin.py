@@ -158,3 +158,32 @@ def test_rt_run_lin_jacobian_matches_finite_differences_of_rt_run():
             scale = max(np.abs(fd).max(), 1e-300)
             err = np.max(np.abs(lin["d" + k][ip] - fd)) / scale
             assert err <= 1e-6, (ip, k, err)
+
+
+def test_lin_outputs_do_not_read_composite_Rmp_Tpp(monkeypatch):
+    """DESIGN.md §3.8, LinMode (interaction_lin.jl:238-306): the composite R-+ / T++ and their derivatives feed only
+    themselves; overwriting them with noise after every interaction leaves the forward outputs and the Jacobians unchanged
+    bit for bit (k_adding_lin does not advance them)."""
+    m = vb.synthetic_o2a_model(nSpec=3, nstreams=3, polarization_type="Stokes_IQU", aerosol=True, albedo=0.2)
+    om = to_oracle(m)
+    nS, Nz, nAer = om.nSpec, om.Nz, len(om.aerosols)
+    P = 2
+    d_rayl = np.zeros((P, nS, Nz)); d_abs = np.zeros((P, nS, Nz)); d_aer = np.zeros((P, nAer, Nz)); d_alb = np.array([0.0, 1.0])
+    d_abs[0] = om.tau_abs
+    ref = orc.rt_run_lin(om, d_rayl, d_abs, d_aer, d_alb)
+    plain = orc.interaction_lin
+    rng = np.random.default_rng(9)
+    calls = []
+
+    def poisoned(*args, **kw):
+        C, dC = plain(*args, **kw)
+        C.Rmp = rng.standard_normal(C.Rmp.shape); C.Tpp = rng.standard_normal(C.Tpp.shape)
+        dC.Rmp = rng.standard_normal(dC.Rmp.shape); dC.Tpp = rng.standard_normal(dC.Tpp.shape)
+        calls.append(1)
+        return C, dC
+
+    monkeypatch.setattr(orc, "interaction_lin", poisoned)
+    out = orc.rt_run_lin(om, d_rayl, d_abs, d_aer, d_alb)
+    assert len(calls) > 2
+    for k in ("R_SFI", "T_SFI", "dR_SFI", "dT_SFI"):
+        assert np.array_equal(out[k], ref[k]), k

@@ -181,3 +181,34 @@ def test_single_scatter_rrs_closure_and_thin_limit():
         s1 = rrs.rt_run_ss_rrs(mm, r)
         gaps.append(np.max(np.abs(full["ieR_SFI"][:, 0, inner] - s1["ieR_SFI"][:, 0, inner]) / np.abs(full["ieR_SFI"][:, 0, inner])))
     assert gaps[0] < 5e-2 and 1.6 < gaps[0] / gaps[1] < 2.4, gaps
+
+
+def test_outputs_do_not_read_composite_ieRmp_ieTpp(monkeypatch):
+    """DESIGN.md §3.8, inelastic half (interaction_inelastic.jl:372-502): ieR-+ reads ieT++, the elastic T++ and itself, ieT++
+    reads itself, and no ieJ0+- / ieT-- / ieR+- line reads either -- nor the elastic R-+ / T++.  Overwriting all four with noise
+    after every interaction leaves the elastic and inelastic outputs unchanged bit for bit."""
+    eps = 0.03
+    m = _flat_model(eps, nS=16, Nz=3, tau=0.05)
+    m.tau_abs = np.linspace(0.0, 0.3, 16)[:, None] * np.ones(3)[None, :]
+    shifts = np.array([-5, -2, 3, 6])
+    w = rrs.normalize_raman_weights(np.array([0.3, 0.2, 0.4, 0.1]), 1.0 - eps)
+    R = rrs.RRS(shifts, w, rrs.get_greek_raman(0.1))
+    ref = rrs.rt_run_rrs(m, R)
+    plain = rrs.interaction_inelastic_11
+    rng = np.random.default_rng(5)
+    calls = []
+
+    def poisoned(*args, **kw):
+        C, CI = plain(*args, **kw)
+        C.Rmp = rng.standard_normal(C.Rmp.shape)
+        C.Tpp = rng.standard_normal(C.Tpp.shape)
+        CI.ieRmp = rng.standard_normal(CI.ieRmp.shape)
+        CI.ieTpp = rng.standard_normal(CI.ieTpp.shape)
+        calls.append(1)
+        return C, CI
+
+    monkeypatch.setattr(rrs, "interaction_inelastic_11", poisoned)
+    out = rrs.rt_run_rrs(m, R)
+    assert len(calls) >= 3
+    for k in ("R_SFI", "T_SFI", "ieR_SFI", "ieT_SFI"):
+        assert np.array_equal(out[k], ref[k]), k
