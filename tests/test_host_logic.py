@@ -29,6 +29,23 @@ def test_z_moments_match_oracle(pol_n, m):
         assert np.max(np.abs(x - y)) <= 1e-12 * max(1.0, np.max(np.abs(y)))
 
 
+def test_z_tables_share_the_legendre_functions_across_scatterers():
+    # z_tables evaluates P/R/T once per moment for the longest Greek expansion and slices it per scatterer
+    # (Rayleigh: 3 terms, aerosol: 20): same tables as the oracle's per-scatterer evaluation
+    from vsmom_b200 import rt_run as rr
+    from helpers import to_oracle
+    m = vb.synthetic_o2a_model(nSpec=4, nstreams=6, polarization_type="Stokes_IQU", aerosol=True)
+    Zpp, Zmp = rr.z_tables(m)
+    om = to_oracle(m)
+    comps = [om.greek_rayleigh] + [a.greek for a in om.aerosols]
+    assert Zpp.shape[:2] == (m.m_max + 1, len(comps))
+    for mm in range(m.m_max + 1):
+        for c, g in enumerate(comps):
+            zp, zm = orc.compute_Z_moments(om.pol_n, om.quad.qp_mu, g, mm)
+            assert np.max(np.abs(Zpp[mm, c] - zp.T)) <= 1e-12 * max(1.0, np.abs(zp).max())
+            assert np.max(np.abs(Zmp[mm, c] - zm.T)) <= 1e-12 * max(1.0, np.abs(zm).max())
+
+
 def test_rayleigh_z_has_three_moments():
     q = vb.rt_set_streams(4, 30.0, [0.0], 3)
     zp, zm = vb.compute_Z_moments(3, q.qp_mu, vb.get_greek_rayleigh(0.03), 2)

@@ -150,16 +150,20 @@ def _prt(mu: np.ndarray, lmax: int, m: int):
     return P, R, -Tn
 
 
-def compute_Z_moments(pol_n: int, mu: np.ndarray, greek: GreekCoefs, m: int):
+def compute_Z_moments(pol_n: int, mu: np.ndarray, greek: GreekCoefs, m: int, prt=None):
     """Fourier moment ``m`` (0-based) of the phase matrix on the stream cosines:
     returns ``(Z⁺⁺, Z⁻⁺)`` of shape (N, N), N = len(mu)*pol_n, float64
-    (compute_Z_matrices.jl:26-110)."""
+    (compute_Z_matrices.jl:26-110).  ``prt``: ``(_prt(mu, L, m), _prt(-mu, L, m))`` with L >= len(greek.beta),
+    when the caller has them already (they depend on the streams and m only, not on the scatterer)."""
     mu = np.asarray(mu, dtype=np.float64)
     nmu = mu.size
     lmax = len(greek.beta)
     fact = 0.5 if m == 0 else 1.0
-    Pp, Rp, Tp = _prt(mu, lmax, m)
-    Pn, Rn, Tn = _prt(-mu, lmax, m)
+    if prt is None:
+        Pp, Rp, Tp = _prt(mu, lmax, m)
+        Pn, Rn, Tn = _prt(-mu, lmax, m)
+    else:
+        (Pp, Rp, Tp), (Pn, Rn, Tn) = ((x[:lmax] for x in side) for side in prt)
 
     def pi_mats(P, R, T):
         Pi = np.zeros((lmax, nmu, pol_n, pol_n))
@@ -181,10 +185,12 @@ def compute_Z_moments(pol_n: int, mu: np.ndarray, greek: GreekCoefs, m: int):
     B = B[:, :pol_n, :pol_n]
     Pi_p = pi_mats(Pp, Rp, Tp)[m:]
     Pi_n = pi_mats(Pn, Rn, Tn)[m:]
-    left = np.einsum('liab,lbc->liac', Pi_p, B[m:])
-    App = np.einsum('liac,ljcd->iajd', left, Pi_p)
-    Amp = np.einsum('liac,ljcd->iajd', left, Pi_n)
     N = nmu * pol_n
+    nl = Pi_p.shape[0]
+    # sum over (l, c) as one matrix product: (i a | l c) (l c | j d)
+    left = np.matmul(Pi_p, B[m:, None]).transpose(1, 2, 0, 3).reshape(N, nl * pol_n)
+    App = (left @ Pi_p.transpose(0, 2, 1, 3).reshape(nl * pol_n, N)).reshape(nmu, pol_n, nmu, pol_n)
+    Amp = (left @ Pi_n.transpose(0, 2, 1, 3).reshape(nl * pol_n, N)).reshape(nmu, pol_n, nmu, pol_n)
     sgn = np.ones((pol_n, pol_n))
     for i in range(pol_n):
         for j in range(pol_n):

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .model import RTModel, compute_Z_moments, layer_control, vza_tables
+from .model import RTModel, _prt, compute_Z_moments, layer_control, vza_tables
 
 
 def _tdtype(FT):
@@ -42,9 +42,11 @@ def z_tables(model: RTModel) -> tuple[np.ndarray, np.ndarray]:
     nM = model.m_max + 1
     Zpp = np.zeros((nM, len(comps), N, N), model.float_type)
     Zmp = np.zeros_like(Zpp)
+    lmax = max(len(g.beta) for g in comps)
     for m in range(nM):
+        prt = (_prt(mu, lmax, m), _prt(-mu, lmax, m))      # shared by every scatterer
         for c, g in enumerate(comps):
-            zp, zm = compute_Z_moments(model.pol_n, mu, g, m)
+            zp, zm = compute_Z_moments(model.pol_n, mu, g, m, prt)
             # memory order (m, c, j, i) == Julia (i, j, c, m)
             Zpp[m, c] = zp.T
             Zmp[m, c] = zm.T
