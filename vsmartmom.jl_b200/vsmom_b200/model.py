@@ -150,18 +150,24 @@ def _prt(mu: np.ndarray, lmax: int, m: int):
     return P, R, -Tn
 
 
+def _prt_pm(mu: np.ndarray, lmax: int, m: int):
+    """``(_prt(mu), _prt(-mu))`` in one pass over l (the recurrences are element-wise in mu)."""
+    n = mu.size
+    P, R, T = _prt(np.concatenate([mu, -mu]), lmax, m)
+    return (P[:, :n], R[:, :n], T[:, :n]), (P[:, n:], R[:, n:], T[:, n:])
+
+
 def compute_Z_moments(pol_n: int, mu: np.ndarray, greek: GreekCoefs, m: int, prt=None):
     """Fourier moment ``m`` (0-based) of the phase matrix on the stream cosines:
     returns ``(Z⁺⁺, Z⁻⁺)`` of shape (N, N), N = len(mu)*pol_n, float64
-    (compute_Z_matrices.jl:26-110).  ``prt``: ``(_prt(mu, L, m), _prt(-mu, L, m))`` with L >= len(greek.beta),
+    (compute_Z_matrices.jl:26-110).  ``prt``: ``_prt_pm(mu, L, m)`` with L >= len(greek.beta),
     when the caller has them already (they depend on the streams and m only, not on the scatterer)."""
     mu = np.asarray(mu, dtype=np.float64)
     nmu = mu.size
     lmax = len(greek.beta)
     fact = 0.5 if m == 0 else 1.0
     if prt is None:
-        Pp, Rp, Tp = _prt(mu, lmax, m)
-        Pn, Rn, Tn = _prt(-mu, lmax, m)
+        (Pp, Rp, Tp), (Pn, Rn, Tn) = _prt_pm(mu, lmax, m)
     else:
         (Pp, Rp, Tp), (Pn, Rn, Tn) = ((x[:lmax] for x in side) for side in prt)
 

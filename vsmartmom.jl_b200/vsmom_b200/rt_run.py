@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .model import RTModel, _prt, compute_Z_moments, layer_control, vza_tables
+from .model import RTModel, _prt_pm, compute_Z_moments, layer_control, vza_tables
 
 
 def _tdtype(FT):
@@ -44,7 +44,7 @@ def z_tables(model: RTModel) -> tuple[np.ndarray, np.ndarray]:
     Zmp = np.zeros_like(Zpp)
     lmax = max(len(g.beta) for g in comps)
     for m in range(nM):
-        prt = (_prt(mu, lmax, m), _prt(-mu, lmax, m))      # shared by every scatterer
+        prt = _prt_pm(mu, lmax, m)                          # shared by every scatterer
         for c, g in enumerate(comps):
             zp, zm = compute_Z_moments(model.pol_n, mu, g, m, prt)
             # memory order (m, c, j, i) == Julia (i, j, c, m)
